@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — follower decode-steps/sec (BASELINE.json metric) on N B200s, one process per GPU.
+
+A "step" is one follower decode step over the whole batch: AttnDecoderLSTM.forward (model.py:377-397)
+fed from the device-resident feature table (replaces follower.py:291-298) plus the rollout tail
+(follower.py:476-505: mask, log-softmax, argmax, next-u gather).  Workload = BASELINE.json configs[1]
+shape: batch 100, instruction length 80, 8 action candidates, 36 x 2176 features, fp32.
+
+  python bench.py [--gpus N --steps K --warmup W]            this repo's CUDA path
+  python bench.py --impl reference [...]                     the reference's CPU arithmetic (oracle port)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+B, L, A = 100, 80, 8
+N_VIEWPOINTS = 10567          # R2R viewpoints -> 3.1 GB table, >> L2
+POOL = 8                      # rotating per-step input sets (ctx 16 MB + actions 7 MB each) > L2 together with the table
+
+
+def algorithmic_bytes(E, F, H, n_params):
+    """bytes one decode step must move (every operand once)."""
+    return 4 * (B * 36 * F + B * L * H + B * A * E + n_params + B * (E + 4 * H) + B * (36 + L + A))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_steps(n_steps, warmup, threads):
+    """Times the oracle port of AttnDecoderLSTM.forward + tail on the host (reference arithmetic, torch CPU)."""
+    from oracle import r2r_oracle as O
+    from speaker_follower_b200 import synth
+    torch.set_num_threads(threads)
+    w = synth.follower_decoder_weights()
+    xs = [synth.follower_step_inputs(B, L, A, seed=900 + i, n_viewpoints=128) for i in range(2)]
+    h, c = xs[0]["h_0"], xs[0]["c_0"]
+    u = xs[0]["u_t_prev"]
+    t0 = None
+    with torch.no_grad():
+        for i in range(warmup + n_steps):
+            if i == warmup:
+                t0 = time.perf_counter()
+            x = xs[i % 2]
+            h, c, alpha, logit, alpha_v = O.attn_decoder_step(u, x["all_u_t"], x["visual_context"], h, c, x["ctx"],
+                                                              x["ctx_mask"], w)
+            _, _, a_t, u, sc = O.follower_step_tail(logit, x["is_valid"], None, "argmax", x["all_u_t"])
+    dt = time.perf_counter() - t0
+    return n_steps / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sps, dt = cpu_steps(args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": "follower decode-steps/sec", "value": sps, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / sps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "follower decode step B=%d L=%d A=%d V=36 F=2176 (AttnDecoderLSTM.forward + rollout tail)" % (B, L, A),
+                   "batch": B, "instr_len": L, "actions": A},
+        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
+                         "sample": "%d decode steps, torch-CPU oracle port of tasks/R2R/model.py (reference is Python/torch; it cannot travel to the GPU box)" % args.steps},
+        "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args, rank, local_rank, world):
+    from speaker_follower_b200 import ops, synth
+    import __graft_entry__ as ge
+    ge.build()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    E = F = synth.FEAT
+    H = synth.HID
+    w_cpu = synth.follower_decoder_weights()
+    n_params = sum(v.numel() for v in w_cpu.values())
+    w = {k: v.to(dev) for k, v in w_cpu.items()}
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    # device-resident feature store (3.1 GB) — synthetic pool5-like features
+    table = torch.empty(N_VIEWPOINTS, 36, synth.IMG_DIM, device=dev)
+    for i in range(0, N_VIEWPOINTS, 1024):
+        table[i:i + 1024].normal_(generator=g).clamp_(min=0).mul_(1.1)
+    store = ops.FeatureStore(table, synth.loc_embedding_table().to(dev))
+
+    # rotating input sets
+    vp = [torch.randint(0, N_VIEWPOINTS, (B,), device=dev, dtype=torch.int32, generator=g) for _ in range(POOL)]
+    view = [torch.randint(0, 36, (B,), device=dev, dtype=torch.int32, generator=g) for _ in range(POOL)]
+    ctx = [torch.tanh(torch.randn(B, L, H, device=dev, generator=g) * 0.6) for _ in range(POOL)]
+    lens = torch.sort(torch.randint(10, L + 1, (B,), generator=torch.Generator().manual_seed(5)), descending=True)[0]
+    lens[0] = L
+    mask = (torch.arange(L).unsqueeze(0) >= lens.unsqueeze(1)).to(dev)
+    U, valid = [], []
+    for j in range(POOL):
+        n_act = torch.randint(2, A + 1, (B,), generator=torch.Generator().manual_seed(70 + j))
+        n_act[0] = A
+        v = (torch.arange(A).unsqueeze(0) < n_act.unsqueeze(1)).float().to(dev)
+        rows = table[vp[j].long().unsqueeze(1), torch.randint(0, 36, (B, A), device=dev, generator=g)]   # [B,A,2048]
+        ang = torch.rand(B, A, 4, device=dev, generator=g) * 6.28 - 3.14
+        locp = torch.cat([torch.sin(ang[..., 0:1]).expand(-1, -1, 32), torch.cos(ang[..., 0:1]).expand(-1, -1, 32),
+                          torch.sin(ang[..., 1:2]).expand(-1, -1, 32), torch.cos(ang[..., 1:2]).expand(-1, -1, 32)], 2)
+        u = torch.cat([rows, locp], 2) * v.unsqueeze(2)
+        u[:, 0] = 0
+        U.append(u.contiguous())
+        valid.append(v.contiguous())
+    del rows, u
+
+    d = ops.follower_dims(w)
+    hbuf = [torch.tanh(torch.randn(B, H, device=dev, generator=g) * 0.5), torch.empty(B, H, device=dev)]
+    cbuf = [torch.randn(B, H, device=dev, generator=g) * 0.5, torch.empty(B, H, device=dev)]
+    ubuf = [torch.zeros(B, E, device=dev), torch.empty(B, E, device=dev)]
+    alpha = torch.empty(B, L, device=dev); logit = torch.empty(B, A, device=dev); alpha_v = torch.empty(B, 36, device=dev)
+    a_t = torch.empty(B, dtype=torch.int32, device=dev); score = torch.empty(B, device=dev)
+    ws = torch.empty(1 << 26, dtype=torch.uint8, device=dev)
+    launches_per_step = [0]
+
+    def step(i):
+        j, s = i % POOL, i % 2
+        ops.follower_step(w, ubuf[s], U[j], None, hbuf[s], cbuf[s], ctx[j], mask, store=store, vp_idx=vp[j],
+                          view_idx=view[j], workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v))
+        n = ops.last_launch_count()
+        ops.follower_tail(logit, valid[j], U[j], "argmax", out=(a_t, ubuf[s ^ 1], score, None))
+        launches_per_step[0] = n + ops.last_launch_count()
+
+    # warm-up outside graphs (also configures kernel attributes), then capture POOL-step graphs
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        for i in range(POOL):
+            step(i)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    chunk = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(chunk):
+        for i in range(POOL):
+            step(i)
+    singles = []
+    for i in range(POOL):
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph):
+            step(i)
+        singles.append(gph)
+
+    def run_steps(k):
+        for _ in range(k // POOL):
+            chunk.replay()
+        for i in range(k % POOL):
+            singles[i].replay()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    run_steps(max(args.warmup, 3))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_steps(args.steps)
+    e1.record()
+    barrier()
+    clocks = sampler.result()
+    ms = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: same step through the public ops API with HOST buffers (pinned), H2D + D2H inside the timed region.
+    # Host inputs per step (what the agent holds on the host after env.observe): viewpoint / view indices, the
+    # action-candidate embeddings + validity (follower.py:300-320); result read back: a_t + logits (follower.py:510).
+    e2e_steps = min(args.steps, 1000)
+    h_vp = [v.cpu().pin_memory() for v in vp]; h_view = [v.cpu().pin_memory() for v in view]
+    h_U = [u.cpu().pin_memory() for u in U]; h_valid = [v.cpu().pin_memory() for v in valid]
+    d_vp = torch.empty_like(vp[0]); d_view = torch.empty_like(view[0]); d_U = torch.empty_like(U[0]); d_valid = torch.empty_like(valid[0])
+    h_a = torch.empty(B, dtype=torch.int32).pin_memory(); h_logit = torch.empty(B, A).pin_memory()
+    graphs2 = []
+    for s in range(2):
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph):
+            ops.follower_step(w, ubuf[s], d_U, None, hbuf[s], cbuf[s], ctx[0], mask, store=store, vp_idx=d_vp,
+                              view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v))
+            ops.follower_tail(logit, d_valid, d_U, "argmax", out=(a_t, ubuf[s ^ 1], score, None))
+        graphs2.append(gph)
+
+    def e2e_step(i):
+        j = i % POOL
+        d_vp.copy_(h_vp[j], non_blocking=True); d_view.copy_(h_view[j], non_blocking=True)
+        d_U.copy_(h_U[j], non_blocking=True); d_valid.copy_(h_valid[j], non_blocking=True)
+        graphs2[i % 2].replay()
+        h_a.copy_(a_t, non_blocking=True); h_logit.copy_(logit, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the agent needs a_t on the host to step the simulator
+
+    for i in range(4):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)], device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps / (float(e2e_ms.item()) * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in (h_vp[0], h_view[0], h_U[0], h_valid[0]))
+    d2h = h_a.numel() * 4 + h_logit.numel() * 4
+
+    # ---- roofline of the attention-gather kernel, timed alone with CUDA events on its launch stream;
+    # every launch reads a different random set of slabs from the 3.1 GB table (inputs >> L2).
+    q = torch.randn(B, F, device=dev, generator=g) * 0.05
+    feat = torch.empty(B, F, device=dev)
+    n_attn = 200
+    vps = [torch.randint(0, N_VIEWPOINTS, (B,), device=dev, dtype=torch.int32, generator=g) for _ in range(n_attn)]
+    for i in range(5):
+        ops.visual_attention_core(q, None, store=store, vp_idx=vps[i], view_idx=view[0], out=(feat, alpha_v))
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_attn)]
+    for i in range(n_attn):
+        evs[i][0].record()
+        ops.visual_attention_core(q, None, store=store, vp_idx=vps[i], view_idx=view[0], out=(feat, alpha_v))
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    attn_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    attn_bytes = 4 * B * 36 * F
+    hbm_peak, peak_src = peaks()
+    attn_gbs = attn_bytes / (attn_ms * 1e-3) / 1e9
+    step_bytes = algorithmic_bytes(E, F, H, n_params)
+    step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
+
+    if rank == 0:
+        cpu_n = 300
+        threads = os.cpu_count() or 1
+        cpu_sps, cpu_dt = cpu_steps(cpu_n, 3, threads)
+        line = {
+            "metric": "follower decode-steps/sec", "value": value, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "follower decode step B=%d L=%d A=%d V=36 F=2176 (AttnDecoderLSTM.forward + rollout tail), per GPU" % (B, L, A),
+                       "batch": B, "instr_len": L, "actions": A, "parallelism": "replicas x%d (instance-sharded, no data-path collective)" % world,
+                       "cache": "inputs larger than L2: per-step slabs gathered from a 3.1 GB device table, %d rotating ctx/action sets; weights (48.5 MB) are step-invariant" % POOL,
+                       "launch": "CUDA graph of %d steps" % POOL},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": launches_per_step[0] * args.steps,
+            "roofline": {"kernel": "soft_dot_attn_kernel (36-view attention gather)", "bound": "hbm",
+                         "achieved": attn_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": attn_gbs / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": attn_bytes,
+                         "us_per_launch": attn_ms * 1e3},
+            "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": step_gbs / hbm_peak, "bytes_per_step": step_bytes},
+            "cpu_baseline": {"value": cpu_sps, "unit": "steps/s", "cores": threads, "kind": "port",
+                             "sample": "%d decode steps of the same workload, torch-CPU oracle port of tasks/R2R/model.py" % cpu_n},
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,209 @@
+/* sf_b200.h — C ABI of the B200-native speaker/follower recurrent hot path.
+ *
+ * The reference (ronghanghu/speaker_follower) has no FFI layer: its hot path is the Python module API
+ * of tasks/R2R/model.py.  This header is the boundary a maintainer binds instead of
+ * those nn.Module forwards: plain device pointers, sizes and a cudaStream_t passed as void*.  No torch
+ * types, no allocation inside the library (the caller provides a workspace), no host synchronisation,
+ * safe under CUDA-graph capture.  Every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - all tensors fp32 row-major contiguous unless a leading dimension is given; indices int32;
+ *     masks uint8 (1 = masked / padded), exactly the reference's ByteTensor masks (follower.py:101).
+ *   - weights are passed in the reference's own state_dict layouts ([out_features, in_features]
+ *     row-major), so nn.Parameter storage is used in place; nothing is re-laid-out or cached.
+ *   - return value: 0 on success, negative sfb_status on error; sfb_last_error() gives the message of
+ *     the last failure on the calling thread.  Argument errors are detected before any launch.
+ *   - every function only enqueues work on `stream`.
+ */
+#ifndef SF_B200_H_
+#define SF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB_ABI_VERSION 1
+
+typedef enum sfb_status {
+  SFB_OK = 0,
+  SFB_ERR_INVALID_ARG = -1,   /* NULL pointer, bad size, unsupported dimension */
+  SFB_ERR_WORKSPACE = -2,     /* workspace too small / misaligned */
+  SFB_ERR_CUDA = -3,          /* a CUDA runtime call failed (message has the CUDA error string) */
+  SFB_ERR_NO_DEVICE = -4      /* no sm_100 device / kernel image not loadable */
+} sfb_status;
+
+/* Model dimensions.  Reference values (tasks/R2R/train.py:30-38, model.py:303,335):
+ * E = action embedding = 2176, F = visual feature = 2176, H = 512, D = 256, V = 36 views. */
+typedef struct sfb_dims {
+  int32_t E, F, H, D, V;
+} sfb_dims;
+
+/* Visual-attention + LSTMCell weights shared by AttnDecoderLSTM (model.py:371-373) and
+ * SpeakerEncoderLSTM (model.py:415-418). */
+typedef struct sfb_vis_lstm_weights {
+  const float* lstm_w_ih;   /* [4H, E+F]  lstm.weight_ih  (gate order i,f,g,o) */
+  const float* lstm_w_hh;   /* [4H, H]    lstm.weight_hh */
+  const float* lstm_b_ih;   /* [4H]       lstm.bias_ih */
+  const float* lstm_b_hh;   /* [4H]       lstm.bias_hh */
+  const float* va_w_h;      /* [D, H]     visual_attention_layer.linear_in_h.weight */
+  const float* va_b_h;      /* [D] */
+  const float* va_w_v;      /* [D, F]     visual_attention_layer.linear_in_v.weight */
+  const float* va_b_v;      /* [D]        (cancels inside the softmax; accepted for completeness) */
+} sfb_vis_lstm_weights;
+
+/* SoftDotAttention weights (model.py:117,119). */
+typedef struct sfb_softdot_weights {
+  const float* w_in;        /* [H, H]   linear_in.weight  (no bias) */
+  const float* w_out;       /* [H, 2H]  linear_out.weight (no bias), input order [weighted_ctx ; h] */
+} sfb_softdot_weights;
+
+/* EltwiseProdScoring weights (model.py:338-340). */
+typedef struct sfb_scoring_weights {
+  const float* w_h;         /* [D, H] linear_in_h.weight */
+  const float* b_h;         /* [D] */
+  const float* w_a;         /* [D, E] linear_in_a.weight */
+  const float* b_a;         /* [D] */
+  const float* w_out;       /* [1, D] linear_out.weight */
+  const float* b_out;       /* [1] */
+} sfb_scoring_weights;
+
+/* Where a step's 36-view feature slab comes from (replaces Seq2SeqAgent._feature_variables,
+ * follower.py:291-298 + ImageFeatures.batch_features, env.py:330-332).
+ *   dense : `visual` = [B, V, F] already on the device (what the reference builds on the host per step);
+ *   gather: `visual` = NULL; row v of batch element b is the concatenation of
+ *           feat_table[vp_idx[b], v, 0:img_dim] and loc_table[view_idx[b], v, 0:F-img_dim]
+ *           (env.py:773: feature = concat(image feature, _static_loc_embeddings[viewIndex])). */
+typedef struct sfb_visual_source {
+  const float*   visual;      /* [B, V, F] or NULL */
+  const float*   feat_table;  /* [n_viewpoints, V, img_dim] */
+  const float*   loc_table;   /* [V, V, F - img_dim]  (env.py:100-101) */
+  const int32_t* vp_idx;      /* [B] row into feat_table */
+  const int32_t* view_idx;    /* [B] agent viewIndex 0..V-1 */
+  int32_t        img_dim;     /* 2048 */
+} sfb_visual_source;
+
+/* ---------------------------------------------------------------------------------------------- */
+
+int32_t     sfb_abi_version(void);
+const char* sfb_last_error(void);
+
+/* Device properties the library was built for / sees.  Fills sm (e.g. 100), number of SMs and max
+ * opt-in shared memory per block; returns SFB_ERR_NO_DEVICE when there is no usable device. */
+int32_t sfb_device_info(int32_t* sm, int32_t* num_sms, int32_t* smem_per_block);
+
+/* Bytes of device workspace one follower decode step needs (also an upper bound for the speaker
+ * encoder step and the two attention entry points at the same B).  256-byte aligned pointer required. */
+size_t sfb_follower_step_workspace_bytes(const sfb_dims* dims, int32_t B, int32_t L, int32_t A);
+
+/* VisualSoftDotAttention.forward — model.py:310-326.
+ * h [B,H] -> feature [B,F], alpha_v [B,V].  Visual rows are read from HBM exactly once. */
+int32_t sfb_visual_attention_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* w, int32_t B,
+                                 const float* h, const sfb_visual_source* vis,
+                                 float* feature, float* alpha_v,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* The attention-gather kernel alone (model.py:320-325): given the projected query q [B,F]
+ * (= W_v^T (W_h h + b_h)), alpha_v = softmax_v(V_v . q), feature = sum_v alpha_v V_v.  One launch; this is
+ * the kernel whose HBM roofline fraction BASELINE.json's "attn HBM %" refers to. */
+int32_t sfb_visual_attention_core_fwd(const sfb_dims* dims, int32_t B, const float* q,
+                                      const sfb_visual_source* vis, float* feature, float* alpha_v, void* stream);
+
+/* SoftDotAttention.forward — model.py:122-143.
+ * h [B,H], ctx [B,L,H], mask [B,L] (may be NULL) -> h_tilde [B,H], alpha [B,L]. */
+int32_t sfb_soft_dot_attention_fwd(const sfb_dims* dims, const sfb_softdot_weights* w, int32_t B, int32_t L,
+                                   const float* h, const float* ctx, const uint8_t* mask,
+                                   float* h_tilde, float* alpha,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* AttnDecoderLSTM.forward — model.py:377-397: ONE follower decode step.
+ *   u_prev [B,E], all_u_t [B,A,E], vis (dense or gather), h0,c0 [B,H], ctx [B,L,H], ctx_mask [B,L]|NULL
+ *   drop_x [B,E+F] / drop_h [B,H]: scaled keep masks of the two nn.Dropout calls (model.py:392,394),
+ *   NULL in eval mode.
+ *   -> h1,c1 [B,H] (un-dropped), alpha [B,L], logit [B,A] (raw, unmasked), alpha_v [B,V].
+ * Intermediates needed by sfb_follower_step_bwd stay in `workspace` (layout private to the library). */
+int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* wl,
+                              const sfb_softdot_weights* wt, const sfb_scoring_weights* ws,
+                              int32_t B, int32_t L, int32_t A,
+                              const float* u_prev, const float* all_u_t, const sfb_visual_source* vis,
+                              const float* h0, const float* c0, const float* ctx, const uint8_t* ctx_mask,
+                              const float* drop_x, const float* drop_h,
+                              float* h1, float* c1, float* alpha, float* logit, float* alpha_v,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* Per-step tail of Seq2SeqAgent._rollout_with_loss — follower.py:476-505.
+ *   logit [B,A] is masked IN PLACE with -inf where is_valid == 0 (477);
+ *   feedback: 0 = teacher (a_t = max(target,0)), 1 = argmax, 2 = sample (inverse CDF of
+ *   softmax(logit)*valid with the caller's uniforms sample_u [B]);
+ *   target [B] int32 (-1 = ignore) or NULL;
+ *   -> a_t [B] int32, u_next [B,E] = all_u_t[b, a_t[b]] (502), action_score [B] = log_softmax(logit)[a_t]
+ *      (504), ce [B] = -log_softmax(logit)[target] or 0 where target < 0 (481; caller averages). */
+int32_t sfb_follower_step_tail(int32_t B, int32_t A, int32_t E, float* logit, const float* is_valid,
+                               const int32_t* target, int32_t feedback, const float* sample_u,
+                               const float* all_u_t, int32_t* a_t, float* u_next, float* action_score,
+                               float* ce, void* stream);
+
+/* EncoderLSTM.forward — model.py:81-104: embedding lookup, 1-layer (optionally bidirectional) LSTM over a
+ * length-sorted padded batch with packed-sequence semantics (rows stop at their own length; ctx is zero
+ * beyond it), decoder_init = tanh(encoder2decoder(h_T)); c_T returned raw.
+ *   seq [B, maxlen] int32 token ids (maxlen = max(lengths)); lengths [B] int32 (any order is accepted);
+ *   drop_embed [B*maxlen, Ew] scaled keep mask or NULL (the reference drops embeddings only without GloVe);
+ *   Hd = hidden size per direction, H = ndir*Hd.
+ *   -> ctx [B, maxlen, H] (un-dropped; forward half then reverse half), decoder_init [B,H], c_t [B,H]
+ *      (bidirectional: cat(reverse, forward), model.py:93-94). */
+typedef struct sfb_encoder_weights {
+  const float* embedding;   /* [vocab, Ew] */
+  const float* w_ih[2];     /* [4Hd, Ew]  lstm.weight_ih_l0, lstm.weight_ih_l0_reverse (or NULL) */
+  const float* w_hh[2];     /* [4Hd, Hd] */
+  const float* b_ih[2];     /* [4Hd] */
+  const float* b_hh[2];     /* [4Hd] */
+  const float* e2d_w;       /* [H, H] encoder2decoder.weight */
+  const float* e2d_b;       /* [H] */
+} sfb_encoder_weights;
+
+size_t sfb_encoder_lstm_workspace_bytes(int32_t ndir, int32_t Hd, int32_t Ew, int32_t B, int32_t maxlen);
+
+int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t Hd, int32_t Ew, int32_t B,
+                             int32_t maxlen, const int32_t* seq, const int32_t* lengths, const float* drop_embed,
+                             float* ctx, float* decoder_init, float* c_t,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* SpeakerEncoderLSTM._forward_one_step — model.py:429-435 (visual attention + LSTMCell). */
+int32_t sfb_speaker_encoder_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* w, int32_t B,
+                                     const float* action_embedding, const sfb_visual_source* vis,
+                                     const float* h0, const float* c0, const float* drop_x,
+                                     float* h1, float* c1,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* SpeakerDecoderLSTM.forward (default branch) — model.py:497-503,515-519.
+ *   prev_word [B] int32, embedding [vocab, Ew], LSTMCell Ew->H, SoftDotAttention over ctx [B,T,H]
+ *   with mask [B,T], vocabulary projection w_voc [vocab, H] + b_voc -> logit [B, vocab]. */
+typedef struct sfb_speaker_decoder_weights {
+  const float* embedding;   /* [vocab, Ew] embedding.weight */
+  const float* lstm_w_ih;   /* [4H, Ew] */
+  const float* lstm_w_hh;   /* [4H, H] */
+  const float* lstm_b_ih;   /* [4H] */
+  const float* lstm_b_hh;   /* [4H] */
+  sfb_softdot_weights attn; /* attention_layer.* */
+  const float* w_voc;       /* [vocab, H] decoder2action.weight */
+  const float* b_voc;       /* [vocab] */
+} sfb_speaker_decoder_weights;
+
+size_t sfb_speaker_decoder_step_workspace_bytes(int32_t H, int32_t Ew, int32_t B);
+
+int32_t sfb_speaker_decoder_step_fwd(const sfb_speaker_decoder_weights* w, int32_t H, int32_t Ew, int32_t vocab,
+                                     int32_t B, int32_t T, const int32_t* prev_word,
+                                     const float* h0, const float* c0, const float* ctx, const uint8_t* ctx_mask,
+                                     const float* drop_e, const float* drop_h,
+                                     float* h1, float* c1, float* alpha, float* logit,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Number of kernels the last successful call on this thread enqueued (bench.py's gpu_launches). */
+int32_t sfb_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SF_B200_H_ */

@@ -1,0 +1,455 @@
+// api.cu — the extern "C" entry points declared in include/sf_b200.h: argument validation, workspace
+// carving and the launch sequence of one decode step.  No allocation, no synchronisation.
+#include <mutex>
+
+#include "kernels.h"
+
+namespace sfb {
+
+static thread_local std::string g_err;
+static thread_local int g_launches = 0;
+
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch(int n) { g_launches += n; }
+void reset_launch_count() { g_launches = 0; }
+
+int device_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+    sms = prop.multiProcessorCount;
+  }
+  return sms;
+}
+
+// ---- workspace carving (all regions 256-byte aligned) ----
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  float* take(size_t nfloats) {
+    float* r = reinterpret_cast<float*>(base + off);
+    off += (nfloats * sizeof(float) + 255) & ~size_t(255);
+    return r;
+  }
+};
+
+struct FollowerWs {
+  float *tv, *q, *feat, *gpart, *gates_act, *h1d, *t, *wc, *htilde, *tp, *g;
+  int splitk;
+  size_t bytes;
+};
+
+static int gates_splitk(const sfb_dims& d, int B) {
+  return gemm_pick_splitk(B, 4 * d.H, d.E + d.F + d.H, device_num_sms());
+}
+
+static FollowerWs carve_follower(const sfb_dims& d, int B, int L, int A, void* ws) {
+  (void)L; (void)A;
+  FollowerWs w;
+  Carver c(ws);
+  w.splitk = gates_splitk(d, B);
+  const int kmax = d.F > d.E ? d.F : d.E;
+  w.tv = c.take((size_t)B * d.D);
+  w.q = c.take((size_t)B * kmax);
+  w.feat = c.take((size_t)B * d.F);
+  w.gpart = c.take((size_t)w.splitk * B * 4 * d.H);
+  w.gates_act = c.take((size_t)B * 4 * d.H);
+  w.h1d = c.take((size_t)B * d.H);
+  w.t = c.take((size_t)B * d.H);
+  w.wc = c.take((size_t)B * d.H);
+  w.htilde = c.take((size_t)B * d.H);
+  w.tp = c.take((size_t)B * d.D);
+  w.g = c.take((size_t)B * kmax);
+  w.bytes = c.off;
+  return w;
+}
+
+struct SpkDecWs {
+  float *gpart, *gates_act, *h1d, *t, *wc, *htilde;
+  int splitk;
+  size_t bytes;
+};
+
+static SpkDecWs carve_spkdec(int H, int Ew, int B, void* ws) {
+  SpkDecWs w;
+  Carver c(ws);
+  w.splitk = gemm_pick_splitk(B, 4 * H, Ew + H, device_num_sms());
+  w.gpart = c.take((size_t)w.splitk * B * 4 * H);
+  w.gates_act = c.take((size_t)B * 4 * H);
+  w.h1d = c.take((size_t)B * H);
+  w.t = c.take((size_t)B * H);
+  w.wc = c.take((size_t)B * H);
+  w.htilde = c.take((size_t)B * H);
+  w.bytes = c.off;
+  return w;
+}
+
+struct EncWs {
+  float *xproj, *h[2], *c[2], *gpart;
+  int splitk;
+  size_t bytes;
+};
+
+static EncWs carve_encoder(int ndir, int Hd, int Ew, int B, int maxlen, void* ws) {
+  (void)Ew;
+  EncWs w;
+  Carver c(ws);
+  w.splitk = gemm_pick_splitk(B, 4 * Hd, Hd, device_num_sms());
+  w.xproj = c.take((size_t)ndir * B * maxlen * 4 * Hd);
+  for (int i = 0; i < 2; ++i) w.h[i] = c.take((size_t)ndir * B * Hd);
+  for (int i = 0; i < 2; ++i) w.c[i] = c.take((size_t)ndir * B * Hd);
+  w.gpart = c.take((size_t)w.splitk * B * 4 * Hd);
+  w.bytes = c.off;
+  return w;
+}
+
+static int32_t check_dims(const sfb_dims* d) {
+  SFB_CHECK_ARG(d != nullptr, "dims is NULL");
+  SFB_CHECK_ARG(d->E > 0 && d->F > 0 && d->H > 0 && d->D > 0 && d->V > 0, "dims must be positive");
+  SFB_CHECK_ARG((d->E % 4) == 0 && (d->F % 4) == 0 && (d->H % 4) == 0 && (d->D % 4) == 0,
+                "E, F, H, D must be multiples of 4");
+  return 0;
+}
+
+static int32_t check_ws(void* ws, size_t have, size_t need) {
+  if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u) != 0 || have < need) {
+    set_error("workspace missing, not 256-byte aligned or too small (need " + std::to_string(need) + " bytes, have " +
+              std::to_string(have) + ")");
+    return SFB_ERR_WORKSPACE;
+  }
+  return 0;
+}
+
+// q = W_v^T (W_h h + b_h)  [B,F]; the b_v . t term is constant over the views and cancels in the softmax.
+static int32_t visual_query(const sfb_dims& d, const sfb_vis_lstm_weights& w, int B, const float* h, float* tv,
+                            float* q, cudaStream_t st) {
+  GemmParams g{};
+  g.nseg = 1;
+  g.seg[0] = GemmSeg{h, d.H, nullptr, nullptr, 0, w.va_w_h, d.H, d.H, 0};
+  g.M = B; g.N = d.D; g.splitk = 1; g.out = tv; g.ldo = d.D; g.bias0 = w.va_b_h;
+  SFB_PROPAGATE(launch_gemm(g, st));
+  GemmParams g2{};
+  g2.nseg = 1;
+  g2.seg[0] = GemmSeg{tv, d.D, nullptr, nullptr, 0, w.va_w_v, d.F, d.D, 1};
+  g2.M = B; g2.N = d.F; g2.splitk = 1; g2.out = q; g2.ldo = d.F;
+  return launch_gemm(g2, st);
+}
+
+static int32_t visual_attend(const sfb_dims& d, int B, const float* q, const sfb_visual_source& v, float* feature,
+                             float* alpha_v, cudaStream_t st) {
+  AttnParams a{};
+  a.q = q; a.ldq = d.F;
+  a.R = d.V; a.D = d.F;
+  if (v.visual) {
+    a.segA = v.visual; a.strideA_b = (long long)d.V * d.F; a.strideA_r = d.F; a.lenA = d.F;
+    a.segB = nullptr; a.lenB = 0;
+  } else {
+    SFB_CHECK_ARG(v.feat_table && v.loc_table && v.vp_idx && v.view_idx, "gather visual source needs tables + indices");
+    SFB_CHECK_ARG(v.img_dim > 0 && v.img_dim < d.F && (v.img_dim % 4) == 0, "bad img_dim");
+    const int loc = d.F - v.img_dim;
+    a.segA = v.feat_table; a.strideA_b = (long long)d.V * v.img_dim; a.strideA_r = v.img_dim; a.lenA = v.img_dim;
+    a.idxA = v.vp_idx;
+    a.segB = v.loc_table; a.strideB_b = (long long)d.V * loc; a.strideB_r = loc; a.lenB = loc;
+    a.idxB = v.view_idx;
+  }
+  a.mask = nullptr;
+  a.out = feature; a.ldo = d.F;
+  a.alpha = alpha_v; a.ldalpha = d.V;
+  return launch_soft_dot_attention(a, B, st);
+}
+
+// gates partials = [xa | feat] (.* drop_x) W_ih^T + h0 W_hh^T ; then the pointwise cell update.
+static int32_t lstm_cell(int Ea, int F, int H, const float* w_ih, const float* w_hh, const float* b_ih,
+                         const float* b_hh, int B, const float* xa, const int32_t* xa_rows, const float* feat,
+                         const float* h0, const float* c0, const float* drop_x, const float* drop_h, float* gpart,
+                         int splitk, float* gates_act, float* h1, float* c1, float* h1d, cudaStream_t st) {
+  GemmParams g{};
+  const int ldw = Ea + F;
+  int s = 0;
+  g.seg[s++] = GemmSeg{xa, Ea, xa_rows, drop_x, drop_x ? ldw : 0, w_ih, ldw, Ea, 0};
+  if (F > 0) g.seg[s++] = GemmSeg{feat, F, nullptr, drop_x ? drop_x + Ea : nullptr, drop_x ? ldw : 0, w_ih + Ea, ldw, F, 0};
+  g.seg[s++] = GemmSeg{h0, H, nullptr, nullptr, 0, w_hh, H, H, 0};
+  g.nseg = s;
+  g.M = B; g.N = 4 * H; g.splitk = splitk; g.out = gpart; g.ldo = 4 * H;
+  SFB_PROPAGATE(launch_gemm(g, st));
+  LstmPointwiseParams p{};
+  p.partial = gpart; p.splitk = splitk; p.b_ih = b_ih; p.b_hh = b_hh; p.c0 = c0; p.drop_h = drop_h;
+  p.h1 = h1; p.c1 = c1; p.h1_drop = h1d; p.gates_act = gates_act; p.B = B; p.H = H;
+  return launch_lstm_pointwise(p, st);
+}
+
+// SoftDotAttention on an already (optionally dropped) h: t = W_in h; attention over ctx; h~ = tanh(W_out [wc;h])
+static int32_t soft_dot(int H, const sfb_softdot_weights& w, int B, int L, const float* h, const float* ctx,
+                        const uint8_t* mask, float* t, float* wc, float* h_tilde, float* alpha, cudaStream_t st) {
+  GemmParams g{};
+  g.nseg = 1;
+  g.seg[0] = GemmSeg{h, H, nullptr, nullptr, 0, w.w_in, H, H, 0};
+  g.M = B; g.N = H; g.splitk = 1; g.out = t; g.ldo = H;
+  SFB_PROPAGATE(launch_gemm(g, st));
+  AttnParams a{};
+  a.q = t; a.ldq = H; a.R = L; a.D = H;
+  a.segA = ctx; a.strideA_b = (long long)L * H; a.strideA_r = H; a.lenA = H; a.lenB = 0;
+  a.mask = mask; a.ldmask = L;
+  a.out = wc; a.ldo = H; a.alpha = alpha; a.ldalpha = L;
+  SFB_PROPAGATE(launch_soft_dot_attention(a, B, st));
+  GemmParams g2{};
+  g2.nseg = 2;
+  g2.seg[0] = GemmSeg{wc, H, nullptr, nullptr, 0, w.w_out, 2 * H, H, 0};
+  g2.seg[1] = GemmSeg{h, H, nullptr, nullptr, 0, w.w_out + H, 2 * H, H, 0};
+  g2.M = B; g2.N = H; g2.splitk = 1; g2.out = h_tilde; g2.ldo = H; g2.act = 1;
+  return launch_gemm(g2, st);
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" {
+
+int32_t sfb_abi_version(void) { return SFB_ABI_VERSION; }
+const char* sfb_last_error(void) { return g_err.c_str(); }
+int32_t sfb_last_launch_count(void) { return g_launches; }
+
+int32_t sfb_device_info(int32_t* sm, int32_t* num_sms, int32_t* smem_per_block) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("no CUDA device");
+    return SFB_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    set_error("cudaGetDeviceProperties failed");
+    return SFB_ERR_NO_DEVICE;
+  }
+  if (sm) *sm = prop.major * 10 + prop.minor;
+  if (num_sms) *num_sms = prop.multiProcessorCount;
+  if (smem_per_block) *smem_per_block = (int32_t)prop.sharedMemPerBlockOptin;
+  if (prop.major != 10) {
+    set_error("this library carries sm_100a code only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+    return SFB_ERR_NO_DEVICE;
+  }
+  return 0;
+}
+
+size_t sfb_follower_step_workspace_bytes(const sfb_dims* dims, int32_t B, int32_t L, int32_t A) {
+  if (!dims || B < 1) return 0;
+  return carve_follower(*dims, B, L, A, nullptr).bytes;
+}
+
+size_t sfb_speaker_decoder_step_workspace_bytes(int32_t H, int32_t Ew, int32_t B) {
+  if (H < 1 || Ew < 1 || B < 1) return 0;
+  return carve_spkdec(H, Ew, B, nullptr).bytes;
+}
+
+int32_t sfb_visual_attention_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* w, int32_t B, const float* h,
+                                 const sfb_visual_source* vis, float* feature, float* alpha_v, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_CHECK_ARG(w && vis && h && feature, "NULL argument");
+  SFB_CHECK_ARG(B >= 1, "B >= 1");
+  FollowerWs ws = carve_follower(*dims, B, 1, 1, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SFB_PROPAGATE(visual_query(*dims, *w, B, h, ws.tv, ws.q, st));
+  return visual_attend(*dims, B, ws.q, *vis, feature, alpha_v, st);
+}
+
+int32_t sfb_visual_attention_core_fwd(const sfb_dims* dims, int32_t B, const float* q, const sfb_visual_source* vis,
+                                      float* feature, float* alpha_v, void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_CHECK_ARG(q && vis && feature, "NULL argument");
+  SFB_CHECK_ARG(B >= 1, "B >= 1");
+  return visual_attend(*dims, B, q, *vis, feature, alpha_v, static_cast<cudaStream_t>(stream));
+}
+
+int32_t sfb_soft_dot_attention_fwd(const sfb_dims* dims, const sfb_softdot_weights* w, int32_t B, int32_t L,
+                                   const float* h, const float* ctx, const uint8_t* mask, float* h_tilde,
+                                   float* alpha, void* workspace, size_t workspace_bytes, void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_CHECK_ARG(w && h && ctx && h_tilde, "NULL argument");
+  SFB_CHECK_ARG(B >= 1 && L >= 1, "B, L >= 1");
+  FollowerWs ws = carve_follower(*dims, B, L, 1, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
+  return soft_dot(dims->H, *w, B, L, h, ctx, mask, ws.t, ws.wc, h_tilde, alpha, static_cast<cudaStream_t>(stream));
+}
+
+int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* wl, const sfb_softdot_weights* wt,
+                              const sfb_scoring_weights* wsc, int32_t B, int32_t L, int32_t A, const float* u_prev,
+                              const float* all_u_t, const sfb_visual_source* vis, const float* h0, const float* c0,
+                              const float* ctx, const uint8_t* ctx_mask, const float* drop_x, const float* drop_h,
+                              float* h1, float* c1, float* alpha, float* logit, float* alpha_v, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_CHECK_ARG(wl && wt && wsc && vis, "NULL weight/source struct");
+  SFB_CHECK_ARG(u_prev && all_u_t && h0 && c0 && ctx && h1 && c1 && logit, "NULL tensor argument");
+  SFB_CHECK_ARG(B >= 1 && L >= 1 && A >= 1, "B, L, A >= 1");
+  const sfb_dims& d = *dims;
+  FollowerWs ws = carve_follower(d, B, L, A, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  // model.py:389  feature, alpha_v = visual_attention_layer(h_0, visual_context)
+  SFB_PROPAGATE(visual_query(d, *wl, B, h0, ws.tv, ws.q, st));
+  SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, alpha_v, st));
+  // model.py:391-394  LSTMCell(drop(cat(u_t_prev, feature)), (h_0, c_0)); h_1_drop = drop(h_1)
+  SFB_PROPAGATE(lstm_cell(d.E, d.F, d.H, wl->lstm_w_ih, wl->lstm_w_hh, wl->lstm_b_ih, wl->lstm_b_hh, B, u_prev, nullptr,
+                          ws.feat, h0, c0, drop_x, drop_h, ws.gpart, ws.splitk, ws.gates_act, h1, c1, ws.h1d, st));
+  // model.py:395  h_tilde, alpha = text_attention_layer(h_1_drop, ctx, ctx_mask)
+  SFB_PROPAGATE(soft_dot(d.H, *wt, B, L, ws.h1d, ctx, ctx_mask, ws.t, ws.wc, ws.htilde, alpha, st));
+  // model.py:396  logit = decoder2action(h_tilde, all_u_t)
+  {
+    GemmParams g{};
+    g.nseg = 1;
+    g.seg[0] = GemmSeg{ws.htilde, d.H, nullptr, nullptr, 0, wsc->w_h, d.H, d.H, 0};
+    g.M = B; g.N = d.D; g.splitk = 1; g.out = ws.tp; g.ldo = d.D; g.bias0 = wsc->b_h;
+    SFB_PROPAGATE(launch_gemm(g, st));
+    GemmParams g2{};
+    g2.nseg = 1;
+    g2.seg[0] = GemmSeg{ws.tp, d.D, nullptr, wsc->w_out, 0, wsc->w_a, d.E, d.D, 1};
+    g2.M = B; g2.N = d.E; g2.splitk = 1; g2.out = ws.g; g2.ldo = d.E;
+    SFB_PROPAGATE(launch_gemm(g2, st));
+    ScoringParams sp{all_u_t, ws.g, ws.tp, wsc->b_a, wsc->w_out, wsc->b_out, logit, B, A, d.E, d.D};
+    SFB_PROPAGATE(launch_action_scoring(sp, st));
+  }
+  return 0;
+}
+
+int32_t sfb_follower_step_tail(int32_t B, int32_t A, int32_t E, float* logit, const float* is_valid,
+                               const int32_t* target, int32_t feedback, const float* sample_u, const float* all_u_t,
+                               int32_t* a_t, float* u_next, float* action_score, float* ce, void* stream) {
+  reset_launch_count();
+  SFB_CHECK_ARG(B >= 1 && A >= 1 && E >= 4 && (E % 4) == 0, "bad sizes");
+  SFB_CHECK_ARG(logit && is_valid && a_t, "NULL argument");
+  SFB_CHECK_ARG(feedback >= 0 && feedback <= 2, "feedback must be 0 (teacher), 1 (argmax) or 2 (sample)");
+  SFB_CHECK_ARG(feedback != 0 || target, "teacher feedback needs target");
+  SFB_CHECK_ARG(feedback != 2 || sample_u, "sample feedback needs sample_u");
+  SFB_CHECK_ARG(!u_next || all_u_t, "u_next needs all_u_t");
+  SFB_CHECK_ARG(!ce || target, "ce needs target");
+  TailParams p{logit, is_valid, target, feedback, sample_u, all_u_t, a_t, u_next, action_score, ce, B, A, E};
+  return launch_follower_tail(p, static_cast<cudaStream_t>(stream));
+}
+
+size_t sfb_encoder_lstm_workspace_bytes(int32_t ndir, int32_t Hd, int32_t Ew, int32_t B, int32_t maxlen) {
+  if (ndir < 1 || ndir > 2 || Hd < 1 || Ew < 1 || B < 1 || maxlen < 1) return 0;
+  return carve_encoder(ndir, Hd, Ew, B, maxlen, nullptr).bytes;
+}
+
+int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t Hd, int32_t Ew, int32_t B,
+                             int32_t maxlen, const int32_t* seq, const int32_t* lengths, const float* drop_embed,
+                             float* ctx, float* decoder_init, float* c_t, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  reset_launch_count();
+  SFB_CHECK_ARG(w && seq && lengths && ctx && decoder_init && c_t, "NULL argument");
+  SFB_CHECK_ARG(ndir == 1 || ndir == 2, "ndir must be 1 or 2");
+  SFB_CHECK_ARG(Hd >= 4 && (Hd % 4) == 0 && Ew >= 4 && (Ew % 4) == 0 && B >= 1 && maxlen >= 1, "bad sizes");
+  EncWs ws = carve_encoder(ndir, Hd, Ew, B, maxlen, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int H = ndir * Hd;
+  const size_t state = (size_t)B * Hd;
+  SFB_CHECK_CUDA(cudaMemsetAsync(ws.h[0], 0, ndir * state * sizeof(float), st));
+  SFB_CHECK_CUDA(cudaMemsetAsync(ws.c[0], 0, ndir * state * sizeof(float), st));
+  int cur[2] = {0, 0};
+  for (int dir = 0; dir < ndir; ++dir) {
+    // hoisted input projection for every time step at once: [B*maxlen, Ew] x W_ih^T  (model.py:85,90)
+    float* xp = ws.xproj + (size_t)dir * B * maxlen * 4 * Hd;
+    GemmParams g{};
+    g.nseg = 1;
+    g.seg[0] = GemmSeg{w->embedding, Ew, seq, drop_embed, drop_embed ? Ew : 0, w->w_ih[dir], Ew, Ew, 0};
+    g.M = B * maxlen; g.N = 4 * Hd; g.splitk = 1; g.out = xp; g.ldo = 4 * Hd;
+    SFB_PROPAGATE(launch_gemm(g, st));
+    for (int s = 0; s < maxlen; ++s) {
+      const int t = dir == 0 ? s : maxlen - 1 - s;
+      float* hp = ws.h[cur[dir]] + dir * state;
+      float* cp = ws.c[cur[dir]] + dir * state;
+      float* hn = ws.h[cur[dir] ^ 1] + dir * state;
+      float* cn = ws.c[cur[dir] ^ 1] + dir * state;
+      GemmParams r{};
+      r.nseg = 1;
+      r.seg[0] = GemmSeg{hp, Hd, nullptr, nullptr, 0, w->w_hh[dir], Hd, Hd, 0};
+      r.M = B; r.N = 4 * Hd; r.splitk = ws.splitk; r.out = ws.gpart; r.ldo = 4 * Hd;
+      SFB_PROPAGATE(launch_gemm(r, st));
+      LstmPointwiseParams p{};
+      p.partial = ws.gpart; p.splitk = ws.splitk; p.b_ih = w->b_ih[dir]; p.b_hh = w->b_hh[dir];
+      p.c0 = cp; p.h0 = hp; p.h1 = hn; p.c1 = cn; p.B = B; p.H = Hd;
+      p.addend = xp + (size_t)t * 4 * Hd; p.ld_addend = (long long)maxlen * 4 * Hd;
+      p.lengths = lengths; p.t = t;
+      p.seq_out = ctx + (size_t)t * H + dir * Hd; p.ld_seq_out = (long long)maxlen * H;
+      SFB_PROPAGATE(launch_lstm_pointwise(p, st));
+      cur[dir] ^= 1;
+    }
+  }
+  // decoder_init = tanh(encoder2decoder(h_t)), h_t = cat(reverse, forward) when bidirectional (model.py:92-99)
+  GemmParams e{};
+  if (ndir == 1) {
+    e.nseg = 1;
+    e.seg[0] = GemmSeg{ws.h[cur[0]], Hd, nullptr, nullptr, 0, w->e2d_w, H, Hd, 0};
+  } else {
+    e.nseg = 2;
+    e.seg[0] = GemmSeg{ws.h[cur[1]] + state, Hd, nullptr, nullptr, 0, w->e2d_w, H, Hd, 0};
+    e.seg[1] = GemmSeg{ws.h[cur[0]], Hd, nullptr, nullptr, 0, w->e2d_w + Hd, H, Hd, 0};
+  }
+  e.M = B; e.N = H; e.splitk = 1; e.out = decoder_init; e.ldo = H; e.bias0 = w->e2d_b; e.act = 1;
+  SFB_PROPAGATE(launch_gemm(e, st));
+  if (ndir == 1) {
+    SFB_CHECK_CUDA(cudaMemcpyAsync(c_t, ws.c[cur[0]], state * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else {
+    SFB_CHECK_CUDA(cudaMemcpy2DAsync(c_t, (size_t)H * 4, ws.c[cur[1]] + state, (size_t)Hd * 4, (size_t)Hd * 4, B,
+                                     cudaMemcpyDeviceToDevice, st));
+    SFB_CHECK_CUDA(cudaMemcpy2DAsync(c_t + Hd, (size_t)H * 4, ws.c[cur[0]], (size_t)Hd * 4, (size_t)Hd * 4, B,
+                                     cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int32_t sfb_speaker_encoder_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* w, int32_t B,
+                                     const float* action_embedding, const sfb_visual_source* vis, const float* h0,
+                                     const float* c0, const float* drop_x, float* h1, float* c1, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_CHECK_ARG(w && vis && action_embedding && h0 && c0 && h1 && c1, "NULL argument");
+  SFB_CHECK_ARG(B >= 1, "B >= 1");
+  const sfb_dims& d = *dims;
+  FollowerWs ws = carve_follower(d, B, 1, 1, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SFB_PROPAGATE(visual_query(d, *w, B, h0, ws.tv, ws.q, st));
+  SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, nullptr, st));
+  return lstm_cell(d.E, d.F, d.H, w->lstm_w_ih, w->lstm_w_hh, w->lstm_b_ih, w->lstm_b_hh, B, action_embedding, nullptr,
+                   ws.feat, h0, c0, drop_x, nullptr, ws.gpart, ws.splitk, ws.gates_act, h1, c1, nullptr, st);
+}
+
+int32_t sfb_speaker_decoder_step_fwd(const sfb_speaker_decoder_weights* w, int32_t H, int32_t Ew, int32_t vocab,
+                                     int32_t B, int32_t T, const int32_t* prev_word, const float* h0, const float* c0,
+                                     const float* ctx, const uint8_t* ctx_mask, const float* drop_e,
+                                     const float* drop_h, float* h1, float* c1, float* alpha, float* logit,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  reset_launch_count();
+  SFB_CHECK_ARG(w && prev_word && h0 && c0 && ctx && h1 && c1 && logit, "NULL argument");
+  SFB_CHECK_ARG(H >= 4 && (H % 4) == 0 && Ew >= 4 && (Ew % 4) == 0 && vocab >= 1 && B >= 1 && T >= 1, "bad sizes");
+  SpkDecWs ws = carve_spkdec(H, Ew, B, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // model.py:497-503,515: LSTMCell(embedding(previous_word)) — the lookup is a row indirection of the A operand
+  SFB_PROPAGATE(lstm_cell(Ew, 0, H, w->lstm_w_ih, w->lstm_w_hh, w->lstm_b_ih, w->lstm_b_hh, B, w->embedding, prev_word,
+                          nullptr, h0, c0, drop_e, drop_h, ws.gpart, ws.splitk, ws.gates_act, h1, c1, ws.h1d, st));
+  // model.py:516-517
+  SFB_PROPAGATE(soft_dot(H, w->attn, B, T, ws.h1d, ctx, ctx_mask, ws.t, ws.wc, ws.htilde, alpha, st));
+  // model.py:518  logit = decoder2action(h_tilde)
+  GemmParams g{};
+  g.nseg = 1;
+  g.seg[0] = GemmSeg{ws.htilde, H, nullptr, nullptr, 0, w->w_voc, H, H, 0};
+  g.M = B; g.N = vocab; g.splitk = 1; g.out = logit; g.ldo = vocab; g.bias0 = w->b_voc;
+  return launch_gemm(g, st);
+}
+
+}  // extern "C"

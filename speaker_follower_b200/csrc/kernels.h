@@ -1,0 +1,85 @@
+// kernels.h — internal kernel parameter blocks and launchers (not part of the C ABI).
+#pragma once
+#include "../../include/sf_b200.h"
+#include "common.cuh"
+
+namespace sfb {
+
+// ---------------------------------------------------------------- attention.cu
+struct AttnParams {
+  const float* q;   int ldq;              // [B, D] query
+  // row r of batch element b = concat(segA[...], segB[...]); lenA + lenB == D
+  const float* segA; long long strideA_b; int strideA_r; int lenA;
+  const float* segB; long long strideB_b; int strideB_r; int lenB;
+  const int32_t* idxA;                    // optional: batch element b reads block idxA[b] of segA (gather)
+  const int32_t* idxB;
+  const uint8_t* mask; int ldmask;        // [B, R], 1 = masked; may be NULL
+  int R, D;
+  float* out;   int ldo;                  // [B, D]
+  float* alpha; int ldalpha;              // [B, R] or NULL
+  int rows_per_cta;                       // filled by the launcher
+};
+int32_t launch_soft_dot_attention(AttnParams p, int B, cudaStream_t stream);
+
+// ---------------------------------------------------------------- gemm_simt.cu
+// out[M,N] = act( sum_s (x_s .* xs_s) · w_s^T + bias0 + bias1 )   with M <= a few hundred ("skinny").
+struct GemmSeg {
+  const float* x;  int ldx;               // [M, k] activations (row stride ldx)
+  const int32_t* xrow;                    // optional row indirection: row m reads x[xrow[m]] (embedding lookup)
+  const float* xs; int ldxs;              // optional elementwise scale (dropout keep mask); ldxs may be 0
+  const float* w;  int ldw;               // w_kn == 0: [N, k] row-major (nn.Linear); w_kn == 1: [k, N] row-major
+  int k;
+  int w_kn;
+};
+struct GemmParams {
+  GemmSeg seg[3];
+  int nseg;
+  int M, N;
+  int splitk;                             // >1: raw partial sums go to out[splitk][M][N] (ldo ignored)
+  float* out; int ldo;
+  const float* bias0; const float* bias1; // [N] or NULL (splitk == 1 only)
+  int act;                                // 0 none, 1 tanh (splitk == 1 only)
+};
+int32_t launch_gemm(const GemmParams& p, cudaStream_t stream);
+int gemm_pick_splitk(int M, int N, int ktotal, int num_sms);
+
+// ---------------------------------------------------------------- pointwise.cu
+// gates = sum_s partial[s] + b_ih + b_hh ; LSTM cell update (torch.nn.LSTMCell gate order i,f,g,o).
+struct LstmPointwiseParams {
+  const float* partial; int splitk;       // [splitk][B][4H]
+  const float* b_ih; const float* b_hh;   // [4H]
+  const float* c0;                        // [B,H]
+  const float* drop_h;                    // [B,H] scaled keep mask or NULL
+  float* h1; float* c1;                   // [B,H]
+  float* h1_drop;                         // [B,H] h1 .* drop_h (== h1 when drop_h is NULL); may be NULL
+  float* gates_act;                       // [B,4H] activated gates (i,f,g,o) kept for backward; may be NULL
+  int B, H;
+  // sequence mode (EncoderLSTM, model.py:89-90): precomputed input projection + packed-sequence masking
+  const float* addend; long long ld_addend;   // [B,4H] rows at stride ld_addend (x_t W_ih^T), or NULL
+  const float* h0;                            // previous hidden state, carried through when t >= lengths[b]
+  const int32_t* lengths; int t;              // rows with t >= lengths[b] keep (h0, c0) and emit zeros
+  float* seq_out; long long ld_seq_out;       // h1 (or 0 when inactive) written at seq_out[b*ld_seq_out + j]
+};
+int32_t launch_lstm_pointwise(const LstmPointwiseParams& p, cudaStream_t stream);
+
+// logit[b,a] = all_u_t[b,a,:] . g[b,:] + sum_d b_a[d] w_out[d] tp[b,d] + b_out   (EltwiseProdScoring rewritten)
+struct ScoringParams {
+  const float* all_u_t;                   // [B,A,E]
+  const float* g;                         // [B,E]
+  const float* tp;                        // [B,D]  linear_in_h(h_tilde)
+  const float* b_a; const float* w_out; const float* b_out;
+  float* logit;                           // [B,A]
+  int B, A, E, D;
+};
+int32_t launch_action_scoring(const ScoringParams& p, cudaStream_t stream);
+
+struct TailParams {
+  float* logit; const float* is_valid; const int32_t* target; int feedback; const float* sample_u;
+  const float* all_u_t; int32_t* a_t; float* u_next; float* action_score; float* ce;
+  int B, A, E;
+};
+int32_t launch_follower_tail(const TailParams& p, cudaStream_t stream);
+
+int device_num_sms();
+
+}  // namespace sfb

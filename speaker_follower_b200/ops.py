@@ -1,0 +1,308 @@
+"""Tensor-level wrappers over the C ABI (include/sf_b200.h): torch owns device memory and streams, the
+library owns every kernel.  All functions require CUDA fp32 contiguous tensors and raise otherwise —
+there is no CPU path in the product (the CPU restatement lives in oracle/ and is test-only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (Dims, EncoderWeights, ScoringWeights, SoftDotWeights, SpeakerDecoderWeights, VisLstmWeights,
+                   VisualSource, check)
+
+Tensor = torch.Tensor
+
+
+def _p(t: Optional[Tensor], dtype=torch.float32, name="tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.SfbError("%s must be a CUDA tensor (sf_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise _lib.SfbError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise _lib.SfbError("%s must be contiguous" % name)
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _mask_u8(mask: Optional[Tensor]) -> Optional[Tensor]:
+    if mask is None:
+        return None
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    if mask.dtype != torch.uint8:
+        mask = mask.to(torch.uint8)
+    return mask.contiguous()
+
+
+def _i32(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    return t.to(torch.int32).contiguous()
+
+
+class FeatureStore:
+    """Device-resident feature table + orientation table: the B200-native replacement of the per-step host
+    np.stack + H2D copy of the 36-view slab (follower.py:291-298, env.py:330-332)."""
+
+    def __init__(self, feat_table: Tensor, loc_table: Tensor):
+        assert feat_table.dim() == 3 and loc_table.dim() == 3
+        self.feat_table = feat_table.contiguous()
+        self.loc_table = loc_table.contiguous()
+        self.img_dim = feat_table.shape[2]
+
+    def dense(self, vp_idx: Tensor, view_idx: Tensor) -> Tensor:
+        """Materialise [B,36,F] (what the reference builds on the host) — for tests only."""
+        return torch.cat((self.feat_table[vp_idx.long()], self.loc_table[view_idx.long()]), dim=2).contiguous()
+
+
+def _visual_source(visual, store: Optional[FeatureStore], vp_idx, view_idx, keep):
+    vs = VisualSource()
+    if visual is not None:
+        vs.visual = _p(visual, name="visual_context")
+        keep.append(visual)
+    else:
+        vp, vw = _i32(vp_idx), _i32(view_idx)
+        keep.extend([vp, vw])
+        vs.visual = None
+        vs.feat_table = _p(store.feat_table, name="feat_table")
+        vs.loc_table = _p(store.loc_table, name="loc_table")
+        vs.vp_idx = _p(vp, torch.int32, "vp_idx")
+        vs.view_idx = _p(vw, torch.int32, "view_idx")
+        vs.img_dim = store.img_dim
+    return vs
+
+
+def _vis_lstm_weights(w: Dict[str, Tensor]) -> VisLstmWeights:
+    s = VisLstmWeights()
+    s.lstm_w_ih = _p(w["lstm.weight_ih"]); s.lstm_w_hh = _p(w["lstm.weight_hh"])
+    s.lstm_b_ih = _p(w["lstm.bias_ih"]); s.lstm_b_hh = _p(w["lstm.bias_hh"])
+    s.va_w_h = _p(w["visual_attention_layer.linear_in_h.weight"])
+    s.va_b_h = _p(w["visual_attention_layer.linear_in_h.bias"])
+    s.va_w_v = _p(w["visual_attention_layer.linear_in_v.weight"])
+    s.va_b_v = _p(w["visual_attention_layer.linear_in_v.bias"])
+    return s
+
+
+def _softdot_weights(w: Dict[str, Tensor], prefix: str) -> SoftDotWeights:
+    s = SoftDotWeights()
+    s.w_in = _p(w[prefix + "linear_in.weight"]); s.w_out = _p(w[prefix + "linear_out.weight"])
+    return s
+
+
+def _scoring_weights(w: Dict[str, Tensor], prefix="decoder2action.") -> ScoringWeights:
+    s = ScoringWeights()
+    s.w_h = _p(w[prefix + "linear_in_h.weight"]); s.b_h = _p(w[prefix + "linear_in_h.bias"])
+    s.w_a = _p(w[prefix + "linear_in_a.weight"]); s.b_a = _p(w[prefix + "linear_in_a.bias"])
+    s.w_out = _p(w[prefix + "linear_out.weight"]); s.b_out = _p(w[prefix + "linear_out.bias"])
+    return s
+
+
+def follower_dims(w: Dict[str, Tensor], V: int = 36) -> Dims:
+    H = w["lstm.weight_hh"].shape[1]
+    F = w["visual_attention_layer.linear_in_v.weight"].shape[1]
+    E = w["lstm.weight_ih"].shape[1] - F
+    D = w["visual_attention_layer.linear_in_h.weight"].shape[0]
+    return Dims(E, F, H, D, V)
+
+
+def _workspace(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual: Optional[Tensor], h0: Tensor,
+                  c0: Tensor, ctx: Tensor, ctx_mask: Optional[Tensor], drop_x: Optional[Tensor] = None,
+                  drop_h: Optional[Tensor] = None, store: Optional[FeatureStore] = None,
+                  vp_idx: Optional[Tensor] = None, view_idx: Optional[Tensor] = None,
+                  workspace: Optional[Tensor] = None, out: Optional[tuple] = None):
+    """AttnDecoderLSTM.forward (model.py:377-397) -> (h1, c1, alpha, logit, alpha_v)."""
+    lib = _lib.load()
+    B, A, E = all_u_t.shape
+    L = ctx.shape[1]
+    V = visual.shape[1] if visual is not None else store.feat_table.shape[1]
+    d = follower_dims(w, V)
+    dev = h0.device
+    keep = []
+    vs = _visual_source(visual, store, vp_idx, view_idx, keep)
+    mask = _mask_u8(ctx_mask)
+    need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, L, A)
+    if workspace is None or workspace.numel() < need:
+        workspace = _workspace(need, dev)
+    if out is None:
+        h1 = torch.empty(B, d.H, device=dev); c1 = torch.empty(B, d.H, device=dev)
+        alpha = torch.empty(B, L, device=dev); logit = torch.empty(B, A, device=dev)
+        alpha_v = torch.empty(B, V, device=dev)
+    else:
+        h1, c1, alpha, logit, alpha_v = out
+    wl, wt, ws = _vis_lstm_weights(w), _softdot_weights(w, "text_attention_layer."), _scoring_weights(w)
+    check(lib.sfb_follower_step_fwd(
+        C.byref(d), C.byref(wl), C.byref(wt), C.byref(ws), B, L, A,
+        _p(u_prev, name="u_t_prev"), _p(all_u_t, name="all_u_t"), C.byref(vs), _p(h0, name="h_0"), _p(c0, name="c_0"),
+        _p(ctx, name="ctx"), _p(mask, torch.uint8, "ctx_mask"), _p(drop_x, name="drop_x"), _p(drop_h, name="drop_h"),
+        _p(h1), _p(c1), _p(alpha), _p(logit), _p(alpha_v), workspace.data_ptr(), workspace.numel(), _stream()))
+    return h1, c1, alpha, logit, alpha_v
+
+
+def follower_tail(logit: Tensor, is_valid: Tensor, all_u_t: Tensor, feedback: str, target: Optional[Tensor] = None,
+                  sample_u: Optional[Tensor] = None, out: Optional[tuple] = None):
+    """follower.py:476-505 -> (a_t int32 [B], u_next [B,E], action_score [B], ce [B]); masks `logit` in place."""
+    lib = _lib.load()
+    B, A, E = all_u_t.shape
+    dev = logit.device
+    fb = {"teacher": 0, "argmax": 1, "sample": 2}[feedback]
+    if out is None:
+        a_t = torch.empty(B, dtype=torch.int32, device=dev)
+        u_next = torch.empty(B, E, device=dev)
+        score = torch.empty(B, device=dev)
+        ce = torch.empty(B, device=dev) if target is not None else None
+    else:
+        a_t, u_next, score, ce = out
+    tgt = _i32(target)
+    check(lib.sfb_follower_step_tail(B, A, E, _p(logit, name="logit"), _p(is_valid, name="is_valid"),
+                                     _p(tgt, torch.int32, "target"), fb, _p(sample_u, name="sample_u"),
+                                     _p(all_u_t, name="all_u_t"), _p(a_t, torch.int32), _p(u_next), _p(score), _p(ce),
+                                     _stream()))
+    return a_t, u_next, score, ce
+
+
+def visual_attention(w: Dict[str, Tensor], h: Tensor, visual: Optional[Tensor], store=None, vp_idx=None,
+                     view_idx=None):
+    """VisualSoftDotAttention.forward (model.py:310-326) -> (feature [B,F], alpha_v [B,V])."""
+    lib = _lib.load()
+    B = h.shape[0]
+    V = visual.shape[1] if visual is not None else store.feat_table.shape[1]
+    H = h.shape[1]
+    F = w["visual_attention_layer.linear_in_v.weight"].shape[1]
+    D = w["visual_attention_layer.linear_in_h.weight"].shape[0]
+    d = Dims(F, F, H, D, V)
+    keep = []
+    vs = _visual_source(visual, store, vp_idx, view_idx, keep)
+    s = VisLstmWeights()
+    s.va_w_h = _p(w["visual_attention_layer.linear_in_h.weight"]); s.va_b_h = _p(w["visual_attention_layer.linear_in_h.bias"])
+    s.va_w_v = _p(w["visual_attention_layer.linear_in_v.weight"]); s.va_b_v = _p(w["visual_attention_layer.linear_in_v.bias"])
+    need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, 1, 1)
+    ws = _workspace(need, h.device)
+    feat = torch.empty(B, F, device=h.device); alpha_v = torch.empty(B, V, device=h.device)
+    check(lib.sfb_visual_attention_fwd(C.byref(d), C.byref(s), B, _p(h, name="h"), C.byref(vs), _p(feat), _p(alpha_v),
+                                       ws.data_ptr(), ws.numel(), _stream()))
+    return feat, alpha_v
+
+
+def visual_attention_core(q: Tensor, visual: Optional[Tensor], store=None, vp_idx=None, view_idx=None,
+                          out: Optional[tuple] = None):
+    """The attention-gather kernel alone: q [B,F] -> (feature [B,F], alpha_v [B,V]); one launch."""
+    lib = _lib.load()
+    B, F = q.shape
+    V = visual.shape[1] if visual is not None else store.feat_table.shape[1]
+    d = Dims(F, F, 4, 4, V)
+    keep = []
+    vs = _visual_source(visual, store, vp_idx, view_idx, keep)
+    if out is None:
+        feat = torch.empty(B, F, device=q.device); alpha_v = torch.empty(B, V, device=q.device)
+    else:
+        feat, alpha_v = out
+    check(lib.sfb_visual_attention_core_fwd(C.byref(d), B, _p(q, name="q"), C.byref(vs), _p(feat), _p(alpha_v),
+                                            _stream()))
+    return feat, alpha_v
+
+
+def soft_dot_attention(w: Dict[str, Tensor], prefix: str, h: Tensor, ctx: Tensor, mask: Optional[Tensor]):
+    """SoftDotAttention.forward (model.py:122-143) -> (h_tilde [B,H], alpha [B,L])."""
+    lib = _lib.load()
+    B, L, H = ctx.shape
+    d = Dims(4, 4, H, 4, 1)
+    sw = _softdot_weights(w, prefix)
+    m = _mask_u8(mask)
+    need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, L, 1)
+    ws = _workspace(need, h.device)
+    ht = torch.empty(B, H, device=h.device); alpha = torch.empty(B, L, device=h.device)
+    check(lib.sfb_soft_dot_attention_fwd(C.byref(d), C.byref(sw), B, L, _p(h, name="h"), _p(ctx, name="ctx"),
+                                         _p(m, torch.uint8, "mask"), _p(ht), _p(alpha), ws.data_ptr(), ws.numel(),
+                                         _stream()))
+    return ht, alpha
+
+
+def encoder_lstm(w: Dict[str, Tensor], seq: Tensor, lengths, bidirectional: bool = False,
+                 drop_embed: Optional[Tensor] = None):
+    """EncoderLSTM.forward (model.py:81-104), without the final ctx dropout -> (ctx, decoder_init, c_t)."""
+    lib = _lib.load()
+    dev = seq.device
+    ndir = 2 if bidirectional else 1
+    Hd = w["lstm.weight_hh_l0"].shape[1]
+    Ew = w["embedding.weight"].shape[1]
+    H = ndir * Hd
+    B = seq.shape[0]
+    lens = torch.as_tensor([int(x) for x in lengths], dtype=torch.int32)
+    maxlen = int(lens.max())
+    seq32 = seq[:, :maxlen].to(torch.int32).contiguous()
+    lens_d = lens.to(dev)
+    ew = EncoderWeights()
+    ew.embedding = _p(w["embedding.weight"])
+    for i, suf in enumerate(["_l0", "_l0_reverse"][:ndir]):
+        ew.w_ih[i] = _p(w["lstm.weight_ih" + suf]); ew.w_hh[i] = _p(w["lstm.weight_hh" + suf])
+        ew.b_ih[i] = _p(w["lstm.bias_ih" + suf]); ew.b_hh[i] = _p(w["lstm.bias_hh" + suf])
+    ew.e2d_w = _p(w["encoder2decoder.weight"]); ew.e2d_b = _p(w["encoder2decoder.bias"])
+    need = lib.sfb_encoder_lstm_workspace_bytes(ndir, Hd, Ew, B, maxlen)
+    ws = _workspace(need, dev)
+    ctx = torch.empty(B, maxlen, H, device=dev); dec = torch.empty(B, H, device=dev); c_t = torch.empty(B, H, device=dev)
+    check(lib.sfb_encoder_lstm_fwd(C.byref(ew), ndir, Hd, Ew, B, maxlen, _p(seq32, torch.int32, "seq"),
+                                   _p(lens_d, torch.int32, "lengths"), _p(drop_embed, name="drop_embed"),
+                                   _p(ctx), _p(dec), _p(c_t), ws.data_ptr(), ws.numel(), _stream()))
+    return ctx, dec, c_t
+
+
+def speaker_encoder_step(w: Dict[str, Tensor], action_embedding: Tensor, visual: Optional[Tensor], h0: Tensor,
+                         c0: Tensor, drop_x: Optional[Tensor] = None, store=None, vp_idx=None, view_idx=None):
+    """SpeakerEncoderLSTM._forward_one_step (model.py:429-435) -> (h1, c1)."""
+    lib = _lib.load()
+    B = h0.shape[0]
+    V = visual.shape[1] if visual is not None else store.feat_table.shape[1]
+    d = follower_dims(w, V)
+    keep = []
+    vs = _visual_source(visual, store, vp_idx, view_idx, keep)
+    wl = _vis_lstm_weights(w)
+    need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, 1, 1)
+    ws = _workspace(need, h0.device)
+    h1 = torch.empty_like(h0); c1 = torch.empty_like(c0)
+    check(lib.sfb_speaker_encoder_step_fwd(C.byref(d), C.byref(wl), B, _p(action_embedding, name="action_embedding"),
+                                           C.byref(vs), _p(h0, name="h_0"), _p(c0, name="c_0"), _p(drop_x, name="drop_x"),
+                                           _p(h1), _p(c1), ws.data_ptr(), ws.numel(), _stream()))
+    return h1, c1
+
+
+def speaker_decoder_step(w: Dict[str, Tensor], prev_word: Tensor, h0: Tensor, c0: Tensor, ctx: Tensor,
+                         ctx_mask: Optional[Tensor], drop_e: Optional[Tensor] = None, drop_h: Optional[Tensor] = None):
+    """SpeakerDecoderLSTM.forward default branch (model.py:497-503,515-519) -> (h1, c1, alpha, logit)."""
+    lib = _lib.load()
+    B, T, H = ctx.shape
+    vocab, Ew = w["embedding.weight"].shape
+    dev = h0.device
+    sw = SpeakerDecoderWeights()
+    sw.embedding = _p(w["embedding.weight"])
+    sw.lstm_w_ih = _p(w["lstm.weight_ih"]); sw.lstm_w_hh = _p(w["lstm.weight_hh"])
+    sw.lstm_b_ih = _p(w["lstm.bias_ih"]); sw.lstm_b_hh = _p(w["lstm.bias_hh"])
+    sw.attn = _softdot_weights(w, "attention_layer.")
+    sw.w_voc = _p(w["decoder2action.weight"]); sw.b_voc = _p(w["decoder2action.bias"])
+    pw = _i32(prev_word.reshape(-1))
+    m = _mask_u8(ctx_mask)
+    need = lib.sfb_speaker_decoder_step_workspace_bytes(H, Ew, B)
+    ws = _workspace(need, dev)
+    h1 = torch.empty(B, H, device=dev); c1 = torch.empty(B, H, device=dev)
+    alpha = torch.empty(B, T, device=dev); logit = torch.empty(B, vocab, device=dev)
+    check(lib.sfb_speaker_decoder_step_fwd(C.byref(sw), H, Ew, vocab, B, T, _p(pw, torch.int32, "previous_word"),
+                                           _p(h0, name="h_0"), _p(c0, name="c_0"), _p(ctx, name="ctx"),
+                                           _p(m, torch.uint8, "ctx_mask"), _p(drop_e, name="drop_e"),
+                                           _p(drop_h, name="drop_h"), _p(h1), _p(c1), _p(alpha), _p(logit),
+                                           ws.data_ptr(), ws.numel(), _stream()))
+    return h1, c1, alpha, logit
+
+
+def last_launch_count() -> int:
+    return int(_lib.load().sfb_last_launch_count())

@@ -1,0 +1,248 @@
+"""GPU parity tests: the CUDA path (through the C ABI, speaker_follower_b200.ops) against
+ (a) the golden vectors produced by the reference's own model.py, and
+ (b) the CPU oracle on the same seeded inputs.
+Tolerance: 1e-4 absolute on fp32 states/logits (BASELINE.json north_star), argmax identical."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, split_golden
+from oracle import r2r_oracle as O
+from speaker_follower_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def cu(x):
+    if isinstance(x, dict):
+        return {k: cu(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [cu(v) for v in x]
+    return x.cuda() if isinstance(x, torch.Tensor) else x
+
+
+def close(a, b, tol=TOL, what=""):
+    a, b = a.detach().float().cpu(), torch.as_tensor(b).float()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    fin = torch.isfinite(b)
+    assert torch.equal(torch.isfinite(a), fin), what
+    err = (a[fin] - b[fin]).abs().max().item() if fin.any() else 0.0
+    assert err <= tol, (what, err)
+    return err
+
+
+def run_step(w, x, drop_x=None, drop_h=None, gather=None):
+    wc, xc = cu(w), cu(x)
+    if gather is None:
+        return ops.follower_step(wc, xc["u_t_prev"], xc["all_u_t"], xc["visual_context"], xc["h_0"], xc["c_0"],
+                                 xc["ctx"], xc["ctx_mask"], cu(drop_x), cu(drop_h))
+    store, vp, view = gather
+    return ops.follower_step(wc, xc["u_t_prev"], xc["all_u_t"], None, xc["h_0"], xc["c_0"], xc["ctx"],
+                             xc["ctx_mask"], cu(drop_x), cu(drop_h), store=store, vp_idx=vp.cuda(), view_idx=view.cuda())
+
+
+NAMES = ("h_1", "c_1", "alpha", "logit", "alpha_v")
+
+
+def test_follower_step_small_golden():
+    w, x, out, _ = split_golden(load_golden("follower_step_small"))
+    res = run_step(w, x)
+    for k, v in zip(NAMES, res):
+        close(v, out[k], what=k)
+
+
+def test_follower_step_small_train_masks_golden():
+    w, x, out, rest = split_golden(load_golden("follower_step_small_train"))
+    res = run_step(w, x, rest["drop.x"], rest["drop.h"])
+    for k, v in zip(NAMES, res):
+        close(v, out[k], what=k)
+
+
+@pytest.mark.parametrize("name", ["follower_step_c1", "follower_step_c2", "follower_step_b3"])
+def test_follower_step_full_golden_and_oracle(name):
+    z = load_golden(name)
+    B, L, A, seed = int(z["B"]), int(z["L"]), int(z["A"]), int(z["seed"])
+    w = synth.follower_decoder_weights()
+    x = synth.follower_step_inputs(B, L, A, seed=seed)
+    res = run_step(w, x)
+    _, _, out, _ = split_golden(z)
+    for k, v in zip(NAMES, res):
+        close(v, out[k], what=k)
+    ref = O.attn_decoder_step(x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
+                              x["ctx_mask"], w)
+    for k, v, r in zip(NAMES, res, ref):
+        close(v, r, what="oracle:" + k)
+    # argmax over valid actions identical (follower.py:477,488)
+    lg = res[3].cpu().masked_fill(x["is_valid"] == 0, -float("inf"))
+    lr = ref[3].masked_fill(x["is_valid"] == 0, -float("inf"))
+    assert torch.equal(lg.max(1)[1], lr.max(1)[1])
+
+
+def test_follower_step_gather_equals_dense():
+    """The device-resident feature table path (replaces follower.py:291-298) gives the same bits as dense."""
+    B, L, A = 100, 80, 8
+    w = synth.follower_decoder_weights()
+    table = synth.feature_table(64, 1031)
+    loc = synth.loc_embedding_table()
+    x = synth.follower_step_inputs(B, L, A, seed=55, table=table, loc=loc)
+    dense = run_step(w, x)
+    store = ops.FeatureStore(table.cuda(), loc.cuda())
+    gath = run_step(w, x, gather=(store, x["vp_idx"], x["view_idx"]))
+    for k, a, b in zip(NAMES, dense, gath):
+        assert torch.equal(a, b), k
+    assert torch.equal(store.dense(x["vp_idx"].cuda(), x["view_idx"].cuda()).cpu(), x["visual_context"])
+
+
+def test_follower_step_properties_full_size():
+    """Size-independent properties at the benchmark size (B=100, L=80, A=8)."""
+    B, L, A = 100, 80, 8
+    w = synth.follower_decoder_weights()
+    x = synth.follower_step_inputs(B, L, A, seed=56)
+    h1, c1, alpha, logit, alpha_v = run_step(w, x)
+    assert torch.allclose(alpha.sum(1).cpu(), torch.ones(B), atol=1e-5)
+    assert torch.allclose(alpha_v.sum(1).cpu(), torch.ones(B), atol=1e-5)
+    assert (alpha.cpu()[x["ctx_mask"]] == 0).all()
+    assert (alpha_v >= 0).all() and (h1.abs() <= 1).all()
+    # batch rows are independent: a permutation of the batch permutes the outputs (bitwise for row-local math)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(3))
+    xp = {k: (v[perm] if isinstance(v, torch.Tensor) and v.shape[:1] == (B,) else v) for k, v in x.items()}
+    res_p = run_step(w, xp)
+    close(res_p[3], logit.cpu()[perm], 1e-5, "perm logit")
+    close(res_p[0], h1.cpu()[perm], 1e-5, "perm h1")
+
+
+@pytest.mark.parametrize("feedback", ["teacher", "argmax", "sample"])
+def test_follower_tail(feedback):
+    g = torch.Generator().manual_seed(7)
+    B, A, E = 37, 9, 2176
+    logit = torch.randn(B, A, generator=g)
+    valid = (torch.rand(B, A, generator=g) > 0.3).float()
+    valid[:, 0] = 1
+    target = torch.randint(-1, A, (B,), generator=g)
+    target = torch.where((target >= 0) & (valid[torch.arange(B), target.clamp(min=0)] == 0), torch.zeros_like(target), target)
+    U = torch.randn(B, A, E, generator=g)
+    su = torch.rand(B, generator=g)
+    lg_ref, loss, a_ref, u_ref, sc_ref = O.follower_step_tail(logit, valid, target, feedback, U, su)
+    lg = logit.clone().cuda()
+    a_t, u_next, score, ce = ops.follower_tail(lg, valid.cuda(), U.cuda(), feedback, target.cuda(), su.cuda())
+    close(lg, lg_ref, 0, "masked logit")
+    assert torch.equal(a_t.cpu().long(), a_ref)
+    assert torch.equal(u_next.cpu(), u_ref)
+    close(score, sc_ref, 1e-5, "score")
+    keep = target >= 0
+    close((ce.cpu() * keep).sum() / keep.sum(), loss, 1e-5, "loss")
+
+
+def test_encoder_small_uni_bi_golden():
+    for name, bi in (("encoder_small", False), ("encoder_small_bi", True)):
+        w, _, out, rest = split_golden(load_golden(name))
+        ctx, h, c = ops.encoder_lstm(cu(w), rest["seq"].cuda(), rest["lengths"].tolist(), bidirectional=bi)
+        close(ctx, out["ctx"], what="ctx"); close(h, out["h"], what="h"); close(c, out["c"], what="c")
+
+
+def test_encoder_full_golden():
+    z = load_golden("encoder_full")
+    w = synth.follower_encoder_weights()
+    seq, mask, lengths = synth.instruction_batch(int(z["B"]), int(z["L"]), seed=int(z["seed"]))
+    ctx, h, c = ops.encoder_lstm(cu(w), seq.cuda(), lengths)
+    _, _, out, _ = split_golden(z)
+    close(ctx, out["ctx"], what="ctx"); close(h, out["h"], what="h"); close(c, out["c"], what="c")
+
+
+def test_encoder_c2_oracle():
+    w = synth.follower_encoder_weights()
+    seq, mask, lengths = synth.instruction_batch(100, 80, seed=43)
+    ctx, h, c = ops.encoder_lstm(cu(w), seq.cuda(), lengths)
+    rctx, rh, rc = O.encoder_lstm(seq, lengths, w)
+    close(ctx, rctx, what="ctx"); close(h, rh, what="h"); close(c, rc, what="c")
+
+
+def test_speaker_small_golden():
+    w, _, out, rest = split_golden(load_golden("speaker_encoder_small"))
+    wc = cu(w)
+    T, N = rest["acts"].shape[:2]
+    H = w["lstm.weight_hh"].shape[1]
+    h = torch.zeros(N, H, device="cuda"); c = torch.zeros(N, H, device="cuda")
+    hs = []
+    for t in range(T):
+        h, c = ops.speaker_encoder_step(wc, rest["acts"][t].cuda(), rest["feats"][t].cuda().contiguous(), h, c)
+        hs.append(h)
+    close(torch.stack(hs, 1), out["ctx"], what="ctx"); close(c, out["c"], what="c")
+    w, _, out, rest = split_golden(load_golden("speaker_decoder_small"))
+    h1, c1, alpha, logit = ops.speaker_decoder_step(cu(w), rest["prev"].cuda(), rest["h_0"].cuda(), rest["c_0"].cuda(),
+                                                    rest["ctx"].cuda(), rest["mask"].cuda())
+    close(h1, out["h_1"]); close(c1, out["c_1"]); close(alpha, out["alpha"]); close(logit, out["logit"])
+
+
+def test_speaker_full_golden():
+    z = load_golden("speaker_full")
+    _, _, out, rest = split_golden(z)
+    N, T, S = int(z["N"]), int(z["T"]), int(z["S"])
+    we, wd = cu(synth.speaker_encoder_weights()), cu(synth.speaker_decoder_weights())
+    h = torch.zeros(N, synth.HID, device="cuda"); c = torch.zeros(N, synth.HID, device="cuda")
+    hs = []
+    for k in range(T):
+        x = synth.follower_step_inputs(N, 8, 6, seed=200 + k)
+        h, c = ops.speaker_encoder_step(we, x["u_t_prev"].cuda(), x["visual_context"].cuda(), h, c)
+        hs.append(h)
+    ctx = torch.stack(hs, 1).contiguous()
+    close(ctx, out["ctx"], what="ctx"); close(c, out["c"], what="c")
+    # decoder_init = tanh(encoder2decoder(h_T)) is host-side plumbing of the module; check through model.py tests
+    h = torch.tanh(h @ we["encoder2decoder.weight"].t() + we["encoder2decoder.bias"])
+    close(h, out["h"], what="dec_init")
+    w_t = torch.full((N,), 3, dtype=torch.long, device="cuda")
+    for s in range(S):
+        h, c, alpha, logit = ops.speaker_decoder_step(wd, w_t, h, c, ctx, rest["mask"].cuda())
+        close(logit, out["logit%d" % s], what="logit%d" % s); close(h, out["h%d" % s], what="h%d" % s)
+        w_t = rest["words"][:, s].cuda()
+
+
+def test_speaker_decoder_c3_oracle():
+    """Config C3 shape: N=256 paths, T=6 path steps, vocabulary 991."""
+    g = torch.Generator().manual_seed(9)
+    N, T, H = 256, 6, synth.HID
+    wd = synth.speaker_decoder_weights()
+    ctx = torch.tanh(torch.randn(N, T, H, generator=g)); h0 = torch.tanh(torch.randn(N, H, generator=g))
+    c0 = torch.randn(N, H, generator=g) * 0.5
+    mask = torch.arange(T).unsqueeze(0) >= torch.randint(1, T + 1, (N, 1), generator=g)
+    prev = torch.randint(0, synth.VOCAB, (N,), generator=g)
+    ref = O.speaker_decoder_step(prev, h0, c0, ctx, mask, wd)
+    res = ops.speaker_decoder_step(cu(wd), prev.cuda(), h0.cuda(), c0.cuda(), ctx.cuda(), mask.cuda())
+    for a, b, k in zip(res, ref, ("h1", "c1", "alpha", "logit")):
+        close(a, b, what=k)
+    assert torch.equal(res[3].cpu().max(1)[1], ref[3].max(1)[1])
+
+
+def test_follower_rollout_full_golden():
+    z = load_golden("follower_rollout_full")
+    _, _, out, _ = split_golden(z)
+    B, L, A, S = int(z["B"]), int(z["L"]), int(z["A"]), int(z["S"])
+    we, wd = cu(synth.follower_encoder_weights()), cu(synth.follower_decoder_weights())
+    seq, mask, lengths = synth.instruction_batch(B, L, seed=41)
+    ctx, h, c = ops.encoder_lstm(we, seq.cuda(), lengths)
+    u_prev = torch.zeros(B, synth.FEAT, device="cuda")
+    mask_c = mask.cuda()
+    total = torch.zeros(B, device="cuda")
+    for s in range(S):
+        x = cu(synth.follower_step_inputs(B, L, A, seed=300 + s))
+        h, c, alpha, logit, alpha_v = ops.follower_step(wd, u_prev, x["all_u_t"], x["visual_context"], h, c, ctx, mask_c)
+        a_t, u_prev, score, _ = ops.follower_tail(logit, x["is_valid"], x["all_u_t"], "argmax")
+        close(logit, out["logit%d" % s], what="logit%d" % s)
+        assert torch.equal(a_t.cpu().long(), out["a%d" % s])
+        close(score, out["score%d" % s], what="score%d" % s)
+        total += score
+    close(total, out["seq_score"], 2e-4, "seq_score")
+    close(h, out["h"], what="h"); close(c, out["c"], what="c")
+
+
+def test_errors_are_loud():
+    from speaker_follower_b200._lib import SfbError
+    w = cu(synth.follower_decoder_weights())
+    x = cu(synth.follower_step_inputs(4, 12, 5, seed=1))
+    with pytest.raises(SfbError):   # CPU tensor on the product path
+        ops.follower_step(w, x["u_t_prev"].cpu(), x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
+                          x["ctx_mask"])
+    with pytest.raises(SfbError):   # non-contiguous
+        ops.follower_step(w, x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"].t().contiguous().t(),
+                          x["c_0"], x["ctx"], x["ctx_mask"])
