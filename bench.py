@@ -132,6 +132,13 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    print("[bench %.1fs] %s" % (time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
+
+
 def run_gpu(args, rank, local_rank, world):
     from speaker_follower_b200 import ops, synth
     import __graft_entry__ as ge
@@ -156,6 +163,7 @@ def run_gpu(args, rank, local_rank, world):
         table[i:i + 1024].normal_(generator=g).clamp_(min=0).mul_(1.1)
     store = ops.FeatureStore(table, synth.loc_embedding_table().to(dev))
 
+    log("feature table ready")
     # rotating input sets
     vp = [torch.randint(0, N_VIEWPOINTS, (B,), device=dev, dtype=torch.int32, generator=g) for _ in range(POOL)]
     view = [torch.randint(0, 36, (B,), device=dev, dtype=torch.int32, generator=g) for _ in range(POOL)]
@@ -195,6 +203,7 @@ def run_gpu(args, rank, local_rank, world):
         ops.follower_tail(logit, valid[j], U[j], "argmax", out=(a_t, ubuf[s ^ 1], score, None))
         launches_per_step[0] = n + ops.last_launch_count()
 
+    log("inputs ready")
     # warm-up outside graphs (also configures kernel attributes), then capture POOL-step graphs
     side = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(side):
@@ -202,6 +211,12 @@ def run_gpu(args, rank, local_rank, world):
             step(i)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    if args.profile_steps:
+        for i in range(args.profile_steps):
+            step(i)
+        torch.cuda.synchronize()
+        log("profile steps done (%d launches per step)" % launches_per_step[0])
+        return
     chunk = torch.cuda.CUDAGraph()
     with torch.cuda.graph(chunk):
         for i in range(POOL):
@@ -212,6 +227,8 @@ def run_gpu(args, rank, local_rank, world):
         with torch.cuda.graph(gph):
             step(i)
         singles.append(gph)
+
+    log("graphs captured")
 
     def run_steps(k):
         for _ in range(k // POOL):
@@ -241,6 +258,7 @@ def run_gpu(args, rank, local_rank, world):
     ms = float(tmax.item())
     value = world * args.steps / (ms * 1e-3)
 
+    log("timed region done: %.3f ms/step" % (ms / args.steps))
     # ---- e2e: same step through the public ops API with HOST buffers (pinned), H2D + D2H inside the timed region.
     # Host inputs per step (what the agent holds on the host after env.observe): viewpoint / view indices, the
     # action-candidate embeddings + validity (follower.py:300-320); result read back: a_t + logits (follower.py:510).
@@ -282,6 +300,7 @@ def run_gpu(args, rank, local_rank, world):
     h2d = sum(t.numel() * t.element_size() for t in (h_vp[0], h_view[0], h_U[0], h_valid[0]))
     d2h = h_a.numel() * 4 + h_logit.numel() * 4
 
+    log("e2e done")
     # ---- roofline of the attention-gather kernel, timed alone with CUDA events on its launch stream;
     # every launch reads a different random set of slabs from the 3.1 GB table (inputs >> L2).
     q = torch.randn(B, F, device=dev, generator=g) * 0.05
@@ -304,6 +323,7 @@ def run_gpu(args, rank, local_rank, world):
     step_bytes = algorithmic_bytes(E, F, H, n_params)
     step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
 
+    log("attention kernel timed: %.2f us" % (attn_ms * 1e3))
     if rank == 0:
         cpu_n = 300
         threads = os.cpu_count() or 1
@@ -340,6 +360,8 @@ def main():
     ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--profile-steps", type=int, default=0,
+                    help="run this many eager (no CUDA graph) steps after warm-up and exit: the command ncu wraps")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -38,7 +38,7 @@ struct Carver {
 };
 
 struct FollowerWs {
-  float *tv, *q, *feat, *gpart, *gates_act, *h1d, *t, *wc, *htilde, *tp, *g;
+  float *tv, *q, *feat, *gates_act, *h1d, *t, *wc, *htilde, *tp, *g;
   int splitk;
   size_t bytes;
 };
@@ -56,7 +56,6 @@ static FollowerWs carve_follower(const sfb_dims& d, int B, int L, int A, void* w
   w.tv = c.take((size_t)B * d.D);
   w.q = c.take((size_t)B * kmax);
   w.feat = c.take((size_t)B * d.F);
-  w.gpart = c.take((size_t)w.splitk * B * 4 * d.H);
   w.gates_act = c.take((size_t)B * 4 * d.H);
   w.h1d = c.take((size_t)B * d.H);
   w.t = c.take((size_t)B * d.H);
@@ -69,7 +68,7 @@ static FollowerWs carve_follower(const sfb_dims& d, int B, int L, int A, void* w
 }
 
 struct SpkDecWs {
-  float *gpart, *gates_act, *h1d, *t, *wc, *htilde;
+  float *gates_act, *h1d, *t, *wc, *htilde;
   int splitk;
   size_t bytes;
 };
@@ -78,7 +77,6 @@ static SpkDecWs carve_spkdec(int H, int Ew, int B, void* ws) {
   SpkDecWs w;
   Carver c(ws);
   w.splitk = gemm_pick_splitk(B, 4 * H, Ew + H, device_num_sms());
-  w.gpart = c.take((size_t)w.splitk * B * 4 * H);
   w.gates_act = c.take((size_t)B * 4 * H);
   w.h1d = c.take((size_t)B * H);
   w.t = c.take((size_t)B * H);
@@ -89,7 +87,7 @@ static SpkDecWs carve_spkdec(int H, int Ew, int B, void* ws) {
 }
 
 struct EncWs {
-  float *xproj, *h[2], *c[2], *gpart;
+  float *xproj, *h[2], *c[2];
   int splitk;
   size_t bytes;
 };
@@ -102,7 +100,6 @@ static EncWs carve_encoder(int ndir, int Hd, int Ew, int B, int maxlen, void* ws
   w.xproj = c.take((size_t)ndir * B * maxlen * 4 * Hd);
   for (int i = 0; i < 2; ++i) w.h[i] = c.take((size_t)ndir * B * Hd);
   for (int i = 0; i < 2; ++i) w.c[i] = c.take((size_t)ndir * B * Hd);
-  w.gpart = c.take((size_t)w.splitk * B * 4 * Hd);
   w.bytes = c.off;
   return w;
 }
@@ -130,12 +127,12 @@ static int32_t visual_query(const sfb_dims& d, const sfb_vis_lstm_weights& w, in
   GemmParams g{};
   g.nseg = 1;
   g.seg[0] = GemmSeg{h, d.H, nullptr, nullptr, 0, w.va_w_h, d.H, d.H, 0};
-  g.M = B; g.N = d.D; g.splitk = 1; g.out = tv; g.ldo = d.D; g.bias0 = w.va_b_h;
+  g.M = B; g.N = d.D; g.splitk = gemm_pick_splitk(B, d.D, d.H, device_num_sms()); g.out = tv; g.ldo = d.D; g.bias0 = w.va_b_h;
   SFB_PROPAGATE(launch_gemm(g, st));
   GemmParams g2{};
   g2.nseg = 1;
   g2.seg[0] = GemmSeg{tv, d.D, nullptr, nullptr, 0, w.va_w_v, d.F, d.D, 1};
-  g2.M = B; g2.N = d.F; g2.splitk = 1; g2.out = q; g2.ldo = d.F;
+  g2.M = B; g2.N = d.F; g2.splitk = gemm_pick_splitk(B, d.F, d.D, device_num_sms()); g2.out = q; g2.ldo = d.F;
   return launch_gemm(g2, st);
 }
 
@@ -162,11 +159,11 @@ static int32_t visual_attend(const sfb_dims& d, int B, const float* q, const sfb
   return launch_soft_dot_attention(a, B, st);
 }
 
-// gates partials = [xa | feat] (.* drop_x) W_ih^T + h0 W_hh^T ; then the pointwise cell update.
+// LSTMCell([xa | feat] .* drop_x, (h0, c0)) as ONE GEMM with the cell update fused into its epilogue.
 static int32_t lstm_cell(int Ea, int F, int H, const float* w_ih, const float* w_hh, const float* b_ih,
                          const float* b_hh, int B, const float* xa, const int32_t* xa_rows, const float* feat,
-                         const float* h0, const float* c0, const float* drop_x, const float* drop_h, float* gpart,
-                         int splitk, float* gates_act, float* h1, float* c1, float* h1d, cudaStream_t st) {
+                         const float* h0, const float* c0, const float* drop_x, const float* drop_h,
+                         float* gates_act, float* h1, float* c1, float* h1d, cudaStream_t st) {
   GemmParams g{};
   const int ldw = Ea + F;
   int s = 0;
@@ -174,12 +171,11 @@ static int32_t lstm_cell(int Ea, int F, int H, const float* w_ih, const float* w
   if (F > 0) g.seg[s++] = GemmSeg{feat, F, nullptr, drop_x ? drop_x + Ea : nullptr, drop_x ? ldw : 0, w_ih + Ea, ldw, F, 0};
   g.seg[s++] = GemmSeg{h0, H, nullptr, nullptr, 0, w_hh, H, H, 0};
   g.nseg = s;
-  g.M = B; g.N = 4 * H; g.splitk = splitk; g.out = gpart; g.ldo = 4 * H;
-  SFB_PROPAGATE(launch_gemm(g, st));
-  LstmPointwiseParams p{};
-  p.partial = gpart; p.splitk = splitk; p.b_ih = b_ih; p.b_hh = b_hh; p.c0 = c0; p.drop_h = drop_h;
-  p.h1 = h1; p.c1 = c1; p.h1_drop = h1d; p.gates_act = gates_act; p.B = B; p.H = H;
-  return launch_lstm_pointwise(p, st);
+  g.M = B; g.N = 4 * H;
+  g.splitk = gemm_pick_splitk(B, 4 * H, Ea + F + H, device_num_sms());
+  g.lstm.H = H; g.lstm.b_ih = b_ih; g.lstm.b_hh = b_hh; g.lstm.c0 = c0; g.lstm.drop_h = drop_h;
+  g.lstm.h1 = h1; g.lstm.c1 = c1; g.lstm.h1_drop = h1d; g.lstm.gates_act = gates_act;
+  return launch_gemm(g, st);
 }
 
 // SoftDotAttention on an already (optionally dropped) h: t = W_in h; attention over ctx; h~ = tanh(W_out [wc;h])
@@ -188,7 +184,7 @@ static int32_t soft_dot(int H, const sfb_softdot_weights& w, int B, int L, const
   GemmParams g{};
   g.nseg = 1;
   g.seg[0] = GemmSeg{h, H, nullptr, nullptr, 0, w.w_in, H, H, 0};
-  g.M = B; g.N = H; g.splitk = 1; g.out = t; g.ldo = H;
+  g.M = B; g.N = H; g.splitk = gemm_pick_splitk(B, H, H, device_num_sms()); g.out = t; g.ldo = H;
   SFB_PROPAGATE(launch_gemm(g, st));
   AttnParams a{};
   a.q = t; a.ldq = H; a.R = L; a.D = H;
@@ -200,7 +196,7 @@ static int32_t soft_dot(int H, const sfb_softdot_weights& w, int B, int L, const
   g2.nseg = 2;
   g2.seg[0] = GemmSeg{wc, H, nullptr, nullptr, 0, w.w_out, 2 * H, H, 0};
   g2.seg[1] = GemmSeg{h, H, nullptr, nullptr, 0, w.w_out + H, 2 * H, H, 0};
-  g2.M = B; g2.N = H; g2.splitk = 1; g2.out = h_tilde; g2.ldo = H; g2.act = 1;
+  g2.M = B; g2.N = H; g2.splitk = gemm_pick_splitk(B, H, 2 * H, device_num_sms()); g2.out = h_tilde; g2.ldo = H; g2.act = 1;
   return launch_gemm(g2, st);
 }
 
@@ -301,7 +297,7 @@ int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
   SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, alpha_v, st));
   // model.py:391-394  LSTMCell(drop(cat(u_t_prev, feature)), (h_0, c_0)); h_1_drop = drop(h_1)
   SFB_PROPAGATE(lstm_cell(d.E, d.F, d.H, wl->lstm_w_ih, wl->lstm_w_hh, wl->lstm_b_ih, wl->lstm_b_hh, B, u_prev, nullptr,
-                          ws.feat, h0, c0, drop_x, drop_h, ws.gpart, ws.splitk, ws.gates_act, h1, c1, ws.h1d, st));
+                          ws.feat, h0, c0, drop_x, drop_h, ws.gates_act, h1, c1, ws.h1d, st));
   // model.py:395  h_tilde, alpha = text_attention_layer(h_1_drop, ctx, ctx_mask)
   SFB_PROPAGATE(soft_dot(d.H, *wt, B, L, ws.h1d, ctx, ctx_mask, ws.t, ws.wc, ws.htilde, alpha, st));
   // model.py:396  logit = decoder2action(h_tilde, all_u_t)
@@ -309,12 +305,12 @@ int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
     GemmParams g{};
     g.nseg = 1;
     g.seg[0] = GemmSeg{ws.htilde, d.H, nullptr, nullptr, 0, wsc->w_h, d.H, d.H, 0};
-    g.M = B; g.N = d.D; g.splitk = 1; g.out = ws.tp; g.ldo = d.D; g.bias0 = wsc->b_h;
+    g.M = B; g.N = d.D; g.splitk = gemm_pick_splitk(B, d.D, d.H, device_num_sms()); g.out = ws.tp; g.ldo = d.D; g.bias0 = wsc->b_h;
     SFB_PROPAGATE(launch_gemm(g, st));
     GemmParams g2{};
     g2.nseg = 1;
     g2.seg[0] = GemmSeg{ws.tp, d.D, nullptr, wsc->w_out, 0, wsc->w_a, d.E, d.D, 1};
-    g2.M = B; g2.N = d.E; g2.splitk = 1; g2.out = ws.g; g2.ldo = d.E;
+    g2.M = B; g2.N = d.E; g2.splitk = gemm_pick_splitk(B, d.E, d.D, device_num_sms()); g2.out = ws.g; g2.ldo = d.E;
     SFB_PROPAGATE(launch_gemm(g2, st));
     ScoringParams sp{all_u_t, ws.g, ws.tp, wsc->b_a, wsc->w_out, wsc->b_out, logit, B, A, d.E, d.D};
     SFB_PROPAGATE(launch_action_scoring(sp, st));
@@ -375,15 +371,14 @@ int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t
       GemmParams r{};
       r.nseg = 1;
       r.seg[0] = GemmSeg{hp, Hd, nullptr, nullptr, 0, w->w_hh[dir], Hd, Hd, 0};
-      r.M = B; r.N = 4 * Hd; r.splitk = ws.splitk; r.out = ws.gpart; r.ldo = 4 * Hd;
-      SFB_PROPAGATE(launch_gemm(r, st));
-      LstmPointwiseParams p{};
-      p.partial = ws.gpart; p.splitk = ws.splitk; p.b_ih = w->b_ih[dir]; p.b_hh = w->b_hh[dir];
-      p.c0 = cp; p.h0 = hp; p.h1 = hn; p.c1 = cn; p.B = B; p.H = Hd;
+      r.M = B; r.N = 4 * Hd; r.splitk = ws.splitk;
+      LstmEpilogue& p = r.lstm;
+      p.H = Hd; p.b_ih = w->b_ih[dir]; p.b_hh = w->b_hh[dir];
+      p.c0 = cp; p.h0 = hp; p.h1 = hn; p.c1 = cn;
       p.addend = xp + (size_t)t * 4 * Hd; p.ld_addend = (long long)maxlen * 4 * Hd;
       p.lengths = lengths; p.t = t;
       p.seq_out = ctx + (size_t)t * H + dir * Hd; p.ld_seq_out = (long long)maxlen * H;
-      SFB_PROPAGATE(launch_lstm_pointwise(p, st));
+      SFB_PROPAGATE(launch_gemm(r, st));
       cur[dir] ^= 1;
     }
   }
@@ -397,7 +392,7 @@ int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t
     e.seg[0] = GemmSeg{ws.h[cur[1]] + state, Hd, nullptr, nullptr, 0, w->e2d_w, H, Hd, 0};
     e.seg[1] = GemmSeg{ws.h[cur[0]], Hd, nullptr, nullptr, 0, w->e2d_w + Hd, H, Hd, 0};
   }
-  e.M = B; e.N = H; e.splitk = 1; e.out = decoder_init; e.ldo = H; e.bias0 = w->e2d_b; e.act = 1;
+  e.M = B; e.N = H; e.splitk = gemm_pick_splitk(B, H, H, device_num_sms()); e.out = decoder_init; e.ldo = H; e.bias0 = w->e2d_b; e.act = 1;
   SFB_PROPAGATE(launch_gemm(e, st));
   if (ndir == 1) {
     SFB_CHECK_CUDA(cudaMemcpyAsync(c_t, ws.c[cur[0]], state * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -425,7 +420,7 @@ int32_t sfb_speaker_encoder_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
   SFB_PROPAGATE(visual_query(d, *w, B, h0, ws.tv, ws.q, st));
   SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, nullptr, st));
   return lstm_cell(d.E, d.F, d.H, w->lstm_w_ih, w->lstm_w_hh, w->lstm_b_ih, w->lstm_b_hh, B, action_embedding, nullptr,
-                   ws.feat, h0, c0, drop_x, nullptr, ws.gpart, ws.splitk, ws.gates_act, h1, c1, nullptr, st);
+                   ws.feat, h0, c0, drop_x, nullptr, ws.gates_act, h1, c1, nullptr, st);
 }
 
 int32_t sfb_speaker_decoder_step_fwd(const sfb_speaker_decoder_weights* w, int32_t H, int32_t Ew, int32_t vocab,
@@ -441,14 +436,14 @@ int32_t sfb_speaker_decoder_step_fwd(const sfb_speaker_decoder_weights* w, int32
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // model.py:497-503,515: LSTMCell(embedding(previous_word)) — the lookup is a row indirection of the A operand
   SFB_PROPAGATE(lstm_cell(Ew, 0, H, w->lstm_w_ih, w->lstm_w_hh, w->lstm_b_ih, w->lstm_b_hh, B, w->embedding, prev_word,
-                          nullptr, h0, c0, drop_e, drop_h, ws.gpart, ws.splitk, ws.gates_act, h1, c1, ws.h1d, st));
+                          nullptr, h0, c0, drop_e, drop_h, ws.gates_act, h1, c1, ws.h1d, st));
   // model.py:516-517
   SFB_PROPAGATE(soft_dot(H, w->attn, B, T, ws.h1d, ctx, ctx_mask, ws.t, ws.wc, ws.htilde, alpha, st));
   // model.py:518  logit = decoder2action(h_tilde)
   GemmParams g{};
   g.nseg = 1;
   g.seg[0] = GemmSeg{ws.htilde, H, nullptr, nullptr, 0, w->w_voc, H, H, 0};
-  g.M = B; g.N = vocab; g.splitk = 1; g.out = logit; g.ldo = vocab; g.bias0 = w->b_voc;
+  g.M = B; g.N = vocab; g.splitk = gemm_pick_splitk(B, vocab, H, device_num_sms()); g.out = logit; g.ldo = vocab; g.bias0 = w->b_voc;
   return launch_gemm(g, st);
 }
 

@@ -1,37 +1,83 @@
-// gemm_simt.cu — exact-fp32 "skinny" GEMM on the FFMA pipe:  out[M,N] = sum_s X_s[M,k_s] · W_s^T  (+bias, act)
+// gemm_simt.cu — exact-fp32 "skinny" GEMM on the FFMA pipe:  out[M,N] = sum_s X_s[M,k_s] · W_s^T  (+epilogue)
 //
 // M is the batch (<= a few hundred rows), the weights are streamed once.  K may be the concatenation of
 // up to three segments with their own activation/weight pointers, which is how cat(u_prev, feature)
 // (model.py:391) and the two addmm's of nn.LSTMCell (model.py:393) run as ONE pass without materialising
 // the concatenation.  Dropout keep-masks (model.py:392,394) are applied while the A tile is loaded, an
-// embedding lookup (model.py:497) is an optional row indirection.  Split-K writes raw partial sums that
-// the consumer kernel reduces in a fixed order (deterministic, no atomics).
+// embedding lookup (model.py:497) is an optional row indirection.
 //
-// This is the general, always-available path (any M, N, K % 4 == 0).  The large LSTM-gate GEMM has a
-// tensor-core (tcgen05) implementation in gemm_tc.cu that is used when its shape constraints hold.
+// B200 mapping: these GEMMs are tiny (<= 2.2 MB of weights) and sit on the step's dependency chain, so the
+// goal is latency: a 128x32 output tile is split along K over the CTAs of a thread-block CLUSTER (up to 8),
+// each CTA does a few 32-wide K chunks, and the partial tiles are reduced through distributed shared
+// memory in a fixed order (deterministic, no atomics, no second kernel).  The epilogue is either
+// bias + activation or — with gate-interleaved tiles — the whole LSTM cell update, so h1/c1 leave the
+// GEMM directly.
 #include "kernels.h"
 
 namespace sfb {
 
 namespace {
-constexpr int BN = 32, BK = 32, SA = 36, SB = 36;
+constexpr int BN = 32, BK = 32, SA = 36, SB = 36, SR = 33;
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// LSTM cell update for one (row, hidden unit); `g` are the four pre-activation gate sums WITHOUT biases.
+__device__ __forceinline__ void lstm_update(const GemmParams& p, int m, int unit, float gi, float gf, float gg,
+                                            float go) {
+  const LstmEpilogue& e = p.lstm;
+  const int H = e.H;
+  const size_t idx = (size_t)m * H + unit;
+  if (e.lengths && e.t >= e.lengths[m]) {   // packed sequence: this row has ended, carry the state
+    e.c1[idx] = e.c0[idx];
+    e.h1[idx] = e.h0[idx];
+    if (e.seq_out) e.seq_out[(size_t)m * e.ld_seq_out + unit] = 0.f;
+    return;
+  }
+  gi += __ldg(e.b_ih + unit) + __ldg(e.b_hh + unit);
+  gf += __ldg(e.b_ih + H + unit) + __ldg(e.b_hh + H + unit);
+  gg += __ldg(e.b_ih + 2 * H + unit) + __ldg(e.b_hh + 2 * H + unit);
+  go += __ldg(e.b_ih + 3 * H + unit) + __ldg(e.b_hh + 3 * H + unit);
+  if (e.addend) {
+    const float* a = e.addend + (size_t)m * e.ld_addend + unit;
+    gi += a[0]; gf += a[H]; gg += a[2 * H]; go += a[3 * H];
+  }
+  const float ig = sigmoidf_acc(gi), fg = sigmoidf_acc(gf), gt = tanhf(gg), og = sigmoidf_acc(go);
+  const float c1 = fg * e.c0[idx] + ig * gt;
+  const float h1 = og * tanhf(c1);
+  e.c1[idx] = c1;
+  e.h1[idx] = h1;
+  if (e.h1_drop) e.h1_drop[idx] = e.drop_h ? h1 * e.drop_h[idx] : h1;
+  if (e.seq_out) e.seq_out[(size_t)m * e.ld_seq_out + unit] = h1;
+  if (e.gates_act) {
+    float* ga = e.gates_act + (size_t)m * 4 * H + unit;
+    ga[0] = ig; ga[H] = fg; ga[2 * H] = gt; ga[3 * H] = og;
+  }
+}
+
+__device__ __forceinline__ void plain_store(const GemmParams& p, int m, int n, float v) {
+  if (p.bias0) v += __ldg(p.bias0 + n);
+  if (p.bias1) v += __ldg(p.bias1 + n);
+  if (p.act == 1) v = tanhf(v);
+  p.out[(size_t)m * p.ldo + n] = v;
+}
 }  // namespace
 
+// grid = (N tiles, splitk, M tiles); cluster = (1, splitk, 1)
 template <int TM, bool KN>
 __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
   constexpr int BM = 32 * TM;
-  __shared__ __align__(16) float As[BM * SA];
+  __shared__ __align__(16) float As[BM * SA];   // re-used as the [BM][SR] partial tile for the cluster reduction
   __shared__ __align__(16) float Bs[32 * SB];
 
   const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
   const int m0 = blockIdx.z * BM, n0 = blockIdx.x * BN;
+  const int S = p.splitk, rank = blockIdx.y;
+  const bool lstm = p.lstm.H > 0;
 
   int nch = 0;
   for (int s = 0; s < p.nseg; ++s) nch += (p.seg[s].k + BK - 1) / BK;
-  const int per = (nch + p.splitk - 1) / p.splitk;
-  const int c_begin = blockIdx.y * per, c_end = min(nch, c_begin + per);
+  const int per = (nch + S - 1) / S;
+  const int c_begin = rank * per, c_end = min(nch, c_begin + per);
 
   float acc[TM][4];
 #pragma unroll
@@ -40,6 +86,9 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   float4 pa[TM], pb;
+  // weight row of local tile column `ty` (gate-interleaved for the LSTM epilogue: col = gate*8 + unit)
+  const int wrow = lstm ? (ty >> 3) * p.lstm.H + blockIdx.x * 8 + (ty & 7) : n0 + ty;
+  const bool wrow_ok = lstm ? (blockIdx.x * 8 + (ty & 7)) < p.lstm.H : wrow < p.N;
 
   auto load_chunk = [&](int c) {
     int s = 0, cc = c;
@@ -70,8 +119,8 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
     }
     pb = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!KN) {
-      const int n = n0 + ty, kk = kofs + tx * 4;
-      if (n < p.N && kk < g.k) pb = ldg4(g.w + (size_t)n * g.ldw + kk);
+      const int kk = kofs + tx * 4;
+      if (wrow_ok && kk < g.k) pb = ldg4(g.w + (size_t)wrow * g.ldw + kk);
     } else {
       const int kk = kofs + ty, nn = n0 + tx * 4;
       if (kk < g.k && nn < p.N) pb = ldg4(g.w + (size_t)kk * g.ldw + nn);
@@ -120,46 +169,106 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
     __syncthreads();
   }
 
-  // epilogue
+  // local tile column of accumulator j of this thread
+  auto col_of = [&](int j) { return KN ? tx * 4 + j : tx + 8 * j; };
+
+  if (S == 1) {
 #pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    const int m = m0 + ty + 32 * i;
-    if (m >= p.M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = KN ? n0 + tx * 4 + j : n0 + tx + 8 * j;
-      if (n >= p.N) continue;
-      float v = acc[i][j];
-      if (p.splitk > 1) {
-        p.out[((size_t)blockIdx.y * p.M + m) * p.N + n] = v;
+    for (int i = 0; i < TM; ++i) {
+      const int m = m0 + ty + 32 * i;
+      if (m >= p.M) continue;
+      if (lstm) {
+        const int unit = blockIdx.x * 8 + tx;   // NT layout: accumulator j is gate j of unit tx
+        if (unit < p.lstm.H) lstm_update(p, m, unit, acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       } else {
-        if (p.bias0) v += __ldg(p.bias0 + n);
-        if (p.bias1) v += __ldg(p.bias1 + n);
-        if (p.act == 1) v = tanhf(v);
-        p.out[(size_t)m * p.ldo + n] = v;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + col_of(j);
+          if (n < p.N) plain_store(p, m, n, acc[i][j]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- split-K: partial tile -> shared memory, reduce across the cluster through DSMEM in rank order
+  float* red = As;   // [BM][SR]
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[(ty + 32 * i) * SR + col_of(j)] = acc[i][j];
+  cluster_sync_all();
+  {
+    const int rows_per = (BM + S - 1) / S;
+    const int rbeg = rank * rows_per, rend = min(BM, rbeg + rows_per);
+    uint32_t peer[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) peer[k] = k < S ? dsmem_addr(red, k) : 0u;
+    if (lstm) {
+      // one thread per (row, unit): the 4 gate columns unit, 8+unit, 16+unit, 24+unit
+      for (int e = tid; e < (rend - rbeg) * 8; e += 256) {
+        const int r = rbeg + (e >> 3), unit_l = e & 7;
+        const int m = m0 + r, unit = blockIdx.x * 8 + unit_l;
+        if (m >= p.M || unit >= p.lstm.H) continue;
+        float g4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < S; ++k)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) g4[q] += dsmem_ld_f32(peer[k] + (uint32_t)(r * SR + q * 8 + unit_l) * 4u);
+        lstm_update(p, m, unit, g4[0], g4[1], g4[2], g4[3]);
+      }
+    } else {
+      for (int e = tid; e < (rend - rbeg) * BN; e += 256) {
+        const int r = rbeg + (e >> 5), cn = e & 31;
+        const int m = m0 + r, n = n0 + cn;
+        if (m >= p.M || n >= p.N) continue;
+        float v = 0.f;
+        for (int k = 0; k < S; ++k) v += dsmem_ld_f32(peer[k] + (uint32_t)(r * SR + cn) * 4u);
+        plain_store(p, m, n, v);
       }
     }
   }
+  cluster_sync_all();   // peers may still be reading this CTA's partial tile
 }
 
 int gemm_pick_splitk(int M, int N, int ktotal, int num_sms) {
   const int bm = M <= 32 ? 32 : 128;
   const int tiles = ((N + BN - 1) / BN) * ((M + bm - 1) / bm);
   const int nch = (ktotal + BK - 1) / BK;
-  int s = (3 * num_sms + tiles / 2) / tiles;
-  if (s > nch / 4) s = nch / 4;
-  if (s > 16) s = 16;
-  if (s < 1) s = 1;
+  int want = (2 * num_sms + tiles - 1) / tiles;   // aim at ~2 CTAs per SM
+  int s = 1;
+  while (s * 2 <= want && s * 2 <= 8 && nch / (s * 2) >= 2) s *= 2;
   return s;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+template <int TM, bool KN>
+static int32_t launch_t(const GemmParams& p, dim3 grid, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = p.splitk;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<TM, KN>, p));
+  count_launch();
+  return 0;
+}
+
 int32_t launch_gemm(const GemmParams& p, cudaStream_t stream) {
   SFB_CHECK_ARG(p.nseg >= 1 && p.nseg <= 3, "gemm: 1..3 K segments");
-  SFB_CHECK_ARG(p.M >= 1 && p.N >= 1 && p.splitk >= 1, "gemm: bad sizes");
-  SFB_CHECK_ARG(p.splitk == 1 || (!p.bias0 && !p.bias1 && p.act == 0), "gemm: no epilogue with split-K");
+  SFB_CHECK_ARG(p.M >= 1 && p.N >= 1, "gemm: bad sizes");
+  SFB_CHECK_ARG(p.splitk == 1 || p.splitk == 2 || p.splitk == 4 || p.splitk == 8, "gemm: splitk must be 1, 2, 4 or 8");
   const int kn = p.seg[0].w_kn;
+  const bool lstm = p.lstm.H > 0;
+  SFB_CHECK_ARG(!lstm || (!kn && p.N == 4 * p.lstm.H && (p.lstm.H % 8) == 0), "gemm: LSTM epilogue needs [4H,K] weights, H % 8 == 0");
+  SFB_CHECK_ARG(lstm || p.out, "gemm: output is NULL");
   for (int s = 0; s < p.nseg; ++s) {
     const GemmSeg& g = p.seg[s];
     SFB_CHECK_ARG(g.w_kn == kn, "gemm: mixed weight layouts");
@@ -171,15 +280,8 @@ int32_t launch_gemm(const GemmParams& p, cudaStream_t stream) {
   }
   const int tm = p.M <= 32 ? 1 : 4;
   dim3 grid((p.N + BN - 1) / BN, p.splitk, (p.M + 32 * tm - 1) / (32 * tm));
-  if (tm == 1) {
-    if (kn) gemm_skinny_kernel<1, true><<<grid, 256, 0, stream>>>(p);
-    else    gemm_skinny_kernel<1, false><<<grid, 256, 0, stream>>>(p);
-  } else {
-    if (kn) gemm_skinny_kernel<4, true><<<grid, 256, 0, stream>>>(p);
-    else    gemm_skinny_kernel<4, false><<<grid, 256, 0, stream>>>(p);
-  }
-  SFB_CHECK_LAUNCH();
-  return 0;
+  if (tm == 1) return kn ? launch_t<1, true>(p, grid, stream) : launch_t<1, false>(p, grid, stream);
+  return kn ? launch_t<4, true>(p, grid, stream) : launch_t<4, false>(p, grid, stream);
 }
 
 }  // namespace sfb

@@ -31,37 +31,36 @@ struct GemmSeg {
   int k;
   int w_kn;
 };
+// Fused LSTM cell epilogue (nn.LSTMCell pointwise part, model.py:393): active when H > 0.  The GEMM then
+// computes the gate pre-activations W_ih x + W_hh h with gate-interleaved 32-column tiles (4 gates x 8 units).
+struct LstmEpilogue {
+  int H;                                  // 0 = plain epilogue
+  const float* b_ih; const float* b_hh;   // [4H]
+  const float* c0;                        // [M,H]
+  const float* drop_h;                    // [M,H] scaled keep mask or NULL
+  float* h1; float* c1;                   // [M,H]
+  float* h1_drop;                         // [M,H] h1 .* drop_h (== h1 when drop_h is NULL); may be NULL
+  float* gates_act;                       // [M,4H] activated gates (i,f,g,o) kept for backward; may be NULL
+  // sequence mode (EncoderLSTM, model.py:89-90): precomputed input projection + packed-sequence masking
+  const float* addend; long long ld_addend;   // [M,4H] rows at stride ld_addend (x_t W_ih^T), or NULL
+  const float* h0;                            // previous hidden state, carried through when t >= lengths[m]
+  const int32_t* lengths; int t;              // rows with t >= lengths[m] keep (h0, c0) and emit zeros
+  float* seq_out; long long ld_seq_out;       // h1 (or 0 when inactive) written at seq_out[m*ld_seq_out + j]
+};
 struct GemmParams {
   GemmSeg seg[3];
   int nseg;
   int M, N;
-  int splitk;                             // >1: raw partial sums go to out[splitk][M][N] (ldo ignored)
-  float* out; int ldo;
-  const float* bias0; const float* bias1; // [N] or NULL (splitk == 1 only)
-  int act;                                // 0 none, 1 tanh (splitk == 1 only)
+  int splitk;                             // 1, 2, 4 or 8: K split over the CTAs of a cluster, reduced through DSMEM
+  float* out; int ldo;                    // plain epilogue: out = act(acc + bias0 + bias1)
+  const float* bias0; const float* bias1; // [N] or NULL
+  int act;                                // 0 none, 1 tanh
+  LstmEpilogue lstm;
 };
 int32_t launch_gemm(const GemmParams& p, cudaStream_t stream);
 int gemm_pick_splitk(int M, int N, int ktotal, int num_sms);
 
 // ---------------------------------------------------------------- pointwise.cu
-// gates = sum_s partial[s] + b_ih + b_hh ; LSTM cell update (torch.nn.LSTMCell gate order i,f,g,o).
-struct LstmPointwiseParams {
-  const float* partial; int splitk;       // [splitk][B][4H]
-  const float* b_ih; const float* b_hh;   // [4H]
-  const float* c0;                        // [B,H]
-  const float* drop_h;                    // [B,H] scaled keep mask or NULL
-  float* h1; float* c1;                   // [B,H]
-  float* h1_drop;                         // [B,H] h1 .* drop_h (== h1 when drop_h is NULL); may be NULL
-  float* gates_act;                       // [B,4H] activated gates (i,f,g,o) kept for backward; may be NULL
-  int B, H;
-  // sequence mode (EncoderLSTM, model.py:89-90): precomputed input projection + packed-sequence masking
-  const float* addend; long long ld_addend;   // [B,4H] rows at stride ld_addend (x_t W_ih^T), or NULL
-  const float* h0;                            // previous hidden state, carried through when t >= lengths[b]
-  const int32_t* lengths; int t;              // rows with t >= lengths[b] keep (h0, c0) and emit zeros
-  float* seq_out; long long ld_seq_out;       // h1 (or 0 when inactive) written at seq_out[b*ld_seq_out + j]
-};
-int32_t launch_lstm_pointwise(const LstmPointwiseParams& p, cudaStream_t stream);
-
 // logit[b,a] = all_u_t[b,a,:] . g[b,:] + sum_d b_a[d] w_out[d] tp[b,d] + b_out   (EltwiseProdScoring rewritten)
 struct ScoringParams {
   const float* all_u_t;                   // [B,A,E]

@@ -1,50 +1,8 @@
-// pointwise.cu — the small fused kernels around the GEMMs: LSTM cell update (nn.LSTMCell pointwise part,
-// model.py:393), action scoring (EltwiseProdScoring, model.py:342-352, in its re-associated form) and
+// pointwise.cu — the small fused kernels around the GEMMs: action scoring (EltwiseProdScoring, model.py:342-352, in its re-associated form) and
 // the per-step tail of the follower rollout (follower.py:476-505).
 #include "kernels.h"
 
 namespace sfb {
-
-// ---------------------------------------------------------------- LSTM cell
-__global__ void __launch_bounds__(256) lstm_pointwise_kernel(const LstmPointwiseParams p) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int H = p.H;
-  if (idx >= p.B * H) return;
-  const int b = idx / H, j = idx - b * H;
-  if (p.lengths && p.t >= p.lengths[b]) {   // packed sequence: this row has ended, carry the state
-    p.c1[idx] = p.c0[idx];
-    p.h1[idx] = p.h0[idx];
-    if (p.seq_out) p.seq_out[(size_t)b * p.ld_seq_out + j] = 0.f;
-    return;
-  }
-  float g4[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int col = q * H + j;
-    float v = __ldg(p.b_ih + col) + __ldg(p.b_hh + col);
-    if (p.addend) v += p.addend[(size_t)b * p.ld_addend + col];
-    for (int s = 0; s < p.splitk; ++s) v += p.partial[((size_t)s * p.B + b) * 4 * H + col];
-    g4[q] = v;
-  }
-  const float ig = sigmoidf_acc(g4[0]), fg = sigmoidf_acc(g4[1]), gg = tanhf(g4[2]), og = sigmoidf_acc(g4[3]);
-  const float c1 = fg * p.c0[idx] + ig * gg;
-  const float h1 = og * tanhf(c1);
-  p.c1[idx] = c1;
-  p.h1[idx] = h1;
-  if (p.h1_drop) p.h1_drop[idx] = p.drop_h ? h1 * p.drop_h[idx] : h1;
-  if (p.seq_out) p.seq_out[(size_t)b * p.ld_seq_out + j] = h1;
-  if (p.gates_act) {
-    float* ga = p.gates_act + (size_t)b * 4 * H + j;
-    ga[0] = ig; ga[H] = fg; ga[2 * H] = gg; ga[3 * H] = og;
-  }
-}
-
-int32_t launch_lstm_pointwise(const LstmPointwiseParams& p, cudaStream_t stream) {
-  const int n = p.B * p.H;
-  lstm_pointwise_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p);
-  SFB_CHECK_LAUNCH();
-  return 0;
-}
 
 // ---------------------------------------------------------------- action scoring
 // w_out . ((W_h ht + b_h) (.) (W_a u + b_a)) + b_out  ==  u . g + c   with  t' = W_h ht + b_h,
