@@ -90,6 +90,11 @@ typedef struct sfb_visual_source {
 int32_t     sfb_abi_version(void);
 const char* sfb_last_error(void);
 
+/* Runtime options (testing / bring-up hooks; process-wide, not thread-safe against concurrent launches):
+ *   "disable_tc" = 1 : run the LSTM-gate GEMM on the exact-fp32 FFMA path instead of tcgen05 (bf16x3);
+ *   "tc_debug"       : descriptor-encoding variants of the tensor-core path (bring-up only). */
+int32_t sfb_set_option(const char* name, int32_t value);
+
 /* Device properties the library was built for / sees.  Fills sm (e.g. 100), number of SMs and max
  * opt-in shared memory per block; returns SFB_ERR_NO_DEVICE when there is no usable device. */
 int32_t sfb_device_info(int32_t* sm, int32_t* num_sms, int32_t* smem_per_block);

@@ -6,6 +6,7 @@
 
 namespace sfb {
 
+int g_disable_tc = 0;
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
 
@@ -175,7 +176,8 @@ static int32_t lstm_cell(int Ea, int F, int H, const float* w_ih, const float* w
   g.splitk = gemm_pick_splitk(B, 4 * H, Ea + F + H, device_num_sms());
   g.lstm.H = H; g.lstm.b_ih = b_ih; g.lstm.b_hh = b_hh; g.lstm.c0 = c0; g.lstm.drop_h = drop_h;
   g.lstm.h1 = h1; g.lstm.c1 = c1; g.lstm.h1_drop = h1d; g.lstm.gates_act = gates_act;
-  return launch_gemm(g, st);
+  if (!g_disable_tc && gemm_tc_supported(g)) return launch_gemm_tc(g, st);   // tcgen05 path (bf16x3, fp32 accumulate)
+  return launch_gemm(g, st);                                                 // exact-fp32 FFMA path (any shape)
 }
 
 // SoftDotAttention on an already (optionally dropped) h: t = W_in h; attention over ctx; h~ = tanh(W_out [wc;h])
@@ -209,6 +211,14 @@ extern "C" {
 int32_t sfb_abi_version(void) { return SFB_ABI_VERSION; }
 const char* sfb_last_error(void) { return g_err.c_str(); }
 int32_t sfb_last_launch_count(void) { return g_launches; }
+
+int32_t sfb_set_option(const char* name, int32_t value) {
+  const std::string n(name ? name : "");
+  if (n == "disable_tc") { g_disable_tc = value; return 0; }
+  if (n == "tc_debug") { gemm_tc_set_debug(value); return 0; }
+  set_error("unknown option: " + n);
+  return SFB_ERR_INVALID_ARG;
+}
 
 int32_t sfb_device_info(int32_t* sm, int32_t* num_sms, int32_t* smem_per_block) {
   int dev = 0;

@@ -60,6 +60,12 @@ struct GemmParams {
 int32_t launch_gemm(const GemmParams& p, cudaStream_t stream);
 int gemm_pick_splitk(int M, int N, int ktotal, int num_sms);
 
+// ---------------------------------------------------------------- gemm_tc.cu (tcgen05 / TMEM, LSTM epilogue only)
+bool gemm_tc_supported(const GemmParams& p);
+int32_t launch_gemm_tc(const GemmParams& p, cudaStream_t stream);
+void gemm_tc_set_debug(int flags);
+extern int g_disable_tc;
+
 // ---------------------------------------------------------------- pointwise.cu
 // logit[b,a] = all_u_t[b,a,:] . g[b,:] + sum_d b_a[d] w_out[d] tp[b,d] + b_out   (EltwiseProdScoring rewritten)
 struct ScoringParams {

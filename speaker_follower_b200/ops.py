@@ -304,5 +304,10 @@ def speaker_decoder_step(w: Dict[str, Tensor], prev_word: Tensor, h0: Tensor, c0
     return h1, c1, alpha, logit
 
 
+def set_option(name: str, value: int) -> None:
+    """Testing hook: 'disable_tc' (1 = exact-fp32 FFMA gates GEMM), 'tc_debug'."""
+    check(_lib.load().sfb_set_option(name.encode(), int(value)))
+
+
 def last_launch_count() -> int:
     return int(_lib.load().sfb_last_launch_count())

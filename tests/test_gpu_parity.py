@@ -246,3 +246,50 @@ def test_errors_are_loud():
     with pytest.raises(SfbError):   # non-contiguous
         ops.follower_step(w, x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"].t().contiguous().t(),
                           x["c_0"], x["ctx"], x["ctx_mask"])
+
+
+@pytest.mark.parametrize("B", [1, 8, 100, 128, 130, 256])
+def test_tensor_core_gates_vs_exact_fp32(B):
+    """The tcgen05 (bf16x3) LSTM-gate GEMM against the exact-fp32 FFMA path of the same library and the oracle."""
+    w = synth.follower_decoder_weights()
+    x = synth.follower_step_inputs(B, 24, 6, seed=500 + B)
+    try:
+        ops.set_option("disable_tc", 1)
+        exact = run_step(w, x)
+        ops.set_option("disable_tc", 0)
+        tc = run_step(w, x)
+    finally:
+        ops.set_option("disable_tc", 0)
+    for k, a, b in zip(NAMES, tc, exact):
+        close(a, b.cpu(), 5e-5, "tc-vs-ffma:" + k)
+    ref = O.attn_decoder_step(x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
+                              x["ctx_mask"], w)
+    for k, a, r in zip(NAMES, tc, ref):
+        close(a, r, what="oracle:" + k)
+
+
+def test_follower_rollout_10_steps_drift():
+    """Error does not compound past the 1e-4 contract over a full-length episode (10 decode steps, B=100)."""
+    B, L, A, S = 100, 80, 8, 10
+    we, wd = synth.follower_encoder_weights(), synth.follower_decoder_weights()
+    seq, mask, lengths = synth.instruction_batch(B, L, seed=47)
+    steps = []
+    for s in range(S):
+        x = synth.follower_step_inputs(B, L, A, seed=600 + s)
+        steps.append({"visual": x["visual_context"], "all_u_t": x["all_u_t"], "is_valid": x["is_valid"]})
+    ref, _, ref_score = O.follower_rollout(seq, mask, lengths, steps, we, wd, feedback="argmax")
+    wec, wdc = cu(we), cu(wd)
+    ctx, h, c = ops.encoder_lstm(wec, seq.cuda(), lengths)
+    u_prev = torch.zeros(B, synth.FEAT, device="cuda")
+    total = torch.zeros(B, device="cuda")
+    worst = 0.0
+    for s in range(S):
+        st = cu(steps[s])
+        h, c, alpha, logit, alpha_v = ops.follower_step(wdc, u_prev, st["all_u_t"], st["visual"], h, c, ctx, mask.cuda())
+        a_t, u_prev, score, _ = ops.follower_tail(logit, st["is_valid"], st["all_u_t"], "argmax")
+        worst = max(worst, close(logit, ref[s]["logit"], what="logit step %d" % s))
+        assert torch.equal(a_t.cpu().long(), ref[s]["a_t"]), "argmax differs at step %d" % s
+        total += score
+    close(h, ref[-1]["h"], what="h"); close(c, ref[-1]["c"], what="c")
+    close(total, ref_score, 5e-4, "sequence score")
+    print("worst |dlogit| over 10 steps: %.2e" % worst)
