@@ -150,6 +150,11 @@ def run_gpu(args, rank, local_rank, world):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    for kv in filter(None, os.environ.get("SFB_OPTIONS", "").split(",")):   # e.g. SFB_OPTIONS=disable_pdl=1 (A/B runs)
+        k, v = kv.split("=")
+        ops.set_option(k, int(v))
+        log("option %s=%s" % (k, v))
+
     E = F = synth.FEAT
     H = synth.HID
     w_cpu = synth.follower_decoder_weights()
@@ -251,12 +256,8 @@ def run_gpu(args, rank, local_rank, world):
     e1.record()
     barrier()
     clocks = sampler.result()
-    ms = e0.elapsed_time(e1)
-    tmax = torch.tensor([ms], device=dev)
-    if dist is not None:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms = float(tmax.item())
-    value = world * args.steps / (ms * 1e-3)
+    from speaker_follower_b200 import dist as sfdist
+    value, ms = sfdist.aggregate_rate(args.steps, e0.elapsed_time(e1), device=dev)   # whole job / slowest rank
 
     log("timed region done: %.3f ms/step" % (ms / args.steps))
     # ---- e2e: same step through the public ops API with HOST buffers (pinned), H2D + D2H inside the timed region.

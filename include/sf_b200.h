@@ -94,6 +94,8 @@ const char* sfb_last_error(void);
  *   "disable_tc" = 1 : run the LSTM-gate GEMM on the exact-fp32 FFMA path instead of tcgen05 (bf16x3);
  *   "tc_debug"       : descriptor-encoding variants of the tensor-core path (bring-up only). */
 int32_t sfb_set_option(const char* name, int32_t value);
+/* Bring-up: phase timestamps (SM clock) of the tensor-core GEMM's CTA 0, valid after a call with tc_debug bit 2. */
+int32_t sfb_debug_read_timestamps(int64_t* out, int32_t n);
 
 /* Device properties the library was built for / sees.  Fills sm (e.g. 100), number of SMs and max
  * opt-in shared memory per block; returns SFB_ERR_NO_DEVICE when there is no usable device. */

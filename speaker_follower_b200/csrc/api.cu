@@ -7,6 +7,7 @@
 namespace sfb {
 
 int g_disable_tc = 0;
+int g_disable_pdl = 0;
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
 
@@ -215,9 +216,14 @@ int32_t sfb_last_launch_count(void) { return g_launches; }
 int32_t sfb_set_option(const char* name, int32_t value) {
   const std::string n(name ? name : "");
   if (n == "disable_tc") { g_disable_tc = value; return 0; }
+  if (n == "disable_pdl") { g_disable_pdl = value; return 0; }
   if (n == "tc_debug") { gemm_tc_set_debug(value); return 0; }
   set_error("unknown option: " + n);
   return SFB_ERR_INVALID_ARG;
+}
+
+int32_t sfb_debug_read_timestamps(int64_t* out, int32_t n) {
+  return gemm_tc_read_timestamps(reinterpret_cast<long long*>(out), n);
 }
 
 int32_t sfb_device_info(int32_t* sm, int32_t* num_sms, int32_t* smem_per_block) {

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) soft_dot_attn_kernel(const AttnParams p) 
 
   const uint8_t* mrow = p.mask ? p.mask + (size_t)b * p.ldmask : nullptr;
 
+  pdl_launch_dependents();   // let the next kernel of the step start its own prologue / prefetch
   // ---- 1. warp 0 arms one mbarrier per row and launches every bulk copy of this CTA at once
   if (warp == 0) {
     for (int r = lane; r < nrows; r += 32) mbar_init(&bars[r], 1);
@@ -53,14 +54,16 @@ __global__ void __launch_bounds__(256) soft_dot_attn_kernel(const AttnParams p) 
                       &bars[r], pol);
     }
   }
-  // ---- 2. query slice of this lane to registers (lane-strided float4)
+  // ---- 2. query slice of this lane to registers (lane-strided float4).  The rows above are step inputs and
+  // were requested before this point; q is produced by the preceding kernel, so wait for it only now.
+  pdl_wait();
   float4 qv[NQ];
   {
     const float4* q4 = reinterpret_cast<const float4*>(p.q + (size_t)b * p.ldq);
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
       const int idx = lane + 32 * j;
-      qv[j] = idx < nvec ? __ldg(q4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      qv[j] = idx < nvec ? q4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   __syncthreads();  // barriers are initialised before anyone waits on them
@@ -209,19 +212,7 @@ static int32_t launch_attn_t(const AttnParams& p, int B, cudaStream_t stream) {
     SFB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(CL, B, 1);
-  cfg.blockDim = dim3(256, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  SFB_CHECK_CUDA(launch_ex(kern, dim3(CL, B, 1), dim3(256, 1, 1), smem, stream, dim3(CL, 1, 1), p));
   count_launch();
   return 0;
 }

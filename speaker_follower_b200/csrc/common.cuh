@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 
 namespace sfb {
 
@@ -45,6 +46,37 @@ void reset_launch_count();
     int32_t _s = (expr);               \
     if (_s != 0) return _s;            \
   } while (0)
+
+// ------------------------------------------------------------------ host launch helper (cluster dims + PDL)
+extern int g_disable_pdl;
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             dim3 cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster.x * cluster.y * cluster.z > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster.x;
+    attr[n].val.clusterDim.y = cluster.y;
+    attr[n].val.clusterDim.z = cluster.z;
+    ++n;
+  }
+  if (!g_disable_pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
@@ -152,6 +184,12 @@ __device__ __forceinline__ float4 dsmem_ld_f32x4(uint32_t addr) {
                : "memory");
   return v;
 }
+
+// ---- programmatic dependent launch (PDL): a kernel may start (prologue + prefetch of operands that no kernel of
+// the step writes: weights, feature slabs, ctx, action embeddings) while its predecessor is still running;
+// pdl_wait() blocks until the predecessor grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
   const int wrow = lstm ? (ty >> 3) * p.lstm.H + blockIdx.x * 8 + (ty & 7) : n0 + ty;
   const bool wrow_ok = lstm ? (blockIdx.x * 8 + (ty & 7)) < p.lstm.H : wrow < p.N;
 
-  auto load_chunk = [&](int c) {
+  auto load_chunk = [&](int c, bool do_a, bool do_b) {
     int s = 0, cc = c;
     while (s + 1 < p.nseg) {
       const int n = (p.seg[s].k + BK - 1) / BK;
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
     }
     const GemmSeg& g = p.seg[s];
     const int kofs = cc * BK;
-    {
+    if (do_a) {
       const int kk = kofs + tx * 4;
 #pragma unroll
       for (int i = 0; i < TM; ++i) {
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < p.M && kk < g.k) {
           const int xr = g.xrow ? g.xrow[m] : m;
-          v = ldg4(g.x + (size_t)xr * g.ldx + kk);
+          v = *reinterpret_cast<const float4*>(g.x + (size_t)xr * g.ldx + kk);
           if (g.xs) {
             const float4 sc = ldg4(g.xs + (size_t)m * g.ldxs + kk);
             v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
@@ -79,23 +79,29 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
         pa[i] = v;
       }
     }
-    pb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!KN) {
-      const int kk = kofs + tx * 4;
-      if (wrow_ok && kk < g.k) pb = ldg4(g.w + (size_t)wrow * g.ldw + kk);
-    } else {
-      const int kk = kofs + ty, nn = n0 + tx * 4;
-      if (kk < g.k && nn < p.N) pb = ldg4(g.w + (size_t)kk * g.ldw + nn);
+    if (do_b) {
+      pb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!KN) {
+        const int kk = kofs + tx * 4;
+        if (wrow_ok && kk < g.k) pb = ldg4(g.w + (size_t)wrow * g.ldw + kk);
+      } else {
+        const int kk = kofs + ty, nn = n0 + tx * 4;
+        if (kk < g.k && nn < p.N) pb = ldg4(g.w + (size_t)kk * g.ldw + nn);
+      }
     }
   };
 
-  if (c_begin < c_end) load_chunk(c_begin);
+  // PDL: weights are step inputs -> fetch the first weight chunk while the producer of the activations still runs
+  pdl_launch_dependents();
+  if (c_begin < c_end) load_chunk(c_begin, false, true);
+  pdl_wait();
+  if (c_begin < c_end) load_chunk(c_begin, true, false);
   for (int c = c_begin; c < c_end; ++c) {
 #pragma unroll
     for (int i = 0; i < TM; ++i) *reinterpret_cast<float4*>(&As[(ty + 32 * i) * SA + tx * 4]) = pa[i];
     *reinterpret_cast<float4*>(&Bs[ty * SB + tx * 4]) = pb;
     __syncthreads();
-    if (c + 1 < c_end) load_chunk(c + 1);
+    if (c + 1 < c_end) load_chunk(c + 1, true, true);
 #pragma unroll
     for (int k4 = 0; k4 < BK / 4; ++k4) {
       float4 a[TM];
@@ -206,19 +212,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 template <int TM, bool KN>
 static int32_t launch_t(const GemmParams& p, dim3 grid, cudaStream_t stream) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(256, 1, 1);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = p.splitk;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<TM, KN>, p));
+  SFB_CHECK_CUDA(launch_ex(gemm_skinny_kernel<TM, KN>, grid, dim3(256, 1, 1), 0, stream, dim3(1, p.splitk, 1), p));
   count_launch();
   return 0;
 }

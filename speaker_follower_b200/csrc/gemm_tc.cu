@@ -32,7 +32,13 @@ constexpr uint32_t CORE = 128;                 // bytes of one 8x16B core matrix
 constexpr uint32_t SBO = (TBK / 8) * CORE;     // byte stride between 8-row groups (1024)
 constexpr uint32_t LBO = CORE;                 // byte stride between K-adjacent core matrices
 
-static int g_tc_debug = 0;   // bit0: swap LBO/SBO, bit1: descriptor version 0  (bring-up only)
+static int g_tc_debug = 0;   // bit0: swap LBO/SBO, bit1: descriptor version 0, bit2: phase timestamps (bring-up only)
+__device__ long long g_tc_ts[256];
+#define TS(i)                                                              \
+  do {                                                                     \
+    if ((dbg & 4) && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (i) < 256) \
+      g_tc_ts[(i)] = clock64();                                            \
+  } while (0)
 
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
   for (uint32_t i = 0; i < (1u << 27); ++i)
@@ -86,6 +92,9 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 }  // namespace
 
 // grid = (4H/128, S, batch tiles), cluster (1, S, 1), 256 threads, dynamic smem
+// HAS_XS: some K segment carries a dropout keep-mask (training); kept out of the eval instantiation so the
+// prefetch loads have no consumer until the conversion phase (a predicated-off FMUL still waits on its inputs).
+template <bool HAS_XS>
 __global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p, const int NB, const int STAGES,
                                                              const int rows_per_z, const int dbg) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -120,6 +129,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
+  TS(0);
 
   // ---- K blocks of this CTA
   int nblk = 0;
@@ -129,9 +139,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p
 
   // per-thread staging coordinates: warp-unit wu = warp + 8*i -> (row group, K half); lane -> (row in group, core)
   const int r_in = lane & 7, kc_in = lane >> 3;
-  float4 ra[4][2], rb[4][2];
+  float4 ra[4][2], rb[4][2], rs[HAS_XS ? 4 : 1][2];
 
-  auto load_block = [&](int blk) {
+  auto load_block = [&](int blk, bool do_a, bool do_b) {
     int s = 0, cc = blk;
     while (s + 1 < p.nseg) {
       const int n = (p.seg[s].k + TBK - 1) / TBK;
@@ -146,7 +156,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p
       const int wu = warp + 8 * i;
       const int rg = wu >> 1, k = kofs + ((wu & 1) * 4 + kc_in) * 8;
       // A operand: weight rows, gate-interleaved: tile row = gate*32 + unit_local
-      {
+      if (do_a) {
         const int row = rg * 8 + r_in;
         const int wrow = (row >> 5) * H + tile * 32 + (row & 31);
         if (k < g.k) {
@@ -158,22 +168,25 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p
         }
       }
       // B operand: activations (batch rows), optional row indirection and dropout scale
-      {
+      if (do_b) {
         const int m = m0 + rg * 8 + r_in;
         if (rg * 8 < NB && m < m_end && k < g.k) {
           const int xr = g.xrow ? g.xrow[m] : m;
           const float* src = g.x + (size_t)xr * g.ldx + k;
-          float4 v0 = ldg4(src), v1 = ldg4(src + 4);
-          if (g.xs) {
-            const float* sp = g.xs + (size_t)m * g.ldxs + k;
-            const float4 s0 = ldg4(sp), s1 = ldg4(sp + 4);
-            v0.x *= s0.x; v0.y *= s0.y; v0.z *= s0.z; v0.w *= s0.w;
-            v1.x *= s1.x; v1.y *= s1.y; v1.z *= s1.z; v1.w *= s1.w;
+          rb[i][0] = *reinterpret_cast<const float4*>(src);       // produced by the previous kernel: coherent loads
+          rb[i][1] = *reinterpret_cast<const float4*>(src + 4);
+          if (HAS_XS) {
+            if (g.xs) {
+              const float* sp = g.xs + (size_t)m * g.ldxs + k;
+              rs[i][0] = ldg4(sp);
+              rs[i][1] = ldg4(sp + 4);
+            } else {
+              rs[i][0] = rs[i][1] = make_float4(1.f, 1.f, 1.f, 1.f);
+            }
           }
-          rb[i][0] = v0;
-          rb[i][1] = v1;
         } else {
           rb[i][0] = rb[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (HAS_XS) rs[i][0] = rs[i][1] = make_float4(1.f, 1.f, 1.f, 1.f);
         }
       }
     }
@@ -182,10 +195,17 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p
   // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=NB
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
 
-  if (b_begin < b_end) load_block(b_begin);
+  // PDL: weights are step inputs -> first weight block is in flight before the activations' producer has finished
+  pdl_launch_dependents();
+  if (b_begin < b_end) load_block(b_begin, true, false);
+  pdl_wait();
+  TS(1);
+  if (b_begin < b_end) load_block(b_begin, false, true);
   for (int blk = b_begin; blk < b_end; ++blk) {
     const int it = blk - b_begin, s = it % STAGES, use = it / STAGES;
+    TS(8 + it * 8 + 0);
     if (use >= 1) mbar_wait_bounded(&bars[s], (uint32_t)(use - 1) & 1u);   // MMAs that read this stage are done
+    TS(8 + it * 8 + 1);
     unsigned char* st = stage_base + (size_t)s * stage_bytes;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -196,14 +216,21 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p
       *reinterpret_cast<uint4*>(st + off) = hi;
       *reinterpret_cast<uint4*>(st + a_bytes + off) = lo;
       if ((wu >> 1) * 8 < NB) {
+        if (HAS_XS) {
+          rb[i][0].x *= rs[i][0].x; rb[i][0].y *= rs[i][0].y; rb[i][0].z *= rs[i][0].z; rb[i][0].w *= rs[i][0].w;
+          rb[i][1].x *= rs[i][1].x; rb[i][1].y *= rs[i][1].y; rb[i][1].z *= rs[i][1].z; rb[i][1].w *= rs[i][1].w;
+        }
         split8(rb[i][0], rb[i][1], hi, lo);
         *reinterpret_cast<uint4*>(st + 2 * a_bytes + off) = hi;
         *reinterpret_cast<uint4*>(st + 2 * a_bytes + b_bytes + off) = lo;
       }
     }
+    TS(8 + it * 8 + 2);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
     __syncthreads();
-    if (blk + 1 < b_end) load_block(blk + 1);                     // next stage's global loads fly during the MMAs
+    TS(8 + it * 8 + 3);
+    if (blk + 1 < b_end) load_block(blk + 1, true, true);         // next stage's global loads fly during the MMAs
+    TS(8 + it * 8 + 4);
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_hi = smem_u32(st), a_lo = a_hi + a_bytes, b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
@@ -219,7 +246,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p
       umma_commit(&bars[s]);
       if (blk + 1 == b_end) umma_commit(&bars[STAGES]);
     }
+    TS(8 + it * 8 + 5);
   }
+  TS(2);
 
   // ---- epilogue: TMEM -> registers -> shared partial tile [128][NBS]
   if (b_begin < b_end) {
@@ -247,8 +276,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p
         *reinterpret_cast<uint4*>(prow + c + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
   }
+  TS(3);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (S > 1) cluster_sync_all(); else __syncthreads();
+  TS(4);
 
   // ---- reduce over the cluster (rank order) + LSTM cell update: CTA `rank` owns 32/S hidden units of the tile
   {
@@ -277,7 +308,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p
       }
     }
   }
+  TS(5);
   if (S > 1) cluster_sync_all(); else __syncthreads();   // peers may still be reading this CTA's partial tile
+  TS(6);
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
 }
@@ -285,6 +318,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p
 // ------------------------------------------------------------------ host side
 
 void gemm_tc_set_debug(int flags) { g_tc_debug = flags; }
+int gemm_tc_read_timestamps(long long* out, int n) {
+  if (n > 256) n = 256;
+  return cudaMemcpyFromSymbol(out, g_tc_ts, n * sizeof(long long)) == cudaSuccess ? 0 : -1;
+}
 
 static int tc_pick_splitk(const GemmParams& p) {
   int nblk = 0;
@@ -319,24 +356,17 @@ int32_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t stream) {
   const size_t part_bytes = (size_t)TBM * (NB + 4) * sizeof(float);
   if (part_bytes + 64 > smem) smem = part_bytes + 64;
   SFB_CHECK_ARG(part_bytes <= stages * stage_bytes, "gemm_tc: partial tile does not fit the stage memory");
-  static size_t configured = 0;
-  if (smem > configured) {
-    SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  bool has_xs = false;
+  for (int s = 0; s < p.nseg; ++s) has_xs |= p.seg[s].xs != nullptr;
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[has_xs]) {
+    if (has_xs) SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_lstm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_lstm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[has_xs] = smem;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p.N / TBM, p.splitk, nz);
-  cfg.blockDim = dim3(256, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = p.splitk;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  SFB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_lstm_kernel, p, NB, stages, rows_per_z, g_tc_debug));
+  const dim3 grid(p.N / TBM, p.splitk, nz), cl(1, p.splitk, 1);
+  if (has_xs) SFB_CHECK_CUDA(launch_ex(gemm_tc_lstm_kernel<true>, grid, dim3(256, 1, 1), smem, stream, cl, p, NB, stages, rows_per_z, g_tc_debug));
+  else SFB_CHECK_CUDA(launch_ex(gemm_tc_lstm_kernel<false>, grid, dim3(256, 1, 1), smem, stream, cl, p, NB, stages, rows_per_z, g_tc_debug));
   count_launch();
   return 0;
 }

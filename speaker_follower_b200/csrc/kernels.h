@@ -64,6 +64,7 @@ int gemm_pick_splitk(int M, int N, int ktotal, int num_sms);
 bool gemm_tc_supported(const GemmParams& p);
 int32_t launch_gemm_tc(const GemmParams& p, cudaStream_t stream);
 void gemm_tc_set_debug(int flags);
+int gemm_tc_read_timestamps(long long* out, int n);
 extern int g_disable_tc;
 
 // ---------------------------------------------------------------- pointwise.cu

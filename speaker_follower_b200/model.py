@@ -1,0 +1,239 @@
+"""Drop-in module layer: the classes of the reference's tasks/R2R/model.py, same names, constructor and
+forward signatures and state_dict keys, with every forward running on the sm_100a library through the C ABI.
+
+    EncoderLSTM          model.py:43-104      AttnDecoderLSTM      model.py:355-397
+    SoftDotAttention     model.py:107-143     SpeakerEncoderLSTM   model.py:405-457
+    VisualSoftDotAttention model.py:300-326   SpeakerDecoderLSTM   model.py:460-519
+    EltwiseProdScoring   model.py:329-352
+
+Parameters live in ordinary nn.Linear / nn.LSTMCell / nn.LSTM / nn.Embedding sub-modules so that
+``state_dict()`` / ``load_state_dict()`` interoperate with the reference's snapshots (follower.py:1022-1035);
+those sub-modules are parameter containers only — their own forward is never called.  The library reads the
+parameter storage in place each step (nothing is cached or re-laid-out).
+
+Scope of this round: inference / scoring forward.  Calling a module while autograd is recording raises
+NotImplementedError (the backward kernels are the next row of SURVEY.md §8); dropout in ``train()`` mode is
+applied with masks drawn here (torch RNG) and passed to the kernels, exactly where the reference applies
+nn.Dropout.  Tensors must be CUDA: there is no CPU path in this package.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _no_autograd(*tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            "speaker_follower_b200: backward kernels are not part of this round; call under torch.no_grad() "
+            "(inference, scoring, search) or use the reference modules for training")
+
+
+def _sd(module: nn.Module):
+    """name -> parameter tensor (no copies), reference state_dict key names."""
+    return {k: v for k, v in module.named_parameters()}
+
+
+class _Drop:
+    """nn.Dropout semantics with an explicit, kernel-visible mask (scaled keep mask or None)."""
+
+    def __init__(self, p: float):
+        self.p = p
+
+    def mask(self, training: bool, shape, device) -> Optional[torch.Tensor]:
+        if not training or self.p <= 0.0:
+            return None
+        keep = (torch.rand(shape, device=device) >= self.p).to(torch.float32)
+        return keep / (1.0 - self.p)
+
+
+class EncoderLSTM(nn.Module):
+    """model.py:43-104."""
+
+    def __init__(self, vocab_size, embedding_size, hidden_size, padding_idx, dropout_ratio, bidirectional=False,
+                 num_layers=1, glove=None):
+        super().__init__()
+        assert num_layers == 1, "the reference only ever uses one layer (train.py:197)"
+        self.embedding_size = embedding_size
+        self.hidden_size = hidden_size
+        self.drop = nn.Dropout(p=dropout_ratio)
+        self._drop = _Drop(dropout_ratio)
+        self.num_directions = 2 if bidirectional else 1
+        self.num_layers = num_layers
+        self.embedding = nn.Embedding(vocab_size, embedding_size, padding_idx)
+        self.use_glove = glove is not None
+        if self.use_glove:
+            print("Using GloVe embedding")
+            self.embedding.weight.data[...] = torch.from_numpy(glove)
+            self.embedding.weight.requires_grad = False
+        self.lstm = nn.LSTM(embedding_size, hidden_size, self.num_layers, batch_first=True,
+                            dropout=0.0, bidirectional=bidirectional)
+        self.encoder2decoder = nn.Linear(hidden_size * self.num_directions, hidden_size * self.num_directions)
+
+    def forward(self, inputs, lengths):
+        """inputs [B, seq_len] int64 (length-sorted, model.py:89), lengths list -> (ctx, decoder_init, c_t)."""
+        _no_autograd(*[p for p in self.parameters()])
+        B = inputs.size(0)
+        maxlen = int(max(int(x) for x in lengths))
+        drop_e = None
+        if not self.use_glove:
+            drop_e = self._drop.mask(self.training, (B * maxlen, self.embedding_size), inputs.device)
+        ctx, decoder_init, c_t = ops.encoder_lstm(_sd(self), inputs, lengths, self.num_directions == 2, drop_e)
+        m = self._drop.mask(self.training, ctx.shape, ctx.device)
+        if m is not None:
+            ctx = ctx * m                                     # model.py:102
+        return ctx, decoder_init, c_t
+
+
+class SoftDotAttention(nn.Module):
+    """model.py:107-143."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.linear_in = nn.Linear(dim, dim, bias=False)
+        self.linear_out = nn.Linear(dim * 2, dim, bias=False)
+
+    def forward(self, h, context, mask=None):
+        _no_autograd(h, context, *self.parameters())
+        w = {"a." + k: v for k, v in self.named_parameters()}
+        return ops.soft_dot_attention(w, "a.", h.contiguous(), context.contiguous(), mask)
+
+
+class VisualSoftDotAttention(nn.Module):
+    """model.py:300-326 (``mask`` is ignored there too)."""
+
+    def __init__(self, h_dim, v_dim, dot_dim=256):
+        super().__init__()
+        self.linear_in_h = nn.Linear(h_dim, dot_dim, bias=True)
+        self.linear_in_v = nn.Linear(v_dim, dot_dim, bias=True)
+
+    def forward(self, h, visual_context, mask=None):
+        _no_autograd(h, visual_context, *self.parameters())
+        w = {"visual_attention_layer." + k: v for k, v in self.named_parameters()}
+        return ops.visual_attention(w, h.contiguous(), visual_context.contiguous())
+
+
+class EltwiseProdScoring(nn.Module):
+    """model.py:329-352 — parameter container; scoring runs inside AttnDecoderLSTM's fused step."""
+
+    def __init__(self, h_dim, a_dim, dot_dim=256):
+        super().__init__()
+        self.linear_in_h = nn.Linear(h_dim, dot_dim, bias=True)
+        self.linear_in_a = nn.Linear(a_dim, dot_dim, bias=True)
+        self.linear_out = nn.Linear(dot_dim, 1, bias=True)
+
+
+class AttnDecoderLSTM(nn.Module):
+    """model.py:355-397: one follower decode step per call."""
+
+    def __init__(self, embedding_size, hidden_size, dropout_ratio, feature_size=2048 + 128, image_attention_layers=None):
+        super().__init__()
+        self.embedding_size = embedding_size
+        self.feature_size = feature_size
+        self.hidden_size = hidden_size
+        self.register_buffer("_u_begin", torch.zeros(embedding_size), persistent=False)
+        self.drop = nn.Dropout(p=dropout_ratio)
+        self._drop = _Drop(dropout_ratio)
+        self.lstm = nn.LSTMCell(embedding_size + feature_size, hidden_size)
+        self.visual_attention_layer = VisualSoftDotAttention(hidden_size, feature_size)
+        self.text_attention_layer = SoftDotAttention(hidden_size)
+        self.decoder2action = EltwiseProdScoring(hidden_size, embedding_size)
+        self.feature_store: Optional[ops.FeatureStore] = None   # set to gather slabs on the device (K13)
+
+    @property
+    def u_begin(self):
+        """zeros[E] on the module's device (model.py:368; read at follower.py:356,462,563,744)."""
+        return self._u_begin
+
+    def forward(self, u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask=None):
+        """-> (h_1, c_1, alpha, logit, alpha_v).  ``visual_context`` is either the dense [B,36,F] tensor of the
+        reference or a ``(vp_idx, view_idx)`` pair of int tensors when ``self.feature_store`` is set."""
+        _no_autograd(u_t_prev, all_u_t, h_0, c_0, ctx, *self.parameters())
+        B = h_0.shape[0]
+        dev = h_0.device
+        drop_x = self._drop.mask(self.training, (B, self.embedding_size + self.feature_size), dev)
+        drop_h = self._drop.mask(self.training, (B, self.hidden_size), dev)
+        u_t_prev = u_t_prev.contiguous()        # u_begin.expand(B, -1) is a stride-0 view (follower.py:462)
+        if isinstance(visual_context, (tuple, list)):
+            vp, view = visual_context
+            return ops.follower_step(_sd(self), u_t_prev, all_u_t.contiguous(), None, h_0.contiguous(),
+                                     c_0.contiguous(), ctx.contiguous(), ctx_mask, drop_x, drop_h,
+                                     store=self.feature_store, vp_idx=vp, view_idx=view)
+        return ops.follower_step(_sd(self), u_t_prev, all_u_t.contiguous(), visual_context.contiguous(),
+                                 h_0.contiguous(), c_0.contiguous(), ctx.contiguous(), ctx_mask, drop_x, drop_h)
+
+
+class SpeakerEncoderLSTM(nn.Module):
+    """model.py:405-457."""
+
+    def __init__(self, action_embedding_size, world_embedding_size, hidden_size, dropout_ratio, bidirectional=False):
+        super().__init__()
+        assert not bidirectional, "Bidirectional is not implemented yet"
+        self.action_embedding_size = action_embedding_size
+        self.word_embedding_size = world_embedding_size
+        self.hidden_size = hidden_size
+        self.drop = nn.Dropout(p=dropout_ratio)
+        self._drop = _Drop(dropout_ratio)
+        self.visual_attention_layer = VisualSoftDotAttention(hidden_size, world_embedding_size)
+        self.lstm = nn.LSTMCell(action_embedding_size + world_embedding_size, hidden_size)
+        self.encoder2decoder = nn.Linear(hidden_size, hidden_size)
+
+    def forward(self, batched_action_embeddings: List[torch.Tensor], world_state_embeddings: List[torch.Tensor]):
+        assert isinstance(batched_action_embeddings, list)
+        assert isinstance(world_state_embeddings, list)
+        assert len(batched_action_embeddings) == len(world_state_embeddings)
+        _no_autograd(*self.parameters())
+        w = _sd(self)
+        B = world_state_embeddings[0].shape[0]
+        dev = world_state_embeddings[0].device
+        h = torch.zeros(B, self.hidden_size, device=dev)
+        c = torch.zeros(B, self.hidden_size, device=dev)
+        hs = []
+        for a, v in zip(batched_action_embeddings, world_state_embeddings):
+            dx = self._drop.mask(self.training, (B, self.action_embedding_size + self.word_embedding_size), dev)
+            h, c = ops.speaker_encoder_step(w, a.contiguous(), v.contiguous(), h, c, dx)
+            hs.append(h)
+        # decoder_init = tanh(encoder2decoder(h_T)) (model.py:453): one [B,H]x[H,H] product per path, host plumbing
+        decoder_init = torch.tanh(torch.addmm(self.encoder2decoder.bias, h, self.encoder2decoder.weight.t()))
+        ctx = torch.stack(hs, dim=1)
+        m = self._drop.mask(self.training, ctx.shape, dev)
+        if m is not None:
+            ctx = ctx * m
+        return ctx, decoder_init, c
+
+
+class SpeakerDecoderLSTM(nn.Module):
+    """model.py:460-519, default branch (use_input_att_feed=False is what train_speaker.py:188-193 builds)."""
+
+    def __init__(self, vocab_size, vocab_embedding_size, hidden_size, dropout_ratio, glove=None, use_input_att_feed=False):
+        super().__init__()
+        if use_input_att_feed:
+            raise NotImplementedError("use_input_att_feed=True is never constructed by the reference's CLIs")
+        self.vocab_size = vocab_size
+        self.vocab_embedding_size = vocab_embedding_size
+        self.hidden_size = hidden_size
+        self.embedding = nn.Embedding(vocab_size, vocab_embedding_size)
+        self.use_glove = glove is not None
+        if self.use_glove:
+            print("Using GloVe embedding")
+            self.embedding.weight.data[...] = torch.from_numpy(glove)
+            self.embedding.weight.requires_grad = False
+        self.drop = nn.Dropout(p=dropout_ratio)
+        self._drop = _Drop(dropout_ratio)
+        self.use_input_att_feed = use_input_att_feed
+        self.lstm = nn.LSTMCell(vocab_embedding_size, hidden_size)
+        self.attention_layer = SoftDotAttention(hidden_size)
+        self.decoder2action = nn.Linear(hidden_size, vocab_size)
+
+    def forward(self, previous_word, h_0, c_0, ctx, ctx_mask=None):
+        _no_autograd(h_0, c_0, ctx, *self.parameters())
+        B = h_0.shape[0]
+        dev = h_0.device
+        drop_e = None if self.use_glove else self._drop.mask(self.training, (B, self.vocab_embedding_size), dev)
+        drop_h = self._drop.mask(self.training, (B, self.hidden_size), dev)
+        return ops.speaker_decoder_step(_sd(self), previous_word, h_0.contiguous(), c_0.contiguous(),
+                                        ctx.contiguous(), ctx_mask, drop_e, drop_h)

@@ -1,0 +1,70 @@
+"""world_size-2 gloo tests (CPU) of the N>1 plumbing: instance sharding, max-over-ranks timing, and the sharded
+pragmatic-inference combine reproducing the single-process result (rational_follower.py:118-150)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import r2r_oracle as O
+from speaker_follower_b200 import dist as D
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = np.random.Generator(np.random.PCG64(5))
+        n_instr, n_cand = 7, 5
+        spk = g.standard_normal((n_instr, n_cand)) * 3 - 20
+        fol = g.standard_normal((n_instr, n_cand)) * 2 - 5
+        mine = D.shard_indices(n_instr, rank, world)
+        recs = torch.tensor([[i, c, fol[i, c], spk[i, c]] for i in mine for c in range(n_cand)], dtype=torch.float64)
+        allr = D.gather_records(recs)
+        s_std = D.global_std(recs[:, 3])
+        f_std = D.global_std(recs[:, 2])
+        rate, ms = D.aggregate_rate(100, 10.0 * (rank + 1))
+        q.put((rank, allr.numpy(), s_std, f_std, rate, ms, spk, fol))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_combine_equals_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    outs.sort(key=lambda o: o[0])
+    _, allr0, s_std, f_std, rate, ms, spk, fol = outs[0]
+    assert np.array_equal(allr0, outs[1][1])                       # every rank sees the same, ordered records
+    assert allr0.shape == (35, 4)
+    assert np.array_equal(allr0[:, 0], np.repeat(np.arange(7), 5))
+    assert abs(s_std - np.std(spk)) < 1e-12 and abs(f_std - np.std(fol)) < 1e-12     # global population std
+    assert ms == 20.0 and abs(rate - 2 * 100 / 0.020) < 1e-9                         # max over ranks, whole-job units
+    # weighted argmax with the sharded statistics == single-process oracle combine
+    groups = [int(i) for i in allr0[:, 0]]
+    best = O.rational_combine(allr0[:, 3], allr0[:, 2], groups, 0.95)
+    comb = 0.95 * spk / np.std(spk) + 0.05 * fol / np.std(fol)
+    for i in range(7):
+        assert int(allr0[best[i], 1]) == int(np.argmax(comb[i]))
+
+
+def test_shard_indices_cover_and_balance():
+    for n in (1, 7, 64, 2560):
+        for w in (1, 2, 4, 8):
+            parts = [D.shard_indices(n, r, w) for r in range(w)]
+            assert sorted(sum(parts, [])) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
