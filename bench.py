@@ -197,7 +197,7 @@ def run_gpu(args, rank, local_rank, world):
     ubuf = [torch.zeros(B, E, device=dev), torch.empty(B, E, device=dev)]
     alpha = torch.empty(B, L, device=dev); logit = torch.empty(B, A, device=dev); alpha_v = torch.empty(B, 36, device=dev)
     a_t = torch.empty(B, dtype=torch.int32, device=dev); score = torch.empty(B, device=dev)
-    ws = torch.empty(1 << 26, dtype=torch.uint8, device=dev)
+    ws = torch.zeros(1 << 26, dtype=torch.uint8, device=dev)   # zero-filled once (semaphores)
     launches_per_step = [0]
 
     def step(i):
@@ -309,12 +309,12 @@ def run_gpu(args, rank, local_rank, world):
     n_attn = 200
     vps = [torch.randint(0, N_VIEWPOINTS, (B,), device=dev, dtype=torch.int32, generator=g) for _ in range(n_attn)]
     for i in range(5):
-        ops.visual_attention_core(q, None, store=store, vp_idx=vps[i], view_idx=view[0], out=(feat, alpha_v))
+        ops.visual_attention_core(q, None, store=store, vp_idx=vps[i], view_idx=view[0], out=(feat, alpha_v), workspace=ws)
     torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_attn)]
     for i in range(n_attn):
         evs[i][0].record()
-        ops.visual_attention_core(q, None, store=store, vp_idx=vps[i], view_idx=view[0], out=(feat, alpha_v))
+        ops.visual_attention_core(q, None, store=store, vp_idx=vps[i], view_idx=view[0], out=(feat, alpha_v), workspace=ws)
         evs[i][1].record()
     torch.cuda.synchronize()
     attn_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))

@@ -96,13 +96,19 @@ const char* sfb_last_error(void);
 int32_t sfb_set_option(const char* name, int32_t value);
 /* Bring-up: phase timestamps (SM clock) of the tensor-core GEMM's CTA 0, valid after a call with tc_debug bit 2. */
 int32_t sfb_debug_read_timestamps(int64_t* out, int32_t n);
+/* Bring-up: after sfb_set_option("trace", 1), every kernel enqueued records {entry, after dependency wait, exit}
+ * (globaltimer ns, block 0) in launch order; returns the number of slots copied (16 int64 each: 0-2 as above, 3-15 kernel-specific phases). */
+int32_t sfb_debug_read_trace(int64_t* out, int32_t max_slots);
 
 /* Device properties the library was built for / sees.  Fills sm (e.g. 100), number of SMs and max
  * opt-in shared memory per block; returns SFB_ERR_NO_DEVICE when there is no usable device. */
 int32_t sfb_device_info(int32_t* sm, int32_t* num_sms, int32_t* smem_per_block);
 
 /* Bytes of device workspace one follower decode step needs (also an upper bound for the speaker
- * encoder step and the two attention entry points at the same B).  256-byte aligned pointer required. */
+ * encoder step and the two attention entry points at the same B).  256-byte aligned pointer required.
+ * WORKSPACE CONTRACT (all *_workspace_bytes functions): the buffer must be zero-filled once before its first
+ * use (its head holds self-resetting inter-CTA semaphores); afterwards it can be re-used by any number of
+ * calls, but not by two calls that may run concurrently on different streams. */
 size_t sfb_follower_step_workspace_bytes(const sfb_dims* dims, int32_t B, int32_t L, int32_t A);
 
 /* VisualSoftDotAttention.forward — model.py:310-326.
@@ -116,7 +122,8 @@ int32_t sfb_visual_attention_fwd(const sfb_dims* dims, const sfb_vis_lstm_weight
  * (= W_v^T (W_h h + b_h)), alpha_v = softmax_v(V_v . q), feature = sum_v alpha_v V_v.  One launch; this is
  * the kernel whose HBM roofline fraction BASELINE.json's "attn HBM %" refers to. */
 int32_t sfb_visual_attention_core_fwd(const sfb_dims* dims, int32_t B, const float* q,
-                                      const sfb_visual_source* vis, float* feature, float* alpha_v, void* stream);
+                                      const sfb_visual_source* vis, float* feature, float* alpha_v,
+                                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* SoftDotAttention.forward — model.py:122-143.
  * h [B,H], ctx [B,L,H], mask [B,L] (may be NULL) -> h_tilde [B,H], alpha [B,L]. */
@@ -198,7 +205,7 @@ typedef struct sfb_speaker_decoder_weights {
   const float* b_voc;       /* [vocab] */
 } sfb_speaker_decoder_weights;
 
-size_t sfb_speaker_decoder_step_workspace_bytes(int32_t H, int32_t Ew, int32_t B);
+size_t sfb_speaker_decoder_step_workspace_bytes(int32_t H, int32_t Ew, int32_t B, int32_t T);
 
 int32_t sfb_speaker_decoder_step_fwd(const sfb_speaker_decoder_weights* w, int32_t H, int32_t Ew, int32_t vocab,
                                      int32_t B, int32_t T, const int32_t* prev_word,

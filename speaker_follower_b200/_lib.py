@@ -59,15 +59,16 @@ SIGNATURES = {
     "sfb_last_error": (C.c_char_p, []),
     "sfb_last_launch_count": (C.c_int32, []),
     "sfb_set_option": (C.c_int32, [C.c_char_p, C.c_int32]),
+    "sfb_debug_read_trace": (C.c_int32, [C.c_void_p, C.c_int32]),
     "sfb_debug_read_timestamps": (C.c_int32, [C.c_void_p, C.c_int32]),
     "sfb_device_info": (C.c_int32, [C.POINTER(C.c_int32)] * 3),
     "sfb_follower_step_workspace_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32, C.c_int32, C.c_int32]),
-    "sfb_speaker_decoder_step_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "sfb_speaker_decoder_step_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "sfb_visual_attention_fwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(VisLstmWeights), C.c_int32, c_float_p,
                                              C.POINTER(VisualSource), c_float_p, c_float_p,
                                              C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_visual_attention_core_fwd": (C.c_int32, [C.POINTER(Dims), C.c_int32, c_float_p, C.POINTER(VisualSource),
-                                                  c_float_p, c_float_p, C.c_void_p]),
+                                                  c_float_p, c_float_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_soft_dot_attention_fwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(SoftDotWeights), C.c_int32, C.c_int32,
                                                c_float_p, c_float_p, c_u8_p, c_float_p, c_float_p,
                                                C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -15,6 +15,13 @@ void set_error(const std::string& msg) { g_err = msg; }
 void count_launch(int n) { g_launches += n; }
 void reset_launch_count() { g_launches = 0; }
 
+static int g_trace_on = 0, g_trace_n = 0;
+static unsigned long long* g_trace_buf = nullptr;   // [64][16] device
+unsigned long long* next_trace_slot() {
+  if (!g_trace_on || !g_trace_buf || g_trace_n >= 64) return nullptr;
+  return g_trace_buf + 16 * (g_trace_n++);
+}
+
 int device_num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -40,6 +47,9 @@ struct Carver {
 };
 
 struct FollowerWs {
+  void* tc; size_t tc_bytes;              // tensor-core GEMM: semaphores (zeroed by the caller once) + partial tiles
+  void* av; size_t av_bytes;              // visual attention: tickets + partial records
+  void* at; size_t at_bytes;              // text attention
   float *tv, *q, *feat, *gates_act, *h1d, *t, *wc, *htilde, *tp, *g;
   int splitk;
   size_t bytes;
@@ -50,10 +60,16 @@ static int gates_splitk(const sfb_dims& d, int B) {
 }
 
 static FollowerWs carve_follower(const sfb_dims& d, int B, int L, int A, void* ws) {
-  (void)L; (void)A;
+  (void)A;
   FollowerWs w;
   Carver c(ws);
   w.splitk = gates_splitk(d, B);
+  w.tc_bytes = (d.H % 32) == 0 ? gemm_tc_plan(B, d.H, d.E + d.F + d.H, 3, device_num_sms()).bytes : 256;
+  w.tc = c.take(w.tc_bytes / sizeof(float));
+  w.av_bytes = attention_plan(B, d.V, d.F, device_num_sms()).bytes;
+  w.av = c.take(w.av_bytes / sizeof(float));
+  w.at_bytes = attention_plan(B, L > 0 ? L : 1, d.H, device_num_sms()).bytes;
+  w.at = c.take(w.at_bytes / sizeof(float));
   const int kmax = d.F > d.E ? d.F : d.E;
   w.tv = c.take((size_t)B * d.D);
   w.q = c.take((size_t)B * kmax);
@@ -70,15 +86,21 @@ static FollowerWs carve_follower(const sfb_dims& d, int B, int L, int A, void* w
 }
 
 struct SpkDecWs {
+  void* tc; size_t tc_bytes;
+  void* at; size_t at_bytes;
   float *gates_act, *h1d, *t, *wc, *htilde;
   int splitk;
   size_t bytes;
 };
 
-static SpkDecWs carve_spkdec(int H, int Ew, int B, void* ws) {
+static SpkDecWs carve_spkdec(int H, int Ew, int B, int T, void* ws) {
   SpkDecWs w;
   Carver c(ws);
   w.splitk = gemm_pick_splitk(B, 4 * H, Ew + H, device_num_sms());
+  w.tc_bytes = (H % 32) == 0 ? gemm_tc_plan(B, H, Ew + H, 2, device_num_sms()).bytes : 256;
+  w.tc = c.take(w.tc_bytes / sizeof(float));
+  w.at_bytes = attention_plan(B, T > 0 ? T : 1, H, device_num_sms()).bytes;
+  w.at = c.take(w.at_bytes / sizeof(float));
   w.gates_act = c.take((size_t)B * 4 * H);
   w.h1d = c.take((size_t)B * H);
   w.t = c.take((size_t)B * H);
@@ -89,6 +111,7 @@ static SpkDecWs carve_spkdec(int H, int Ew, int B, void* ws) {
 }
 
 struct EncWs {
+  void* tc; size_t tc_bytes;
   float *xproj, *h[2], *c[2];
   int splitk;
   size_t bytes;
@@ -99,6 +122,8 @@ static EncWs carve_encoder(int ndir, int Hd, int Ew, int B, int maxlen, void* ws
   EncWs w;
   Carver c(ws);
   w.splitk = gemm_pick_splitk(B, 4 * Hd, Hd, device_num_sms());
+  w.tc_bytes = (Hd % 32) == 0 ? gemm_tc_plan(B, Hd, Hd, 1, device_num_sms()).bytes : 256;
+  w.tc = c.take(w.tc_bytes / sizeof(float));
   w.xproj = c.take((size_t)ndir * B * maxlen * 4 * Hd);
   for (int i = 0; i < 2; ++i) w.h[i] = c.take((size_t)ndir * B * Hd);
   for (int i = 0; i < 2; ++i) w.c[i] = c.take((size_t)ndir * B * Hd);
@@ -139,7 +164,7 @@ static int32_t visual_query(const sfb_dims& d, const sfb_vis_lstm_weights& w, in
 }
 
 static int32_t visual_attend(const sfb_dims& d, int B, const float* q, const sfb_visual_source& v, float* feature,
-                             float* alpha_v, cudaStream_t st) {
+                             float* alpha_v, void* aws, size_t aws_bytes, cudaStream_t st) {
   AttnParams a{};
   a.q = q; a.ldq = d.F;
   a.R = d.V; a.D = d.F;
@@ -158,14 +183,15 @@ static int32_t visual_attend(const sfb_dims& d, int B, const float* q, const sfb
   a.mask = nullptr;
   a.out = feature; a.ldo = d.F;
   a.alpha = alpha_v; a.ldalpha = d.V;
-  return launch_soft_dot_attention(a, B, st);
+  return launch_soft_dot_attention(a, B, aws, aws_bytes, st);
 }
 
 // LSTMCell([xa | feat] .* drop_x, (h0, c0)) as ONE GEMM with the cell update fused into its epilogue.
 static int32_t lstm_cell(int Ea, int F, int H, const float* w_ih, const float* w_hh, const float* b_ih,
                          const float* b_hh, int B, const float* xa, const int32_t* xa_rows, const float* feat,
                          const float* h0, const float* c0, const float* drop_x, const float* drop_h,
-                         float* gates_act, float* h1, float* c1, float* h1d, cudaStream_t st) {
+                         float* gates_act, float* h1, float* c1, float* h1d, void* tc, size_t tc_bytes,
+                         cudaStream_t st) {
   GemmParams g{};
   const int ldw = Ea + F;
   int s = 0;
@@ -177,13 +203,14 @@ static int32_t lstm_cell(int Ea, int F, int H, const float* w_ih, const float* w
   g.splitk = gemm_pick_splitk(B, 4 * H, Ea + F + H, device_num_sms());
   g.lstm.H = H; g.lstm.b_ih = b_ih; g.lstm.b_hh = b_hh; g.lstm.c0 = c0; g.lstm.drop_h = drop_h;
   g.lstm.h1 = h1; g.lstm.c1 = c1; g.lstm.h1_drop = h1d; g.lstm.gates_act = gates_act;
-  if (!g_disable_tc && gemm_tc_supported(g)) return launch_gemm_tc(g, st);   // tcgen05 path (bf16x3, fp32 accumulate)
+  if (!g_disable_tc && gemm_tc_supported(g)) return launch_gemm_tc(g, st, tc, tc_bytes);   // tcgen05 (bf16x3)
   return launch_gemm(g, st);                                                 // exact-fp32 FFMA path (any shape)
 }
 
 // SoftDotAttention on an already (optionally dropped) h: t = W_in h; attention over ctx; h~ = tanh(W_out [wc;h])
 static int32_t soft_dot(int H, const sfb_softdot_weights& w, int B, int L, const float* h, const float* ctx,
-                        const uint8_t* mask, float* t, float* wc, float* h_tilde, float* alpha, cudaStream_t st) {
+                        const uint8_t* mask, float* t, float* wc, float* h_tilde, float* alpha, void* aws,
+                        size_t aws_bytes, cudaStream_t st) {
   GemmParams g{};
   g.nseg = 1;
   g.seg[0] = GemmSeg{h, H, nullptr, nullptr, 0, w.w_in, H, H, 0};
@@ -194,7 +221,7 @@ static int32_t soft_dot(int H, const sfb_softdot_weights& w, int B, int L, const
   a.segA = ctx; a.strideA_b = (long long)L * H; a.strideA_r = H; a.lenA = H; a.lenB = 0;
   a.mask = mask; a.ldmask = L;
   a.out = wc; a.ldo = H; a.alpha = alpha; a.ldalpha = L;
-  SFB_PROPAGATE(launch_soft_dot_attention(a, B, st));
+  SFB_PROPAGATE(launch_soft_dot_attention(a, B, aws, aws_bytes, st));
   GemmParams g2{};
   g2.nseg = 2;
   g2.seg[0] = GemmSeg{wc, H, nullptr, nullptr, 0, w.w_out, 2 * H, H, 0};
@@ -217,9 +244,25 @@ int32_t sfb_set_option(const char* name, int32_t value) {
   const std::string n(name ? name : "");
   if (n == "disable_tc") { g_disable_tc = value; return 0; }
   if (n == "disable_pdl") { g_disable_pdl = value; return 0; }
+  if (n == "trace") {   // value 1: (re)start recording kernel slots; 0: stop
+    g_trace_on = value;
+    g_trace_n = 0;
+    if (value && !g_trace_buf) {
+      if (cudaMalloc(&g_trace_buf, 64 * 16 * sizeof(unsigned long long)) != cudaSuccess) return SFB_ERR_CUDA;
+    }
+    if (value) cudaMemset(g_trace_buf, 0, 64 * 16 * sizeof(unsigned long long));
+    return 0;
+  }
   if (n == "tc_debug") { gemm_tc_set_debug(value); return 0; }
   set_error("unknown option: " + n);
   return SFB_ERR_INVALID_ARG;
+}
+
+int32_t sfb_debug_read_trace(int64_t* out, int32_t max_slots) {
+  if (!g_trace_buf) return 0;
+  const int n = g_trace_n < max_slots ? g_trace_n : max_slots;
+  if (cudaMemcpy(out, g_trace_buf, (size_t)n * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return n;
 }
 
 int32_t sfb_debug_read_timestamps(int64_t* out, int32_t n) {
@@ -252,9 +295,9 @@ size_t sfb_follower_step_workspace_bytes(const sfb_dims* dims, int32_t B, int32_
   return carve_follower(*dims, B, L, A, nullptr).bytes;
 }
 
-size_t sfb_speaker_decoder_step_workspace_bytes(int32_t H, int32_t Ew, int32_t B) {
-  if (H < 1 || Ew < 1 || B < 1) return 0;
-  return carve_spkdec(H, Ew, B, nullptr).bytes;
+size_t sfb_speaker_decoder_step_workspace_bytes(int32_t H, int32_t Ew, int32_t B, int32_t T) {
+  if (H < 1 || Ew < 1 || B < 1 || T < 1) return 0;
+  return carve_spkdec(H, Ew, B, T, nullptr).bytes;
 }
 
 int32_t sfb_visual_attention_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* w, int32_t B, const float* h,
@@ -268,16 +311,19 @@ int32_t sfb_visual_attention_fwd(const sfb_dims* dims, const sfb_vis_lstm_weight
   SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SFB_PROPAGATE(visual_query(*dims, *w, B, h, ws.tv, ws.q, st));
-  return visual_attend(*dims, B, ws.q, *vis, feature, alpha_v, st);
+  return visual_attend(*dims, B, ws.q, *vis, feature, alpha_v, ws.av, ws.av_bytes, st);
 }
 
 int32_t sfb_visual_attention_core_fwd(const sfb_dims* dims, int32_t B, const float* q, const sfb_visual_source* vis,
-                                      float* feature, float* alpha_v, void* stream) {
+                                      float* feature, float* alpha_v, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
   reset_launch_count();
   SFB_PROPAGATE(check_dims(dims));
   SFB_CHECK_ARG(q && vis && feature, "NULL argument");
   SFB_CHECK_ARG(B >= 1, "B >= 1");
-  return visual_attend(*dims, B, q, *vis, feature, alpha_v, static_cast<cudaStream_t>(stream));
+  FollowerWs ws = carve_follower(*dims, B, 1, 1, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
+  return visual_attend(*dims, B, q, *vis, feature, alpha_v, ws.av, ws.av_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int32_t sfb_soft_dot_attention_fwd(const sfb_dims* dims, const sfb_softdot_weights* w, int32_t B, int32_t L,
@@ -289,7 +335,8 @@ int32_t sfb_soft_dot_attention_fwd(const sfb_dims* dims, const sfb_softdot_weigh
   SFB_CHECK_ARG(B >= 1 && L >= 1, "B, L >= 1");
   FollowerWs ws = carve_follower(*dims, B, L, 1, workspace);
   SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
-  return soft_dot(dims->H, *w, B, L, h, ctx, mask, ws.t, ws.wc, h_tilde, alpha, static_cast<cudaStream_t>(stream));
+  return soft_dot(dims->H, *w, B, L, h, ctx, mask, ws.t, ws.wc, h_tilde, alpha, ws.at, ws.at_bytes,
+                  static_cast<cudaStream_t>(stream));
 }
 
 int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* wl, const sfb_softdot_weights* wt,
@@ -310,25 +357,25 @@ int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
 
   // model.py:389  feature, alpha_v = visual_attention_layer(h_0, visual_context)
   SFB_PROPAGATE(visual_query(d, *wl, B, h0, ws.tv, ws.q, st));
-  SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, alpha_v, st));
+  SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, alpha_v, ws.av, ws.av_bytes, st));
   // model.py:391-394  LSTMCell(drop(cat(u_t_prev, feature)), (h_0, c_0)); h_1_drop = drop(h_1)
   SFB_PROPAGATE(lstm_cell(d.E, d.F, d.H, wl->lstm_w_ih, wl->lstm_w_hh, wl->lstm_b_ih, wl->lstm_b_hh, B, u_prev, nullptr,
-                          ws.feat, h0, c0, drop_x, drop_h, ws.gates_act, h1, c1, ws.h1d, st));
+                          ws.feat, h0, c0, drop_x, drop_h, ws.gates_act, h1, c1, ws.h1d, ws.tc, ws.tc_bytes, st));
   // model.py:395  h_tilde, alpha = text_attention_layer(h_1_drop, ctx, ctx_mask)
-  SFB_PROPAGATE(soft_dot(d.H, *wt, B, L, ws.h1d, ctx, ctx_mask, ws.t, ws.wc, ws.htilde, alpha, st));
+  SFB_PROPAGATE(soft_dot(d.H, *wt, B, L, ws.h1d, ctx, ctx_mask, ws.t, ws.wc, ws.htilde, alpha, ws.at, ws.at_bytes, st));
   // model.py:396  logit = decoder2action(h_tilde, all_u_t)
   {
     GemmParams g{};
     g.nseg = 1;
     g.seg[0] = GemmSeg{ws.htilde, d.H, nullptr, nullptr, 0, wsc->w_h, d.H, d.H, 0};
-    g.M = B; g.N = d.D; g.splitk = gemm_pick_splitk(B, d.D, d.H, device_num_sms()); g.out = ws.tp; g.ldo = d.D; g.bias0 = wsc->b_h;
+    g.M = B; g.N = d.D; g.splitk = gemm_pick_splitk(B, d.D, d.H, device_num_sms()); g.out = ws.tp; g.ldo = d.D; g.bias0 = wsc->b_h; g.oscale = wsc->w_out;   // tp = w_out (.) (W_h ht + b_h)
     SFB_PROPAGATE(launch_gemm(g, st));
     GemmParams g2{};
     g2.nseg = 1;
-    g2.seg[0] = GemmSeg{ws.tp, d.D, nullptr, wsc->w_out, 0, wsc->w_a, d.E, d.D, 1};
+    g2.seg[0] = GemmSeg{ws.tp, d.D, nullptr, nullptr, 0, wsc->w_a, d.E, d.D, 1};
     g2.M = B; g2.N = d.E; g2.splitk = gemm_pick_splitk(B, d.E, d.D, device_num_sms()); g2.out = ws.g; g2.ldo = d.E;
     SFB_PROPAGATE(launch_gemm(g2, st));
-    ScoringParams sp{all_u_t, ws.g, ws.tp, wsc->b_a, wsc->w_out, wsc->b_out, logit, B, A, d.E, d.D};
+    ScoringParams sp{all_u_t, ws.g, ws.tp, wsc->b_a, wsc->b_out, logit, B, A, d.E, d.D};
     SFB_PROPAGATE(launch_action_scoring(sp, st));
   }
   return 0;
@@ -394,7 +441,8 @@ int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t
       p.addend = xp + (size_t)t * 4 * Hd; p.ld_addend = (long long)maxlen * 4 * Hd;
       p.lengths = lengths; p.t = t;
       p.seq_out = ctx + (size_t)t * H + dir * Hd; p.ld_seq_out = (long long)maxlen * H;
-      SFB_PROPAGATE(launch_gemm(r, st));
+      if (!g_disable_tc && gemm_tc_supported(r)) SFB_PROPAGATE(launch_gemm_tc(r, st, ws.tc, ws.tc_bytes));
+      else SFB_PROPAGATE(launch_gemm(r, st));
       cur[dir] ^= 1;
     }
   }
@@ -434,9 +482,9 @@ int32_t sfb_speaker_encoder_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
   SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SFB_PROPAGATE(visual_query(d, *w, B, h0, ws.tv, ws.q, st));
-  SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, nullptr, st));
+  SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, nullptr, ws.av, ws.av_bytes, st));
   return lstm_cell(d.E, d.F, d.H, w->lstm_w_ih, w->lstm_w_hh, w->lstm_b_ih, w->lstm_b_hh, B, action_embedding, nullptr,
-                   ws.feat, h0, c0, drop_x, nullptr, ws.gates_act, h1, c1, nullptr, st);
+                   ws.feat, h0, c0, drop_x, nullptr, ws.gates_act, h1, c1, nullptr, ws.tc, ws.tc_bytes, st);
 }
 
 int32_t sfb_speaker_decoder_step_fwd(const sfb_speaker_decoder_weights* w, int32_t H, int32_t Ew, int32_t vocab,
@@ -447,14 +495,14 @@ int32_t sfb_speaker_decoder_step_fwd(const sfb_speaker_decoder_weights* w, int32
   reset_launch_count();
   SFB_CHECK_ARG(w && prev_word && h0 && c0 && ctx && h1 && c1 && logit, "NULL argument");
   SFB_CHECK_ARG(H >= 4 && (H % 4) == 0 && Ew >= 4 && (Ew % 4) == 0 && vocab >= 1 && B >= 1 && T >= 1, "bad sizes");
-  SpkDecWs ws = carve_spkdec(H, Ew, B, workspace);
+  SpkDecWs ws = carve_spkdec(H, Ew, B, T, workspace);
   SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // model.py:497-503,515: LSTMCell(embedding(previous_word)) — the lookup is a row indirection of the A operand
   SFB_PROPAGATE(lstm_cell(Ew, 0, H, w->lstm_w_ih, w->lstm_w_hh, w->lstm_b_ih, w->lstm_b_hh, B, w->embedding, prev_word,
-                          nullptr, h0, c0, drop_e, drop_h, ws.gates_act, h1, c1, ws.h1d, st));
+                          nullptr, h0, c0, drop_e, drop_h, ws.gates_act, h1, c1, ws.h1d, ws.tc, ws.tc_bytes, st));
   // model.py:516-517
-  SFB_PROPAGATE(soft_dot(H, w->attn, B, T, ws.h1d, ctx, ctx_mask, ws.t, ws.wc, ws.htilde, alpha, st));
+  SFB_PROPAGATE(soft_dot(H, w->attn, B, T, ws.h1d, ctx, ctx_mask, ws.t, ws.wc, ws.htilde, alpha, ws.at, ws.at_bytes, st));
   // model.py:518  logit = decoder2action(h_tilde)
   GemmParams g{};
   g.nseg = 1;

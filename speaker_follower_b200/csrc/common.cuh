@@ -191,6 +191,16 @@ __device__ __forceinline__ float4 dsmem_ld_f32x4(uint32_t addr) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- step trace (bring-up): slot = {entry, after PDL wait, exit} of block 0 / thread 0, in globaltimer ns
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_mark(unsigned long long* slot, int which) {
+  if (slot && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) slot[which] = globaltimer_ns();
+}
+
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 #endif  // __CUDACC__

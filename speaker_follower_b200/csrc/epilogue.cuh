@@ -41,6 +41,7 @@ __device__ __forceinline__ void plain_store(const GemmParams& p, int m, int n, f
   if (p.bias0) v += __ldg(p.bias0 + n);
   if (p.bias1) v += __ldg(p.bias1 + n);
   if (p.act == 1) v = tanhf(v);
+  if (p.oscale) v *= __ldg(p.oscale + n);
   p.out[(size_t)m * p.ldo + n] = v;
 }
 

@@ -3,33 +3,45 @@
 // M is the batch (<= a few hundred rows), the weights are streamed once.  K may be the concatenation of
 // up to three segments with their own activation/weight pointers, which is how cat(u_prev, feature)
 // (model.py:391) and the two addmm's of nn.LSTMCell (model.py:393) run as ONE pass without materialising
-// the concatenation.  Dropout keep-masks (model.py:392,394) are applied while the A tile is loaded, an
+// the concatenation.  Dropout keep-masks (model.py:392,394) are applied while the A tile is read, an
 // embedding lookup (model.py:497) is an optional row indirection.
 //
 // B200 mapping: these GEMMs are tiny (<= 2.2 MB of weights) and sit on the step's dependency chain, so the
-// goal is latency: a 128x32 output tile is split along K over the CTAs of a thread-block CLUSTER (up to 8),
-// each CTA does a few 32-wide K chunks, and the partial tiles are reduced through distributed shared
-// memory in a fixed order (deterministic, no atomics, no second kernel).  The epilogue is either
-// bias + activation or — with gate-interleaved tiles — the whole LSTM cell update, so h1/c1 leave the
-// GEMM directly.
-#include "kernels.h"
+// design goal is LATENCY, i.e. as few dependent memory round trips as possible:
+//   * a 128x32 output tile is split along K over the CTAs of a thread-block CLUSTER (<= 8 CTAs);
+//   * a CTA requests ALL its K chunks at once with cp.async (weights before the PDL dependency wait,
+//     activations after), waits once, and runs the FFMA loop out of shared memory without further syncs;
+//   * partial tiles are PUSHED into the owner CTA's shared memory (st.shared::cluster) and reduced there in
+//     rank order after a single cluster barrier (deterministic, no atomics, no second kernel);
+//   * the epilogue is bias + activation or — with gate-interleaved tiles — the whole LSTM cell update.
 #include "epilogue.cuh"
+#include "kernels.h"
 
 namespace sfb {
 
 namespace {
 constexpr int BN = 32, BK = 32, SA = 36, SB = 36, SR = 33;
+constexpr int MAXC = 4;   // K chunks resident in shared memory per pass
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;   // src-size 0 -> the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 }  // namespace
 
-// grid = (N tiles, splitk, M tiles); cluster = (1, splitk, 1)
-template <int TM, bool KN>
+// grid = (N tiles, splitk, M tiles); cluster = (1, splitk, 1); dynamic smem = MAXC*(As+Bs) [+ scale tiles] + recv
+template <int TM, bool KN, bool HAS_XS>
 __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
   constexpr int BM = 32 * TM;
-  __shared__ __align__(16) float As[BM * SA];   // re-used as the [BM][SR] partial tile for the cluster reduction
-  __shared__ __align__(16) float Bs[32 * SB];
+  extern __shared__ __align__(16) float dsm[];
+  float* As = dsm;                                   // [MAXC][BM][SA]
+  float* Bs = As + MAXC * BM * SA;                   // [MAXC][32][SB]
+  float* Xs = Bs + MAXC * 32 * SB;                   // [MAXC][BM][SA] dropout scale tiles (HAS_XS only)
+  float* recv = Xs + (HAS_XS ? MAXC * BM * SA : 0);  // [S][rows_per][SR] partial rows pushed by the cluster peers
 
   const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
   const int m0 = blockIdx.z * BM, n0 = blockIdx.x * BN;
@@ -47,12 +59,11 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  float4 pa[TM], pb;
   // weight row of local tile column `ty` (gate-interleaved for the LSTM epilogue: col = gate*8 + unit)
   const int wrow = lstm ? (ty >> 3) * p.lstm.H + blockIdx.x * 8 + (ty & 7) : n0 + ty;
   const bool wrow_ok = lstm ? (blockIdx.x * 8 + (ty & 7)) < p.lstm.H : wrow < p.N;
 
-  auto load_chunk = [&](int c, bool do_a, bool do_b) {
+  auto locate = [&](int c, int& kofs) -> const GemmSeg& {
     int s = 0, cc = c;
     while (s + 1 < p.nseg) {
       const int n = (p.seg[s].k + BK - 1) / BK;
@@ -60,82 +71,105 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
       cc -= n;
       ++s;
     }
-    const GemmSeg& g = p.seg[s];
-    const int kofs = cc * BK;
-    if (do_a) {
+    kofs = cc * BK;
+    return p.seg[s];
+  };
+  // request the weight / activation tile of chunk c into slot `slot` (16-byte cp.async, zero-filled out of range)
+  auto request_b = [&](int c, int slot) {
+    int kofs;
+    const GemmSeg& g = locate(c, kofs);
+    float* dst = Bs + slot * 32 * SB + ty * SB + tx * 4;
+    if (!KN) {
       const int kk = kofs + tx * 4;
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        const int m = m0 + ty + 32 * i;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < p.M && kk < g.k) {
-          const int xr = g.xrow ? g.xrow[m] : m;
-          v = *reinterpret_cast<const float4*>(g.x + (size_t)xr * g.ldx + kk);
-          if (g.xs) {
-            const float4 sc = ldg4(g.xs + (size_t)m * g.ldxs + kk);
-            v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
-          }
-        }
-        pa[i] = v;
-      }
+      const bool ok = wrow_ok && kk < g.k;
+      cp_async16(dst, ok ? g.w + (size_t)wrow * g.ldw + kk : g.w, ok);
+    } else {
+      const int kk = kofs + ty, nn = n0 + tx * 4;
+      const bool ok = kk < g.k && nn < p.N;
+      cp_async16(dst, ok ? g.w + (size_t)kk * g.ldw + nn : g.w, ok);
     }
-    if (do_b) {
-      pb = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (!KN) {
-        const int kk = kofs + tx * 4;
-        if (wrow_ok && kk < g.k) pb = ldg4(g.w + (size_t)wrow * g.ldw + kk);
-      } else {
-        const int kk = kofs + ty, nn = n0 + tx * 4;
-        if (kk < g.k && nn < p.N) pb = ldg4(g.w + (size_t)kk * g.ldw + nn);
+  };
+  auto request_a = [&](int c, int slot) {
+    int kofs;
+    const GemmSeg& g = locate(c, kofs);
+    const int kk = kofs + tx * 4;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int m = m0 + ty + 32 * i;
+      const bool ok = m < p.M && kk < g.k;
+      const int xr = ok ? (g.xrow ? g.xrow[m] : m) : 0;
+      cp_async16(As + slot * BM * SA + (ty + 32 * i) * SA + tx * 4, ok ? g.x + (size_t)xr * g.ldx + kk : g.x, ok);
+      if (HAS_XS) {
+        float* xd = Xs + slot * BM * SA + (ty + 32 * i) * SA + tx * 4;
+        if (g.xs) cp_async16(xd, ok ? g.xs + (size_t)m * g.ldxs + kk : g.xs, ok);
+        else *reinterpret_cast<float4*>(xd) = make_float4(1.f, 1.f, 1.f, 1.f);
       }
     }
   };
 
-  // PDL: weights are step inputs -> fetch the first weight chunk while the producer of the activations still runs
+  trace_mark(p.trace, 0);
   pdl_launch_dependents();
-  if (c_begin < c_end) load_chunk(c_begin, false, true);
+  // PDL: weights are step inputs -> all weight chunks of the first pass are in flight before the dependency wait
+  const int first = min(MAXC, c_end - c_begin);
+  for (int k = 0; k < first; ++k) request_b(c_begin + k, k);
   pdl_wait();
-  if (c_begin < c_end) load_chunk(c_begin, true, false);
-  for (int c = c_begin; c < c_end; ++c) {
-#pragma unroll
-    for (int i = 0; i < TM; ++i) *reinterpret_cast<float4*>(&As[(ty + 32 * i) * SA + tx * 4]) = pa[i];
-    *reinterpret_cast<float4*>(&Bs[ty * SB + tx * 4]) = pb;
+  trace_mark(p.trace, 1);
+
+  for (int c0 = c_begin; c0 < c_end; c0 += MAXC) {
+    const int nc = min(MAXC, c_end - c0);
+    if (c0 > c_begin) {
+      __syncthreads();   // previous pass fully consumed
+      for (int k = 0; k < nc; ++k) request_b(c0 + k, k);
+    }
+    for (int k = 0; k < nc; ++k) request_a(c0 + k, k);
+    cp_async_wait_all();
     __syncthreads();
-    if (c + 1 < c_end) load_chunk(c + 1, true, true);
+    trace_mark(p.trace, 4);
+    for (int k = 0; k < nc; ++k) {
+      const float* Ak = As + k * BM * SA;
+      const float* Bk = Bs + k * 32 * SB;
+      const float* Xk = Xs + k * BM * SA;
 #pragma unroll
-    for (int k4 = 0; k4 < BK / 4; ++k4) {
-      float4 a[TM];
+      for (int k4 = 0; k4 < BK / 4; ++k4) {
+        float4 a[TM];
 #pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(&As[(ty + 32 * i) * SA + k4 * 4]);
-      if (!KN) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b = *reinterpret_cast<const float4*>(&Bs[(tx + 8 * j) * SB + k4 * 4]);
-#pragma unroll
-          for (int i = 0; i < TM; ++i) {
-            acc[i][j] = fmaf(a[i].x, b.x, acc[i][j]);
-            acc[i][j] = fmaf(a[i].y, b.y, acc[i][j]);
-            acc[i][j] = fmaf(a[i].z, b.z, acc[i][j]);
-            acc[i][j] = fmaf(a[i].w, b.w, acc[i][j]);
+        for (int i = 0; i < TM; ++i) {
+          a[i] = *reinterpret_cast<const float4*>(&Ak[(ty + 32 * i) * SA + k4 * 4]);
+          if (HAS_XS) {
+            const float4 sc = *reinterpret_cast<const float4*>(&Xk[(ty + 32 * i) * SA + k4 * 4]);
+            a[i].x *= sc.x; a[i].y *= sc.y; a[i].z *= sc.z; a[i].w *= sc.w;
           }
         }
-      } else {
+        if (!KN) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const float4 b = *reinterpret_cast<const float4*>(&Bs[(k4 * 4 + kk) * SB + tx * 4]);
+          for (int j = 0; j < 4; ++j) {
+            const float4 b = *reinterpret_cast<const float4*>(&Bk[(tx + 8 * j) * SB + k4 * 4]);
 #pragma unroll
-          for (int i = 0; i < TM; ++i) {
-            const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
-            acc[i][0] = fmaf(av, b.x, acc[i][0]);
-            acc[i][1] = fmaf(av, b.y, acc[i][1]);
-            acc[i][2] = fmaf(av, b.z, acc[i][2]);
-            acc[i][3] = fmaf(av, b.w, acc[i][3]);
+            for (int i = 0; i < TM; ++i) {
+              acc[i][j] = fmaf(a[i].x, b.x, acc[i][j]);
+              acc[i][j] = fmaf(a[i].y, b.y, acc[i][j]);
+              acc[i][j] = fmaf(a[i].z, b.z, acc[i][j]);
+              acc[i][j] = fmaf(a[i].w, b.w, acc[i][j]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const float4 b = *reinterpret_cast<const float4*>(&Bk[(k4 * 4 + kk) * SB + tx * 4]);
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+              const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+              acc[i][0] = fmaf(av, b.x, acc[i][0]);
+              acc[i][1] = fmaf(av, b.y, acc[i][1]);
+              acc[i][2] = fmaf(av, b.z, acc[i][2]);
+              acc[i][3] = fmaf(av, b.w, acc[i][3]);
+            }
           }
         }
       }
     }
-    __syncthreads();
   }
+  trace_mark(p.trace, 5);
 
   // local tile column of accumulator j of this thread
   auto col_of = [&](int j) { return KN ? tx * 4 + j : tx + 8 * j; };
@@ -156,53 +190,60 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
         }
       }
     }
+    trace_mark(p.trace, 2);
     return;
   }
 
-  // ---- split-K: partial tile -> shared memory, reduce across the cluster through DSMEM in rank order
-  float* red = As;   // [BM][SR]
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) red[(ty + 32 * i) * SR + col_of(j)] = acc[i][j];
-  cluster_sync_all();
+  // ---- split-K: push every partial row to the CTA that owns it, one cluster barrier, reduce locally in rank order
+  const int rows_per = (BM + S - 1) / S;
   {
-    const int rows_per = (BM + S - 1) / S;
-    const int rbeg = rank * rows_per, rend = min(BM, rbeg + rows_per);
     uint32_t peer[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) peer[k] = k < S ? dsmem_addr(red, k) : 0u;
+    for (int k = 0; k < 8; ++k) peer[k] = k < S ? dsmem_addr(recv, k) : 0u;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int r = ty + 32 * i, owner = r / rows_per, lr = r - owner * rows_per;
+      const uint32_t base = peer[owner] + (uint32_t)((rank * rows_per + lr) * SR) * 4u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st_cluster_f32(base + (uint32_t)col_of(j) * 4u, acc[i][j]);
+    }
+  }
+  trace_mark(p.trace, 6);
+  cluster_sync_all();   // release/acquire: the pushed rows are visible to their owner
+  trace_mark(p.trace, 7);
+  {
+    const int rbeg = rank * rows_per, rend = min(BM, rbeg + rows_per);
     if (lstm) {
       // one thread per (row, unit): the 4 gate columns unit, 8+unit, 16+unit, 24+unit
       for (int e = tid; e < (rend - rbeg) * 8; e += 256) {
-        const int r = rbeg + (e >> 3), unit_l = e & 7;
-        const int m = m0 + r, unit = blockIdx.x * 8 + unit_l;
+        const int lr = e >> 3, unit_l = e & 7;
+        const int m = m0 + rbeg + lr, unit = blockIdx.x * 8 + unit_l;
         if (m >= p.M || unit >= p.lstm.H) continue;
         float g4[4] = {0.f, 0.f, 0.f, 0.f};
         for (int k = 0; k < S; ++k)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) g4[q] += dsmem_ld_f32(peer[k] + (uint32_t)(r * SR + q * 8 + unit_l) * 4u);
+          for (int q = 0; q < 4; ++q) g4[q] += recv[(k * rows_per + lr) * SR + q * 8 + unit_l];
         lstm_update(p, m, unit, g4[0], g4[1], g4[2], g4[3]);
       }
     } else {
       for (int e = tid; e < (rend - rbeg) * BN; e += 256) {
-        const int r = rbeg + (e >> 5), cn = e & 31;
-        const int m = m0 + r, n = n0 + cn;
+        const int lr = e >> 5, cn = e & 31;
+        const int m = m0 + rbeg + lr, n = n0 + cn;
         if (m >= p.M || n >= p.N) continue;
         float v = 0.f;
-        for (int k = 0; k < S; ++k) v += dsmem_ld_f32(peer[k] + (uint32_t)(r * SR + cn) * 4u);
+        for (int k = 0; k < S; ++k) v += recv[(k * rows_per + lr) * SR + cn];
         plain_store(p, m, n, v);
       }
     }
   }
-  cluster_sync_all();   // peers may still be reading this CTA's partial tile
+  trace_mark(p.trace, 2);
 }
 
 int gemm_pick_splitk(int M, int N, int ktotal, int num_sms) {
   const int bm = M <= 32 ? 32 : 128;
   const int tiles = ((N + BN - 1) / BN) * ((M + bm - 1) / bm);
   const int nch = (ktotal + BK - 1) / BK;
-  int want = (2 * num_sms + tiles - 1) / tiles;   // aim at ~2 CTAs per SM
+  int want = (num_sms + tiles - 1) / tiles;       // aim at one CTA per SM: the SM's FFMA pipe is the limit
   int s = 1;
   while (s * 2 <= want && s * 2 <= 8 && nch / (s * 2) >= 2) s *= 2;
   return s;
@@ -210,14 +251,26 @@ int gemm_pick_splitk(int M, int N, int ktotal, int num_sms) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <int TM, bool KN>
+template <int TM, bool KN, bool HAS_XS>
 static int32_t launch_t(const GemmParams& p, dim3 grid, cudaStream_t stream) {
-  SFB_CHECK_CUDA(launch_ex(gemm_skinny_kernel<TM, KN>, grid, dim3(256, 1, 1), 0, stream, dim3(1, p.splitk, 1), p));
+  constexpr int BM = 32 * TM;
+  const int rows_per = (BM + p.splitk - 1) / p.splitk;
+  const size_t tiles = ((size_t)MAXC * (BM * SA + 32 * SB) + (HAS_XS ? (size_t)MAXC * BM * SA : 0)) * sizeof(float);
+  const size_t smem = tiles + (size_t)p.splitk * rows_per * SR * sizeof(float);
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    const size_t mx = tiles + (size_t)(BM + 8) * SR * sizeof(float);
+    SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<TM, KN, HAS_XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+    configured = true;
+  }
+  SFB_CHECK_CUDA(launch_ex(gemm_skinny_kernel<TM, KN, HAS_XS>, grid, dim3(256, 1, 1), smem, stream, dim3(1, p.splitk, 1), p));
   count_launch();
   return 0;
 }
 
-int32_t launch_gemm(const GemmParams& p, cudaStream_t stream) {
+int32_t launch_gemm(const GemmParams& p_in, cudaStream_t stream) {
+  GemmParams p = p_in;
+  p.trace = next_trace_slot();
   SFB_CHECK_ARG(p.nseg >= 1 && p.nseg <= 3, "gemm: 1..3 K segments");
   SFB_CHECK_ARG(p.M >= 1 && p.N >= 1, "gemm: bad sizes");
   SFB_CHECK_ARG(p.splitk == 1 || p.splitk == 2 || p.splitk == 4 || p.splitk == 8, "gemm: splitk must be 1, 2, 4 or 8");
@@ -225,8 +278,10 @@ int32_t launch_gemm(const GemmParams& p, cudaStream_t stream) {
   const bool lstm = p.lstm.H > 0;
   SFB_CHECK_ARG(!lstm || (!kn && p.N == 4 * p.lstm.H && (p.lstm.H % 8) == 0), "gemm: LSTM epilogue needs [4H,K] weights, H % 8 == 0");
   SFB_CHECK_ARG(lstm || p.out, "gemm: output is NULL");
+  bool has_xs = false;
   for (int s = 0; s < p.nseg; ++s) {
     const GemmSeg& g = p.seg[s];
+    has_xs |= g.xs != nullptr;
     SFB_CHECK_ARG(g.w_kn == kn, "gemm: mixed weight layouts");
     SFB_CHECK_ARG(g.k >= 4 && (g.k % 4) == 0, "gemm: K segment must be a multiple of 4");
     SFB_CHECK_ARG(g.x && g.w && aligned16(g.x) && aligned16(g.w) && (g.ldx % 4) == 0 && (g.ldw % 4) == 0,
@@ -236,8 +291,12 @@ int32_t launch_gemm(const GemmParams& p, cudaStream_t stream) {
   }
   const int tm = p.M <= 32 ? 1 : 4;
   dim3 grid((p.N + BN - 1) / BN, p.splitk, (p.M + 32 * tm - 1) / (32 * tm));
-  if (tm == 1) return kn ? launch_t<1, true>(p, grid, stream) : launch_t<1, false>(p, grid, stream);
-  return kn ? launch_t<4, true>(p, grid, stream) : launch_t<4, false>(p, grid, stream);
+  if (tm == 1) {
+    if (has_xs) return kn ? launch_t<1, true, true>(p, grid, stream) : launch_t<1, false, true>(p, grid, stream);
+    return kn ? launch_t<1, true, false>(p, grid, stream) : launch_t<1, false, false>(p, grid, stream);
+  }
+  if (has_xs) return kn ? launch_t<4, true, true>(p, grid, stream) : launch_t<4, false, true>(p, grid, stream);
+  return kn ? launch_t<4, true, false>(p, grid, stream) : launch_t<4, false, false>(p, grid, stream);
 }
 
 }  // namespace sfb

@@ -11,12 +11,14 @@
 // Mapping (one CTA = one UMMA tile):
 //   UMMA M = 128 weight rows = 4 gates x 32 hidden units (gate-interleaved, so the epilogue owns whole cells),
 //   UMMA N = batch rounded up to 16 (<= 256), UMMA K = 16 per instruction, 64 per pipeline stage.
-//   K is split over the CTAs of a thread-block cluster (<= 8); partial accumulators go TMEM -> registers ->
-//   shared memory and are reduced across the cluster through DSMEM in rank order (deterministic), then the
-//   LSTM cell update runs in the same kernel and writes h1 / c1.
-//   Operand staging: all 8 warps load fp32 with coalesced 128-bit loads (next stage prefetched in registers),
-//   split, and store bf16 core matrices (8 rows x 16 B, no swizzle, K-major); one thread issues the MMAs and
-//   commits them to the stage's mbarrier, which is what frees the stage for re-use (3-stage ring).
+//   K is split over S CTAs per tile so that tiles x S ~ number of SMs (16 x 9 = 144 on a B200), all resident in
+//   ONE wave.  Partial accumulators go TMEM -> registers -> an L2-resident partial buffer; the S CTAs of a tile
+//   meet at a self-resetting semaphore (they are co-resident: grid <= #SMs, 1 CTA/SM) and each reduces its share
+//   in split order (deterministic) and runs the LSTM cell update, so h1 / c1 leave this kernel.
+//   Warp roles: warps 0-7 are producers (coalesced 128-bit fp32 loads, next block prefetched into a second
+//   register set, bf16 hi/lo split, 8x16B core matrices, no swizzle, K-major, fence.proxy.async, arrive on the
+//   stage's "full" mbarrier); warp 8 issues the tcgen05.mma's and commits them to the stage's "empty" mbarrier
+//   (3-stage ring).  Producers never wait for the issuer.
 #include <cuda_bf16.h>
 
 #include "epilogue.cuh"
@@ -91,32 +93,35 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 
 }  // namespace
 
-// grid = (4H/128, S, batch tiles), cluster (1, S, 1), 256 threads, dynamic smem
-// HAS_XS: some K segment carries a dropout keep-mask (training); kept out of the eval instantiation so the
-// prefetch loads have no consumer until the conversion phase (a predicated-off FMUL still waits on its inputs).
+// grid = (4H/128, S, batch tiles), 288 threads (8 producer warps + 1 MMA-issuer warp), dynamic smem
 template <bool HAS_XS>
-__global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p, const int NB, const int STAGES,
-                                                             const int rows_per_z, const int dbg) {
+__global__ void __launch_bounds__(288, 1) gemm_tc_lstm_kernel(const GemmParams p, const int NB, const int rows_per_z,
+                                                             float* __restrict__ partial, unsigned int* sem,
+                                                             const int dbg) {
+  constexpr int STAGES = 3;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x, S = p.splitk, rank = blockIdx.y;
+  const int tile = blockIdx.x, S = gridDim.y, rank = blockIdx.y, tiles = gridDim.x;
   const int H = p.lstm.H;
   const int m0 = blockIdx.z * rows_per_z, m_end = min(p.M, m0 + rows_per_z);   // batch rows of this CTA
 
   const uint32_t a_bytes = (TBM / 8) * SBO;          // 16 KB per (hi|lo) A tile
   const uint32_t b_bytes = (uint32_t)(NB / 8) * SBO;  // per (hi|lo) B tile
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  unsigned char* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes);   // [STAGES] empty + [1] done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + STAGES + 1);
-  const int NBS = NB + 4;
-  float* part = reinterpret_cast<float*>(smem);       // [128][NBS], aliases the stages after the last MMA
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes);   // [STAGES] producers -> issuer
+  uint64_t* empty = full + STAGES;                                                     // [STAGES] tensor core -> producers
+  uint64_t* done = empty + STAGES;                                                     // [1] all MMAs retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   // ---- one-time setup: barriers, TMEM allocation (warp 0), visible to everyone after the sync
   const uint32_t tmem_cols = NB <= 32 ? 32 : NB <= 64 ? 64 : NB <= 128 ? 128 : 256;
   if (warp == 0) {
     if (lane == 0) {
-      for (int s = 0; s <= STAGES; ++s) mbar_init(&bars[s], 1);
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full[s], 256);
+        mbar_init(&empty[s], 1);
+      }
+      mbar_init(done, 1);
       mbar_fence_init();
     }
     __syncwarp();
@@ -136,131 +141,154 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p
   for (int s = 0; s < p.nseg; ++s) nblk += (p.seg[s].k + TBK - 1) / TBK;
   const int per = (nblk + S - 1) / S;
   const int b_begin = rank * per, b_end = min(nblk, b_begin + per);
+  const int nit = max(0, b_end - b_begin);
 
-  // per-thread staging coordinates: warp-unit wu = warp + 8*i -> (row group, K half); lane -> (row in group, core)
-  const int r_in = lane & 7, kc_in = lane >> 3;
-  float4 ra[4][2], rb[4][2], rs[HAS_XS ? 4 : 1][2];
-
-  auto load_block = [&](int blk, bool do_a, bool do_b) {
-    int s = 0, cc = blk;
-    while (s + 1 < p.nseg) {
-      const int n = (p.seg[s].k + TBK - 1) / TBK;
-      if (cc < n) break;
-      cc -= n;
-      ++s;
-    }
-    const GemmSeg& g = p.seg[s];
-    const int kofs = cc * TBK;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int wu = warp + 8 * i;
-      const int rg = wu >> 1, k = kofs + ((wu & 1) * 4 + kc_in) * 8;
-      // A operand: weight rows, gate-interleaved: tile row = gate*32 + unit_local
-      if (do_a) {
-        const int row = rg * 8 + r_in;
-        const int wrow = (row >> 5) * H + tile * 32 + (row & 31);
-        if (k < g.k) {
-          const float* src = g.w + (size_t)wrow * g.ldw + k;
-          ra[i][0] = ldg4(src);
-          ra[i][1] = ldg4(src + 4);
-        } else {
-          ra[i][0] = ra[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      // B operand: activations (batch rows), optional row indirection and dropout scale
-      if (do_b) {
-        const int m = m0 + rg * 8 + r_in;
-        if (rg * 8 < NB && m < m_end && k < g.k) {
-          const int xr = g.xrow ? g.xrow[m] : m;
-          const float* src = g.x + (size_t)xr * g.ldx + k;
-          rb[i][0] = *reinterpret_cast<const float4*>(src);       // produced by the previous kernel: coherent loads
-          rb[i][1] = *reinterpret_cast<const float4*>(src + 4);
-          if (HAS_XS) {
-            if (g.xs) {
-              const float* sp = g.xs + (size_t)m * g.ldxs + k;
-              rs[i][0] = ldg4(sp);
-              rs[i][1] = ldg4(sp + 4);
-            } else {
-              rs[i][0] = rs[i][1] = make_float4(1.f, 1.f, 1.f, 1.f);
-            }
-          }
-        } else {
-          rb[i][0] = rb[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (HAS_XS) rs[i][0] = rs[i][1] = make_float4(1.f, 1.f, 1.f, 1.f);
-        }
-      }
-    }
-  };
-
-  // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=NB
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-
-  // PDL: weights are step inputs -> first weight block is in flight before the activations' producer has finished
+  trace_mark(p.trace, 0);
   pdl_launch_dependents();
-  if (b_begin < b_end) load_block(b_begin, true, false);
-  pdl_wait();
-  TS(1);
-  if (b_begin < b_end) load_block(b_begin, false, true);
-  for (int blk = b_begin; blk < b_end; ++blk) {
-    const int it = blk - b_begin, s = it % STAGES, use = it / STAGES;
-    TS(8 + it * 8 + 0);
-    if (use >= 1) mbar_wait_bounded(&bars[s], (uint32_t)(use - 1) & 1u);   // MMAs that read this stage are done
-    TS(8 + it * 8 + 1);
-    unsigned char* st = stage_base + (size_t)s * stage_bytes;
+
+  if (warp < 8) {
+    // =============================== producers ===============================
+    const int r_in = lane & 7, kc_in = lane >> 3;
+    float4 ra[2][4][2], rb[2][4][2], rs[HAS_XS ? 2 : 1][HAS_XS ? 4 : 1][2];
+
+    auto load_block = [&](int blk, int set, bool do_a, bool do_b) {
+      int s = 0, cc = blk;
+      while (s + 1 < p.nseg) {
+        const int n = (p.seg[s].k + TBK - 1) / TBK;
+        if (cc < n) break;
+        cc -= n;
+        ++s;
+      }
+      const GemmSeg& g = p.seg[s];
+      const int kofs = cc * TBK;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int wu = warp + 8 * i;
-      const uint32_t off = (uint32_t)(wu >> 1) * SBO + (uint32_t)((wu & 1) * 4 + kc_in) * CORE + (uint32_t)r_in * 16u;
-      uint4 hi, lo;
-      split8(ra[i][0], ra[i][1], hi, lo);
-      *reinterpret_cast<uint4*>(st + off) = hi;
-      *reinterpret_cast<uint4*>(st + a_bytes + off) = lo;
-      if ((wu >> 1) * 8 < NB) {
-        if (HAS_XS) {
-          rb[i][0].x *= rs[i][0].x; rb[i][0].y *= rs[i][0].y; rb[i][0].z *= rs[i][0].z; rb[i][0].w *= rs[i][0].w;
-          rb[i][1].x *= rs[i][1].x; rb[i][1].y *= rs[i][1].y; rb[i][1].z *= rs[i][1].z; rb[i][1].w *= rs[i][1].w;
+      for (int i = 0; i < 4; ++i) {
+        const int wu = warp + 8 * i;
+        const int rg = wu >> 1, k = kofs + ((wu & 1) * 4 + kc_in) * 8;
+        if (do_a) {   // weight rows, gate-interleaved: tile row = gate*32 + unit_local
+          const int row = rg * 8 + r_in;
+          const int wrow = (row >> 5) * H + tile * 32 + (row & 31);
+          if (k < g.k) {
+            const float* src = g.w + (size_t)wrow * g.ldw + k;
+            ra[set][i][0] = ldg4(src);
+            ra[set][i][1] = ldg4(src + 4);
+          } else {
+            ra[set][i][0] = ra[set][i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
-        split8(rb[i][0], rb[i][1], hi, lo);
-        *reinterpret_cast<uint4*>(st + 2 * a_bytes + off) = hi;
-        *reinterpret_cast<uint4*>(st + 2 * a_bytes + b_bytes + off) = lo;
+        if (do_b) {   // activations (batch rows), optional row indirection; dropout scale kept separate
+          const int m = m0 + rg * 8 + r_in;
+          if (rg * 8 < NB && m < m_end && k < g.k) {
+            const int xr = g.xrow ? g.xrow[m] : m;
+            const float* src = g.x + (size_t)xr * g.ldx + k;
+            rb[set][i][0] = *reinterpret_cast<const float4*>(src);   // produced by the previous kernel: coherent loads
+            rb[set][i][1] = *reinterpret_cast<const float4*>(src + 4);
+            if (HAS_XS) {
+              if (g.xs) {
+                const float* sp = g.xs + (size_t)m * g.ldxs + k;
+                rs[set][i][0] = ldg4(sp);
+                rs[set][i][1] = ldg4(sp + 4);
+              } else {
+                rs[set][i][0] = rs[set][i][1] = make_float4(1.f, 1.f, 1.f, 1.f);
+              }
+            }
+          } else {
+            rb[set][i][0] = rb[set][i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HAS_XS) rs[set][i][0] = rs[set][i][1] = make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+        }
       }
-    }
-    TS(8 + it * 8 + 2);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-    __syncthreads();
-    TS(8 + it * 8 + 3);
-    if (blk + 1 < b_end) load_block(blk + 1, true, true);         // next stage's global loads fly during the MMAs
-    TS(8 + it * 8 + 4);
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + a_bytes, b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
+    };
+
+    // PDL: weights are step inputs -> the first weight block is in flight before the activations' producer is done
+    if (nit > 0) load_block(b_begin, 0, true, false);
+    pdl_wait();
+    trace_mark(p.trace, 1);
+    TS(1);
+    if (nit > 0) load_block(b_begin, 0, false, true);
+
+    for (int it0 = 0; it0 < nit; it0 += 2) {
 #pragma unroll
-      for (int j = 0; j < TBK / 16; ++j) {
-        const uint32_t ko = (uint32_t)j * 2u * CORE;   // 16 K elements = 2 core matrices
-        const uint64_t dah = make_desc(a_hi + ko, dbg), dal = make_desc(a_lo + ko, dbg);
-        const uint64_t dbh = make_desc(b_hi + ko, dbg), dbl = make_desc(b_lo + ko, dbg);
-        umma_bf16(tmem_d, dah, dbh, idesc, (it > 0 || j > 0) ? 1u : 0u);
-        umma_bf16(tmem_d, dah, dbl, idesc, 1u);
-        umma_bf16(tmem_d, dal, dbh, idesc, 1u);
+      for (int u = 0; u < 2; ++u) {
+        const int it = it0 + u;
+        if (it >= nit) break;
+        const int s = it % STAGES, use = it / STAGES;
+        if (it + 1 < nit) load_block(b_begin + it + 1, u ^ 1, true, true);   // next block's loads fly during this convert
+        TS(8 + it * 8 + 0);
+        if (use >= 1) mbar_wait_bounded(&empty[s], (uint32_t)(use - 1) & 1u);  // MMAs that read this stage retired
+        TS(8 + it * 8 + 1);
+        unsigned char* st = smem + (size_t)s * stage_bytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int wu = warp + 8 * i;
+          const uint32_t off = (uint32_t)(wu >> 1) * SBO + (uint32_t)((wu & 1) * 4 + kc_in) * CORE + (uint32_t)r_in * 16u;
+          uint4 hi, lo;
+          split8(ra[u][i][0], ra[u][i][1], hi, lo);
+          *reinterpret_cast<uint4*>(st + off) = hi;
+          *reinterpret_cast<uint4*>(st + a_bytes + off) = lo;
+          if ((wu >> 1) * 8 < NB) {
+            float4 b0 = rb[u][i][0], b1 = rb[u][i][1];
+            if (HAS_XS) {
+              const float4 s0 = rs[u][i][0], s1 = rs[u][i][1];
+              b0.x *= s0.x; b0.y *= s0.y; b0.z *= s0.z; b0.w *= s0.w;
+              b1.x *= s1.x; b1.y *= s1.y; b1.z *= s1.z; b1.w *= s1.w;
+            }
+            split8(b0, b1, hi, lo);
+            *reinterpret_cast<uint4*>(st + 2 * a_bytes + off) = hi;
+            *reinterpret_cast<uint4*>(st + 2 * a_bytes + b_bytes + off) = lo;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(&full[s]);
+        TS(8 + it * 8 + 2);
       }
-      umma_commit(&bars[s]);
-      if (blk + 1 == b_end) umma_commit(&bars[STAGES]);
     }
-    TS(8 + it * 8 + 5);
+  } else {
+    // =============================== MMA issuer (warp 8) ===============================
+    pdl_wait();
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=NB
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    for (int it = 0; it < nit; ++it) {
+      const int s = it % STAGES, use = it / STAGES;
+      mbar_wait_bounded(&full[s], (uint32_t)use & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + a_bytes, b_hi = a_hi + 2 * a_bytes,
+                       b_lo = b_hi + b_bytes;
+#pragma unroll
+        for (int j = 0; j < TBK / 16; ++j) {
+          const uint32_t ko = (uint32_t)j * 2u * CORE;   // 16 K elements = 2 core matrices
+          const uint64_t dah = make_desc(a_hi + ko, dbg), dal = make_desc(a_lo + ko, dbg);
+          const uint64_t dbh = make_desc(b_hi + ko, dbg), dbl = make_desc(b_lo + ko, dbg);
+          umma_bf16(tmem_d, dah, dbh, idesc, (it > 0 || j > 0) ? 1u : 0u);
+          umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+          umma_bf16(tmem_d, dal, dbh, idesc, 1u);
+        }
+        umma_commit(&empty[s]);
+        if (it + 1 == nit) umma_commit(done);
+      }
+      __syncwarp();
+    }
   }
   TS(2);
 
-  // ---- epilogue: TMEM -> registers -> shared partial tile [128][NBS]
-  if (b_begin < b_end) {
-    mbar_wait_bounded(&bars[STAGES], 0);
+  // ---- epilogue 1: TMEM -> registers -> shared [128][NB+4] -> coalesced store of this CTA's partial tile into the
+  // (L2-resident) partial buffer.  Stage memory is free: every MMA has retired when `done` flips.
+  float* mypart = partial + ((size_t)(blockIdx.z * tiles + tile) * S + rank) * (size_t)(TBM * NB);
+  const int NBS = NB + 4;
+  float* stg = reinterpret_cast<float*>(smem);
+  if (nit > 0) {
+    mbar_wait_bounded(done, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
-  if (warp < 4) {
-    float* prow = part + (size_t)(warp * 32 + lane) * NBS;
-    for (int c = 0; c < NB; c += 16) {
+  if (warp < 8) {
+    // warp w reads TMEM lanes 32*(w%4).. (hardware restriction); warps w and w+4 split the columns
+    const int lq = warp & 3, half = warp >> 2;
+    float* prow = stg + (size_t)(lq * 32 + lane) * NBS;
+    for (int c = half * 16; c < NB; c += 32) {
       uint32_t v[16];
-      if (b_begin < b_end) {
-        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
+      if (nit > 0) {
+        const uint32_t taddr = tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)c;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -276,41 +304,66 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_lstm_kernel(const GemmParams p
         *reinterpret_cast<uint4*>(prow + c + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     }
   }
-  TS(3);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  if (S > 1) cluster_sync_all(); else __syncthreads();
+  __syncthreads();
+  {
+    const int nq4 = NB >> 2;
+    for (int i = tid; i < TBM * nq4; i += 288) {
+      const int row = i / nq4, c4 = i - row * nq4;
+      __stcg(reinterpret_cast<float4*>(mypart) + i, *reinterpret_cast<const float4*>(stg + (size_t)row * NBS + c4 * 4));
+    }
+    __threadfence();
+  }
+  TS(3);
+  __syncthreads();
+
+  // ---- the S CTAs of this tile meet at a semaphore (all co-resident: grid <= #SMs at 1 CTA/SM)
+  unsigned int* my_sem = sem + 2 * (blockIdx.z * tiles + tile);
+  if (S > 1) {
+    if (tid == 0) {
+      atomicAdd(my_sem, 1u);
+      unsigned int seen = 0;
+      for (uint32_t i = 0; i < (1u << 26); ++i) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(my_sem) : "memory");
+        if (seen >= (unsigned int)S) break;
+      }
+      if (seen < (unsigned int)S) __trap();
+      __threadfence();
+    }
+    __syncthreads();
+  }
   TS(4);
 
-  // ---- reduce over the cluster (rank order) + LSTM cell update: CTA `rank` owns 32/S hidden units of the tile
+  // ---- epilogue 2: reduce the S partial tiles (split order) + LSTM cell update; one thread per (unit, batch row),
+  // consecutive threads -> consecutive batch rows (coalesced partial reads)
   {
-    const int units_per = 32 / S;
-    const int nq = NB >> 2;                       // batch quads
-    uint32_t peer[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) peer[k] = (S > 1 && k < S) ? dsmem_addr(part, k) : smem_u32(part);
-    for (int e = tid; e < units_per * nq; e += 256) {
-      const int ul = rank * units_per + e / nq, bq = e % nq;
-      float g[4][4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) g[q][0] = g[q][1] = g[q][2] = g[q][3] = 0.f;
+    const int total = 32 * NB, share = (total + S - 1) / S;
+    const int e_beg = rank * share, e_end = min(total, e_beg + share);
+    const float* tbase = partial + (size_t)(blockIdx.z * tiles + tile) * S * (size_t)(TBM * NB);
+    for (int e = e_beg + tid; e < e_end; e += 288) {
+      const int ul = e / NB, bm = e - ul * NB;
+      const int m = m0 + bm;
+      if (m >= m_end) continue;
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
       for (int k = 0; k < S; ++k) {
+        const float* pk = tbase + (size_t)k * (TBM * NB) + (size_t)ul * NB + bm;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 v = dsmem_ld_f32x4(peer[k] + (uint32_t)((q * 32 + ul) * NBS + bq * 4) * 4u);
-          g[q][0] += v.x; g[q][1] += v.y; g[q][2] += v.z; g[q][3] += v.w;
-        }
+        for (int q = 0; q < 4; ++q) g[q] += __ldcg(pk + (size_t)q * 32 * NB);
       }
-      const int unit = tile * 32 + ul;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int m = m0 + bq * 4 + j;
-        if (m < m_end) lstm_update(p, m, unit, g[0][j], g[1][j], g[2][j], g[3][j]);
-      }
+      lstm_update(p, m, tile * 32 + ul, g[0], g[1], g[2], g[3]);
     }
   }
   TS(5);
-  if (S > 1) cluster_sync_all(); else __syncthreads();   // peers may still be reading this CTA's partial tile
+  __syncthreads();
+  if (S > 1 && tid == 0) {   // last CTA to leave re-arms the semaphore for the next launch
+    const unsigned int gone = atomicAdd(my_sem + 1, 1u);
+    if (gone == (unsigned int)S - 1) {
+      atomicExch(my_sem + 1, 0u);
+      atomicExch(my_sem, 0u);
+    }
+  }
   TS(6);
+  trace_mark(p.trace, 2);
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
 }
@@ -323,12 +376,21 @@ int gemm_tc_read_timestamps(long long* out, int n) {
   return cudaMemcpyFromSymbol(out, g_tc_ts, n * sizeof(long long)) == cudaSuccess ? 0 : -1;
 }
 
-static int tc_pick_splitk(const GemmParams& p) {
-  int nblk = 0;
-  for (int s = 0; s < p.nseg; ++s) nblk += (p.seg[s].k + TBK - 1) / TBK;
-  int s = 1;
-  while (s * 2 <= 8 && nblk / (s * 2) >= 2) s *= 2;
-  return s;
+TcPlan gemm_tc_plan(int M, int H, int ktotal, int nseg, int num_sms) {
+  TcPlan pl{};
+  pl.tiles = (4 * H) / TBM;
+  pl.nz = (M + 127) / 128;                              // batch tiles of <= 128 rows (weights re-read per tile)
+  pl.rows_per_z = (M + pl.nz - 1) / pl.nz;
+  pl.NB = (pl.rows_per_z + 15) & ~15;
+  const int nblk_max = (ktotal + TBK - 1) / TBK + nseg;  // upper bound on K blocks
+  int s = num_sms / (pl.tiles * pl.nz);                 // co-residency: tiles*S*nz <= #SMs (spin semaphore)
+  if (s > nblk_max / 2) s = nblk_max / 2;
+  if (s > 16) s = 16;
+  if (s < 1) s = 1;
+  pl.S = s;
+  pl.sem_bytes = ((size_t)pl.tiles * pl.nz * 2 * sizeof(unsigned int) + 255) & ~size_t(255);
+  pl.bytes = pl.sem_bytes + (size_t)pl.tiles * pl.nz * pl.S * TBM * pl.NB * sizeof(float);
+  return pl;
 }
 
 bool gemm_tc_supported(const GemmParams& p) {
@@ -343,19 +405,18 @@ bool gemm_tc_supported(const GemmParams& p) {
   return true;
 }
 
-int32_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t stream) {
+int32_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t stream, void* ws, size_t ws_bytes) {
   SFB_CHECK_ARG(gemm_tc_supported(p_in), "gemm_tc: unsupported shape");
   GemmParams p = p_in;
-  p.splitk = tc_pick_splitk(p);
-  const int nz = (p.M + 127) / 128;                 // batch tiles of <= 128 rows (weights are re-read per tile)
-  const int rows_per_z = (p.M + nz - 1) / nz;
-  const int NB = (rows_per_z + 15) & ~15;
-  const int stages = 3;
-  const size_t stage_bytes = 2 * (size_t)(TBM / 8) * SBO + 2 * (size_t)(NB / 8) * SBO;
-  size_t smem = stages * stage_bytes + (stages + 1) * sizeof(uint64_t) + 16;
-  const size_t part_bytes = (size_t)TBM * (NB + 4) * sizeof(float);
-  if (part_bytes + 64 > smem) smem = part_bytes + 64;
-  SFB_CHECK_ARG(part_bytes <= stages * stage_bytes, "gemm_tc: partial tile does not fit the stage memory");
+  p.trace = next_trace_slot();
+  int ktotal = 0;
+  for (int s = 0; s < p.nseg; ++s) ktotal += p.seg[s].k;
+  const TcPlan pl = gemm_tc_plan(p.M, p.lstm.H, ktotal, p.nseg, device_num_sms());
+  SFB_CHECK_ARG(ws && ws_bytes >= pl.bytes && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "gemm_tc: workspace");
+  unsigned int* sem = static_cast<unsigned int*>(ws);
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + pl.sem_bytes);
+  const size_t stage_bytes = 2 * (size_t)(TBM / 8) * SBO + 2 * (size_t)(pl.NB / 8) * SBO;
+  const size_t smem = 3 * stage_bytes + 8 * sizeof(uint64_t) + 16;
   bool has_xs = false;
   for (int s = 0; s < p.nseg; ++s) has_xs |= p.seg[s].xs != nullptr;
   static size_t configured[2] = {0, 0};
@@ -364,9 +425,9 @@ int32_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t stream) {
     else SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_lstm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[has_xs] = smem;
   }
-  const dim3 grid(p.N / TBM, p.splitk, nz), cl(1, p.splitk, 1);
-  if (has_xs) SFB_CHECK_CUDA(launch_ex(gemm_tc_lstm_kernel<true>, grid, dim3(256, 1, 1), smem, stream, cl, p, NB, stages, rows_per_z, g_tc_debug));
-  else SFB_CHECK_CUDA(launch_ex(gemm_tc_lstm_kernel<false>, grid, dim3(256, 1, 1), smem, stream, cl, p, NB, stages, rows_per_z, g_tc_debug));
+  const dim3 grid(pl.tiles, pl.S, pl.nz), cl(1, 1, 1);
+  if (has_xs) SFB_CHECK_CUDA(launch_ex(gemm_tc_lstm_kernel<true>, grid, dim3(288, 1, 1), smem, stream, cl, p, pl.NB, pl.rows_per_z, partial, sem, g_tc_debug));
+  else SFB_CHECK_CUDA(launch_ex(gemm_tc_lstm_kernel<false>, grid, dim3(288, 1, 1), smem, stream, cl, p, pl.NB, pl.rows_per_z, partial, sem, g_tc_debug));
   count_launch();
   return 0;
 }

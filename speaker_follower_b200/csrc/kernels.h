@@ -17,9 +17,18 @@ struct AttnParams {
   int R, D;
   float* out;   int ldo;                  // [B, D]
   float* alpha; int ldalpha;              // [B, R] or NULL
-  int rows_per_cta;                       // filled by the launcher
+  unsigned long long* trace;              // bring-up: 3 timestamps of block 0, or NULL
+  // filled by the launcher
+  int rows_per_cta, stages;
+  float* part;                            // [B][SPLIT][D+4] partial (max, sum, weighted sum) records
+  unsigned int* ticket;                   // [B] self-resetting arrival counters (must start zeroed)
 };
-int32_t launch_soft_dot_attention(AttnParams p, int B, cudaStream_t stream);
+struct AttnPlan {
+  int split, rows_per_cta, stages;
+  size_t ticket_bytes, bytes;             // workspace: tickets + partial records
+};
+AttnPlan attention_plan(int B, int R, int D, int num_sms);
+int32_t launch_soft_dot_attention(AttnParams p, int B, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // ---------------------------------------------------------------- gemm_simt.cu
 // out[M,N] = act( sum_s (x_s .* xs_s) · w_s^T + bias0 + bias1 )   with M <= a few hundred ("skinny").
@@ -54,15 +63,22 @@ struct GemmParams {
   int splitk;                             // 1, 2, 4 or 8: K split over the CTAs of a cluster, reduced through DSMEM
   float* out; int ldo;                    // plain epilogue: out = act(acc + bias0 + bias1)
   const float* bias0; const float* bias1; // [N] or NULL
+  const float* oscale;                    // [N] or NULL: out = act(acc + biases) * oscale[n]
   int act;                                // 0 none, 1 tanh
   LstmEpilogue lstm;
+  unsigned long long* trace;              // bring-up: 3 timestamps of block 0, or NULL
 };
 int32_t launch_gemm(const GemmParams& p, cudaStream_t stream);
 int gemm_pick_splitk(int M, int N, int ktotal, int num_sms);
 
 // ---------------------------------------------------------------- gemm_tc.cu (tcgen05 / TMEM, LSTM epilogue only)
+struct TcPlan {
+  int tiles, nz, rows_per_z, NB, S;
+  size_t sem_bytes, bytes;               // workspace: self-resetting semaphores (must start zeroed) + partial tiles
+};
+TcPlan gemm_tc_plan(int M, int H, int ktotal, int nseg, int num_sms);
 bool gemm_tc_supported(const GemmParams& p);
-int32_t launch_gemm_tc(const GemmParams& p, cudaStream_t stream);
+int32_t launch_gemm_tc(const GemmParams& p, cudaStream_t stream, void* ws, size_t ws_bytes);
 void gemm_tc_set_debug(int flags);
 int gemm_tc_read_timestamps(long long* out, int n);
 extern int g_disable_tc;
@@ -72,10 +88,11 @@ extern int g_disable_tc;
 struct ScoringParams {
   const float* all_u_t;                   // [B,A,E]
   const float* g;                         // [B,E]
-  const float* tp;                        // [B,D]  linear_in_h(h_tilde)
-  const float* b_a; const float* w_out; const float* b_out;
+  const float* tp;                        // [B,D]  linear_in_h(h_tilde) (.) w_out
+  const float* b_a; const float* b_out;
   float* logit;                           // [B,A]
   int B, A, E, D;
+  unsigned long long* trace;
 };
 int32_t launch_action_scoring(const ScoringParams& p, cudaStream_t stream);
 
@@ -83,9 +100,11 @@ struct TailParams {
   float* logit; const float* is_valid; const int32_t* target; int feedback; const float* sample_u;
   const float* all_u_t; int32_t* a_t; float* u_next; float* action_score; float* ce;
   int B, A, E;
+  unsigned long long* trace;
 };
 int32_t launch_follower_tail(const TailParams& p, cudaStream_t stream);
 
 int device_num_sms();
+unsigned long long* next_trace_slot();   // NULL unless sfb_set_option("trace", 1)
 
 }  // namespace sfb

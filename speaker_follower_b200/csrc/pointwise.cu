@@ -5,8 +5,8 @@
 namespace sfb {
 
 // ---------------------------------------------------------------- action scoring
-// w_out . ((W_h ht + b_h) (.) (W_a u + b_a)) + b_out  ==  u . g + c   with  t' = W_h ht + b_h,
-// g = W_a^T (w_out (.) t')  and  c = sum_d b_a[d] w_out[d] t'[d] + b_out   (SURVEY.md §7 hard part 1).
+// w_out . ((W_h ht + b_h) (.) (W_a u + b_a)) + b_out  ==  u . g + c   with  tp = w_out (.) (W_h ht + b_h),
+// g = W_a^T tp  and  c = sum_d b_a[d] tp[d] + b_out   (SURVEY.md §7 hard part 1).
 // The A candidate rows of a batch element are step inputs: with PDL they are pulled into shared memory (bulk
 // async copies) while the kernels producing g / t' are still running.
 __global__ void __launch_bounds__(256) action_scoring_kernel(const ScoringParams p, const int stage_rows) {
@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) action_scoring_kernel(const ScoringParams
   __shared__ float red[8];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nvec = p.E >> 2;
+  trace_mark(p.trace, 0);
   pdl_launch_dependents();
   if (stage_rows && tid == 0) {
     mbar_init(bar, 1);
@@ -27,10 +28,11 @@ __global__ void __launch_bounds__(256) action_scoring_kernel(const ScoringParams
       bulk_g2s_hint(us + (size_t)a * p.E, p.all_u_t + ((size_t)b * p.A + a) * p.E, (uint32_t)p.E * 4u, bar, pol);
   }
   pdl_wait();
+  trace_mark(p.trace, 1);
   const float4* g4 = reinterpret_cast<const float4*>(p.g + (size_t)b * p.E);
   for (int j = tid; j < nvec; j += 256) reinterpret_cast<float4*>(gs)[j] = g4[j];
   float c = 0.f;
-  for (int d = tid; d < p.D; d += 256) c = fmaf(__ldg(p.b_a + d) * __ldg(p.w_out + d), p.tp[(size_t)b * p.D + d], c);
+  for (int d = tid; d < p.D; d += 256) c = fmaf(__ldg(p.b_a + d), p.tp[(size_t)b * p.D + d], c);
   c = warp_sum(c);
   if (lane == 0) red[warp] = c;
   __syncthreads();
@@ -53,9 +55,13 @@ __global__ void __launch_bounds__(256) action_scoring_kernel(const ScoringParams
     acc = warp_sum(acc);
     if (lane == 0) p.logit[(size_t)b * p.A + a] = acc + cst;
   }
+  __syncthreads();
+  trace_mark(p.trace, 2);
 }
 
-int32_t launch_action_scoring(const ScoringParams& p, cudaStream_t stream) {
+int32_t launch_action_scoring(const ScoringParams& p_in, cudaStream_t stream) {
+  ScoringParams p = p_in;
+  p.trace = next_trace_slot();
   SFB_CHECK_ARG((p.E % 4) == 0, "scoring: E % 4");
   const size_t staged = ((size_t)p.A + 1) * p.E * sizeof(float) + 16;
   const int stage_rows = staged <= 160 * 1024 ? 1 : 0;
@@ -75,8 +81,10 @@ int32_t launch_action_scoring(const ScoringParams& p, cudaStream_t stream) {
 __global__ void __launch_bounds__(128) follower_tail_kernel(const TailParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + warp;
+  trace_mark(p.trace, 0);
   pdl_launch_dependents();
   pdl_wait();
+  trace_mark(p.trace, 1);
   if (b >= p.B) return;
   float* lg = p.logit + (size_t)b * p.A;
   const float* valid = p.is_valid + (size_t)b * p.A;
@@ -139,9 +147,13 @@ __global__ void __launch_bounds__(128) follower_tail_kernel(const TailParams p) 
     float4* dst = reinterpret_cast<float4*>(p.u_next + (size_t)b * p.E);
     for (int j = lane; j < (p.E >> 2); j += 32) dst[j] = __ldg(src + j);   // all_u_t is a step input
   }
+  __syncwarp();
+  trace_mark(p.trace, 2);
 }
 
-int32_t launch_follower_tail(const TailParams& p, cudaStream_t stream) {
+int32_t launch_follower_tail(const TailParams& p_in, cudaStream_t stream) {
+  TailParams p = p_in;
+  p.trace = next_trace_slot();
   SFB_CHECK_CUDA(launch_ex(follower_tail_kernel, dim3((p.B + 3) / 4, 1, 1), dim3(128, 1, 1), 0, stream, dim3(1, 1, 1), p));
   count_launch();
   return 0;

@@ -114,7 +114,8 @@ def follower_dims(w: Dict[str, Tensor], V: int = 36) -> Dims:
 
 
 def _workspace(nbytes: int, device) -> Tensor:
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    """Zero-filled: the head of a workspace holds self-resetting semaphores (include/sf_b200.h contract)."""
+    return torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
 def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual: Optional[Tensor], h0: Tensor,
@@ -196,7 +197,7 @@ def visual_attention(w: Dict[str, Tensor], h: Tensor, visual: Optional[Tensor], 
 
 
 def visual_attention_core(q: Tensor, visual: Optional[Tensor], store=None, vp_idx=None, view_idx=None,
-                          out: Optional[tuple] = None):
+                          out: Optional[tuple] = None, workspace: Optional[Tensor] = None):
     """The attention-gather kernel alone: q [B,F] -> (feature [B,F], alpha_v [B,V]); one launch."""
     lib = _lib.load()
     B, F = q.shape
@@ -208,8 +209,11 @@ def visual_attention_core(q: Tensor, visual: Optional[Tensor], store=None, vp_id
         feat = torch.empty(B, F, device=q.device); alpha_v = torch.empty(B, V, device=q.device)
     else:
         feat, alpha_v = out
+    need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, 1, 1)
+    if workspace is None or workspace.numel() < need:
+        workspace = _workspace(need, q.device)
     check(lib.sfb_visual_attention_core_fwd(C.byref(d), B, _p(q, name="q"), C.byref(vs), _p(feat), _p(alpha_v),
-                                            _stream()))
+                                            workspace.data_ptr(), workspace.numel(), _stream()))
     return feat, alpha_v
 
 
@@ -292,7 +296,7 @@ def speaker_decoder_step(w: Dict[str, Tensor], prev_word: Tensor, h0: Tensor, c0
     sw.w_voc = _p(w["decoder2action.weight"]); sw.b_voc = _p(w["decoder2action.bias"])
     pw = _i32(prev_word.reshape(-1))
     m = _mask_u8(ctx_mask)
-    need = lib.sfb_speaker_decoder_step_workspace_bytes(H, Ew, B)
+    need = lib.sfb_speaker_decoder_step_workspace_bytes(H, Ew, B, T)
     ws = _workspace(need, dev)
     h1 = torch.empty(B, H, device=dev); c1 = torch.empty(B, H, device=dev)
     alpha = torch.empty(B, T, device=dev); logit = torch.empty(B, vocab, device=dev)

@@ -35,7 +35,7 @@ def test_abi_version_and_workspace_queries(lib):
     n = lib.sfb_follower_step_workspace_bytes(C.byref(d), 100, 80, 8)
     assert n > 100 * 2048 * 4 and n % 256 == 0
     assert lib.sfb_follower_step_workspace_bytes(None, 100, 80, 8) == 0
-    assert lib.sfb_speaker_decoder_step_workspace_bytes(512, 300, 256) > 0
+    assert lib.sfb_speaker_decoder_step_workspace_bytes(512, 300, 256, 6) > 0
     assert lib.sfb_encoder_lstm_workspace_bytes(1, 512, 300, 100, 80) > 100 * 80 * 2048 * 4
 
 

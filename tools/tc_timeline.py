@@ -15,9 +15,8 @@ buf = (C.c_int64 * 256)()
 _lib.load().sfb_debug_read_timestamps(buf, 256)
 t = list(buf)
 base = t[0]
-print("setup->wait", t[1] - t[0], "loop end", t[2] - t[0], "tmem->smem", t[3] - t[2], "csync", t[4] - t[3], "reduce", t[5] - t[4], "csync2", t[6] - t[5])
+print("setup->pdl_wait", t[1] - t[0], "| producer loop end", t[2] - t[0], "| tmem->L2", t[3] - t[2], "| semaphore", t[4] - t[3], "| reduce+lstm", t[5] - t[4], "| exit", t[6] - t[5])
 for it in range(12):
-    r = t[8 + it * 8: 8 + it * 8 + 6]
+    r = t[8 + it * 8: 8 + it * 8 + 3]
     if r[0] == 0: break
-    print("it %2d start %7d | wait_empty %5d convert %5d fence+sync %5d loadissue %5d mma %5d" % (
-        it, r[0] - base, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4]))
+    print("it %2d start %7d | wait_empty %5d convert+arrive %5d" % (it, r[0] - base, r[1] - r[0], r[2] - r[1]))
