@@ -1,0 +1,395 @@
+"""Follower agent on the sm_100a kernels: the control loops of tasks/R2R/follower.py:Seq2SeqAgent (261-1035)
+with the same class / method names, arguments and result dictionaries, modernised for today's torch (bool masks,
+`.item()`), and with every per-step tensor operation on the device:
+
+    _feature_variables (291-298)      -> indices into a device-resident FeatureStore when the env provides
+                                         `vp_index` (else the reference's host stack + copy)
+    decoder(...) (473)                -> sfb_follower_step_fwd  (one call)
+    mask / CE / argmax|sample / u_t_prev gather / score (476-505)  -> sfb_follower_step_tail (one call)
+
+Only `a_t` (B int32) crosses back to the host each step, because the simulator needs it (follower.py:509-513).
+Written from the behaviour described in SURVEY.md A.2; no reference code is reused.
+"""
+from __future__ import annotations
+
+import json
+import random
+from collections import namedtuple
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+
+vocab_pad_idx, vocab_unk_idx, vocab_eos_idx, vocab_bos_idx = 0, 1, 2, 3      # utils.py:19-24
+
+InferenceState = namedtuple("InferenceState", "prev_inference_state, world_state, observation, flat_index, last_action, "
+                            "last_action_embedding, action_count, score, h_t, c_t, last_alpha")   # follower.py:19
+
+
+def _device(module) -> torch.device:
+    return next(module.parameters()).device
+
+
+def path_element_from_observation(ob):
+    return (ob["viewpoint"], ob["heading"], ob["elevation"])
+
+
+def backchain_inference_states(last):
+    """follower.py:32-50: walk parent pointers back to the start; actions/scores/attentions exclude the start."""
+    chain = []
+    s = last
+    while s is not None:
+        chain.append(s)
+        s = s.prev_inference_state
+    chain.reverse()
+    states = [s.world_state for s in chain]
+    observations = [s.observation for s in chain]
+    actions = [s.last_action for s in chain][1:]
+    scores = [b.score - a.score for a, b in zip(chain[:-1], chain[1:])]
+    attentions = [s.last_alpha for s in chain][1:]
+    return states, observations, actions, scores, attentions
+
+
+def batch_instructions_from_encoded(encoded_instructions, max_length, reverse=False, sort=False, device=None):
+    """follower.py:75-105: [reversed] tokens + <EOS>, truncated to max_length, padded with <PAD>; mask = PAD
+    positions cut to the longest sequence.  Returns (seq int64 [N,max_length], mask bool [N,max(len)], lengths
+    [, perm_idx when sort])."""
+    n = len(encoded_instructions)
+    seq = np.full((n, max_length), vocab_pad_idx, dtype=np.int64)
+    lengths = []
+    for i, inst in enumerate(encoded_instructions):
+        inst = list(inst)
+        if inst:
+            assert inst[-1] != vocab_eos_idx
+        if reverse:
+            inst = inst[::-1]
+        inst = (inst + [vocab_eos_idx])[:max_length]
+        seq[i, :len(inst)] = inst
+        lengths.append(len(inst))
+    seq_t = torch.from_numpy(seq)
+    perm = None
+    if sort:
+        order = np.argsort(-np.asarray(lengths), kind="stable")
+        perm = [int(i) for i in order]
+        seq_t = seq_t[order]
+        lengths = [lengths[i] for i in perm]
+    mask = (seq_t == vocab_pad_idx)[:, :max(lengths)]
+    if device is not None:
+        seq_t, mask = seq_t.to(device), mask.to(device)
+    out = (seq_t, mask, lengths)
+    return out + (perm,) if sort else out
+
+
+class BaseAgent(object):
+    """follower.py:107-195."""
+
+    def __init__(self, env, results_path):
+        self.env = env
+        self.results_path = results_path
+        random.seed(1)
+        self.results = {}
+        self.losses = []
+
+    def write_results(self):
+        results = {k: {"instr_id": v["instr_id"], "trajectory": v["trajectory"]} for k, v in self.results.items()}
+        with open(self.results_path, "w") as f:
+            json.dump(results, f)
+
+    def rollout(self):
+        raise NotImplementedError
+
+    def test(self):
+        self.env.reset_epoch()
+        self.losses = []
+        self.results = {}
+        looped = False
+        while True:
+            for result in self.rollout():
+                if result["instr_id"] in self.results:
+                    looped = True
+                else:
+                    self.results[result["instr_id"]] = result
+            if looped:
+                break
+        return self.results
+
+
+class Seq2SeqAgent(BaseAgent):
+    """follower.py:261-1035."""
+    feedback_options = ["teacher", "argmax", "sample"]
+
+    def __init__(self, env, results_path, encoder, decoder, episode_len=10, beam_size=1, reverse_instruction=True,
+                 max_instruction_length=80):
+        super().__init__(env, results_path)
+        self.encoder, self.decoder = encoder, decoder
+        self.episode_len = episode_len
+        self.losses = []
+        self.beam_size = beam_size
+        self.reverse_instruction = reverse_instruction
+        self.max_instruction_length = max_instruction_length
+        self.feedback = "argmax"
+        self.loss = 0
+        self._sample_gen: Optional[torch.Generator] = None
+
+    # ---------------------------------------------------------------- batching shims (follower.py:291-332)
+    def _feature_variables(self, obs, beamed=False):
+        """Device feature store + (viewpoint row, viewIndex) when available, else the dense [N,36,F] host stack."""
+        flat = [o for beam in obs for o in beam] if beamed else list(obs)
+        dev = _device(self.decoder)
+        store = getattr(self.decoder, "feature_store", None)
+        if store is not None and all("vp_index" in ob for ob in flat):
+            vp = torch.tensor([ob["vp_index"] for ob in flat], dtype=torch.int32, device=dev)
+            view = torch.tensor([ob["viewIndex"] for ob in flat], dtype=torch.int32, device=dev)
+            return [(vp, view)]
+        feats = np.stack([ob["feature"][0] for ob in flat])
+        return [torch.from_numpy(feats).to(dev)]
+
+    def _action_variable(self, obs):
+        dev = _device(self.decoder)
+        max_a = max(len(ob["adj_loc_list"]) for ob in obs)
+        dim = obs[0]["action_embedding"].shape[-1]
+        is_valid = np.zeros((len(obs), max_a), np.float32)
+        emb = np.zeros((len(obs), max_a, dim), np.float32)
+        for i, ob in enumerate(obs):
+            n = len(ob["adj_loc_list"])
+            is_valid[i, :n] = 1.0
+            emb[i, :n] = ob["action_embedding"]
+        return torch.from_numpy(emb).to(dev), torch.from_numpy(is_valid).to(dev), is_valid
+
+    def _teacher_action(self, obs, ended):
+        a = [(-1 if ended[i] else int(ob["teacher"])) for i, ob in enumerate(obs)]
+        return torch.tensor(a, dtype=torch.int32, device=_device(self.decoder))
+
+    def _proc_batch(self, obs, beamed=False):
+        flat = [o for beam in obs for o in beam] if beamed else obs
+        enc = [ob["instr_encoding"] for ob in flat]
+        return batch_instructions_from_encoded(enc, self.max_instruction_length, reverse=self.reverse_instruction,
+                                               device=_device(self.encoder))
+
+    def _sample_uniform(self, n, dev):
+        if self._sample_gen is None:
+            self._sample_gen = torch.Generator(device=dev)
+            self._sample_gen.manual_seed(torch.initial_seed() & 0x7FFFFFFF)
+        return torch.rand(n, device=dev, generator=self._sample_gen)
+
+    def _step(self, u_t_prev, obs, h_t, c_t, ctx, seq_mask, target, feedback):
+        """One decode step + tail on the device.  Returns (h, c, alpha, masked logit, a_t[int32], u_next, score, ce)."""
+        f_t = self._feature_variables(obs)[0]
+        all_u_t, is_valid, _ = self._action_variable(obs)
+        h_t, c_t, alpha, logit, alpha_v = self.decoder(u_t_prev, all_u_t, f_t, h_t, c_t, ctx, seq_mask)
+        su = self._sample_uniform(len(obs), logit.device) if feedback == "sample" else None
+        a_t, u_next, score, ce = ops.follower_tail(logit, is_valid, all_u_t, feedback, target=target, sample_u=su)
+        return h_t, c_t, alpha, logit, a_t, u_next, score, ce
+
+    # ---------------------------------------------------------------- rollouts
+    def rollout(self):
+        if self.beam_size == 1:
+            return self._rollout_with_loss()
+        beams, _, _ = self.beam_search(self.beam_size)
+        return [beam[0] for beam in beams]
+
+    def _rollout_with_loss(self):
+        """follower.py:430-539."""
+        world_states = self.env.reset(sort=True)
+        obs = self.env.observe(world_states)
+        batch_size = len(obs)
+        seq, seq_mask, seq_lengths = self._proc_batch(obs)
+        dev = _device(self.decoder)
+        self.loss = torch.zeros((), device=dev)
+        feedback = self.feedback
+        ctx, h_t, c_t = self.encoder(seq, seq_lengths)
+        traj = [{"instr_id": ob["instr_id"], "trajectory": [path_element_from_observation(ob)], "actions": [],
+                 "scores": [], "observations": [ob], "instr_encoding": ob["instr_encoding"]} for ob in obs]
+        u_t_prev = self.decoder.u_begin.expand(batch_size, -1)
+        ended = np.zeros(batch_size, dtype=bool)
+        sequence_scores = torch.zeros(batch_size, device=dev)
+        for t in range(self.episode_len):
+            target = self._teacher_action(obs, ended)
+            h_t, c_t, alpha, logit, a_t, u_t_prev, score, ce = self._step(u_t_prev, obs, h_t, c_t, ctx, seq_mask, target, feedback)
+            n_keep = int((target >= 0).sum())
+            self.loss = self.loss + (ce.sum() / n_keep if n_keep > 0 else ce.sum() * float("nan"))   # CE(ignore_index=-1), 278,481
+            sequence_scores = sequence_scores + score
+            env_action = a_t.tolist()                                     # the one device->host read of the step
+            scores_host = score.tolist()
+            world_states = self.env.step(world_states, env_action, obs)
+            obs = self.env.observe(world_states)
+            seq_host = sequence_scores.tolist()
+            for i, ob in enumerate(obs):                                  # follower.py:518-530
+                if not ended[i]:
+                    traj[i]["trajectory"].append(path_element_from_observation(ob))
+                    traj[i]["score"] = seq_host[i]
+                    traj[i]["scores"].append(scores_host[i])
+                    traj[i]["actions"].append(env_action[i])
+                    traj[i]["observations"].append(ob)
+                if env_action[i] == 0:
+                    ended[i] = True
+            if ended.all():
+                break
+        self.losses.append(float(self.loss))
+        return traj
+
+    def _score_obs_actions_and_instructions(self, path_obs, path_actions, encoded_instructions):
+        """follower.py:342-428: teacher-forced scoring of given (observations, actions, instruction) triples."""
+        batch_size = len(path_obs)
+        assert len(path_actions) == batch_size and len(encoded_instructions) == batch_size
+        for o, a in zip(path_obs, path_actions):
+            assert len(o) == len(a) + 1
+        dev = _device(self.decoder)
+        seq, seq_mask, seq_lengths, perm = batch_instructions_from_encoded(
+            encoded_instructions, self.max_instruction_length, reverse=self.reverse_instruction, sort=True, device=dev)
+        loss = torch.zeros((), device=dev)
+        ctx, h_t, c_t = self.encoder(seq, seq_lengths)
+        u_t_prev = self.decoder.u_begin.expand(batch_size, -1)
+        ended = np.zeros(batch_size, dtype=bool)
+        sequence_scores = torch.zeros(batch_size, device=dev)
+        traj = [{"instr_id": o[0]["instr_id"], "trajectory": [path_element_from_observation(o[0])], "actions": [],
+                 "scores": [], "observations": [o[0]], "instr_encoding": o[0]["instr_encoding"]} for o in path_obs]
+        obs = None
+        for t in range(self.episode_len):
+            nxt_obs, nxt_tgt = [], []
+            for pi, src in enumerate(perm):
+                if t < len(path_actions[src]):
+                    nxt_tgt.append(int(path_actions[src][t]))
+                    nxt_obs.append(path_obs[src][t])
+                else:
+                    nxt_tgt.append(-1)
+                    nxt_obs.append(obs[pi])
+            obs = nxt_obs
+            target = torch.tensor(nxt_tgt, dtype=torch.int32, device=dev)
+            h_t, c_t, alpha, logit, a_t, u_t_prev, score, ce = self._step(u_t_prev, obs, h_t, c_t, ctx, seq_mask, target, "teacher")
+            n_keep = int((target >= 0).sum())
+            loss = loss + (ce.sum() / n_keep if n_keep > 0 else 0.0)
+            # reference: action_scores = -CE(logit, target, ignore_index=-1) -> 0 for finished rows (405)
+            step_scores = torch.where(target >= 0, score, torch.zeros_like(score))
+            sequence_scores = sequence_scores + step_scores
+            a_host, s_host, seq_host = a_t.tolist(), step_scores.tolist(), sequence_scores.tolist()
+            for pi, src in enumerate(perm):
+                if not ended[pi]:
+                    traj[src]["trajectory"].append(path_element_from_observation(obs[pi]))
+                    traj[src]["score"] = seq_host[pi]
+                    traj[src]["scores"].append(s_host[pi])
+                    traj[src]["actions"].append(a_host[pi])
+                if a_host[pi] == 0:
+                    ended[pi] = True
+            if ended.all():
+                break
+        return traj, loss
+
+    # ---------------------------------------------------------------- beam search (follower.py:541-718)
+    def beam_search(self, beam_size, load_next_minibatch=True, mask_undo=False):
+        assert self.env.beam_size >= beam_size
+        world_states = self.env.reset(sort=True, beamed=True, load_next_minibatch=load_next_minibatch)
+        obs = self.env.observe(world_states, beamed=True)
+        batch_size = len(world_states)
+        seq, seq_mask, seq_lengths = self._proc_batch(obs, beamed=True)
+        ctx, h_t, c_t = self.encoder(seq, seq_lengths)
+        dev = _device(self.decoder)
+        completed = [[] for _ in range(batch_size)]
+        beams = [[InferenceState(None, ws[0], o[0], i, -1, self.decoder.u_begin.view(-1), 0, 0.0, None, None, None)]
+                 for i, (ws, o) in enumerate(zip(world_states, obs))]
+        for t in range(self.episode_len):
+            flat_states = [s for beam in beams for s in beam]
+            beam_of = [bi for bi, beam in enumerate(beams) for _ in beam]
+            flat_obs = [s.observation for s in flat_states]
+            flat_idx = torch.tensor([s.flat_index for s in flat_states], dtype=torch.long, device=dev)
+            beam_idx = torch.tensor(beam_of, dtype=torch.long, device=dev)
+            u_t_prev = torch.stack([s.last_action_embedding for s in flat_states], 0).contiguous()
+            f_t = self._feature_variables(flat_obs)[0]
+            all_u_t, is_valid, is_valid_np = self._action_variable(flat_obs)
+            h_t, c_t, alpha, logit, alpha_v = self.decoder(u_t_prev, all_u_t, f_t, h_t[flat_idx].contiguous(),
+                                                           c_t[flat_idx].contiguous(), ctx[beam_idx].contiguous(),
+                                                           seq_mask[beam_idx].contiguous())
+            logit = logit.masked_fill(is_valid == 0, -float("inf"))                       # 600
+            log_probs = torch.log_softmax(logit, dim=1)
+            k = min(beam_size, logit.shape[1])
+            _, action_indices = logit.topk(k, dim=1)                                      # ranks on masked LOGITS (608)
+            action_scores = log_probs.gather(1, action_indices)
+            idx_h, sc_h = action_indices.tolist(), action_scores.tolist()
+            all_successors, start = [], 0
+            for bi, beam in enumerate(beams):
+                succ = []
+                for j, st in enumerate(beam):
+                    fi = start + j
+                    for sc, ai in zip(sc_h[fi], idx_h[fi]):
+                        if is_valid_np[fi, ai] == 0:
+                            continue
+                        succ.append(InferenceState(st, st.world_state, st.observation, fi, ai, all_u_t[fi, ai],
+                                                   st.action_count + 1, float(st.score + sc), None, None, alpha[fi]))
+                start += len(beam)
+                succ.sort(key=lambda s: s.score, reverse=True)
+                all_successors.append(succ[:beam_size])
+            new_ws = self.env.step([[s.world_state for s in ss] for ss in all_successors],
+                                   [[s.last_action for s in ss] for ss in all_successors],
+                                   [[s.observation for s in ss] for ss in all_successors], beamed=True)
+            new_obs = self.env.observe(new_ws, beamed=True)
+            all_successors = [[s._replace(world_state=w, observation=o) for s, w, o in zip(ss, ws_, os_)]
+                              for ss, ws_, os_ in zip(all_successors, new_ws, new_obs)]
+            beams = []
+            for bi, ss in enumerate(all_successors):
+                nb = []
+                for s in ss:
+                    (completed[bi] if (s.last_action == 0 or t == self.episode_len - 1) else nb).append(s)
+                beams.append([] if len(completed[bi]) >= beam_size else nb)
+            if not any(beams):
+                break
+        trajs = []
+        for done in completed:
+            assert done
+            out = []
+            for s in sorted(done, key=lambda s: s.score, reverse=True)[:beam_size]:
+                states, observations, actions, scores, attentions = backchain_inference_states(s)
+                out.append({"instr_id": observations[0]["instr_id"], "instr_encoding": observations[0]["instr_encoding"],
+                            "trajectory": [path_element_from_observation(o) for o in observations],
+                            "observations": observations, "actions": actions, "score": s.score, "scores": scores,
+                            "attentions": attentions})
+            trajs.append(out)
+        return trajs, completed, None
+
+    def state_factored_search(self, completion_size, successor_size, load_next_minibatch=True, mask_undo=False,
+                              first_n_ws_key=4):
+        raise NotImplementedError("state-factored search (follower.py:720-980) is the next row of SURVEY.md §8 (a10)")
+
+    # ---------------------------------------------------------------- driver methods (follower.py:982-1035)
+    def set_beam_size(self, beam_size):
+        if self.env.beam_size < beam_size:
+            self.env.set_beam_size(beam_size)
+        self.beam_size = beam_size
+
+    def test(self, use_dropout=False, feedback="argmax", allow_cheat=False, beam_size=1):
+        if not allow_cheat:
+            assert feedback in ["argmax", "sample"]
+        self.feedback = feedback
+        (self.encoder.train if use_dropout else self.encoder.eval)()
+        (self.decoder.train if use_dropout else self.decoder.eval)()
+        self.set_beam_size(beam_size)
+        with torch.no_grad():
+            return super().test()
+
+    def train(self, encoder_optimizer, decoder_optimizer, n_iters, feedback="teacher"):
+        assert all(f in self.feedback_options for f in feedback.split("+"))
+        self.feedback = feedback
+        self.encoder.train()
+        self.decoder.train()
+        self.losses = []
+        for _ in range(1, n_iters + 1):
+            encoder_optimizer.zero_grad()
+            decoder_optimizer.zero_grad()
+            self._rollout_with_loss()
+            self.loss.backward()          # raises while the modules are forward-only
+            encoder_optimizer.step()
+            decoder_optimizer.step()
+
+    def _encoder_and_decoder_paths(self, base_path):
+        return base_path + "_enc", base_path + "_dec"
+
+    def save(self, path):
+        e, d = self._encoder_and_decoder_paths(path)
+        torch.save(self.encoder.state_dict(), e)
+        torch.save(self.decoder.state_dict(), d)
+
+    def load(self, path, **kwargs):
+        e, d = self._encoder_and_decoder_paths(path)
+        self.encoder.load_state_dict(torch.load(e, **kwargs))
+        self.decoder.load_state_dict(torch.load(d, **kwargs))

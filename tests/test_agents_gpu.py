@@ -1,0 +1,127 @@
+"""Agent-level parity on a fake environment (tests/fake_env.py): the CUDA agents (speaker_follower_b200.follower /
+.speaker) against the CPU oracle fed with the observations the rollout actually saw, plus the invariants the
+reference states in comments (follower.py:147-180): beam_search(1) == greedy rollout, teacher rollout ==
+_score_obs_actions_and_instructions."""
+import numpy as np
+import pytest
+import torch
+
+from fake_env import FakeR2RBatch
+from oracle import r2r_oracle as O
+from speaker_follower_b200 import follower as Fo, model as M, ops, speaker as Sp, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def make_follower(env, store=False, seed_shift=0):
+    glove = synth.follower_encoder_weights()["embedding.weight"].numpy()
+    enc = M.EncoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0, 0.5, glove=glove).cuda().eval()
+    dec = M.AttnDecoderLSTM(synth.FEAT, synth.HID, 0.5).cuda().eval()
+    we, wd = synth.follower_encoder_weights(), synth.follower_decoder_weights()
+    enc.load_state_dict(we); dec.load_state_dict(wd)
+    if store:
+        dec.feature_store = ops.FeatureStore(torch.from_numpy(env.table).cuda(), torch.from_numpy(env.loc).cuda())
+    return Fo.Seq2SeqAgent(env, "", enc, dec, episode_len=6, max_instruction_length=20), we, wd
+
+
+def oracle_check(agent, traj, we, wd, feedback):
+    """Re-run the recorded observation sequence through the CPU oracle and compare actions / scores."""
+    B = len(traj)
+    enc = [t["instr_encoding"] for t in traj]
+    seq, mask, lengths = Fo.batch_instructions_from_encoded(enc, agent.max_instruction_length, reverse=True)
+    T = max(len(t["actions"]) for t in traj)
+    steps = []
+    for s in range(T):
+        obs = [t["observations"][min(s, len(t["observations"]) - 2)] for t in traj]
+        A = max(len(o["adj_loc_list"]) for o in obs)
+        U = torch.zeros(B, A, synth.FEAT); valid = torch.zeros(B, A)
+        for i, o in enumerate(obs):
+            n = len(o["adj_loc_list"]); U[i, :n] = torch.from_numpy(o["action_embedding"]); valid[i, :n] = 1
+        vis = torch.from_numpy(np.stack([o["feature"][0] for o in obs]))
+        tgt = torch.tensor([(t["actions"][s] if s < len(t["actions"]) else -1) for t in traj])
+        steps.append({"visual": vis, "all_u_t": U, "is_valid": valid, "target": tgt if feedback == "teacher" else None})
+    res, loss, score = O.follower_rollout(seq, mask, lengths, steps, we, wd, feedback=feedback)
+    for i, t in enumerate(traj):
+        for s, a in enumerate(t["actions"]):
+            assert int(res[s]["a_t"][i]) == int(a), (i, s)
+            assert abs(float(res[s]["scores"][i]) - t["scores"][s]) < 1e-4
+    return res, loss, score
+
+
+@pytest.mark.parametrize("store", [False, True])
+def test_greedy_rollout_matches_oracle(store):
+    env = FakeR2RBatch(n_viewpoints=20, n_instr=8, batch_size=8, seed=3)
+    agent, we, wd = make_follower(env, store=store)
+    agent.feedback = "argmax"
+    with torch.no_grad():
+        traj = agent.rollout()
+    assert len(traj) == 8 and all(len(t["trajectory"]) == len(t["actions"]) + 1 for t in traj)
+    # rows that ended keep stepping in the reference (follower.py:509-513) but stop recording
+    oracle_check(agent, traj, we, wd, "argmax")
+
+
+def test_beam1_equals_greedy_and_beams_are_sorted():
+    env = FakeR2RBatch(n_viewpoints=20, n_instr=8, batch_size=8, seed=4, beam_size=4)
+    agent, we, wd = make_follower(env)
+    agent.feedback = "argmax"
+    with torch.no_grad():
+        greedy = agent._rollout_with_loss()
+        beams1, _, _ = agent.beam_search(1, load_next_minibatch=False)
+        beams4, _, _ = agent.beam_search(4, load_next_minibatch=False)
+    for g, b in zip(greedy, beams1):
+        assert g["instr_id"] == b[0]["instr_id"]
+        assert g["trajectory"] == b[0]["trajectory"]
+        assert abs(g["score"] - b[0]["score"]) < 1e-4
+    for g, bs in zip(greedy, beams4):
+        sc = [b["score"] for b in bs]
+        assert sc == sorted(sc, reverse=True) and 1 <= len(bs) <= 4
+        assert abs(sum(bs[0]["scores"]) - bs[0]["score"]) < 1e-4          # rational_speaker.py:87-89 invariant
+    # teacher-forced rescoring of a returned beam reproduces its score (a8)
+    obs_paths = [bs[0]["observations"] for bs in beams4]
+    act_paths = [bs[0]["actions"] for bs in beams4]
+    encs = [bs[0]["instr_encoding"] for bs in beams4]
+    with torch.no_grad():
+        scored, _ = agent._score_obs_actions_and_instructions(obs_paths, act_paths, encs)
+    for s, bs in zip(scored, beams4):
+        assert abs(s["score"] - bs[0]["score"]) < 2e-4 and [int(a) for a in s["actions"]] == [int(a) for a in bs[0]["actions"]]
+
+
+def test_teacher_rollout_loss_and_sample_feedback():
+    env = FakeR2RBatch(n_viewpoints=16, n_instr=8, batch_size=8, seed=5)
+    agent, we, wd = make_follower(env)
+    agent.feedback = "teacher"
+    with torch.no_grad():
+        traj = agent.rollout()
+    res, loss, score = oracle_check(agent, traj, we, wd, "teacher")
+    torch.manual_seed(0)
+    agent.feedback = "sample"
+    with torch.no_grad():
+        traj = agent.rollout()
+    for t in traj:                      # sampled actions are always valid actions
+        for o, a in zip(t["observations"], t["actions"]):
+            assert 0 <= a < len(o["adj_loc_list"])
+
+
+def test_speaker_teacher_scoring_matches_oracle():
+    env = FakeR2RBatch(n_viewpoints=16, n_instr=6, batch_size=6, seed=6)
+    we, wd = synth.speaker_encoder_weights(), synth.speaker_decoder_weights()
+    enc = M.SpeakerEncoderLSTM(synth.FEAT, synth.FEAT, synth.HID, 0.5).cuda().eval()
+    dec = M.SpeakerDecoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0.5, glove=wd["embedding.weight"].numpy()).cuda().eval()
+    enc.load_state_dict(we); dec.load_state_dict(wd)
+    spk = Sp.Seq2SeqSpeaker(env, "", enc, dec, instruction_len=12, max_episode_len=6)
+    path_obs, path_actions, encoded = env.gold_obs_actions_and_instructions(6)
+    with torch.no_grad():
+        outs, loss = spk._score_obs_actions_and_instructions(path_obs, path_actions, encoded, "teacher")
+    # oracle on the same batch
+    _, feats, acts, mask, _, _, _ = spk._batch_observations_and_actions(path_obs, path_actions, encoded)
+    instr, _, _ = Fo.batch_instructions_from_encoded(encoded, 12)
+    sc, l, words, wsc = O.speaker_score_teacher([a.cpu() for a in acts], [f.cpu() for f in feats], mask.cpu().bool(), instr, we, wd)
+    for i, o in enumerate(outs):
+        assert abs(o["score"] - float(sc[i])) < 2e-3 * max(1.0, abs(float(sc[i])))
+        n = len(o["word_indices"])
+        assert o["word_indices"] == [int(x) for x in words[i, :n]]
+    assert abs(float(loss) - float(l)) < 1e-3 * max(1.0, abs(float(l)))
+    spk.feedback = "argmax"
+    with torch.no_grad():
+        res = spk.test()
+    assert len(res) == 6
