@@ -5,39 +5,48 @@
 // which is the core of VisualSoftDotAttention.forward (model.py:320-325: rows = the 36-view feature slab,
 // q = W_v^T (W_h h + b_h)) and of SoftDotAttention.forward (model.py:132-139: rows = ctx, q = W_in h).
 //
-// B200 mapping.  The rows of one batch element are split over SPLIT CTAs (grid = SPLIT x B, all co-resident:
-// <= 40 KB of shared memory each).  A CTA streams its rows HBM -> shared memory through a ring of bulk async
-// copies (cp.async.bulk, TMA engine, one mbarrier per stage, evict-first, masked rows never fetched; in gather
-// mode a row is two copies: feature table + orientation table).  Each thread keeps its slice of the row in
-// registers between the score and the accumulation, so a row is read from shared memory once: block-wide dot
-// (warp shuffles + one __syncthreads), online softmax, FMA into the running weighted sum.  The SPLIT partial
-// results (max, sum, weighted sum) meet in an L2-resident buffer; the last CTA to arrive (atomic ticket,
-// self-resetting) merges them.  With PDL the ring is primed before the producer of q has finished.
+// B200 mapping.  One thread-block CLUSTER of CL CTAs per batch element (grid = CL x B, CL in {1,2,4,8}); CTA `rank`
+// owns rows rank, rank+CL, ... (interleaved, so padding masks at the end of a sequence stay balanced).  A CTA streams
+// its rows HBM -> shared memory through a ring of bulk async copies (cp.async.bulk = TMA engine, one mbarrier per
+// stage, evict-first, masked rows never fetched; in gather mode a row is two copies: feature table + orientation
+// table).  The ring is as deep as 70 KB allows (8 slab rows; 3 CTAs per SM -> ~200 KB of loads in flight per SM) and
+// a stage is refilled the moment its row has been consumed, so the stream never drains.  Each thread keeps its slice
+// of the row in registers between the score and the accumulation (a row is read from shared memory once): block-wide
+// dot (warp shuffles + one __syncthreads), online softmax, FMA into the running weighted sum.  The CL partial results
+// (max, sum, weighted sum) are merged INSIDE the cluster through distributed shared memory: stats are read from the
+// peers, every CTA pushes its rescaled partial columns to the column's owner (st.shared::cluster), the owner adds them
+// in rank order and writes the output — no global partial buffer, no atomics, two cluster barriers.  With PDL the
+// ring is primed before the producer of q has finished.
 #include "kernels.h"
 
 namespace sfb {
 
 namespace {
-constexpr int ATT_THREADS = 256;
-constexpr int ATT_MAX_ROWS = 64;   // rows per CTA
-constexpr int ATT_MAX_STAGES = 32; // ring depth == rows processed per pass
-}
+constexpr int ATT_MAX_STAGES = 32;            // ring depth (one lane of warp 0 per stage when priming)
+constexpr size_t ATT_RING_BUDGET = 70 * 1024;  // bytes of ring per CTA -> 3 CTAs per SM
 
-template <int NJ>   // float4 slices per thread: D <= NJ * 1024
-__global__ void __launch_bounds__(ATT_THREADS) soft_dot_attn_kernel(const AttnParams p) {
+__device__ __forceinline__ void st_cluster_f32x4(uint32_t addr, const float4& v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+}  // namespace
+
+template <int NJ, int NT>   // float4 slices per thread, threads per CTA: D <= NJ * NT * 4
+__global__ void __launch_bounds__(NT) soft_dot_attn_kernel(const AttnParams p) {
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y, split = blockIdx.x, SPLIT = gridDim.x;
+  const int b = blockIdx.y, rank = blockIdx.x, CL = gridDim.x;
   const int D = p.D, nvec = D >> 2, NSTG = p.stages;
-  const int r0 = split * p.rows_per_cta;
-  const int nrows = max(0, min(p.rows_per_cta, p.R - r0));
+  const int nmine = rank < p.R ? (p.R - rank + CL - 1) / CL : 0;   // rows rank, rank+CL, ...
 
-  float* ring = reinterpret_cast<float*>(smem_raw);                   // [NSTG][D]
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)NSTG * D);   // [NSTG]
-  float* red = reinterpret_cast<float*>(full + NSTG);                 // [8][ATT_MAX_STAGES] per-warp partial dots
-  float* sc = red + 8 * ATT_MAX_STAGES;                               // [ATT_MAX_ROWS] raw scores of this CTA's rows
-  int* list = reinterpret_cast<int*>(sc + ATT_MAX_ROWS);              // [ATT_MAX_ROWS] unmasked local row ids
-  __shared__ int s_nvalid, s_last;
+  float* ring = reinterpret_cast<float*>(smem_raw);                          // [NSTG][D]; reused as the merge inbox
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)NSTG * D);     // [NSTG]
+  float* red = reinterpret_cast<float*>(full + NSTG);                        // [2][NW] per-warp partial dots
+  float* stat = red + 2 * NW;                                                // [2] (max, sum) of this CTA, read by peers
+  float* sc = stat + 2;                                                      // [rows_per_cta] raw scores (local order)
+  int* list = reinterpret_cast<int*>(sc + p.rows_per_cta);                   // [rows_per_cta] unmasked local row ids
+  __shared__ int s_nvalid;
 
   const uint8_t* mrow = p.mask ? p.mask + (size_t)b * p.ldmask : nullptr;
 
@@ -47,13 +56,21 @@ __global__ void __launch_bounds__(ATT_THREADS) soft_dot_attn_kernel(const AttnPa
   // ---- 1. warp 0: compact the unmasked rows, arm the ring, launch the first NSTG copies
   size_t ba = 0, bb = 0;
   uint64_t pol = 0;
+  auto fetch = [&](int i, int stage) {   // local unmasked row #i -> ring[stage]
+    const int gr = rank + CL * list[i];
+    float* dst = ring + (size_t)stage * D;
+    mbar_expect_tx(&full[stage], (uint32_t)D * 4u);
+    bulk_g2s_hint(dst, p.segA + ba + (size_t)gr * p.strideA_r, (uint32_t)p.lenA * 4u, &full[stage], pol);
+    if (p.lenB > 0)
+      bulk_g2s_hint(dst + p.lenA, p.segB + bb + (size_t)gr * p.strideB_r, (uint32_t)p.lenB * 4u, &full[stage], pol);
+  };
   if (warp == 0) {
     int n = 0;
-    for (int base = 0; base < nrows; base += 32) {
-      const int r = base + lane;
-      const bool ok = r < nrows && !(mrow && mrow[r0 + r]);
+    for (int base = 0; base < nmine; base += 32) {
+      const int i = base + lane;
+      const bool ok = i < nmine && !(mrow && mrow[rank + CL * i]);
       const unsigned bal = __ballot_sync(0xffffffffu, ok);
-      if (ok) list[n + __popc(bal & ((1u << lane) - 1u))] = r;
+      if (ok) list[n + __popc(bal & ((1u << lane) - 1u))] = i;
       n += __popc(bal);
     }
     if (lane == 0) s_nvalid = n;
@@ -63,16 +80,9 @@ __global__ void __launch_bounds__(ATT_THREADS) soft_dot_attn_kernel(const AttnPa
     ba = (size_t)(p.idxA ? p.idxA[b] : b) * p.strideA_b;
     bb = (size_t)(p.idxB ? p.idxB[b] : b) * p.strideB_b;
     pol = policy_evict_first();
-    if (lane < NSTG && lane < n) {
-      const int gr = r0 + list[lane];
-      float* dst = ring + (size_t)lane * D;
-      mbar_expect_tx(&full[lane], (uint32_t)D * 4u);
-      bulk_g2s_hint(dst, p.segA + ba + (size_t)gr * p.strideA_r, (uint32_t)p.lenA * 4u, &full[lane], pol);
-      if (p.lenB > 0)
-        bulk_g2s_hint(dst + p.lenA, p.segB + bb + (size_t)gr * p.strideB_r, (uint32_t)p.lenB * 4u, &full[lane], pol);
-    }
+    if (lane < NSTG && lane < n) fetch(lane, lane);
   }
-  for (int r = tid; r < nrows; r += ATT_THREADS) sc[r] = -INFINITY;
+  for (int i = tid; i < nmine; i += NT) sc[i] = -INFINITY;
   // ---- 2. q is produced by the preceding kernel: wait for it only now (rows above are step inputs)
   pdl_wait();
   trace_mark(p.trace, 1);
@@ -81,7 +91,7 @@ __global__ void __launch_bounds__(ATT_THREADS) soft_dot_attn_kernel(const AttnPa
     const float4* q4 = reinterpret_cast<const float4*>(p.q + (size_t)b * p.ldq);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const int idx = tid + ATT_THREADS * j;
+      const int idx = tid + NT * j;
       qv[j] = idx < nvec ? q4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
       acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -90,227 +100,165 @@ __global__ void __launch_bounds__(ATT_THREADS) soft_dot_attn_kernel(const AttnPa
   const int nvalid = s_nvalid;
   trace_mark(p.trace, 4);
 
-  // ---- 3. stream the rows in passes of up to NSTG rows (the whole ring): all rows of a pass are in flight
-  // together, so a pass costs one memory round trip.  Pass = dots for every row (warp shuffles, per-warp partials
-  // in smem) | scores | online-softmax update with the rows re-read from the ring | refill the ring.
+  // ---- 3. stream: one row per iteration, one block barrier per row, stage refilled as soon as it is consumed
   float m = -INFINITY, Z = 0.f;
-  for (int i0 = 0; i0 < nvalid; i0 += NSTG) {
-    const int nb = min(NSTG, nvalid - i0);
-    const uint32_t parity = (uint32_t)(i0 / NSTG) & 1u;
-    for (int r = 0; r < nb; ++r) {
-      mbar_wait(&full[r], parity);
-      const float4* row4 = reinterpret_cast<const float4*>(ring + (size_t)r * D);
-      float part = 0.f;
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const int idx = tid + ATT_THREADS * j;
-        if (idx < nvec) {
-          const float4 v = row4[idx];
-          part = fmaf(v.x, qv[j].x, part);
-          part = fmaf(v.y, qv[j].y, part);
-          part = fmaf(v.z, qv[j].z, part);
-          part = fmaf(v.w, qv[j].w, part);
-        }
-      }
-      part = warp_sum(part);
-      if (lane == 0) red[warp * ATT_MAX_STAGES + r] = part;
-    }
-    __syncthreads();
-    if (tid < nb) {
-      float sr = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) sr += red[w * ATT_MAX_STAGES + tid];
-      sc[list[i0 + tid]] = sr;
-    }
-    __syncthreads();
-    float mb = m;
-    for (int r = 0; r < nb; ++r) mb = fmaxf(mb, sc[list[i0 + r]]);
-    const float corr = __expf(m - mb);
-    Z *= corr;
+  for (int i = 0; i < nvalid; ++i) {
+    const int s = i % NSTG;
+    mbar_wait(&full[s], (uint32_t)(i / NSTG) & 1u);
+    const float4* row4 = reinterpret_cast<const float4*>(ring + (size_t)s * D);
+    float4 v[NJ];
+    float part = 0.f;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      acc[j].x *= corr; acc[j].y *= corr; acc[j].z *= corr; acc[j].w *= corr;
+      const int idx = tid + NT * j;
+      v[j] = idx < nvec ? row4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+      part = fmaf(v[j].x, qv[j].x, part);
+      part = fmaf(v[j].y, qv[j].y, part);
+      part = fmaf(v[j].z, qv[j].z, part);
+      part = fmaf(v[j].w, qv[j].w, part);
     }
-    for (int r = 0; r < nb; ++r) {
-      const float e = __expf(sc[list[i0 + r]] - mb);
-      Z += e;
-      const float4* row4 = reinterpret_cast<const float4*>(ring + (size_t)r * D);
+    part = warp_sum(part);
+    float* rb = red + (i & 1) * NW;
+    if (lane == 0) rb[warp] = part;
+    __syncthreads();   // every thread holds its slice in registers -> the stage is free
+    if (tid == 0 && i + NSTG < nvalid) fetch(i + NSTG, s);
+    float sr = 0.f;
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const int idx = tid + ATT_THREADS * j;
-        if (idx < nvec) {
-          const float4 v = row4[idx];
-          acc[j].x = fmaf(e, v.x, acc[j].x);
-          acc[j].y = fmaf(e, v.y, acc[j].y);
-          acc[j].z = fmaf(e, v.z, acc[j].z);
-          acc[j].w = fmaf(e, v.w, acc[j].w);
-        }
-      }
+    for (int w = 0; w < NW; ++w) sr += rb[w];
+    if (tid == 0) sc[list[i]] = sr;
+    const float mn = fmaxf(m, sr);
+    const float corr = __expf(m - mn), e = __expf(sr - mn);
+    Z = fmaf(Z, corr, e);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      acc[j].x = fmaf(acc[j].x, corr, e * v[j].x);
+      acc[j].y = fmaf(acc[j].y, corr, e * v[j].y);
+      acc[j].z = fmaf(acc[j].z, corr, e * v[j].z);
+      acc[j].w = fmaf(acc[j].w, corr, e * v[j].w);
     }
-    m = mb;
-    if (i0 + NSTG < nvalid) {
-      __syncthreads();   // every thread is done with the ring -> refill it (one lane per row)
-      if (warp == 0) {
-        const int i = i0 + NSTG + lane;
-        if (lane < NSTG && i < nvalid) {
-          const int gr = r0 + list[i];
-          float* dst = ring + (size_t)lane * D;
-          mbar_expect_tx(&full[lane], (uint32_t)D * 4u);
-          bulk_g2s_hint(dst, p.segA + ba + (size_t)gr * p.strideA_r, (uint32_t)p.lenA * 4u, &full[lane], pol);
-          if (p.lenB > 0)
-            bulk_g2s_hint(dst + p.lenA, p.segB + bb + (size_t)gr * p.strideB_r, (uint32_t)p.lenB * 4u, &full[lane], pol);
-        }
-      }
-    }
+    m = mn;
   }
-  __syncthreads();   // sc[] complete
   trace_mark(p.trace, 5);
 
-  if (SPLIT == 1) {
-    const float inv = 1.0f / Z;
-    float4* out4 = reinterpret_cast<float4*>(p.out + (size_t)b * p.ldo);
+  // ---- 4. merge inside the cluster through distributed shared memory
+  if (tid == 0) {
+    stat[0] = m;
+    stat[1] = Z;
+  }
+  cluster_sync_all();   // stats + scores visible; every CTA of the cluster is done with its ring
+  trace_mark(p.trace, 6);
+  float M = -INFINITY, Zt = 0.f;
+  {
+    float mk[8], zk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      mk[k] = -INFINITY;
+      zk[k] = 0.f;
+      if (k < CL) {
+        const uint32_t a = dsmem_addr(stat, (uint32_t)k);
+        mk[k] = dsmem_ld_f32(a);
+        zk[k] = dsmem_ld_f32(a + 4u);
+      }
+      M = fmaxf(M, mk[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (mk[k] != -INFINITY) Zt = fmaf(zk[k], __expf(mk[k] - M), Zt);
+  }
+  const float inv = Zt > 0.f ? 1.0f / Zt : 0.f;      // every row masked -> zeros (the reference would give NaN)
+  const float wgt = (m == -INFINITY) ? 0.f : __expf(m - M) * inv;
+  const int cpo = (nvec + CL - 1) / CL;             // float4 columns per owner CTA
+  {
+    const uint32_t inbox = smem_u32(ring);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const int idx = tid + ATT_THREADS * j;
-      if (idx < nvec) out4[idx] = make_float4(acc[j].x * inv, acc[j].y * inv, acc[j].z * inv, acc[j].w * inv);
-    }
-    if (p.alpha)
-      for (int r = tid; r < nrows; r += ATT_THREADS)
-        p.alpha[(size_t)b * p.ldalpha + r0 + r] = sc[r] == -INFINITY ? 0.f : __expf(sc[r] - m) * inv;
-    trace_mark(p.trace, 2);
-    return;
-  }
-
-  // ---- 4. publish this CTA's partial (m, Z, weighted sum) and its raw scores; the last arriver merges
-  const int PS = D + 4;   // floats per partial record
-  float* mine = p.part + ((size_t)b * SPLIT + split) * PS;
-  if (tid == 0) {
-    mine[0] = m;
-    mine[1] = Z;
-  }
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    const int idx = tid + ATT_THREADS * j;
-    if (idx < nvec) __stcg(reinterpret_cast<float4*>(mine + 4) + idx, acc[j]);
-  }
-  if (p.alpha)
-    for (int r = tid; r < nrows; r += ATT_THREADS) __stcg(p.alpha + (size_t)b * p.ldalpha + r0 + r, sc[r]);
-  trace_mark(p.trace, 6);
-  __threadfence();
-  __syncthreads();
-  trace_mark(p.trace, 7);
-  if (tid == 0) {
-    const unsigned int t = atomicAdd(p.ticket + b, 1u);
-    s_last = (t == (unsigned int)SPLIT - 1u);
-    if (s_last) atomicExch(p.ticket + b, 0u);   // re-arm for the next launch
-    __threadfence();
-  }
-  __syncthreads();
-  trace_mark(p.trace, 8);
-  if (!s_last) { trace_mark(p.trace, 2); return; }
-
-  // merge: every load of a phase is independent (two L2 round trips in total, not one per partial)
-  const float* recs = p.part + (size_t)b * SPLIT * PS;
-  float wk[16];
-  {
-    float mk[16], zk[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      mk[k] = k < SPLIT ? __ldcg(recs + (size_t)k * PS) : -INFINITY;
-      zk[k] = k < SPLIT ? __ldcg(recs + (size_t)k * PS + 1) : 0.f;
-    }
-    float M = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) M = fmaxf(M, mk[k]);
-    float Zt = 0.f;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      wk[k] = (mk[k] == -INFINITY) ? 0.f : __expf(mk[k] - M);
-      Zt = fmaf(zk[k], wk[k], Zt);
-    }
-    const float inv = 1.0f / Zt;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) wk[k] *= inv;
-    if (p.alpha) {   // raw scores -> probabilities (masked rows hold -inf -> 0)
-      float* al = p.alpha + (size_t)b * p.ldalpha;
-      for (int r = tid; r < p.R; r += ATT_THREADS) {
-        const float sv = __ldcg(al + r);
-        al[r] = (sv == -INFINITY) ? 0.f : __expf(sv - M) * inv;
+      const int idx = tid + NT * j;
+      if (idx < nvec) {
+        const int owner = idx / cpo, lc = idx - owner * cpo;
+        const uint32_t base = CL > 1 ? dsmem_addr(ring, (uint32_t)owner) : inbox;
+        st_cluster_f32x4(base + (uint32_t)(rank * cpo + lc) * 16u,
+                         make_float4(acc[j].x * wgt, acc[j].y * wgt, acc[j].z * wgt, acc[j].w * wgt));
       }
     }
   }
-  float4* out4 = reinterpret_cast<float4*>(p.out + (size_t)b * p.ldo);
-  for (int idx = tid; idx < nvec; idx += ATT_THREADS) {
-    float4 a[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-      a[k] = k < SPLIT ? __ldcg(reinterpret_cast<const float4*>(recs + (size_t)k * PS + 4) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      o.x = fmaf(wk[k], a[k].x, o.x);
-      o.y = fmaf(wk[k], a[k].y, o.y);
-      o.z = fmaf(wk[k], a[k].z, o.z);
-      o.w = fmaf(wk[k], a[k].w, o.w);
+  if (p.alpha)
+    for (int i = tid; i < nmine; i += NT)
+      p.alpha[(size_t)b * p.ldalpha + rank + CL * i] = sc[i] == -INFINITY ? 0.f : __expf(sc[i] - M) * inv;
+  cluster_sync_all();   // pushed partial columns visible to their owner
+  trace_mark(p.trace, 7);
+  {
+    const float4* in4 = reinterpret_cast<const float4*>(ring);
+    float4* out4 = reinterpret_cast<float4*>(p.out + (size_t)b * p.ldo);
+    for (int lc = tid; lc < cpo; lc += NT) {
+      const int col = rank * cpo + lc;
+      if (col >= nvec) break;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < CL; ++k) {
+        const float4 a = in4[k * cpo + lc];
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      out4[col] = o;
     }
-    out4[idx] = o;
   }
-  if (p.trace && tid == 0) p.trace[3] = globaltimer_ns();   // exit of a merging CTA (any block)
+  trace_mark(p.trace, 2);
+  if (p.trace && tid == 0 && b == gridDim.y - 1 && rank == CL - 1) p.trace[3] = globaltimer_ns();   // last cluster
 }
 
 // ------------------------------------------------------------------ host launcher
 
-static size_t attn_smem_bytes(int stages, int D) {
-  return (size_t)stages * D * sizeof(float) + (size_t)stages * sizeof(uint64_t) + 8 * ATT_MAX_STAGES * sizeof(float) +
-         ATT_MAX_ROWS * (sizeof(float) + sizeof(int));
+static size_t attn_smem_bytes(int stages, int D, int rows_per_cta) {
+  return (size_t)stages * D * sizeof(float) + (size_t)stages * sizeof(uint64_t) + (2 * 8 + 2) * sizeof(float) +
+         (size_t)rows_per_cta * (sizeof(float) + sizeof(int));
 }
 
 AttnPlan attention_plan(int B, int R, int D, int num_sms) {
   AttnPlan pl{};
-  // enough CTAs to cover the machine ~2.5x, at least 4 rows per CTA, at most ATT_MAX_ROWS rows per CTA
-  int split = 1;
-  while (split < 16 && ((long long)B * split < (long long)(5 * num_sms) / 2) && (R + split) / (split * 2) >= 4) split *= 2;
-  while ((R + split - 1) / split > ATT_MAX_ROWS) split *= 2;
-  pl.split = split;
-  pl.rows_per_cta = (R + split - 1) / split;
-  int stages = (int)((44 * 1024) / ((size_t)D * 4));     // <= 44 KB ring -> 5 CTAs per SM; a pass = the whole ring
+  // cluster size: as many CTAs per batch element as still fit in ONE resident wave (3 CTAs per SM), >= 4 rows each
+  int cl = 1;
+  while (cl < 8 && (long long)B * cl * 2 <= 3LL * num_sms && R / (cl * 2) >= 4) cl *= 2;
+  pl.split = cl;
+  pl.rows_per_cta = (R + cl - 1) / cl;
+  int stages = (int)(ATT_RING_BUDGET / ((size_t)D * 4));
   if (stages > pl.rows_per_cta) stages = pl.rows_per_cta;
-  if (stages < 1) stages = 1;
   if (stages > ATT_MAX_STAGES) stages = ATT_MAX_STAGES;
+  if (stages < 2) stages = 2;   // the ring doubles as the merge inbox (one row + rounding)
   pl.stages = stages;
-  pl.ticket_bytes = ((size_t)B * sizeof(unsigned int) + 255) & ~size_t(255);
-  pl.bytes = pl.ticket_bytes + (((size_t)B * split * (D + 4) * sizeof(float) + 255) & ~size_t(255));
+  pl.ticket_bytes = 0;
+  pl.bytes = 256;   // no global scratch any more; kept non-zero so workspace carving stays uniform
   return pl;
 }
 
-template <int NJ>
-static int32_t launch_attn_t(const AttnParams& p, int B, int split, cudaStream_t stream) {
-  auto kern = soft_dot_attn_kernel<NJ>;
-  const size_t smem = attn_smem_bytes(p.stages, p.D);
+template <int NJ, int NT>
+static int32_t launch_attn_t(const AttnParams& p, int B, int cl, cudaStream_t stream) {
+  auto kern = soft_dot_attn_kernel<NJ, NT>;
+  const size_t smem = attn_smem_bytes(p.stages, p.D, p.rows_per_cta);
   static size_t configured = 0;  // per instantiation
   if (smem > configured) {
     SFB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  SFB_CHECK_CUDA(launch_ex(kern, dim3(split, B, 1), dim3(ATT_THREADS, 1, 1), smem, stream, dim3(1, 1, 1), p));
+  SFB_CHECK_CUDA(launch_ex(kern, dim3(cl, B, 1), dim3(NT, 1, 1), smem, stream, dim3(cl, 1, 1), p));
   count_launch();
   return 0;
 }
 
 int32_t launch_soft_dot_attention(AttnParams p, int B, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  (void)ws; (void)ws_bytes;
   SFB_CHECK_ARG(p.D > 0 && (p.D % 4) == 0, "attention row length must be a positive multiple of 4");
   SFB_CHECK_ARG(p.D <= 3072, "attention row length > 3072 is not supported");
   SFB_CHECK_ARG((p.lenA % 4) == 0 && (p.lenB % 4) == 0 && p.lenA + p.lenB == p.D, "bad row segments");
   SFB_CHECK_ARG(p.R >= 1, "need at least one row");
+  SFB_CHECK_ARG(B <= 65535, "attention: batch > 65535");
   const AttnPlan pl = attention_plan(B, p.R, p.D, device_num_sms());
-  SFB_CHECK_ARG(ws && ws_bytes >= pl.bytes && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "attention: workspace");
   p.rows_per_cta = pl.rows_per_cta;
   p.stages = pl.stages;
   p.trace = next_trace_slot();
-  p.ticket = static_cast<unsigned int*>(ws);
-  p.part = reinterpret_cast<float*>(static_cast<char*>(ws) + pl.ticket_bytes);
-  SFB_CHECK_ARG(attn_smem_bytes(p.stages, p.D) <= 200 * 1024, "attention rows do not fit shared memory");
-  return p.D <= 1024 ? launch_attn_t<1>(p, B, pl.split, stream) : launch_attn_t<3>(p, B, pl.split, stream);
+  p.ticket = nullptr;
+  p.part = nullptr;
+  SFB_CHECK_ARG(attn_smem_bytes(p.stages, p.D, p.rows_per_cta) <= 200 * 1024, "attention rows do not fit shared memory");
+  if (p.D <= 512) return launch_attn_t<1, 128>(p, B, pl.split, stream);
+  if (p.D <= 1024) return launch_attn_t<1, 256>(p, B, pl.split, stream);
+  return launch_attn_t<3, 256>(p, B, pl.split, stream);
 }
 
 }  // namespace sfb

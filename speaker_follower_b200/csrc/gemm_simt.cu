@@ -1,4 +1,7 @@
-// gemm_simt.cu — exact-fp32 "skinny" GEMM on the FFMA pipe:  out[M,N] = sum_s X_s[M,k_s] · W_s^T  (+epilogue)
+// gemm_simt.cu — "skinny" GEMM:  out[M,N] = sum_s X_s[M,k_s] · W_s^T  (+epilogue), two arithmetic paths that share
+// the tile movement: exact fp32 on the FFMA pipe, and 3xTF32 error-compensated mma.sync (hi·hi + hi·lo + lo·hi,
+// fp32 accumulate, per-product error ~2^-21) for the projections on the step's dependency chain, where the FFMA
+// pipe (64 FMA/clk/SM) — not memory — set the latency.
 //
 // M is the batch (<= a few hundred rows), the weights are streamed once.  K may be the concatenation of
 // up to three segments with their own activation/weight pointers, which is how cat(u_prev, feature)
@@ -20,7 +23,9 @@
 namespace sfb {
 
 namespace {
-constexpr int BN = 32, BK = 32, SA = 36, SB = 36, SR = 33;
+constexpr int BN = 32, BK = 32, SA = 36, SR = 33;
+// weight-tile row stride: 36 ([N,k] tiles; FFMA and mma B fragments conflict-free), 40 for [k,N] tiles on the mma path
+template <bool KN, bool TC> struct SBStride { static constexpr int v = (KN && TC) ? 40 : 36; };
 constexpr int MAXC = 4;   // K chunks resident in shared memory per pass
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
@@ -31,12 +36,26 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// x = hi + lo with hi, lo representable in TF32 (round-to-nearest)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 }  // namespace
 
 // grid = (N tiles, splitk, M tiles); cluster = (1, splitk, 1); dynamic smem = MAXC*(As+Bs) [+ scale tiles] + recv
-template <int TM, bool KN, bool HAS_XS>
+// TC (TM == 4 only): warp w owns rows 16w..16w+15 of the 128-row tile and all 32 columns (4 m16n8k8 tiles).
+template <int TM, bool KN, bool HAS_XS, bool TC>
 __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
   constexpr int BM = 32 * TM;
+  constexpr int SB = SBStride<KN, TC>::v;
+  static_assert(!TC || TM == 4, "mma path is built for the 128-row tile");
   extern __shared__ __align__(16) float dsm[];
   float* As = dsm;                                   // [MAXC][BM][SA]
   float* Bs = As + MAXC * BM * SA;                   // [MAXC][32][SB]
@@ -129,40 +148,74 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
       const float* Ak = As + k * BM * SA;
       const float* Bk = Bs + k * 32 * SB;
       const float* Xk = Xs + k * BM * SA;
+      if constexpr (TC) {
+        const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+        if (m0 + 16 * warp < p.M) {   // warps whose 16 rows are all padding do nothing
 #pragma unroll
-      for (int k4 = 0; k4 < BK / 4; ++k4) {
-        float4 a[TM];
+          for (int k8 = 0; k8 < BK / 8; ++k8) {
+            const int ra = (16 * warp + g) * SA + k8 * 8 + t;
+            float av[4] = {Ak[ra], Ak[ra + 8 * SA], Ak[ra + 4], Ak[ra + 8 * SA + 4]};
+            if (HAS_XS) {
+              av[0] *= Xk[ra]; av[1] *= Xk[ra + 8 * SA]; av[2] *= Xk[ra + 4]; av[3] *= Xk[ra + 8 * SA + 4];
+            }
+            uint32_t ah[4], al[4];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-          a[i] = *reinterpret_cast<const float4*>(&Ak[(ty + 32 * i) * SA + k4 * 4]);
-          if (HAS_XS) {
-            const float4 sc = *reinterpret_cast<const float4*>(&Xk[(ty + 32 * i) * SA + k4 * 4]);
-            a[i].x *= sc.x; a[i].y *= sc.y; a[i].z *= sc.z; a[i].w *= sc.w;
-          }
-        }
-        if (!KN) {
+            for (int q = 0; q < 4; ++q) split_tf32(av[q], ah[q], al[q]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b = *reinterpret_cast<const float4*>(&Bk[(tx + 8 * j) * SB + k4 * 4]);
-#pragma unroll
-            for (int i = 0; i < TM; ++i) {
-              acc[i][j] = fmaf(a[i].x, b.x, acc[i][j]);
-              acc[i][j] = fmaf(a[i].y, b.y, acc[i][j]);
-              acc[i][j] = fmaf(a[i].z, b.z, acc[i][j]);
-              acc[i][j] = fmaf(a[i].w, b.w, acc[i][j]);
+            for (int nt = 0; nt < 4; ++nt) {
+              float b0, b1;
+              if (!KN) {
+                b0 = Bk[(nt * 8 + g) * SB + k8 * 8 + t];
+                b1 = Bk[(nt * 8 + g) * SB + k8 * 8 + t + 4];
+              } else {
+                b0 = Bk[(k8 * 8 + t) * SB + nt * 8 + g];
+                b1 = Bk[(k8 * 8 + t + 4) * SB + nt * 8 + g];
+              }
+              uint32_t bh0, bl0, bh1, bl1;
+              split_tf32(b0, bh0, bl0);
+              split_tf32(b1, bh1, bl1);
+              mma_tf32(acc[nt], al, bh0, bh1);   // small terms first
+              mma_tf32(acc[nt], ah, bl0, bl1);
+              mma_tf32(acc[nt], ah, bh0, bh1);
             }
           }
-        } else {
+        }
+      } else {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const float4 b = *reinterpret_cast<const float4*>(&Bk[(k4 * 4 + kk) * SB + tx * 4]);
+        for (int k4 = 0; k4 < BK / 4; ++k4) {
+          float4 a[TM];
 #pragma unroll
-            for (int i = 0; i < TM; ++i) {
-              const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
-              acc[i][0] = fmaf(av, b.x, acc[i][0]);
-              acc[i][1] = fmaf(av, b.y, acc[i][1]);
-              acc[i][2] = fmaf(av, b.z, acc[i][2]);
-              acc[i][3] = fmaf(av, b.w, acc[i][3]);
+          for (int i = 0; i < TM; ++i) {
+            a[i] = *reinterpret_cast<const float4*>(&Ak[(ty + 32 * i) * SA + k4 * 4]);
+            if (HAS_XS) {
+              const float4 sc = *reinterpret_cast<const float4*>(&Xk[(ty + 32 * i) * SA + k4 * 4]);
+              a[i].x *= sc.x; a[i].y *= sc.y; a[i].z *= sc.z; a[i].w *= sc.w;
+            }
+          }
+          if (!KN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = *reinterpret_cast<const float4*>(&Bk[(tx + 8 * j) * SB + k4 * 4]);
+#pragma unroll
+              for (int i = 0; i < TM; ++i) {
+                acc[i][j] = fmaf(a[i].x, b.x, acc[i][j]);
+                acc[i][j] = fmaf(a[i].y, b.y, acc[i][j]);
+                acc[i][j] = fmaf(a[i].z, b.z, acc[i][j]);
+                acc[i][j] = fmaf(a[i].w, b.w, acc[i][j]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const float4 b = *reinterpret_cast<const float4*>(&Bk[(k4 * 4 + kk) * SB + tx * 4]);
+#pragma unroll
+              for (int i = 0; i < TM; ++i) {
+                const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+                acc[i][0] = fmaf(av, b.x, acc[i][0]);
+                acc[i][1] = fmaf(av, b.y, acc[i][1]);
+                acc[i][2] = fmaf(av, b.z, acc[i][2]);
+                acc[i][3] = fmaf(av, b.w, acc[i][3]);
+              }
             }
           }
         }
@@ -171,24 +224,44 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
   }
   trace_mark(p.trace, 5);
 
-  // local tile column of accumulator j of this thread
-  auto col_of = [&](int j) { return KN ? tx * 4 + j : tx + 8 * j; };
+  // tile-local (row, column) of accumulator acc[i][j] of this thread
+  auto row_of = [&](int i, int j) {
+    if constexpr (TC) return 16 * (tid >> 5) + ((tid & 31) >> 2) + 8 * (j >> 1);
+    else return ty + 32 * i;
+  };
+  auto col_of = [&](int i, int j) {
+    if constexpr (TC) return i * 8 + 2 * (tid & 3) + (j & 1);
+    else return KN ? tx * 4 + j : tx + 8 * j;
+  };
 
   if (S == 1) {
+    if (lstm) {
+      // gate-interleaved tile: column = gate*8 + unit.  FFMA: acc[i][gate] of unit tx, row ty+32i.
+      // mma: acc[gate][2*half+e] of unit 2t+e, row 16w+g+8*half.
+      if constexpr (TC) {
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      const int m = m0 + ty + 32 * i;
-      if (m >= p.M) continue;
-      if (lstm) {
-        const int unit = blockIdx.x * 8 + tx;   // NT layout: accumulator j is gate j of unit tx
-        if (unit < p.lstm.H) lstm_update(p, m, unit, acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int m = m0 + row_of(0, 2 * hh), unit = blockIdx.x * 8 + 2 * (tid & 3) + e;
+            if (m < p.M && unit < p.lstm.H)
+              lstm_update(p, m, unit, acc[0][2 * hh + e], acc[1][2 * hh + e], acc[2][2 * hh + e], acc[3][2 * hh + e]);
+          }
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int n = n0 + col_of(j);
-          if (n < p.N) plain_store(p, m, n, acc[i][j]);
+        for (int i = 0; i < TM; ++i) {
+          const int m = m0 + ty + 32 * i, unit = blockIdx.x * 8 + tx;
+          if (m < p.M && unit < p.lstm.H) lstm_update(p, m, unit, acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
       }
+    } else {
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int m = m0 + row_of(i, j), n = n0 + col_of(i, j);
+          if (m < p.M && n < p.N) plain_store(p, m, n, acc[i][j]);
+        }
     }
     trace_mark(p.trace, 2);
     return;
@@ -201,12 +274,13 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmParams p) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) peer[k] = k < S ? dsmem_addr(recv, k) : 0u;
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      const int r = ty + 32 * i, owner = r / rows_per, lr = r - owner * rows_per;
-      const uint32_t base = peer[owner] + (uint32_t)((rank * rows_per + lr) * SR) * 4u;
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) st_cluster_f32(base + (uint32_t)col_of(j) * 4u, acc[i][j]);
-    }
+      for (int j = 0; j < 4; ++j) {
+        const int r = row_of(i, j), owner = r / rows_per, lr = r - owner * rows_per;
+        if (m0 + r < p.M)   // padding rows are never read back
+          st_cluster_f32(peer[owner] + (uint32_t)((rank * rows_per + lr) * SR + col_of(i, j)) * 4u, acc[i][j]);
+      }
   }
   trace_mark(p.trace, 6);
   cluster_sync_all();   // release/acquire: the pushed rows are visible to their owner
@@ -251,19 +325,20 @@ int gemm_pick_splitk(int M, int N, int ktotal, int num_sms) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <int TM, bool KN, bool HAS_XS>
+template <int TM, bool KN, bool HAS_XS, bool TC>
 static int32_t launch_t(const GemmParams& p, dim3 grid, cudaStream_t stream) {
   constexpr int BM = 32 * TM;
+  constexpr int SB = SBStride<KN, TC>::v;
   const int rows_per = (BM + p.splitk - 1) / p.splitk;
   const size_t tiles = ((size_t)MAXC * (BM * SA + 32 * SB) + (HAS_XS ? (size_t)MAXC * BM * SA : 0)) * sizeof(float);
   const size_t smem = tiles + (size_t)p.splitk * rows_per * SR * sizeof(float);
   static bool configured = false;   // per instantiation
   if (!configured) {
     const size_t mx = tiles + (size_t)(BM + 8) * SR * sizeof(float);
-    SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<TM, KN, HAS_XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+    SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<TM, KN, HAS_XS, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
     configured = true;
   }
-  SFB_CHECK_CUDA(launch_ex(gemm_skinny_kernel<TM, KN, HAS_XS>, grid, dim3(256, 1, 1), smem, stream, dim3(1, p.splitk, 1), p));
+  SFB_CHECK_CUDA(launch_ex(gemm_skinny_kernel<TM, KN, HAS_XS, TC>, grid, dim3(256, 1, 1), smem, stream, dim3(1, p.splitk, 1), p));
   count_launch();
   return 0;
 }
@@ -292,11 +367,15 @@ int32_t launch_gemm(const GemmParams& p_in, cudaStream_t stream) {
   const int tm = p.M <= 32 ? 1 : 4;
   dim3 grid((p.N + BN - 1) / BN, p.splitk, (p.M + 32 * tm - 1) / (32 * tm));
   if (tm == 1) {
-    if (has_xs) return kn ? launch_t<1, true, true>(p, grid, stream) : launch_t<1, false, true>(p, grid, stream);
-    return kn ? launch_t<1, true, false>(p, grid, stream) : launch_t<1, false, false>(p, grid, stream);
+    if (has_xs) return kn ? launch_t<1, true, true, false>(p, grid, stream) : launch_t<1, false, true, false>(p, grid, stream);
+    return kn ? launch_t<1, true, false, false>(p, grid, stream) : launch_t<1, false, false, false>(p, grid, stream);
   }
-  if (has_xs) return kn ? launch_t<4, true, true>(p, grid, stream) : launch_t<4, false, true>(p, grid, stream);
-  return kn ? launch_t<4, true, false>(p, grid, stream) : launch_t<4, false, false>(p, grid, stream);
+  if (!g_disable_tc && !p.exact) {   // 3xTF32 mma.sync
+    if (has_xs) return kn ? launch_t<4, true, true, true>(p, grid, stream) : launch_t<4, false, true, true>(p, grid, stream);
+    return kn ? launch_t<4, true, false, true>(p, grid, stream) : launch_t<4, false, false, true>(p, grid, stream);
+  }
+  if (has_xs) return kn ? launch_t<4, true, true, false>(p, grid, stream) : launch_t<4, false, true, false>(p, grid, stream);
+  return kn ? launch_t<4, true, false, false>(p, grid, stream) : launch_t<4, false, false, false>(p, grid, stream);
 }
 
 }  // namespace sfb

@@ -65,6 +65,7 @@ struct GemmParams {
   const float* bias0; const float* bias1; // [N] or NULL
   const float* oscale;                    // [N] or NULL: out = act(acc + biases) * oscale[n]
   int act;                                // 0 none, 1 tanh
+  int exact;                              // 1: force the exact-fp32 FFMA path (default: 3xTF32 mma.sync for M > 32)
   LstmEpilogue lstm;
   unsigned long long* trace;              // bring-up: 3 timestamps of block 0, or NULL
 };
