@@ -10,7 +10,8 @@
  *   - all tensors fp32 row-major contiguous unless a leading dimension is given; indices int32;
  *     masks uint8 (1 = masked / padded), exactly the reference's ByteTensor masks (follower.py:101).
  *   - weights are passed in the reference's own state_dict layouts ([out_features, in_features]
- *     row-major), so nn.Parameter storage is used in place; nothing is re-laid-out or cached.
+ *     row-major), so nn.Parameter storage is used in place; the only derived copy is the caller-owned
+ *     packed blob of sfb_follower_pack_weights (explicit, refreshed by the caller when weights change).
  *   - return value: 0 on success, negative sfb_status on error; sfb_last_error() gives the message of
  *     the last failure on the calling thread.  Argument errors are detected before any launch.
  *   - every function only enqueues work on `stream`.
@@ -146,6 +147,31 @@ int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
                               const float* drop_x, const float* drop_h,
                               float* h1, float* c1, float* alpha, float* logit, float* alpha_v,
                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- packed-weight fast path of the same step (AttnDecoderLSTM.forward, model.py:377-397) ------------------
+ * sfb_follower_pack_weights re-lays the decoder weights out ONCE PER WEIGHT VERSION into a caller-owned device
+ * blob ("shadow copies refreshed when param._version changes"):
+ *   - every projection matrix as bf16 (hi, lo) pairs in tcgen05's shared-memory operand layout, one contiguous
+ *     32 KB block per (128-row tile, 64-wide K block), LSTM gates interleaved so a tile owns whole cells;
+ *   - linear_in_h/linear_in_v of the visual attention folded into M_q = W_v^T W_h (model.py:316-320) and
+ *     EltwiseProdScoring folded into M_g = W_a^T diag(w_o) W_h' plus one constant row (model.py:348-351).
+ * sfb_follower_step_packed_fwd then runs the step as: q projection -> attention gather -> pack activations ->
+ * gate GEMM + LSTM cell -> [t | W_out_h h] projection -> text attention -> h~ projection -> g projection ->
+ * action logits (9 launches, all projections on tcgen05 fed by bulk async copies).  Same arguments, outputs and
+ * workspace as sfb_follower_step_fwd; `wl` is still needed for the LSTM biases.  Requires H % 128 == 0 and
+ * E, F % 8 == 0 (sfb_follower_packed_bytes returns 0 otherwise -> use sfb_follower_step_fwd). */
+size_t  sfb_follower_packed_bytes(const sfb_dims* dims);
+int32_t sfb_follower_pack_weights(const sfb_dims* dims, const sfb_vis_lstm_weights* wl,
+                                  const sfb_softdot_weights* wt, const sfb_scoring_weights* ws,
+                                  void* packed, size_t packed_bytes, void* stream);
+int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* wl,
+                                     const void* packed, size_t packed_bytes,
+                                     int32_t B, int32_t L, int32_t A,
+                                     const float* u_prev, const float* all_u_t, const sfb_visual_source* vis,
+                                     const float* h0, const float* c0, const float* ctx, const uint8_t* ctx_mask,
+                                     const float* drop_x, const float* drop_h,
+                                     float* h1, float* c1, float* alpha, float* logit, float* alpha_v,
+                                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* Per-step tail of Seq2SeqAgent._rollout_with_loss — follower.py:476-505.
  *   logit [B,A] is masked IN PLACE with -inf where is_valid == 0 (477);

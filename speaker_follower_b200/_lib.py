@@ -78,6 +78,15 @@ SIGNATURES = {
                                           c_float_p, c_u8_p, c_float_p, c_float_p,
                                           c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                           C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sfb_follower_packed_bytes": (C.c_size_t, [C.POINTER(Dims)]),
+    "sfb_follower_pack_weights": (C.c_int32, [C.POINTER(Dims), C.POINTER(VisLstmWeights), C.POINTER(SoftDotWeights),
+                                              C.POINTER(ScoringWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sfb_follower_step_packed_fwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(VisLstmWeights), C.c_void_p, C.c_size_t,
+                                                 C.c_int32, C.c_int32, C.c_int32,
+                                                 c_float_p, c_float_p, C.POINTER(VisualSource), c_float_p, c_float_p,
+                                                 c_float_p, c_u8_p, c_float_p, c_float_p,
+                                                 c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                                 C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_follower_step_tail": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, c_float_p, c_float_p, c_int_p, C.c_int32,
                                            c_float_p, c_float_p, c_int_p, c_float_p, c_float_p, c_float_p,
                                            C.c_void_p]),

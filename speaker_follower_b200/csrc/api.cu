@@ -51,9 +51,16 @@ struct FollowerWs {
   void* av; size_t av_bytes;              // visual attention: tickets + partial records
   void* at; size_t at_bytes;              // text attention
   float *tv, *q, *feat, *gates_act, *h1d, *t, *wc, *htilde, *tp, *g;
+  // packed-weight path (gemm_pk.cu): semaphores + partial tiles, packed gate-GEMM activations, [t | W_out_h h] buffer
+  void* pk; size_t pk_bytes;
+  unsigned char* bpk; size_t bpk_bytes;
+  float* th;
+  int ldg;
   int splitk;
   size_t bytes;
 };
+
+static int kblocks(int k) { return (k + 63) / 64; }
 
 static int gates_splitk(const sfb_dims& d, int B) {
   return gemm_pick_splitk(B, 4 * d.H, d.E + d.F + d.H, device_num_sms());
@@ -80,9 +87,54 @@ static FollowerWs carve_follower(const sfb_dims& d, int B, int L, int A, void* w
   w.wc = c.take((size_t)B * d.H);
   w.htilde = c.take((size_t)B * d.H);
   w.tp = c.take((size_t)B * d.D);
-  w.g = c.take((size_t)B * kmax);
+  w.ldg = kmax + 4;
+  w.g = c.take((size_t)B * w.ldg);
+  {
+    const int sms = device_num_sms();
+    const int nkb_h = kblocks(d.H), nkb_g = kblocks(d.E) + kblocks(d.F) + kblocks(d.H);
+    size_t mx = gemm_pk_plan(B, 4 * d.H, nkb_g, true, sms).bytes;
+    const int rows[4] = {d.F, 2 * d.H, d.H, d.E + 1};
+    for (int i = 0; i < 4; ++i) {
+      const size_t b = gemm_pk_plan(B, rows[i], nkb_h, false, sms).bytes;
+      if (b > mx) mx = b;
+    }
+    w.pk_bytes = mx;
+    w.pk = c.take(mx / sizeof(float));
+    w.bpk_bytes = pk_act_bytes(B, nkb_g);
+    w.bpk = reinterpret_cast<unsigned char*>(c.take(w.bpk_bytes / sizeof(float)));
+    w.th = c.take((size_t)B * 2 * d.H);
+  }
   w.bytes = c.off;
   return w;
+}
+
+// ---- packed follower-decoder weights: offsets into the caller-owned blob
+struct FollowerPk {
+  size_t a_q, b_q, a_gates, a_th, a_wc, a_g, b_g, mq, mg, bytes;
+  int nkb_h, nkb_gates;
+};
+static FollowerPk layout_follower_pk(const sfb_dims& d) {
+  FollowerPk L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t r = off; off += (bytes + 255) & ~size_t(255); return r; };
+  L.nkb_h = kblocks(d.H);
+  L.nkb_gates = kblocks(d.E) + kblocks(d.F) + kblocks(d.H);
+  L.a_q = take(pk_weight_bytes(d.F, L.nkb_h));
+  L.b_q = take((size_t)d.F * 4);
+  L.a_gates = take(pk_weight_bytes(4 * d.H, L.nkb_gates));
+  L.a_th = take(pk_weight_bytes(2 * d.H, L.nkb_h));
+  L.a_wc = take(pk_weight_bytes(d.H, L.nkb_h));
+  L.a_g = take(pk_weight_bytes(d.E + 1, L.nkb_h));
+  L.b_g = take((size_t)(d.E + 4) * 4);
+  L.mq = take((size_t)d.F * d.H * 4);
+  L.mg = take((size_t)(d.E + 1) * d.H * 4);
+  L.bytes = off;
+  return L;
+}
+static int32_t check_packable(const sfb_dims& d) {
+  SFB_CHECK_ARG((d.H % 128) == 0 && (d.E % 8) == 0 && (d.F % 8) == 0 && (d.D % 4) == 0,
+                "packed path needs H % 128 == 0 and E, F % 8 == 0");
+  return 0;
 }
 
 struct SpkDecWs {
@@ -375,7 +427,7 @@ int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
     g2.seg[0] = GemmSeg{ws.tp, d.D, nullptr, nullptr, 0, wsc->w_a, d.E, d.D, 1};
     g2.M = B; g2.N = d.E; g2.splitk = gemm_pick_splitk(B, d.E, d.D, device_num_sms()); g2.out = ws.g; g2.ldo = d.E;
     SFB_PROPAGATE(launch_gemm(g2, st));
-    ScoringParams sp{all_u_t, ws.g, ws.tp, wsc->b_a, wsc->b_out, logit, B, A, d.E, d.D};
+    ScoringParams sp{all_u_t, ws.g, ws.tp, wsc->b_a, wsc->b_out, d.E, logit, B, A, d.E, d.D};
     SFB_PROPAGATE(launch_action_scoring(sp, st));
   }
   return 0;
@@ -509,6 +561,127 @@ int32_t sfb_speaker_decoder_step_fwd(const sfb_speaker_decoder_weights* w, int32
   g.seg[0] = GemmSeg{ws.htilde, H, nullptr, nullptr, 0, w->w_voc, H, H, 0};
   g.M = B; g.N = vocab; g.splitk = gemm_pick_splitk(B, vocab, H, device_num_sms()); g.out = logit; g.ldo = vocab; g.bias0 = w->b_voc;
   return launch_gemm(g, st);
+}
+
+size_t sfb_follower_packed_bytes(const sfb_dims* dims) {
+  if (!dims || check_dims(dims) != 0 || check_packable(*dims) != 0) return 0;
+  return layout_follower_pk(*dims).bytes;
+}
+
+int32_t sfb_follower_pack_weights(const sfb_dims* dims, const sfb_vis_lstm_weights* wl, const sfb_softdot_weights* wt,
+                                  const sfb_scoring_weights* wsc, void* packed, size_t packed_bytes, void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_PROPAGATE(check_packable(*dims));
+  SFB_CHECK_ARG(wl && wt && wsc && packed, "NULL argument");
+  const sfb_dims& d = *dims;
+  const FollowerPk L = layout_follower_pk(d);
+  SFB_CHECK_ARG(packed_bytes >= L.bytes && (reinterpret_cast<uintptr_t>(packed) & 255u) == 0, "packed buffer too small / misaligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned char* base = static_cast<unsigned char*>(packed);
+  float* mq = reinterpret_cast<float*>(base + L.mq);
+  float* mg = reinterpret_cast<float*>(base + L.mg);
+  float* bq = reinterpret_cast<float*>(base + L.b_q);
+  float* bg = reinterpret_cast<float*>(base + L.b_g);
+  // M_q = W_v^T W_h, b_q = W_v^T b_h           (model.py:316-320; b_v . t cancels in the softmax)
+  SFB_PROPAGATE(launch_fold(wl->va_w_v, d.F, nullptr, wl->va_w_h, d.H, wl->va_b_h, d.D, d.F, d.H, mq, d.H, bq, nullptr, st));
+  // M_g = W_a^T diag(w_o) W_h', b_g = W_a^T (w_o . b_h'); extra row E carries the per-row constant
+  // (b_a . w_o)^T (W_h' h~ + b_h') + b_o       (model.py:348-351)
+  SFB_PROPAGATE(launch_fold(wsc->w_a, d.E, wsc->w_out, wsc->w_h, d.H, wsc->b_h, d.D, d.E, d.H, mg, d.H, bg, nullptr, st));
+  SFB_PROPAGATE(launch_fold(wsc->b_a, 1, wsc->w_out, wsc->w_h, d.H, wsc->b_h, d.D, 1, d.H, mg + (size_t)d.E * d.H, d.H,
+                            bg + d.E, wsc->b_out, st));
+  auto plain = [&](const float* w, int ldw, int rows, int k, unsigned char* out) {
+    PackParams p{};
+    p.nseg = 1;
+    p.seg[0] = PackSeg{w, ldw, k, nullptr, 0, nullptr};
+    p.ntile = (rows + 127) / 128; p.R = 128; p.rows_per_tile = 128; p.rows_valid = rows; p.lstm_H = 0;
+    p.out = out;
+    return launch_pack_rows(p, st);
+  };
+  SFB_PROPAGATE(plain(mq, d.H, d.F, d.H, base + L.a_q));
+  {
+    PackParams p{};
+    p.nseg = 3;
+    p.seg[0] = PackSeg{wl->lstm_w_ih, d.E + d.F, d.E, nullptr, 0, nullptr};
+    p.seg[1] = PackSeg{wl->lstm_w_ih + d.E, d.E + d.F, d.F, nullptr, 0, nullptr};
+    p.seg[2] = PackSeg{wl->lstm_w_hh, d.H, d.H, nullptr, 0, nullptr};
+    p.ntile = d.H / 32; p.R = 128; p.rows_per_tile = 128; p.rows_valid = 4 * d.H; p.lstm_H = d.H;
+    p.out = base + L.a_gates;
+    SFB_PROPAGATE(launch_pack_rows(p, st));
+  }
+  // rows 0..H-1: W_in (t = W_in h); rows H..2H-1: W_out[:, H:2H] (the h part of linear_out)   (model.py:129,140-142)
+  SFB_PROPAGATE(plain(wt->w_in, d.H, d.H, d.H, base + L.a_th));
+  SFB_PROPAGATE(plain(wt->w_out + d.H, 2 * d.H, d.H, d.H, base + L.a_th + pk_weight_bytes(d.H, L.nkb_h)));
+  SFB_PROPAGATE(plain(wt->w_out, 2 * d.H, d.H, d.H, base + L.a_wc));
+  SFB_PROPAGATE(plain(mg, d.H, d.E + 1, d.H, base + L.a_g));
+  return 0;
+}
+
+int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* wl, const void* packed,
+                                     size_t packed_bytes, int32_t B, int32_t L, int32_t A, const float* u_prev,
+                                     const float* all_u_t, const sfb_visual_source* vis, const float* h0,
+                                     const float* c0, const float* ctx, const uint8_t* ctx_mask, const float* drop_x,
+                                     const float* drop_h, float* h1, float* c1, float* alpha, float* logit,
+                                     float* alpha_v, void* workspace, size_t workspace_bytes, void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_PROPAGATE(check_packable(*dims));
+  SFB_CHECK_ARG(wl && vis && packed, "NULL weight/source struct");
+  SFB_CHECK_ARG(u_prev && all_u_t && h0 && c0 && ctx && h1 && c1 && logit, "NULL tensor argument");
+  SFB_CHECK_ARG(B >= 1 && L >= 1 && A >= 1, "B, L, A >= 1");
+  const sfb_dims& d = *dims;
+  const FollowerPk P = layout_follower_pk(d);
+  SFB_CHECK_ARG(packed_bytes >= P.bytes && (reinterpret_cast<uintptr_t>(packed) & 255u) == 0, "packed buffer too small / misaligned");
+  FollowerWs ws = carve_follower(d, B, L, A, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned char* base = static_cast<const unsigned char*>(packed);
+  auto proj = [&](const unsigned char* a_pk, const float* x, int ldx, int k, int n_out, float* out, int ldo,
+                  const float* bias, const float* padd, int ld_padd, int act) {
+    PkParams q{};
+    q.a_pk = a_pk; q.b_pk = nullptr; q.nkb = kblocks(k);
+    q.g.nseg = 1;
+    q.g.seg[0] = GemmSeg{x, ldx, nullptr, nullptr, 0, nullptr, 0, k, 0};
+    q.g.M = B; q.g.N = n_out; q.g.out = out; q.g.ldo = ldo; q.g.bias0 = bias; q.g.padd = padd; q.g.ld_padd = ld_padd; q.g.act = act;
+    return launch_gemm_pk(q, st, ws.pk, ws.pk_bytes);
+  };
+  // model.py:389  feature, alpha_v = visual_attention_layer(h_0, visual_context):  q = M_q h0 + b_q
+  SFB_PROPAGATE(proj(base + P.a_q, h0, d.H, d.H, d.F, ws.q, d.F, reinterpret_cast<const float*>(base + P.b_q), nullptr, 0, 0));
+  SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, alpha_v, ws.av, ws.av_bytes, st));
+  // model.py:391-393  LSTMCell(drop(cat(u_t_prev, feature)), (h_0, c_0)): activations packed once, then tcgen05
+  {
+    PackParams p{};
+    p.nseg = 3;
+    p.seg[0] = PackSeg{u_prev, d.E, d.E, drop_x, drop_x ? d.E + d.F : 0, nullptr};
+    p.seg[1] = PackSeg{ws.feat, d.F, d.F, drop_x ? drop_x + d.E : nullptr, drop_x ? d.E + d.F : 0, nullptr};
+    p.seg[2] = PackSeg{h0, d.H, d.H, nullptr, 0, nullptr};
+    const PkPlan pl = gemm_pk_plan(B, 4 * d.H, P.nkb_gates, true, device_num_sms());
+    p.ntile = pl.nz; p.R = pl.NB; p.rows_per_tile = pl.rows_per_z; p.rows_valid = B; p.lstm_H = 0;
+    p.out = ws.bpk;
+    SFB_PROPAGATE(launch_pack_rows(p, st));
+    PkParams q{};
+    q.a_pk = base + P.a_gates; q.b_pk = ws.bpk; q.nkb = P.nkb_gates;
+    q.g.M = B; q.g.N = 4 * d.H;
+    LstmEpilogue& e = q.g.lstm;
+    e.H = d.H; e.b_ih = wl->lstm_b_ih; e.b_hh = wl->lstm_b_hh; e.c0 = c0; e.drop_h = drop_h;
+    e.h1 = h1; e.c1 = c1; e.h1_drop = ws.h1d; e.gates_act = ws.gates_act;
+    SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));
+  }
+  // model.py:395  text attention: [t | W_out_h h1d] in one projection, attention over ctx, h~ = tanh(W_out_c wc + .)
+  SFB_PROPAGATE(proj(base + P.a_th, ws.h1d, d.H, d.H, 2 * d.H, ws.th, 2 * d.H, nullptr, nullptr, 0, 0));
+  {
+    AttnParams a{};
+    a.q = ws.th; a.ldq = 2 * d.H; a.R = L; a.D = d.H;
+    a.segA = ctx; a.strideA_b = (long long)L * d.H; a.strideA_r = d.H; a.lenA = d.H; a.lenB = 0;
+    a.mask = ctx_mask; a.ldmask = L;
+    a.out = ws.wc; a.ldo = d.H; a.alpha = alpha; a.ldalpha = L;
+    SFB_PROPAGATE(launch_soft_dot_attention(a, B, ws.at, ws.at_bytes, st));
+  }
+  SFB_PROPAGATE(proj(base + P.a_wc, ws.wc, d.H, d.H, d.H, ws.htilde, d.H, nullptr, ws.th + d.H, 2 * d.H, 1));
+  // model.py:396  logit = decoder2action(h_tilde, all_u_t):  g = M_g h~ + b_g (column E = the per-row constant)
+  SFB_PROPAGATE(proj(base + P.a_g, ws.htilde, d.H, d.H, d.E + 1, ws.g, ws.ldg, reinterpret_cast<const float*>(base + P.b_g), nullptr, 0, 0));
+  ScoringParams sp{all_u_t, ws.g, nullptr, nullptr, nullptr, ws.ldg, logit, B, A, d.E, d.D};
+  return launch_action_scoring(sp, st);
 }
 
 }  // extern "C"

@@ -40,6 +40,7 @@ __device__ __forceinline__ void lstm_update(const GemmParams& p, int m, int unit
 __device__ __forceinline__ void plain_store(const GemmParams& p, int m, int n, float v) {
   if (p.bias0) v += __ldg(p.bias0 + n);
   if (p.bias1) v += __ldg(p.bias1 + n);
+  if (p.padd) v += p.padd[(size_t)m * p.ld_padd + n];
   if (p.act == 1) v = tanhf(v);
   if (p.oscale) v *= __ldg(p.oscale + n);
   p.out[(size_t)m * p.ldo + n] = v;

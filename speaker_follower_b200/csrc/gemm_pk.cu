@@ -1,0 +1,449 @@
+// gemm_pk.cu — projections on Blackwell tensor cores from PRE-PACKED weights:  out[m, n] = sum_k X[m,k] W[n,k]
+//
+// The weight operand is packed once per weight version (pack.cu) into bf16 (hi, lo) pairs laid out exactly as
+// tcgen05.mma wants them in shared memory (no-swizzle K-major core matrices), one contiguous 32 KB block per
+// (128-row tile, 64-wide K block).  The kernel is then the canonical Blackwell pipeline with nothing to convert on
+// the weight side:
+//   warp 9  : producer — ONE cp.async.bulk (TMA engine) per stage for the weights (+ one for the activations when
+//             they come pre-packed too), completing on the stage's "full" mbarrier; weight copies are issued BEFORE
+//             the PDL dependency wait (weights are never written inside a step);
+//   warp 8  : one elected thread issues tcgen05.mma kind::f16 (bf16x3: hi·hi + hi·lo + lo·hi, fp32 accumulate in
+//             TMEM) and commits each stage to its "empty" mbarrier;
+//   warps 0-7: when the activations are fp32 in global memory (the small projections: K-range <= 3 blocks per CTA)
+//             they split them into bf16 hi/lo core matrices on the fly; afterwards they are the epilogue warps.
+// UMMA M = 128 weight rows (for the LSTM gates: 4 gates x 32 hidden units, interleaved at pack time), UMMA N = the
+// batch rounded up to 16, K = 16 per instruction, 64 per stage, 3 stages (~180 KB of loads in flight per SM).
+// K is split over S CTAs per tile so that tiles x S ~ #SMs in ONE resident wave; partial accumulators go
+// TMEM -> registers -> an L2-resident [col][row] partial buffer (coalesced), the S CTAs meet at a self-resetting
+// semaphore and each reduces its share in split order (deterministic) and applies the epilogue (bias / tanh /
+// addend / scale, or the whole LSTM cell update).
+#include <cuda_bf16.h>
+
+#include "epilogue.cuh"
+#include "kernels.h"
+
+namespace sfb {
+
+namespace {
+
+constexpr int PBM = 128;   // weight rows per tile
+constexpr int PBK = 64;    // K per stage
+constexpr int PSTAGES = 3;
+constexpr uint32_t PCORE = 128;
+constexpr uint32_t PSBO = (PBK / 8) * PCORE;   // 1024: byte stride between 8-row groups
+constexpr uint32_t PLBO = PCORE;               // byte stride between K-adjacent core matrices
+constexpr uint32_t PA_HALF = (PBM / 8) * PSBO; // 16 KB: one (hi | lo) weight tile
+
+__device__ __forceinline__ void pk_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 27); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();   // never hang the device
+}
+__device__ __forceinline__ uint64_t pk_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(PLBO >> 4) << 16;
+  d |= (uint64_t)(PSBO >> 4) << 32;
+  d |= 1ull << 46;   // descriptor version 1 (Blackwell); base_offset 0, SWIZZLE_NONE
+  return d;
+}
+__device__ __forceinline__ void pk_umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void pk_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pk_split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+}  // namespace
+
+// grid = (tiles, S, batch tiles), 320 threads, dynamic smem = PSTAGES stages + barriers
+template <bool B_PACKED, bool HAS_XS>
+__global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const GemmParams& p = q.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, S = gridDim.y, rank = blockIdx.y, tiles = gridDim.x, z = blockIdx.z;
+  const int NB = q.NB;
+  const int m0 = z * q.rows_per_z, m_end = min(p.M, m0 + q.rows_per_z);
+  const bool lstm = p.lstm.H > 0;
+
+  const uint32_t b_half = (uint32_t)(NB / 8) * PSBO;          // bytes of one (hi | lo) activation tile
+  const uint32_t stage_bytes = 2 * PA_HALF + 2 * b_half;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)PSTAGES * stage_bytes);
+  uint64_t* empty = full + PSTAGES;
+  uint64_t* done = empty + PSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const uint32_t tmem_cols = NB <= 32 ? 32 : NB <= 64 ? 64 : NB <= 128 ? 128 : 256;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < PSTAGES; ++s) {
+        mbar_init(&full[s], B_PACKED ? 1 : 1 + 256);
+        mbar_init(&empty[s], 1);
+      }
+      mbar_init(done, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  // K blocks of this CTA
+  const int per = (q.nkb + S - 1) / S;
+  const int kb_begin = rank * per, kb_end = min(q.nkb, kb_begin + per);
+  const int nit = max(0, kb_end - kb_begin);
+
+  trace_mark(p.trace, 0);
+  pdl_launch_dependents();
+
+  if (warp == 9) {
+    // =============================== producer: bulk copies ===============================
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_last();   // weights are re-read every step: keep them in L2
+      const unsigned char* a_src = q.a_pk + ((size_t)tile * q.nkb + kb_begin) * (2 * PA_HALF);
+      const unsigned char* b_src = B_PACKED ? q.b_pk + ((size_t)z * q.nkb + kb_begin) * (2 * b_half) : nullptr;
+      const uint32_t tx = 2 * PA_HALF + (B_PACKED ? 2 * b_half : 0u);
+      const int pre = min(nit, PSTAGES);
+      for (int it = 0; it < pre; ++it) {   // weights first: not produced inside the step
+        mbar_expect_tx(&full[it], tx);
+        bulk_g2s_hint(smem + (size_t)it * stage_bytes, a_src + (size_t)it * (2 * PA_HALF), 2 * PA_HALF, &full[it], pol);
+      }
+      pdl_wait();
+      if (B_PACKED)
+        for (int it = 0; it < pre; ++it)
+          bulk_g2s(smem + (size_t)it * stage_bytes + 2 * PA_HALF, b_src + (size_t)it * (2 * b_half), 2 * b_half, &full[it]);
+      for (int it = pre; it < nit; ++it) {
+        const int s = it % PSTAGES, use = it / PSTAGES;
+        pk_wait(&empty[s], (uint32_t)(use - 1) & 1u);
+        mbar_expect_tx(&full[s], tx);
+        bulk_g2s_hint(smem + (size_t)s * stage_bytes, a_src + (size_t)it * (2 * PA_HALF), 2 * PA_HALF, &full[s], pol);
+        if (B_PACKED)
+          bulk_g2s(smem + (size_t)s * stage_bytes + 2 * PA_HALF, b_src + (size_t)it * (2 * b_half), 2 * b_half, &full[s]);
+      }
+    } else {
+      pdl_wait();
+    }
+  } else if (warp == 8) {
+    // =============================== MMA issuer ===============================
+    pdl_wait();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(PBM >> 4) << 24);
+    for (int it = 0; it < nit; ++it) {
+      const int s = it % PSTAGES, use = it / PSTAGES;
+      pk_wait(&full[s], (uint32_t)use & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + PA_HALF, b_hi = a_hi + 2 * PA_HALF,
+                       b_lo = b_hi + b_half;
+#pragma unroll
+        for (int j = 0; j < PBK / 16; ++j) {
+          const uint32_t ko = (uint32_t)j * 2u * PCORE;
+          const uint64_t dah = pk_desc(a_hi + ko), dal = pk_desc(a_lo + ko);
+          const uint64_t dbh = pk_desc(b_hi + ko), dbl = pk_desc(b_lo + ko);
+          pk_umma(tmem_d, dal, dbh, idesc, (it > 0 || j > 0) ? 1u : 0u);   // small terms first
+          pk_umma(tmem_d, dah, dbl, idesc, 1u);
+          pk_umma(tmem_d, dah, dbh, idesc, 1u);
+        }
+        pk_commit(&empty[s]);
+        if (it + 1 == nit) pk_commit(done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== warps 0-7 ===============================
+    pdl_wait();
+    trace_mark(p.trace, 1);
+    if (!B_PACKED) {
+      // fp32 activations -> bf16 hi/lo core matrices (nit <= PSTAGES: every block has its own stage)
+      const int r_in = lane & 7, kc_in = lane >> 3;
+      float4 rb[2][4][2], rs[HAS_XS ? 2 : 1][HAS_XS ? 4 : 1][2];
+      auto load_block = [&](int blk, int set) {
+        int s = 0, cc = blk;
+        while (s + 1 < p.nseg) {
+          const int n = (p.seg[s].k + PBK - 1) / PBK;
+          if (cc < n) break;
+          cc -= n;
+          ++s;
+        }
+        const GemmSeg& g = p.seg[s];
+        const int kofs = cc * PBK;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int wu = warp + 8 * i;
+          const int rg = wu >> 1, k = kofs + ((wu & 1) * 4 + kc_in) * 8;
+          const int m = m0 + rg * 8 + r_in;
+          if (rg * 8 < NB && m < m_end && k < g.k) {
+            const int xr = g.xrow ? g.xrow[m] : m;
+            const float* src = g.x + (size_t)xr * g.ldx + k;
+            rb[set][i][0] = *reinterpret_cast<const float4*>(src);
+            rb[set][i][1] = *reinterpret_cast<const float4*>(src + 4);
+            if (HAS_XS) {
+              if (g.xs) {
+                const float* sp = g.xs + (size_t)m * g.ldxs + k;
+                rs[set][i][0] = __ldg(reinterpret_cast<const float4*>(sp));
+                rs[set][i][1] = __ldg(reinterpret_cast<const float4*>(sp + 4));
+              } else {
+                rs[set][i][0] = rs[set][i][1] = make_float4(1.f, 1.f, 1.f, 1.f);
+              }
+            }
+          } else {
+            rb[set][i][0] = rb[set][i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HAS_XS) rs[set][i][0] = rs[set][i][1] = make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+        }
+      };
+      if (nit > 0) load_block(kb_begin, 0);
+#pragma unroll 1
+      for (int it0 = 0; it0 < nit; it0 += 2) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int it = it0 + u;
+          if (it >= nit) break;
+          if (it + 1 < nit) load_block(kb_begin + it + 1, u ^ 1);
+          unsigned char* st = smem + (size_t)it * stage_bytes + 2 * PA_HALF;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int wu = warp + 8 * i;
+            if ((wu >> 1) * 8 < NB) {
+              const uint32_t off = (uint32_t)(wu >> 1) * PSBO + (uint32_t)((wu & 1) * 4 + kc_in) * PCORE + (uint32_t)r_in * 16u;
+              float4 b0 = rb[u][i][0], b1 = rb[u][i][1];
+              if (HAS_XS) {
+                const float4 s0 = rs[u][i][0], s1 = rs[u][i][1];
+                b0.x *= s0.x; b0.y *= s0.y; b0.z *= s0.z; b0.w *= s0.w;
+                b1.x *= s1.x; b1.y *= s1.y; b1.z *= s1.z; b1.w *= s1.w;
+              }
+              uint4 hi, lo;
+              pk_split8(b0, b1, hi, lo);
+              *reinterpret_cast<uint4*>(st + off) = hi;
+              *reinterpret_cast<uint4*>(st + b_half + off) = lo;
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&full[it]);
+        }
+      }
+    }
+  }
+  trace_mark(p.trace, 4);
+
+  // ---- epilogue 1: TMEM -> registers -> (direct output | [col][row] partial tile in L2)
+  const bool direct = (S == 1) && !lstm;
+  float* mypart = q.partial + ((size_t)(z * tiles + tile) * S + rank) * (size_t)(PBM * NB);
+  if (nit > 0 && warp < 8) {
+    pk_wait(done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  if (warp < 8) {
+    // warp w may only read TMEM lanes 32*(w%4)..+31; warps w and w+4 split the columns
+    const int lq = warp & 3, half = warp >> 2;
+    const int row = lq * 32 + lane;
+    const int ncols = m_end - m0;
+    for (int c = half * 16; c < NB; c += 32) {
+      if (c >= ncols) break;
+      uint32_t v[16];
+      if (nit > 0) {
+        const uint32_t taddr = tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)c;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      if (direct) {
+        const int n = tile * PBM + row;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c + j < ncols && n < p.N) plain_store(p, m0 + c + j, n, __uint_as_float(v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c + j < ncols) __stcg(mypart + (size_t)(c + j) * PBM + row, __uint_as_float(v[j]));   // lanes -> consecutive rows
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  trace_mark(p.trace, 5);
+  if (!direct) {
+    __threadfence();
+    __syncthreads();
+    // ---- the S CTAs of this tile meet at a semaphore (all co-resident: grid <= #SMs at 1 CTA/SM)
+    unsigned int* my_sem = q.sem + 2 * (z * tiles + tile);
+    if (S > 1) {
+      if (tid == 0) {
+        atomicAdd(my_sem, 1u);
+        unsigned int seen = 0;
+        for (uint32_t i = 0; i < (1u << 26); ++i) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(my_sem) : "memory");
+          if (seen >= (unsigned int)S) break;
+        }
+        if (seen < (unsigned int)S) __trap();
+        __threadfence();
+      }
+      __syncthreads();
+    }
+    trace_mark(p.trace, 6);
+    // ---- epilogue 2: reduce the S partial tiles in split order + epilogue op; consecutive threads -> consecutive rows
+    const int ncols = m_end - m0;
+    const float* tbase = q.partial + (size_t)(z * tiles + tile) * S * (size_t)(PBM * NB);
+    const size_t pstride = (size_t)PBM * NB;
+    if (lstm) {
+      const int total = ncols * 32, share = (((total + S - 1) / S) + 31) & ~31;
+      const int e_beg = rank * share, e_end = min(total, e_beg + share);
+      for (int e = e_beg + tid; e < e_end; e += 320) {
+        const int col = e >> 5, ul = e & 31;
+        const float* pk = tbase + (size_t)col * PBM + ul;
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < S; ++k) {
+          const float* pp = pk + (size_t)k * pstride;
+          g0 += __ldcg(pp);
+          g1 += __ldcg(pp + 32);
+          g2 += __ldcg(pp + 64);
+          g3 += __ldcg(pp + 96);
+        }
+        lstm_update(p, m0 + col, tile * 32 + ul, g0, g1, g2, g3);
+      }
+    } else {
+      const int total = ncols * PBM, share = (((total + S - 1) / S) + 31) & ~31;
+      const int e_beg = rank * share, e_end = min(total, e_beg + share);
+      for (int e = e_beg + tid; e < e_end; e += 320) {
+        const int col = e >> 7, row = e & 127;
+        const int n = tile * PBM + row;
+        if (n >= p.N) continue;
+        const float* pk = tbase + e;
+        float v = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < S; ++k) v += __ldcg(pk + (size_t)k * pstride);
+        plain_store(p, m0 + col, n, v);
+      }
+    }
+    __syncthreads();
+    if (S > 1 && tid == 0) {   // last CTA to leave re-arms the semaphore for the next launch
+      const unsigned int gone = atomicAdd(my_sem + 1, 1u);
+      if (gone == (unsigned int)S - 1) {
+        atomicExch(my_sem + 1, 0u);
+        atomicExch(my_sem, 0u);
+      }
+    }
+  } else {
+    __syncthreads();
+  }
+  trace_mark(p.trace, 2);
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+}
+
+// ------------------------------------------------------------------ host side
+
+int pk_num_kblocks(const int* seg_k, int nseg) {
+  int n = 0;
+  for (int s = 0; s < nseg; ++s) n += (seg_k[s] + PBK - 1) / PBK;
+  return n;
+}
+
+PkPlan gemm_pk_plan(int M, int N_rows, int nkb, bool b_packed, int num_sms) {
+  PkPlan pl{};
+  pl.tiles = (N_rows + PBM - 1) / PBM;
+  pl.nz = (M + 127) / 128;
+  pl.rows_per_z = (M + pl.nz - 1) / pl.nz;
+  pl.NB = (pl.rows_per_z + 15) & ~15;
+  int s = num_sms / (pl.tiles * pl.nz);            // co-residency: tiles*S*nz <= #SMs (spin semaphore)
+  if (s > nkb) s = nkb;
+  if (s > 16) s = 16;
+  if (s < 1) s = 1;
+  if (!b_packed) {                                  // in-kernel conversion keeps every K block in its own stage
+    const int need = (nkb + PSTAGES - 1) / PSTAGES;
+    if (s < need) s = need;
+  }
+  pl.S = s;
+  pl.sem_bytes = ((size_t)pl.tiles * pl.nz * 2 * sizeof(unsigned int) + 255) & ~size_t(255);
+  pl.bytes = pl.sem_bytes + (((size_t)pl.tiles * pl.nz * pl.S * PBM * pl.NB * sizeof(float) + 255) & ~size_t(255));
+  return pl;
+}
+
+size_t pk_weight_bytes(int N_rows, int nkb) { return (size_t)((N_rows + PBM - 1) / PBM) * nkb * 2 * PA_HALF; }
+size_t pk_act_bytes(int M, int nkb) {
+  const int nz = (M + 127) / 128, rpz = (M + nz - 1) / nz, NB = (rpz + 15) & ~15;
+  return (size_t)nz * nkb * 2 * (size_t)(NB / 8) * PSBO;
+}
+
+int32_t launch_gemm_pk(const PkParams& q_in, cudaStream_t stream, void* ws, size_t ws_bytes) {
+  PkParams q = q_in;
+  GemmParams& p = q.g;
+  p.trace = next_trace_slot();
+  const bool b_packed = q.b_pk != nullptr;
+  const bool lstm = p.lstm.H > 0;
+  SFB_CHECK_ARG(q.a_pk && (reinterpret_cast<uintptr_t>(q.a_pk) & 127u) == 0, "gemm_pk: packed weights missing / misaligned");
+  SFB_CHECK_ARG(p.M >= 1 && q.nkb >= 1, "gemm_pk: bad sizes");
+  SFB_CHECK_ARG(!lstm || (p.lstm.H % 32) == 0, "gemm_pk: LSTM epilogue needs H % 32 == 0");
+  const int n_rows = lstm ? 4 * p.lstm.H : p.N;
+  bool has_xs = false;
+  if (!b_packed) {
+    SFB_CHECK_ARG(p.nseg >= 1 && p.nseg <= 3, "gemm_pk: 1..3 K segments");
+    int kk[3];
+    for (int s = 0; s < p.nseg; ++s) {
+      const GemmSeg& g = p.seg[s];
+      kk[s] = g.k;
+      has_xs |= g.xs != nullptr;
+      SFB_CHECK_ARG(g.x && (g.k % 8) == 0 && (g.ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(g.x) & 15u) == 0,
+                    "gemm_pk: fp32 activations must be 16-byte aligned, K % 8 == 0");
+      SFB_CHECK_ARG(!g.xs || ((reinterpret_cast<uintptr_t>(g.xs) & 15u) == 0 && (g.ldxs % 4) == 0), "gemm_pk: scale alignment");
+    }
+    SFB_CHECK_ARG(pk_num_kblocks(kk, p.nseg) == q.nkb, "gemm_pk: K segments do not match the packed weights");
+  } else {
+    SFB_CHECK_ARG((reinterpret_cast<uintptr_t>(q.b_pk) & 127u) == 0, "gemm_pk: packed activations misaligned");
+  }
+  const PkPlan pl = gemm_pk_plan(p.M, n_rows, q.nkb, b_packed, device_num_sms());
+  SFB_CHECK_ARG(b_packed || (q.nkb + pl.S - 1) / pl.S <= PSTAGES, "gemm_pk: K too long for in-kernel activation conversion");
+  SFB_CHECK_ARG(ws && ws_bytes >= pl.bytes && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "gemm_pk: workspace");
+  q.sem = static_cast<unsigned int*>(ws);
+  q.partial = reinterpret_cast<float*>(static_cast<char*>(ws) + pl.sem_bytes);
+  q.NB = pl.NB;
+  q.rows_per_z = pl.rows_per_z;
+  const size_t stage_bytes = 2 * (size_t)PA_HALF + 2 * (size_t)(pl.NB / 8) * PSBO;
+  const size_t smem = PSTAGES * stage_bytes + 8 * sizeof(uint64_t) + 16;
+  const dim3 grid(pl.tiles, pl.S, pl.nz), block(320, 1, 1), cl(1, 1, 1);
+#define SFB_PK_LAUNCH(BP, XS)                                                                                       \
+  do {                                                                                                              \
+    static size_t configured = 0;                                                                                   \
+    if (smem > configured) {                                                                                        \
+      SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<BP, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      configured = smem;                                                                                            \
+    }                                                                                                               \
+    SFB_CHECK_CUDA(launch_ex(gemm_pk_kernel<BP, XS>, grid, block, smem, stream, cl, q));                            \
+  } while (0)
+  if (b_packed) SFB_PK_LAUNCH(true, false);
+  else if (has_xs) SFB_PK_LAUNCH(false, true);
+  else SFB_PK_LAUNCH(false, false);
+#undef SFB_PK_LAUNCH
+  count_launch();
+  return 0;
+}
+
+}  // namespace sfb

@@ -64,6 +64,7 @@ struct GemmParams {
   float* out; int ldo;                    // plain epilogue: out = act(acc + bias0 + bias1)
   const float* bias0; const float* bias1; // [N] or NULL
   const float* oscale;                    // [N] or NULL: out = act(acc + biases) * oscale[n]
+  const float* padd; int ld_padd;         // [M, >=N] or NULL: added before the activation (pre-computed partial sum)
   int act;                                // 0 none, 1 tanh
   int exact;                              // 1: force the exact-fp32 FFMA path (default: 3xTF32 mma.sync for M > 32)
   LstmEpilogue lstm;
@@ -84,13 +85,55 @@ void gemm_tc_set_debug(int flags);
 int gemm_tc_read_timestamps(long long* out, int n);
 extern int g_disable_tc;
 
+// ---------------------------------------------------------------- gemm_pk.cu (tcgen05 from pre-packed weights)
+struct PkParams {
+  GemmParams g;                          // epilogue (plain or LSTM), M, N; seg[] = fp32 activations when b_pk == NULL
+  const unsigned char* a_pk;             // packed weights [tiles][nkb][32 KB]
+  const unsigned char* b_pk;             // packed activations [nz][nkb][2*NB*128 B] or NULL
+  int nkb;                               // 64-wide K blocks (all segments)
+  // filled by the launcher
+  int NB, rows_per_z;
+  float* partial; unsigned int* sem;
+};
+struct PkPlan {
+  int tiles, nz, rows_per_z, NB, S;
+  size_t sem_bytes, bytes;               // workspace: self-resetting semaphores (must start zeroed) + partial tiles
+};
+PkPlan gemm_pk_plan(int M, int N_rows, int nkb, bool b_packed, int num_sms);
+int pk_num_kblocks(const int* seg_k, int nseg);
+size_t pk_weight_bytes(int N_rows, int nkb);
+size_t pk_act_bytes(int M, int nkb);
+int32_t launch_gemm_pk(const PkParams& q, cudaStream_t stream, void* ws, size_t ws_bytes);
+
+// ---------------------------------------------------------------- pack.cu
+struct PackSeg {
+  const float* x; int ldx; int k;
+  const float* xs; int ldxs;             // optional elementwise scale, indexed by the logical row
+  const int32_t* xrow;                   // optional row indirection
+};
+struct PackParams {
+  PackSeg seg[3];
+  int nseg;
+  int ntile;                             // row tiles (weights: ceil(N/128) or H/32; activations: batch tiles)
+  int R;                                 // packed rows per tile (128 for weights, NB for activations)
+  int rows_per_tile, rows_valid;         // plain mapping: source row = tile*rows_per_tile + r, valid below rows_valid
+  int lstm_H;                            // > 0: gate-interleaved LSTM weights, source row = (r/32)*H + tile*32 + r%32
+  unsigned char* out;
+  int nkb;                               // filled by the launcher
+  unsigned long long* trace;
+};
+int32_t launch_pack_rows(const PackParams& p, cudaStream_t stream);
+int32_t launch_fold(const float* A, int lda, const float* s, const float* Bm, int ldb, const float* bv, int D, int NA,
+                    int NJ, float* out, int ldo, float* obias, const float* obias_add, cudaStream_t stream);
+
 // ---------------------------------------------------------------- pointwise.cu
 // logit[b,a] = all_u_t[b,a,:] . g[b,:] + sum_d b_a[d] w_out[d] tp[b,d] + b_out   (EltwiseProdScoring rewritten)
 struct ScoringParams {
   const float* all_u_t;                   // [B,A,E]
   const float* g;                         // [B,E]
-  const float* tp;                        // [B,D]  linear_in_h(h_tilde) (.) w_out
+  const float* tp;                        // [B,D]  linear_in_h(h_tilde) (.) w_out; NULL: constant = g[b*ldg + E] (folded weights)
   const float* b_a; const float* b_out;
+  int ldg;                                // row stride of g
   float* logit;                           // [B,A]
   int B, A, E, D;
   unsigned long long* trace;

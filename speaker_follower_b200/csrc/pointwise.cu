@@ -29,14 +29,15 @@ __global__ void __launch_bounds__(256) action_scoring_kernel(const ScoringParams
   }
   pdl_wait();
   trace_mark(p.trace, 1);
-  const float4* g4 = reinterpret_cast<const float4*>(p.g + (size_t)b * p.E);
+  const float4* g4 = reinterpret_cast<const float4*>(p.g + (size_t)b * p.ldg);
   for (int j = tid; j < nvec; j += 256) reinterpret_cast<float4*>(gs)[j] = g4[j];
   float c = 0.f;
-  for (int d = tid; d < p.D; d += 256) c = fmaf(__ldg(p.b_a + d), p.tp[(size_t)b * p.D + d], c);
+  if (p.tp)
+    for (int d = tid; d < p.D; d += 256) c = fmaf(__ldg(p.b_a + d), p.tp[(size_t)b * p.D + d], c);
   c = warp_sum(c);
   if (lane == 0) red[warp] = c;
   __syncthreads();
-  float cst = __ldg(p.b_out);
+  float cst = p.tp ? __ldg(p.b_out) : p.g[(size_t)b * p.ldg + p.E];   // folded weights carry the constant as g[E]
 #pragma unroll
   for (int w = 0; w < 8; ++w) cst += red[w];
   if (stage_rows) mbar_wait(bar, 0);
@@ -63,6 +64,8 @@ int32_t launch_action_scoring(const ScoringParams& p_in, cudaStream_t stream) {
   ScoringParams p = p_in;
   p.trace = next_trace_slot();
   SFB_CHECK_ARG((p.E % 4) == 0, "scoring: E % 4");
+  if (p.ldg == 0) p.ldg = p.E;
+  SFB_CHECK_ARG((p.ldg % 4) == 0, "scoring: ldg % 4");
   const size_t staged = ((size_t)p.A + 1) * p.E * sizeof(float) + 16;
   const int stage_rows = staged <= 160 * 1024 ? 1 : 0;
   const size_t smem = stage_rows ? staged : (size_t)p.E * sizeof(float) + 16;

@@ -118,12 +118,54 @@ def _workspace(nbytes: int, device) -> Tensor:
     return torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+_FOLLOWER_KEYS = ("lstm.weight_ih", "lstm.weight_hh", "lstm.bias_ih", "lstm.bias_hh",
+                  "visual_attention_layer.linear_in_h.weight", "visual_attention_layer.linear_in_h.bias",
+                  "visual_attention_layer.linear_in_v.weight", "text_attention_layer.linear_in.weight",
+                  "text_attention_layer.linear_out.weight", "decoder2action.linear_in_h.weight",
+                  "decoder2action.linear_in_h.bias", "decoder2action.linear_in_a.weight",
+                  "decoder2action.linear_in_a.bias", "decoder2action.linear_out.weight",
+                  "decoder2action.linear_out.bias")
+
+
+class PackedFollower:
+    """Device blob of sfb_follower_pack_weights, re-packed when any weight tensor's storage or version changes
+    (shadow copies keyed on param._version)."""
+
+    def __init__(self):
+        self.blob: Optional[Tensor] = None
+        self.key = None
+
+    @staticmethod
+    def _key(w):
+        return tuple((w[k].data_ptr(), w[k]._version) for k in _FOLLOWER_KEYS)
+
+    def get(self, w: Dict[str, Tensor], V: int = 36) -> Optional[Tensor]:
+        key = self._key(w)
+        if self.blob is not None and key == self.key:
+            return self.blob
+        lib = _lib.load()
+        d = follower_dims(w, V)
+        n = lib.sfb_follower_packed_bytes(C.byref(d))
+        if n == 0:
+            return None   # dimensions the packed path does not cover -> caller uses the in-place path
+        dev = w["lstm.weight_ih"].device
+        if self.blob is None or self.blob.numel() < n or self.blob.device != dev:
+            self.blob = torch.empty(n, dtype=torch.uint8, device=dev)
+        wl, wt, ws = _vis_lstm_weights(w), _softdot_weights(w, "text_attention_layer."), _scoring_weights(w)
+        check(lib.sfb_follower_pack_weights(C.byref(d), C.byref(wl), C.byref(wt), C.byref(ws), self.blob.data_ptr(),
+                                            self.blob.numel(), _stream()))
+        self.key = key
+        return self.blob
+
+
 def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual: Optional[Tensor], h0: Tensor,
                   c0: Tensor, ctx: Tensor, ctx_mask: Optional[Tensor], drop_x: Optional[Tensor] = None,
                   drop_h: Optional[Tensor] = None, store: Optional[FeatureStore] = None,
                   vp_idx: Optional[Tensor] = None, view_idx: Optional[Tensor] = None,
-                  workspace: Optional[Tensor] = None, out: Optional[tuple] = None):
-    """AttnDecoderLSTM.forward (model.py:377-397) -> (h1, c1, alpha, logit, alpha_v)."""
+                  workspace: Optional[Tensor] = None, out: Optional[tuple] = None,
+                  packed: Optional[Tensor] = None):
+    """AttnDecoderLSTM.forward (model.py:377-397) -> (h1, c1, alpha, logit, alpha_v).
+    `packed`: blob from PackedFollower.get(w) -> the packed-weight tcgen05 path (sfb_follower_step_packed_fwd)."""
     lib = _lib.load()
     B, A, E = all_u_t.shape
     L = ctx.shape[1]
@@ -142,6 +184,15 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
         alpha_v = torch.empty(B, V, device=dev)
     else:
         h1, c1, alpha, logit, alpha_v = out
+    if packed is not None:
+        wl = _vis_lstm_weights(w)
+        check(lib.sfb_follower_step_packed_fwd(
+            C.byref(d), C.byref(wl), packed.data_ptr(), packed.numel(), B, L, A,
+            _p(u_prev, name="u_t_prev"), _p(all_u_t, name="all_u_t"), C.byref(vs), _p(h0, name="h_0"),
+            _p(c0, name="c_0"), _p(ctx, name="ctx"), _p(mask, torch.uint8, "ctx_mask"), _p(drop_x, name="drop_x"),
+            _p(drop_h, name="drop_h"), _p(h1), _p(c1), _p(alpha), _p(logit), _p(alpha_v), workspace.data_ptr(),
+            workspace.numel(), _stream()))
+        return h1, c1, alpha, logit, alpha_v
     wl, wt, ws = _vis_lstm_weights(w), _softdot_weights(w, "text_attention_layer."), _scoring_weights(w)
     check(lib.sfb_follower_step_fwd(
         C.byref(d), C.byref(wl), C.byref(wt), C.byref(ws), B, L, A,

@@ -1,0 +1,147 @@
+"""GPU parity of the packed-weight tcgen05 path (sfb_follower_pack_weights + sfb_follower_step_packed_fwd) against
+the CPU oracle, the reference-generated goldens and the in-place path of the same library.
+Tolerance: 1e-4 absolute on fp32 states/logits (BASELINE.json north_star), argmax identical."""
+import pytest
+import torch
+
+from conftest import load_golden, split_golden
+from oracle import r2r_oracle as O
+from speaker_follower_b200 import ops, synth
+from test_gpu_parity import NAMES, close, cu
+
+pytestmark = pytest.mark.gpu
+
+
+def run_packed(wc, xc, packed, drop_x=None, drop_h=None, gather=None):
+    if gather is None:
+        return ops.follower_step(wc, xc["u_t_prev"], xc["all_u_t"], xc["visual_context"], xc["h_0"], xc["c_0"],
+                                 xc["ctx"], xc["ctx_mask"], drop_x, drop_h, packed=packed)
+    store, vp, view = gather
+    return ops.follower_step(wc, xc["u_t_prev"], xc["all_u_t"], None, xc["h_0"], xc["c_0"], xc["ctx"], xc["ctx_mask"],
+                             drop_x, drop_h, store=store, vp_idx=vp, view_idx=view, packed=packed)
+
+
+@pytest.fixture(scope="module")
+def weights():
+    w = synth.follower_decoder_weights()
+    wc = cu(w)
+    pk = ops.PackedFollower()
+    blob = pk.get(wc)
+    assert blob is not None
+    return w, wc, pk, blob
+
+
+@pytest.mark.parametrize("B,L,A", [(1, 12, 3), (8, 20, 6), (100, 80, 8), (128, 40, 14), (130, 33, 5), (256, 24, 6)])
+def test_packed_step_vs_oracle(weights, B, L, A):
+    w, wc, _, blob = weights
+    x = synth.follower_step_inputs(B, L, A, seed=700 + B)
+    res = run_packed(wc, cu(x), blob)
+    ref = O.attn_decoder_step(x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
+                              x["ctx_mask"], w)
+    for k, v, r in zip(NAMES, res, ref):
+        close(v, r, what="oracle:" + k)
+    lg = res[3].cpu().masked_fill(x["is_valid"] == 0, -float("inf"))
+    lr = ref[3].masked_fill(x["is_valid"] == 0, -float("inf"))
+    margin = lr.topk(min(2, A), 1)[0]
+    safe = (margin[:, 0] - margin[:, -1] > 1e-4) | (A == 1)          # tie guard
+    assert torch.equal(lg.max(1)[1][safe], lr.max(1)[1][safe])
+
+
+@pytest.mark.parametrize("name", ["follower_step_c1", "follower_step_c2", "follower_step_b3"])
+def test_packed_step_reference_golden(weights, name):
+    """Against outputs of the reference's own model.py (tests/golden/make_golden.py)."""
+    _, wc, _, blob = weights
+    z = load_golden(name)
+    B, L, A, seed = int(z["B"]), int(z["L"]), int(z["A"]), int(z["seed"])
+    x = synth.follower_step_inputs(B, L, A, seed=seed)
+    res = run_packed(wc, cu(x), blob)
+    _, _, out, _ = split_golden(z)
+    for k, v in zip(NAMES, res):
+        close(v, out[k], what=k)
+
+
+def test_packed_step_train_masks(weights):
+    """Dropout keep masks (model.py:392,394) injected as tensors: packed path == oracle with the same masks."""
+    w, wc, _, blob = weights
+    B, L, A = 100, 80, 8
+    x = synth.follower_step_inputs(B, L, A, seed=801)
+    g = torch.Generator().manual_seed(9)
+    drop_x = (torch.rand(B, 2 * synth.FEAT, generator=g) > 0.5).float() * 2.0
+    drop_h = (torch.rand(B, synth.HID, generator=g) > 0.5).float() * 2.0
+    res = run_packed(wc, cu(x), blob, drop_x.cuda(), drop_h.cuda())
+    ref = O.attn_decoder_step(x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
+                              x["ctx_mask"], w, drop_x, drop_h)
+    for k, v, r in zip(NAMES, res, ref):
+        close(v, r, what="train:" + k)
+
+
+def test_packed_equals_inplace_path(weights):
+    """Same library, two weight formats: packed/folded tcgen05 path vs the in-place path."""
+    w, wc, _, blob = weights
+    x = cu(synth.follower_step_inputs(100, 80, 8, seed=802))
+    a = run_packed(wc, x, blob)
+    b = ops.follower_step(wc, x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"], x["ctx_mask"])
+    for k, u, v in zip(NAMES, a, b):
+        close(u, v.cpu(), 5e-5, "packed-vs-inplace:" + k)
+
+
+def test_packed_gather_equals_dense(weights):
+    _, wc, _, blob = weights
+    table, loc = synth.feature_table(64, 1031), synth.loc_embedding_table()
+    x = synth.follower_step_inputs(100, 80, 8, seed=55, table=table, loc=loc)
+    xc = cu(x)
+    dense = run_packed(wc, xc, blob)
+    store = ops.FeatureStore(table.cuda(), loc.cuda())
+    gath = run_packed(wc, xc, blob, gather=(store, xc["vp_idx"], xc["view_idx"]))
+    for k, a, b in zip(NAMES, dense, gath):
+        assert torch.equal(a, b), k
+
+
+def test_repack_on_weight_change():
+    """The packed blob follows the weights: an in-place update bumps _version and triggers a re-pack."""
+    w = synth.follower_decoder_weights()
+    wc = cu(w)
+    pk = ops.PackedFollower()
+    x = synth.follower_step_inputs(8, 20, 6, seed=803)
+    xc = cu(x)
+    r0 = [t.clone() for t in run_packed(wc, xc, pk.get(wc))]
+    key0 = pk.key
+    assert pk.get(wc) is pk.blob and pk.key == key0            # cached
+    wc["text_attention_layer.linear_out.weight"].mul_(0.5)
+    wc["lstm.weight_hh"].add_(0.01)
+    w2 = {k: v.cpu() for k, v in wc.items()}
+    r1 = run_packed(wc, xc, pk.get(wc))
+    assert pk.key != key0
+    ref = O.attn_decoder_step(x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
+                              x["ctx_mask"], w2)
+    for k, v, r in zip(NAMES, r1, ref):
+        close(v, r, what="repacked:" + k)
+    assert (r1[3] - r0[3]).abs().max().item() > 1e-3
+
+
+def test_packed_rollout_10_steps_drift(weights):
+    """Error does not compound past the contract over a full episode (10 decode steps, B=100), packed path."""
+    w, wdc, _, blob = weights
+    B, L, A, S = 100, 80, 8, 10
+    we = synth.follower_encoder_weights()
+    seq, mask, lengths = synth.instruction_batch(B, L, seed=47)
+    steps = []
+    for s in range(S):
+        x = synth.follower_step_inputs(B, L, A, seed=600 + s)
+        steps.append({"visual": x["visual_context"], "all_u_t": x["all_u_t"], "is_valid": x["is_valid"]})
+    ref, _, ref_score = O.follower_rollout(seq, mask, lengths, steps, we, w, feedback="argmax")
+    ctx, h, c = ops.encoder_lstm(cu(we), seq.cuda(), lengths)
+    u_prev = torch.zeros(B, synth.FEAT, device="cuda")
+    total = torch.zeros(B, device="cuda")
+    worst = 0.0
+    for s in range(S):
+        st = cu(steps[s])
+        h, c, alpha, logit, alpha_v = ops.follower_step(wdc, u_prev, st["all_u_t"], st["visual"], h, c, ctx,
+                                                        mask.cuda(), packed=blob)
+        a_t, u_prev, score, _ = ops.follower_tail(logit, st["is_valid"], st["all_u_t"], "argmax")
+        worst = max(worst, close(logit, ref[s]["logit"], what="logit step %d" % s))
+        assert torch.equal(a_t.cpu().long(), ref[s]["a_t"]), "argmax differs at step %d" % s
+        total += score
+    close(h, ref[-1]["h"], what="h"); close(c, ref[-1]["c"], what="c")
+    close(total, ref_score, 5e-4, "sequence score")
+    print("packed path: worst |dlogit| over 10 steps: %.2e" % worst)

@@ -5,8 +5,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from speaker_follower_b200 import ops, synth, _lib
 torch.cuda.set_device(0)
+PACKED = 0
 for kv in sys.argv[1:]:
-    k, v = kv.split("="); ops.set_option(k, int(v)); print("option", k, v)
+    k, v = kv.split("=")
+    if k == "packed":
+        PACKED = int(v)
+    else:
+        ops.set_option(k, int(v)); print("option", k, v)
 dev = torch.device("cuda")
 B, L, A = 100, 80, 8
 w = {k: v.cuda() for k, v in synth.follower_decoder_weights().items()}
@@ -17,10 +22,11 @@ cb = [xs[0]["c_0"].clone(), torch.empty(B, 512, device=dev)]
 ub = [xs[0]["u_t_prev"].clone(), torch.empty(B, 2176, device=dev)]
 alpha = torch.empty(B, L, device=dev); logit = torch.empty(B, A, device=dev); av = torch.empty(B, 36, device=dev)
 a_t = torch.empty(B, dtype=torch.int32, device=dev); score = torch.empty(B, device=dev)
+blob = ops.PackedFollower().get(w) if PACKED else None
 def step(i):
     x, s = xs[i % 2], i % 2
     ops.follower_step(w, ub[s], x["all_u_t"], x["visual_context"], hb[s], cb[s], x["ctx"], x["ctx_mask"], workspace=ws,
-                      out=(hb[s ^ 1], cb[s ^ 1], alpha, logit, av))
+                      out=(hb[s ^ 1], cb[s ^ 1], alpha, logit, av), packed=blob)
     ops.follower_tail(logit, x["is_valid"], x["all_u_t"], "argmax", out=(a_t, ub[s ^ 1], score, None))
 side = torch.cuda.Stream()
 with torch.cuda.stream(side):
@@ -40,12 +46,14 @@ print("graph of 1 step: %.1f us per step" % (e0.elapsed_time(e1) * 1e3 / 50))
 buf = (C.c_int64 * (64 * 16))()
 n = _lib.load().sfb_debug_read_trace(buf, 64)
 names = ["gemm t_v", "gemm q", "attn visual", "gemm gates(TC)+lstm", "gemm t", "attn text", "gemm h~", "gemm t'", "gemm g", "scoring", "tail"]
+if PACKED:
+    names = ["pk q", "attn visual", "pack acts", "pk gates+lstm", "pk [t|hh]", "attn text", "pk h~", "pk g", "scoring", "tail"]
 t0 = buf[0]
 prev_exit = t0
 for k in range(n):
     e, wt, x, x2 = buf[16 * k], buf[16 * k + 1], buf[16 * k + 2], buf[16 * k + 3]
     print("%2d %-22s entry %8.2f  wait_done %8.2f  exit %8.2f  (dur %6.2f us, after wait %6.2f us)%s" % (
-        k, names[k % 11], (e - t0) / 1e3, (wt - t0) / 1e3, (x - t0) / 1e3, (x - e) / 1e3, (x - wt) / 1e3,
+        k, names[k % len(names)], (e - t0) / 1e3, (wt - t0) / 1e3, (x - t0) / 1e3, (x - e) / 1e3, (x - wt) / 1e3,
         ("  merge_exit %.2f" % ((x2 - t0) / 1e3)) if x2 else ""))
     ph = [buf[16 * k + j] for j in range(4, 12)]
     if any(ph):
