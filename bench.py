@@ -192,6 +192,9 @@ def run_gpu(args, rank, local_rank, world):
     del rows, u
 
     d = ops.follower_dims(w)
+    # weights re-laid out once per weight version (sfb_follower_pack_weights); SFB_INPLACE=1 benches the in-place path
+    packer = ops.PackedFollower()
+    blob = None if os.environ.get("SFB_INPLACE") else packer.get(w)
     hbuf = [torch.tanh(torch.randn(B, H, device=dev, generator=g) * 0.5), torch.empty(B, H, device=dev)]
     cbuf = [torch.randn(B, H, device=dev, generator=g) * 0.5, torch.empty(B, H, device=dev)]
     ubuf = [torch.zeros(B, E, device=dev), torch.empty(B, E, device=dev)]
@@ -203,7 +206,7 @@ def run_gpu(args, rank, local_rank, world):
     def step(i):
         j, s = i % POOL, i % 2
         ops.follower_step(w, ubuf[s], U[j], None, hbuf[s], cbuf[s], ctx[j], mask, store=store, vp_idx=vp[j],
-                          view_idx=view[j], workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v))
+                          view_idx=view[j], workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v), packed=blob)
         n = ops.last_launch_count()
         ops.follower_tail(logit, valid[j], U[j], "argmax", out=(a_t, ubuf[s ^ 1], score, None))
         launches_per_step[0] = n + ops.last_launch_count()
@@ -273,7 +276,8 @@ def run_gpu(args, rank, local_rank, world):
         gph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gph):
             ops.follower_step(w, ubuf[s], d_U, None, hbuf[s], cbuf[s], ctx[0], mask, store=store, vp_idx=d_vp,
-                              view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v))
+                              view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v),
+                              packed=blob)
             ops.follower_tail(logit, d_valid, d_U, "argmax", out=(a_t, ubuf[s ^ 1], score, None))
         graphs2.append(gph)
 

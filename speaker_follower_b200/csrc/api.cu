@@ -216,8 +216,13 @@ static int32_t visual_query(const sfb_dims& d, const sfb_vis_lstm_weights& w, in
 }
 
 static int32_t visual_attend(const sfb_dims& d, int B, const float* q, const sfb_visual_source& v, float* feature,
-                             float* alpha_v, void* aws, size_t aws_bytes, cudaStream_t st) {
+                             float* alpha_v, void* aws, size_t aws_bytes, cudaStream_t st,
+                             const AttnParams* pk = nullptr) {
   AttnParams a{};
+  if (pk) {
+    a.pk_out = pk->pk_out; a.pk_kb0 = pk->pk_kb0; a.pk_nkb = pk->pk_nkb; a.pk_NB = pk->pk_NB;
+    a.pk_rows_per_z = pk->pk_rows_per_z; a.pk_scale = pk->pk_scale; a.pk_ldscale = pk->pk_ldscale;
+  }
   a.q = q; a.ldq = d.F;
   a.R = d.V; a.D = d.F;
   if (v.visual) {
@@ -637,28 +642,35 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned char* base = static_cast<const unsigned char*>(packed);
   auto proj = [&](const unsigned char* a_pk, const float* x, int ldx, int k, int n_out, float* out, int ldo,
-                  const float* bias, const float* padd, int ld_padd, int act) {
+                  const float* bias, const float* padd, int ld_padd, int act, const PackParams* side) {
     PkParams q{};
     q.a_pk = a_pk; q.b_pk = nullptr; q.nkb = kblocks(k);
     q.g.nseg = 1;
     q.g.seg[0] = GemmSeg{x, ldx, nullptr, nullptr, 0, nullptr, 0, k, 0};
     q.g.M = B; q.g.N = n_out; q.g.out = out; q.g.ldo = ldo; q.g.bias0 = bias; q.g.padd = padd; q.g.ld_padd = ld_padd; q.g.act = act;
+    if (side) { q.has_side = 1; q.side = *side; }
     return launch_gemm_pk(q, st, ws.pk, ws.pk_bytes);
   };
+  // The gate GEMM's activation operand [u_prev | feature | h0] (.) drop_x is packed by its producers: u_prev and h0 by
+  // the idle warps of the q projection (side job), feature by the attention kernel's epilogue.
+  const PkPlan gpl = gemm_pk_plan(B, 4 * d.H, P.nkb_gates, true, device_num_sms());
+  PackParams side{};
+  side.nseg = 3;
+  side.seg[0] = PackSeg{u_prev, d.E, d.E, drop_x, drop_x ? d.E + d.F : 0, nullptr};
+  side.seg[1] = PackSeg{nullptr, d.F, d.F, nullptr, 0, nullptr};   // written by the attention epilogue
+  side.seg[2] = PackSeg{h0, d.H, d.H, nullptr, 0, nullptr};
+  side.ntile = gpl.nz; side.R = gpl.NB; side.rows_per_tile = gpl.rows_per_z; side.rows_valid = B; side.lstm_H = 0;
+  side.out = ws.bpk;
   // model.py:389  feature, alpha_v = visual_attention_layer(h_0, visual_context):  q = M_q h0 + b_q
-  SFB_PROPAGATE(proj(base + P.a_q, h0, d.H, d.H, d.F, ws.q, d.F, reinterpret_cast<const float*>(base + P.b_q), nullptr, 0, 0));
-  SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, alpha_v, ws.av, ws.av_bytes, st));
-  // model.py:391-393  LSTMCell(drop(cat(u_t_prev, feature)), (h_0, c_0)): activations packed once, then tcgen05
+  SFB_PROPAGATE(proj(base + P.a_q, h0, d.H, d.H, d.F, ws.q, d.F, reinterpret_cast<const float*>(base + P.b_q), nullptr, 0, 0, &side));
   {
-    PackParams p{};
-    p.nseg = 3;
-    p.seg[0] = PackSeg{u_prev, d.E, d.E, drop_x, drop_x ? d.E + d.F : 0, nullptr};
-    p.seg[1] = PackSeg{ws.feat, d.F, d.F, drop_x ? drop_x + d.E : nullptr, drop_x ? d.E + d.F : 0, nullptr};
-    p.seg[2] = PackSeg{h0, d.H, d.H, nullptr, 0, nullptr};
-    const PkPlan pl = gemm_pk_plan(B, 4 * d.H, P.nkb_gates, true, device_num_sms());
-    p.ntile = pl.nz; p.R = pl.NB; p.rows_per_tile = pl.rows_per_z; p.rows_valid = B; p.lstm_H = 0;
-    p.out = ws.bpk;
-    SFB_PROPAGATE(launch_pack_rows(p, st));
+    AttnParams pk{};
+    pk.pk_out = ws.bpk; pk.pk_kb0 = kblocks(d.E); pk.pk_nkb = P.nkb_gates; pk.pk_NB = gpl.NB; pk.pk_rows_per_z = gpl.rows_per_z;
+    pk.pk_scale = drop_x ? drop_x + d.E : nullptr; pk.pk_ldscale = d.E + d.F;
+    SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, alpha_v, ws.av, ws.av_bytes, st, &pk));
+  }
+  // model.py:391-393  LSTMCell(drop(cat(u_t_prev, feature)), (h_0, c_0)) on tcgen05 from the packed operands
+  {
     PkParams q{};
     q.a_pk = base + P.a_gates; q.b_pk = ws.bpk; q.nkb = P.nkb_gates;
     q.g.M = B; q.g.N = 4 * d.H;
@@ -668,7 +680,7 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
     SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));
   }
   // model.py:395  text attention: [t | W_out_h h1d] in one projection, attention over ctx, h~ = tanh(W_out_c wc + .)
-  SFB_PROPAGATE(proj(base + P.a_th, ws.h1d, d.H, d.H, 2 * d.H, ws.th, 2 * d.H, nullptr, nullptr, 0, 0));
+  SFB_PROPAGATE(proj(base + P.a_th, ws.h1d, d.H, d.H, 2 * d.H, ws.th, 2 * d.H, nullptr, nullptr, 0, 0, nullptr));
   {
     AttnParams a{};
     a.q = ws.th; a.ldq = 2 * d.H; a.R = L; a.D = d.H;
@@ -677,9 +689,9 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
     a.out = ws.wc; a.ldo = d.H; a.alpha = alpha; a.ldalpha = L;
     SFB_PROPAGATE(launch_soft_dot_attention(a, B, ws.at, ws.at_bytes, st));
   }
-  SFB_PROPAGATE(proj(base + P.a_wc, ws.wc, d.H, d.H, d.H, ws.htilde, d.H, nullptr, ws.th + d.H, 2 * d.H, 1));
+  SFB_PROPAGATE(proj(base + P.a_wc, ws.wc, d.H, d.H, d.H, ws.htilde, d.H, nullptr, ws.th + d.H, 2 * d.H, 1, nullptr));
   // model.py:396  logit = decoder2action(h_tilde, all_u_t):  g = M_g h~ + b_g (column E = the per-row constant)
-  SFB_PROPAGATE(proj(base + P.a_g, ws.htilde, d.H, d.H, d.E + 1, ws.g, ws.ldg, reinterpret_cast<const float*>(base + P.b_g), nullptr, 0, 0));
+  SFB_PROPAGATE(proj(base + P.a_g, ws.htilde, d.H, d.H, d.E + 1, ws.g, ws.ldg, reinterpret_cast<const float*>(base + P.b_g), nullptr, 0, 0, nullptr));
   ScoringParams sp{all_u_t, ws.g, nullptr, nullptr, nullptr, ws.ldg, logit, B, A, d.E, d.D};
   return launch_action_scoring(sp, st);
 }

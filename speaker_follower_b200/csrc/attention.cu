@@ -17,6 +17,8 @@
 // peers, every CTA pushes its rescaled partial columns to the column's owner (st.shared::cluster), the owner adds them
 // in rank order and writes the output — no global partial buffer, no atomics, two cluster barriers.  With PDL the
 // ring is primed before the producer of q has finished.
+#include <cuda_bf16.h>
+
 #include "kernels.h"
 
 namespace sfb {
@@ -31,7 +33,8 @@ __device__ __forceinline__ void st_cluster_f32x4(uint32_t addr, const float4& v)
 }
 }  // namespace
 
-template <int NJ, int NT>   // float4 slices per thread, threads per CTA: D <= NJ * NT * 4
+// NJ float4 slices per thread, NT threads per CTA (D <= NJ * NT * 4), RB rows consumed per block barrier
+template <int NJ, int NT, int RB>
 __global__ void __launch_bounds__(NT) soft_dot_attn_kernel(const AttnParams p) {
   constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -42,8 +45,8 @@ __global__ void __launch_bounds__(NT) soft_dot_attn_kernel(const AttnParams p) {
 
   float* ring = reinterpret_cast<float*>(smem_raw);                          // [NSTG][D]; reused as the merge inbox
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)NSTG * D);     // [NSTG]
-  float* red = reinterpret_cast<float*>(full + NSTG);                        // [2][NW] per-warp partial dots
-  float* stat = red + 2 * NW;                                                // [2] (max, sum) of this CTA, read by peers
+  float* red = reinterpret_cast<float*>(full + NSTG);                        // [2][NW][RB] per-warp partial dots
+  float* stat = red + 2 * NW * RB;                                                // [2] (max, sum) of this CTA, read by peers
   float* sc = stat + 2;                                                      // [rows_per_cta] raw scores (local order)
   int* list = reinterpret_cast<int*>(sc + p.rows_per_cta);                   // [rows_per_cta] unmasked local row ids
   __shared__ int s_nvalid;
@@ -100,41 +103,77 @@ __global__ void __launch_bounds__(NT) soft_dot_attn_kernel(const AttnParams p) {
   const int nvalid = s_nvalid;
   trace_mark(p.trace, 4);
 
-  // ---- 3. stream: one row per iteration, one block barrier per row, stage refilled as soon as it is consumed
+  // ---- 3. stream: RB rows per iteration (independent dot products -> ILP), one block barrier per iteration, every
+  // stage refilled as soon as its row sits in registers
   float m = -INFINITY, Z = 0.f;
-  for (int i = 0; i < nvalid; ++i) {
-    const int s = i % NSTG;
-    mbar_wait(&full[s], (uint32_t)(i / NSTG) & 1u);
-    const float4* row4 = reinterpret_cast<const float4*>(ring + (size_t)s * D);
-    float4 v[NJ];
-    float part = 0.f;
+  for (int i0 = 0; i0 < nvalid; i0 += RB) {
+    const int nb = min(RB, nvalid - i0);
+    float4 v[RB][NJ];
+    float part[RB];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int idx = tid + NT * j;
-      v[j] = idx < nvec ? row4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-      part = fmaf(v[j].x, qv[j].x, part);
-      part = fmaf(v[j].y, qv[j].y, part);
-      part = fmaf(v[j].z, qv[j].z, part);
-      part = fmaf(v[j].w, qv[j].w, part);
+    for (int r = 0; r < RB; ++r) {
+      part[r] = 0.f;
+      if (r < nb) {
+        const int i = i0 + r, s = i % NSTG;
+        mbar_wait(&full[s], (uint32_t)(i / NSTG) & 1u);
+        const float4* row4 = reinterpret_cast<const float4*>(ring + (size_t)s * D);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int idx = tid + NT * j;
+          v[r][j] = idx < nvec ? row4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+          part[r] = fmaf(v[r][j].x, qv[j].x, part[r]);
+          part[r] = fmaf(v[r][j].y, qv[j].y, part[r]);
+          part[r] = fmaf(v[r][j].z, qv[j].z, part[r]);
+          part[r] = fmaf(v[r][j].w, qv[j].w, part[r]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) v[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-    part = warp_sum(part);
-    float* rb = red + (i & 1) * NW;
-    if (lane == 0) rb[warp] = part;
-    __syncthreads();   // every thread holds its slice in registers -> the stage is free
-    if (tid == 0 && i + NSTG < nvalid) fetch(i + NSTG, s);
-    float sr = 0.f;
 #pragma unroll
-    for (int w = 0; w < NW; ++w) sr += rb[w];
-    if (tid == 0) sc[list[i]] = sr;
-    const float mn = fmaxf(m, sr);
-    const float corr = __expf(m - mn), e = __expf(sr - mn);
-    Z = fmaf(Z, corr, e);
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < RB; ++r) part[r] += __shfl_xor_sync(0xffffffffu, part[r], o);
+    float* rb = red + ((i0 / RB) & 1) * NW * RB;
+    if (lane == 0)
+#pragma unroll
+      for (int r = 0; r < RB; ++r) rb[warp * RB + r] = part[r];
+    __syncthreads();   // every thread holds its slices in registers -> the stages are free
+    if (tid == 0)
+      for (int r = 0; r < nb; ++r)
+        if (i0 + r + NSTG < nvalid) fetch(i0 + r + NSTG, (i0 + r) % NSTG);
+    float sr[RB], mn = m;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      sr[r] = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) sr[r] += rb[w * RB + r];
+      if (r >= nb) sr[r] = -INFINITY;
+      mn = fmaxf(mn, sr[r]);
+    }
+    if (tid == 0)
+      for (int r = 0; r < nb; ++r) sc[list[i0 + r]] = sr[r];
+    const float corr = __expf(m - mn);
+    float e[RB], esum = 0.f;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      e[r] = __expf(sr[r] - mn);   // rows beyond nb: exp(-inf) = 0
+      esum += e[r];
+    }
+    Z = fmaf(Z, corr, esum);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      acc[j].x = fmaf(acc[j].x, corr, e * v[j].x);
-      acc[j].y = fmaf(acc[j].y, corr, e * v[j].y);
-      acc[j].z = fmaf(acc[j].z, corr, e * v[j].z);
-      acc[j].w = fmaf(acc[j].w, corr, e * v[j].w);
+      float4 a = acc[j];
+      a.x *= corr; a.y *= corr; a.z *= corr; a.w *= corr;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        a.x = fmaf(e[r], v[r][j].x, a.x);
+        a.y = fmaf(e[r], v[r][j].y, a.y);
+        a.z = fmaf(e[r], v[r][j].z, a.z);
+        a.w = fmaf(e[r], v[r][j].w, a.w);
+      }
+      acc[j] = a;
     }
     m = mn;
   }
@@ -198,6 +237,21 @@ __global__ void __launch_bounds__(NT) soft_dot_attn_kernel(const AttnParams p) {
         o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
       }
       out4[col] = o;
+      if (p.pk_out) {   // the same 4 values as bf16 (hi, lo) in the gate GEMM's packed activation operand
+        const int k = col * 4, zt = b / p.pk_rows_per_z, r = b - zt * p.pk_rows_per_z;
+        if (p.pk_scale) {
+          const float4 sc = *reinterpret_cast<const float4*>(p.pk_scale + (size_t)b * p.pk_ldscale + k);
+          o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w;
+        }
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
+        const size_t half = (size_t)p.pk_NB * 128;
+        unsigned char* dst = p.pk_out + ((size_t)zt * p.pk_nkb + p.pk_kb0 + (k >> 6)) * (2 * half) + (size_t)(r >> 3) * 1024 +
+                             (size_t)((k & 63) >> 3) * 128 + (size_t)(r & 7) * 16 + (size_t)(k & 7) * 2;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(dst + half) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      }
     }
   }
   trace_mark(p.trace, 2);
@@ -207,30 +261,43 @@ __global__ void __launch_bounds__(NT) soft_dot_attn_kernel(const AttnParams p) {
 // ------------------------------------------------------------------ host launcher
 
 static size_t attn_smem_bytes(int stages, int D, int rows_per_cta) {
-  return (size_t)stages * D * sizeof(float) + (size_t)stages * sizeof(uint64_t) + (2 * 8 + 2) * sizeof(float) +
+  return (size_t)stages * D * sizeof(float) + (size_t)stages * sizeof(uint64_t) + (2 * 8 * 4 + 2) * sizeof(float) +
          (size_t)rows_per_cta * (sizeof(float) + sizeof(int));
 }
 
 AttnPlan attention_plan(int B, int R, int D, int num_sms) {
   AttnPlan pl{};
-  // cluster size: as many CTAs per batch element as still fit in ONE resident wave (3 CTAs per SM), >= 4 rows each
-  int cl = 1;
-  while (cl < 8 && (long long)B * cl * 2 <= 3LL * num_sms && R / (cl * 2) >= 4) cl *= 2;
-  pl.split = cl;
-  pl.rows_per_cta = (R + cl - 1) / cl;
+  // cluster size: the largest CL whose B x CL CTAs are still ONE resident wave, with >= 4 rows per CTA
+  const int nt = D <= 512 ? 128 : 256;
+  int best = 1;
+  for (int cl = 8; cl >= 1; cl >>= 1) {
+    if (cl > 1 && R / cl < 4) continue;
+    const int rows = (R + cl - 1) / cl;
+    int st = (int)(ATT_RING_BUDGET / ((size_t)D * 4));
+    st = st > rows ? rows : st;
+    st = st > ATT_MAX_STAGES ? ATT_MAX_STAGES : st;
+    st = st < 4 ? 4 : st;
+    const size_t smem = attn_smem_bytes(st, D, rows) + 1024;
+    long long per_sm = (long long)((220 * 1024) / smem);
+    if (per_sm > 2048 / nt) per_sm = 2048 / nt;
+    if (per_sm > 16) per_sm = 16;
+    if (cl == 1 || (long long)B * cl <= per_sm * num_sms) { best = cl; break; }
+  }
+  pl.split = best;
+  pl.rows_per_cta = (R + best - 1) / best;
   int stages = (int)(ATT_RING_BUDGET / ((size_t)D * 4));
   if (stages > pl.rows_per_cta) stages = pl.rows_per_cta;
   if (stages > ATT_MAX_STAGES) stages = ATT_MAX_STAGES;
-  if (stages < 2) stages = 2;   // the ring doubles as the merge inbox (one row + rounding)
+  if (stages < 4) stages = 4;   // >= rows per barrier; the ring doubles as the merge inbox (one row + rounding)
   pl.stages = stages;
   pl.ticket_bytes = 0;
   pl.bytes = 256;   // no global scratch any more; kept non-zero so workspace carving stays uniform
   return pl;
 }
 
-template <int NJ, int NT>
+template <int NJ, int NT, int RB>
 static int32_t launch_attn_t(const AttnParams& p, int B, int cl, cudaStream_t stream) {
-  auto kern = soft_dot_attn_kernel<NJ, NT>;
+  auto kern = soft_dot_attn_kernel<NJ, NT, RB>;
   const size_t smem = attn_smem_bytes(p.stages, p.D, p.rows_per_cta);
   static size_t configured = 0;  // per instantiation
   if (smem > configured) {
@@ -256,9 +323,9 @@ int32_t launch_soft_dot_attention(AttnParams p, int B, void* ws, size_t ws_bytes
   p.ticket = nullptr;
   p.part = nullptr;
   SFB_CHECK_ARG(attn_smem_bytes(p.stages, p.D, p.rows_per_cta) <= 200 * 1024, "attention rows do not fit shared memory");
-  if (p.D <= 512) return launch_attn_t<1, 128>(p, B, pl.split, stream);
-  if (p.D <= 1024) return launch_attn_t<1, 256>(p, B, pl.split, stream);
-  return launch_attn_t<3, 256>(p, B, pl.split, stream);
+  if (p.D <= 512) return launch_attn_t<1, 128, 4>(p, B, pl.split, stream);
+  if (p.D <= 1024) return launch_attn_t<1, 256, 4>(p, B, pl.split, stream);
+  return launch_attn_t<3, 256, 2>(p, B, pl.split, stream);
 }
 
 }  // namespace sfb

@@ -46,4 +46,27 @@ __device__ __forceinline__ void plain_store(const GemmParams& p, int m, int n, f
   p.out[(size_t)m * p.ldo + n] = v;
 }
 
+// four consecutive output features n..n+3 of row m (n % 4 == 0); vector store when the row stride allows it
+__device__ __forceinline__ void plain_store4(const GemmParams& p, int m, int n, float4 v) {
+  if (n + 3 < p.N && (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0) {
+    float r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x = r[i];
+      if (p.bias0) x += __ldg(p.bias0 + n + i);
+      if (p.bias1) x += __ldg(p.bias1 + n + i);
+      if (p.padd) x += p.padd[(size_t)m * p.ld_padd + n + i];
+      if (p.act == 1) x = tanhf(x);
+      if (p.oscale) x *= __ldg(p.oscale + n + i);
+      r[i] = x;
+    }
+    *reinterpret_cast<float4*>(p.out + (size_t)m * p.ldo + n) = make_float4(r[0], r[1], r[2], r[3]);
+  } else {
+    if (n < p.N) plain_store(p, m, n, v.x);
+    if (n + 1 < p.N) plain_store(p, m, n + 1, v.y);
+    if (n + 2 < p.N) plain_store(p, m, n + 2, v.z);
+    if (n + 3 < p.N) plain_store(p, m, n + 3, v.w);
+  }
+}
+
 }  // namespace sfb

@@ -21,6 +21,7 @@
 
 #include "epilogue.cuh"
 #include "kernels.h"
+#include "pack.cuh"
 
 namespace sfb {
 
@@ -57,21 +58,6 @@ __device__ __forceinline__ void pk_umma(uint32_t d_tmem, uint64_t adesc, uint64_
 __device__ __forceinline__ void pk_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void pk_split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
-  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const float2 hf = __bfloat1622float2(hh);
-    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
-    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
 }  // namespace
 
 // grid = (tiles, S, batch tiles), 320 threads, dynamic smem = PSTAGES stages + barriers
@@ -235,7 +221,7 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
                 b1.x *= s1.x; b1.y *= s1.y; b1.z *= s1.z; b1.w *= s1.w;
               }
               uint4 hi, lo;
-              pk_split8(b0, b1, hi, lo);
+              bf16_split8(b0, b1, hi, lo);
               *reinterpret_cast<uint4*>(st + off) = hi;
               *reinterpret_cast<uint4*>(st + b_half + off) = lo;
             }
@@ -244,6 +230,11 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
           mbar_arrive(&full[it]);
         }
       }
+    }
+    if (q.has_side) {   // side job while the tensor core works: pack another operand of the step (grid-strided)
+      const long long total = (long long)q.side.ntile * q.side.nkb * q.side.R * 8;
+      const long long cta = ((long long)z * S + rank) * tiles + tile, nthreads = (long long)tiles * S * gridDim.z * 256;
+      for (long long idx = cta * 256 + tid; idx < total; idx += nthreads) pack_item(q.side, idx);
     }
   }
   trace_mark(p.trace, 4);
@@ -313,34 +304,49 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
     const float* tbase = q.partial + (size_t)(z * tiles + tile) * S * (size_t)(PBM * NB);
     const size_t pstride = (size_t)PBM * NB;
     if (lstm) {
-      const int total = ncols * 32, share = (((total + S - 1) / S) + 31) & ~31;
+      // float4 = 4 consecutive hidden units; the 4 gates of a unit sit 32 rows apart in the tile
+      const int total = ncols * 8, share = (((total + S - 1) / S) + 7) & ~7;
       const int e_beg = rank * share, e_end = min(total, e_beg + share);
       for (int e = e_beg + tid; e < e_end; e += 320) {
-        const int col = e >> 5, ul = e & 31;
+        const int col = e >> 3, ul = (e & 7) * 4;
         const float* pk = tbase + (size_t)col * PBM + ul;
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+        float4 g[4];
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) g[gq] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
         for (int k = 0; k < S; ++k) {
           const float* pp = pk + (size_t)k * pstride;
-          g0 += __ldcg(pp);
-          g1 += __ldcg(pp + 32);
-          g2 += __ldcg(pp + 64);
-          g3 += __ldcg(pp + 96);
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(pp + 32 * gq));
+            g[gq].x += v.x; g[gq].y += v.y; g[gq].z += v.z; g[gq].w += v.w;
+          }
         }
-        lstm_update(p, m0 + col, tile * 32 + ul, g0, g1, g2, g3);
+        const int m = m0 + col, unit = tile * 32 + ul;
+        lstm_update(p, m, unit + 0, g[0].x, g[1].x, g[2].x, g[3].x);
+        lstm_update(p, m, unit + 1, g[0].y, g[1].y, g[2].y, g[3].y);
+        lstm_update(p, m, unit + 2, g[0].z, g[1].z, g[2].z, g[3].z);
+        lstm_update(p, m, unit + 3, g[0].w, g[1].w, g[2].w, g[3].w);
       }
     } else {
-      const int total = ncols * PBM, share = (((total + S - 1) / S) + 31) & ~31;
+      // float4 = 4 consecutive output features; two groups per thread per pass so all partial loads are in flight
+      const int total = ncols * (PBM / 4), share = (((total + S - 1) / S) + 7) & ~7;
       const int e_beg = rank * share, e_end = min(total, e_beg + share);
-      for (int e = e_beg + tid; e < e_end; e += 320) {
-        const int col = e >> 7, row = e & 127;
-        const int n = tile * PBM + row;
-        if (n >= p.N) continue;
-        const float* pk = tbase + e;
-        float v = 0.f;
+      for (int e0 = e_beg + tid; e0 < e_end; e0 += 640) {
+        const int e1 = e0 + 320;
+        const bool has1 = e1 < e_end;
+        const float* pa = tbase + (size_t)e0 * 4;
+        const float* pb = tbase + (size_t)(has1 ? e1 : e0) * 4;
+        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
 #pragma unroll 8
-        for (int k = 0; k < S; ++k) v += __ldcg(pk + (size_t)k * pstride);
-        plain_store(p, m0 + col, n, v);
+        for (int k = 0; k < S; ++k) {
+          const float4 x = __ldcg(reinterpret_cast<const float4*>(pa + (size_t)k * pstride));
+          const float4 y = __ldcg(reinterpret_cast<const float4*>(pb + (size_t)k * pstride));
+          va.x += x.x; va.y += x.y; va.z += x.z; va.w += x.w;
+          vb.x += y.x; vb.y += y.y; vb.z += y.z; vb.w += y.w;
+        }
+        plain_store4(p, m0 + (e0 >> 5), tile * PBM + (e0 & 31) * 4, va);
+        if (has1) plain_store4(p, m0 + (e1 >> 5), tile * PBM + (e1 & 31) * 4, vb);
       }
     }
     __syncthreads();
@@ -422,6 +428,7 @@ int32_t launch_gemm_pk(const PkParams& q_in, cudaStream_t stream, void* ws, size
   const PkPlan pl = gemm_pk_plan(p.M, n_rows, q.nkb, b_packed, device_num_sms());
   SFB_CHECK_ARG(b_packed || (q.nkb + pl.S - 1) / pl.S <= PSTAGES, "gemm_pk: K too long for in-kernel activation conversion");
   SFB_CHECK_ARG(ws && ws_bytes >= pl.bytes && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "gemm_pk: workspace");
+  if (q.has_side) SFB_PROPAGATE(pack_prepare(q.side));
   q.sem = static_cast<unsigned int*>(ws);
   q.partial = reinterpret_cast<float*>(static_cast<char*>(ws) + pl.sem_bytes);
   q.NB = pl.NB;

@@ -17,6 +17,10 @@ struct AttnParams {
   int R, D;
   float* out;   int ldo;                  // [B, D]
   float* alpha; int ldalpha;              // [B, R] or NULL
+  // optional second output: `out` (times an elementwise scale = dropout keep mask) written as bf16 hi/lo into the
+  // packed activation operand of the following gate GEMM (layout: pack.cu), K blocks pk_kb0.. of pk_nkb
+  unsigned char* pk_out; int pk_kb0, pk_nkb, pk_NB, pk_rows_per_z;
+  const float* pk_scale; int pk_ldscale;
   unsigned long long* trace;              // bring-up: 3 timestamps of block 0, or NULL
   // filled by the launcher
   int rows_per_cta, stages;
@@ -85,26 +89,6 @@ void gemm_tc_set_debug(int flags);
 int gemm_tc_read_timestamps(long long* out, int n);
 extern int g_disable_tc;
 
-// ---------------------------------------------------------------- gemm_pk.cu (tcgen05 from pre-packed weights)
-struct PkParams {
-  GemmParams g;                          // epilogue (plain or LSTM), M, N; seg[] = fp32 activations when b_pk == NULL
-  const unsigned char* a_pk;             // packed weights [tiles][nkb][32 KB]
-  const unsigned char* b_pk;             // packed activations [nz][nkb][2*NB*128 B] or NULL
-  int nkb;                               // 64-wide K blocks (all segments)
-  // filled by the launcher
-  int NB, rows_per_z;
-  float* partial; unsigned int* sem;
-};
-struct PkPlan {
-  int tiles, nz, rows_per_z, NB, S;
-  size_t sem_bytes, bytes;               // workspace: self-resetting semaphores (must start zeroed) + partial tiles
-};
-PkPlan gemm_pk_plan(int M, int N_rows, int nkb, bool b_packed, int num_sms);
-int pk_num_kblocks(const int* seg_k, int nseg);
-size_t pk_weight_bytes(int N_rows, int nkb);
-size_t pk_act_bytes(int M, int nkb);
-int32_t launch_gemm_pk(const PkParams& q, cudaStream_t stream, void* ws, size_t ws_bytes);
-
 // ---------------------------------------------------------------- pack.cu
 struct PackSeg {
   const float* x; int ldx; int k;
@@ -122,9 +106,31 @@ struct PackParams {
   int nkb;                               // filled by the launcher
   unsigned long long* trace;
 };
+int32_t pack_prepare(PackParams& p);   // validates and fills nkb
 int32_t launch_pack_rows(const PackParams& p, cudaStream_t stream);
 int32_t launch_fold(const float* A, int lda, const float* s, const float* Bm, int ldb, const float* bv, int D, int NA,
                     int NJ, float* out, int ldo, float* obias, const float* obias_add, cudaStream_t stream);
+
+// ---------------------------------------------------------------- gemm_pk.cu (tcgen05 from pre-packed weights)
+struct PkParams {
+  GemmParams g;                          // epilogue (plain or LSTM), M, N; seg[] = fp32 activations when b_pk == NULL
+  const unsigned char* a_pk;             // packed weights [tiles][nkb][32 KB]
+  const unsigned char* b_pk;             // packed activations [nz][nkb][2*NB*128 B] or NULL
+  int nkb;                               // 64-wide K blocks (all segments)
+  int has_side; PackParams side;         // optional side job for the otherwise idle warps: pack another operand
+  // filled by the launcher
+  int NB, rows_per_z;
+  float* partial; unsigned int* sem;
+};
+struct PkPlan {
+  int tiles, nz, rows_per_z, NB, S;
+  size_t sem_bytes, bytes;               // workspace: self-resetting semaphores (must start zeroed) + partial tiles
+};
+PkPlan gemm_pk_plan(int M, int N_rows, int nkb, bool b_packed, int num_sms);
+int pk_num_kblocks(const int* seg_k, int nseg);
+size_t pk_weight_bytes(int N_rows, int nkb);
+size_t pk_act_bytes(int M, int nkb);
+int32_t launch_gemm_pk(const PkParams& q, cudaStream_t stream, void* ws, size_t ws_bytes);
 
 // ---------------------------------------------------------------- pointwise.cu
 // logit[b,a] = all_u_t[b,a,:] . g[b,:] + sum_d b_a[d] w_out[d] tp[b,d] + b_out   (EltwiseProdScoring rewritten)

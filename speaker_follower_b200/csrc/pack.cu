@@ -10,28 +10,9 @@
 // fold_kernel (pack time only): out[n][j] = sum_d A[d][n] s[d] Bm[d][j], obias[n] = sum_d A[d][n] s[d] bv[d] —
 // collapses the two chained projections of VisualSoftDotAttention (model.py:316-320) and EltwiseProdScoring
 // (model.py:348-351) into one matrix each (DESIGN.md "Arithmetic re-association").
-#include <cuda_bf16.h>
-
-#include "kernels.h"
+#include "pack.cuh"
 
 namespace sfb {
-
-namespace {
-__device__ __forceinline__ void pack_split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
-  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    const float2 hf = __bfloat1622float2(hh);
-    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
-    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-    l[i] = *reinterpret_cast<const uint32_t*>(&ll);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-}  // namespace
 
 // one thread per (tile, kblock, row, 8-wide k group)
 __global__ void __launch_bounds__(256) pack_rows_kernel(const PackParams p) {
@@ -40,71 +21,31 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const PackParams p) {
   pdl_wait();
   trace_mark(p.trace, 1);
   const long long total = (long long)p.ntile * p.nkb * p.R * 8;
-  const size_t half = (size_t)p.R * 128;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int kc = (int)(idx & 7);
-    long long t = idx >> 3;
-    const int r = (int)(t % p.R);
-    t /= p.R;
-    const int kb = (int)(t % p.nkb);
-    const int tile = (int)(t / p.nkb);
-    // source row
-    int src_row;
-    bool row_ok;
-    if (p.lstm_H > 0) {   // gate-interleaved: tile row = gate*32 + unit_local
-      src_row = (r >> 5) * p.lstm_H + tile * 32 + (r & 31);
-      row_ok = tile * 32 + (r & 31) < p.lstm_H;
-    } else {
-      src_row = tile * p.rows_per_tile + r;
-      row_ok = r < p.rows_per_tile && src_row < p.rows_valid;
-    }
-    // K block -> segment
-    int s = 0, cc = kb;
-    while (s + 1 < p.nseg) {
-      const int n = (p.seg[s].k + 63) / 64;
-      if (cc < n) break;
-      cc -= n;
-      ++s;
-    }
-    const PackSeg& g = p.seg[s];
-    const int k = cc * 64 + kc * 8;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (row_ok && k < g.k) {
-      const int xr = g.xrow ? g.xrow[src_row] : src_row;
-      const float* src = g.x + (size_t)xr * g.ldx + k;
-      a = *reinterpret_cast<const float4*>(src);
-      b = *reinterpret_cast<const float4*>(src + 4);
-      if (g.xs) {
-        const float* sp = g.xs + (size_t)src_row * g.ldxs + k;
-        const float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 4);
-        a.x *= s0.x; a.y *= s0.y; a.z *= s0.z; a.w *= s0.w;
-        b.x *= s1.x; b.y *= s1.y; b.z *= s1.z; b.w *= s1.w;
-      }
-    }
-    uint4 hi, lo;
-    pack_split8(a, b, hi, lo);
-    unsigned char* dst = p.out + ((size_t)tile * p.nkb + kb) * (2 * half) + (size_t)(r >> 3) * 1024 + (size_t)kc * 128 + (size_t)(r & 7) * 16;
-    *reinterpret_cast<uint4*>(dst) = hi;
-    *reinterpret_cast<uint4*>(dst + half) = lo;
-  }
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    pack_item(p, idx);
   trace_mark(p.trace, 2);
 }
 
-int32_t launch_pack_rows(const PackParams& p_in, cudaStream_t stream) {
-  PackParams p = p_in;
-  p.trace = next_trace_slot();
+int32_t pack_prepare(PackParams& p) {
   SFB_CHECK_ARG(p.out && (reinterpret_cast<uintptr_t>(p.out) & 127u) == 0, "pack: output missing / misaligned");
   SFB_CHECK_ARG(p.nseg >= 1 && p.nseg <= 3 && p.R >= 8 && (p.R % 8) == 0 && p.ntile >= 1, "pack: bad sizes");
   int nkb = 0;
   for (int s = 0; s < p.nseg; ++s) {
     const PackSeg& g = p.seg[s];
-    SFB_CHECK_ARG(g.x && (g.k % 8) == 0 && (g.ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(g.x) & 15u) == 0,
+    SFB_CHECK_ARG((g.k % 8) == 0 && (g.ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(g.x) & 15u) == 0,
                   "pack: source must be 16-byte aligned with K % 8 == 0");
     SFB_CHECK_ARG(!g.xs || ((reinterpret_cast<uintptr_t>(g.xs) & 15u) == 0 && (g.ldxs % 4) == 0), "pack: scale alignment");
     nkb += (g.k + 63) / 64;
   }
   p.nkb = nkb;
-  const long long total = (long long)p.ntile * nkb * p.R * 8;
+  return 0;
+}
+
+int32_t launch_pack_rows(const PackParams& p_in, cudaStream_t stream) {
+  PackParams p = p_in;
+  p.trace = next_trace_slot();
+  SFB_PROPAGATE(pack_prepare(p));
+  const long long total = (long long)p.ntile * p.nkb * p.R * 8;
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)device_num_sms() * 8;
   if (blocks > cap) blocks = cap;
