@@ -203,20 +203,30 @@ def run_gpu(args, rank, local_rank, world):
     ws = torch.zeros(1 << 26, dtype=torch.uint8, device=dev)   # zero-filled once (semaphores)
     launches_per_step = [0]
 
-    def step(i):
+    qbuf = [torch.empty(B, F, device=dev), torch.empty(B, F, device=dev)]   # visual query carried across steps
+
+    def step(i, first=False):
         j, s = i % POOL, i % 2
+        if blob is None:   # in-place weights: 11 launches + separate tail
+            ops.follower_step(w, ubuf[s], U[j], None, hbuf[s], cbuf[s], ctx[j], mask, store=store, vp_idx=vp[j],
+                              view_idx=view[j], workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v))
+            n = ops.last_launch_count()
+            ops.follower_tail(logit, valid[j], U[j], "argmax", out=(a_t, ubuf[s ^ 1], score, None))
+            launches_per_step[0] = n + ops.last_launch_count()
+            return
+        # packed weights; q_next of this step is the q_in of the next one; rollout tail fused into the last kernel
         ops.follower_step(w, ubuf[s], U[j], None, hbuf[s], cbuf[s], ctx[j], mask, store=store, vp_idx=vp[j],
-                          view_idx=view[j], workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v), packed=blob)
-        n = ops.last_launch_count()
-        ops.follower_tail(logit, valid[j], U[j], "argmax", out=(a_t, ubuf[s ^ 1], score, None))
-        launches_per_step[0] = n + ops.last_launch_count()
+                          view_idx=view[j], workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v),
+                          packed=blob, q_in=None if first else qbuf[s], q_next=qbuf[s ^ 1],
+                          tail={"is_valid": valid[j], "feedback": "argmax", "out": (a_t, ubuf[s ^ 1], score, None)})
+        launches_per_step[0] = ops.last_launch_count()
 
     log("inputs ready")
     # warm-up outside graphs (also configures kernel attributes), then capture POOL-step graphs
     side = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(side):
         for i in range(POOL):
-            step(i)
+            step(i, first=(i == 0))
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     if args.profile_steps:
@@ -275,10 +285,15 @@ def run_gpu(args, rank, local_rank, world):
     for s in range(2):
         gph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gph):
-            ops.follower_step(w, ubuf[s], d_U, None, hbuf[s], cbuf[s], ctx[0], mask, store=store, vp_idx=d_vp,
-                              view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v),
-                              packed=blob)
-            ops.follower_tail(logit, d_valid, d_U, "argmax", out=(a_t, ubuf[s ^ 1], score, None))
+            if blob is None:
+                ops.follower_step(w, ubuf[s], d_U, None, hbuf[s], cbuf[s], ctx[0], mask, store=store, vp_idx=d_vp,
+                                  view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v))
+                ops.follower_tail(logit, d_valid, d_U, "argmax", out=(a_t, ubuf[s ^ 1], score, None))
+            else:
+                ops.follower_step(w, ubuf[s], d_U, None, hbuf[s], cbuf[s], ctx[0], mask, store=store, vp_idx=d_vp,
+                                  view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v),
+                                  packed=blob, q_in=qbuf[s], q_next=qbuf[s ^ 1],
+                                  tail={"is_valid": d_valid, "feedback": "argmax", "out": (a_t, ubuf[s ^ 1], score, None)})
         graphs2.append(gph)
 
     def e2e_step(i):

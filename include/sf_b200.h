@@ -100,6 +100,9 @@ int32_t sfb_debug_read_timestamps(int64_t* out, int32_t n);
 /* Bring-up: after sfb_set_option("trace", 1), every kernel enqueued records {entry, after dependency wait, exit}
  * (globaltimer ns, block 0) in launch order; returns the number of slots copied (16 int64 each: 0-2 as above, 3-15 kernel-specific phases). */
 int32_t sfb_debug_read_trace(int64_t* out, int32_t max_slots);
+/* Bring-up: after sfb_set_option("cta_trace", 1), the attention kernel records per CTA {entry, first row landed,
+ * stream done, exit, smid, query ready} (8 int64 per CTA, globaltimer ns); returns the number of CTA records copied. */
+int32_t sfb_debug_read_cta_trace(int64_t* out, int32_t max_ctas);
 
 /* Device properties the library was built for / sees.  Fills sm (e.g. 100), number of SMs and max
  * opt-in shared memory per block; returns SFB_ERR_NO_DEVICE when there is no usable device. */
@@ -155,11 +158,28 @@ int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
  *     32 KB block per (128-row tile, 64-wide K block), LSTM gates interleaved so a tile owns whole cells;
  *   - linear_in_h/linear_in_v of the visual attention folded into M_q = W_v^T W_h (model.py:316-320) and
  *     EltwiseProdScoring folded into M_g = W_a^T diag(w_o) W_h' plus one constant row (model.py:348-351).
- * sfb_follower_step_packed_fwd then runs the step as: q projection -> attention gather -> pack activations ->
- * gate GEMM + LSTM cell -> [t | W_out_h h] projection -> text attention -> h~ projection -> g projection ->
- * action logits (9 launches, all projections on tcgen05 fed by bulk async copies).  Same arguments, outputs and
- * workspace as sfb_follower_step_fwd; `wl` is still needed for the LSTM biases.  Requires H % 128 == 0 and
- * E, F % 8 == 0 (sfb_follower_packed_bytes returns 0 otherwise -> use sfb_follower_step_fwd). */
+ * sfb_follower_step_packed_fwd then runs the step as: [q projection ->] attention gather (+ packs the gate GEMM's
+ * activations) -> gate GEMM + LSTM cell -> [t | W_out_h h | next q] projection -> text attention -> h~ projection
+ * -> g projection -> action logits [+ rollout tail] (7-8 launches, all projections on tcgen05 fed by bulk async
+ * copies).  Same arguments, outputs and workspace as sfb_follower_step_fwd; `wl` is still needed for the LSTM
+ * biases.  Requires H % 128 == 0 and E, F % 8 == 0 (sfb_follower_packed_bytes returns 0 otherwise -> use
+ * sfb_follower_step_fwd).  Three optional extras, all NULL-able:
+ *   q_in   [B,F]: the visual query W_v^T (W_h h0 + b_h) of THIS step if the caller already has it (the q_next of the
+ *                 call that produced h0) — skips the q projection, the first kernel of the dependency chain;
+ *   q_next [B,F]: receives the query for the NEXT step (computed from h1 in the same launch as the text-attention
+ *                 projection; in train mode, where that launch sees the dropped h1, by one extra launch);
+ *   tail        : arguments of sfb_follower_step_tail — the rollout tail (follower.py:476-505) runs fused behind the
+ *                 logits in the last kernel; `logit` is then masked in place exactly as by the separate call. */
+typedef struct sfb_step_tail {
+  const float*   is_valid;      /* [B,A] */
+  const int32_t* target;        /* [B] or NULL */
+  int32_t        feedback;      /* 0 teacher, 1 argmax, 2 sample */
+  const float*   sample_u;      /* [B] uniforms (feedback == 2) */
+  int32_t*       a_t;           /* [B] */
+  float*         u_next;        /* [B,E] or NULL */
+  float*         action_score;  /* [B] or NULL */
+  float*         ce;            /* [B] or NULL */
+} sfb_step_tail;
 size_t  sfb_follower_packed_bytes(const sfb_dims* dims);
 int32_t sfb_follower_pack_weights(const sfb_dims* dims, const sfb_vis_lstm_weights* wl,
                                   const sfb_softdot_weights* wt, const sfb_scoring_weights* ws,
@@ -171,6 +191,7 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
                                      const float* h0, const float* c0, const float* ctx, const uint8_t* ctx_mask,
                                      const float* drop_x, const float* drop_h,
                                      float* h1, float* c1, float* alpha, float* logit, float* alpha_v,
+                                     const float* q_in, float* q_next, const sfb_step_tail* tail,
                                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Per-step tail of Seq2SeqAgent._rollout_with_loss — follower.py:476-505.

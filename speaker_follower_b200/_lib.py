@@ -42,6 +42,11 @@ class VisualSource(C.Structure):
                 ("vp_idx", c_int_p), ("view_idx", c_int_p), ("img_dim", C.c_int32)]
 
 
+class StepTail(C.Structure):
+    _fields_ = [("is_valid", c_float_p), ("target", c_int_p), ("feedback", C.c_int32), ("sample_u", c_float_p),
+                ("a_t", c_int_p), ("u_next", c_float_p), ("action_score", c_float_p), ("ce", c_float_p)]
+
+
 class SpeakerDecoderWeights(C.Structure):
     _fields_ = [("embedding", c_float_p), ("lstm_w_ih", c_float_p), ("lstm_w_hh", c_float_p),
                 ("lstm_b_ih", c_float_p), ("lstm_b_hh", c_float_p), ("attn", SoftDotWeights),
@@ -60,6 +65,7 @@ SIGNATURES = {
     "sfb_last_launch_count": (C.c_int32, []),
     "sfb_set_option": (C.c_int32, [C.c_char_p, C.c_int32]),
     "sfb_debug_read_trace": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "sfb_debug_read_cta_trace": (C.c_int32, [C.c_void_p, C.c_int32]),
     "sfb_debug_read_timestamps": (C.c_int32, [C.c_void_p, C.c_int32]),
     "sfb_device_info": (C.c_int32, [C.POINTER(C.c_int32)] * 3),
     "sfb_follower_step_workspace_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32, C.c_int32, C.c_int32]),
@@ -86,6 +92,7 @@ SIGNATURES = {
                                                  c_float_p, c_float_p, C.POINTER(VisualSource), c_float_p, c_float_p,
                                                  c_float_p, c_u8_p, c_float_p, c_float_p,
                                                  c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                                 c_float_p, c_float_p, C.POINTER(StepTail),
                                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_follower_step_tail": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, c_float_p, c_float_p, c_int_p, C.c_int32,
                                            c_float_p, c_float_p, c_int_p, c_float_p, c_float_p, c_float_p,

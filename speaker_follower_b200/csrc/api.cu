@@ -22,6 +22,11 @@ unsigned long long* next_trace_slot() {
   return g_trace_buf + 16 * (g_trace_n++);
 }
 
+static unsigned long long* g_cta_buf = nullptr;   // [4096][8]
+static int g_cta_on = 0;
+int g_attn_force_cl = 0;
+unsigned long long* cta_trace_buffer() { return g_cta_on ? g_cta_buf : nullptr; }
+
 int device_num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -93,8 +98,8 @@ static FollowerWs carve_follower(const sfb_dims& d, int B, int L, int A, void* w
     const int sms = device_num_sms();
     const int nkb_h = kblocks(d.H), nkb_g = kblocks(d.E) + kblocks(d.F) + kblocks(d.H);
     size_t mx = gemm_pk_plan(B, 4 * d.H, nkb_g, true, sms).bytes;
-    const int rows[4] = {d.F, 2 * d.H, d.H, d.E + 1};
-    for (int i = 0; i < 4; ++i) {
+    const int rows[5] = {d.F, 2 * d.H, d.H, d.E + 1, 2 * d.H + d.F};
+    for (int i = 0; i < 5; ++i) {
       const size_t b = gemm_pk_plan(B, rows[i], nkb_h, false, sms).bytes;
       if (b > mx) mx = b;
     }
@@ -119,10 +124,10 @@ static FollowerPk layout_follower_pk(const sfb_dims& d) {
   auto take = [&](size_t bytes) { const size_t r = off; off += (bytes + 255) & ~size_t(255); return r; };
   L.nkb_h = kblocks(d.H);
   L.nkb_gates = kblocks(d.E) + kblocks(d.F) + kblocks(d.H);
-  L.a_q = take(pk_weight_bytes(d.F, L.nkb_h));
+  L.a_th = take(pk_weight_bytes(2 * d.H, L.nkb_h));   // [W_in ; W_out_h] immediately followed by M_q:
+  L.a_q = take(pk_weight_bytes(d.F, L.nkb_h));        // one contiguous 2H+F row operand for the fused projection
   L.b_q = take((size_t)d.F * 4);
   L.a_gates = take(pk_weight_bytes(4 * d.H, L.nkb_gates));
-  L.a_th = take(pk_weight_bytes(2 * d.H, L.nkb_h));
   L.a_wc = take(pk_weight_bytes(d.H, L.nkb_h));
   L.a_g = take(pk_weight_bytes(d.E + 1, L.nkb_h));
   L.b_g = take((size_t)(d.E + 4) * 4);
@@ -222,6 +227,7 @@ static int32_t visual_attend(const sfb_dims& d, int B, const float* q, const sfb
   if (pk) {
     a.pk_out = pk->pk_out; a.pk_kb0 = pk->pk_kb0; a.pk_nkb = pk->pk_nkb; a.pk_NB = pk->pk_NB;
     a.pk_rows_per_z = pk->pk_rows_per_z; a.pk_scale = pk->pk_scale; a.pk_ldscale = pk->pk_ldscale;
+    a.has_side = pk->has_side; a.side = pk->side;
   }
   a.q = q; a.ldq = d.F;
   a.R = d.V; a.D = d.F;
@@ -311,6 +317,13 @@ int32_t sfb_set_option(const char* name, int32_t value) {
     return 0;
   }
   if (n == "tc_debug") { gemm_tc_set_debug(value); return 0; }
+  if (n == "attn_cl") { g_attn_force_cl = value; return 0; }
+  if (n == "cta_trace") {   // per-CTA timeline of the attention kernel (last launch wins)
+    g_cta_on = value;
+    if (value && !g_cta_buf && cudaMalloc(&g_cta_buf, 4096 * 8 * sizeof(unsigned long long)) != cudaSuccess) return SFB_ERR_CUDA;
+    if (value) cudaMemset(g_cta_buf, 0, 4096 * 8 * sizeof(unsigned long long));
+    return 0;
+  }
   set_error("unknown option: " + n);
   return SFB_ERR_INVALID_ARG;
 }
@@ -319,6 +332,13 @@ int32_t sfb_debug_read_trace(int64_t* out, int32_t max_slots) {
   if (!g_trace_buf) return 0;
   const int n = g_trace_n < max_slots ? g_trace_n : max_slots;
   if (cudaMemcpy(out, g_trace_buf, (size_t)n * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return n;
+}
+
+int32_t sfb_debug_read_cta_trace(int64_t* out, int32_t max_ctas) {
+  if (!g_cta_buf) return 0;
+  const int n = max_ctas < 4096 ? max_ctas : 4096;
+  if (cudaMemcpy(out, g_cta_buf, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return n;
 }
 
@@ -432,7 +452,9 @@ int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
     g2.seg[0] = GemmSeg{ws.tp, d.D, nullptr, nullptr, 0, wsc->w_a, d.E, d.D, 1};
     g2.M = B; g2.N = d.E; g2.splitk = gemm_pick_splitk(B, d.E, d.D, device_num_sms()); g2.out = ws.g; g2.ldo = d.E;
     SFB_PROPAGATE(launch_gemm(g2, st));
-    ScoringParams sp{all_u_t, ws.g, ws.tp, wsc->b_a, wsc->b_out, d.E, logit, B, A, d.E, d.D};
+    ScoringParams sp{};
+    sp.all_u_t = all_u_t; sp.g = ws.g; sp.tp = ws.tp; sp.b_a = wsc->b_a; sp.b_out = wsc->b_out; sp.ldg = d.E;
+    sp.logit = logit; sp.B = B; sp.A = A; sp.E = d.E; sp.D = d.D;
     SFB_PROPAGATE(launch_action_scoring(sp, st));
   }
   return 0;
@@ -627,47 +649,64 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
                                      const float* all_u_t, const sfb_visual_source* vis, const float* h0,
                                      const float* c0, const float* ctx, const uint8_t* ctx_mask, const float* drop_x,
                                      const float* drop_h, float* h1, float* c1, float* alpha, float* logit,
-                                     float* alpha_v, void* workspace, size_t workspace_bytes, void* stream) {
+                                     float* alpha_v, const float* q_in, float* q_next, const sfb_step_tail* tail,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
   reset_launch_count();
   SFB_PROPAGATE(check_dims(dims));
   SFB_PROPAGATE(check_packable(*dims));
   SFB_CHECK_ARG(wl && vis && packed, "NULL weight/source struct");
   SFB_CHECK_ARG(u_prev && all_u_t && h0 && c0 && ctx && h1 && c1 && logit, "NULL tensor argument");
   SFB_CHECK_ARG(B >= 1 && L >= 1 && A >= 1, "B, L, A >= 1");
+  if (tail) {
+    SFB_CHECK_ARG(tail->is_valid && tail->a_t, "tail: is_valid and a_t are required");
+    SFB_CHECK_ARG(tail->feedback >= 0 && tail->feedback <= 2, "tail: feedback must be 0 (teacher), 1 (argmax) or 2 (sample)");
+    SFB_CHECK_ARG(tail->feedback != 0 || tail->target, "tail: teacher feedback needs target");
+    SFB_CHECK_ARG(tail->feedback != 2 || tail->sample_u, "tail: sample feedback needs sample_u");
+    SFB_CHECK_ARG(!tail->ce || tail->target, "tail: ce needs target");
+  }
   const sfb_dims& d = *dims;
   const FollowerPk P = layout_follower_pk(d);
+  SFB_CHECK_ARG(P.a_q == P.a_th + pk_weight_bytes(2 * d.H, P.nkb_h), "packed layout: fused projection operand not contiguous");
   SFB_CHECK_ARG(packed_bytes >= P.bytes && (reinterpret_cast<uintptr_t>(packed) & 255u) == 0, "packed buffer too small / misaligned");
   FollowerWs ws = carve_follower(d, B, L, A, workspace);
   SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned char* base = static_cast<const unsigned char*>(packed);
+  const float* b_q = reinterpret_cast<const float*>(base + P.b_q);
   auto proj = [&](const unsigned char* a_pk, const float* x, int ldx, int k, int n_out, float* out, int ldo,
-                  const float* bias, const float* padd, int ld_padd, int act, const PackParams* side) {
+                  const float* bias, const float* padd, int ld_padd, int act, int n_split, float* out2, int ldo2,
+                  const float* bias2) {
     PkParams q{};
     q.a_pk = a_pk; q.b_pk = nullptr; q.nkb = kblocks(k);
     q.g.nseg = 1;
     q.g.seg[0] = GemmSeg{x, ldx, nullptr, nullptr, 0, nullptr, 0, k, 0};
     q.g.M = B; q.g.N = n_out; q.g.out = out; q.g.ldo = ldo; q.g.bias0 = bias; q.g.padd = padd; q.g.ld_padd = ld_padd; q.g.act = act;
-    if (side) { q.has_side = 1; q.side = *side; }
+    q.g.n_split = n_split; q.g.out2 = out2; q.g.ldo2 = ldo2; q.g.bias2 = bias2;
     return launch_gemm_pk(q, st, ws.pk, ws.pk_bytes);
   };
-  // The gate GEMM's activation operand [u_prev | feature | h0] (.) drop_x is packed by its producers: u_prev and h0 by
-  // the idle warps of the q projection (side job), feature by the attention kernel's epilogue.
+  // model.py:389  visual query q = W_v^T (W_h h_0 + b_h) = M_q h_0 + b_q: carried over from the previous step's fused
+  // projection when the caller passes it (q_in), computed here otherwise
+  const float* qv = q_in;
+  if (!qv) {
+    SFB_PROPAGATE(proj(base + P.a_q, h0, d.H, d.H, d.F, ws.q, d.F, b_q, nullptr, 0, 0, 0, nullptr, 0, nullptr));
+    qv = ws.q;
+  }
+  // The gate GEMM's activation operand [u_prev | feature | h0] (.) drop_x is packed by the attention kernel: u_prev and
+  // h0 as a side job of all its threads, feature in its epilogue.
   const PkPlan gpl = gemm_pk_plan(B, 4 * d.H, P.nkb_gates, true, device_num_sms());
-  PackParams side{};
-  side.nseg = 3;
-  side.seg[0] = PackSeg{u_prev, d.E, d.E, drop_x, drop_x ? d.E + d.F : 0, nullptr};
-  side.seg[1] = PackSeg{nullptr, d.F, d.F, nullptr, 0, nullptr};   // written by the attention epilogue
-  side.seg[2] = PackSeg{h0, d.H, d.H, nullptr, 0, nullptr};
-  side.ntile = gpl.nz; side.R = gpl.NB; side.rows_per_tile = gpl.rows_per_z; side.rows_valid = B; side.lstm_H = 0;
-  side.out = ws.bpk;
-  // model.py:389  feature, alpha_v = visual_attention_layer(h_0, visual_context):  q = M_q h0 + b_q
-  SFB_PROPAGATE(proj(base + P.a_q, h0, d.H, d.H, d.F, ws.q, d.F, reinterpret_cast<const float*>(base + P.b_q), nullptr, 0, 0, &side));
   {
     AttnParams pk{};
     pk.pk_out = ws.bpk; pk.pk_kb0 = kblocks(d.E); pk.pk_nkb = P.nkb_gates; pk.pk_NB = gpl.NB; pk.pk_rows_per_z = gpl.rows_per_z;
     pk.pk_scale = drop_x ? drop_x + d.E : nullptr; pk.pk_ldscale = d.E + d.F;
-    SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, alpha_v, ws.av, ws.av_bytes, st, &pk));
+    pk.has_side = 1;
+    PackParams& side = pk.side;
+    side.nseg = 3;
+    side.seg[0] = PackSeg{u_prev, d.E, d.E, drop_x, drop_x ? d.E + d.F : 0, nullptr};
+    side.seg[1] = PackSeg{nullptr, d.F, d.F, nullptr, 0, nullptr};   // written by the attention epilogue
+    side.seg[2] = PackSeg{h0, d.H, d.H, nullptr, 0, nullptr};
+    side.ntile = gpl.nz; side.R = gpl.NB; side.rows_per_tile = gpl.rows_per_z; side.rows_valid = B; side.lstm_H = 0;
+    side.out = ws.bpk;
+    SFB_PROPAGATE(visual_attend(d, B, qv, *vis, ws.feat, alpha_v, ws.av, ws.av_bytes, st, &pk));
   }
   // model.py:391-393  LSTMCell(drop(cat(u_t_prev, feature)), (h_0, c_0)) on tcgen05 from the packed operands
   {
@@ -679,8 +718,14 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
     e.h1 = h1; e.c1 = c1; e.h1_drop = ws.h1d; e.gates_act = ws.gates_act;
     SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));
   }
-  // model.py:395  text attention: [t | W_out_h h1d] in one projection, attention over ctx, h~ = tanh(W_out_c wc + .)
-  SFB_PROPAGATE(proj(base + P.a_th, ws.h1d, d.H, d.H, 2 * d.H, ws.th, 2 * d.H, nullptr, nullptr, 0, 0, nullptr));
+  // model.py:395  text attention: [t | W_out_h h1d] in one projection — and, software-pipelined across the
+  // recurrence, the NEXT step's visual query M_q h_1 + b_q in the same launch (eval mode: h1d == h_1)
+  if (q_next && !drop_h) {
+    SFB_PROPAGATE(proj(base + P.a_th, ws.h1d, d.H, d.H, 2 * d.H + d.F, ws.th, 2 * d.H, nullptr, nullptr, 0, 0, 2 * d.H, q_next,
+                       d.F, b_q));
+  } else {
+    SFB_PROPAGATE(proj(base + P.a_th, ws.h1d, d.H, d.H, 2 * d.H, ws.th, 2 * d.H, nullptr, nullptr, 0, 0, 0, nullptr, 0, nullptr));
+  }
   {
     AttnParams a{};
     a.q = ws.th; a.ldq = 2 * d.H; a.R = L; a.D = d.H;
@@ -689,11 +734,21 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
     a.out = ws.wc; a.ldo = d.H; a.alpha = alpha; a.ldalpha = L;
     SFB_PROPAGATE(launch_soft_dot_attention(a, B, ws.at, ws.at_bytes, st));
   }
-  SFB_PROPAGATE(proj(base + P.a_wc, ws.wc, d.H, d.H, d.H, ws.htilde, d.H, nullptr, ws.th + d.H, 2 * d.H, 1, nullptr));
+  SFB_PROPAGATE(proj(base + P.a_wc, ws.wc, d.H, d.H, d.H, ws.htilde, d.H, nullptr, ws.th + d.H, 2 * d.H, 1, 0, nullptr, 0, nullptr));
   // model.py:396  logit = decoder2action(h_tilde, all_u_t):  g = M_g h~ + b_g (column E = the per-row constant)
-  SFB_PROPAGATE(proj(base + P.a_g, ws.htilde, d.H, d.H, d.E + 1, ws.g, ws.ldg, reinterpret_cast<const float*>(base + P.b_g), nullptr, 0, 0, nullptr));
-  ScoringParams sp{all_u_t, ws.g, nullptr, nullptr, nullptr, ws.ldg, logit, B, A, d.E, d.D};
-  return launch_action_scoring(sp, st);
+  SFB_PROPAGATE(proj(base + P.a_g, ws.htilde, d.H, d.H, d.E + 1, ws.g, ws.ldg, reinterpret_cast<const float*>(base + P.b_g), nullptr,
+                     0, 0, 0, nullptr, 0, nullptr));
+  ScoringParams sp{};
+  sp.all_u_t = all_u_t; sp.g = ws.g; sp.tp = nullptr; sp.ldg = ws.ldg; sp.logit = logit; sp.B = B; sp.A = A; sp.E = d.E; sp.D = d.D;
+  if (tail) {   // follower.py:476-505 fused behind the logits
+    sp.has_tail = 1;
+    sp.tail = TailParams{logit, tail->is_valid, tail->target, tail->feedback, tail->sample_u, all_u_t, tail->a_t,
+                         tail->u_next, tail->action_score, tail->ce, B, A, d.E, nullptr};
+  }
+  SFB_PROPAGATE(launch_action_scoring(sp, st));
+  if (q_next && drop_h)   // train mode: the next query needs the un-dropped h_1 -> its own projection
+    SFB_PROPAGATE(proj(base + P.a_q, h1, d.H, d.H, d.F, q_next, d.F, b_q, nullptr, 0, 0, 0, nullptr, 0, nullptr));
+  return 0;
 }
 
 }  // extern "C"

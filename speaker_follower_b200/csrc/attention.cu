@@ -9,8 +9,9 @@
 // owns rows rank, rank+CL, ... (interleaved, so padding masks at the end of a sequence stay balanced).  A CTA streams
 // its rows HBM -> shared memory through a ring of bulk async copies (cp.async.bulk = TMA engine, one mbarrier per
 // stage, evict-first, masked rows never fetched; in gather mode a row is two copies: feature table + orientation
-// table).  The ring is as deep as 70 KB allows (8 slab rows; 3 CTAs per SM -> ~200 KB of loads in flight per SM) and
-// a stage is refilled the moment its row has been consumed, so the stream never drains.  Each thread keeps its slice
+// table).  The ring is as deep as 52 KB allows (6 slab rows; 4 CTAs per SM -> ~200 KB of loads in flight per SM, and
+// enough free CTA slots that all clusters of a B=100 launch are resident in ONE wave) and a stage is refilled the
+// moment its row has been consumed, so the stream never drains.  Each thread keeps its slice
 // of the row in registers between the score and the accumulation (a row is read from shared memory once): block-wide
 // dot (warp shuffles + one __syncthreads), online softmax, FMA into the running weighted sum.  The CL partial results
 // (max, sum, weighted sum) are merged INSIDE the cluster through distributed shared memory: stats are read from the
@@ -20,12 +21,13 @@
 #include <cuda_bf16.h>
 
 #include "kernels.h"
+#include "pack.cuh"
 
 namespace sfb {
 
 namespace {
 constexpr int ATT_MAX_STAGES = 32;            // ring depth (one lane of warp 0 per stage when priming)
-constexpr size_t ATT_RING_BUDGET = 70 * 1024;  // bytes of ring per CTA -> 3 CTAs per SM
+constexpr size_t ATT_RING_BUDGET = 52 * 1024;  // bytes of ring per CTA -> 4 CTAs per SM (6 slab rows each)
 
 __device__ __forceinline__ void st_cluster_f32x4(uint32_t addr, const float4& v) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
@@ -35,7 +37,7 @@ __device__ __forceinline__ void st_cluster_f32x4(uint32_t addr, const float4& v)
 
 // NJ float4 slices per thread, NT threads per CTA (D <= NJ * NT * 4), RB rows consumed per block barrier
 template <int NJ, int NT, int RB>
-__global__ void __launch_bounds__(NT) soft_dot_attn_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(const AttnParams p) {
   constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -55,6 +57,13 @@ __global__ void __launch_bounds__(NT) soft_dot_attn_kernel(const AttnParams p) {
 
   trace_mark(p.trace, 0);
   pdl_launch_dependents();   // let the next kernel of the step start its own prologue / prefetch
+  unsigned long long* ct = p.cta_trace ? p.cta_trace + (size_t)(b * CL + rank) * 8 : nullptr;
+  if (ct && tid == 0) {
+    ct[0] = globaltimer_ns();
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    ct[4] = smid;
+  }
 
   // ---- 1. warp 0: compact the unmasked rows, arm the ring, launch the first NSTG copies
   size_t ba = 0, bb = 0;
@@ -99,9 +108,15 @@ __global__ void __launch_bounds__(NT) soft_dot_attn_kernel(const AttnParams p) {
       acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  if (p.has_side) {   // side job: pack step operands another kernel needs (one item per thread at B=100)
+    const long long total = (long long)p.side.ntile * p.side.nkb * p.side.R * 8;
+    const long long nthreads = (long long)gridDim.x * gridDim.y * NT;
+    for (long long idx = ((long long)b * CL + rank) * NT + tid; idx < total; idx += nthreads) pack_item(p.side, idx);
+  }
   __syncthreads();
   const int nvalid = s_nvalid;
   trace_mark(p.trace, 4);
+  if (ct && tid == 0) ct[5] = globaltimer_ns();   // q available, ring primed
 
   // ---- 3. stream: RB rows per iteration (independent dot products -> ILP), one block barrier per iteration, every
   // stage refilled as soon as its row sits in registers
@@ -135,6 +150,7 @@ __global__ void __launch_bounds__(NT) soft_dot_attn_kernel(const AttnParams p) {
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
       for (int r = 0; r < RB; ++r) part[r] += __shfl_xor_sync(0xffffffffu, part[r], o);
+    if (ct && tid == 0 && i0 == 0) ct[1] = globaltimer_ns();
     float* rb = red + ((i0 / RB) & 1) * NW * RB;
     if (lane == 0)
 #pragma unroll
@@ -178,6 +194,7 @@ __global__ void __launch_bounds__(NT) soft_dot_attn_kernel(const AttnParams p) {
     m = mn;
   }
   trace_mark(p.trace, 5);
+  if (ct && tid == 0) ct[2] = globaltimer_ns();
 
   // ---- 4. merge inside the cluster through distributed shared memory
   if (tid == 0) {
@@ -220,11 +237,11 @@ __global__ void __launch_bounds__(NT) soft_dot_attn_kernel(const AttnParams p) {
       }
     }
   }
+  cluster_sync_all();   // pushed partial columns visible to their owner (no global stores pending: cheap release)
+  trace_mark(p.trace, 7);
   if (p.alpha)
     for (int i = tid; i < nmine; i += NT)
       p.alpha[(size_t)b * p.ldalpha + rank + CL * i] = sc[i] == -INFINITY ? 0.f : __expf(sc[i] - M) * inv;
-  cluster_sync_all();   // pushed partial columns visible to their owner
-  trace_mark(p.trace, 7);
   {
     const float4* in4 = reinterpret_cast<const float4*>(ring);
     float4* out4 = reinterpret_cast<float4*>(p.out + (size_t)b * p.ldo);
@@ -255,6 +272,7 @@ __global__ void __launch_bounds__(NT) soft_dot_attn_kernel(const AttnParams p) {
     }
   }
   trace_mark(p.trace, 2);
+  if (ct && tid == 0) ct[3] = globaltimer_ns();
   if (p.trace && tid == 0 && b == gridDim.y - 1 && rank == CL - 1) p.trace[3] = globaltimer_ns();   // last cluster
 }
 
@@ -316,16 +334,25 @@ int32_t launch_soft_dot_attention(AttnParams p, int B, void* ws, size_t ws_bytes
   SFB_CHECK_ARG((p.lenA % 4) == 0 && (p.lenB % 4) == 0 && p.lenA + p.lenB == p.D, "bad row segments");
   SFB_CHECK_ARG(p.R >= 1, "need at least one row");
   SFB_CHECK_ARG(B <= 65535, "attention: batch > 65535");
-  const AttnPlan pl = attention_plan(B, p.R, p.D, device_num_sms());
+  AttnPlan pl = attention_plan(B, p.R, p.D, device_num_sms());
+  if (g_attn_force_cl > 0) {   // bring-up: force the cluster size
+    pl.split = g_attn_force_cl;
+    pl.rows_per_cta = (p.R + pl.split - 1) / pl.split;
+    int st = (int)(ATT_RING_BUDGET / ((size_t)p.D * 4));
+    st = st > pl.rows_per_cta ? pl.rows_per_cta : st;
+    pl.stages = st < 4 ? 4 : (st > ATT_MAX_STAGES ? ATT_MAX_STAGES : st);
+  }
+  p.cta_trace = (size_t)B * pl.split <= 4096 ? cta_trace_buffer() : nullptr;
   p.rows_per_cta = pl.rows_per_cta;
   p.stages = pl.stages;
   p.trace = next_trace_slot();
   p.ticket = nullptr;
   p.part = nullptr;
+  if (p.has_side) SFB_PROPAGATE(pack_prepare(p.side));
   SFB_CHECK_ARG(attn_smem_bytes(p.stages, p.D, p.rows_per_cta) <= 200 * 1024, "attention rows do not fit shared memory");
   if (p.D <= 512) return launch_attn_t<1, 128, 4>(p, B, pl.split, stream);
   if (p.D <= 1024) return launch_attn_t<1, 256, 4>(p, B, pl.split, stream);
-  return launch_attn_t<3, 256, 2>(p, B, pl.split, stream);
+  return launch_attn_t<3, 256, 1>(p, B, pl.split, stream);
 }
 
 }  // namespace sfb

@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
 
   const uint32_t b_half = (uint32_t)(NB / 8) * PSBO;          // bytes of one (hi | lo) activation tile
   const uint32_t stage_bytes = 2 * PA_HALF + 2 * b_half;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)PSTAGES * stage_bytes);
+  const int NST = q.nstages;   // allocated stages (<= PSTAGES)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NST * stage_bytes);
   uint64_t* empty = full + PSTAGES;
   uint64_t* done = empty + PSTAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
 
   trace_mark(p.trace, 0);
   pdl_launch_dependents();
+  unsigned int sem_gen = 0;
 
   if (warp == 9) {
     // =============================== producer: bulk copies ===============================
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
       const unsigned char* a_src = q.a_pk + ((size_t)tile * q.nkb + kb_begin) * (2 * PA_HALF);
       const unsigned char* b_src = B_PACKED ? q.b_pk + ((size_t)z * q.nkb + kb_begin) * (2 * b_half) : nullptr;
       const uint32_t tx = 2 * PA_HALF + (B_PACKED ? 2 * b_half : 0u);
-      const int pre = min(nit, PSTAGES);
+      const int pre = min(nit, NST);
       for (int it = 0; it < pre; ++it) {   // weights first: not produced inside the step
         mbar_expect_tx(&full[it], tx);
         bulk_g2s_hint(smem + (size_t)it * stage_bytes, a_src + (size_t)it * (2 * PA_HALF), 2 * PA_HALF, &full[it], pol);
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
         for (int it = 0; it < pre; ++it)
           bulk_g2s(smem + (size_t)it * stage_bytes + 2 * PA_HALF, b_src + (size_t)it * (2 * b_half), 2 * b_half, &full[it]);
       for (int it = pre; it < nit; ++it) {
-        const int s = it % PSTAGES, use = it / PSTAGES;
+        const int s = it % NST, use = it / NST;
         pk_wait(&empty[s], (uint32_t)(use - 1) & 1u);
         mbar_expect_tx(&full[s], tx);
         bulk_g2s_hint(smem + (size_t)s * stage_bytes, a_src + (size_t)it * (2 * PA_HALF), 2 * PA_HALF, &full[s], pol);
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
     pdl_wait();
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(PBM >> 4) << 24);
     for (int it = 0; it < nit; ++it) {
-      const int s = it % PSTAGES, use = it / PSTAGES;
+      const int s = it % NST, use = it / NST;
       pk_wait(&full[s], (uint32_t)use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
@@ -161,8 +163,10 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
     // =============================== warps 0-7 ===============================
     pdl_wait();
     trace_mark(p.trace, 1);
+    if (tid == 0 && S > 1)   // generation of this tile's split-K barrier, read long before it is needed
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(sem_gen) : "l"(q.sem + 2 * (z * tiles + tile) + 1) : "memory");
     if (!B_PACKED) {
-      // fp32 activations -> bf16 hi/lo core matrices (nit <= PSTAGES: every block has its own stage)
+      // fp32 activations -> bf16 hi/lo core matrices, one K block per stage of the ring
       const int r_in = lane & 7, kc_in = lane >> 3;
       float4 rb[2][4][2], rs[HAS_XS ? 2 : 1][HAS_XS ? 4 : 1][2];
       auto load_block = [&](int blk, int set) {
@@ -208,7 +212,9 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
           const int it = it0 + u;
           if (it >= nit) break;
           if (it + 1 < nit) load_block(kb_begin + it + 1, u ^ 1);
-          unsigned char* st = smem + (size_t)it * stage_bytes + 2 * PA_HALF;
+          const int sidx = it % NST;
+          if (it >= NST) pk_wait(&empty[sidx], (uint32_t)(it / NST - 1) & 1u);   // ring: the MMAs that read it retired
+          unsigned char* st = smem + (size_t)sidx * stage_bytes + 2 * PA_HALF;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int wu = warp + 8 * i;
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
             }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(&full[it]);
+          mbar_arrive(&full[sidx]);
         }
       }
     }
@@ -283,17 +289,23 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
   if (!direct) {
     __threadfence();
     __syncthreads();
-    // ---- the S CTAs of this tile meet at a semaphore (all co-resident: grid <= #SMs at 1 CTA/SM)
+    // ---- the S CTAs of this tile meet at a sense-reversing barrier {count, generation} (all co-resident:
+    // grid <= #SMs at 1 CTA/SM).  The last arriver resets the count BEFORE it releases the others, so nothing is left
+    // to do on the exit path and the barrier is valid for any S on its next use.
     unsigned int* my_sem = q.sem + 2 * (z * tiles + tile);
     if (S > 1) {
       if (tid == 0) {
-        atomicAdd(my_sem, 1u);
-        unsigned int seen = 0;
-        for (uint32_t i = 0; i < (1u << 26); ++i) {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(my_sem) : "memory");
-          if (seen >= (unsigned int)S) break;
+        const unsigned int old = atomicAdd(my_sem, 1u);
+        if (old == (unsigned int)S - 1u) {
+          atomicExch(my_sem, 0u);
+          __threadfence();
+          atomicAdd(my_sem + 1, 1u);
+        } else {
+          unsigned int gen = sem_gen;
+          for (uint32_t i = 0; i < (1u << 26) && gen == sem_gen; ++i)
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(my_sem + 1) : "memory");
+          if (gen == sem_gen) __trap();
         }
-        if (seen < (unsigned int)S) __trap();
         __threadfence();
       }
       __syncthreads();
@@ -322,11 +334,7 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
             g[gq].x += v.x; g[gq].y += v.y; g[gq].z += v.z; g[gq].w += v.w;
           }
         }
-        const int m = m0 + col, unit = tile * 32 + ul;
-        lstm_update(p, m, unit + 0, g[0].x, g[1].x, g[2].x, g[3].x);
-        lstm_update(p, m, unit + 1, g[0].y, g[1].y, g[2].y, g[3].y);
-        lstm_update(p, m, unit + 2, g[0].z, g[1].z, g[2].z, g[3].z);
-        lstm_update(p, m, unit + 3, g[0].w, g[1].w, g[2].w, g[3].w);
+        lstm_update4(p, m0 + col, tile * 32 + ul, g[0], g[1], g[2], g[3]);
       }
     } else {
       // float4 = 4 consecutive output features; two groups per thread per pass so all partial loads are in flight
@@ -350,13 +358,6 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
       }
     }
     __syncthreads();
-    if (S > 1 && tid == 0) {   // last CTA to leave re-arms the semaphore for the next launch
-      const unsigned int gone = atomicAdd(my_sem + 1, 1u);
-      if (gone == (unsigned int)S - 1) {
-        atomicExch(my_sem + 1, 0u);
-        atomicExch(my_sem, 0u);
-      }
-    }
   } else {
     __syncthreads();
   }
@@ -383,12 +384,12 @@ PkPlan gemm_pk_plan(int M, int N_rows, int nkb, bool b_packed, int num_sms) {
   if (s > nkb) s = nkb;
   if (s > 16) s = 16;
   if (s < 1) s = 1;
-  if (!b_packed) {                                  // in-kernel conversion keeps every K block in its own stage
-    const int need = (nkb + PSTAGES - 1) / PSTAGES;
-    if (s < need) s = need;
-  }
+  (void)b_packed;
   pl.S = s;
-  pl.sem_bytes = ((size_t)pl.tiles * pl.nz * 2 * sizeof(unsigned int) + 255) & ~size_t(255);
+  // fixed-size barrier region: projections of different geometry share one workspace, so the partial tiles must
+  // start at the same offset for all of them (split-K happens only when tiles*nz <= #SMs/2, far below 512 pairs)
+  pl.sem_bytes = 4096;
+  if (pl.tiles * pl.nz > 512) pl.S = 1;
   pl.bytes = pl.sem_bytes + (((size_t)pl.tiles * pl.nz * pl.S * PBM * pl.NB * sizeof(float) + 255) & ~size_t(255));
   return pl;
 }
@@ -426,7 +427,6 @@ int32_t launch_gemm_pk(const PkParams& q_in, cudaStream_t stream, void* ws, size
     SFB_CHECK_ARG((reinterpret_cast<uintptr_t>(q.b_pk) & 127u) == 0, "gemm_pk: packed activations misaligned");
   }
   const PkPlan pl = gemm_pk_plan(p.M, n_rows, q.nkb, b_packed, device_num_sms());
-  SFB_CHECK_ARG(b_packed || (q.nkb + pl.S - 1) / pl.S <= PSTAGES, "gemm_pk: K too long for in-kernel activation conversion");
   SFB_CHECK_ARG(ws && ws_bytes >= pl.bytes && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "gemm_pk: workspace");
   if (q.has_side) SFB_PROPAGATE(pack_prepare(q.side));
   q.sem = static_cast<unsigned int*>(ws);
@@ -434,7 +434,12 @@ int32_t launch_gemm_pk(const PkParams& q_in, cudaStream_t stream, void* ws, size
   q.NB = pl.NB;
   q.rows_per_z = pl.rows_per_z;
   const size_t stage_bytes = 2 * (size_t)PA_HALF + 2 * (size_t)(pl.NB / 8) * PSBO;
-  const size_t smem = PSTAGES * stage_bytes + 8 * sizeof(uint64_t) + 16;
+  // only as many stages as this launch can fill: a 1-block K range leaves room for the NEXT kernel's CTAs to become
+  // resident early (PDL) and prefetch their own operands
+  int nst = (q.nkb + pl.S - 1) / pl.S;
+  if (nst > PSTAGES) nst = PSTAGES;
+  q.nstages = nst;
+  const size_t smem = (size_t)nst * stage_bytes + 8 * sizeof(uint64_t) + 16;
   const dim3 grid(pl.tiles, pl.S, pl.nz), block(320, 1, 1), cl(1, 1, 1);
 #define SFB_PK_LAUNCH(BP, XS)                                                                                       \
   do {                                                                                                              \

@@ -5,6 +5,28 @@
 
 namespace sfb {
 
+// ---------------------------------------------------------------- pack.cu
+struct PackSeg {
+  const float* x; int ldx; int k;
+  const float* xs; int ldxs;             // optional elementwise scale, indexed by the logical row
+  const int32_t* xrow;                   // optional row indirection
+};
+struct PackParams {
+  PackSeg seg[3];
+  int nseg;
+  int ntile;                             // row tiles (weights: ceil(N/128) or H/32; activations: batch tiles)
+  int R;                                 // packed rows per tile (128 for weights, NB for activations)
+  int rows_per_tile, rows_valid;         // plain mapping: source row = tile*rows_per_tile + r, valid below rows_valid
+  int lstm_H;                            // > 0: gate-interleaved LSTM weights, source row = (r/32)*H + tile*32 + r%32
+  unsigned char* out;
+  int nkb;                               // filled by the launcher
+  unsigned long long* trace;
+};
+int32_t pack_prepare(PackParams& p);   // validates and fills nkb
+int32_t launch_pack_rows(const PackParams& p, cudaStream_t stream);
+int32_t launch_fold(const float* A, int lda, const float* s, const float* Bm, int ldb, const float* bv, int D, int NA,
+                    int NJ, float* out, int ldo, float* obias, const float* obias_add, cudaStream_t stream);
+
 // ---------------------------------------------------------------- attention.cu
 struct AttnParams {
   const float* q;   int ldq;              // [B, D] query
@@ -21,6 +43,8 @@ struct AttnParams {
   // packed activation operand of the following gate GEMM (layout: pack.cu), K blocks pk_kb0.. of pk_nkb
   unsigned char* pk_out; int pk_kb0, pk_nkb, pk_NB, pk_rows_per_z;
   const float* pk_scale; int pk_ldscale;
+  int has_side; PackParams side;          // optional side job after the dependency wait: pack other step operands
+  unsigned long long* cta_trace;          // bring-up: per-CTA {entry, first row landed, stream done, exit, smid}
   unsigned long long* trace;              // bring-up: 3 timestamps of block 0, or NULL
   // filled by the launcher
   int rows_per_cta, stages;
@@ -69,6 +93,8 @@ struct GemmParams {
   const float* bias0; const float* bias1; // [N] or NULL
   const float* oscale;                    // [N] or NULL: out = act(acc + biases) * oscale[n]
   const float* padd; int ld_padd;         // [M, >=N] or NULL: added before the activation (pre-computed partial sum)
+  // optional split output: columns n >= n_split (a multiple of 128) go to out2[m*ldo2 + n - n_split] + bias2, no act
+  int n_split; float* out2; int ldo2; const float* bias2;
   int act;                                // 0 none, 1 tanh
   int exact;                              // 1: force the exact-fp32 FFMA path (default: 3xTF32 mma.sync for M > 32)
   LstmEpilogue lstm;
@@ -89,28 +115,6 @@ void gemm_tc_set_debug(int flags);
 int gemm_tc_read_timestamps(long long* out, int n);
 extern int g_disable_tc;
 
-// ---------------------------------------------------------------- pack.cu
-struct PackSeg {
-  const float* x; int ldx; int k;
-  const float* xs; int ldxs;             // optional elementwise scale, indexed by the logical row
-  const int32_t* xrow;                   // optional row indirection
-};
-struct PackParams {
-  PackSeg seg[3];
-  int nseg;
-  int ntile;                             // row tiles (weights: ceil(N/128) or H/32; activations: batch tiles)
-  int R;                                 // packed rows per tile (128 for weights, NB for activations)
-  int rows_per_tile, rows_valid;         // plain mapping: source row = tile*rows_per_tile + r, valid below rows_valid
-  int lstm_H;                            // > 0: gate-interleaved LSTM weights, source row = (r/32)*H + tile*32 + r%32
-  unsigned char* out;
-  int nkb;                               // filled by the launcher
-  unsigned long long* trace;
-};
-int32_t pack_prepare(PackParams& p);   // validates and fills nkb
-int32_t launch_pack_rows(const PackParams& p, cudaStream_t stream);
-int32_t launch_fold(const float* A, int lda, const float* s, const float* Bm, int ldb, const float* bv, int D, int NA,
-                    int NJ, float* out, int ldo, float* obias, const float* obias_add, cudaStream_t stream);
-
 // ---------------------------------------------------------------- gemm_pk.cu (tcgen05 from pre-packed weights)
 struct PkParams {
   GemmParams g;                          // epilogue (plain or LSTM), M, N; seg[] = fp32 activations when b_pk == NULL
@@ -119,7 +123,7 @@ struct PkParams {
   int nkb;                               // 64-wide K blocks (all segments)
   int has_side; PackParams side;         // optional side job for the otherwise idle warps: pack another operand
   // filled by the launcher
-  int NB, rows_per_z;
+  int NB, rows_per_z, nstages;
   float* partial; unsigned int* sem;
 };
 struct PkPlan {
@@ -133,6 +137,12 @@ size_t pk_act_bytes(int M, int nkb);
 int32_t launch_gemm_pk(const PkParams& q, cudaStream_t stream, void* ws, size_t ws_bytes);
 
 // ---------------------------------------------------------------- pointwise.cu
+struct TailParams {
+  float* logit; const float* is_valid; const int32_t* target; int feedback; const float* sample_u;
+  const float* all_u_t; int32_t* a_t; float* u_next; float* action_score; float* ce;
+  int B, A, E;
+  unsigned long long* trace;
+};
 // logit[b,a] = all_u_t[b,a,:] . g[b,:] + sum_d b_a[d] w_out[d] tp[b,d] + b_out   (EltwiseProdScoring rewritten)
 struct ScoringParams {
   const float* all_u_t;                   // [B,A,E]
@@ -140,21 +150,18 @@ struct ScoringParams {
   const float* tp;                        // [B,D]  linear_in_h(h_tilde) (.) w_out; NULL: constant = g[b*ldg + E] (folded weights)
   const float* b_a; const float* b_out;
   int ldg;                                // row stride of g
+  int has_tail; TailParams tail;          // optional fused rollout tail (follower.py:476-505) on the fresh logits
   float* logit;                           // [B,A]
   int B, A, E, D;
   unsigned long long* trace;
 };
 int32_t launch_action_scoring(const ScoringParams& p, cudaStream_t stream);
 
-struct TailParams {
-  float* logit; const float* is_valid; const int32_t* target; int feedback; const float* sample_u;
-  const float* all_u_t; int32_t* a_t; float* u_next; float* action_score; float* ce;
-  int B, A, E;
-  unsigned long long* trace;
-};
 int32_t launch_follower_tail(const TailParams& p, cudaStream_t stream);
 
 int device_num_sms();
-unsigned long long* next_trace_slot();   // NULL unless sfb_set_option("trace", 1)
+unsigned long long* next_trace_slot();
+unsigned long long* cta_trace_buffer();  // NULL unless sfb_set_option("cta_trace", 1)
+extern int g_attn_force_cl;   // NULL unless sfb_set_option("trace", 1)
 
 }  // namespace sfb

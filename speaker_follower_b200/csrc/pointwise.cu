@@ -4,91 +4,9 @@
 
 namespace sfb {
 
-// ---------------------------------------------------------------- action scoring
-// w_out . ((W_h ht + b_h) (.) (W_a u + b_a)) + b_out  ==  u . g + c   with  tp = w_out (.) (W_h ht + b_h),
-// g = W_a^T tp  and  c = sum_d b_a[d] tp[d] + b_out   (SURVEY.md §7 hard part 1).
-// The A candidate rows of a batch element are step inputs: with PDL they are pulled into shared memory (bulk
-// async copies) while the kernels producing g / t' are still running.
-__global__ void __launch_bounds__(256) action_scoring_kernel(const ScoringParams p, const int stage_rows) {
-  extern __shared__ __align__(128) unsigned char sraw[];
-  float* gs = reinterpret_cast<float*>(sraw);                       // [E]
-  float* us = gs + p.E;                                             // [A][E] when stage_rows
-  uint64_t* bar = reinterpret_cast<uint64_t*>(us + (stage_rows ? (size_t)p.A * p.E : 0));
-  __shared__ float red[8];
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nvec = p.E >> 2;
-  trace_mark(p.trace, 0);
-  pdl_launch_dependents();
-  if (stage_rows && tid == 0) {
-    mbar_init(bar, 1);
-    mbar_fence_init();
-    mbar_expect_tx(bar, (uint32_t)((size_t)p.A * p.E * 4));
-    const uint64_t pol = policy_evict_first();
-    for (int a = 0; a < p.A; ++a)
-      bulk_g2s_hint(us + (size_t)a * p.E, p.all_u_t + ((size_t)b * p.A + a) * p.E, (uint32_t)p.E * 4u, bar, pol);
-  }
-  pdl_wait();
-  trace_mark(p.trace, 1);
-  const float4* g4 = reinterpret_cast<const float4*>(p.g + (size_t)b * p.ldg);
-  for (int j = tid; j < nvec; j += 256) reinterpret_cast<float4*>(gs)[j] = g4[j];
-  float c = 0.f;
-  if (p.tp)
-    for (int d = tid; d < p.D; d += 256) c = fmaf(__ldg(p.b_a + d), p.tp[(size_t)b * p.D + d], c);
-  c = warp_sum(c);
-  if (lane == 0) red[warp] = c;
-  __syncthreads();
-  float cst = p.tp ? __ldg(p.b_out) : p.g[(size_t)b * p.ldg + p.E];   // folded weights carry the constant as g[E]
-#pragma unroll
-  for (int w = 0; w < 8; ++w) cst += red[w];
-  if (stage_rows) mbar_wait(bar, 0);
-  for (int a = warp; a < p.A; a += 8) {
-    const float4* u4 = stage_rows ? reinterpret_cast<const float4*>(us + (size_t)a * p.E)
-                                  : reinterpret_cast<const float4*>(p.all_u_t + ((size_t)b * p.A + a) * p.E);
-    float acc = 0.f;
-    for (int j = lane; j < nvec; j += 32) {
-      const float4 u = u4[j];
-      const float4 g = reinterpret_cast<const float4*>(gs)[j];
-      acc = fmaf(u.x, g.x, acc);
-      acc = fmaf(u.y, g.y, acc);
-      acc = fmaf(u.z, g.z, acc);
-      acc = fmaf(u.w, g.w, acc);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) p.logit[(size_t)b * p.A + a] = acc + cst;
-  }
-  __syncthreads();
-  trace_mark(p.trace, 2);
-}
-
-int32_t launch_action_scoring(const ScoringParams& p_in, cudaStream_t stream) {
-  ScoringParams p = p_in;
-  p.trace = next_trace_slot();
-  SFB_CHECK_ARG((p.E % 4) == 0, "scoring: E % 4");
-  if (p.ldg == 0) p.ldg = p.E;
-  SFB_CHECK_ARG((p.ldg % 4) == 0, "scoring: ldg % 4");
-  const size_t staged = ((size_t)p.A + 1) * p.E * sizeof(float) + 16;
-  const int stage_rows = staged <= 160 * 1024 ? 1 : 0;
-  const size_t smem = stage_rows ? staged : (size_t)p.E * sizeof(float) + 16;
-  SFB_CHECK_ARG(smem <= 200 * 1024, "scoring: E too large");
-  static size_t configured = 0;
-  if (smem > configured) {
-    SFB_CHECK_CUDA(cudaFuncSetAttribute(action_scoring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  SFB_CHECK_CUDA(launch_ex(action_scoring_kernel, dim3(p.B, 1, 1), dim3(256, 1, 1), smem, stream, dim3(1, 1, 1), p, stage_rows));
-  count_launch();
-  return 0;
-}
-
-// ---------------------------------------------------------------- follower rollout tail (one warp per row)
-__global__ void __launch_bounds__(128) follower_tail_kernel(const TailParams p) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 4 + warp;
-  trace_mark(p.trace, 0);
-  pdl_launch_dependents();
-  pdl_wait();
-  trace_mark(p.trace, 1);
-  if (b >= p.B) return;
+// ---------------------------------------------------------------- rollout tail of one batch row, executed by one warp
+// (follower.py:476-505): mask, log-softmax, teacher / argmax / inverse-CDF sample, next-u gather, score and CE terms
+__device__ __forceinline__ void tail_row(const TailParams& p, const int b, const int lane) {
   float* lg = p.logit + (size_t)b * p.A;
   const float* valid = p.is_valid + (size_t)b * p.A;
   // mask, max / first argmax (torch.max returns the first maximal index)
@@ -150,6 +68,95 @@ __global__ void __launch_bounds__(128) follower_tail_kernel(const TailParams p) 
     float4* dst = reinterpret_cast<float4*>(p.u_next + (size_t)b * p.E);
     for (int j = lane; j < (p.E >> 2); j += 32) dst[j] = __ldg(src + j);   // all_u_t is a step input
   }
+}
+
+// ---------------------------------------------------------------- action scoring
+// w_out . ((W_h ht + b_h) (.) (W_a u + b_a)) + b_out  ==  u . g + c   with  tp = w_out (.) (W_h ht + b_h),
+// g = W_a^T tp  and  c = sum_d b_a[d] tp[d] + b_out   (SURVEY.md §7 hard part 1).
+// The A candidate rows of a batch element are step inputs: with PDL they are pulled into shared memory (bulk
+// async copies) while the kernels producing g / t' are still running.
+__global__ void __launch_bounds__(256) action_scoring_kernel(const ScoringParams p, const int stage_rows) {
+  extern __shared__ __align__(128) unsigned char sraw[];
+  float* gs = reinterpret_cast<float*>(sraw);                       // [E]
+  float* us = gs + p.E;                                             // [A][E] when stage_rows
+  uint64_t* bar = reinterpret_cast<uint64_t*>(us + (stage_rows ? (size_t)p.A * p.E : 0));
+  __shared__ float red[8];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nvec = p.E >> 2;
+  trace_mark(p.trace, 0);
+  pdl_launch_dependents();
+  if (stage_rows && tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(bar, (uint32_t)((size_t)p.A * p.E * 4));
+    const uint64_t pol = policy_evict_first();
+    for (int a = 0; a < p.A; ++a)
+      bulk_g2s_hint(us + (size_t)a * p.E, p.all_u_t + ((size_t)b * p.A + a) * p.E, (uint32_t)p.E * 4u, bar, pol);
+  }
+  pdl_wait();
+  trace_mark(p.trace, 1);
+  const float4* g4 = reinterpret_cast<const float4*>(p.g + (size_t)b * p.ldg);
+  for (int j = tid; j < nvec; j += 256) reinterpret_cast<float4*>(gs)[j] = g4[j];
+  float c = 0.f;
+  if (p.tp)
+    for (int d = tid; d < p.D; d += 256) c = fmaf(__ldg(p.b_a + d), p.tp[(size_t)b * p.D + d], c);
+  c = warp_sum(c);
+  if (lane == 0) red[warp] = c;
+  __syncthreads();
+  float cst = p.tp ? __ldg(p.b_out) : p.g[(size_t)b * p.ldg + p.E];   // folded weights carry the constant as g[E]
+#pragma unroll
+  for (int w = 0; w < 8; ++w) cst += red[w];
+  if (stage_rows) mbar_wait(bar, 0);
+  for (int a = warp; a < p.A; a += 8) {
+    const float4* u4 = stage_rows ? reinterpret_cast<const float4*>(us + (size_t)a * p.E)
+                                  : reinterpret_cast<const float4*>(p.all_u_t + ((size_t)b * p.A + a) * p.E);
+    float acc = 0.f;
+    for (int j = lane; j < nvec; j += 32) {
+      const float4 u = u4[j];
+      const float4 g = reinterpret_cast<const float4*>(gs)[j];
+      acc = fmaf(u.x, g.x, acc);
+      acc = fmaf(u.y, g.y, acc);
+      acc = fmaf(u.z, g.z, acc);
+      acc = fmaf(u.w, g.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) p.logit[(size_t)b * p.A + a] = acc + cst;
+  }
+  __syncthreads();
+  if (p.has_tail && warp == 0) tail_row(p.tail, b, lane);   // logits of this row were written by this CTA
+  trace_mark(p.trace, 2);
+}
+
+int32_t launch_action_scoring(const ScoringParams& p_in, cudaStream_t stream) {
+  ScoringParams p = p_in;
+  p.trace = next_trace_slot();
+  SFB_CHECK_ARG((p.E % 4) == 0, "scoring: E % 4");
+  if (p.ldg == 0) p.ldg = p.E;
+  SFB_CHECK_ARG((p.ldg % 4) == 0, "scoring: ldg % 4");
+  const size_t staged = ((size_t)p.A + 1) * p.E * sizeof(float) + 16;
+  const int stage_rows = staged <= 160 * 1024 ? 1 : 0;
+  const size_t smem = stage_rows ? staged : (size_t)p.E * sizeof(float) + 16;
+  SFB_CHECK_ARG(smem <= 200 * 1024, "scoring: E too large");
+  static size_t configured = 0;
+  if (smem > configured) {
+    SFB_CHECK_CUDA(cudaFuncSetAttribute(action_scoring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  SFB_CHECK_CUDA(launch_ex(action_scoring_kernel, dim3(p.B, 1, 1), dim3(256, 1, 1), smem, stream, dim3(1, 1, 1), p, stage_rows));
+  count_launch();
+  return 0;
+}
+
+// ---------------------------------------------------------------- follower rollout tail (one warp per row)
+__global__ void __launch_bounds__(128) follower_tail_kernel(const TailParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + warp;
+  trace_mark(p.trace, 0);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace_mark(p.trace, 1);
+  if (b >= p.B) return;
+  tail_row(p, b, lane);
   __syncwarp();
   trace_mark(p.trace, 2);
 }

@@ -163,9 +163,13 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
                   drop_h: Optional[Tensor] = None, store: Optional[FeatureStore] = None,
                   vp_idx: Optional[Tensor] = None, view_idx: Optional[Tensor] = None,
                   workspace: Optional[Tensor] = None, out: Optional[tuple] = None,
-                  packed: Optional[Tensor] = None):
+                  packed: Optional[Tensor] = None, q_in: Optional[Tensor] = None, q_next: Optional[Tensor] = None,
+                  tail: Optional[dict] = None):
     """AttnDecoderLSTM.forward (model.py:377-397) -> (h1, c1, alpha, logit, alpha_v).
-    `packed`: blob from PackedFollower.get(w) -> the packed-weight tcgen05 path (sfb_follower_step_packed_fwd)."""
+    `packed`: blob from PackedFollower.get(w) -> the packed-weight tcgen05 path (sfb_follower_step_packed_fwd).
+    Packed path only: `q_in` / `q_next` [B,F] carry the visual query across steps (see include/sf_b200.h);
+    `tail` = dict(is_valid, feedback, target=None, sample_u=None, out=(a_t, u_next, score, ce)) fuses the rollout
+    tail (follower.py:476-505) behind the logits; the outputs are left in tail["out"]."""
     lib = _lib.load()
     B, A, E = all_u_t.shape
     L = ctx.shape[1]
@@ -184,13 +188,28 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
         alpha_v = torch.empty(B, V, device=dev)
     else:
         h1, c1, alpha, logit, alpha_v = out
+    if packed is None and (q_in is not None or q_next is not None or tail is not None):
+        raise _lib.SfbError("q_in / q_next / tail need the packed path (packed=PackedFollower.get(w))")
     if packed is not None:
         wl = _vis_lstm_weights(w)
+        tl = None
+        if tail is not None:
+            tgt = _i32(tail.get("target"))
+            if tail.get("out") is None:
+                tail["out"] = (torch.empty(B, dtype=torch.int32, device=dev), torch.empty(B, E, device=dev),
+                               torch.empty(B, device=dev), torch.empty(B, device=dev) if tgt is not None else None)
+            a_t, u_next, score, ce = tail["out"]
+            tl = _lib.StepTail(_p(tail["is_valid"], name="is_valid"), _p(tgt, torch.int32, "target"),
+                               {"teacher": 0, "argmax": 1, "sample": 2}[tail["feedback"]],
+                               _p(tail.get("sample_u"), name="sample_u"), _p(a_t, torch.int32), _p(u_next), _p(score),
+                               _p(ce))
+            keep.append(tgt)
         check(lib.sfb_follower_step_packed_fwd(
             C.byref(d), C.byref(wl), packed.data_ptr(), packed.numel(), B, L, A,
             _p(u_prev, name="u_t_prev"), _p(all_u_t, name="all_u_t"), C.byref(vs), _p(h0, name="h_0"),
             _p(c0, name="c_0"), _p(ctx, name="ctx"), _p(mask, torch.uint8, "ctx_mask"), _p(drop_x, name="drop_x"),
-            _p(drop_h, name="drop_h"), _p(h1), _p(c1), _p(alpha), _p(logit), _p(alpha_v), workspace.data_ptr(),
+            _p(drop_h, name="drop_h"), _p(h1), _p(c1), _p(alpha), _p(logit), _p(alpha_v), _p(q_in, name="q_in"),
+            _p(q_next, name="q_next"), C.byref(tl) if tl is not None else None, workspace.data_ptr(),
             workspace.numel(), _stream()))
         return h1, c1, alpha, logit, alpha_v
     wl, wt, ws = _vis_lstm_weights(w), _softdot_weights(w, "text_attention_layer."), _scoring_weights(w)

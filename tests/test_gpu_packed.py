@@ -145,3 +145,82 @@ def test_packed_rollout_10_steps_drift(weights):
     close(h, ref[-1]["h"], what="h"); close(c, ref[-1]["c"], what="c")
     close(total, ref_score, 5e-4, "sequence score")
     print("packed path: worst |dlogit| over 10 steps: %.2e" % worst)
+
+
+def test_packed_query_carry_and_fused_tail(weights):
+    """Software pipelining across the recurrence: q_next of step t fed as q_in of step t+1, rollout tail fused into
+    the last kernel — same results as the plain packed step + separate tail, oracle parity, bit-exact actions."""
+    w, wc, _, blob = weights
+    B, L, A, S = 100, 80, 8, 4
+    steps = [cu(synth.follower_step_inputs(B, L, A, seed=900 + s)) for s in range(S)]
+    x0 = steps[0]
+    ctx, mask = x0["ctx"], x0["ctx_mask"]
+    # reference chain: plain packed step + separate tail
+    h, c, u = x0["h_0"].clone(), x0["c_0"].clone(), x0["u_t_prev"].clone()
+    ref = []
+    for s in range(S):
+        st = steps[s]
+        h, c, alpha, logit, av = ops.follower_step(wc, u, st["all_u_t"], st["visual_context"], h, c, ctx, mask, packed=blob)
+        a_t, u, score, _ = ops.follower_tail(logit, st["is_valid"], st["all_u_t"], "argmax")
+        ref.append((h.clone(), c.clone(), logit.clone(), a_t.clone(), score.clone(), u.clone()))
+    # pipelined chain
+    h, c, u = x0["h_0"].clone(), x0["c_0"].clone(), x0["u_t_prev"].clone()
+    q = [torch.empty(B, synth.FEAT, device="cuda") for _ in range(2)]
+    for s in range(S):
+        st = steps[s]
+        tail = {"is_valid": st["is_valid"], "feedback": "argmax"}
+        h, c, alpha, logit, av = ops.follower_step(wc, u, st["all_u_t"], st["visual_context"], h, c, ctx, mask, packed=blob,
+                                                   q_in=q[s % 2] if s > 0 else None, q_next=q[(s + 1) % 2], tail=tail)
+        a_t, u, score, _ = tail["out"]
+        rh, rc, rl, ra, rs, ru = ref[s]
+        close(h, rh.cpu(), 2e-5, "carry h step %d" % s)
+        close(c, rc.cpu(), 2e-5, "carry c step %d" % s)
+        close(logit, rl.cpu(), 2e-5, "carry logit step %d" % s)
+        assert torch.equal(a_t, ra), "fused tail a_t step %d" % s
+        assert torch.equal(u, ru), "fused tail u_next step %d" % s
+        close(score, rs.cpu(), 2e-5, "fused tail score step %d" % s)
+
+
+def test_packed_query_carry_train_mode(weights):
+    """With dropout on h_1 the next query must come from the UN-dropped h_1 (model.py:389 sees h_0 = h_1)."""
+    w, wc, _, blob = weights
+    B, L, A = 16, 20, 5
+    x = synth.follower_step_inputs(B, L, A, seed=910)
+    xc = cu(x)
+    g = torch.Generator().manual_seed(5)
+    drop_x = (torch.rand(B, 2 * synth.FEAT, generator=g) > 0.5).float() * 2.0
+    drop_h = (torch.rand(B, synth.HID, generator=g) > 0.5).float() * 2.0
+    qn = torch.empty(B, synth.FEAT, device="cuda")
+    res = ops.follower_step(wc, xc["u_t_prev"], xc["all_u_t"], xc["visual_context"], xc["h_0"], xc["c_0"], xc["ctx"],
+                            xc["ctx_mask"], drop_x.cuda(), drop_h.cuda(), packed=blob, q_next=qn)
+    ref = O.attn_decoder_step(x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
+                              x["ctx_mask"], w, drop_x, drop_h)
+    for k, v, r in zip(NAMES, res, ref):
+        close(v, r, what="train:" + k)
+    # q_next == W_v^T (W_h h_1 + b_h)
+    t = ref[0] @ w["visual_attention_layer.linear_in_h.weight"].t() + w["visual_attention_layer.linear_in_h.bias"]
+    close(qn, t @ w["visual_attention_layer.linear_in_v.weight"], 1e-4, "q_next (train)")
+
+
+@pytest.mark.parametrize("feedback", ["teacher", "argmax", "sample"])
+def test_fused_tail_matches_oracle(weights, feedback):
+    w, wc, _, blob = weights
+    B, L, A = 100, 40, 8
+    x = synth.follower_step_inputs(B, L, A, seed=920)
+    xc = cu(x)
+    g = torch.Generator().manual_seed(11)
+    target = torch.randint(-1, 2, (B,), generator=g)
+    su = torch.rand(B, generator=g)
+    tail = {"is_valid": xc["is_valid"], "feedback": feedback, "target": target.cuda(), "sample_u": su.cuda()}
+    res = ops.follower_step(wc, xc["u_t_prev"], xc["all_u_t"], xc["visual_context"], xc["h_0"], xc["c_0"], xc["ctx"],
+                            xc["ctx_mask"], packed=blob, tail=tail)
+    a_t, u_next, score, ce = tail["out"]
+    ref = O.attn_decoder_step(x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
+                              x["ctx_mask"], w)
+    # the tail is checked on the GPU's own logits (bit-exact index contract), the logits against the oracle
+    lg_gpu = res[3].cpu().clone()
+    close(res[3].cpu().masked_fill(x["is_valid"] == 0, 0.0), ref[3].masked_fill(x["is_valid"] == 0, 0.0), what="logit")
+    lg_ref, loss, a_ref, u_ref, sc_ref = O.follower_step_tail(lg_gpu.clone(), x["is_valid"], target, feedback, x["all_u_t"], su)
+    assert torch.equal(a_t.cpu().long(), a_ref)
+    assert torch.equal(u_next.cpu(), u_ref)
+    close(score, sc_ref, 1e-5, "action score")
