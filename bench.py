@@ -176,20 +176,27 @@ def run_gpu(args, rank, local_rank, world):
     lens = torch.sort(torch.randint(10, L + 1, (B,), generator=torch.Generator().manual_seed(5)), descending=True)[0]
     lens[0] = L
     mask = (torch.arange(L).unsqueeze(0) >= lens.unsqueeze(1)).to(dev)
-    U, valid = [], []
+    # action candidates (env.py:60-75): candidate a of row b is view cview[b,a] of the current viewpoint's slab plus
+    # the sin/cos of its relative heading/elevation; row 0 = stop = zeros.  The packed path gathers them on the device
+    # from (cview, ctrig); the dense [B,A,E] tensor U is what the reference ships per step (in-place path / e2e bytes).
+    U, valid, cview, ctrig = [], [], [], []
     for j in range(POOL):
         n_act = torch.randint(2, A + 1, (B,), generator=torch.Generator().manual_seed(70 + j))
         n_act[0] = A
         v = (torch.arange(A).unsqueeze(0) < n_act.unsqueeze(1)).float().to(dev)
-        rows = table[vp[j].long().unsqueeze(1), torch.randint(0, 36, (B, A), device=dev, generator=g)]   # [B,A,2048]
-        ang = torch.rand(B, A, 4, device=dev, generator=g) * 6.28 - 3.14
-        locp = torch.cat([torch.sin(ang[..., 0:1]).expand(-1, -1, 32), torch.cos(ang[..., 0:1]).expand(-1, -1, 32),
-                          torch.sin(ang[..., 1:2]).expand(-1, -1, 32), torch.cos(ang[..., 1:2]).expand(-1, -1, 32)], 2)
-        u = torch.cat([rows, locp], 2) * v.unsqueeze(2)
-        u[:, 0] = 0
-        U.append(u.contiguous())
-        valid.append(v.contiguous())
-    del rows, u
+        cv = torch.randint(0, 36, (B, A), device=dev, generator=g).int()
+        cv = torch.where(v > 0, cv, torch.full_like(cv, -1))
+        cv[:, 0] = -1
+        ang = torch.rand(B, A, 2, device=dev, generator=g) * 6.28 - 3.14
+        trig = torch.stack([torch.sin(ang[..., 0]), torch.cos(ang[..., 0]), torch.sin(ang[..., 1]), torch.cos(ang[..., 1])], 2).contiguous()
+        cview.append(cv.contiguous()); ctrig.append(trig); valid.append(v.contiguous())
+        if os.environ.get("SFB_INPLACE"):
+            rows = table[vp[j].long().unsqueeze(1), cv.clamp(min=0).long()]   # [B,A,2048]
+            u = torch.cat([rows, trig.repeat_interleave(32, dim=2)], 2) * (cv >= 0).unsqueeze(2)
+            U.append(u.contiguous())
+            del rows, u
+        else:
+            U.append(None)
 
     d = ops.follower_dims(w)
     # weights re-laid out once per weight version (sfb_follower_pack_weights); SFB_INPLACE=1 benches the in-place path
@@ -215,9 +222,10 @@ def run_gpu(args, rank, local_rank, world):
             launches_per_step[0] = n + ops.last_launch_count()
             return
         # packed weights; q_next of this step is the q_in of the next one; rollout tail fused into the last kernel
-        ops.follower_step(w, ubuf[s], U[j], None, hbuf[s], cbuf[s], ctx[j], mask, store=store, vp_idx=vp[j],
+        ops.follower_step(w, ubuf[s], None, None, hbuf[s], cbuf[s], ctx[j], mask, store=store, vp_idx=vp[j],
                           view_idx=view[j], workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v),
                           packed=blob, q_in=None if first else qbuf[s], q_next=qbuf[s ^ 1],
+                          cand_view=cview[j], cand_trig=ctrig[j],
                           tail={"is_valid": valid[j], "feedback": "argmax", "out": (a_t, ubuf[s ^ 1], score, None)})
         launches_per_step[0] = ops.last_launch_count()
 
@@ -276,11 +284,33 @@ def run_gpu(args, rank, local_rank, world):
     # ---- e2e: same step through the public ops API with HOST buffers (pinned), H2D + D2H inside the timed region.
     # Host inputs per step (what the agent holds on the host after env.observe): viewpoint / view indices, the
     # action-candidate embeddings + validity (follower.py:300-320); result read back: a_t + logits (follower.py:510).
-    e2e_steps = min(args.steps, 1000)
-    h_vp = [v.cpu().pin_memory() for v in vp]; h_view = [v.cpu().pin_memory() for v in view]
-    h_U = [u.cpu().pin_memory() for u in U]; h_valid = [v.cpu().pin_memory() for v in valid]
-    d_vp = torch.empty_like(vp[0]); d_view = torch.empty_like(view[0]); d_U = torch.empty_like(U[0]); d_valid = torch.empty_like(valid[0])
-    h_a = torch.empty(B, dtype=torch.int32).pin_memory(); h_logit = torch.empty(B, A).pin_memory()
+    e2e_steps = min(args.steps, 2000)
+    if blob is None:
+        # in-place path: the reference's per-step host inputs (follower.py:291-320 minus the slab): indices, the dense
+        # candidate embeddings and validity
+        h_in = [[t.cpu().pin_memory() for t in (vp[j], view[j], U[j], valid[j])] for j in range(POOL)]
+        d_in = [torch.empty_like(t) for t in (vp[0], view[0], U[0], valid[0])]
+        d_vp, d_view, d_U, d_valid = d_in
+        d_out = [a_t, logit]
+        h_out = [torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty(B, A).pin_memory()]
+    else:
+        # packed path: everything the agent holds on the host after env.observe fits ONE pinned staging buffer:
+        # viewpoint / view indices, candidate view indices + 4 trig values, validity (20 KB); one H2D, one D2H
+        n_i, n_c = B, B * A
+        host_i = [torch.cat([vp[j].cpu().view(-1), view[j].cpu().view(-1), cview[j].cpu().view(-1)]).int() for j in range(POOL)]
+        host_f = [torch.cat([ctrig[j].cpu().view(-1), valid[j].cpu().view(-1)]).float() for j in range(POOL)]
+        h_in = [[torch.cat([hi.view(torch.uint8), hf.view(torch.uint8)]).pin_memory()] for hi, hf in zip(host_i, host_f)]
+        stage = torch.empty_like(h_in[0][0], device=dev)
+        d_in = [stage]
+        ib = (2 * n_i + n_c) * 4
+        di = stage[:ib].view(torch.int32)
+        df = stage[ib:].view(torch.float32)
+        d_vp, d_view, d_cview = di[:n_i], di[n_i:2 * n_i], di[2 * n_i:].view(B, A)
+        d_ctrig, d_valid = df[:n_c * 4].view(B, A, 4), df[n_c * 4:].view(B, A)
+        obuf = torch.empty(B + B * A, dtype=torch.int32, device=dev)        # [a_t | logit] -> one D2H
+        a_t2, logit2 = obuf[:B], obuf[B:].view(torch.float32).view(B, A)
+        d_out = [obuf]
+        h_out = [torch.empty(B + B * A, dtype=torch.int32).pin_memory()]
     graphs2 = []
     for s in range(2):
         gph = torch.cuda.CUDAGraph()
@@ -290,18 +320,19 @@ def run_gpu(args, rank, local_rank, world):
                                   view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v))
                 ops.follower_tail(logit, d_valid, d_U, "argmax", out=(a_t, ubuf[s ^ 1], score, None))
             else:
-                ops.follower_step(w, ubuf[s], d_U, None, hbuf[s], cbuf[s], ctx[0], mask, store=store, vp_idx=d_vp,
-                                  view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v),
-                                  packed=blob, q_in=qbuf[s], q_next=qbuf[s ^ 1],
-                                  tail={"is_valid": d_valid, "feedback": "argmax", "out": (a_t, ubuf[s ^ 1], score, None)})
+                ops.follower_step(w, ubuf[s], None, None, hbuf[s], cbuf[s], ctx[0], mask, store=store, vp_idx=d_vp,
+                                  view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit2, alpha_v),
+                                  packed=blob, q_in=qbuf[s], q_next=qbuf[s ^ 1], cand_view=d_cview, cand_trig=d_ctrig,
+                                  tail={"is_valid": d_valid, "feedback": "argmax", "out": (a_t2, ubuf[s ^ 1], score, None)})
         graphs2.append(gph)
 
     def e2e_step(i):
         j = i % POOL
-        d_vp.copy_(h_vp[j], non_blocking=True); d_view.copy_(h_view[j], non_blocking=True)
-        d_U.copy_(h_U[j], non_blocking=True); d_valid.copy_(h_valid[j], non_blocking=True)
+        for dst, src in zip(d_in, h_in[j]):
+            dst.copy_(src, non_blocking=True)
         graphs2[i % 2].replay()
-        h_a.copy_(a_t, non_blocking=True); h_logit.copy_(logit, non_blocking=True)
+        for dst, src in zip(h_out, d_out):
+            dst.copy_(src, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the agent needs a_t on the host to step the simulator
 
     for i in range(4):
@@ -317,8 +348,8 @@ def run_gpu(args, rank, local_rank, world):
     if dist is not None:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_steps / (float(e2e_ms.item()) * 1e-3)
-    h2d = sum(t.numel() * t.element_size() for t in (h_vp[0], h_view[0], h_U[0], h_valid[0]))
-    d2h = h_a.numel() * 4 + h_logit.numel() * 4
+    h2d = sum(t.numel() * t.element_size() for t in h_in[0])
+    d2h = sum(t.numel() * t.element_size() for t in h_out)
 
     log("e2e done")
     # ---- roofline of the attention-gather kernel, timed alone with CUDA events on its launch stream;

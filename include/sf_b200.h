@@ -169,7 +169,24 @@ int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
  *   q_next [B,F]: receives the query for the NEXT step (computed from h1 in the same launch as the text-attention
  *                 projection; in train mode, where that launch sees the dropped h1, by one extra launch);
  *   tail        : arguments of sfb_follower_step_tail — the rollout tail (follower.py:476-505) runs fused behind the
- *                 logits in the last kernel; `logit` is then masked in place exactly as by the separate call. */
+ *                 logits in the last kernel; `logit` is then masked in place exactly as by the separate call;
+ *   act         : gather source of the action candidates (then `all_u_t` may be NULL). */
+/* Where a step's action-candidate embeddings come from (replaces Seq2SeqAgent._action_variable, follower.py:300-320
+ * + _build_action_embedding, env.py:60-75).  dense: all_u_t [B,A,E] on the device.  gather: all_u_t = NULL and
+ * candidate a of batch row b is  [ feat_table[vp_idx[b], cand_view[b,a], 0:img_dim] , sin(rh) x n, cos(rh) x n,
+ * sin(re) x n, cos(re) x n ]  with n = (E - img_dim)/4 and cand_trig[b,a] = {sin rh, cos rh, sin re, cos re}
+ * (computed by the host exactly as env.py:68-74 does); cand_view < 0 (the stop action, padding) = all zeros.
+ * The candidate rows are views of the slab the attention gather reads, so nothing but indices and 4 floats per
+ * candidate crosses PCIe. */
+typedef struct sfb_action_source {
+  const float*   all_u_t;     /* [B,A,E] or NULL */
+  const float*   feat_table;  /* [n_viewpoints, V, img_dim] */
+  const int32_t* vp_idx;      /* [B] */
+  const int32_t* cand_view;   /* [B,A] view index 0..V-1, or -1 */
+  const float*   cand_trig;   /* [B,A,4] */
+  int32_t        img_dim;
+} sfb_action_source;
+
 typedef struct sfb_step_tail {
   const float*   is_valid;      /* [B,A] */
   const int32_t* target;        /* [B] or NULL */
@@ -192,6 +209,7 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
                                      const float* drop_x, const float* drop_h,
                                      float* h1, float* c1, float* alpha, float* logit, float* alpha_v,
                                      const float* q_in, float* q_next, const sfb_step_tail* tail,
+                                     const sfb_action_source* act,
                                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Per-step tail of Seq2SeqAgent._rollout_with_loss — follower.py:476-505.

@@ -47,6 +47,11 @@ class StepTail(C.Structure):
                 ("a_t", c_int_p), ("u_next", c_float_p), ("action_score", c_float_p), ("ce", c_float_p)]
 
 
+class ActionSource(C.Structure):
+    _fields_ = [("all_u_t", c_float_p), ("feat_table", c_float_p), ("vp_idx", c_int_p), ("cand_view", c_int_p),
+                ("cand_trig", c_float_p), ("img_dim", C.c_int32)]
+
+
 class SpeakerDecoderWeights(C.Structure):
     _fields_ = [("embedding", c_float_p), ("lstm_w_ih", c_float_p), ("lstm_w_hh", c_float_p),
                 ("lstm_b_ih", c_float_p), ("lstm_b_hh", c_float_p), ("attn", SoftDotWeights),
@@ -92,7 +97,7 @@ SIGNATURES = {
                                                  c_float_p, c_float_p, C.POINTER(VisualSource), c_float_p, c_float_p,
                                                  c_float_p, c_u8_p, c_float_p, c_float_p,
                                                  c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
-                                                 c_float_p, c_float_p, C.POINTER(StepTail),
+                                                 c_float_p, c_float_p, C.POINTER(StepTail), C.POINTER(ActionSource),
                                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_follower_step_tail": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, c_float_p, c_float_p, c_int_p, C.c_int32,
                                            c_float_p, c_float_p, c_int_p, c_float_p, c_float_p, c_float_p,

@@ -650,13 +650,22 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
                                      const float* c0, const float* ctx, const uint8_t* ctx_mask, const float* drop_x,
                                      const float* drop_h, float* h1, float* c1, float* alpha, float* logit,
                                      float* alpha_v, const float* q_in, float* q_next, const sfb_step_tail* tail,
-                                     void* workspace, size_t workspace_bytes, void* stream) {
+                                     const sfb_action_source* act, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
   reset_launch_count();
   SFB_PROPAGATE(check_dims(dims));
   SFB_PROPAGATE(check_packable(*dims));
   SFB_CHECK_ARG(wl && vis && packed, "NULL weight/source struct");
-  SFB_CHECK_ARG(u_prev && all_u_t && h0 && c0 && ctx && h1 && c1 && logit, "NULL tensor argument");
+  SFB_CHECK_ARG(u_prev && h0 && c0 && ctx && h1 && c1 && logit, "NULL tensor argument");
   SFB_CHECK_ARG(B >= 1 && L >= 1 && A >= 1, "B, L, A >= 1");
+  const bool act_gather = act && act->all_u_t == nullptr;
+  if (act_gather) {
+    SFB_CHECK_ARG(act->feat_table && act->vp_idx && act->cand_view && act->cand_trig, "gather action source needs table, indices and trig values");
+    SFB_CHECK_ARG(act->img_dim > 0 && act->img_dim < dims->E && (act->img_dim % 4) == 0, "bad action img_dim");
+  } else {
+    if (act) all_u_t = act->all_u_t;
+    SFB_CHECK_ARG(all_u_t, "all_u_t is NULL and no gather action source given");
+  }
   if (tail) {
     SFB_CHECK_ARG(tail->is_valid && tail->a_t, "tail: is_valid and a_t are required");
     SFB_CHECK_ARG(tail->feedback >= 0 && tail->feedback <= 2, "tail: feedback must be 0 (teacher), 1 (argmax) or 2 (sample)");
@@ -740,9 +749,13 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
                      0, 0, 0, nullptr, 0, nullptr));
   ScoringParams sp{};
   sp.all_u_t = all_u_t; sp.g = ws.g; sp.tp = nullptr; sp.ldg = ws.ldg; sp.logit = logit; sp.B = B; sp.A = A; sp.E = d.E; sp.D = d.D;
+  if (act_gather) {
+    sp.all_u_t = nullptr; sp.cand_table = act->feat_table; sp.vp_idx = act->vp_idx; sp.cand_view = act->cand_view;
+    sp.cand_trig = act->cand_trig; sp.img_dim = act->img_dim; sp.cand_V = d.V;
+  }
   if (tail) {   // follower.py:476-505 fused behind the logits
     sp.has_tail = 1;
-    sp.tail = TailParams{logit, tail->is_valid, tail->target, tail->feedback, tail->sample_u, all_u_t, tail->a_t,
+    sp.tail = TailParams{logit, tail->is_valid, tail->target, tail->feedback, tail->sample_u, sp.all_u_t, tail->a_t,
                          tail->u_next, tail->action_score, tail->ce, B, A, d.E, nullptr};
   }
   SFB_PROPAGATE(launch_action_scoring(sp, st));

@@ -151,6 +151,9 @@ struct ScoringParams {
   const float* b_a; const float* b_out;
   int ldg;                                // row stride of g
   int has_tail; TailParams tail;          // optional fused rollout tail (follower.py:476-505) on the fresh logits
+  // optional gather source replacing all_u_t (env.py:60-75): candidate a of row b = view cand_view[b,a] of the
+  // viewpoint's slab in the feature table + the 4 trig values of its relative heading / elevation; view < 0 = zeros
+  const float* cand_table; const int32_t* vp_idx; const int32_t* cand_view; const float* cand_trig; int img_dim, cand_V;
   float* logit;                           // [B,A]
   int B, A, E, D;
   unsigned long long* trace;

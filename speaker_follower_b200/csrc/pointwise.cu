@@ -6,7 +6,7 @@ namespace sfb {
 
 // ---------------------------------------------------------------- rollout tail of one batch row, executed by one warp
 // (follower.py:476-505): mask, log-softmax, teacher / argmax / inverse-CDF sample, next-u gather, score and CE terms
-__device__ __forceinline__ void tail_row(const TailParams& p, const int b, const int lane) {
+__device__ __forceinline__ void tail_row(const TailParams& p, const int b, const int lane, const float* rows) {
   float* lg = p.logit + (size_t)b * p.A;
   const float* valid = p.is_valid + (size_t)b * p.A;
   // mask, max / first argmax (torch.max returns the first maximal index)
@@ -64,9 +64,9 @@ __device__ __forceinline__ void tail_row(const TailParams& p, const int b, const
     if (p.ce) p.ce[b] = tgt < 0 ? 0.f : -(lg[tgt] - lse);
   }
   if (p.u_next) {
-    const float4* src = reinterpret_cast<const float4*>(p.all_u_t + ((size_t)b * p.A + a_t) * p.E);
+    const float4* src = reinterpret_cast<const float4*>(rows + (size_t)a_t * p.E);   // global all_u_t or staged smem rows
     float4* dst = reinterpret_cast<float4*>(p.u_next + (size_t)b * p.E);
-    for (int j = lane; j < (p.E >> 2); j += 32) dst[j] = __ldg(src + j);   // all_u_t is a step input
+    for (int j = lane; j < (p.E >> 2); j += 32) dst[j] = src[j];
   }
 }
 
@@ -85,13 +85,38 @@ __global__ void __launch_bounds__(256) action_scoring_kernel(const ScoringParams
   const int nvec = p.E >> 2;
   trace_mark(p.trace, 0);
   pdl_launch_dependents();
+  const bool gather = p.cand_table != nullptr;   // candidates = rows of the device-resident feature table + 4 angles
   if (stage_rows && tid == 0) {
     mbar_init(bar, 1);
     mbar_fence_init();
-    mbar_expect_tx(bar, (uint32_t)((size_t)p.A * p.E * 4));
     const uint64_t pol = policy_evict_first();
+    if (!gather) {
+      mbar_expect_tx(bar, (uint32_t)((size_t)p.A * p.E * 4));
+      for (int a = 0; a < p.A; ++a)
+        bulk_g2s_hint(us + (size_t)a * p.E, p.all_u_t + ((size_t)b * p.A + a) * p.E, (uint32_t)p.E * 4u, bar, pol);
+    } else {
+      int n = 0;
+      for (int a = 0; a < p.A; ++a) n += p.cand_view[(size_t)b * p.A + a] >= 0;
+      mbar_expect_tx(bar, (uint32_t)((size_t)n * p.img_dim * 4));
+      const float* slab = p.cand_table + (size_t)p.vp_idx[b] * p.cand_V * p.img_dim;
+      for (int a = 0; a < p.A; ++a) {
+        const int v = p.cand_view[(size_t)b * p.A + a];
+        if (v >= 0) bulk_g2s_hint(us + (size_t)a * p.E, slab + (size_t)v * p.img_dim, (uint32_t)p.img_dim * 4u, bar, pol);
+      }
+    }
+  }
+  if (gather) {
+    // env.py:60-75: row a = [feature[absViewIndex_a, :img_dim], sin(rh) x n, cos(rh) x n, sin(re) x n, cos(re) x n],
+    // n = (E - img_dim) / 4; rows without a view (the stop action, padding) are zero
+    const int loc = p.E - p.img_dim, grp = loc >> 2;
+    for (int i = tid; i < p.A * loc; i += 256) {
+      const int a = i / loc, j = i - a * loc;
+      const bool ok = p.cand_view[(size_t)b * p.A + a] >= 0;
+      us[(size_t)a * p.E + p.img_dim + j] = ok ? p.cand_trig[((size_t)b * p.A + a) * 4 + j / grp] : 0.f;
+    }
     for (int a = 0; a < p.A; ++a)
-      bulk_g2s_hint(us + (size_t)a * p.E, p.all_u_t + ((size_t)b * p.A + a) * p.E, (uint32_t)p.E * 4u, bar, pol);
+      if (p.cand_view[(size_t)b * p.A + a] < 0)
+        for (int i = tid; i < p.img_dim; i += 256) us[(size_t)a * p.E + i] = 0.f;
   }
   pdl_wait();
   trace_mark(p.trace, 1);
@@ -123,7 +148,8 @@ __global__ void __launch_bounds__(256) action_scoring_kernel(const ScoringParams
     if (lane == 0) p.logit[(size_t)b * p.A + a] = acc + cst;
   }
   __syncthreads();
-  if (p.has_tail && warp == 0) tail_row(p.tail, b, lane);   // logits of this row were written by this CTA
+  if (p.has_tail && warp == 0)   // logits of this row were written by this CTA
+    tail_row(p.tail, b, lane, stage_rows ? us : p.all_u_t + (size_t)b * p.A * p.E);
   trace_mark(p.trace, 2);
 }
 
@@ -135,6 +161,13 @@ int32_t launch_action_scoring(const ScoringParams& p_in, cudaStream_t stream) {
   SFB_CHECK_ARG((p.ldg % 4) == 0, "scoring: ldg % 4");
   const size_t staged = ((size_t)p.A + 1) * p.E * sizeof(float) + 16;
   const int stage_rows = staged <= 160 * 1024 ? 1 : 0;
+  if (p.cand_table) {
+    SFB_CHECK_ARG(stage_rows, "scoring: too many action candidates for the gather source (A * E * 4 must fit 160 KB)");
+    SFB_CHECK_ARG(p.vp_idx && p.cand_view && p.cand_trig && p.img_dim > 0 && p.img_dim < p.E && (p.img_dim % 4) == 0 &&
+                      ((p.E - p.img_dim) % 4) == 0 && p.cand_V > 0, "scoring: bad gather source");
+  } else {
+    SFB_CHECK_ARG(p.all_u_t, "scoring: all_u_t is NULL");
+  }
   const size_t smem = stage_rows ? staged : (size_t)p.E * sizeof(float) + 16;
   SFB_CHECK_ARG(smem <= 200 * 1024, "scoring: E too large");
   static size_t configured = 0;
@@ -156,7 +189,7 @@ __global__ void __launch_bounds__(128) follower_tail_kernel(const TailParams p) 
   pdl_wait();
   trace_mark(p.trace, 1);
   if (b >= p.B) return;
-  tail_row(p, b, lane);
+  tail_row(p, b, lane, p.all_u_t + (size_t)b * p.A * p.E);
   __syncwarp();
   trace_mark(p.trace, 2);
 }

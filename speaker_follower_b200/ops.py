@@ -164,17 +164,24 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
                   vp_idx: Optional[Tensor] = None, view_idx: Optional[Tensor] = None,
                   workspace: Optional[Tensor] = None, out: Optional[tuple] = None,
                   packed: Optional[Tensor] = None, q_in: Optional[Tensor] = None, q_next: Optional[Tensor] = None,
-                  tail: Optional[dict] = None):
+                  tail: Optional[dict] = None, cand_view: Optional[Tensor] = None, cand_trig: Optional[Tensor] = None):
     """AttnDecoderLSTM.forward (model.py:377-397) -> (h1, c1, alpha, logit, alpha_v).
     `packed`: blob from PackedFollower.get(w) -> the packed-weight tcgen05 path (sfb_follower_step_packed_fwd).
     Packed path only: `q_in` / `q_next` [B,F] carry the visual query across steps (see include/sf_b200.h);
     `tail` = dict(is_valid, feedback, target=None, sample_u=None, out=(a_t, u_next, score, ce)) fuses the rollout
-    tail (follower.py:476-505) behind the logits; the outputs are left in tail["out"]."""
+    tail (follower.py:476-505) behind the logits; the outputs are left in tail["out"];
+    `all_u_t=None` with `cand_view` [B,A] int32 / `cand_trig` [B,A,4] (+ store, vp_idx): action candidates gathered
+    on the device from the feature table (env.py:60-75) instead of being shipped as a dense [B,A,E] tensor."""
     lib = _lib.load()
-    B, A, E = all_u_t.shape
     L = ctx.shape[1]
     V = visual.shape[1] if visual is not None else store.feat_table.shape[1]
     d = follower_dims(w, V)
+    if all_u_t is not None:
+        B, A, E = all_u_t.shape
+    else:
+        if packed is None or cand_view is None or cand_trig is None or store is None or vp_idx is None:
+            raise _lib.SfbError("all_u_t=None needs packed=, store=, vp_idx=, cand_view= and cand_trig=")
+        (B, A), E = cand_view.shape, d.E
     dev = h0.device
     keep = []
     vs = _visual_source(visual, store, vp_idx, view_idx, keep)
@@ -204,13 +211,18 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
                                _p(tail.get("sample_u"), name="sample_u"), _p(a_t, torch.int32), _p(u_next), _p(score),
                                _p(ce))
             keep.append(tgt)
+        act = None
+        if all_u_t is None:
+            act = _lib.ActionSource(None, _p(store.feat_table), _p(_i32(vp_idx), torch.int32, "vp_idx"),
+                                    _p(cand_view, torch.int32, "cand_view"), _p(cand_trig, name="cand_trig"),
+                                    store.feat_table.shape[2])
         check(lib.sfb_follower_step_packed_fwd(
             C.byref(d), C.byref(wl), packed.data_ptr(), packed.numel(), B, L, A,
             _p(u_prev, name="u_t_prev"), _p(all_u_t, name="all_u_t"), C.byref(vs), _p(h0, name="h_0"),
             _p(c0, name="c_0"), _p(ctx, name="ctx"), _p(mask, torch.uint8, "ctx_mask"), _p(drop_x, name="drop_x"),
             _p(drop_h, name="drop_h"), _p(h1), _p(c1), _p(alpha), _p(logit), _p(alpha_v), _p(q_in, name="q_in"),
-            _p(q_next, name="q_next"), C.byref(tl) if tl is not None else None, workspace.data_ptr(),
-            workspace.numel(), _stream()))
+            _p(q_next, name="q_next"), C.byref(tl) if tl is not None else None,
+            C.byref(act) if act is not None else None, workspace.data_ptr(), workspace.numel(), _stream()))
         return h1, c1, alpha, logit, alpha_v
     wl, wt, ws = _vis_lstm_weights(w), _softdot_weights(w, "text_attention_layer."), _scoring_weights(w)
     check(lib.sfb_follower_step_fwd(

@@ -224,3 +224,33 @@ def test_fused_tail_matches_oracle(weights, feedback):
     assert torch.equal(a_t.cpu().long(), a_ref)
     assert torch.equal(u_next.cpu(), u_ref)
     close(score, sc_ref, 1e-5, "action score")
+
+
+def test_action_candidates_gathered_on_device(weights):
+    """Action candidates as (view index, 4 trig values) gathered from the feature table inside the last kernel
+    (env.py:60-75) == the dense [B,A,E] tensor the reference ships: same bits, fused tail included."""
+    _, wc, _, blob = weights
+    B, L, A = 100, 80, 8
+    table, loc = synth.feature_table(64, 1031), synth.loc_embedding_table()
+    x = cu(synth.follower_step_inputs(B, L, A, seed=930, table=table, loc=loc))
+    store = ops.FeatureStore(table.cuda(), loc.cuda())
+    g = torch.Generator().manual_seed(3)
+    n_act = torch.randint(1, A + 1, (B,), generator=g)
+    valid = (torch.arange(A).unsqueeze(0) < n_act.unsqueeze(1))
+    cv = torch.where(valid, torch.randint(0, 36, (B, A), generator=g), torch.full((B, A), -1)).int()
+    cv[:, 0] = -1                                                      # stop action: zero embedding (env.py:64-66)
+    ang = torch.rand(B, A, 2, generator=g) * 6.28 - 3.14
+    trig = torch.stack([torch.sin(ang[..., 0]), torch.cos(ang[..., 0]), torch.sin(ang[..., 1]), torch.cos(ang[..., 1])], 2)
+    rows = table[x["vp_idx"].cpu().long().unsqueeze(1), cv.clamp(min=0).long()]
+    U = (torch.cat([rows, trig.repeat_interleave(32, dim=2)], 2) * (cv >= 0).unsqueeze(2)).contiguous().cuda()
+    vf = valid.float().cuda()
+    outs = []
+    for dense in (True, False):
+        tail = {"is_valid": vf, "feedback": "argmax"}
+        res = ops.follower_step(wc, x["u_t_prev"], U if dense else None, None, x["h_0"], x["c_0"], x["ctx"], x["ctx_mask"],
+                                store=store, vp_idx=x["vp_idx"], view_idx=x["view_idx"], packed=blob, tail=tail,
+                                cand_view=None if dense else cv.cuda(), cand_trig=None if dense else trig.contiguous().cuda())
+        outs.append((res[3].clone(), [t.clone() for t in tail["out"][:3]]))
+    assert torch.equal(outs[0][0], outs[1][0]), "logits differ"
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
