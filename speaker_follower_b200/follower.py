@@ -52,6 +52,26 @@ def backchain_inference_states(last):
     return states, observations, actions, scores, attentions
 
 
+def least_common_viewpoint_path(inf_state_a, inf_state_b):
+    """follower.py:52-73: the physical walk from A to B through the search tree — up from A to its first ancestor X
+    whose viewpoint also occurs among B's ancestors, then down from that ancestor of B (the OLDEST one with that
+    viewpoint) to B.  Returns the list of inference states, X counted once."""
+    down = {}                       # viewpointId -> [ancestor, ..., B]; older ancestors overwrite newer ones
+    chain, x = [], inf_state_b
+    while x is not None:
+        chain.insert(0, x)
+        down[x.world_state.viewpointId] = list(chain)
+        x = x.prev_inference_state
+    up, x = [], inf_state_a
+    while x is not None:
+        up.append(x)
+        tail = down.get(x.world_state.viewpointId)
+        if tail is not None:
+            return up + tail[1:]
+        x = x.prev_inference_state
+    raise AssertionError("no common ancestor found")
+
+
 def batch_instructions_from_encoded(encoded_instructions, max_length, reverse=False, sort=False, device=None):
     """follower.py:75-105: [reversed] tokens + <EOS>, truncated to max_length, padded with <PAD>; mask = PAD
     positions cut to the longest sequence.  Returns (seq int64 [N,max_length], mask bool [N,max(len)], lengths
@@ -174,12 +194,29 @@ class Seq2SeqAgent(BaseAgent):
             self._sample_gen.manual_seed(torch.initial_seed() & 0x7FFFFFFF)
         return torch.rand(n, device=dev, generator=self._sample_gen)
 
-    def _step(self, u_t_prev, obs, h_t, c_t, ctx, seq_mask, target, feedback):
-        """One decode step + tail on the device.  Returns (h, c, alpha, masked logit, a_t[int32], u_next, score, ce)."""
+    def _step(self, u_t_prev, obs, h_t, c_t, ctx, seq_mask, target, feedback, carry=None):
+        """One decode step + tail on the device.  Returns (h, c, alpha, masked logit, a_t[int32], u_next, score, ce).
+        ``carry``: a dict that lives as long as (h_t, c_t) are fed back unchanged (a rollout) — it holds the visual
+        query of the next step computed by this one (packed path), so the next call skips that projection."""
         f_t = self._feature_variables(obs)[0]
         all_u_t, is_valid, _ = self._action_variable(obs)
+        su = self._sample_uniform(len(obs), h_t.device) if feedback == "sample" else None
+        if getattr(self.decoder, "supports_fused_step", False):
+            tail = {"is_valid": is_valid, "feedback": feedback, "target": target, "sample_u": su}
+            q_in = q_next = None
+            if carry is not None:
+                q_in = carry.get("q")
+                q_next = carry.get("spare")
+                if q_next is None or q_next.shape[0] != len(obs):
+                    q_next = torch.empty(len(obs), self.decoder.feature_size, device=h_t.device)
+                carry["spare"] = q_in
+            h_t, c_t, alpha, logit, alpha_v = self.decoder.decode_step(u_t_prev, all_u_t, f_t, h_t, c_t, ctx, seq_mask,
+                                                                       tail=tail, q_in=q_in, q_next=q_next)
+            if carry is not None:
+                carry["q"] = q_next
+            a_t, u_next, score, ce = tail["out"]
+            return h_t, c_t, alpha, logit, a_t, u_next, score, ce
         h_t, c_t, alpha, logit, alpha_v = self.decoder(u_t_prev, all_u_t, f_t, h_t, c_t, ctx, seq_mask)
-        su = self._sample_uniform(len(obs), logit.device) if feedback == "sample" else None
         a_t, u_next, score, ce = ops.follower_tail(logit, is_valid, all_u_t, feedback, target=target, sample_u=su)
         return h_t, c_t, alpha, logit, a_t, u_next, score, ce
 
@@ -205,9 +242,10 @@ class Seq2SeqAgent(BaseAgent):
         u_t_prev = self.decoder.u_begin.expand(batch_size, -1)
         ended = np.zeros(batch_size, dtype=bool)
         sequence_scores = torch.zeros(batch_size, device=dev)
+        carry = {}   # visual query of the next step, produced by the current one (packed path)
         for t in range(self.episode_len):
             target = self._teacher_action(obs, ended)
-            h_t, c_t, alpha, logit, a_t, u_t_prev, score, ce = self._step(u_t_prev, obs, h_t, c_t, ctx, seq_mask, target, feedback)
+            h_t, c_t, alpha, logit, a_t, u_t_prev, score, ce = self._step(u_t_prev, obs, h_t, c_t, ctx, seq_mask, target, feedback, carry)
             n_keep = int((target >= 0).sum())
             self.loss = self.loss + (ce.sum() / n_keep if n_keep > 0 else ce.sum() * float("nan"))   # CE(ignore_index=-1), 278,481
             sequence_scores = sequence_scores + score
@@ -247,6 +285,7 @@ class Seq2SeqAgent(BaseAgent):
         traj = [{"instr_id": o[0]["instr_id"], "trajectory": [path_element_from_observation(o[0])], "actions": [],
                  "scores": [], "observations": [o[0]], "instr_encoding": o[0]["instr_encoding"]} for o in path_obs]
         obs = None
+        carry = {}
         for t in range(self.episode_len):
             nxt_obs, nxt_tgt = [], []
             for pi, src in enumerate(perm):
@@ -258,7 +297,7 @@ class Seq2SeqAgent(BaseAgent):
                     nxt_obs.append(obs[pi])
             obs = nxt_obs
             target = torch.tensor(nxt_tgt, dtype=torch.int32, device=dev)
-            h_t, c_t, alpha, logit, a_t, u_t_prev, score, ce = self._step(u_t_prev, obs, h_t, c_t, ctx, seq_mask, target, "teacher")
+            h_t, c_t, alpha, logit, a_t, u_t_prev, score, ce = self._step(u_t_prev, obs, h_t, c_t, ctx, seq_mask, target, "teacher", carry)
             n_keep = int((target >= 0).sum())
             loss = loss + (ce.sum() / n_keep if n_keep > 0 else 0.0)
             # reference: action_scores = -CE(logit, target, ignore_index=-1) -> 0 for finished rows (405)
@@ -349,7 +388,124 @@ class Seq2SeqAgent(BaseAgent):
 
     def state_factored_search(self, completion_size, successor_size, load_next_minibatch=True, mask_undo=False,
                               first_n_ws_key=4):
-        raise NotImplementedError("state-factored search (follower.py:720-980) is the next row of SURVEY.md §8 (a10)")
+        """follower.py:720-980.  Search over WORLD STATES instead of action sequences: per instance a table keeps the
+        best-scoring inference state reaching each world-state key (scan, viewpoint, heading, elevation); every
+        iteration the `successor_size` best not-yet-expanded entries (open or finished) are expanded; finished ones move
+        to `completed` until `completion_size` distinct end states exist.  Returns (trajs, completed_list,
+        traversed_lists) exactly like the reference; traversed_lists = physical states visited in expansion order."""
+        import heapq
+        assert self.env.beam_size >= successor_size
+        world_states = self.env.reset(sort=True, beamed=True, load_next_minibatch=load_next_minibatch)
+        initial_obs = self.env.observe(world_states, beamed=True)
+        n_inst = len(world_states)
+        seq, seq_mask, seq_lengths = self._proc_batch(initial_obs, beamed=True)
+        ctx, h_t, c_t = self.encoder(seq, seq_lengths)
+        dev = _device(self.decoder)
+
+        def ws_key(ws):
+            return tuple(ws[0:first_n_ws_key])
+
+        completed = [dict() for _ in range(n_inst)]      # key -> finished inference state that has been expanded
+        holding = [dict() for _ in range(n_inst)]        # key -> [finished inference state, expanded?]
+        cache, beams = [], []                            # key -> [open inference state, expanded?]
+        for i, (ws, o) in enumerate(zip(world_states, initial_obs)):
+            root = InferenceState(None, ws[0], o[0], None, -1, self.decoder.u_begin.view(-1), 0, np.float32(0.0),
+                                  h_t[i], c_t[i], None)
+            cache.append({ws_key(ws[0]): [root, True]})
+            beams.append([root])
+        last_expanded = [beam[0] for beam in beams]
+        traversed_lists = [[beam[0]] for beam in beams]
+
+        def extend_traversed(groups):                    # follower.py:764-779
+            for i, group in enumerate(groups):
+                cur = last_expanded[i]
+                for st in group:
+                    walk = least_common_viewpoint_path(cur, st)
+                    assert walk[0].world_state.viewpointId == cur.world_state.viewpointId
+                    assert walk[-1].world_state.viewpointId == st.world_state.viewpointId
+                    traversed_lists[i].extend(walk[1:])
+                    cur = st
+                last_expanded[i] = cur
+
+        while any(len(c) < completion_size for c in completed):
+            flat = [st for beam in beams for st in beam]
+            owner = [bi for bi, beam in enumerate(beams) for _ in beam]
+            flat_obs = [st.observation for st in flat]
+            own_t = torch.tensor(owner, dtype=torch.long, device=dev)
+            u_prev = torch.stack([st.last_action_embedding for st in flat], 0).contiguous()
+            h_in = torch.stack([st.h_t for st in flat], 0).contiguous()
+            c_in = torch.stack([st.c_t for st in flat], 0).contiguous()
+            f_t = self._feature_variables(flat_obs)[0]
+            all_u_t, is_valid, is_valid_np = self._action_variable(flat_obs)
+            h_new, c_new, alpha, logit, _ = self.decoder(u_prev, all_u_t, f_t, h_in, c_in, ctx[own_t].contiguous(),
+                                                         seq_mask[own_t].contiguous())
+            logit = logit.masked_fill(is_valid == 0, -float("inf"))                       # 808
+            lp_host = torch.log_softmax(logit, dim=1).cpu().numpy()                       # the one D2H of the iteration
+
+            # every valid action of every beam state is a successor (follower.py:832-857), best first
+            all_succ, fi = [], 0
+            for beam in beams:
+                succ = []
+                for st in beam:
+                    for ai in range(lp_host.shape[1]):
+                        if is_valid_np[fi, ai] == 0:
+                            continue
+                        succ.append(InferenceState(st, st.world_state, flat_obs[fi], None, ai, all_u_t[fi, ai],
+                                                   st.action_count + 1, np.float32(st.score + lp_host[fi, ai]),
+                                                   h_new[fi], c_new[fi], alpha[fi]))
+                    fi += 1
+                succ.sort(key=lambda x: x.score, reverse=True)
+                all_succ.append(succ)
+            new_ws = self.env.step([[x.world_state for x in ss] for ss in all_succ],
+                                   [[x.last_action for x in ss] for ss in all_succ],
+                                   [[x.observation for x in ss] for ss in all_succ], beamed=True)
+            all_succ = [[x._replace(world_state=w) for x, w in zip(ss, ws_)] for ss, ws_ in zip(all_succ, new_ws)]
+
+            new_beams = []
+            for i, succ in enumerate(all_succ):
+                if len(completed[i]) >= completion_size:                                  # 889-891
+                    new_beams.append([])
+                    continue
+                for x in succ:                                                            # keep the best per world state
+                    k = ws_key(x.world_state)
+                    table = holding[i] if (x.last_action == 0 or x.action_count == self.episode_len) else cache[i]
+                    if k not in table or table[k][0].score < x.score:
+                        table[k] = [x, False]
+                pool = [(k, e[0], False) for k, e in cache[i].items() if not e[1]] + \
+                       [(k, e[0], True) for k, e in holding[i].items() if not e[1]]
+                beam = []
+                for k, st, finished in heapq.nlargest(successor_size, pool, key=lambda t: t[1].score):
+                    if finished:
+                        holding[i][k][1] = True
+                        if k not in completed[i] or completed[i][k].score < st.score:
+                            completed[i][k] = st
+                    else:
+                        cache[i][k][1] = True
+                        beam.append(st)
+                new_beams.append([] if len(completed[i]) >= completion_size else beam)
+            beams = new_beams
+            if not any(beams):
+                break
+            new_obs = self.env.observe([[st.world_state for st in beam] for beam in beams], beamed=True)
+            beams = [[st._replace(observation=o) for st, o in zip(beam, os_)] for beam, os_ in zip(beams, new_obs)]
+            extend_traversed(beams)
+
+        completed_list = [sorted(c.values(), key=lambda x: x.score, reverse=True)[:completion_size] for c in completed]
+        final_obs = self.env.observe([[st.world_state for st in cl] for cl in completed_list], beamed=True)
+        completed_list = [[st._replace(observation=o) for st, o in zip(cl, os_)] for cl, os_ in zip(completed_list, final_obs)]
+        extend_traversed(completed_list)
+        trajs = []
+        for cl in completed_list:
+            assert cl
+            out = []
+            for st in cl:
+                states, observations, actions, scores, attentions = backchain_inference_states(st)
+                out.append({"instr_id": observations[0]["instr_id"], "instr_encoding": observations[0]["instr_encoding"],
+                            "trajectory": [path_element_from_observation(o) for o in observations],
+                            "observations": observations, "actions": actions, "score": st.score, "scores": scores,
+                            "attentions": attentions})
+            trajs.append(out)
+        return trajs, completed_list, traversed_lists
 
     # ---------------------------------------------------------------- driver methods (follower.py:982-1035)
     def set_beam_size(self, beam_size):

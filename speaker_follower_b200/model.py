@@ -143,6 +143,7 @@ class AttnDecoderLSTM(nn.Module):
         self.text_attention_layer = SoftDotAttention(hidden_size)
         self.decoder2action = EltwiseProdScoring(hidden_size, embedding_size)
         self.feature_store: Optional[ops.FeatureStore] = None   # set to gather slabs on the device (K13)
+        self._packer = ops.PackedFollower()   # bf16 hi/lo tcgen05 operand copies, refreshed when a weight changes
 
     @property
     def u_begin(self):
@@ -152,19 +153,36 @@ class AttnDecoderLSTM(nn.Module):
     def forward(self, u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask=None):
         """-> (h_1, c_1, alpha, logit, alpha_v).  ``visual_context`` is either the dense [B,36,F] tensor of the
         reference or a ``(vp_idx, view_idx)`` pair of int tensors when ``self.feature_store`` is set."""
+        return self.decode_step(u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask)
+
+    def decode_step(self, u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask=None, tail=None, q_in=None,
+                    q_next=None):
+        """forward() plus the fast-path extras of the packed C ABI (include/sf_b200.h): ``tail`` fuses the rollout
+        tail (follower.py:476-505) behind the logits, ``q_in``/``q_next`` carry the visual query across steps."""
         _no_autograd(u_t_prev, all_u_t, h_0, c_0, ctx, *self.parameters())
         B = h_0.shape[0]
         dev = h_0.device
         drop_x = self._drop.mask(self.training, (B, self.embedding_size + self.feature_size), dev)
         drop_h = self._drop.mask(self.training, (B, self.hidden_size), dev)
         u_t_prev = u_t_prev.contiguous()        # u_begin.expand(B, -1) is a stride-0 view (follower.py:462)
+        sd = _sd(self)
+        packed = self._packer.get(sd)           # None for dimensions the packed path does not cover
+        extra = {}
+        if packed is not None:
+            extra = dict(packed=packed, tail=tail, q_in=q_in, q_next=q_next)
+        elif tail is not None or q_in is not None or q_next is not None:
+            raise NotImplementedError("fused tail / carried query need the packed path (H % 128 == 0)")
         if isinstance(visual_context, (tuple, list)):
             vp, view = visual_context
-            return ops.follower_step(_sd(self), u_t_prev, all_u_t.contiguous(), None, h_0.contiguous(),
+            return ops.follower_step(sd, u_t_prev, all_u_t.contiguous(), None, h_0.contiguous(),
                                      c_0.contiguous(), ctx.contiguous(), ctx_mask, drop_x, drop_h,
-                                     store=self.feature_store, vp_idx=vp, view_idx=view)
-        return ops.follower_step(_sd(self), u_t_prev, all_u_t.contiguous(), visual_context.contiguous(),
-                                 h_0.contiguous(), c_0.contiguous(), ctx.contiguous(), ctx_mask, drop_x, drop_h)
+                                     store=self.feature_store, vp_idx=vp, view_idx=view, **extra)
+        return ops.follower_step(sd, u_t_prev, all_u_t.contiguous(), visual_context.contiguous(),
+                                 h_0.contiguous(), c_0.contiguous(), ctx.contiguous(), ctx_mask, drop_x, drop_h, **extra)
+
+    @property
+    def supports_fused_step(self) -> bool:
+        return self._packer.get(_sd(self)) is not None
 
 
 class SpeakerEncoderLSTM(nn.Module):

@@ -9,7 +9,22 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from collections import namedtuple
+
 from .follower import batch_instructions_from_encoded, vocab_bos_idx, vocab_eos_idx, vocab_pad_idx, _device
+
+InferenceState = namedtuple("InferenceState", "prev_inference_state, flat_index, last_word, word_count, score, last_alpha")   # speaker.py:16
+
+
+def backchain_inference_states(last):
+    """speaker.py:18-32: words / per-word scores / attentions along the parent chain, BOS excluded."""
+    chain, x = [], last
+    while x is not None:
+        chain.append(x)
+        x = x.prev_inference_state
+    chain.reverse()
+    return ([x.last_word for x in chain][1:], [b.score - a.score for a, b in zip(chain[:-1], chain[1:])],
+            [x.last_alpha for x in chain][1:])
 
 
 class Seq2SeqSpeaker(object):
@@ -107,7 +122,54 @@ class Seq2SeqSpeaker(object):
         return outputs
 
     def beam_search(self, beam_size, path_obs, path_actions):
-        raise NotImplementedError("word-level beam search (speaker.py:211-318) is the next row of SURVEY.md §8 (a15)")
+        """speaker.py:211-318: word-level beam search.  Ranking uses top-k of the logits, scores are the gathered
+        log-probabilities; a hypothesis completes on <EOS> or at instruction_len; an instance stops expanding once it
+        holds beam_size completions.  Returns, per input path, up to beam_size dicts sorted by score."""
+        assert len(path_obs) == len(path_actions)
+        start_obs, feats, acts, path_mask, _, _, perm = self._batch_observations_and_actions(path_obs, path_actions, None)
+        N = len(start_obs)
+        dev = _device(self.decoder)
+        ctx, h_t, c_t = self.encoder(acts, feats)
+        completed = [[] for _ in range(N)]
+        beams = [[InferenceState(None, i, vocab_bos_idx, 0, np.float32(0.0), None)] for i in range(N)]
+        for t in range(self.instruction_len):
+            flat = [st for beam in beams for st in beam]
+            owner = torch.tensor([bi for bi, beam in enumerate(beams) for _ in beam], dtype=torch.long, device=dev)
+            src = torch.tensor([st.flat_index for st in flat], dtype=torch.long, device=dev)
+            w_t = torch.tensor([st.last_word for st in flat], dtype=torch.long, device=dev)
+            h_t, c_t, alpha, logit = self.decoder(w_t.view(-1, 1), h_t[src].contiguous(), c_t[src].contiguous(),
+                                                  ctx[owner].contiguous(), path_mask[owner].contiguous())
+            log_probs = F.log_softmax(logit, dim=1)
+            k = min(beam_size, logit.shape[1])
+            _, word_indices = logit.topk(k, dim=1)
+            word_scores = log_probs.gather(1, word_indices)
+            wi_h, ws_h = word_indices.tolist(), word_scores.cpu().numpy()
+            new_beams, fi = [], 0
+            for bi, beam in enumerate(beams):
+                succ = []
+                for st in beam:
+                    for j in range(k):
+                        succ.append(InferenceState(st, fi, wi_h[fi][j], st.word_count + 1,
+                                                   np.float32(st.score + ws_h[fi, j]), alpha[fi]))
+                    fi += 1
+                succ.sort(key=lambda x: x.score, reverse=True)
+                nb = []
+                for x in succ[:beam_size]:
+                    (completed[bi] if (x.last_word == vocab_eos_idx or t == self.instruction_len - 1) else nb).append(x)
+                new_beams.append([] if len(completed[bi]) >= beam_size else nb)
+            beams = new_beams
+            if not any(beams):
+                break
+        tok = getattr(self.env, "tokenizer", None)
+        outputs = [[] for _ in range(N)]
+        for pi, si in enumerate(perm):
+            for st in sorted(completed[pi], key=lambda x: x.score, reverse=True)[:beam_size]:
+                words, scores, attentions = backchain_inference_states(st)
+                outputs[si].append({"instr_id": start_obs[pi]["instr_id"], "word_indices": words, "score": st.score,
+                                    "scores": scores,
+                                    "words": tok.decode_sentence(words, break_on_eos=True, join=False) if tok else None,
+                                    "attentions": attentions})
+        return outputs
 
     # ---------------------------------------------------------------- drivers (speaker.py:320-410)
     def test(self, use_dropout=False, feedback="argmax", allow_cheat=False, beam_size=1):

@@ -125,3 +125,67 @@ def test_speaker_teacher_scoring_matches_oracle():
     with torch.no_grad():
         res = spk.test()
     assert len(res) == 6
+
+
+def test_state_factored_search_invariants():
+    """follower.py:720-980 on the fake env: distinct end states per instance, sorted by score, per-step scores add up
+    (rational_speaker.py:87-89), teacher-forced rescoring of every candidate reproduces its score (the invariant
+    rational_follower.py relies on), and the traversal list is a connected physical walk from the start."""
+    env = FakeR2RBatch(n_viewpoints=20, n_instr=8, batch_size=8, seed=9, beam_size=3)
+    agent, we, wd = make_follower(env)
+    with torch.no_grad():
+        trajs, completed, traversed = agent.state_factored_search(completion_size=3, successor_size=1,
+                                                                  load_next_minibatch=True)
+    assert len(trajs) == 8 and len(completed) == 8 and len(traversed) == 8
+    for cands, states, walk in zip(trajs, completed, traversed):
+        assert 1 <= len(cands) <= 3
+        sc = [float(c["score"]) for c in cands]
+        assert sc == sorted(sc, reverse=True)
+        keys = [tuple(s.world_state[0:4]) for s in states]
+        assert len(set(keys)) == len(keys)                                   # one candidate per end world state
+        for c in cands:
+            assert abs(sum(float(x) for x in c["scores"]) - float(c["score"])) < 1e-4
+            assert len(c["trajectory"]) == len(c["actions"]) + 1
+            assert c["actions"][-1] == 0 or len(c["actions"]) == agent.episode_len
+        assert walk[0].prev_inference_state is None                          # starts at the root
+        for a, b in zip(walk[:-1], walk[1:]):                                # a connected walk on the navigation graph
+            va, vb = a.world_state.viewpointId, b.world_state.viewpointId
+            assert va == vb or vb in env.adj[va], (va, vb)
+        assert walk[-1].world_state.viewpointId == states[-1].world_state.viewpointId
+    flat = [c for cands in trajs for c in cands]
+    with torch.no_grad():
+        scored, _ = agent._score_obs_actions_and_instructions([c["observations"] for c in flat], [c["actions"] for c in flat],
+                                                              [c["instr_encoding"] for c in flat])
+    for s, c in zip(scored, flat):
+        assert abs(s["score"] - float(c["score"])) < 3e-4, (s["score"], c["score"])
+    # successor_size > 1 expands more states per iteration and still satisfies the same contract
+    env2 = FakeR2RBatch(n_viewpoints=20, n_instr=8, batch_size=8, seed=9, beam_size=3)
+    agent2, _, _ = make_follower(env2)
+    with torch.no_grad():
+        trajs2, _, _ = agent2.state_factored_search(completion_size=2, successor_size=3, load_next_minibatch=True)
+    assert all(1 <= len(c) <= 2 for c in trajs2)
+
+
+def test_speaker_beam_search():
+    """speaker.py:211-318: beam 1 == greedy argmax decode; wider beams are sorted, scores add up, best beam >= greedy."""
+    env = FakeR2RBatch(n_viewpoints=16, n_instr=6, batch_size=6, seed=6)
+    we, wd = synth.speaker_encoder_weights(), synth.speaker_decoder_weights()
+    enc = M.SpeakerEncoderLSTM(synth.FEAT, synth.FEAT, synth.HID, 0.5).cuda().eval()
+    dec = M.SpeakerDecoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0.5, glove=wd["embedding.weight"].numpy()).cuda().eval()
+    enc.load_state_dict(we); dec.load_state_dict(wd)
+    spk = Sp.Seq2SeqSpeaker(env, "", enc, dec, instruction_len=12, max_episode_len=6)
+    path_obs, path_actions, encoded = env.gold_obs_actions_and_instructions(6)
+    with torch.no_grad():
+        greedy, _ = spk._score_obs_actions_and_instructions(path_obs, path_actions, encoded, "argmax")
+        b1 = spk.beam_search(1, path_obs, path_actions)
+        b4 = spk.beam_search(4, path_obs, path_actions)
+    for g, one, four in zip(greedy, b1, b4):
+        assert len(one) == 1 and one[0]["instr_id"] == g["instr_id"]
+        assert one[0]["word_indices"] == g["word_indices"]
+        assert abs(float(one[0]["score"]) - g["score"]) < 1e-3
+        sc = [float(x["score"]) for x in four]
+        assert 1 <= len(four) <= 4 and sc == sorted(sc, reverse=True)
+        assert sc[0] >= float(one[0]["score"]) - 1e-4
+        for x in four:
+            assert abs(sum(float(s) for s in x["scores"]) - float(x["score"])) < 1e-3
+            assert x["word_indices"][-1] == 2 or len(x["word_indices"]) == 12      # <EOS> or instruction_len
