@@ -26,6 +26,7 @@ import torch  # noqa: E402
 
 B, L, A = 100, 80, 8
 N_VIEWPOINTS = 10567          # R2R viewpoints -> 3.1 GB table, >> L2
+ATTN_NCU_TRAFFIC = 30782976   # dram__bytes_read.sum + dram__bytes_write.sum of one attention launch (ncu --set full)
 POOL = 8                      # rotating per-step input sets (ctx 16 MB + actions 7 MB each) > L2 together with the table
 
 
@@ -90,16 +91,27 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_steps(n_steps, warmup, threads):
-    """Times the oracle port of AttnDecoderLSTM.forward + tail on the host (reference arithmetic, torch CPU)."""
-    from oracle import r2r_oracle as O
-    from speaker_follower_b200 import synth
+_CPU_STATE = {}
+
+
+def _cpu_setup():
+    if not _CPU_STATE:
+        from oracle import r2r_oracle as O
+        from speaker_follower_b200 import synth
+        w = synth.follower_decoder_weights()
+        xs = [synth.follower_step_inputs(B, L, A, seed=900 + i, n_viewpoints=128) for i in range(2)]
+        _CPU_STATE.update(O=O, w=w, xs=xs)
+    return _CPU_STATE["O"], _CPU_STATE["w"], _CPU_STATE["xs"]
+
+
+def cpu_steps(n_steps, warmup, threads, budget_s=None):
+    """Times the oracle port of AttnDecoderLSTM.forward + tail on the host (reference arithmetic, torch CPU).
+    Stops early once `budget_s` seconds of timed work have been spent; returns (steps/s, seconds, steps done)."""
+    O, w, xs = _cpu_setup()
     torch.set_num_threads(threads)
-    w = synth.follower_decoder_weights()
-    xs = [synth.follower_step_inputs(B, L, A, seed=900 + i, n_viewpoints=128) for i in range(2)]
     h, c = xs[0]["h_0"], xs[0]["c_0"]
     u = xs[0]["u_t_prev"]
-    t0 = None
+    t0, done = None, 0
     with torch.no_grad():
         for i in range(warmup + n_steps):
             if i == warmup:
@@ -108,23 +120,43 @@ def cpu_steps(n_steps, warmup, threads):
             h, c, alpha, logit, alpha_v = O.attn_decoder_step(u, x["all_u_t"], x["visual_context"], h, c, x["ctx"],
                                                               x["ctx_mask"], w)
             _, _, a_t, u, sc = O.follower_step_tail(logit, x["is_valid"], None, "argmax", x["all_u_t"])
+            if i >= warmup:
+                done += 1
+                if budget_s is not None and time.perf_counter() - t0 > budget_s:
+                    break
     dt = time.perf_counter() - t0
-    return n_steps / dt, dt
+    return done / dt, dt, done
+
+
+def cpu_best_threads():
+    """The reference is plain torch-CPU code: give it the thread count it runs fastest with on this host (intra-op
+    parallelism of MKL GEMMs stops paying long before all hardware threads are used)."""
+    n = os.cpu_count() or 1
+    cands = sorted({t for t in (4, 8, 16, 32, 64, n) if t <= n})
+    best, best_sps = cands[0], 0.0
+    for t in cands:
+        sps, _, _ = cpu_steps(6, 2, t)
+        if sps > best_sps:
+            best, best_sps = t, sps
+    return best
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    sps, dt = cpu_steps(args.steps, args.warmup, threads)
+    threads = cpu_best_threads()
+    # bounded sample: every step is the full B=100 workload; at most ~60 s of CPU work whatever --steps says
+    sps, dt, done = cpu_steps(args.steps, max(args.warmup, 3) if args.warmup < 20 else 5, threads, budget_s=60.0)
     line = {
         "impl": "reference", "metric": "follower decode-steps/sec", "value": sps, "unit": "steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / sps,
+        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 / sps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "follower decode step B=%d L=%d A=%d V=36 F=2176 (AttnDecoderLSTM.forward + rollout tail)" % (B, L, A),
                    "batch": B, "instr_len": L, "actions": A},
         "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
-                         "sample": "%d decode steps, torch-CPU oracle port of tasks/R2R/model.py (reference is Python/torch; it cannot travel to the GPU box)" % args.steps},
+                         "sample": "%d decode steps (%.1f s) of the same workload, torch-CPU oracle port of tasks/R2R/model.py; "
+                                   "thread count picked as the fastest of a short sweep up to %d hardware threads "
+                                   "(the reference is Python/torch and cannot travel to the GPU box)" % (done, dt, os.cpu_count() or 1)},
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -356,18 +388,20 @@ def run_gpu(args, rank, local_rank, world):
     # every launch reads a different random set of slabs from the 3.1 GB table (inputs >> L2).
     q = torch.randn(B, F, device=dev, generator=g) * 0.05
     feat = torch.empty(B, F, device=dev)
-    n_attn = 200
+    n_attn = 400
     vps = [torch.randint(0, N_VIEWPOINTS, (B,), device=dev, dtype=torch.int32, generator=g) for _ in range(n_attn)]
     for i in range(5):
         ops.visual_attention_core(q, None, store=store, vp_idx=vps[i], view_idx=view[0], out=(feat, alpha_v), workspace=ws)
     torch.cuda.synchronize()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_attn)]
+    # average launch duration over a timed region of n_attn launches on the launch stream (CUDA events around the
+    # region, a synchronize on both sides); every launch gathers a fresh random set of slabs (12.5 GB touched in total)
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
     for i in range(n_attn):
-        evs[i][0].record()
         ops.visual_attention_core(q, None, store=store, vp_idx=vps[i], view_idx=view[0], out=(feat, alpha_v), workspace=ws)
-        evs[i][1].record()
+    eb.record()
     torch.cuda.synchronize()
-    attn_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    attn_ms = ea.elapsed_time(eb) / n_attn
     attn_bytes = 4 * B * 36 * F
     hbm_peak, peak_src = peaks()
     attn_gbs = attn_bytes / (attn_ms * 1e-3) / 1e9
@@ -376,9 +410,8 @@ def run_gpu(args, rank, local_rank, world):
 
     log("attention kernel timed: %.2f us" % (attn_ms * 1e3))
     if rank == 0:
-        cpu_n = 300
-        threads = os.cpu_count() or 1
-        cpu_sps, cpu_dt = cpu_steps(cpu_n, 3, threads)
+        threads = cpu_best_threads()
+        cpu_sps, cpu_dt, cpu_n = cpu_steps(4000, 3, threads, budget_s=15.0)
         line = {
             "metric": "follower decode-steps/sec", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -393,12 +426,15 @@ def run_gpu(args, rank, local_rank, world):
             "gpu_launches": launches_per_step[0] * args.steps,
             "roofline": {"kernel": "soft_dot_attn_kernel (36-view attention gather)", "bound": "hbm",
                          "achieved": attn_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": attn_gbs / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": attn_bytes,
-                         "us_per_launch": attn_ms * 1e3},
+                         "traffic": ATTN_NCU_TRAFFIC, "peak_source": peak_src, "bytes_per_launch": attn_bytes,
+                         "us_per_launch": attn_ms * 1e3,
+                         "how": "%d back-to-back launches between two CUDA events, fresh slabs per launch; traffic = dram read+write "
+                                "per launch from profiles/r01_attn_ncu_full.txt" % n_attn},
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s",
                               "frac": step_gbs / hbm_peak, "bytes_per_step": step_bytes},
             "cpu_baseline": {"value": cpu_sps, "unit": "steps/s", "cores": threads, "kind": "port",
-                             "sample": "%d decode steps of the same workload, torch-CPU oracle port of tasks/R2R/model.py" % cpu_n},
+                             "sample": "%d decode steps (%.1f s) of the same workload, torch-CPU oracle port of tasks/R2R/model.py, "
+                                       "fastest thread count of a short sweep" % (cpu_n, cpu_dt)},
         }
         print(json.dumps(line))
     if dist is not None:
