@@ -243,6 +243,8 @@ def run_gpu(args, rank, local_rank, world):
     launches_per_step = [0]
 
     qbuf = [torch.empty(B, F, device=dev), torch.empty(B, F, device=dev)]   # visual query carried across steps
+    # per-episode projections of ctx (computed once per rollout right after the encoder, not per decode step)
+    cproj = [ops.follower_project_ctx(w, blob, c) for c in ctx] if (blob is not None and not os.environ.get("SFB_NO_CTXPROJ")) else [None] * POOL
 
     def step(i, first=False):
         j, s = i % POOL, i % 2
@@ -257,7 +259,7 @@ def run_gpu(args, rank, local_rank, world):
         ops.follower_step(w, ubuf[s], None, None, hbuf[s], cbuf[s], ctx[j], mask, store=store, vp_idx=vp[j],
                           view_idx=view[j], workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v),
                           packed=blob, q_in=None if first else qbuf[s], q_next=qbuf[s ^ 1],
-                          cand_view=cview[j], cand_trig=ctrig[j],
+                          cand_view=cview[j], cand_trig=ctrig[j], ctx_proj=cproj[j],
                           tail={"is_valid": valid[j], "feedback": "argmax", "out": (a_t, ubuf[s ^ 1], score, None)})
         launches_per_step[0] = ops.last_launch_count()
 
@@ -355,6 +357,7 @@ def run_gpu(args, rank, local_rank, world):
                 ops.follower_step(w, ubuf[s], None, None, hbuf[s], cbuf[s], ctx[0], mask, store=store, vp_idx=d_vp,
                                   view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit2, alpha_v),
                                   packed=blob, q_in=qbuf[s], q_next=qbuf[s ^ 1], cand_view=d_cview, cand_trig=d_ctrig,
+                                  ctx_proj=cproj[0],
                                   tail={"is_valid": d_valid, "feedback": "argmax", "out": (a_t2, ubuf[s ^ 1], score, None)})
         graphs2.append(gph)
 

@@ -170,7 +170,8 @@ int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
  *                 projection; in train mode, where that launch sees the dropped h1, by one extra launch);
  *   tail        : arguments of sfb_follower_step_tail — the rollout tail (follower.py:476-505) runs fused behind the
  *                 logits in the last kernel; `logit` is then masked in place exactly as by the separate call;
- *   act         : gather source of the action candidates (then `all_u_t` may be NULL). */
+ *   act         : gather source of the action candidates (then `all_u_t` may be NULL);
+ *   ctx_k, ctx_o: per-episode projections of ctx from sfb_follower_project_ctx (both or neither). */
 /* Where a step's action-candidate embeddings come from (replaces Seq2SeqAgent._action_variable, follower.py:300-320
  * + _build_action_embedding, env.py:60-75).  dense: all_u_t [B,A,E] on the device.  gather: all_u_t = NULL and
  * candidate a of batch row b is  [ feat_table[vp_idx[b], cand_view[b,a], 0:img_dim] , sin(rh) x n, cos(rh) x n,
@@ -209,8 +210,20 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
                                      const float* drop_x, const float* drop_h,
                                      float* h1, float* c1, float* alpha, float* logit, float* alpha_v,
                                      const float* q_in, float* q_next, const sfb_step_tail* tail,
-                                     const sfb_action_source* act,
+                                     const sfb_action_source* act, const float* ctx_k, const float* ctx_o,
                                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Per-EPISODE projections of the encoder context (ctx is constant over the decode steps of a rollout,
+ * follower.py:446-473): ctx_k = ctx W_in (so that SoftDotAttention's scores ctx . (W_in h) = ctx_k . h, model.py:129-
+ * 132) and ctx_o = ctx W_out_c^T (so that W_out_c (sum alpha ctx) = sum alpha ctx_o, model.py:139-141).  Passing both
+ * to sfb_follower_step_packed_fwd removes every projection between the LSTM cell and the text attention from the
+ * step's dependency chain: W_out_h h is a small projection that runs CONCURRENTLY with the attention (programmatic
+ * dependent launch with a deferred dependency wait), tanh is applied while the next projection loads its operand.
+ * ctx, ctx_k, ctx_o: [B, L, H]; workspace: sfb_follower_project_ctx_workspace_bytes() (zero-filled once). */
+size_t  sfb_follower_project_ctx_workspace_bytes(const sfb_dims* dims, int32_t B, int32_t L);
+int32_t sfb_follower_project_ctx(const sfb_dims* dims, const void* packed, size_t packed_bytes,
+                                 int32_t B, int32_t L, const float* ctx, float* ctx_k, float* ctx_o,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* Per-step tail of Seq2SeqAgent._rollout_with_loss — follower.py:476-505.
  *   logit [B,A] is masked IN PLACE with -inf where is_valid == 0 (477);

@@ -98,8 +98,8 @@ static FollowerWs carve_follower(const sfb_dims& d, int B, int L, int A, void* w
     const int sms = device_num_sms();
     const int nkb_h = kblocks(d.H), nkb_g = kblocks(d.E) + kblocks(d.F) + kblocks(d.H);
     size_t mx = gemm_pk_plan(B, 4 * d.H, nkb_g, true, sms).bytes;
-    const int rows[5] = {d.F, 2 * d.H, d.H, d.E + 1, 2 * d.H + d.F};
-    for (int i = 0; i < 5; ++i) {
+    const int rows[6] = {d.F, 2 * d.H, d.H, d.E + 1, 2 * d.H + d.F, ((d.E + 1 + 127) / 128) * 128 + d.F};
+    for (int i = 0; i < 6; ++i) {
       const size_t b = gemm_pk_plan(B, rows[i], nkb_h, false, sms).bytes;
       if (b > mx) mx = b;
     }
@@ -115,7 +115,7 @@ static FollowerWs carve_follower(const sfb_dims& d, int B, int L, int A, void* w
 
 // ---- packed follower-decoder weights: offsets into the caller-owned blob
 struct FollowerPk {
-  size_t a_q, b_q, a_gates, a_th, a_wc, a_g, b_g, mq, mg, bytes;
+  size_t a_q, b_q, a_gates, a_th, a_wc, a_g, a_gq, b_g, a_kin, mq, mg, bytes;
   int nkb_h, nkb_gates;
 };
 static FollowerPk layout_follower_pk(const sfb_dims& d) {
@@ -129,8 +129,10 @@ static FollowerPk layout_follower_pk(const sfb_dims& d) {
   L.b_q = take((size_t)d.F * 4);
   L.a_gates = take(pk_weight_bytes(4 * d.H, L.nkb_gates));
   L.a_wc = take(pk_weight_bytes(d.H, L.nkb_h));
-  L.a_g = take(pk_weight_bytes(d.E + 1, L.nkb_h));
+  L.a_g = take(pk_weight_bytes(d.E + 1, L.nkb_h));    // M_g (+ constant row) immediately followed by a second copy
+  L.a_gq = take(pk_weight_bytes(d.F, L.nkb_h));       // of M_q: one operand for the fused [g | next query] projection
   L.b_g = take((size_t)(d.E + 4) * 4);
+  L.a_kin = take(pk_weight_bytes(d.H, L.nkb_h));      // W_in^T: the per-episode key projection ctx @ W_in
   L.mq = take((size_t)d.F * d.H * 4);
   L.mg = take((size_t)(d.E + 1) * d.H * 4);
   L.bytes = off;
@@ -626,6 +628,7 @@ int32_t sfb_follower_pack_weights(const sfb_dims* dims, const sfb_vis_lstm_weigh
     return launch_pack_rows(p, st);
   };
   SFB_PROPAGATE(plain(mq, d.H, d.F, d.H, base + L.a_q));
+  SFB_PROPAGATE(plain(mq, d.H, d.F, d.H, base + L.a_gq));
   {
     PackParams p{};
     p.nseg = 3;
@@ -641,6 +644,38 @@ int32_t sfb_follower_pack_weights(const sfb_dims* dims, const sfb_vis_lstm_weigh
   SFB_PROPAGATE(plain(wt->w_out + d.H, 2 * d.H, d.H, d.H, base + L.a_th + pk_weight_bytes(d.H, L.nkb_h)));
   SFB_PROPAGATE(plain(wt->w_out, 2 * d.H, d.H, d.H, base + L.a_wc));
   SFB_PROPAGATE(plain(mg, d.H, d.E + 1, d.H, base + L.a_g));
+  // W_in^T (scratch: the M_q area, already consumed above) for sfb_follower_project_ctx
+  SFB_PROPAGATE(launch_transpose(wt->w_in, d.H, d.H, d.H, mq, d.H, st));
+  SFB_PROPAGATE(plain(mq, d.H, d.H, d.H, base + L.a_kin));
+  return 0;
+}
+
+size_t sfb_follower_project_ctx_workspace_bytes(const sfb_dims* dims, int32_t B, int32_t L) {
+  if (!dims || B < 1 || L < 1) return 0;
+  return gemm_pk_plan(B * L, dims->H, kblocks(dims->H), false, device_num_sms()).bytes;
+}
+
+int32_t sfb_follower_project_ctx(const sfb_dims* dims, const void* packed, size_t packed_bytes, int32_t B, int32_t L,
+                                 const float* ctx, float* ctx_k, float* ctx_o, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_PROPAGATE(check_packable(*dims));
+  SFB_CHECK_ARG(packed && ctx && ctx_k && ctx_o && B >= 1 && L >= 1, "NULL / bad argument");
+  const sfb_dims& d = *dims;
+  const FollowerPk P = layout_follower_pk(d);
+  SFB_CHECK_ARG(packed_bytes >= P.bytes && (reinterpret_cast<uintptr_t>(packed) & 255u) == 0, "packed buffer too small / misaligned");
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, sfb_follower_project_ctx_workspace_bytes(dims, B, L)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned char* base = static_cast<const unsigned char*>(packed);
+  for (int which = 0; which < 2; ++which) {   // ctx_k = ctx W_in (keys of the text attention), ctx_o = ctx W_out_c^T (values)
+    PkParams q{};
+    q.a_pk = base + (which == 0 ? P.a_kin : P.a_wc); q.b_pk = nullptr; q.nkb = kblocks(d.H);
+    q.g.nseg = 1;
+    q.g.seg[0] = GemmSeg{ctx, d.H, nullptr, nullptr, 0, nullptr, 0, d.H, 0};
+    q.g.M = B * L; q.g.N = d.H; q.g.out = which == 0 ? ctx_k : ctx_o; q.g.ldo = d.H;
+    SFB_PROPAGATE(launch_gemm_pk(q, st, workspace, workspace_bytes));
+  }
   return 0;
 }
 
@@ -650,14 +685,15 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
                                      const float* c0, const float* ctx, const uint8_t* ctx_mask, const float* drop_x,
                                      const float* drop_h, float* h1, float* c1, float* alpha, float* logit,
                                      float* alpha_v, const float* q_in, float* q_next, const sfb_step_tail* tail,
-                                     const sfb_action_source* act, void* workspace, size_t workspace_bytes,
-                                     void* stream) {
+                                     const sfb_action_source* act, const float* ctx_k, const float* ctx_o,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
   reset_launch_count();
   SFB_PROPAGATE(check_dims(dims));
   SFB_PROPAGATE(check_packable(*dims));
   SFB_CHECK_ARG(wl && vis && packed, "NULL weight/source struct");
   SFB_CHECK_ARG(u_prev && h0 && c0 && ctx && h1 && c1 && logit, "NULL tensor argument");
   SFB_CHECK_ARG(B >= 1 && L >= 1 && A >= 1, "B, L, A >= 1");
+  SFB_CHECK_ARG((ctx_k == nullptr) == (ctx_o == nullptr), "ctx_k and ctx_o must be given together");
   const bool act_gather = act && act->all_u_t == nullptr;
   if (act_gather) {
     SFB_CHECK_ARG(act->feat_table && act->vp_idx && act->cand_view && act->cand_trig, "gather action source needs table, indices and trig values");
@@ -727,26 +763,72 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
     e.h1 = h1; e.c1 = c1; e.h1_drop = ws.h1d; e.gates_act = ws.gates_act;
     SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));
   }
-  // model.py:395  text attention: [t | W_out_h h1d] in one projection — and, software-pipelined across the
-  // recurrence, the NEXT step's visual query M_q h_1 + b_q in the same launch (eval mode: h1d == h_1)
-  if (q_next && !drop_h) {
-    SFB_PROPAGATE(proj(base + P.a_th, ws.h1d, d.H, d.H, 2 * d.H + d.F, ws.th, 2 * d.H, nullptr, nullptr, 0, 0, 2 * d.H, q_next,
-                       d.F, b_q));
+  const float* b_g = reinterpret_cast<const float*>(base + P.b_g);
+  if (ctx_k) {
+    // model.py:395-396 with the per-episode projections of ctx (sfb_follower_project_ctx): the text attention reads
+    // h_1 directly (scores = (ctx W_in) . h, output = sum alpha (ctx W_out_c^T) = W_out_c wc), so NO projection sits
+    // between the LSTM cell and the attention.  hh = W_out_h h is its own small projection that triggers its
+    // dependents only after its dependency wait; the attention (which needs nothing from it) then runs CONCURRENTLY
+    // with it and waits for it only at its very end.  h~ = tanh(W_out_c wc + hh) is formed while the g projection
+    // loads its activation operand, and the same launch computes the next step's query from h_1 (extra tiles).
+    {
+      PkParams q{};
+      q.a_pk = base + P.a_th + pk_weight_bytes(d.H, P.nkb_h); q.nkb = kblocks(d.H);   // rows of W_out[:, H:2H]
+      q.g.nseg = 1;
+      q.g.seg[0] = GemmSeg{ws.h1d, d.H, nullptr, nullptr, 0, nullptr, 0, d.H, 0};
+      q.g.M = B; q.g.N = d.H; q.g.out = ws.th; q.g.ldo = d.H;
+      q.late_trigger = 1;
+      SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));
+    }
+    {
+      AttnParams a{};
+      a.q = ws.h1d; a.ldq = d.H; a.R = L; a.D = d.H;
+      a.segA = ctx_o; a.strideA_b = (long long)L * d.H; a.strideA_r = d.H; a.lenA = d.H; a.lenB = 0;
+      a.keyA = ctx_k; a.strideK_b = (long long)L * d.H; a.strideK_r = d.H;
+      a.mask = ctx_mask; a.ldmask = L;
+      a.out = ws.wc; a.ldo = d.H; a.alpha = alpha; a.ldalpha = L;
+      a.defer_wait = 1;
+      SFB_PROPAGATE(launch_soft_dot_attention(a, B, ws.at, ws.at_bytes, st));
+    }
+    {
+      PkParams q{};
+      q.a_pk = base + P.a_g; q.b_pk = nullptr; q.nkb = kblocks(d.H);
+      q.g.nseg = 1;
+      q.g.seg[0] = GemmSeg{ws.wc, d.H, nullptr, nullptr, 0, nullptr, 0, d.H, 0, ws.th, d.H, 1};   // tanh(W_out_c wc + hh)
+      q.g.M = B; q.g.out = ws.g; q.g.ldo = ws.ldg; q.g.bias0 = b_g;
+      const int g_tiles = (d.E + 1 + 127) / 128;
+      if (q_next) {   // tiles g_tiles.. = M_q rows, fed with the un-dropped h_1: the next step's visual query
+        SFB_CHECK_ARG(P.a_gq == P.a_g + pk_weight_bytes(d.E + 1, P.nkb_h), "packed layout: g / q operand not contiguous");
+        q.g.N = g_tiles * 128 + d.F;
+        q.g.n_split = g_tiles * 128; q.g.n1_valid = d.E + 1; q.g.out2 = q_next; q.g.ldo2 = d.F; q.g.bias2 = b_q;
+        q.alt_tile0 = g_tiles;
+        q.alt_seg = GemmSeg{h1, d.H, nullptr, nullptr, 0, nullptr, 0, d.H, 0};
+      } else {
+        q.g.N = d.E + 1;
+      }
+      SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));
+    }
   } else {
-    SFB_PROPAGATE(proj(base + P.a_th, ws.h1d, d.H, d.H, 2 * d.H, ws.th, 2 * d.H, nullptr, nullptr, 0, 0, 0, nullptr, 0, nullptr));
+    // model.py:395  text attention: [t | W_out_h h1d] in one projection — and, software-pipelined across the
+    // recurrence, the NEXT step's visual query M_q h_1 + b_q in the same launch (eval mode: h1d == h_1)
+    if (q_next && !drop_h) {
+      SFB_PROPAGATE(proj(base + P.a_th, ws.h1d, d.H, d.H, 2 * d.H + d.F, ws.th, 2 * d.H, nullptr, nullptr, 0, 0, 2 * d.H, q_next,
+                         d.F, b_q));
+    } else {
+      SFB_PROPAGATE(proj(base + P.a_th, ws.h1d, d.H, d.H, 2 * d.H, ws.th, 2 * d.H, nullptr, nullptr, 0, 0, 0, nullptr, 0, nullptr));
+    }
+    {
+      AttnParams a{};
+      a.q = ws.th; a.ldq = 2 * d.H; a.R = L; a.D = d.H;
+      a.segA = ctx; a.strideA_b = (long long)L * d.H; a.strideA_r = d.H; a.lenA = d.H; a.lenB = 0;
+      a.mask = ctx_mask; a.ldmask = L;
+      a.out = ws.wc; a.ldo = d.H; a.alpha = alpha; a.ldalpha = L;
+      SFB_PROPAGATE(launch_soft_dot_attention(a, B, ws.at, ws.at_bytes, st));
+    }
+    SFB_PROPAGATE(proj(base + P.a_wc, ws.wc, d.H, d.H, d.H, ws.htilde, d.H, nullptr, ws.th + d.H, 2 * d.H, 1, 0, nullptr, 0, nullptr));
+    // model.py:396  logit = decoder2action(h_tilde, all_u_t):  g = M_g h~ + b_g (column E = the per-row constant)
+    SFB_PROPAGATE(proj(base + P.a_g, ws.htilde, d.H, d.H, d.E + 1, ws.g, ws.ldg, b_g, nullptr, 0, 0, 0, nullptr, 0, nullptr));
   }
-  {
-    AttnParams a{};
-    a.q = ws.th; a.ldq = 2 * d.H; a.R = L; a.D = d.H;
-    a.segA = ctx; a.strideA_b = (long long)L * d.H; a.strideA_r = d.H; a.lenA = d.H; a.lenB = 0;
-    a.mask = ctx_mask; a.ldmask = L;
-    a.out = ws.wc; a.ldo = d.H; a.alpha = alpha; a.ldalpha = L;
-    SFB_PROPAGATE(launch_soft_dot_attention(a, B, ws.at, ws.at_bytes, st));
-  }
-  SFB_PROPAGATE(proj(base + P.a_wc, ws.wc, d.H, d.H, d.H, ws.htilde, d.H, nullptr, ws.th + d.H, 2 * d.H, 1, 0, nullptr, 0, nullptr));
-  // model.py:396  logit = decoder2action(h_tilde, all_u_t):  g = M_g h~ + b_g (column E = the per-row constant)
-  SFB_PROPAGATE(proj(base + P.a_g, ws.htilde, d.H, d.H, d.E + 1, ws.g, ws.ldg, reinterpret_cast<const float*>(base + P.b_g), nullptr,
-                     0, 0, 0, nullptr, 0, nullptr));
   ScoringParams sp{};
   sp.all_u_t = all_u_t; sp.g = ws.g; sp.tp = nullptr; sp.ldg = ws.ldg; sp.logit = logit; sp.B = B; sp.A = A; sp.E = d.E; sp.D = d.D;
   if (act_gather) {
@@ -759,7 +841,7 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
                          tail->u_next, tail->action_score, tail->ce, B, A, d.E, nullptr};
   }
   SFB_PROPAGATE(launch_action_scoring(sp, st));
-  if (q_next && drop_h)   // train mode: the next query needs the un-dropped h_1 -> its own projection
+  if (q_next && drop_h && !ctx_k)   // train mode: the next query needs the un-dropped h_1 -> its own projection
     SFB_PROPAGATE(proj(base + P.a_q, h1, d.H, d.H, d.F, q_next, d.F, b_q, nullptr, 0, 0, 0, nullptr, 0, nullptr));
   return 0;
 }

@@ -43,10 +43,11 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, rank = blockIdx.x, CL = gridDim.x;
   const int D = p.D, nvec = D >> 2, NSTG = p.stages;
+  const int SD = p.keyA ? 2 * D : D;   // floats per stage: value row [+ separate key row]
   const int nmine = rank < p.R ? (p.R - rank + CL - 1) / CL : 0;   // rows rank, rank+CL, ...
 
   float* ring = reinterpret_cast<float*>(smem_raw);                          // [NSTG][D]; reused as the merge inbox
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)NSTG * D);     // [NSTG]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)NSTG * SD);    // [NSTG]
   float* red = reinterpret_cast<float*>(full + NSTG);                        // [2][NW][RB] per-warp partial dots
   float* stat = red + 2 * NW * RB;                                                // [2] (max, sum) of this CTA, read by peers
   float* sc = stat + 2;                                                      // [rows_per_cta] raw scores (local order)
@@ -70,8 +71,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
   uint64_t pol = 0;
   auto fetch = [&](int i, int stage) {   // local unmasked row #i -> ring[stage]
     const int gr = rank + CL * list[i];
-    float* dst = ring + (size_t)stage * D;
-    mbar_expect_tx(&full[stage], (uint32_t)D * 4u);
+    float* dst = ring + (size_t)stage * SD;
+    mbar_expect_tx(&full[stage], (uint32_t)SD * 4u);
+    if (p.keyA)   // scores use a separate (pre-projected) key row, the weighted sum the value row
+      bulk_g2s_hint(dst + D, p.keyA + (size_t)b * p.strideK_b + (size_t)gr * p.strideK_r, (uint32_t)D * 4u, &full[stage], pol);
     bulk_g2s_hint(dst, p.segA + ba + (size_t)gr * p.strideA_r, (uint32_t)p.lenA * 4u, &full[stage], pol);
     if (p.lenB > 0)
       bulk_g2s_hint(dst + p.lenA, p.segB + bb + (size_t)gr * p.strideB_r, (uint32_t)p.lenB * 4u, &full[stage], pol);
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
   }
   for (int i = tid; i < nmine; i += NT) sc[i] = -INFINITY;
   // ---- 2. q is produced by the preceding kernel: wait for it only now (rows above are step inputs)
-  pdl_wait();
+  if (!p.defer_wait) pdl_wait();
   trace_mark(p.trace, 1);
   float4 qv[NJ], acc[NJ];
   {
@@ -131,15 +134,17 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
       if (r < nb) {
         const int i = i0 + r, s = i % NSTG;
         mbar_wait(&full[s], (uint32_t)(i / NSTG) & 1u);
-        const float4* row4 = reinterpret_cast<const float4*>(ring + (size_t)s * D);
+        const float4* row4 = reinterpret_cast<const float4*>(ring + (size_t)s * SD);
+        const float4* key4 = p.keyA ? row4 + nvec : row4;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           const int idx = tid + NT * j;
           v[r][j] = idx < nvec ? row4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-          part[r] = fmaf(v[r][j].x, qv[j].x, part[r]);
-          part[r] = fmaf(v[r][j].y, qv[j].y, part[r]);
-          part[r] = fmaf(v[r][j].z, qv[j].z, part[r]);
-          part[r] = fmaf(v[r][j].w, qv[j].w, part[r]);
+          const float4 kx = p.keyA ? (idx < nvec ? key4[idx] : make_float4(0.f, 0.f, 0.f, 0.f)) : v[r][j];
+          part[r] = fmaf(kx.x, qv[j].x, part[r]);
+          part[r] = fmaf(kx.y, qv[j].y, part[r]);
+          part[r] = fmaf(kx.z, qv[j].z, part[r]);
+          part[r] = fmaf(kx.w, qv[j].w, part[r]);
         }
       } else {
 #pragma unroll
@@ -271,6 +276,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
       }
     }
   }
+  if (p.defer_wait) pdl_wait();   // grid completion must imply the predecessor's completion (see AttnParams)
   trace_mark(p.trace, 2);
   if (ct && tid == 0) ct[3] = globaltimer_ns();
   if (p.trace && tid == 0 && b == gridDim.y - 1 && rank == CL - 1) p.trace[3] = globaltimer_ns();   // last cluster
@@ -278,15 +284,16 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
 
 // ------------------------------------------------------------------ host launcher
 
-static size_t attn_smem_bytes(int stages, int D, int rows_per_cta) {
+static size_t attn_smem_bytes(int stages, int D, int rows_per_cta) {   // D = floats per stage
   return (size_t)stages * D * sizeof(float) + (size_t)stages * sizeof(uint64_t) + (2 * 8 * 4 + 2) * sizeof(float) +
          (size_t)rows_per_cta * (sizeof(float) + sizeof(int));
 }
 
-AttnPlan attention_plan(int B, int R, int D, int num_sms) {
+AttnPlan attention_plan(int B, int R, int D, int num_sms, bool kv) {
+  if (kv) D *= 2;   // a stage holds the value row and the key row
   AttnPlan pl{};
   // cluster size: the largest CL whose B x CL CTAs are still ONE resident wave, with >= 4 rows per CTA
-  const int nt = D <= 512 ? 128 : 256;
+  const int nt = (kv ? D / 2 : D) <= 512 ? 128 : 256;
   int best = 1;
   for (int cl = 8; cl >= 1; cl >>= 1) {
     if (cl > 1 && R / cl < 4) continue;
@@ -316,7 +323,7 @@ AttnPlan attention_plan(int B, int R, int D, int num_sms) {
 template <int NJ, int NT, int RB>
 static int32_t launch_attn_t(const AttnParams& p, int B, int cl, cudaStream_t stream) {
   auto kern = soft_dot_attn_kernel<NJ, NT, RB>;
-  const size_t smem = attn_smem_bytes(p.stages, p.D, p.rows_per_cta);
+  const size_t smem = attn_smem_bytes(p.stages, p.keyA ? 2 * p.D : p.D, p.rows_per_cta);
   static size_t configured = 0;  // per instantiation
   if (smem > configured) {
     SFB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -334,11 +341,15 @@ int32_t launch_soft_dot_attention(AttnParams p, int B, void* ws, size_t ws_bytes
   SFB_CHECK_ARG((p.lenA % 4) == 0 && (p.lenB % 4) == 0 && p.lenA + p.lenB == p.D, "bad row segments");
   SFB_CHECK_ARG(p.R >= 1, "need at least one row");
   SFB_CHECK_ARG(B <= 65535, "attention: batch > 65535");
-  AttnPlan pl = attention_plan(B, p.R, p.D, device_num_sms());
+  const int SD = p.keyA ? 2 * p.D : p.D;
+  SFB_CHECK_ARG(!p.keyA || p.D <= 1024, "attention: separate key rows are supported for row length <= 1024");
+  SFB_CHECK_ARG(!p.keyA || ((reinterpret_cast<uintptr_t>(p.keyA) & 15u) == 0 && (p.strideK_r % 4) == 0 && (p.strideK_b % 4) == 0),
+                "attention: key rows must be 16-byte aligned");
+  AttnPlan pl = attention_plan(B, p.R, p.D, device_num_sms(), p.keyA != nullptr);
   if (g_attn_force_cl > 0) {   // bring-up: force the cluster size
     pl.split = g_attn_force_cl;
     pl.rows_per_cta = (p.R + pl.split - 1) / pl.split;
-    int st = (int)(ATT_RING_BUDGET / ((size_t)p.D * 4));
+    int st = (int)(ATT_RING_BUDGET / ((size_t)SD * 4));
     st = st > pl.rows_per_cta ? pl.rows_per_cta : st;
     pl.stages = st < 4 ? 4 : (st > ATT_MAX_STAGES ? ATT_MAX_STAGES : st);
   }
@@ -349,7 +360,7 @@ int32_t launch_soft_dot_attention(AttnParams p, int B, void* ws, size_t ws_bytes
   p.ticket = nullptr;
   p.part = nullptr;
   if (p.has_side) SFB_PROPAGATE(pack_prepare(p.side));
-  SFB_CHECK_ARG(attn_smem_bytes(p.stages, p.D, p.rows_per_cta) <= 200 * 1024, "attention rows do not fit shared memory");
+  SFB_CHECK_ARG(attn_smem_bytes(p.stages, SD, p.rows_per_cta) <= 200 * 1024, "attention rows do not fit shared memory");
   if (p.D <= 512) return launch_attn_t<1, 128, 4>(p, B, pl.split, stream);
   if (p.D <= 1024) return launch_attn_t<1, 256, 4>(p, B, pl.split, stream);
   return launch_attn_t<3, 256, 1>(p, B, pl.split, stream);

@@ -87,6 +87,7 @@ __device__ __forceinline__ void plain_store(const GemmParams& p, int m, int n, f
     p.out2[(size_t)m * p.ldo2 + n2] = v;
     return;
   }
+  if (p.out2 && p.n1_valid > 0 && n >= p.n1_valid) return;   // padding rows of the first output block
   if (p.bias0) v += __ldg(p.bias0 + n);
   if (p.bias1) v += __ldg(p.bias1 + n);
   if (p.padd) v += p.padd[(size_t)m * p.ld_padd + n];
@@ -113,7 +114,8 @@ __device__ __forceinline__ void plain_store4(const GemmParams& p, int m, int n, 
     }
     return;
   }
-  if (n + 3 < p.N && (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0) {
+  const int n_end = (p.out2 && p.n1_valid > 0) ? p.n1_valid : p.N;
+  if (n + 3 < n_end && (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0) {
     float r[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

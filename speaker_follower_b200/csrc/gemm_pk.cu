@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
   const int nit = max(0, kb_end - kb_begin);
 
   trace_mark(p.trace, 0);
-  pdl_launch_dependents();
+  if (!q.late_trigger) pdl_launch_dependents();
   unsigned int sem_gen = 0;
 
   if (warp == 9) {
@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
         bulk_g2s_hint(smem + (size_t)it * stage_bytes, a_src + (size_t)it * (2 * PA_HALF), 2 * PA_HALF, &full[it], pol);
       }
       pdl_wait();
+      if (q.late_trigger) pdl_launch_dependents();
       if (B_PACKED)
         for (int it = 0; it < pre; ++it)
           bulk_g2s(smem + (size_t)it * stage_bytes + 2 * PA_HALF, b_src + (size_t)it * (2 * b_half), 2 * b_half, &full[it]);
@@ -133,10 +134,12 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
       }
     } else {
       pdl_wait();
+      if (q.late_trigger) pdl_launch_dependents();
     }
   } else if (warp == 8) {
     // =============================== MMA issuer ===============================
     pdl_wait();
+    if (q.late_trigger) pdl_launch_dependents();
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(PBM >> 4) << 24);
     for (int it = 0; it < nit; ++it) {
       const int s = it % NST, use = it / NST;
@@ -162,6 +165,7 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
   } else {
     // =============================== warps 0-7 ===============================
     pdl_wait();
+    if (q.late_trigger) pdl_launch_dependents();
     trace_mark(p.trace, 1);
     if (tid == 0 && S > 1)   // generation of this tile's split-K barrier, read long before it is needed
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(sem_gen) : "l"(q.sem + 2 * (z * tiles + tile) + 1) : "memory");
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
           cc -= n;
           ++s;
         }
-        const GemmSeg& g = p.seg[s];
+        const GemmSeg& g = (q.alt_tile0 > 0 && tile >= q.alt_tile0) ? q.alt_seg : p.seg[s];
         const int kofs = cc * PBK;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -189,6 +193,18 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
             const float* src = g.x + (size_t)xr * g.ldx + k;
             rb[set][i][0] = *reinterpret_cast<const float4*>(src);
             rb[set][i][1] = *reinterpret_cast<const float4*>(src + 4);
+            if (g.xadd) {
+              const float* ap = g.xadd + (size_t)m * g.ldxadd + k;
+              const float4 a0 = *reinterpret_cast<const float4*>(ap), a1 = *reinterpret_cast<const float4*>(ap + 4);
+              float4& r0 = rb[set][i][0];
+              float4& r1 = rb[set][i][1];
+              r0.x += a0.x; r0.y += a0.y; r0.z += a0.z; r0.w += a0.w;
+              r1.x += a1.x; r1.y += a1.y; r1.z += a1.z; r1.w += a1.w;
+              if (g.xtanh) {
+                r0.x = tanhf(r0.x); r0.y = tanhf(r0.y); r0.z = tanhf(r0.z); r0.w = tanhf(r0.w);
+                r1.x = tanhf(r1.x); r1.y = tanhf(r1.y); r1.z = tanhf(r1.z); r1.w = tanhf(r1.w);
+              }
+            }
             if (HAS_XS) {
               if (g.xs) {
                 const float* sp = g.xs + (size_t)m * g.ldxs + k;
@@ -421,13 +437,18 @@ int32_t launch_gemm_pk(const PkParams& q_in, cudaStream_t stream, void* ws, size
       SFB_CHECK_ARG(g.x && (g.k % 8) == 0 && (g.ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(g.x) & 15u) == 0,
                     "gemm_pk: fp32 activations must be 16-byte aligned, K % 8 == 0");
       SFB_CHECK_ARG(!g.xs || ((reinterpret_cast<uintptr_t>(g.xs) & 15u) == 0 && (g.ldxs % 4) == 0), "gemm_pk: scale alignment");
+      SFB_CHECK_ARG(!g.xadd || ((reinterpret_cast<uintptr_t>(g.xadd) & 15u) == 0 && (g.ldxadd % 4) == 0), "gemm_pk: addend alignment");
     }
     SFB_CHECK_ARG(pk_num_kblocks(kk, p.nseg) == q.nkb, "gemm_pk: K segments do not match the packed weights");
+    SFB_CHECK_ARG(q.alt_tile0 == 0 || (p.nseg == 1 && q.alt_seg.x && q.alt_seg.k == p.seg[0].k && !q.alt_seg.xs && !p.seg[0].xs &&
+                                       (q.alt_seg.ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(q.alt_seg.x) & 15u) == 0),
+                  "gemm_pk: alternative activation source must match the single K segment");
   } else {
     SFB_CHECK_ARG((reinterpret_cast<uintptr_t>(q.b_pk) & 127u) == 0, "gemm_pk: packed activations misaligned");
   }
   const PkPlan pl = gemm_pk_plan(p.M, n_rows, q.nkb, b_packed, device_num_sms());
-  SFB_CHECK_ARG(ws && ws_bytes >= pl.bytes && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "gemm_pk: workspace");
+  const size_t ws_need = (pl.S == 1 && !lstm) ? pl.sem_bytes : pl.bytes;   // direct epilogue: no partial tiles
+  SFB_CHECK_ARG(ws && ws_bytes >= ws_need && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "gemm_pk: workspace");
   if (q.has_side) SFB_PROPAGATE(pack_prepare(q.side));
   q.sem = static_cast<unsigned int*>(ws);
   q.partial = reinterpret_cast<float*>(static_cast<char*>(ws) + pl.sem_bytes);

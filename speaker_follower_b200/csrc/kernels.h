@@ -24,6 +24,7 @@ struct PackParams {
 };
 int32_t pack_prepare(PackParams& p);   // validates and fills nkb
 int32_t launch_pack_rows(const PackParams& p, cudaStream_t stream);
+int32_t launch_transpose(const float* src, int lds, int R, int Cc, float* dst, int ldd, cudaStream_t stream);
 int32_t launch_fold(const float* A, int lda, const float* s, const float* Bm, int ldb, const float* bv, int D, int NA,
                     int NJ, float* out, int ldo, float* obias, const float* obias_add, cudaStream_t stream);
 
@@ -33,6 +34,8 @@ struct AttnParams {
   // row r of batch element b = concat(segA[...], segB[...]); lenA + lenB == D
   const float* segA; long long strideA_b; int strideA_r; int lenA;
   const float* segB; long long strideB_b; int strideB_r; int lenB;
+  // optional separate KEY rows (same length D, dense [B,R,D] addressing): scores = key . q, output = sum alpha * row
+  const float* keyA; long long strideK_b; int strideK_r;
   const int32_t* idxA;                    // optional: batch element b reads block idxA[b] of segA (gather)
   const int32_t* idxB;
   const uint8_t* mask; int ldmask;        // [B, R], 1 = masked; may be NULL
@@ -44,6 +47,10 @@ struct AttnParams {
   unsigned char* pk_out; int pk_kb0, pk_nkb, pk_NB, pk_rows_per_z;
   const float* pk_scale; int pk_ldscale;
   int has_side; PackParams side;          // optional side job after the dependency wait: pack other step operands
+  // 1: the query was produced TWO kernels back and the predecessor (which triggers its dependents only after its own
+  // dependency wait) writes nothing this kernel reads -> run concurrently with it; the dependency wait moves to the end
+  // of the kernel so that this grid's completion still implies the predecessor's
+  int defer_wait;
   unsigned long long* cta_trace;          // bring-up: per-CTA {entry, first row landed, stream done, exit, smid}
   unsigned long long* trace;              // bring-up: 3 timestamps of block 0, or NULL
   // filled by the launcher
@@ -55,7 +62,7 @@ struct AttnPlan {
   int split, rows_per_cta, stages;
   size_t ticket_bytes, bytes;             // workspace: tickets + partial records
 };
-AttnPlan attention_plan(int B, int R, int D, int num_sms);
+AttnPlan attention_plan(int B, int R, int D, int num_sms, bool kv = false);
 int32_t launch_soft_dot_attention(AttnParams p, int B, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 // ---------------------------------------------------------------- gemm_simt.cu
@@ -67,6 +74,9 @@ struct GemmSeg {
   const float* w;  int ldw;               // w_kn == 0: [N, k] row-major (nn.Linear); w_kn == 1: [k, N] row-major
   int k;
   int w_kn;
+  // gemm_pk only: the activation actually multiplied is f(x + xadd) with f = tanh when xtanh (fuses the
+  // h~ = tanh(W_out_c wc + W_out_h h) pointwise step of SoftDotAttention into the next projection's operand load)
+  const float* xadd; int ldxadd; int xtanh;
 };
 // Fused LSTM cell epilogue (nn.LSTMCell pointwise part, model.py:393): active when H > 0.  The GEMM then
 // computes the gate pre-activations W_ih x + W_hh h with gate-interleaved 32-column tiles (4 gates x 8 units).
@@ -95,6 +105,7 @@ struct GemmParams {
   const float* padd; int ld_padd;         // [M, >=N] or NULL: added before the activation (pre-computed partial sum)
   // optional split output: columns n >= n_split (a multiple of 128) go to out2[m*ldo2 + n - n_split] + bias2, no act
   int n_split; float* out2; int ldo2; const float* bias2;
+  int n1_valid;                           // with out2: columns n1_valid <= n < n_split are padding and not stored (0 = n_split)
   int act;                                // 0 none, 1 tanh
   int exact;                              // 1: force the exact-fp32 FFMA path (default: 3xTF32 mma.sync for M > 32)
   LstmEpilogue lstm;
@@ -122,6 +133,8 @@ struct PkParams {
   const unsigned char* b_pk;             // packed activations [nz][nkb][2*NB*128 B] or NULL
   int nkb;                               // 64-wide K blocks (all segments)
   int has_side; PackParams side;         // optional side job for the otherwise idle warps: pack another operand
+  int late_trigger;                      // 1: griddepcontrol.launch_dependents only after the dependency wait (see AttnParams::defer_wait)
+  int alt_tile0; GemmSeg alt_seg;        // tiles >= alt_tile0 (> 0) read their fp32 activations from alt_seg instead of g.seg[0]
   // filled by the launcher
   int NB, rows_per_z, nstages;
   float* partial; unsigned int* sem;

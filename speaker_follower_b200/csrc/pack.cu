@@ -93,6 +93,26 @@ __global__ void __launch_bounds__(256) fold_kernel(const float* __restrict__ A, 
     obias[n0 + tx] = (float)(bacc + (obias_add ? (double)obias_add[0] : 0.0));
 }
 
+// dst[c][r] = src[r][c]  (pack time only)
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, int lds, int R, int Cc,
+                                                        float* __restrict__ dst, int ldd) {
+  __shared__ float t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = ty; i < 32; i += 8)
+    t[i][tx] = (r0 + i < R && c0 + tx < Cc) ? src[(size_t)(r0 + i) * lds + c0 + tx] : 0.f;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < Cc && r0 + tx < R) dst[(size_t)(c0 + i) * ldd + r0 + tx] = t[tx][i];
+}
+
+int32_t launch_transpose(const float* src, int lds, int R, int Cc, float* dst, int ldd, cudaStream_t stream) {
+  SFB_CHECK_ARG(src && dst && R >= 1 && Cc >= 1, "transpose: bad arguments");
+  transpose_kernel<<<dim3((Cc + 31) / 32, (R + 31) / 32, 1), 256, 0, stream>>>(src, lds, R, Cc, dst, ldd);
+  SFB_CHECK_LAUNCH();
+  return 0;
+}
+
 int32_t launch_fold(const float* A, int lda, const float* s, const float* Bm, int ldb, const float* bv, int D, int NA,
                     int NJ, float* out, int ldo, float* obias, const float* obias_add, cudaStream_t stream) {
   SFB_CHECK_ARG(A && Bm && out && D >= 1 && NA >= 1 && NJ >= 1, "fold: bad arguments");

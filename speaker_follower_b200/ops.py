@@ -164,14 +164,17 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
                   vp_idx: Optional[Tensor] = None, view_idx: Optional[Tensor] = None,
                   workspace: Optional[Tensor] = None, out: Optional[tuple] = None,
                   packed: Optional[Tensor] = None, q_in: Optional[Tensor] = None, q_next: Optional[Tensor] = None,
-                  tail: Optional[dict] = None, cand_view: Optional[Tensor] = None, cand_trig: Optional[Tensor] = None):
+                  tail: Optional[dict] = None, cand_view: Optional[Tensor] = None, cand_trig: Optional[Tensor] = None,
+                  ctx_proj: Optional[tuple] = None):
     """AttnDecoderLSTM.forward (model.py:377-397) -> (h1, c1, alpha, logit, alpha_v).
     `packed`: blob from PackedFollower.get(w) -> the packed-weight tcgen05 path (sfb_follower_step_packed_fwd).
     Packed path only: `q_in` / `q_next` [B,F] carry the visual query across steps (see include/sf_b200.h);
     `tail` = dict(is_valid, feedback, target=None, sample_u=None, out=(a_t, u_next, score, ce)) fuses the rollout
     tail (follower.py:476-505) behind the logits; the outputs are left in tail["out"];
     `all_u_t=None` with `cand_view` [B,A] int32 / `cand_trig` [B,A,4] (+ store, vp_idx): action candidates gathered
-    on the device from the feature table (env.py:60-75) instead of being shipped as a dense [B,A,E] tensor."""
+    on the device from the feature table (env.py:60-75) instead of being shipped as a dense [B,A,E] tensor;
+    `ctx_proj` = (ctx_k, ctx_o) from follower_project_ctx(): per-episode projections of ctx that take the text-side
+    projections off the step's dependency chain."""
     lib = _lib.load()
     L = ctx.shape[1]
     V = visual.shape[1] if visual is not None else store.feat_table.shape[1]
@@ -222,7 +225,10 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
             _p(c0, name="c_0"), _p(ctx, name="ctx"), _p(mask, torch.uint8, "ctx_mask"), _p(drop_x, name="drop_x"),
             _p(drop_h, name="drop_h"), _p(h1), _p(c1), _p(alpha), _p(logit), _p(alpha_v), _p(q_in, name="q_in"),
             _p(q_next, name="q_next"), C.byref(tl) if tl is not None else None,
-            C.byref(act) if act is not None else None, workspace.data_ptr(), workspace.numel(), _stream()))
+            C.byref(act) if act is not None else None,
+            _p(ctx_proj[0], name="ctx_k") if ctx_proj is not None else None,
+            _p(ctx_proj[1], name="ctx_o") if ctx_proj is not None else None,
+            workspace.data_ptr(), workspace.numel(), _stream()))
         return h1, c1, alpha, logit, alpha_v
     wl, wt, ws = _vis_lstm_weights(w), _softdot_weights(w, "text_attention_layer."), _scoring_weights(w)
     check(lib.sfb_follower_step_fwd(
@@ -231,6 +237,18 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
         _p(ctx, name="ctx"), _p(mask, torch.uint8, "ctx_mask"), _p(drop_x, name="drop_x"), _p(drop_h, name="drop_h"),
         _p(h1), _p(c1), _p(alpha), _p(logit), _p(alpha_v), workspace.data_ptr(), workspace.numel(), _stream()))
     return h1, c1, alpha, logit, alpha_v
+
+
+def follower_project_ctx(w: Dict[str, Tensor], packed: Tensor, ctx: Tensor, out: Optional[tuple] = None):
+    """Per-episode (ctx_k, ctx_o) = (ctx W_in, ctx W_out_c^T) for follower_step(ctx_proj=...) — include/sf_b200.h."""
+    lib = _lib.load()
+    d = follower_dims(w)
+    B, L, H = ctx.shape
+    ctx_k, ctx_o = out if out is not None else (torch.empty_like(ctx), torch.empty_like(ctx))
+    ws = _workspace(lib.sfb_follower_project_ctx_workspace_bytes(C.byref(d), B, L), ctx.device)
+    check(lib.sfb_follower_project_ctx(C.byref(d), packed.data_ptr(), packed.numel(), B, L, _p(ctx, name="ctx"),
+                                       _p(ctx_k), _p(ctx_o), ws.data_ptr(), ws.numel(), _stream()))
+    return ctx_k, ctx_o
 
 
 def follower_tail(logit: Tensor, is_valid: Tensor, all_u_t: Tensor, feedback: str, target: Optional[Tensor] = None,

@@ -254,3 +254,42 @@ def test_action_candidates_gathered_on_device(weights):
     assert torch.equal(outs[0][0], outs[1][0]), "logits differ"
     for a, b in zip(outs[0][1], outs[1][1]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,L,A", [(8, 20, 6), (100, 80, 8), (130, 33, 5)])
+def test_ctx_projections_take_text_side_off_the_chain(weights, B, L, A):
+    """Per-episode ctx_k = ctx W_in / ctx_o = ctx W_out_c^T: the step with ctx_proj (attention straight from h_1, W_out_h h
+    on the helper stream, tanh fused into the next projection's operand load) == oracle, incl. carry + fused tail."""
+    w, wc, _, blob = weights
+    x = synth.follower_step_inputs(B, L, A, seed=940 + B)
+    xc = cu(x)
+    ck, co = ops.follower_project_ctx(wc, blob, xc["ctx"])
+    close(ck, x["ctx"] @ w["text_attention_layer.linear_in.weight"], 2e-5, "ctx_k")
+    close(co, x["ctx"] @ w["text_attention_layer.linear_out.weight"][:, :synth.HID].t(), 2e-5, "ctx_o")
+    qn = torch.empty(B, synth.FEAT, device="cuda")
+    tail = {"is_valid": xc["is_valid"], "feedback": "argmax"}
+    res = ops.follower_step(wc, xc["u_t_prev"], xc["all_u_t"], xc["visual_context"], xc["h_0"], xc["c_0"], xc["ctx"],
+                            xc["ctx_mask"], packed=blob, ctx_proj=(ck, co), q_next=qn, tail=tail)
+    ref = O.attn_decoder_step(x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
+                              x["ctx_mask"], w)
+    for k, v, r in zip(NAMES, res, ref):
+        if k == "logit":
+            close(v.cpu().masked_fill(x["is_valid"] == 0, 0.0), r.masked_fill(x["is_valid"] == 0, 0.0), what="ctxproj:" + k)
+        else:
+            close(v, r, what="ctxproj:" + k)
+    t = ref[0] @ w["visual_attention_layer.linear_in_h.weight"].t() + w["visual_attention_layer.linear_in_h.bias"]
+    close(qn, t @ w["visual_attention_layer.linear_in_v.weight"], 1e-4, "q_next")
+    lr = ref[3].masked_fill(x["is_valid"] == 0, -float("inf"))
+    top = lr.topk(min(2, A), 1)[0]
+    safe = (top[:, 0] - top[:, -1] > 1e-4)
+    assert torch.equal(tail["out"][0].cpu().long()[safe], lr.max(1)[1][safe])
+    # train mode: dropout masks on x and h_1
+    g = torch.Generator().manual_seed(2)
+    drop_x = (torch.rand(B, 2 * synth.FEAT, generator=g) > 0.5).float() * 2.0
+    drop_h = (torch.rand(B, synth.HID, generator=g) > 0.5).float() * 2.0
+    res = ops.follower_step(wc, xc["u_t_prev"], xc["all_u_t"], xc["visual_context"], xc["h_0"], xc["c_0"], xc["ctx"],
+                            xc["ctx_mask"], drop_x.cuda(), drop_h.cuda(), packed=blob, ctx_proj=(ck, co), q_next=qn)
+    ref = O.attn_decoder_step(x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
+                              x["ctx_mask"], w, drop_x, drop_h)
+    for k, v, r in zip(NAMES, res, ref):
+        close(v, r, what="ctxproj-train:" + k)
