@@ -769,8 +769,8 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
     // h_1 directly (scores = (ctx W_in) . h, output = sum alpha (ctx W_out_c^T) = W_out_c wc), so NO projection sits
     // between the LSTM cell and the attention.  hh = W_out_h h is its own small projection that triggers its
     // dependents only after its dependency wait; the attention (which needs nothing from it) then runs CONCURRENTLY
-    // with it and waits for it only at its very end.  h~ = tanh(W_out_c wc + hh) is formed while the g projection
-    // loads its activation operand, and the same launch computes the next step's query from h_1 (extra tiles).
+    // with it and waits for it only before its epilogue, where h~ = tanh(W_out_c wc + hh) is formed.  The g projection
+    // also computes the next step's query from h_1 (extra tiles fed from a second activation source).
     {
       PkParams q{};
       q.a_pk = base + P.a_th + pk_weight_bytes(d.H, P.nkb_h); q.nkb = kblocks(d.H);   // rows of W_out[:, H:2H]
@@ -786,15 +786,16 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
       a.segA = ctx_o; a.strideA_b = (long long)L * d.H; a.strideA_r = d.H; a.lenA = d.H; a.lenB = 0;
       a.keyA = ctx_k; a.strideK_b = (long long)L * d.H; a.strideK_r = d.H;
       a.mask = ctx_mask; a.ldmask = L;
-      a.out = ws.wc; a.ldo = d.H; a.alpha = alpha; a.ldalpha = L;
+      a.out = ws.htilde; a.ldo = d.H; a.alpha = alpha; a.ldalpha = L;
       a.defer_wait = 1;
+      a.post_add = ws.th; a.ld_post = d.H; a.post_tanh = 1;   // h~ = tanh(W_out_c wc + hh), once, in the epilogue
       SFB_PROPAGATE(launch_soft_dot_attention(a, B, ws.at, ws.at_bytes, st));
     }
     {
       PkParams q{};
       q.a_pk = base + P.a_g; q.b_pk = nullptr; q.nkb = kblocks(d.H);
       q.g.nseg = 1;
-      q.g.seg[0] = GemmSeg{ws.wc, d.H, nullptr, nullptr, 0, nullptr, 0, d.H, 0, ws.th, d.H, 1};   // tanh(W_out_c wc + hh)
+      q.g.seg[0] = GemmSeg{ws.htilde, d.H, nullptr, nullptr, 0, nullptr, 0, d.H, 0};
       q.g.M = B; q.g.out = ws.g; q.g.ldo = ws.ldg; q.g.bias0 = b_g;
       const int g_tiles = (d.E + 1 + 127) / 128;
       if (q_next) {   // tiles g_tiles.. = M_q rows, fed with the un-dropped h_1: the next step's visual query

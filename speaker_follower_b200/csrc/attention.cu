@@ -247,6 +247,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
   if (p.alpha)
     for (int i = tid; i < nmine; i += NT)
       p.alpha[(size_t)b * p.ldalpha + rank + CL * i] = sc[i] == -INFINITY ? 0.f : __expf(sc[i] - M) * inv;
+  // grid completion must imply the predecessor's completion; its output (post_add) is consumed right below
+  if (p.defer_wait) pdl_wait();
   {
     const float4* in4 = reinterpret_cast<const float4*>(ring);
     float4* out4 = reinterpret_cast<float4*>(p.out + (size_t)b * p.ldo);
@@ -257,6 +259,11 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
       for (int k = 0; k < CL; ++k) {
         const float4 a = in4[k * cpo + lc];
         o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+      }
+      if (p.post_add) {   // out = f(attention output + post_add): h~ = tanh(W_out_c wc + W_out_h h), model.py:140-142
+        const float4 a = *reinterpret_cast<const float4*>(p.post_add + (size_t)b * p.ld_post + col * 4);
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        if (p.post_tanh) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
       }
       out4[col] = o;
       if (p.pk_out) {   // the same 4 values as bf16 (hi, lo) in the gate GEMM's packed activation operand
@@ -276,7 +283,6 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
       }
     }
   }
-  if (p.defer_wait) pdl_wait();   // grid completion must imply the predecessor's completion (see AttnParams)
   trace_mark(p.trace, 2);
   if (ct && tid == 0) ct[3] = globaltimer_ns();
   if (p.trace && tid == 0 && b == gridDim.y - 1 && rank == CL - 1) p.trace[3] = globaltimer_ns();   // last cluster
@@ -341,6 +347,7 @@ int32_t launch_soft_dot_attention(AttnParams p, int B, void* ws, size_t ws_bytes
   SFB_CHECK_ARG((p.lenA % 4) == 0 && (p.lenB % 4) == 0 && p.lenA + p.lenB == p.D, "bad row segments");
   SFB_CHECK_ARG(p.R >= 1, "need at least one row");
   SFB_CHECK_ARG(B <= 65535, "attention: batch > 65535");
+  SFB_CHECK_ARG(!p.post_add || ((reinterpret_cast<uintptr_t>(p.post_add) & 15u) == 0 && (p.ld_post % 4) == 0), "attention: post_add alignment");
   const int SD = p.keyA ? 2 * p.D : p.D;
   SFB_CHECK_ARG(!p.keyA || p.D <= 1024, "attention: separate key rows are supported for row length <= 1024");
   SFB_CHECK_ARG(!p.keyA || ((reinterpret_cast<uintptr_t>(p.keyA) & 15u) == 0 && (p.strideK_r % 4) == 0 && (p.strideK_b % 4) == 0),

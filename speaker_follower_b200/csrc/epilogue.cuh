@@ -96,6 +96,36 @@ __device__ __forceinline__ void plain_store(const GemmParams& p, int m, int n, f
   p.out[(size_t)m * p.ldo + n] = v;
 }
 
+// Epilogue operands of one float4 group, fetched BEFORE the split-K barrier so that their latency hides behind it.
+struct PlainPre { float4 add; bool ok; };
+__device__ __forceinline__ PlainPre plain_preload(const GemmParams& p, int m, int n) {
+  PlainPre r;
+  r.add = make_float4(0.f, 0.f, 0.f, 0.f);
+  r.ok = false;
+  const bool second = p.out2 && n >= p.n_split;
+  const int n_end = second ? p.N : ((p.out2 && p.n1_valid > 0) ? p.n1_valid : p.N);
+  if (n + 3 >= n_end || p.bias1 || p.oscale) return r;   // rare shapes take the plain path
+  auto ld4 = [](const float* q) { return *reinterpret_cast<const float4*>(q); };
+  if (second) {
+    if (p.bias2) {
+      if (reinterpret_cast<uintptr_t>(p.bias2) & 15u) return r;
+      r.add = ld4(p.bias2 + (n - p.n_split));
+    }
+  } else {
+    if (p.bias0) {
+      if (reinterpret_cast<uintptr_t>(p.bias0) & 15u) return r;
+      r.add = ld4(p.bias0 + n);
+    }
+    if (p.padd) {
+      if ((reinterpret_cast<uintptr_t>(p.padd) & 15u) || (p.ld_padd & 3)) return r;
+      const float4 a = ld4(p.padd + (size_t)m * p.ld_padd + n);
+      r.add.x += a.x; r.add.y += a.y; r.add.z += a.z; r.add.w += a.w;
+    }
+  }
+  r.ok = true;
+  return r;
+}
+
 // four consecutive output features n..n+3 of row m (n % 4 == 0); vector store when the row stride allows it
 __device__ __forceinline__ void plain_store4(const GemmParams& p, int m, int n, float4 v) {
   if (p.out2 && n >= p.n_split) {   // second output (n_split is tile aligned, so a float4 never straddles)
@@ -133,6 +163,69 @@ __device__ __forceinline__ void plain_store4(const GemmParams& p, int m, int n, 
     if (n + 1 < p.N) plain_store(p, m, n + 1, v.y);
     if (n + 2 < p.N) plain_store(p, m, n + 2, v.z);
     if (n + 3 < p.N) plain_store(p, m, n + 3, v.w);
+  }
+}
+
+__device__ __forceinline__ void plain_store4_pre(const GemmParams& p, int m, int n, float4 v, const PlainPre& pre) {
+  if (!pre.ok) { plain_store4(p, m, n, v); return; }
+  const bool second = p.out2 && n >= p.n_split;
+  v.x += pre.add.x; v.y += pre.add.y; v.z += pre.add.z; v.w += pre.add.w;
+  if (!second && p.act == 1) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+  float* dst = second ? p.out2 + (size_t)m * p.ldo2 + (n - p.n_split) : p.out + (size_t)m * p.ldo + n;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    *reinterpret_cast<float4*>(dst) = v;
+  } else {
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+  }
+}
+
+// LSTM epilogue operands of 4 consecutive units, fetched before the split-K barrier
+struct LstmPre { float4 bi, bf, bg, bo, c0, dh; bool ok; };
+__device__ __forceinline__ LstmPre lstm_preload(const GemmParams& p, int m, int unit) {
+  const LstmEpilogue& e = p.lstm;
+  const int H = e.H;
+  LstmPre r;
+  r.ok = !(e.lengths || e.addend || e.seq_out || (H & 3));
+  if (!r.ok) return r;
+  auto ld4 = [](const float* q) { return __ldg(reinterpret_cast<const float4*>(q)); };
+  auto add4 = [](float4 a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; return a; };
+  r.bi = add4(ld4(e.b_ih + unit), ld4(e.b_hh + unit));
+  r.bf = add4(ld4(e.b_ih + H + unit), ld4(e.b_hh + H + unit));
+  r.bg = add4(ld4(e.b_ih + 2 * H + unit), ld4(e.b_hh + 2 * H + unit));
+  r.bo = add4(ld4(e.b_ih + 3 * H + unit), ld4(e.b_hh + 3 * H + unit));
+  const size_t idx = (size_t)m * H + unit;
+  r.c0 = *reinterpret_cast<const float4*>(e.c0 + idx);
+  r.dh = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (e.h1_drop && e.drop_h) r.dh = *reinterpret_cast<const float4*>(e.drop_h + idx);
+  return r;
+}
+__device__ __forceinline__ void lstm_update4_pre(const GemmParams& p, int m, int unit, float4 gi, float4 gf, float4 gg, float4 go,
+                                                 const LstmPre& pre) {
+  if (!pre.ok) { lstm_update4(p, m, unit, gi, gf, gg, go); return; }
+  const LstmEpilogue& e = p.lstm;
+  const int H = e.H;
+  const size_t idx = (size_t)m * H + unit;
+  const float pi[4] = {gi.x + pre.bi.x, gi.y + pre.bi.y, gi.z + pre.bi.z, gi.w + pre.bi.w};
+  const float pf[4] = {gf.x + pre.bf.x, gf.y + pre.bf.y, gf.z + pre.bf.z, gf.w + pre.bf.w};
+  const float pg[4] = {gg.x + pre.bg.x, gg.y + pre.bg.y, gg.z + pre.bg.z, gg.w + pre.bg.w};
+  const float po[4] = {go.x + pre.bo.x, go.y + pre.bo.y, go.z + pre.bo.z, go.w + pre.bo.w};
+  const float cc[4] = {pre.c0.x, pre.c0.y, pre.c0.z, pre.c0.w};
+  float ig[4], fg[4], gt[4], og[4], c1[4], h1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ig[i] = sigmoidf_acc(pi[i]); fg[i] = sigmoidf_acc(pf[i]); gt[i] = tanhf(pg[i]); og[i] = sigmoidf_acc(po[i]);
+    c1[i] = fg[i] * cc[i] + ig[i] * gt[i];
+    h1[i] = og[i] * tanhf(c1[i]);
+  }
+  *reinterpret_cast<float4*>(e.c1 + idx) = make_float4(c1[0], c1[1], c1[2], c1[3]);
+  *reinterpret_cast<float4*>(e.h1 + idx) = make_float4(h1[0], h1[1], h1[2], h1[3]);
+  if (e.h1_drop) *reinterpret_cast<float4*>(e.h1_drop + idx) = make_float4(h1[0] * pre.dh.x, h1[1] * pre.dh.y, h1[2] * pre.dh.z, h1[3] * pre.dh.w);
+  if (e.gates_act) {
+    float* ga = e.gates_act + (size_t)m * 4 * H + unit;
+    *reinterpret_cast<float4*>(ga) = make_float4(ig[0], ig[1], ig[2], ig[3]);
+    *reinterpret_cast<float4*>(ga + H) = make_float4(fg[0], fg[1], fg[2], fg[3]);
+    *reinterpret_cast<float4*>(ga + 2 * H) = make_float4(gt[0], gt[1], gt[2], gt[3]);
+    *reinterpret_cast<float4*>(ga + 3 * H) = make_float4(og[0], og[1], og[2], og[3]);
   }
 }
 

@@ -167,8 +167,6 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
     pdl_wait();
     if (q.late_trigger) pdl_launch_dependents();
     trace_mark(p.trace, 1);
-    if (tid == 0 && S > 1)   // generation of this tile's split-K barrier, read long before it is needed
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(sem_gen) : "l"(q.sem + 2 * (z * tiles + tile) + 1) : "memory");
     if (!B_PACKED) {
       // fp32 activations -> bf16 hi/lo core matrices, one K block per stage of the ring
       const int r_in = lane & 7, kc_in = lane >> 3;
@@ -253,6 +251,8 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
         }
       }
     }
+    if (tid == 0 && S > 1)   // generation of this tile's split-K barrier, read long before it is needed
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(sem_gen) : "l"(q.sem + 2 * (z * tiles + tile) + 1) : "memory");
     if (q.has_side) {   // side job while the tensor core works: pack another operand of the step (grid-strided)
       const long long total = (long long)q.side.ntile * q.side.nkb * q.side.R * 8;
       const long long cta = ((long long)z * S + rank) * tiles + tile, nthreads = (long long)tiles * S * gridDim.z * 256;
@@ -303,6 +303,24 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   trace_mark(p.trace, 5);
   if (!direct) {
+    // epilogue operands of this thread's first-pass elements: requested now, consumed after the barrier
+    const int ncols_e = m_end - m0;
+    LstmPre lpre;
+    PlainPre ppre0, ppre1;
+    lpre.ok = false; ppre0.ok = false; ppre1.ok = false;
+    {
+      if (lstm) {
+        const int total = ncols_e * 8, share = (((total + S - 1) / S) + 7) & ~7;
+        const int e = rank * share + tid;
+        if (e < min(total, rank * share + share)) lpre = lstm_preload(p, m0 + (e >> 3), tile * 32 + (e & 7) * 4);
+      } else {
+        const int total = ncols_e * (PBM / 4), share = (((total + S - 1) / S) + 7) & ~7;
+        const int e_end = min(total, rank * share + share);
+        const int e0 = rank * share + tid, e1 = e0 + 320;
+        if (e0 < e_end) ppre0 = plain_preload(p, m0 + (e0 >> 5), tile * PBM + (e0 & 31) * 4);
+        if (e1 < e_end) ppre1 = plain_preload(p, m0 + (e1 >> 5), tile * PBM + (e1 & 31) * 4);
+      }
+    }
     __threadfence();
     __syncthreads();
     // ---- the S CTAs of this tile meet at a sense-reversing barrier {count, generation} (all co-resident:
@@ -350,7 +368,8 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
             g[gq].x += v.x; g[gq].y += v.y; g[gq].z += v.z; g[gq].w += v.w;
           }
         }
-        lstm_update4(p, m0 + col, tile * 32 + ul, g[0], g[1], g[2], g[3]);
+        if (e == e_beg + tid) lstm_update4_pre(p, m0 + col, tile * 32 + ul, g[0], g[1], g[2], g[3], lpre);
+        else lstm_update4(p, m0 + col, tile * 32 + ul, g[0], g[1], g[2], g[3]);
       }
     } else {
       // float4 = 4 consecutive output features; two groups per thread per pass so all partial loads are in flight
@@ -369,8 +388,13 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
           va.x += x.x; va.y += x.y; va.z += x.z; va.w += x.w;
           vb.x += y.x; vb.y += y.y; vb.z += y.z; vb.w += y.w;
         }
-        plain_store4(p, m0 + (e0 >> 5), tile * PBM + (e0 & 31) * 4, va);
-        if (has1) plain_store4(p, m0 + (e1 >> 5), tile * PBM + (e1 & 31) * 4, vb);
+        if (e0 == e_beg + tid) {
+          plain_store4_pre(p, m0 + (e0 >> 5), tile * PBM + (e0 & 31) * 4, va, ppre0);
+          if (has1) plain_store4_pre(p, m0 + (e1 >> 5), tile * PBM + (e1 & 31) * 4, vb, ppre1);
+        } else {
+          plain_store4(p, m0 + (e0 >> 5), tile * PBM + (e0 & 31) * 4, va);
+          if (has1) plain_store4(p, m0 + (e1 >> 5), tile * PBM + (e1 & 31) * 4, vb);
+        }
       }
     }
     __syncthreads();

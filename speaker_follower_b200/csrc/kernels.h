@@ -51,6 +51,7 @@ struct AttnParams {
   // dependency wait) writes nothing this kernel reads -> run concurrently with it; the dependency wait moves to the end
   // of the kernel so that this grid's completion still implies the predecessor's
   int defer_wait;
+  const float* post_add; int ld_post; int post_tanh;   // out = tanh?(attention output + post_add[b, :]) (read after the wait)
   unsigned long long* cta_trace;          // bring-up: per-CTA {entry, first row landed, stream done, exit, smid}
   unsigned long long* trace;              // bring-up: 3 timestamps of block 0, or NULL
   // filled by the launcher
