@@ -300,27 +300,36 @@ AttnPlan attention_plan(int B, int R, int D, int num_sms, bool kv) {
   AttnPlan pl{};
   // cluster size: the largest CL whose B x CL CTAs are still ONE resident wave, with >= 4 rows per CTA
   const int nt = (kv ? D / 2 : D) <= 512 ? 128 : 256;
-  int best = 1;
-  for (int cl = 8; cl >= 1; cl >>= 1) {
+  // the largest cluster whose B x CL CTAs are ONE resident wave; the ring may shrink (>= 6 rows or all rows) to fit
+  int best = 1, best_st = 4;
+  bool found = false;
+  for (int cl = 8; cl >= 1 && !found; cl >>= 1) {
     if (cl > 1 && R / cl < 4) continue;
+    if (cl == 8 && (long long)B * cl > 2LL * num_sms) continue;   // 8-CTA clusters place badly once the machine is full
     const int rows = (R + cl - 1) / cl;
-    int st = (int)(ATT_RING_BUDGET / ((size_t)D * 4));
-    st = st > rows ? rows : st;
-    st = st > ATT_MAX_STAGES ? ATT_MAX_STAGES : st;
-    st = st < 4 ? 4 : st;
-    const size_t smem = attn_smem_bytes(st, D, rows) + 1024;
-    long long per_sm = (long long)((220 * 1024) / smem);
-    if (per_sm > 2048 / nt) per_sm = 2048 / nt;
-    if (per_sm > 16) per_sm = 16;
-    if (cl == 1 || (long long)B * cl <= per_sm * num_sms) { best = cl; break; }
+    int st_hi = (int)(ATT_RING_BUDGET / ((size_t)D * 4));
+    st_hi = st_hi > rows ? rows : st_hi;
+    st_hi = st_hi > ATT_MAX_STAGES ? ATT_MAX_STAGES : st_hi;
+    st_hi = st_hi < 4 ? 4 : st_hi;
+    int st_lo = rows < 6 ? rows : 6;
+    st_lo = st_lo < 4 ? 4 : st_lo;
+    if (st_lo > st_hi) st_lo = st_hi;
+    for (int st = st_hi; st >= st_lo; --st) {
+      const size_t smem = attn_smem_bytes(st, D, rows) + 1024;
+      long long per_sm = (long long)((220 * 1024) / smem);
+      if (per_sm > 2048 / nt) per_sm = 2048 / nt;
+      if (per_sm > 16) per_sm = 16;
+      // 20 % of the slots stay free: clusters need all their CTAs inside one GPC at once, and a launch that almost fills
+      // the machine leaves some clusters waiting for a second wave (measured: +10 us on the late ones)
+      if (cl == 1 || (long long)B * cl * 5 <= per_sm * num_sms * 4) {
+        best = cl; best_st = st; found = true;
+        break;
+      }
+    }
   }
   pl.split = best;
   pl.rows_per_cta = (R + best - 1) / best;
-  int stages = (int)(ATT_RING_BUDGET / ((size_t)D * 4));
-  if (stages > pl.rows_per_cta) stages = pl.rows_per_cta;
-  if (stages > ATT_MAX_STAGES) stages = ATT_MAX_STAGES;
-  if (stages < 4) stages = 4;   // >= rows per barrier; the ring doubles as the merge inbox (one row + rounding)
-  pl.stages = stages;
+  pl.stages = best_st;
   pl.ticket_bytes = 0;
   pl.bytes = 256;   // no global scratch any more; kept non-zero so workspace carving stays uniform
   return pl;

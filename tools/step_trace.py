@@ -75,3 +75,23 @@ for k in range(n):
     ph = [buf[16 * k + j] for j in range(4, 12)]
     if any(ph):
         print("      phases(us since wait): " + "  ".join("%d:%.2f" % (j + 4, (v - wt) / 1e3) for j, v in enumerate(ph) if v))
+# per-CTA timeline of the LAST attention launch of the step (the text attention)
+import numpy as np
+ops.set_option("trace", 0)
+ops.set_option("cta_trace", 1)
+g2 = torch.cuda.CUDAGraph()          # the trace pointer is a kernel argument: capture again with it set
+with torch.cuda.graph(g2):
+    step(0)
+for _ in range(3): g2.replay()
+torch.cuda.synchronize()
+nb = 4096
+cbuf = (C.c_int64 * (nb * 8))()
+_lib.load().sfb_debug_read_cta_trace(cbuf, nb)
+t = np.array(list(cbuf), dtype=np.int64).reshape(nb, 8)
+t = t[t[:, 0] > 0]
+if len(t):
+    base = np.median(t[:, 0])
+    ent, first, done, ex, qr = [(t[:, k] - base) / 1e3 for k in (0, 1, 2, 3, 5)]
+    ok = t[:, 1] > 0
+    print("text attention CTAs (us rel. to median entry): %d | entry min %.2f max %.2f | q ready med %.2f | first rows med %.2f max %.2f | stream done med %.2f max %.2f | exit med %.2f max %.2f"
+          % (len(t), ent.min(), ent.max(), np.median(qr), np.median(first[ok]), first[ok].max(), np.median(done), done.max(), np.median(ex), ex.max()))
