@@ -24,7 +24,7 @@ unsigned long long* next_trace_slot() {
 
 static unsigned long long* g_cta_buf = nullptr;   // [4096][8]
 static int g_cta_on = 0;
-int g_attn_force_cl = 0;
+int g_attn_force_cl = 0, g_attn_force_stages = 0, g_attn_no_hint = 0;
 unsigned long long* cta_trace_buffer() { return g_cta_on ? g_cta_buf : nullptr; }
 
 int device_num_sms() {
@@ -320,6 +320,8 @@ int32_t sfb_set_option(const char* name, int32_t value) {
   }
   if (n == "tc_debug") { gemm_tc_set_debug(value); return 0; }
   if (n == "attn_cl") { g_attn_force_cl = value; return 0; }
+  if (n == "attn_stages") { g_attn_force_stages = value; return 0; }
+  if (n == "attn_nohint") { g_attn_no_hint = value; return 0; }
   if (n == "cta_trace") {   // per-CTA timeline of the attention kernel (last launch wins)
     g_cta_on = value;
     if (value && !g_cta_buf && cudaMalloc(&g_cta_buf, 4096 * 8 * sizeof(unsigned long long)) != cudaSuccess) return SFB_ERR_CUDA;

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
     __syncwarp();
     ba = (size_t)(p.idxA ? p.idxA[b] : b) * p.strideA_b;
     bb = (size_t)(p.idxB ? p.idxB[b] : b) * p.strideB_b;
-    pol = policy_evict_first();
+    pol = p.no_hint ? policy_evict_normal() : policy_evict_first();
     if (lane < NSTG && lane < n) fetch(lane, lane);
   }
   for (int i = tid; i < nmine; i += NT) sc[i] = -INFINITY;
@@ -369,6 +369,8 @@ int32_t launch_soft_dot_attention(AttnParams p, int B, void* ws, size_t ws_bytes
     st = st > pl.rows_per_cta ? pl.rows_per_cta : st;
     pl.stages = st < 4 ? 4 : (st > ATT_MAX_STAGES ? ATT_MAX_STAGES : st);
   }
+  if (g_attn_force_stages > 0 && g_attn_force_stages <= pl.rows_per_cta) pl.stages = g_attn_force_stages < 4 ? 4 : g_attn_force_stages;
+  p.no_hint = g_attn_no_hint;
   p.cta_trace = (size_t)B * pl.split <= 4096 ? cta_trace_buffer() : nullptr;
   p.rows_per_cta = pl.rows_per_cta;
   p.stages = pl.stages;

@@ -229,4 +229,39 @@ __device__ __forceinline__ void lstm_update4_pre(const GemmParams& p, int m, int
   }
 }
 
+// one hidden unit per thread (all threads busy; operands fetched before the split-K barrier)
+struct LstmPre1 { float bi, bf, bg, bo, c0, dh; bool ok; };
+__device__ __forceinline__ LstmPre1 lstm_preload1(const GemmParams& p, int m, int unit) {
+  const LstmEpilogue& e = p.lstm;
+  const int H = e.H;
+  LstmPre1 r;
+  r.ok = !(e.lengths || e.addend || e.seq_out);
+  if (!r.ok) return r;
+  r.bi = __ldg(e.b_ih + unit) + __ldg(e.b_hh + unit);
+  r.bf = __ldg(e.b_ih + H + unit) + __ldg(e.b_hh + H + unit);
+  r.bg = __ldg(e.b_ih + 2 * H + unit) + __ldg(e.b_hh + 2 * H + unit);
+  r.bo = __ldg(e.b_ih + 3 * H + unit) + __ldg(e.b_hh + 3 * H + unit);
+  const size_t idx = (size_t)m * H + unit;
+  r.c0 = e.c0[idx];
+  r.dh = (e.h1_drop && e.drop_h) ? e.drop_h[idx] : 1.f;
+  return r;
+}
+__device__ __forceinline__ void lstm_update1_pre(const GemmParams& p, int m, int unit, float gi, float gf, float gg, float go,
+                                                 const LstmPre1& pre) {
+  if (!pre.ok) { lstm_update(p, m, unit, gi, gf, gg, go); return; }
+  const LstmEpilogue& e = p.lstm;
+  const int H = e.H;
+  const size_t idx = (size_t)m * H + unit;
+  const float ig = sigmoidf_acc(gi + pre.bi), fg = sigmoidf_acc(gf + pre.bf), gt = tanhf(gg + pre.bg), og = sigmoidf_acc(go + pre.bo);
+  const float c1 = fg * pre.c0 + ig * gt;
+  const float h1 = og * tanhf(c1);
+  e.c1[idx] = c1;
+  e.h1[idx] = h1;
+  if (e.h1_drop) e.h1_drop[idx] = h1 * pre.dh;
+  if (e.gates_act) {
+    float* ga = e.gates_act + (size_t)m * 4 * H + unit;
+    ga[0] = ig; ga[H] = fg; ga[2 * H] = gt; ga[3 * H] = og;
+  }
+}
+
 }  // namespace sfb

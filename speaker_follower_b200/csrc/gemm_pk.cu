@@ -316,14 +316,16 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
   if (!direct) {
     // epilogue operands of this thread's first-pass elements: requested now, consumed after the barrier
     const int ncols_e = m_end - m0;
-    LstmPre lpre;
+    LstmPre1 lpre0, lpre1;
     PlainPre ppre0, ppre1;
-    lpre.ok = false; ppre0.ok = false; ppre1.ok = false;
+    lpre0.ok = false; lpre1.ok = false; ppre0.ok = false; ppre1.ok = false;
     {
       if (lstm) {
-        const int total = ncols_e * 8, share = (((total + S - 1) / S) + 7) & ~7;
-        const int e = rank * share + tid;
-        if (e < min(total, rank * share + share)) lpre = lstm_preload(p, m0 + (e >> 3), tile * 32 + (e & 7) * 4);
+        const int total = ncols_e * 32, share = (((total + S - 1) / S) + 31) & ~31;
+        const int e_end = min(total, rank * share + share);
+        const int e0 = rank * share + tid, e1 = e0 + 320;
+        if (e0 < e_end) lpre0 = lstm_preload1(p, m0 + (e0 >> 5), tile * 32 + (e0 & 31));
+        if (e1 < e_end) lpre1 = lstm_preload1(p, m0 + (e1 >> 5), tile * 32 + (e1 & 31));
       } else {
         const int total = ncols_e * (PBM / 4), share = (((total + S - 1) / S) + 7) & ~7;
         const int e_end = min(total, rank * share + share);
@@ -361,26 +363,34 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
     const float* tbase = q.partial + (size_t)(z * tiles + tile) * S * (size_t)(PBM * NB);
     const size_t pstride = (size_t)PBM * NB;
     if (lstm) {
-      // float4 = 4 consecutive hidden units; the 4 gates of a unit sit 32 rows apart in the tile
-      const int total = ncols * 8, share = (((total + S - 1) / S) + 7) & ~7;
+      // one (batch row, hidden unit) per thread: every thread of the CTA is busy with the transcendental-heavy cell
+      // update; the 4 gates of a unit sit 32 rows apart in the tile; all S x 4 partial loads of a thread are issued
+      // together (predicated full unroll), lanes -> consecutive units (coalesced)
+      const int total = ncols * 32, share = (((total + S - 1) / S) + 31) & ~31;
       const int e_beg = rank * share, e_end = min(total, e_beg + share);
       for (int e = e_beg + tid; e < e_end; e += 320) {
-        const int col = e >> 3, ul = (e & 7) * 4;
+        const int col = e >> 5, ul = e & 31;
         const float* pk = tbase + (size_t)col * PBM + ul;
-        float4 g[4];
+        float v[16][4];
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) g[gq] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int k = 0; k < S; ++k) {
-          const float* pp = pk + (size_t)k * pstride;
+        for (int k = 0; k < 16; ++k) {
+          if (k < S) {
+            const float* pp = pk + (size_t)k * pstride;
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(pp + 32 * gq));
-            g[gq].x += v.x; g[gq].y += v.y; g[gq].z += v.z; g[gq].w += v.w;
+            for (int gq = 0; gq < 4; ++gq) v[k][gq] = __ldcg(pp + 32 * gq);
           }
         }
-        if (e == e_beg + tid) lstm_update4_pre(p, m0 + col, tile * 32 + ul, g[0], g[1], g[2], g[3], lpre);
-        else lstm_update4(p, m0 + col, tile * 32 + ul, g[0], g[1], g[2], g[3]);
+        float g4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (k < S) {
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) g4[gq] += v[k][gq];
+          }
+        const int which = (e - e_beg - tid) / 320;
+        if (which == 0) lstm_update1_pre(p, m0 + col, tile * 32 + ul, g4[0], g4[1], g4[2], g4[3], lpre0);
+        else if (which == 1) lstm_update1_pre(p, m0 + col, tile * 32 + ul, g4[0], g4[1], g4[2], g4[3], lpre1);
+        else lstm_update(p, m0 + col, tile * 32 + ul, g4[0], g4[1], g4[2], g4[3]);
       }
     } else {
       // float4 = 4 consecutive output features; two groups per thread per pass so all partial loads are in flight

@@ -52,6 +52,7 @@ struct AttnParams {
   // of the kernel so that this grid's completion still implies the predecessor's
   int defer_wait;
   const float* post_add; int ld_post; int post_tanh;   // out = tanh?(attention output + post_add[b, :]) (read after the wait)
+  int no_hint;                            // bring-up: plain L2 policy instead of evict-first
   unsigned long long* cta_trace;          // bring-up: per-CTA {entry, first row landed, stream done, exit, smid}
   unsigned long long* trace;              // bring-up: 3 timestamps of block 0, or NULL
   // filled by the launcher
@@ -182,6 +183,6 @@ int32_t launch_follower_tail(const TailParams& p, cudaStream_t stream);
 int device_num_sms();
 unsigned long long* next_trace_slot();
 unsigned long long* cta_trace_buffer();  // NULL unless sfb_set_option("cta_trace", 1)
-extern int g_attn_force_cl;   // NULL unless sfb_set_option("trace", 1)
+extern int g_attn_force_cl, g_attn_force_stages, g_attn_no_hint;   // NULL unless sfb_set_option("trace", 1)
 
 }  // namespace sfb

@@ -24,14 +24,7 @@ def b2b(n=200):
     for i in range(n): run(i + 5)
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) * 1e3 / n
-for cl in (0, 1, 2, 4, 8):
-    ops.set_option("attn_cl", cl)
-    for pdl in (0, 1):
-        ops.set_option("disable_pdl", 1 - pdl)
-        print("attn_cl=%d pdl=%d : %.2f us/launch back-to-back (31.3 MB -> %.0f GB/s)" % (cl, pdl, b2b(), 31.3344 / b2b() * 1e3))
-ops.set_option("disable_pdl", 0)
-for cl in (4, 2, 1):
-    ops.set_option("attn_cl", cl)
+def timeline(tag, cl=4):
     for i in range(3): run(i)
     torch.cuda.synchronize()
     ops.set_option("cta_trace", 1)
@@ -42,8 +35,16 @@ for cl in (4, 2, 1):
     ops.set_option("cta_trace", 0)
     t = np.array(list(buf), dtype=np.int64).reshape(n, 8)
     t0 = t[:, 0].min()
-    ent, first, done, ex, sm, qr = [(t[:, k] - t0) / 1e3 for k in (0, 1, 2, 3, 4, 5)]
-    print("cl=%d: entry  min %.2f med %.2f max %.2f | first-row med %.2f max %.2f | stream-done med %.2f max %.2f | exit med %.2f max %.2f us"
-          % (cl, ent.min(), np.median(ent), ent.max(), np.median(first), first.max(), np.median(done), done.max(), np.median(ex), ex.max()))
-    print("      per-CTA: entry->first %.2f, first->done %.2f, done->exit %.2f (medians); distinct SMs %d" % (
-        np.median(first - ent), np.median(done - first), np.median(ex - done), len(set(t[:, 4].tolist()))))
+    ent, first, done, ex = [(t[:, k] - t0) / 1e3 for k in (0, 1, 2, 3)]
+    print("%-28s b2b %.2f us | entry max %.2f | first-row med %.2f | stream-done med %.2f max %.2f | exit med %.2f max %.2f" % (
+        tag, b2b(), ent.max(), np.median(first), np.median(done), done.max(), np.median(ex), ex.max()))
+ops.set_option("attn_cl", 4)
+for st in (4, 5, 6):
+    for nh in (0, 1):
+        ops.set_option("attn_stages", st); ops.set_option("attn_nohint", nh)
+        timeline("cl=4 stages=%d nohint=%d" % (st, nh))
+ops.set_option("attn_stages", 0); ops.set_option("attn_nohint", 0)
+ops.set_option("attn_cl", 2)
+for st in (6, 8):
+    ops.set_option("attn_stages", st)
+    timeline("cl=2 stages=%d" % st, cl=2)
