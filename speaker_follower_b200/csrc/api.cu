@@ -128,11 +128,11 @@ static FollowerPk layout_follower_pk(const sfb_dims& d) {
   L.a_q = take(pk_weight_bytes(d.F, L.nkb_h));        // one contiguous 2H+F row operand for the fused projection
   L.b_q = take((size_t)d.F * 4);
   L.a_gates = take(pk_weight_bytes(4 * d.H, L.nkb_gates));
-  L.a_wc = take(pk_weight_bytes(d.H, L.nkb_h));
+  L.a_kin = take(pk_weight_bytes(d.H, L.nkb_h));      // W_in^T immediately followed by W_out_c: one operand for the
+  L.a_wc = take(pk_weight_bytes(d.H, L.nkb_h));       // per-episode projection [ctx W_in | ctx W_out_c^T]
   L.a_g = take(pk_weight_bytes(d.E + 1, L.nkb_h));    // M_g (+ constant row) immediately followed by a second copy
   L.a_gq = take(pk_weight_bytes(d.F, L.nkb_h));       // of M_q: one operand for the fused [g | next query] projection
   L.b_g = take((size_t)(d.E + 4) * 4);
-  L.a_kin = take(pk_weight_bytes(d.H, L.nkb_h));      // W_in^T: the per-episode key projection ctx @ W_in
   L.mq = take((size_t)d.F * d.H * 4);
   L.mg = take((size_t)(d.E + 1) * d.H * 4);
   L.bytes = off;
@@ -654,7 +654,8 @@ int32_t sfb_follower_pack_weights(const sfb_dims* dims, const sfb_vis_lstm_weigh
 
 size_t sfb_follower_project_ctx_workspace_bytes(const sfb_dims* dims, int32_t B, int32_t L) {
   if (!dims || B < 1 || L < 1) return 0;
-  return gemm_pk_plan(B * L, dims->H, kblocks(dims->H), false, device_num_sms()).bytes;
+  const int nkb = kblocks(dims->H);
+  return gemm_pk_plan(B * L, 2 * dims->H, nkb, true, device_num_sms()).bytes + ((pk_act_bytes(B * L, nkb) + 255) & ~size_t(255));
 }
 
 int32_t sfb_follower_project_ctx(const sfb_dims* dims, const void* packed, size_t packed_bytes, int32_t B, int32_t L,
@@ -666,19 +667,27 @@ int32_t sfb_follower_project_ctx(const sfb_dims* dims, const void* packed, size_
   SFB_CHECK_ARG(packed && ctx && ctx_k && ctx_o && B >= 1 && L >= 1, "NULL / bad argument");
   const sfb_dims& d = *dims;
   const FollowerPk P = layout_follower_pk(d);
+  SFB_CHECK_ARG(P.a_wc == P.a_kin + pk_weight_bytes(d.H, P.nkb_h), "packed layout: ctx projection operand not contiguous");
   SFB_CHECK_ARG(packed_bytes >= P.bytes && (reinterpret_cast<uintptr_t>(packed) & 255u) == 0, "packed buffer too small / misaligned");
   SFB_PROPAGATE(check_ws(workspace, workspace_bytes, sfb_follower_project_ctx_workspace_bytes(dims, B, L)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned char* base = static_cast<const unsigned char*>(packed);
-  for (int which = 0; which < 2; ++which) {   // ctx_k = ctx W_in (keys of the text attention), ctx_o = ctx W_out_c^T (values)
-    PkParams q{};
-    q.a_pk = base + (which == 0 ? P.a_kin : P.a_wc); q.b_pk = nullptr; q.nkb = kblocks(d.H);
-    q.g.nseg = 1;
-    q.g.seg[0] = GemmSeg{ctx, d.H, nullptr, nullptr, 0, nullptr, 0, d.H, 0};
-    q.g.M = B * L; q.g.N = d.H; q.g.out = which == 0 ? ctx_k : ctx_o; q.g.ldo = d.H;
-    SFB_PROPAGATE(launch_gemm_pk(q, st, workspace, workspace_bytes));
-  }
-  return 0;
+  const int M = B * L, nkb = kblocks(d.H);
+  const PkPlan pl = gemm_pk_plan(M, 2 * d.H, nkb, true, device_num_sms());
+  unsigned char* xpk = static_cast<unsigned char*>(workspace) + pl.bytes;
+  // 1. ctx rows -> bf16 hi/lo operand tiles, once (both projections and all four weight tiles of each share them)
+  PackParams pp{};
+  pp.nseg = 1;
+  pp.seg[0] = PackSeg{ctx, d.H, d.H, nullptr, 0, nullptr};
+  pp.ntile = pl.nz; pp.R = pl.NB; pp.rows_per_tile = pl.rows_per_z; pp.rows_valid = M; pp.lstm_H = 0;
+  pp.out = xpk;
+  SFB_PROPAGATE(launch_pack_rows(pp, st));
+  // 2. [ctx_k | ctx_o] = ctx [W_in | W_out_c^T]: one tcgen05 projection, bulk-copy fed on both operands
+  PkParams q{};
+  q.a_pk = base + P.a_kin; q.b_pk = xpk; q.nkb = nkb;
+  q.g.M = M; q.g.N = 2 * d.H; q.g.out = ctx_k; q.g.ldo = d.H;
+  q.g.n_split = d.H; q.g.out2 = ctx_o; q.g.ldo2 = d.H;
+  return launch_gemm_pk(q, st, workspace, pl.bytes);
 }
 
 int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* wl, const void* packed,

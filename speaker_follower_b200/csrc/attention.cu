@@ -14,9 +14,10 @@
 // moment its row has been consumed, so the stream never drains.  Each thread keeps its slice
 // of the row in registers between the score and the accumulation (a row is read from shared memory once): block-wide
 // dot (warp shuffles + one __syncthreads), online softmax, FMA into the running weighted sum.  The CL partial results
-// (max, sum, weighted sum) are merged INSIDE the cluster through distributed shared memory: stats are read from the
-// peers, every CTA pushes its rescaled partial columns to the column's owner (st.shared::cluster), the owner adds them
-// in rank order and writes the output — no global partial buffer, no atomics, two cluster barriers.  With PDL the
+// (max, sum, weighted sum) are merged INSIDE the cluster through distributed shared memory: every CTA parks its partial
+// in its own ring, one cluster barrier, then the owner of a column block pulls the CL partials and (max, sum) pairs
+// of its columns from the peers (ld.shared::cluster), combines them in rank order and writes the output — no global
+// partial buffer, no atomics; a second barrier only guards the exit.  With PDL the
 // ring is primed before the producer of q has finished.
 #include <cuda_bf16.h>
 
@@ -201,14 +202,25 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
   trace_mark(p.trace, 5);
   if (ct && tid == 0) ct[2] = globaltimer_ns();
 
-  // ---- 4. merge inside the cluster through distributed shared memory
-  if (tid == 0) {
-    stat[0] = m;
-    stat[1] = Z;
+  // ---- 4. merge inside the cluster through distributed shared memory (pull): every CTA parks its un-normalised
+  // partial in its OWN ring (all its rows are consumed), ONE cluster barrier, then the owner of a column block reads
+  // the CL partials of its columns and the CL (max, sum) pairs straight out of the peers' shared memory
+  {
+    float4* mine = reinterpret_cast<float4*>(ring);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int idx = tid + NT * j;
+      if (idx < nvec) mine[idx] = acc[j];
+    }
+    if (tid == 0) {
+      stat[0] = m;
+      stat[1] = Z;
+    }
   }
-  cluster_sync_all();   // stats + scores visible; every CTA of the cluster is done with its ring
+  cluster_sync_all();   // partials, stats and scores of every CTA of the cluster are in place
   trace_mark(p.trace, 6);
   float M = -INFINITY, Zt = 0.f;
+  float wk[8];
   {
     float mk[8], zk[8];
 #pragma unroll
@@ -223,26 +235,15 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
       M = fmaxf(M, mk[k]);
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (mk[k] != -INFINITY) Zt = fmaf(zk[k], __expf(mk[k] - M), Zt);
-  }
-  const float inv = Zt > 0.f ? 1.0f / Zt : 0.f;      // every row masked -> zeros (the reference would give NaN)
-  const float wgt = (m == -INFINITY) ? 0.f : __expf(m - M) * inv;
-  const int cpo = (nvec + CL - 1) / CL;             // float4 columns per owner CTA
-  {
-    const uint32_t inbox = smem_u32(ring);
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int idx = tid + NT * j;
-      if (idx < nvec) {
-        const int owner = idx / cpo, lc = idx - owner * cpo;
-        const uint32_t base = CL > 1 ? dsmem_addr(ring, (uint32_t)owner) : inbox;
-        st_cluster_f32x4(base + (uint32_t)(rank * cpo + lc) * 16u,
-                         make_float4(acc[j].x * wgt, acc[j].y * wgt, acc[j].z * wgt, acc[j].w * wgt));
-      }
+    for (int k = 0; k < 8; ++k) {
+      wk[k] = (mk[k] != -INFINITY) ? __expf(mk[k] - M) : 0.f;
+      Zt = fmaf(zk[k], wk[k], Zt);
     }
   }
-  cluster_sync_all();   // pushed partial columns visible to their owner (no global stores pending: cheap release)
+  const float inv = Zt > 0.f ? 1.0f / Zt : 0.f;      // every row masked -> zeros (the reference would give NaN)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) wk[k] *= inv;
+  const int cpo = (nvec + CL - 1) / CL;             // float4 columns per owner CTA
   trace_mark(p.trace, 7);
   if (p.alpha)
     for (int i = tid; i < nmine; i += NT)
@@ -250,16 +251,21 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
   // grid completion must imply the predecessor's completion; its output (post_add) is consumed right below
   if (p.defer_wait) pdl_wait();
   {
-    const float4* in4 = reinterpret_cast<const float4*>(ring);
     float4* out4 = reinterpret_cast<float4*>(p.out + (size_t)b * p.ldo);
     for (int lc = tid; lc < cpo; lc += NT) {
       const int col = rank * cpo + lc;
       if (col >= nvec) break;
+      float4 pk4[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)   // all peer loads in flight together (rank order = summation order)
+        if (k < CL) pk4[k] = dsmem_ld_f32x4(dsmem_addr(ring, (uint32_t)k) + (uint32_t)col * 16u);
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int k = 0; k < CL; ++k) {
-        const float4 a = in4[k * cpo + lc];
-        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < CL) {
+          o.x = fmaf(wk[k], pk4[k].x, o.x); o.y = fmaf(wk[k], pk4[k].y, o.y);
+          o.z = fmaf(wk[k], pk4[k].z, o.z); o.w = fmaf(wk[k], pk4[k].w, o.w);
+        }
       if (p.post_add) {   // out = f(attention output + post_add): h~ = tanh(W_out_c wc + W_out_h h), model.py:140-142
         const float4 a = *reinterpret_cast<const float4*>(p.post_add + (size_t)b * p.ld_post + col * 4);
         o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
@@ -283,6 +289,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
       }
     }
   }
+  cluster_sync_all();   // nobody leaves while a peer may still read its shared memory
   trace_mark(p.trace, 2);
   if (ct && tid == 0) ct[3] = globaltimer_ns();
   if (p.trace && tid == 0 && b == gridDim.y - 1 && rank == CL - 1) p.trace[3] = globaltimer_ns();   // last cluster

@@ -210,8 +210,11 @@ class Seq2SeqAgent(BaseAgent):
                 if q_next is None or q_next.shape[0] != len(obs):
                     q_next = torch.empty(len(obs), self.decoder.feature_size, device=h_t.device)
                 carry["spare"] = q_in
-            h_t, c_t, alpha, logit, alpha_v = self.decoder.decode_step(u_t_prev, all_u_t, f_t, h_t, c_t, ctx, seq_mask,
-                                                                       tail=tail, q_in=q_in, q_next=q_next)
+            if carry is not None and "ctx_proj" not in carry:      # once per rollout: ctx is constant over its steps
+                carry["ctx_proj"] = self.decoder.project_ctx(ctx)
+            h_t, c_t, alpha, logit, alpha_v = self.decoder.decode_step(
+                u_t_prev, all_u_t, f_t, h_t, c_t, ctx, seq_mask, tail=tail, q_in=q_in, q_next=q_next,
+                ctx_proj=carry.get("ctx_proj") if carry is not None else None)
             if carry is not None:
                 carry["q"] = q_next
             a_t, u_next, score, ce = tail["out"]

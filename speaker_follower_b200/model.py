@@ -155,10 +155,17 @@ class AttnDecoderLSTM(nn.Module):
         reference or a ``(vp_idx, view_idx)`` pair of int tensors when ``self.feature_store`` is set."""
         return self.decode_step(u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask)
 
+    def project_ctx(self, ctx):
+        """Per-episode (ctx W_in, ctx W_out_c^T) for decode_step(ctx_proj=...); None when the packed path is off."""
+        sd = _sd(self)
+        packed = self._packer.get(sd)
+        return ops.follower_project_ctx(sd, packed, ctx.contiguous()) if packed is not None else None
+
     def decode_step(self, u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask=None, tail=None, q_in=None,
-                    q_next=None):
+                    q_next=None, ctx_proj=None):
         """forward() plus the fast-path extras of the packed C ABI (include/sf_b200.h): ``tail`` fuses the rollout
-        tail (follower.py:476-505) behind the logits, ``q_in``/``q_next`` carry the visual query across steps."""
+        tail (follower.py:476-505) behind the logits, ``q_in``/``q_next`` carry the visual query across steps,
+        ``ctx_proj`` = project_ctx(ctx) takes the text-side projections off the step's dependency chain."""
         _no_autograd(u_t_prev, all_u_t, h_0, c_0, ctx, *self.parameters())
         B = h_0.shape[0]
         dev = h_0.device
@@ -169,8 +176,8 @@ class AttnDecoderLSTM(nn.Module):
         packed = self._packer.get(sd)           # None for dimensions the packed path does not cover
         extra = {}
         if packed is not None:
-            extra = dict(packed=packed, tail=tail, q_in=q_in, q_next=q_next)
-        elif tail is not None or q_in is not None or q_next is not None:
+            extra = dict(packed=packed, tail=tail, q_in=q_in, q_next=q_next, ctx_proj=ctx_proj)
+        elif tail is not None or q_in is not None or q_next is not None or ctx_proj is not None:
             raise NotImplementedError("fused tail / carried query need the packed path (H % 128 == 0)")
         if isinstance(visual_context, (tuple, list)):
             vp, view = visual_context

@@ -58,6 +58,65 @@ class FeatureStore:
         self.loc_table = loc_table.contiguous()
         self.img_dim = feat_table.shape[2]
 
+    @classmethod
+    def from_tsv(cls, tsv_paths, loc_table: Tensor, device="cuda", num_views: int = 36, dim: int = 2048,
+                 chunk_rows: int = 512):
+        """Build the device table straight from the reference's precomputed feature files (env.py:350-375:
+        tab-separated scanId, viewpointId, image_w, image_h, vfov, base64(float32[36*2048])); several files are
+        concatenated along the feature axis like MeanPooledImageFeatures does (372-375).  Returns the store; its
+        ``index`` maps "scanId_viewpointId" (env.py:377-378) to the table row, which is what an env puts into
+        ``ob['vp_index']`` so that a step ships two integers instead of a 36 x 2176 slab.  Rows are decoded into a
+        pinned staging buffer and uploaded in chunks: the 3 GB Python dict of the reference never exists."""
+        import base64
+        import csv
+        import numpy as np
+        if isinstance(tsv_paths, str):
+            tsv_paths = [tsv_paths]
+        tsv_paths = sorted(tsv_paths)
+        fields = ["scanId", "viewpointId", "image_w", "image_h", "vfov", "features"]
+        csv.field_size_limit(1 << 30)
+        index, tables = {}, []
+        for fi, path in enumerate(tsv_paths):
+            rows, ids = [], []
+            stage = torch.empty(chunk_rows, num_views, dim, dtype=torch.float32).pin_memory() if torch.cuda.is_available() \
+                else torch.empty(chunk_rows, num_views, dim, dtype=torch.float32)
+            parts, n_in = [], 0
+            with open(path, "rt") as f:
+                for item in csv.DictReader(f, delimiter="\t", fieldnames=fields):
+                    buf = base64.b64decode(item["features"])
+                    feat = np.frombuffer(buf, dtype=np.float32)
+                    if feat.size != num_views * dim:
+                        raise ValueError("%s: feature blob of %s_%s has %d floats, expected %d" % (
+                            path, item["scanId"], item["viewpointId"], feat.size, num_views * dim))
+                    stage[n_in].copy_(torch.from_numpy(feat.reshape(num_views, dim).copy()))
+                    ids.append(item["scanId"] + "_" + item["viewpointId"])
+                    n_in += 1
+                    if n_in == chunk_rows:
+                        parts.append(stage[:n_in].to(device, non_blocking=False).clone())
+                        n_in = 0
+            if n_in:
+                parts.append(stage[:n_in].to(device).clone())
+            table = torch.cat(parts, 0) if parts else torch.empty(0, num_views, dim, device=device)
+            if fi == 0:
+                index = {k: i for i, k in enumerate(ids)}
+                if len(index) != len(ids):
+                    raise ValueError("%s: duplicate scanId_viewpointId" % path)
+            else:   # same viewpoints, possibly another order: align to the first file
+                if set(ids) != set(index):
+                    raise ValueError("%s: viewpoint set differs from %s" % (path, tsv_paths[0]))
+                order = torch.empty(len(ids), dtype=torch.long)
+                for i, k in enumerate(ids):
+                    order[index[k]] = i
+                table = table[order.to(table.device)]
+            tables.append(table)
+        store = cls(torch.cat(tables, 2) if len(tables) > 1 else tables[0], loc_table.to(device))
+        store.index = index
+        return store
+
+    def rows(self, long_ids) -> Tensor:
+        """int32 table rows of "scanId_viewpointId" ids (host list -> device tensor), for vp_idx."""
+        return torch.tensor([self.index[k] for k in long_ids], dtype=torch.int32, device=self.feat_table.device)
+
     def dense(self, vp_idx: Tensor, view_idx: Tensor) -> Tensor:
         """Materialise [B,36,F] (what the reference builds on the host) — for tests only."""
         return torch.cat((self.feat_table[vp_idx.long()], self.loc_table[view_idx.long()]), dim=2).contiguous()

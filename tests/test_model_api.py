@@ -113,3 +113,35 @@ def test_train_mode_dropout_statistics():
         c, d = dec(*args), dec(*args)
         assert not torch.equal(c[3], d[3])
         assert torch.isfinite(c[3]).all()
+
+
+def test_feature_store_from_tsv(tmp_path):
+    """The reference's precomputed-feature TSV (env.py:350-375) -> one contiguous table + index map (SURVEY §8 f-3);
+    CPU-only check of the loader (device='cpu'), two files concatenated along the feature axis like env.py:372-375."""
+    import base64
+    import numpy as np
+    from speaker_follower_b200 import ops
+    rng = np.random.default_rng(0)
+    ids = [("scanA", "vp%02d" % i) for i in range(5)] + [("scanB", "vp00")]
+    feats = {k: rng.standard_normal((36, 2048)).astype(np.float32) for k in ids}
+    feats2 = {k: rng.standard_normal((36, 2048)).astype(np.float32) for k in ids}
+
+    def write(path, table, order):
+        with open(path, "wt") as f:
+            for k in order:
+                f.write("\t".join([k[0], k[1], "640", "480", "60", base64.b64encode(table[k].tobytes()).decode()]) + "\n")
+
+    p1, p2 = str(tmp_path / "a.tsv"), str(tmp_path / "b.tsv")
+    write(p1, feats, ids)
+    write(p2, feats2, ids[::-1])                                  # other file lists the viewpoints in another order
+    loc = torch.zeros(36, 36, 128)
+    store = ops.FeatureStore.from_tsv(p1, loc, device="cpu", chunk_rows=4)
+    assert store.feat_table.shape == (6, 36, 2048) and store.img_dim == 2048
+    for k in ids:
+        assert torch.equal(store.feat_table[store.index[k[0] + "_" + k[1]]], torch.from_numpy(feats[k]))
+    both = ops.FeatureStore.from_tsv([p1, p2], loc, device="cpu", chunk_rows=4)
+    assert both.feat_table.shape == (6, 36, 4096)
+    for k in ids:
+        row = both.feat_table[both.index[k[0] + "_" + k[1]]]
+        assert torch.equal(row[:, :2048], torch.from_numpy(feats[k])) and torch.equal(row[:, 2048:], torch.from_numpy(feats2[k]))
+    assert both.rows(["scanB_vp00", "scanA_vp03"]).tolist() == [5, 3]
