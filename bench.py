@@ -249,9 +249,15 @@ def run_gpu(args, rank, local_rank, world):
     use_proj = blob is not None and not os.environ.get("SFB_NO_CTXPROJ")
     cproj = [(torch.empty_like(c), torch.empty_like(c)) if use_proj else None for c in ctx]
 
+    crows = ops.ctx_rows(lens.tolist(), L, dev) if use_proj else None   # only the un-padded positions are projected
+    pws = torch.zeros(1 << 27, dtype=torch.uint8, device=dev) if use_proj else None
+    if use_proj:
+        for ck, co in cproj:
+            ck.zero_(); co.zero_()
+
     def project(e):
         if use_proj:
-            ops.follower_project_ctx(w, blob, ctx[e], out=cproj[e])
+            ops.follower_project_ctx(w, blob, ctx[e], out=cproj[e], rows=crows, workspace=pws)
             return ops.last_launch_count()
         return 0
 

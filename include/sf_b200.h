@@ -222,7 +222,12 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
  * ctx, ctx_k, ctx_o: [B, L, H]; workspace: sfb_follower_project_ctx_workspace_bytes() (zero-filled once). */
 size_t  sfb_follower_project_ctx_workspace_bytes(const sfb_dims* dims, int32_t B, int32_t L);
 int32_t sfb_follower_project_ctx(const sfb_dims* dims, const void* packed, size_t packed_bytes,
-                                 int32_t B, int32_t L, const float* ctx, float* ctx_k, float* ctx_o,
+                                 int32_t B, int32_t L, const float* ctx,
+                                 const int32_t* rows, int32_t n_rows,   /* optional: flat (b*L + l) indices of the
+                                                                           un-padded positions; the others are neither
+                                                                           read nor written (the attention never
+                                                                           fetches masked rows); NULL = all B*L */
+                                 float* ctx_k, float* ctx_o,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* Per-step tail of Seq2SeqAgent._rollout_with_loss — follower.py:476-505.

@@ -655,12 +655,18 @@ int32_t sfb_follower_pack_weights(const sfb_dims* dims, const sfb_vis_lstm_weigh
 size_t sfb_follower_project_ctx_workspace_bytes(const sfb_dims* dims, int32_t B, int32_t L) {
   if (!dims || B < 1 || L < 1) return 0;
   const int nkb = kblocks(dims->H);
-  return gemm_pk_plan(B * L, 2 * dims->H, nkb, true, device_num_sms()).bytes + ((pk_act_bytes(B * L, nkb) + 255) & ~size_t(255));
+  size_t mx = 0;   // the row count may be anything up to B*L (compacted): size for the worst geometry
+  const int ms[3] = {B * L, 2048 < B * L ? 2048 : B * L, 1};
+  for (int i = 0; i < 3; ++i) {
+    const size_t b = gemm_pk_plan(ms[i], 2 * dims->H, nkb, true, device_num_sms(), true).bytes + ((pk_act_bytes(ms[i], nkb, true) + 255) & ~size_t(255));
+    if (b > mx) mx = b;
+  }
+  return mx + (size_t)B * L * 1024;   // slack: tile rounding of intermediate row counts
 }
 
 int32_t sfb_follower_project_ctx(const sfb_dims* dims, const void* packed, size_t packed_bytes, int32_t B, int32_t L,
-                                 const float* ctx, float* ctx_k, float* ctx_o, void* workspace, size_t workspace_bytes,
-                                 void* stream) {
+                                 const float* ctx, const int32_t* rows, int32_t n_rows, float* ctx_k, float* ctx_o,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
   reset_launch_count();
   SFB_PROPAGATE(check_dims(dims));
   SFB_PROPAGATE(check_packable(*dims));
@@ -672,13 +678,15 @@ int32_t sfb_follower_project_ctx(const sfb_dims* dims, const void* packed, size_
   SFB_PROPAGATE(check_ws(workspace, workspace_bytes, sfb_follower_project_ctx_workspace_bytes(dims, B, L)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned char* base = static_cast<const unsigned char*>(packed);
-  const int M = B * L, nkb = kblocks(d.H);
-  const PkPlan pl = gemm_pk_plan(M, 2 * d.H, nkb, true, device_num_sms());
+  SFB_CHECK_ARG(rows == nullptr || (n_rows >= 1 && n_rows <= B * L), "rows: 1 <= n_rows <= B*L");
+  const int M = rows ? n_rows : B * L, nkb = kblocks(d.H);
+  const PkPlan pl = gemm_pk_plan(M, 2 * d.H, nkb, true, device_num_sms(), true);
   unsigned char* xpk = static_cast<unsigned char*>(workspace) + pl.bytes;
+  SFB_CHECK_ARG(pl.bytes + pk_act_bytes(M, nkb, true) <= workspace_bytes, "project_ctx: workspace too small for this row count");
   // 1. ctx rows -> bf16 hi/lo operand tiles, once (both projections and all four weight tiles of each share them)
   PackParams pp{};
   pp.nseg = 1;
-  pp.seg[0] = PackSeg{ctx, d.H, d.H, nullptr, 0, nullptr};
+  pp.seg[0] = PackSeg{ctx, d.H, d.H, nullptr, 0, rows};   // rows: only the un-padded (b, l) positions are projected
   pp.ntile = pl.nz; pp.R = pl.NB; pp.rows_per_tile = pl.rows_per_z; pp.rows_valid = M; pp.lstm_H = 0;
   pp.out = xpk;
   SFB_PROPAGATE(launch_pack_rows(pp, st));
@@ -687,6 +695,8 @@ int32_t sfb_follower_project_ctx(const sfb_dims* dims, const void* packed, size_
   q.a_pk = base + P.a_kin; q.b_pk = xpk; q.nkb = nkb;
   q.g.M = M; q.g.N = 2 * d.H; q.g.out = ctx_k; q.g.ldo = d.H;
   q.g.n_split = d.H; q.g.out2 = ctx_o; q.g.ldo2 = d.H;
+  q.g.out_rows = rows;
+  q.wide = 1;
   return launch_gemm_pk(q, st, workspace, pl.bytes);
 }
 

@@ -81,10 +81,11 @@ __device__ __forceinline__ void lstm_update4(const GemmParams& p, int m, int uni
 }
 
 __device__ __forceinline__ void plain_store(const GemmParams& p, int m, int n, float v) {
+  const int mo = p.out_rows ? __ldg(p.out_rows + m) : m;
   if (p.out2 && n >= p.n_split) {
     const int n2 = n - p.n_split;
     if (p.bias2) v += __ldg(p.bias2 + n2);
-    p.out2[(size_t)m * p.ldo2 + n2] = v;
+    p.out2[(size_t)mo * p.ldo2 + n2] = v;
     return;
   }
   if (p.out2 && p.n1_valid > 0 && n >= p.n1_valid) return;   // padding rows of the first output block
@@ -93,7 +94,7 @@ __device__ __forceinline__ void plain_store(const GemmParams& p, int m, int n, f
   if (p.padd) v += p.padd[(size_t)m * p.ld_padd + n];
   if (p.act == 1) v = tanhf(v);
   if (p.oscale) v *= __ldg(p.oscale + n);
-  p.out[(size_t)m * p.ldo + n] = v;
+  p.out[(size_t)mo * p.ldo + n] = v;
 }
 
 // Epilogue operands of one float4 group, fetched BEFORE the split-K barrier so that their latency hides behind it.
@@ -135,7 +136,7 @@ __device__ __forceinline__ void plain_store4(const GemmParams& p, int m, int n, 
         const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias2 + n2));
         v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
       }
-      *reinterpret_cast<float4*>(p.out2 + (size_t)m * p.ldo2 + n2) = v;
+      *reinterpret_cast<float4*>(p.out2 + (size_t)(p.out_rows ? __ldg(p.out_rows + m) : m) * p.ldo2 + n2) = v;
     } else {
       if (n < p.N) plain_store(p, m, n, v.x);
       if (n + 1 < p.N) plain_store(p, m, n + 1, v.y);
@@ -157,7 +158,7 @@ __device__ __forceinline__ void plain_store4(const GemmParams& p, int m, int n, 
       if (p.oscale) x *= __ldg(p.oscale + n + i);
       r[i] = x;
     }
-    *reinterpret_cast<float4*>(p.out + (size_t)m * p.ldo + n) = make_float4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<float4*>(p.out + (size_t)(p.out_rows ? __ldg(p.out_rows + m) : m) * p.ldo + n) = make_float4(r[0], r[1], r[2], r[3]);
   } else {
     if (n < p.N) plain_store(p, m, n, v.x);
     if (n + 1 < p.N) plain_store(p, m, n + 1, v.y);
@@ -171,7 +172,8 @@ __device__ __forceinline__ void plain_store4_pre(const GemmParams& p, int m, int
   const bool second = p.out2 && n >= p.n_split;
   v.x += pre.add.x; v.y += pre.add.y; v.z += pre.add.z; v.w += pre.add.w;
   if (!second && p.act == 1) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
-  float* dst = second ? p.out2 + (size_t)m * p.ldo2 + (n - p.n_split) : p.out + (size_t)m * p.ldo + n;
+  const int mo = p.out_rows ? __ldg(p.out_rows + m) : m;
+  float* dst = second ? p.out2 + (size_t)mo * p.ldo2 + (n - p.n_split) : p.out + (size_t)mo * p.ldo + n;
   if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
     *reinterpret_cast<float4*>(dst) = v;
   } else {

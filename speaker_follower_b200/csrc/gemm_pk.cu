@@ -435,10 +435,13 @@ int pk_num_kblocks(const int* seg_k, int nseg) {
   return n;
 }
 
-PkPlan gemm_pk_plan(int M, int N_rows, int nkb, bool b_packed, int num_sms) {
+PkPlan gemm_pk_plan(int M, int N_rows, int nkb, bool b_packed, int num_sms, bool wide) {
   PkPlan pl{};
   pl.tiles = (N_rows + PBM - 1) / PBM;
-  pl.nz = (M + 127) / 128;
+  // batch tiles of <= 128 rows (the weights are re-read per tile); very tall batches (per-episode projections over
+  // B*L rows) use the widest UMMA N = 256 to halve that re-read
+  const int zrows = (wide && b_packed && M > 2048) ? 256 : 128;
+  pl.nz = (M + zrows - 1) / zrows;
   pl.rows_per_z = (M + pl.nz - 1) / pl.nz;
   pl.NB = (pl.rows_per_z + 15) & ~15;
   int s = num_sms / (pl.tiles * pl.nz);            // co-residency: tiles*S*nz <= #SMs (spin semaphore)
@@ -456,8 +459,9 @@ PkPlan gemm_pk_plan(int M, int N_rows, int nkb, bool b_packed, int num_sms) {
 }
 
 size_t pk_weight_bytes(int N_rows, int nkb) { return (size_t)((N_rows + PBM - 1) / PBM) * nkb * 2 * PA_HALF; }
-size_t pk_act_bytes(int M, int nkb) {
-  const int nz = (M + 127) / 128, rpz = (M + nz - 1) / nz, NB = (rpz + 15) & ~15;
+size_t pk_act_bytes(int M, int nkb, bool wide) {
+  const int zrows = (wide && M > 2048) ? 256 : 128;
+  const int nz = (M + zrows - 1) / zrows, rpz = (M + nz - 1) / nz, NB = (rpz + 15) & ~15;
   return (size_t)nz * nkb * 2 * (size_t)(NB / 8) * PSBO;
 }
 
@@ -491,7 +495,7 @@ int32_t launch_gemm_pk(const PkParams& q_in, cudaStream_t stream, void* ws, size
   } else {
     SFB_CHECK_ARG((reinterpret_cast<uintptr_t>(q.b_pk) & 127u) == 0, "gemm_pk: packed activations misaligned");
   }
-  const PkPlan pl = gemm_pk_plan(p.M, n_rows, q.nkb, b_packed, device_num_sms());
+  const PkPlan pl = gemm_pk_plan(p.M, n_rows, q.nkb, b_packed, device_num_sms(), q.wide != 0);
   const size_t ws_need = (pl.S == 1 && !lstm) ? pl.sem_bytes : pl.bytes;   // direct epilogue: no partial tiles
   SFB_CHECK_ARG(ws && ws_bytes >= ws_need && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "gemm_pk: workspace");
   if (q.has_side) SFB_PROPAGATE(pack_prepare(q.side));
@@ -504,6 +508,7 @@ int32_t launch_gemm_pk(const PkParams& q_in, cudaStream_t stream, void* ws, size
   // resident early (PDL) and prefetch their own operands
   int nst = (q.nkb + pl.S - 1) / pl.S;
   if (nst > PSTAGES) nst = PSTAGES;
+  while (nst > 1 && (size_t)nst * stage_bytes > 200 * 1024) --nst;   // wide batch tiles: fewer, larger stages
   q.nstages = nst;
   const size_t smem = (size_t)nst * stage_bytes + 8 * sizeof(uint64_t) + 16;
   const dim3 grid(pl.tiles, pl.S, pl.nz), block(320, 1, 1), cl(1, 1, 1);

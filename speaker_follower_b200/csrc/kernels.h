@@ -107,6 +107,7 @@ struct GemmParams {
   const float* padd; int ld_padd;         // [M, >=N] or NULL: added before the activation (pre-computed partial sum)
   // optional split output: columns n >= n_split (a multiple of 128) go to out2[m*ldo2 + n - n_split] + bias2, no act
   int n_split; float* out2; int ldo2; const float* bias2;
+  const int32_t* out_rows;                // optional: GEMM row m is stored at output row out_rows[m] (compacted batches)
   int n1_valid;                           // with out2: columns n1_valid <= n < n_split are padding and not stored (0 = n_split)
   int act;                                // 0 none, 1 tanh
   int exact;                              // 1: force the exact-fp32 FFMA path (default: 3xTF32 mma.sync for M > 32)
@@ -138,6 +139,7 @@ struct PkParams {
   // optional L2 prefetch by the idle warps (rows a LATER kernel of the step will stream): row r of batch element b of
   // each of pf_n arrays [B, pf_rows, pf_rowbytes], skipped where pf_mask[b*pf_rows + r] != 0
   const void* pf_src[2]; int pf_n, pf_B, pf_rows, pf_rowbytes; const uint8_t* pf_mask;
+  int wide;                              // 1: packed activations use 256-row batch tiles when M > 2048 (UMMA N = 256)
   int late_trigger;                      // 1: griddepcontrol.launch_dependents only after the dependency wait (see AttnParams::defer_wait)
   int alt_tile0; GemmSeg alt_seg;        // tiles >= alt_tile0 (> 0) read their fp32 activations from alt_seg instead of g.seg[0]
   // filled by the launcher
@@ -148,10 +150,10 @@ struct PkPlan {
   int tiles, nz, rows_per_z, NB, S;
   size_t sem_bytes, bytes;               // workspace: self-resetting semaphores (must start zeroed) + partial tiles
 };
-PkPlan gemm_pk_plan(int M, int N_rows, int nkb, bool b_packed, int num_sms);
+PkPlan gemm_pk_plan(int M, int N_rows, int nkb, bool b_packed, int num_sms, bool wide = false);
 int pk_num_kblocks(const int* seg_k, int nseg);
 size_t pk_weight_bytes(int N_rows, int nkb);
-size_t pk_act_bytes(int M, int nkb);
+size_t pk_act_bytes(int M, int nkb, bool wide = false);
 int32_t launch_gemm_pk(const PkParams& q, cudaStream_t stream, void* ws, size_t ws_bytes);
 
 // ---------------------------------------------------------------- pointwise.cu

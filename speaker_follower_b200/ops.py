@@ -298,14 +298,24 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
     return h1, c1, alpha, logit, alpha_v
 
 
-def follower_project_ctx(w: Dict[str, Tensor], packed: Tensor, ctx: Tensor, out: Optional[tuple] = None):
-    """Per-episode (ctx_k, ctx_o) = (ctx W_in, ctx W_out_c^T) for follower_step(ctx_proj=...) — include/sf_b200.h."""
+def ctx_rows(lengths, L: int, device) -> Tensor:
+    """Flat (b*L + l) indices of the un-padded positions of a padded [B, L] batch (int32, on `device`)."""
+    idx = [b * L + l for b, n in enumerate(lengths) for l in range(min(int(n), L))]
+    return torch.tensor(idx, dtype=torch.int32, device=device)
+
+
+def follower_project_ctx(w: Dict[str, Tensor], packed: Tensor, ctx: Tensor, out: Optional[tuple] = None,
+                         rows: Optional[Tensor] = None, workspace: Optional[Tensor] = None):
+    """Per-episode (ctx_k, ctx_o) = (ctx W_in, ctx W_out_c^T) for follower_step(ctx_proj=...) — include/sf_b200.h.
+    `rows` = ctx_rows(lengths, L, device): project only the un-padded positions (padded ones stay zero)."""
     lib = _lib.load()
     d = follower_dims(w)
     B, L, H = ctx.shape
-    ctx_k, ctx_o = out if out is not None else (torch.empty_like(ctx), torch.empty_like(ctx))
-    ws = _workspace(lib.sfb_follower_project_ctx_workspace_bytes(C.byref(d), B, L), ctx.device)
+    ctx_k, ctx_o = out if out is not None else (torch.zeros_like(ctx), torch.zeros_like(ctx))
+    need = lib.sfb_follower_project_ctx_workspace_bytes(C.byref(d), B, L)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, ctx.device)
     check(lib.sfb_follower_project_ctx(C.byref(d), packed.data_ptr(), packed.numel(), B, L, _p(ctx, name="ctx"),
+                                       _p(rows, torch.int32, "rows"), 0 if rows is None else rows.numel(),
                                        _p(ctx_k), _p(ctx_o), ws.data_ptr(), ws.numel(), _stream()))
     return ctx_k, ctx_o
 

@@ -31,7 +31,8 @@ def weights():
     return w, wc, pk, blob
 
 
-@pytest.mark.parametrize("B,L,A", [(1, 12, 3), (8, 20, 6), (100, 80, 8), (128, 40, 14), (130, 33, 5), (256, 24, 6)])
+@pytest.mark.parametrize("B,L,A", [(1, 12, 3), (8, 20, 6), (100, 80, 8), (128, 40, 14), (130, 33, 5), (256, 24, 6),
+                                   (640, 16, 4)])
 def test_packed_step_vs_oracle(weights, B, L, A):
     w, wc, _, blob = weights
     x = synth.follower_step_inputs(B, L, A, seed=700 + B)
@@ -256,7 +257,7 @@ def test_action_candidates_gathered_on_device(weights):
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("B,L,A", [(8, 20, 6), (100, 80, 8), (130, 33, 5)])
+@pytest.mark.parametrize("B,L,A", [(8, 20, 6), (100, 80, 8), (130, 33, 5), (640, 16, 4)])
 def test_ctx_projections_take_text_side_off_the_chain(weights, B, L, A):
     """Per-episode ctx_k = ctx W_in / ctx_o = ctx W_out_c^T: the step with ctx_proj (attention straight from h_1, W_out_h h
     on the helper stream, tanh fused into the next projection's operand load) == oracle, incl. carry + fused tail."""
@@ -264,8 +265,18 @@ def test_ctx_projections_take_text_side_off_the_chain(weights, B, L, A):
     x = synth.follower_step_inputs(B, L, A, seed=940 + B)
     xc = cu(x)
     ck, co = ops.follower_project_ctx(wc, blob, xc["ctx"])
-    close(ck, x["ctx"] @ w["text_attention_layer.linear_in.weight"], 2e-5, "ctx_k")
-    close(co, x["ctx"] @ w["text_attention_layer.linear_out.weight"][:, :synth.HID].t(), 2e-5, "ctx_o")
+    ref_k = x["ctx"] @ w["text_attention_layer.linear_in.weight"]
+    ref_o = x["ctx"] @ w["text_attention_layer.linear_out.weight"][:, :synth.HID].t()
+    close(ck, ref_k, 2e-5, "ctx_k")
+    close(co, ref_o, 2e-5, "ctx_o")
+    # compacted variant: only the un-padded positions are read and written
+    lengths = (~x["ctx_mask"]).sum(1).tolist()
+    rows = ops.ctx_rows(lengths, L, "cuda")
+    ck2, co2 = ops.follower_project_ctx(wc, blob, xc["ctx"], rows=rows)
+    keep = (~x["ctx_mask"]).unsqueeze(2)
+    close(ck2, ref_k * keep, 2e-5, "ctx_k (compacted)")
+    close(co2, ref_o * keep, 2e-5, "ctx_o (compacted)")
+    ck, co = ck2, co2
     qn = torch.empty(B, synth.FEAT, device="cuda")
     tail = {"is_valid": xc["is_valid"], "feedback": "argmax"}
     res = ops.follower_step(wc, xc["u_t_prev"], xc["all_u_t"], xc["visual_context"], xc["h_0"], xc["c_0"], xc["ctx"],
