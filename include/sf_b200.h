@@ -161,7 +161,8 @@ int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
  * sfb_follower_step_packed_fwd then runs the step as: [q projection ->] attention gather (+ packs the gate GEMM's
  * activations) -> gate GEMM + LSTM cell -> [t | W_out_h h | next q] projection -> text attention -> h~ projection
  * -> g projection -> action logits [+ rollout tail] (7-8 launches, all projections on tcgen05 fed by bulk async
- * copies).  Same arguments, outputs and workspace as sfb_follower_step_fwd; `wl` is still needed for the LSTM
+ * copies); with ctx_k/ctx_o: ... -> gate GEMM + LSTM cell -> W_out_h h || text attention (forms h~) -> [g | next q]
+ * -> action logits + tail (6 launches).  Same arguments, outputs and workspace as sfb_follower_step_fwd; `wl` is still needed for the LSTM
  * biases.  Requires H % 128 == 0 and E, F % 8 == 0 (sfb_follower_packed_bytes returns 0 otherwise -> use
  * sfb_follower_step_fwd).  Three optional extras, all NULL-able:
  *   q_in   [B,F]: the visual query W_v^T (W_h h0 + b_h) of THIS step if the caller already has it (the q_next of the
