@@ -25,6 +25,7 @@ unsigned long long* next_trace_slot() {
 static unsigned long long* g_cta_buf = nullptr;   // [4096][8]
 static int g_cta_on = 0;
 int g_attn_force_cl = 0, g_attn_force_stages = 0, g_attn_no_hint = 0;
+static int g_q_with_hh = 0;
 unsigned long long* cta_trace_buffer() { return g_cta_on ? g_cta_buf : nullptr; }
 
 int device_num_sms() {
@@ -98,8 +99,8 @@ static FollowerWs carve_follower(const sfb_dims& d, int B, int L, int A, void* w
     const int sms = device_num_sms();
     const int nkb_h = kblocks(d.H), nkb_g = kblocks(d.E) + kblocks(d.F) + kblocks(d.H);
     size_t mx = gemm_pk_plan(B, 4 * d.H, nkb_g, true, sms).bytes;
-    const int rows[6] = {d.F, 2 * d.H, d.H, d.E + 1, 2 * d.H + d.F, ((d.E + 1 + 127) / 128) * 128 + d.F};
-    for (int i = 0; i < 6; ++i) {
+    const int rows[7] = {d.F, 2 * d.H, d.H, d.E + 1, 2 * d.H + d.F, ((d.E + 1 + 127) / 128) * 128 + d.F, d.H + d.F};
+    for (int i = 0; i < 7; ++i) {
       const size_t b = gemm_pk_plan(B, rows[i], nkb_h, false, sms).bytes;
       if (b > mx) mx = b;
     }
@@ -321,6 +322,7 @@ int32_t sfb_set_option(const char* name, int32_t value) {
   if (n == "tc_debug") { gemm_tc_set_debug(value); return 0; }
   if (n == "attn_cl") { g_attn_force_cl = value; return 0; }
   if (n == "attn_stages") { g_attn_force_stages = value; return 0; }
+  if (n == "q_with_hh") { g_q_with_hh = value; return 0; }
   if (n == "attn_nohint") { g_attn_no_hint = value; return 0; }
   if (n == "cta_trace") {   // per-CTA timeline of the attention kernel (last launch wins)
     g_cta_on = value;
@@ -792,12 +794,19 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
     // dependents only after its dependency wait; the attention (which needs nothing from it) then runs CONCURRENTLY
     // with it and waits for it only before its epilogue, where h~ = tanh(W_out_c wc + hh) is formed.  The g projection
     // also computes the next step's query from h_1 (extra tiles fed from a second activation source).
+    const bool q_with_hh = g_q_with_hh != 0;   // where the next step's query is computed: with hh (off the chain) or with g
     {
       PkParams q{};
-      q.a_pk = base + P.a_th + pk_weight_bytes(d.H, P.nkb_h); q.nkb = kblocks(d.H);   // rows of W_out[:, H:2H]
+      q.a_pk = base + P.a_th + pk_weight_bytes(d.H, P.nkb_h); q.nkb = kblocks(d.H);   // rows [W_out[:, H:2H] ; M_q]
       q.g.nseg = 1;
       q.g.seg[0] = GemmSeg{ws.h1d, d.H, nullptr, nullptr, 0, nullptr, 0, d.H, 0};
       q.g.M = B; q.g.N = d.H; q.g.out = ws.th; q.g.ldo = d.H;
+      if (q_next && q_with_hh) {   // tiles H/128.. = M_q rows fed with the un-dropped h_1
+        q.g.N = d.H + d.F;
+        q.g.n_split = d.H; q.g.out2 = q_next; q.g.ldo2 = d.F; q.g.bias2 = b_q;
+        q.alt_tile0 = d.H / 128;
+        q.alt_seg = GemmSeg{h1, d.H, nullptr, nullptr, 0, nullptr, 0, d.H, 0};
+      }
       q.late_trigger = 1;
       SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));
     }
@@ -819,7 +828,7 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
       q.g.seg[0] = GemmSeg{ws.htilde, d.H, nullptr, nullptr, 0, nullptr, 0, d.H, 0};
       q.g.M = B; q.g.out = ws.g; q.g.ldo = ws.ldg; q.g.bias0 = b_g;
       const int g_tiles = (d.E + 1 + 127) / 128;
-      if (q_next) {   // tiles g_tiles.. = M_q rows, fed with the un-dropped h_1: the next step's visual query
+      if (q_next && !q_with_hh) {   // tiles g_tiles.. = M_q rows, fed with the un-dropped h_1: the next step's visual query
         SFB_CHECK_ARG(P.a_gq == P.a_g + pk_weight_bytes(d.E + 1, P.nkb_h), "packed layout: g / q operand not contiguous");
         q.g.N = g_tiles * 128 + d.F;
         q.g.n_split = g_tiles * 128; q.g.n1_valid = d.E + 1; q.g.out2 = q_next; q.g.ldo2 = d.F; q.g.bias2 = b_q;

@@ -16,9 +16,15 @@ from ._lib import (Dims, EncoderWeights, ScoringWeights, SoftDotWeights, Speaker
 Tensor = torch.Tensor
 
 
-def _p(t: Optional[Tensor], dtype=torch.float32, name="tensor") -> Optional[int]:
+def _p(t: Optional[Tensor], dtype=torch.float32, name="tensor", pinned_ok: bool = False) -> Optional[int]:
     if t is None:
         return None
+    if pinned_ok and not t.is_cuda and t.is_pinned():
+        # page-locked host memory is device-accessible at the same address (UVA): small step inputs / results can be
+        # read / written by the kernels directly over PCIe instead of through a separate memcpy node
+        if t.dtype != dtype or not t.is_contiguous():
+            raise _lib.SfbError("%s must be contiguous %s" % (name, dtype))
+        return t.data_ptr()
     if not t.is_cuda:
         raise _lib.SfbError("%s must be a CUDA tensor (sf_b200 has no CPU path)" % name)
     if t.dtype != dtype:
@@ -270,7 +276,8 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
             a_t, u_next, score, ce = tail["out"]
             tl = _lib.StepTail(_p(tail["is_valid"], name="is_valid"), _p(tgt, torch.int32, "target"),
                                {"teacher": 0, "argmax": 1, "sample": 2}[tail["feedback"]],
-                               _p(tail.get("sample_u"), name="sample_u"), _p(a_t, torch.int32), _p(u_next), _p(score),
+                               _p(tail.get("sample_u"), name="sample_u"), _p(a_t, torch.int32, "a_t", pinned_ok=True),
+                               _p(u_next), _p(score),
                                _p(ce))
             keep.append(tgt)
         act = None
