@@ -30,10 +30,6 @@ namespace {
 constexpr int ATT_MAX_STAGES = 32;            // ring depth (one lane of warp 0 per stage when priming)
 constexpr size_t ATT_RING_BUDGET = 52 * 1024;  // bytes of ring per CTA -> 4 CTAs per SM (6 slab rows each)
 
-__device__ __forceinline__ void st_cluster_f32x4(uint32_t addr, const float4& v) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
-}
 }  // namespace
 
 // NJ float4 slices per thread, NT threads per CTA (D <= NJ * NT * 4), RB rows consumed per block barrier

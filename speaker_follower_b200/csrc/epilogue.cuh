@@ -37,49 +37,6 @@ __device__ __forceinline__ void lstm_update(const GemmParams& p, int m, int unit
   }
 }
 
-// four consecutive hidden units (unit % 4 == 0): 128-bit loads/stores when H % 4 == 0 and no sequence mode
-__device__ __forceinline__ void lstm_update4(const GemmParams& p, int m, int unit, float4 gi, float4 gf, float4 gg, float4 go) {
-  const LstmEpilogue& e = p.lstm;
-  const int H = e.H;
-  if (e.lengths || e.addend || e.seq_out || (H & 3)) {
-    lstm_update(p, m, unit + 0, gi.x, gf.x, gg.x, go.x);
-    lstm_update(p, m, unit + 1, gi.y, gf.y, gg.y, go.y);
-    lstm_update(p, m, unit + 2, gi.z, gf.z, gg.z, go.z);
-    lstm_update(p, m, unit + 3, gi.w, gf.w, gg.w, go.w);
-    return;
-  }
-  auto ld4 = [](const float* q) { return __ldg(reinterpret_cast<const float4*>(q)); };
-  const float4 bi0 = ld4(e.b_ih + unit), bi1 = ld4(e.b_hh + unit), bf0 = ld4(e.b_ih + H + unit), bf1 = ld4(e.b_hh + H + unit);
-  const float4 bg0 = ld4(e.b_ih + 2 * H + unit), bg1 = ld4(e.b_hh + 2 * H + unit), bo0 = ld4(e.b_ih + 3 * H + unit),
-               bo1 = ld4(e.b_hh + 3 * H + unit);
-  const size_t idx = (size_t)m * H + unit;
-  const float4 c0 = *reinterpret_cast<const float4*>(e.c0 + idx);
-  float4 dh = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (e.h1_drop && e.drop_h) dh = *reinterpret_cast<const float4*>(e.drop_h + idx);
-  const float pi[4] = {gi.x + bi0.x + bi1.x, gi.y + bi0.y + bi1.y, gi.z + bi0.z + bi1.z, gi.w + bi0.w + bi1.w};
-  const float pf[4] = {gf.x + bf0.x + bf1.x, gf.y + bf0.y + bf1.y, gf.z + bf0.z + bf1.z, gf.w + bf0.w + bf1.w};
-  const float pg[4] = {gg.x + bg0.x + bg1.x, gg.y + bg0.y + bg1.y, gg.z + bg0.z + bg1.z, gg.w + bg0.w + bg1.w};
-  const float po[4] = {go.x + bo0.x + bo1.x, go.y + bo0.y + bo1.y, go.z + bo0.z + bo1.z, go.w + bo0.w + bo1.w};
-  const float cc[4] = {c0.x, c0.y, c0.z, c0.w};
-  float ig[4], fg[4], gt[4], og[4], c1[4], h1[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    ig[i] = sigmoidf_acc(pi[i]); fg[i] = sigmoidf_acc(pf[i]); gt[i] = tanhf(pg[i]); og[i] = sigmoidf_acc(po[i]);
-    c1[i] = fg[i] * cc[i] + ig[i] * gt[i];
-    h1[i] = og[i] * tanhf(c1[i]);
-  }
-  *reinterpret_cast<float4*>(e.c1 + idx) = make_float4(c1[0], c1[1], c1[2], c1[3]);
-  *reinterpret_cast<float4*>(e.h1 + idx) = make_float4(h1[0], h1[1], h1[2], h1[3]);
-  if (e.h1_drop) *reinterpret_cast<float4*>(e.h1_drop + idx) = make_float4(h1[0] * dh.x, h1[1] * dh.y, h1[2] * dh.z, h1[3] * dh.w);
-  if (e.gates_act) {
-    float* ga = e.gates_act + (size_t)m * 4 * H + unit;
-    *reinterpret_cast<float4*>(ga) = make_float4(ig[0], ig[1], ig[2], ig[3]);
-    *reinterpret_cast<float4*>(ga + H) = make_float4(fg[0], fg[1], fg[2], fg[3]);
-    *reinterpret_cast<float4*>(ga + 2 * H) = make_float4(gt[0], gt[1], gt[2], gt[3]);
-    *reinterpret_cast<float4*>(ga + 3 * H) = make_float4(og[0], og[1], og[2], og[3]);
-  }
-}
-
 __device__ __forceinline__ void plain_store(const GemmParams& p, int m, int n, float v) {
   const int mo = p.out_rows ? __ldg(p.out_rows + m) : m;
   if (p.out2 && n >= p.n_split) {
@@ -178,56 +135,6 @@ __device__ __forceinline__ void plain_store4_pre(const GemmParams& p, int m, int
     *reinterpret_cast<float4*>(dst) = v;
   } else {
     dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-  }
-}
-
-// LSTM epilogue operands of 4 consecutive units, fetched before the split-K barrier
-struct LstmPre { float4 bi, bf, bg, bo, c0, dh; bool ok; };
-__device__ __forceinline__ LstmPre lstm_preload(const GemmParams& p, int m, int unit) {
-  const LstmEpilogue& e = p.lstm;
-  const int H = e.H;
-  LstmPre r;
-  r.ok = !(e.lengths || e.addend || e.seq_out || (H & 3));
-  if (!r.ok) return r;
-  auto ld4 = [](const float* q) { return __ldg(reinterpret_cast<const float4*>(q)); };
-  auto add4 = [](float4 a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; return a; };
-  r.bi = add4(ld4(e.b_ih + unit), ld4(e.b_hh + unit));
-  r.bf = add4(ld4(e.b_ih + H + unit), ld4(e.b_hh + H + unit));
-  r.bg = add4(ld4(e.b_ih + 2 * H + unit), ld4(e.b_hh + 2 * H + unit));
-  r.bo = add4(ld4(e.b_ih + 3 * H + unit), ld4(e.b_hh + 3 * H + unit));
-  const size_t idx = (size_t)m * H + unit;
-  r.c0 = *reinterpret_cast<const float4*>(e.c0 + idx);
-  r.dh = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (e.h1_drop && e.drop_h) r.dh = *reinterpret_cast<const float4*>(e.drop_h + idx);
-  return r;
-}
-__device__ __forceinline__ void lstm_update4_pre(const GemmParams& p, int m, int unit, float4 gi, float4 gf, float4 gg, float4 go,
-                                                 const LstmPre& pre) {
-  if (!pre.ok) { lstm_update4(p, m, unit, gi, gf, gg, go); return; }
-  const LstmEpilogue& e = p.lstm;
-  const int H = e.H;
-  const size_t idx = (size_t)m * H + unit;
-  const float pi[4] = {gi.x + pre.bi.x, gi.y + pre.bi.y, gi.z + pre.bi.z, gi.w + pre.bi.w};
-  const float pf[4] = {gf.x + pre.bf.x, gf.y + pre.bf.y, gf.z + pre.bf.z, gf.w + pre.bf.w};
-  const float pg[4] = {gg.x + pre.bg.x, gg.y + pre.bg.y, gg.z + pre.bg.z, gg.w + pre.bg.w};
-  const float po[4] = {go.x + pre.bo.x, go.y + pre.bo.y, go.z + pre.bo.z, go.w + pre.bo.w};
-  const float cc[4] = {pre.c0.x, pre.c0.y, pre.c0.z, pre.c0.w};
-  float ig[4], fg[4], gt[4], og[4], c1[4], h1[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    ig[i] = sigmoidf_acc(pi[i]); fg[i] = sigmoidf_acc(pf[i]); gt[i] = tanhf(pg[i]); og[i] = sigmoidf_acc(po[i]);
-    c1[i] = fg[i] * cc[i] + ig[i] * gt[i];
-    h1[i] = og[i] * tanhf(c1[i]);
-  }
-  *reinterpret_cast<float4*>(e.c1 + idx) = make_float4(c1[0], c1[1], c1[2], c1[3]);
-  *reinterpret_cast<float4*>(e.h1 + idx) = make_float4(h1[0], h1[1], h1[2], h1[3]);
-  if (e.h1_drop) *reinterpret_cast<float4*>(e.h1_drop + idx) = make_float4(h1[0] * pre.dh.x, h1[1] * pre.dh.y, h1[2] * pre.dh.z, h1[3] * pre.dh.w);
-  if (e.gates_act) {
-    float* ga = e.gates_act + (size_t)m * 4 * H + unit;
-    *reinterpret_cast<float4*>(ga) = make_float4(ig[0], ig[1], ig[2], ig[3]);
-    *reinterpret_cast<float4*>(ga + H) = make_float4(fg[0], fg[1], fg[2], fg[3]);
-    *reinterpret_cast<float4*>(ga + 2 * H) = make_float4(gt[0], gt[1], gt[2], gt[3]);
-    *reinterpret_cast<float4*>(ga + 3 * H) = make_float4(og[0], og[1], og[2], og[3]);
   }
 }
 

@@ -253,17 +253,6 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
     }
     if (tid == 0 && S > 1)   // generation of this tile's split-K barrier, read long before it is needed
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(sem_gen) : "l"(q.sem + 2 * (z * tiles + tile) + 1) : "memory");
-    if (q.pf_n > 0) {   // warm L2 with rows a later kernel of this step streams (step inputs: safe before any wait)
-      const long long total = (long long)q.pf_B * q.pf_rows;
-      const long long cta = ((long long)z * S + rank) * tiles + tile, nthreads = (long long)tiles * S * gridDim.z * 256;
-      for (long long r = cta * 256 + tid; r < total; r += nthreads) {
-        if (q.pf_mask && q.pf_mask[r]) continue;
-        for (int a = 0; a < q.pf_n; ++a)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(static_cast<const char*>(q.pf_src[a]) + r * q.pf_rowbytes),
-                       "r"(q.pf_rowbytes)
-                       : "memory");
-      }
-    }
     if (q.has_side) {   // side job while the tensor core works: pack another operand of the step (grid-strided)
       const long long total = (long long)q.side.ntile * q.side.nkb * q.side.R * 8;
       const long long cta = ((long long)z * S + rank) * tiles + tile, nthreads = (long long)tiles * S * gridDim.z * 256;

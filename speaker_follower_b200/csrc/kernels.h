@@ -136,9 +136,6 @@ struct PkParams {
   const unsigned char* b_pk;             // packed activations [nz][nkb][2*NB*128 B] or NULL
   int nkb;                               // 64-wide K blocks (all segments)
   int has_side; PackParams side;         // optional side job for the otherwise idle warps: pack another operand
-  // optional L2 prefetch by the idle warps (rows a LATER kernel of the step will stream): row r of batch element b of
-  // each of pf_n arrays [B, pf_rows, pf_rowbytes], skipped where pf_mask[b*pf_rows + r] != 0
-  const void* pf_src[2]; int pf_n, pf_B, pf_rows, pf_rowbytes; const uint8_t* pf_mask;
   int wide;                              // 1: packed activations use 256-row batch tiles when M > 2048 (UMMA N = 256)
   int late_trigger;                      // 1: griddepcontrol.launch_dependents only after the dependency wait (see AttnParams::defer_wait)
   int alt_tile0; GemmSeg alt_seg;        // tiles >= alt_tile0 (> 0) read their fp32 activations from alt_seg instead of g.seg[0]

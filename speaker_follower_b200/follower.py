@@ -201,6 +201,13 @@ class Seq2SeqAgent(BaseAgent):
         f_t = self._feature_variables(obs)[0]
         all_u_t, is_valid, _ = self._action_variable(obs)
         su = self._sample_uniform(len(obs), h_t.device) if feedback == "sample" else None
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.decoder.parameters()):
+            # training: the decoder call is autograd-aware; the CE terms must be differentiable w.r.t. the logits
+            from . import _functional as Fn
+            h_t, c_t, alpha, logit, alpha_v = self.decoder(u_t_prev, all_u_t, f_t, h_t, c_t, ctx, seq_mask)
+            ce = Fn.tail_loss_terms(logit, is_valid, target) if target is not None else None
+            a_t, u_next, score, _ = ops.follower_tail(logit.detach().clone(), is_valid, all_u_t, feedback, target=target, sample_u=su)
+            return h_t, c_t, alpha, logit, a_t, u_next, score, ce
         if getattr(self.decoder, "supports_fused_step", False):
             tail = {"is_valid": is_valid, "feedback": feedback, "target": target, "sample_u": su}
             q_in = q_next = None
@@ -268,7 +275,7 @@ class Seq2SeqAgent(BaseAgent):
                     ended[i] = True
             if ended.all():
                 break
-        self.losses.append(float(self.loss))
+        self.losses.append(float(self.loss.detach()) if torch.is_tensor(self.loss) else float(self.loss))
         return traj
 
     def _score_obs_actions_and_instructions(self, path_obs, path_actions, encoded_instructions):
@@ -536,7 +543,7 @@ class Seq2SeqAgent(BaseAgent):
             encoder_optimizer.zero_grad()
             decoder_optimizer.zero_grad()
             self._rollout_with_loss()
-            self.loss.backward()          # raises while the modules are forward-only
+            self.loss.backward()          # gradients: torch autograd over the device-side restatement
             encoder_optimizer.step()
             decoder_optimizer.step()
 

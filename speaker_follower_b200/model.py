@@ -23,14 +23,15 @@ from typing import List, Optional
 import torch
 import torch.nn as nn
 
+from . import _functional as Fn
 from . import ops
 
 
 def _no_autograd(*tensors):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
         raise NotImplementedError(
-            "speaker_follower_b200: backward kernels are not part of this round; call under torch.no_grad() "
-            "(inference, scoring, search) or use the reference modules for training")
+            "speaker_follower_b200: this attention sub-module is forward-only when called on its own; call it under "
+            "torch.no_grad(), or go through AttnDecoderLSTM / SpeakerDecoderLSTM, which are differentiable")
 
 
 def _sd(module: nn.Module):
@@ -76,7 +77,8 @@ class EncoderLSTM(nn.Module):
 
     def forward(self, inputs, lengths):
         """inputs [B, seq_len] int64 (length-sorted, model.py:89), lengths list -> (ctx, decoder_init, c_t)."""
-        _no_autograd(*[p for p in self.parameters()])
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_autograd(inputs, lengths)
         B = inputs.size(0)
         maxlen = int(max(int(x) for x in lengths))
         drop_e = None
@@ -87,6 +89,24 @@ class EncoderLSTM(nn.Module):
         if m is not None:
             ctx = ctx * m                                     # model.py:102
         return ctx, decoder_init, c_t
+
+
+    def _forward_autograd(self, inputs, lengths):
+        """Training: the once-per-rollout encoder runs on torch's own LSTM (cuDNN) so that autograd reaches its weights
+        — model.py:81-104 verbatim; the inference path above stays on the sm_100a kernels."""
+        embeds = self.embedding(inputs)
+        if not self.use_glove:
+            embeds = self.drop(embeds)
+        packed = nn.utils.rnn.pack_padded_sequence(embeds, [int(x) for x in lengths], batch_first=True)
+        enc_h, (enc_h_t, enc_c_t) = self.lstm(packed)
+        if self.num_directions == 2:
+            h_t = torch.cat((enc_h_t[-1], enc_h_t[-2]), 1)
+            c_t = torch.cat((enc_c_t[-1], enc_c_t[-2]), 1)
+        else:
+            h_t, c_t = enc_h_t[-1], enc_c_t[-1]
+        decoder_init = torch.tanh(self.encoder2decoder(h_t))
+        ctx, _ = nn.utils.rnn.pad_packed_sequence(enc_h, batch_first=True)
+        return self.drop(ctx), decoder_init, c_t
 
 
 class SoftDotAttention(nn.Module):
@@ -166,13 +186,14 @@ class AttnDecoderLSTM(nn.Module):
         """forward() plus the fast-path extras of the packed C ABI (include/sf_b200.h): ``tail`` fuses the rollout
         tail (follower.py:476-505) behind the logits, ``q_in``/``q_next`` carry the visual query across steps,
         ``ctx_proj`` = project_ctx(ctx) takes the text-side projections off the step's dependency chain."""
-        _no_autograd(u_t_prev, all_u_t, h_0, c_0, ctx, *self.parameters())
         B = h_0.shape[0]
         dev = h_0.device
         drop_x = self._drop.mask(self.training, (B, self.embedding_size + self.feature_size), dev)
         drop_h = self._drop.mask(self.training, (B, self.hidden_size), dev)
         u_t_prev = u_t_prev.contiguous()        # u_begin.expand(B, -1) is a stride-0 view (follower.py:462)
         sd = _sd(self)
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (u_t_prev, all_u_t, h_0, c_0, ctx, *sd.values())):
+            return self._decode_step_autograd(sd, u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask, drop_x, drop_h)
         packed = self._packer.get(sd)           # None for dimensions the packed path does not cover
         extra = {}
         if packed is not None:
@@ -186,6 +207,24 @@ class AttnDecoderLSTM(nn.Module):
                                      store=self.feature_store, vp_idx=vp, view_idx=view, **extra)
         return ops.follower_step(sd, u_t_prev, all_u_t.contiguous(), visual_context.contiguous(),
                                  h_0.contiguous(), c_0.contiguous(), ctx.contiguous(), ctx_mask, drop_x, drop_h, **extra)
+
+    def _decode_step_autograd(self, sd, u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask, drop_x, drop_h):
+        """Training: forward on the CUDA kernels (detached), gradients from torch autograd over the device-side
+        restatement in _functional.py with the same dropout masks (hand-written backward kernels: DESIGN.md §10)."""
+        if isinstance(visual_context, (tuple, list)):
+            vp, view = visual_context
+            visual_context = self.feature_store.dense(vp, view)
+        names = list(sd.keys())
+        inputs = [u_t_prev, all_u_t.contiguous(), visual_context.contiguous(), h_0.contiguous(), c_0.contiguous(), ctx.contiguous()]
+        params = [sd[k] for k in names]
+
+        def run_cuda():
+            with torch.no_grad():
+                d = [t.detach() for t in inputs]
+                w = {k: v.detach() for k, v in sd.items()}
+                return ops.follower_step(w, d[0], d[1], d[2], d[3], d[4], d[5], ctx_mask, drop_x, drop_h,
+                                         packed=self._packer.get(w))
+        return Fn.FollowerStepFn.apply(run_cuda, names, len(inputs), ctx_mask, drop_x, drop_h, *inputs, *params)
 
     @property
     def supports_fused_step(self) -> bool:
@@ -211,8 +250,9 @@ class SpeakerEncoderLSTM(nn.Module):
         assert isinstance(batched_action_embeddings, list)
         assert isinstance(world_state_embeddings, list)
         assert len(batched_action_embeddings) == len(world_state_embeddings)
-        _no_autograd(*self.parameters())
         w = _sd(self)
+        grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        names = list(w.keys())
         B = world_state_embeddings[0].shape[0]
         dev = world_state_embeddings[0].device
         h = torch.zeros(B, self.hidden_size, device=dev)
@@ -220,7 +260,17 @@ class SpeakerEncoderLSTM(nn.Module):
         hs = []
         for a, v in zip(batched_action_embeddings, world_state_embeddings):
             dx = self._drop.mask(self.training, (B, self.action_embedding_size + self.word_embedding_size), dev)
-            h, c = ops.speaker_encoder_step(w, a.contiguous(), v.contiguous(), h, c, dx)
+            a, v = a.contiguous(), v.contiguous()
+            if grad:   # forward on the CUDA kernels, gradients by torch autograd over _functional
+                def run_cuda(a=a, v=v, h=h, c=c, dx=dx):
+                    with torch.no_grad():
+                        return ops.speaker_encoder_step({k: t.detach() for k, t in w.items()}, a, v, h.detach(), c.detach(), dx)
+
+                def restate(a_, v_, h_, c_, *ps, dx=dx):
+                    return Fn.speaker_encoder_step(dict(zip(names, ps)), a_, v_, h_, c_, dx)
+                h, c = Fn.RecomputeFn.apply(run_cuda, restate, (), a, v, h, c, *[w[k] for k in names])
+            else:
+                h, c = ops.speaker_encoder_step(w, a, v, h, c, dx)
             hs.append(h)
         # decoder_init = tanh(encoder2decoder(h_T)) (model.py:453): one [B,H]x[H,H] product per path, host plumbing
         decoder_init = torch.tanh(torch.addmm(self.encoder2decoder.bias, h, self.encoder2decoder.weight.t()))
@@ -255,10 +305,21 @@ class SpeakerDecoderLSTM(nn.Module):
         self.decoder2action = nn.Linear(hidden_size, vocab_size)
 
     def forward(self, previous_word, h_0, c_0, ctx, ctx_mask=None):
-        _no_autograd(h_0, c_0, ctx, *self.parameters())
         B = h_0.shape[0]
         dev = h_0.device
         drop_e = None if self.use_glove else self._drop.mask(self.training, (B, self.vocab_embedding_size), dev)
         drop_h = self._drop.mask(self.training, (B, self.hidden_size), dev)
-        return ops.speaker_decoder_step(_sd(self), previous_word, h_0.contiguous(), c_0.contiguous(),
-                                        ctx.contiguous(), ctx_mask, drop_e, drop_h)
+        w = _sd(self)
+        h_0, c_0, ctx = h_0.contiguous(), c_0.contiguous(), ctx.contiguous()
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (h_0, c_0, ctx, *w.values())):
+            names = list(w.keys())   # forward on the CUDA kernels, gradients by torch autograd over _functional
+
+            def run_cuda():
+                with torch.no_grad():
+                    return ops.speaker_decoder_step({k: t.detach() for k, t in w.items()}, previous_word, h_0.detach(),
+                                                    c_0.detach(), ctx.detach(), ctx_mask, drop_e, drop_h)
+
+            def restate(h_, c_, x_, *ps):
+                return Fn.speaker_decoder_step(dict(zip(names, ps)), previous_word, h_, c_, x_, ctx_mask, drop_e, drop_h)
+            return Fn.RecomputeFn.apply(run_cuda, restate, (2,), h_0, c_0, ctx, *[w[k] for k in names])
+        return ops.speaker_decoder_step(w, previous_word, h_0, c_0, ctx, ctx_mask, drop_e, drop_h)

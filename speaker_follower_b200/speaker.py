@@ -118,7 +118,7 @@ class Seq2SeqSpeaker(object):
             self.max_episode_len, load_next_minibatch=load_next_minibatch)
         outputs, loss = self._score_obs_actions_and_instructions(path_obs, path_actions, encoded, self.feedback)
         self.loss = loss
-        self.losses.append(float(loss))
+        self.losses.append(float(loss.detach()))
         return outputs
 
     def beam_search(self, beam_size, path_obs, path_actions):
@@ -203,7 +203,7 @@ class Seq2SeqSpeaker(object):
             encoder_optimizer.zero_grad()
             decoder_optimizer.zero_grad()
             self.rollout()
-            self.loss.backward()          # raises while the modules are forward-only
+            self.loss.backward()          # gradients: torch autograd over the device-side restatement
             encoder_optimizer.step()
             decoder_optimizer.step()
 

@@ -1,0 +1,128 @@
+"""Training support: forward on the sm_100a kernels, gradients by torch autograd
+over the device-side restatement in speaker_follower_b200/_functional.py with the same dropout masks.
+Pinned against the gradients the REFERENCE's own modules produce (tests/golden/follower_step_small_train.npz, written
+by tests/golden/make_golden.py from tasks/R2R/model.py) and against autograd through the CPU oracle at full size."""
+import pytest
+import torch
+
+from conftest import load_golden, split_golden
+from fake_env import FakeR2RBatch
+from oracle import r2r_oracle as O
+from speaker_follower_b200 import _functional as Fn, follower as Fo, model as M, ops, synth
+from test_gpu_parity import NAMES, close, cu
+
+pytestmark = pytest.mark.gpu
+IN = ("u_t_prev", "all_u_t", "visual_context", "h_0", "c_0", "ctx")
+
+
+def test_reference_gradients_small_train_golden():
+    """Same inputs, same dropout masks, same cotangents as the reference run -> same input and weight gradients."""
+    w, x, out, rest = split_golden(load_golden("follower_step_small_train"))
+    names = list(w.keys())
+    wc = {k: v.cuda().requires_grad_(True) for k, v in w.items()}
+    xin = [x[k].cuda().requires_grad_(True) for k in IN]
+    mask, dx, dh = x["ctx_mask"].cuda(), rest["drop.x"].cuda(), rest["drop.h"].cuda()
+
+    def run_cuda():
+        with torch.no_grad():
+            return ops.follower_step({k: v.detach() for k, v in wc.items()}, *[t.detach() for t in xin], mask, dx, dh)
+    res = Fn.FollowerStepFn.apply(run_cuda, names, len(xin), mask, dx, dh, *xin, *[wc[k] for k in names])
+    for k, v in zip(NAMES, res):
+        close(v, out[k], what="fwd:" + k)                       # the forward really came from the CUDA kernels
+    loss = (res[0] * rest["cot.h_1"].cuda()).sum() + (res[1] * rest["cot.c_1"].cuda()).sum() + \
+           (res[3] * rest["cot.logit"].cuda()).sum()
+    loss.backward()
+    for k, t in zip(IN, xin):
+        close(t.grad, rest["gin." + k], 5e-5, "gin." + k)
+    for k in names:
+        close(wc[k].grad, rest["gw." + k], 1e-4, "gw." + k)
+
+
+def test_module_gradients_match_oracle_autograd_full_size():
+    """nn.Module level (eval mode: no dropout), reference dimensions, packed forward: grads == autograd through the oracle."""
+    B, L, A = 8, 20, 6
+    w = synth.follower_decoder_weights()
+    x = synth.follower_step_inputs(B, L, A, seed=77)
+    dec = M.AttnDecoderLSTM(synth.FEAT, synth.HID, 0.5).cuda().eval()
+    dec.load_state_dict(w)
+    xc = cu(x)
+    h0, c0, ctx = xc["h_0"].clone().requires_grad_(True), xc["c_0"].clone().requires_grad_(True), xc["ctx"].clone().requires_grad_(True)
+    g = torch.Generator().manual_seed(1)
+    cot = [torch.randn(B, synth.HID, generator=g), torch.randn(B, synth.HID, generator=g), torch.randn(B, A, generator=g)]
+    h1, c1, alpha, logit, av = dec(xc["u_t_prev"], xc["all_u_t"], xc["visual_context"], h0, c0, ctx, xc["ctx_mask"])
+    ((h1 * cot[0].cuda()).sum() + (c1 * cot[1].cuda()).sum() + (logit * cot[2].cuda()).sum()).backward()
+    # oracle autograd on the CPU
+    wr = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    hr, cr, ctr = x["h_0"].clone().requires_grad_(True), x["c_0"].clone().requires_grad_(True), x["ctx"].clone().requires_grad_(True)
+    r = O.attn_decoder_step(x["u_t_prev"], x["all_u_t"], x["visual_context"], hr, cr, ctr, x["ctx_mask"], wr)
+    ((r[0] * cot[0]).sum() + (r[1] * cot[1]).sum() + (r[3] * cot[2]).sum()).backward()
+    close(h1, r[0], what="h1"); close(logit, r[3], what="logit")
+    close(h0.grad, hr.grad, 1e-4, "d h_0"); close(c0.grad, cr.grad, 1e-4, "d c_0"); close(ctx.grad, ctr.grad, 1e-4, "d ctx")
+    for k, p in dec.named_parameters():
+        scale = max(1.0, float(wr[k].grad.abs().max()))
+        close(p.grad / scale, wr[k].grad / scale, 1e-4, "d " + k)
+
+
+def test_agent_train_iterations_reduce_the_loss():
+    """Seq2SeqAgent.train (follower.py:1001-1020) runs end to end: encoder + decoder receive gradients, Adam steps
+    change the weights (the packed copies follow), and the teacher-forced loss on the same batch goes down."""
+    env = FakeR2RBatch(n_viewpoints=20, n_instr=8, batch_size=8, seed=11)
+    glove = synth.follower_encoder_weights()["embedding.weight"].numpy()
+    enc = M.EncoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0, 0.0, glove=glove).cuda()
+    dec = M.AttnDecoderLSTM(synth.FEAT, synth.HID, 0.0).cuda()
+    enc.load_state_dict(synth.follower_encoder_weights()); dec.load_state_dict(synth.follower_decoder_weights())
+    agent = Fo.Seq2SeqAgent(env, "", enc, dec, episode_len=6, max_instruction_length=20)
+    eo = torch.optim.Adam([p for p in enc.parameters() if p.requires_grad], lr=1e-3)
+    do = torch.optim.Adam(dec.parameters(), lr=1e-3)
+    w0 = dec.lstm.weight_ih.detach().clone()
+    agent.train(eo, do, 1, feedback="teacher")
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0 for p in dec.parameters())
+    assert all(p.grad is not None and p.grad.abs().sum() > 0 for p in enc.parameters() if p.requires_grad)
+    first = agent.losses[0]
+    agent.train(eo, do, 5, feedback="teacher")
+    assert not torch.equal(dec.lstm.weight_ih.detach(), w0)
+    assert agent.losses[-1] < first, (first, agent.losses)
+    # inference after training uses the re-packed weights: packed step == in-place step on the updated parameters
+    dec.eval(); enc.eval()
+    agent.feedback = "argmax"
+    with torch.no_grad():
+        traj = agent.rollout()
+    assert len(traj) == 8
+
+
+def test_speaker_train_iteration_and_gradients():
+    """Seq2SeqSpeaker.train (speaker.py:376-395): speaker encoder/decoder gradients == autograd through the CPU oracle
+    (teacher-forced loss on the same batch), and Adam iterations reduce the loss."""
+    from speaker_follower_b200 import speaker as Sp
+    env = FakeR2RBatch(n_viewpoints=16, n_instr=6, batch_size=6, seed=6)
+    we, wd = synth.speaker_encoder_weights(), synth.speaker_decoder_weights()
+    enc = M.SpeakerEncoderLSTM(synth.FEAT, synth.FEAT, synth.HID, 0.0).cuda()
+    dec = M.SpeakerDecoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0.0, glove=wd["embedding.weight"].numpy()).cuda()
+    enc.load_state_dict(we); dec.load_state_dict(wd)
+    spk = Sp.Seq2SeqSpeaker(env, "", enc, dec, instruction_len=12, max_episode_len=6)
+    path_obs, path_actions, encoded = env.gold_obs_actions_and_instructions(6)
+    outs, loss = spk._score_obs_actions_and_instructions(path_obs, path_actions, encoded, "teacher")
+    loss.backward()
+    # the same loss through the CPU oracle with autograd
+    _, feats, acts, mask, _, _, _ = spk._batch_observations_and_actions(path_obs, path_actions, encoded)
+    instr, _, _ = Fo.batch_instructions_from_encoded(encoded, 12)
+    wer = {k: v.clone().requires_grad_(True) for k, v in we.items()}
+    wdr = {k: v.clone().requires_grad_(k != "embedding.weight") for k, v in wd.items()}
+    sc, l, words, wsc = O.speaker_score_teacher([a.cpu() for a in acts], [f.cpu() for f in feats], mask.cpu().bool(), instr, wer, wdr)
+    l.backward()
+    assert abs(float(loss) - float(l)) < 1e-3 * max(1.0, abs(float(l)))
+    for mod, ref_w in ((enc, wer), (dec, wdr)):
+        for k, p in mod.named_parameters():
+            if not p.requires_grad:
+                continue
+            ref = ref_w[k].grad
+            scale = max(1.0, float(ref.abs().max()))
+            close(p.grad / scale, ref / scale, 2e-4, "d " + k)
+    eo, do = torch.optim.Adam(enc.parameters(), lr=1e-3), torch.optim.Adam([p for p in dec.parameters() if p.requires_grad], lr=1e-3)
+    env.reset_epoch()
+    spk.train(eo, do, 1)
+    first = spk.losses[0]
+    for _ in range(5):
+        env.reset_epoch()
+        spk.train(eo, do, 1)
+    assert spk.losses[-1] < first

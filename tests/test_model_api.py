@@ -43,14 +43,19 @@ def test_full_size_parameter_counts():
     assert sum(p.numel() for p in enc.parameters() if p.requires_grad) == 4 * 512 * (300 + 512 + 2) + 512 * 513
 
 
-def test_modules_refuse_cpu_and_autograd():
+def test_modules_refuse_cpu():
+    """No CPU fallback: the forward always runs on the CUDA kernels (also under autograd, where only the gradients come
+    from torch), so CPU tensors are refused with or without grad mode; the stand-alone attention sub-modules are
+    forward-only."""
     from speaker_follower_b200._lib import SfbError
     dec = M.AttnDecoderLSTM(48, 32, 0.5, feature_size=40).eval()
     x = torch.zeros(2, 48), torch.zeros(2, 3, 48), torch.zeros(2, 36, 40), torch.zeros(2, 32), torch.zeros(2, 32), torch.zeros(2, 5, 32)
-    with pytest.raises(NotImplementedError):
-        dec(*x)                                   # parameters require grad and autograd is recording
+    with pytest.raises(SfbError):
+        dec(*x)                                   # autograd recording: forward still goes to the (absent) GPU
     with torch.no_grad(), pytest.raises(SfbError):
         dec(*x)                                   # CPU tensors: no fallback
+    with pytest.raises(NotImplementedError):
+        dec.visual_attention_layer(x[3], x[2])    # sub-module on its own under autograd: not differentiable here
 
 
 @pytest.mark.gpu
