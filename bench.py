@@ -26,7 +26,7 @@ import torch  # noqa: E402
 
 B, L, A = 100, 80, 8
 N_VIEWPOINTS = 10567          # R2R viewpoints -> 3.1 GB table, >> L2
-ATTN_NCU_TRAFFIC = 30782976   # dram__bytes_read.sum + dram__bytes_write.sum of one attention launch (ncu --set full)
+ATTN_NCU_TRAFFIC = 32172544   # dram__bytes_read.sum + dram__bytes_write.sum of one attention launch (ncu --set full)
 POOL = 10                     # per-step input sets = the steps of one episode (episode_len = 10, train.py:29)
 N_CTX = 4                     # rotating episodes: instruction contexts (16 MB each + 32 MB of per-episode projections)
 
