@@ -373,31 +373,32 @@ def run_gpu(args, rank, local_rank, world):
         np_at = h_at.numpy()
         a_t2, logit2 = h_at, logit
         d_out, h_out = [], [h_at]
-    graphs2 = []
-    for s in range(2):
-        gph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gph):
-            if blob is None:
-                ops.follower_step(w, ubuf[s], d_U, None, hbuf[s], cbuf[s], ctx[0], mask, store=store, vp_idx=d_vp,
-                                  view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v))
-                ops.follower_tail(logit, d_valid, d_U, "argmax", out=(a_t, ubuf[s ^ 1], score, None))
-            else:
-                ops.follower_step(w, ubuf[s], None, None, hbuf[s], cbuf[s], ctx[0], mask, store=store, vp_idx=d_vp,
-                                  view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit2, alpha_v),
-                                  packed=blob, q_in=qbuf[s], q_next=qbuf[s ^ 1], cand_view=d_cview, cand_trig=d_ctrig,
-                                  ctx_proj=cproj[0],
-                                  tail={"is_valid": d_valid, "feedback": "argmax", "out": (a_t2, ubuf[s ^ 1], score, None)})
-        graphs2.append(gph)
+    graphs2, graphs2_first = [], []          # [parity]; *_first = first step of an episode (ctx projection inside)
+    for with_proj in (False, True):
+        for s in range(2):
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                if with_proj:
+                    project(0)                         # new episode: per-episode ctx projections (2 launches)
+                if blob is None:
+                    ops.follower_step(w, ubuf[s], d_U, None, hbuf[s], cbuf[s], ctx[0], mask, store=store, vp_idx=d_vp,
+                                      view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v))
+                    ops.follower_tail(logit, d_valid, d_U, "argmax", out=(a_t, ubuf[s ^ 1], score, None))
+                else:
+                    ops.follower_step(w, ubuf[s], None, None, hbuf[s], cbuf[s], ctx[0], mask, store=store, vp_idx=d_vp,
+                                      view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit2, alpha_v),
+                                      packed=blob, q_in=qbuf[s], q_next=qbuf[s ^ 1], cand_view=d_cview, cand_trig=d_ctrig,
+                                      ctx_proj=cproj[0],
+                                      tail={"is_valid": d_valid, "feedback": "argmax", "out": (a_t2, ubuf[s ^ 1], score, None)})
+            (graphs2_first if with_proj else graphs2).append(gph)
 
     def e2e_step(i):
         j = i % POOL
-        if j == 0:
-            project(0)                                 # new episode: per-episode ctx projections (2 launches)
         if blob is not None:
             np_at.fill(-1)
         for dst, src in zip(d_in, h_in[j]):
             dst.copy_(src, non_blocking=True)
-        graphs2[i % 2].replay()
+        (graphs2_first if j == 0 else graphs2)[i % 2].replay()
         if blob is None:
             for dst, src in zip(h_out, d_out):
                 dst.copy_(src, non_blocking=True)
