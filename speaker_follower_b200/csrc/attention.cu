@@ -77,20 +77,28 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(co
       bulk_g2s_hint(dst + p.lenA, p.segB + bb + (size_t)gr * p.strideB_r, (uint32_t)p.lenB * 4u, &full[stage], pol);
   };
   if (warp == 0) {
+    // the slab addresses hang on a dependent index load: request it first, use it after the barrier setup
+    const long long ia = p.idxA ? (long long)p.idxA[b] : (long long)b;
+    const long long ib = p.idxB ? (long long)p.idxB[b] : (long long)b;
     int n = 0;
-    for (int base = 0; base < nmine; base += 32) {
-      const int i = base + lane;
-      const bool ok = i < nmine && !(mrow && mrow[rank + CL * i]);
-      const unsigned bal = __ballot_sync(0xffffffffu, ok);
-      if (ok) list[n + __popc(bal & ((1u << lane) - 1u))] = i;
-      n += __popc(bal);
+    if (mrow) {
+      for (int base = 0; base < nmine; base += 32) {
+        const int i = base + lane;
+        const bool ok = i < nmine && !mrow[rank + CL * i];
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (ok) list[n + __popc(bal & ((1u << lane) - 1u))] = i;
+        n += __popc(bal);
+      }
+    } else {   // no mask: every row is live
+      for (int i = lane; i < nmine; i += 32) list[i] = i;
+      n = nmine;
     }
     if (lane == 0) s_nvalid = n;
     if (lane < NSTG) mbar_init(&full[lane], 1);
     mbar_fence_init();
     __syncwarp();
-    ba = (size_t)(p.idxA ? p.idxA[b] : b) * p.strideA_b;
-    bb = (size_t)(p.idxB ? p.idxB[b] : b) * p.strideB_b;
+    ba = (size_t)ia * p.strideA_b;
+    bb = (size_t)ib * p.strideB_b;
     pol = p.no_hint ? policy_evict_normal() : policy_evict_first();
     if (lane < NSTG && lane < n) fetch(lane, lane);
   }
