@@ -67,3 +67,30 @@ def gather_records(local: torch.Tensor) -> torch.Tensor:
         allr = torch.cat([b[: int(s.item())] for b, s in zip(bufs, sizes)], 0)
     key = allr[:, 0] * 1e6 + allr[:, 1]
     return allr[torch.argsort(key)]
+
+
+def gather_json_shards(items: Sequence[Tuple[int, dict]]) -> List[dict]:
+    """C5 (data_augmentation_from_speaker.py:52-82 sharded by trajectory): every rank holds the generated records of
+    its own instances as (global instance index, JSON-serialisable dict).  One all-gather of the byte lengths and one of
+    the padded uint8 buffers; every rank returns the records of ALL ranks in global-index order, i.e. exactly the list a
+    single process would have written (the JSON file of the single-GPU run is reproduced byte for byte by dumping it)."""
+    import json
+    rank, ws = world()
+    payload = json.dumps([[int(i), rec] for i, rec in items]).encode("utf-8")
+    if ws == 1:
+        merged = json.loads(payload.decode("utf-8"))
+    else:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        n = torch.tensor([len(payload)], dtype=torch.int64, device=dev)
+        sizes = [torch.zeros_like(n) for _ in range(ws)]
+        dist.all_gather(sizes, n)
+        mx = int(max(int(s.item()) for s in sizes))
+        buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
+        buf[: len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+        bufs = [torch.zeros_like(buf) for _ in range(ws)]
+        dist.all_gather(bufs, buf)
+        merged = []
+        for b, s in zip(bufs, sizes):
+            merged.extend(json.loads(bytes(b[: int(s.item())].cpu().tolist()).decode("utf-8")))
+    merged.sort(key=lambda t: t[0])
+    return [rec for _, rec in merged]

@@ -31,7 +31,11 @@ def _worker(rank, world, port, q):
         s_std = D.global_std(recs[:, 3])
         f_std = D.global_std(recs[:, 2])
         rate, ms = D.aggregate_rate(100, 10.0 * (rank + 1))
-        q.put((rank, allr.numpy(), s_std, f_std, rate, ms, spk, fol))
+        # C5: generated instructions of this rank's trajectories, gathered into single-process order
+        traj = [(i, {"path_id": i, "instr_id": "%d_0" % i, "words": ["w%d" % ((i * 7 + k) % 11) for k in range(3 + i % 4)],
+                     "score": float(spk[i % n_instr, 0])}) for i in D.shard_indices(11, rank, world)]
+        shards = D.gather_json_shards(traj)
+        q.put((rank, allr.numpy(), s_std, f_std, rate, ms, spk, fol, shards))
     finally:
         dist.destroy_process_group()
 
@@ -48,7 +52,10 @@ def test_two_rank_sharded_combine_equals_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     outs.sort(key=lambda o: o[0])
-    _, allr0, s_std, f_std, rate, ms, spk, fol = outs[0]
+    _, allr0, s_std, f_std, rate, ms, spk, fol, shards0 = outs[0]
+    # JSON shard gather (data_augmentation_from_speaker.py:52-82 sharded): both ranks hold all 11 records in index order
+    assert shards0 == outs[1][8] and [r["path_id"] for r in shards0] == list(range(11))
+    assert all(r["words"] == ["w%d" % ((r["path_id"] * 7 + k) % 11) for k in range(3 + r["path_id"] % 4)] for r in shards0)
     assert np.array_equal(allr0, outs[1][1])                       # every rank sees the same, ordered records
     assert allr0.shape == (35, 4)
     assert np.array_equal(allr0[:, 0], np.repeat(np.arange(7), 5))
