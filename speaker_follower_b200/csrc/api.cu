@@ -172,18 +172,31 @@ static SpkDecWs carve_spkdec(int H, int Ew, int B, int T, void* ws) {
 
 struct EncWs {
   void* tc; size_t tc_bytes;
+  void* pk; size_t pk_bytes;            // gemm_pk barrier words + partial tiles
+  unsigned char* whh_pk[2]; size_t whh_bytes;   // W_hh packed per call (4 MB: negligible next to maxlen recurrent steps)
+  unsigned char* wih_pk[2]; size_t wih_bytes;   // W_ih packed per call for the hoisted input projection
   float *xproj, *h[2], *c[2];
   int splitk;
   size_t bytes;
 };
 
 static EncWs carve_encoder(int ndir, int Hd, int Ew, int B, int maxlen, void* ws) {
-  (void)Ew;
   EncWs w;
   Carver c(ws);
   w.splitk = gemm_pick_splitk(B, 4 * Hd, Hd, device_num_sms());
   w.tc_bytes = (Hd % 32) == 0 ? gemm_tc_plan(B, Hd, Hd, 1, device_num_sms()).bytes : 256;
   w.tc = c.take(w.tc_bytes / sizeof(float));
+  w.pk_bytes = 256;
+  if ((Hd % 32) == 0) {   // recurrent step (M = B) and hoisted input projection (M = B*maxlen) share the region
+    const size_t a = gemm_pk_plan(B, 4 * Hd, kblocks(Hd), false, device_num_sms()).bytes;
+    const size_t b = gemm_pk_plan(B * maxlen, 4 * Hd, kblocks(Ew), false, device_num_sms()).bytes;
+    w.pk_bytes = a > b ? a : b;
+  }
+  w.wih_bytes = (Hd % 32) == 0 ? pk_weight_bytes(4 * Hd, kblocks(Ew)) : 256;
+  for (int i = 0; i < 2; ++i) w.wih_pk[i] = reinterpret_cast<unsigned char*>(c.take(w.wih_bytes / sizeof(float)));
+  w.pk = c.take(w.pk_bytes / sizeof(float));
+  w.whh_bytes = (Hd % 32) == 0 ? pk_weight_bytes(4 * Hd, kblocks(Hd)) : 256;
+  for (int i = 0; i < 2; ++i) w.whh_pk[i] = reinterpret_cast<unsigned char*>(c.take(w.whh_bytes / sizeof(float)));
   w.xproj = c.take((size_t)ndir * B * maxlen * 4 * Hd);
   for (int i = 0; i < 2; ++i) w.h[i] = c.take((size_t)ndir * B * Hd);
   for (int i = 0; i < 2; ++i) w.c[i] = c.take((size_t)ndir * B * Hd);
@@ -502,6 +515,25 @@ int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t
   SFB_CHECK_CUDA(cudaMemsetAsync(ws.h[0], 0, ndir * state * sizeof(float), st));
   SFB_CHECK_CUDA(cudaMemsetAsync(ws.c[0], 0, ndir * state * sizeof(float), st));
   int cur[2] = {0, 0};
+  // recurrent projection on tcgen05 from packed W_hh (gemm_pk.cu): pack once per call, then one launch per time step
+  const bool use_pk = !g_disable_tc && (Hd % 32) == 0 && (Hd % 8) == 0 &&
+                      (reinterpret_cast<uintptr_t>(w->w_hh[0]) & 15u) == 0 && (ndir == 1 || (reinterpret_cast<uintptr_t>(w->w_hh[1]) & 15u) == 0);
+  if (use_pk) {
+    for (int dir = 0; dir < ndir; ++dir) {
+      PackParams p{};
+      p.nseg = 1;
+      p.seg[0] = PackSeg{w->w_hh[dir], Hd, Hd, nullptr, 0, nullptr};
+      p.ntile = Hd / 32; p.R = 128; p.rows_per_tile = 128; p.rows_valid = 4 * Hd; p.lstm_H = Hd;
+      p.out = ws.whh_pk[dir];
+      SFB_PROPAGATE(launch_pack_rows(p, st));
+      PackParams pi{};   // W_ih in natural row order: the projection's columns stay [i | f | g | o]
+      pi.nseg = 1;
+      pi.seg[0] = PackSeg{w->w_ih[dir], Ew, Ew, nullptr, 0, nullptr};
+      pi.ntile = (4 * Hd + 127) / 128; pi.R = 128; pi.rows_per_tile = 128; pi.rows_valid = 4 * Hd; pi.lstm_H = 0;
+      pi.out = ws.wih_pk[dir];
+      SFB_PROPAGATE(launch_pack_rows(pi, st));
+    }
+  }
   for (int dir = 0; dir < ndir; ++dir) {
     // hoisted input projection for every time step at once: [B*maxlen, Ew] x W_ih^T  (model.py:85,90)
     float* xp = ws.xproj + (size_t)dir * B * maxlen * 4 * Hd;
@@ -509,7 +541,14 @@ int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t
     g.nseg = 1;
     g.seg[0] = GemmSeg{w->embedding, Ew, seq, drop_embed, drop_embed ? Ew : 0, w->w_ih[dir], Ew, Ew, 0};
     g.M = B * maxlen; g.N = 4 * Hd; g.splitk = 1; g.out = xp; g.ldo = 4 * Hd;
-    SFB_PROPAGATE(launch_gemm(g, st));
+    if (use_pk && (reinterpret_cast<uintptr_t>(w->w_ih[dir]) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w->embedding) & 15u) == 0) {
+      PkParams q{};   // tcgen05, weights bulk-copied, embedding rows gathered + split on the fly
+      q.g = g;
+      q.a_pk = ws.wih_pk[dir]; q.b_pk = nullptr; q.nkb = kblocks(Ew);
+      SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));
+    } else {
+      SFB_PROPAGATE(launch_gemm(g, st));
+    }
     for (int s = 0; s < maxlen; ++s) {
       const int t = dir == 0 ? s : maxlen - 1 - s;
       float* hp = ws.h[cur[dir]] + dir * state;
@@ -526,8 +565,16 @@ int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t
       p.addend = xp + (size_t)t * 4 * Hd; p.ld_addend = (long long)maxlen * 4 * Hd;
       p.lengths = lengths; p.t = t;
       p.seq_out = ctx + (size_t)t * H + dir * Hd; p.ld_seq_out = (long long)maxlen * H;
-      if (!g_disable_tc && gemm_tc_supported(r)) SFB_PROPAGATE(launch_gemm_tc(r, st, ws.tc, ws.tc_bytes));
-      else SFB_PROPAGATE(launch_gemm(r, st));
+      if (use_pk) {
+        PkParams q{};
+        q.g = r;
+        q.a_pk = ws.whh_pk[dir]; q.b_pk = nullptr; q.nkb = kblocks(Hd);
+        SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));
+      } else if (!g_disable_tc && gemm_tc_supported(r)) {
+        SFB_PROPAGATE(launch_gemm_tc(r, st, ws.tc, ws.tc_bytes));
+      } else {
+        SFB_PROPAGATE(launch_gemm(r, st));
+      }
       cur[dir] ^= 1;
     }
   }

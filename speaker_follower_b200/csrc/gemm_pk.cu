@@ -189,11 +189,13 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
           if (rg * 8 < NB && m < m_end && k < g.k) {
             const int xr = g.xrow ? g.xrow[m] : m;
             const float* src = g.x + (size_t)xr * g.ldx + k;
+            const bool hi4 = k + 4 < g.k;   // K % 8 == 4: the last group is half full
             rb[set][i][0] = *reinterpret_cast<const float4*>(src);
-            rb[set][i][1] = *reinterpret_cast<const float4*>(src + 4);
+            rb[set][i][1] = hi4 ? *reinterpret_cast<const float4*>(src + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (g.xadd) {
               const float* ap = g.xadd + (size_t)m * g.ldxadd + k;
-              const float4 a0 = *reinterpret_cast<const float4*>(ap), a1 = *reinterpret_cast<const float4*>(ap + 4);
+              const float4 a0 = *reinterpret_cast<const float4*>(ap);
+              const float4 a1 = hi4 ? *reinterpret_cast<const float4*>(ap + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
               float4& r0 = rb[set][i][0];
               float4& r1 = rb[set][i][1];
               r0.x += a0.x; r0.y += a0.y; r0.z += a0.z; r0.w += a0.w;
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(320, 1) gemm_pk_kernel(const PkParams q) {
               if (g.xs) {
                 const float* sp = g.xs + (size_t)m * g.ldxs + k;
                 rs[set][i][0] = __ldg(reinterpret_cast<const float4*>(sp));
-                rs[set][i][1] = __ldg(reinterpret_cast<const float4*>(sp + 4));
+                rs[set][i][1] = hi4 ? __ldg(reinterpret_cast<const float4*>(sp + 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
               } else {
                 rs[set][i][0] = rs[set][i][1] = make_float4(1.f, 1.f, 1.f, 1.f);
               }
@@ -472,8 +474,8 @@ int32_t launch_gemm_pk(const PkParams& q_in, cudaStream_t stream, void* ws, size
       const GemmSeg& g = p.seg[s];
       kk[s] = g.k;
       has_xs |= g.xs != nullptr;
-      SFB_CHECK_ARG(g.x && (g.k % 8) == 0 && (g.ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(g.x) & 15u) == 0,
-                    "gemm_pk: fp32 activations must be 16-byte aligned, K % 8 == 0");
+      SFB_CHECK_ARG(g.x && (g.k % 4) == 0 && (g.ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(g.x) & 15u) == 0,
+                    "gemm_pk: fp32 activations must be 16-byte aligned, K % 4 == 0");
       SFB_CHECK_ARG(!g.xs || ((reinterpret_cast<uintptr_t>(g.xs) & 15u) == 0 && (g.ldxs % 4) == 0), "gemm_pk: scale alignment");
       SFB_CHECK_ARG(!g.xadd || ((reinterpret_cast<uintptr_t>(g.xadd) & 15u) == 0 && (g.ldxadd % 4) == 0), "gemm_pk: addend alignment");
     }

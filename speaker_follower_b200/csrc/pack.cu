@@ -32,8 +32,8 @@ int32_t pack_prepare(PackParams& p) {
   int nkb = 0;
   for (int s = 0; s < p.nseg; ++s) {
     const PackSeg& g = p.seg[s];
-    SFB_CHECK_ARG((g.k % 8) == 0 && (g.ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(g.x) & 15u) == 0,
-                  "pack: source must be 16-byte aligned with K % 8 == 0");
+    SFB_CHECK_ARG((g.k % 4) == 0 && (g.ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(g.x) & 15u) == 0,
+                  "pack: source must be 16-byte aligned with K % 4 == 0");
     SFB_CHECK_ARG(!g.xs || ((reinterpret_cast<uintptr_t>(g.xs) & 15u) == 0 && (g.ldxs % 4) == 0), "pack: scale alignment");
     nkb += (g.k + 63) / 64;
   }

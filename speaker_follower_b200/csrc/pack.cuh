@@ -56,10 +56,11 @@ __device__ __forceinline__ void pack_item(const PackParams& p, long long idx) {
     const int xr = g.xrow ? g.xrow[src_row] : src_row;
     const float* src = g.x + (size_t)xr * g.ldx + k;
     a = *reinterpret_cast<const float4*>(src);
-    b = *reinterpret_cast<const float4*>(src + 4);
+    if (k + 4 < g.k) b = *reinterpret_cast<const float4*>(src + 4);   // K % 8 == 4: the last group is half full
     if (g.xs) {
       const float* sp = g.xs + (size_t)src_row * g.ldxs + k;
-      const float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 4);
+      const float4 s0 = *reinterpret_cast<const float4*>(sp);
+      const float4 s1 = (k + 4 < g.k) ? *reinterpret_cast<const float4*>(sp + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       a.x *= s0.x; a.y *= s0.y; a.z *= s0.z; a.w *= s0.w;
       b.x *= s1.x; b.y *= s1.y; b.z *= s1.z; b.w *= s1.w;
     }
