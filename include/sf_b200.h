@@ -298,6 +298,34 @@ int32_t sfb_speaker_decoder_step_fwd(const sfb_speaker_decoder_weights* w, int32
                                      float* h1, float* c1, float* alpha, float* logit,
                                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- packed-weight fast paths of the two speaker steps (same idea as sfb_follower_pack_weights) ------------------
+ * sfb_vis_lstm_pack_weights: folded visual query M_q = W_v^T W_h + gate-interleaved [W_ih | W_hh] as tcgen05 operand
+ * tiles; sfb_speaker_encoder_step_packed_fwd = SpeakerEncoderLSTM._forward_one_step (model.py:429-435) in 3 launches
+ * (q projection, attention gather that also packs the gate GEMM's activations, gate GEMM + LSTM cell).
+ * sfb_speaker_decoder_pack_weights / _step_packed_fwd = SpeakerDecoderLSTM.forward (model.py:497-503,515-519) in
+ * 5 launches, every projection on tcgen05 (the embedding row of the previous word is gathered and split to bf16
+ * hi/lo while the gate GEMM loads its operand).  Same arguments, outputs and workspaces as the in-place entry points;
+ * *_packed_bytes return 0 for dimensions the packed path does not cover (H % 128, E/F % 8, Ew % 4, vocab <= 4096). */
+size_t  sfb_vis_lstm_packed_bytes(const sfb_dims* dims);
+int32_t sfb_vis_lstm_pack_weights(const sfb_dims* dims, const sfb_vis_lstm_weights* w,
+                                  void* packed, size_t packed_bytes, void* stream);
+int32_t sfb_speaker_encoder_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* w,
+                                            const void* packed, size_t packed_bytes, int32_t B,
+                                            const float* action_embedding, const sfb_visual_source* vis,
+                                            const float* h0, const float* c0, const float* drop_x,
+                                            float* h1, float* c1,
+                                            void* workspace, size_t workspace_bytes, void* stream);
+size_t  sfb_speaker_decoder_packed_bytes(int32_t H, int32_t Ew, int32_t vocab);
+int32_t sfb_speaker_decoder_pack_weights(const sfb_speaker_decoder_weights* w, int32_t H, int32_t Ew, int32_t vocab,
+                                         void* packed, size_t packed_bytes, void* stream);
+int32_t sfb_speaker_decoder_step_packed_fwd(const sfb_speaker_decoder_weights* w, const void* packed, size_t packed_bytes,
+                                            int32_t H, int32_t Ew, int32_t vocab, int32_t B, int32_t T,
+                                            const int32_t* prev_word,
+                                            const float* h0, const float* c0, const float* ctx, const uint8_t* ctx_mask,
+                                            const float* drop_e, const float* drop_h,
+                                            float* h1, float* c1, float* alpha, float* logit,
+                                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* Number of kernels the last successful call on this thread enqueued (bench.py's gpu_launches). */
 int32_t sfb_last_launch_count(void);
 

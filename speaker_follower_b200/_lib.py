@@ -118,6 +118,18 @@ SIGNATURES = {
                                                  C.c_int32, C.c_int32, c_int_p, c_float_p, c_float_p, c_float_p,
                                                  c_u8_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                                  c_float_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sfb_vis_lstm_packed_bytes": (C.c_size_t, [C.POINTER(Dims)]),
+    "sfb_vis_lstm_pack_weights": (C.c_int32, [C.POINTER(Dims), C.POINTER(VisLstmWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sfb_speaker_encoder_step_packed_fwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(VisLstmWeights), C.c_void_p, C.c_size_t,
+                                                        C.c_int32, c_float_p, C.POINTER(VisualSource), c_float_p, c_float_p,
+                                                        c_float_p, c_float_p, c_float_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sfb_speaker_decoder_packed_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "sfb_speaker_decoder_pack_weights": (C.c_int32, [C.POINTER(SpeakerDecoderWeights), C.c_int32, C.c_int32, C.c_int32,
+                                                     C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sfb_speaker_decoder_step_packed_fwd": (C.c_int32, [C.POINTER(SpeakerDecoderWeights), C.c_void_p, C.c_size_t, C.c_int32,
+                                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_int_p, c_float_p,
+                                                        c_float_p, c_float_p, c_u8_p, c_float_p, c_float_p, c_float_p,
+                                                        c_float_p, c_float_p, c_float_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 _lib = None

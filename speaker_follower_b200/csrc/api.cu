@@ -148,6 +148,8 @@ static int32_t check_packable(const sfb_dims& d) {
 struct SpkDecWs {
   void* tc; size_t tc_bytes;
   void* at; size_t at_bytes;
+  void* pk; size_t pk_bytes;              // packed path: barrier words + partial tiles
+  float* th;                              // packed path: [t | W_out_h h]
   float *gates_act, *h1d, *t, *wc, *htilde;
   int splitk;
   size_t bytes;
@@ -166,6 +168,18 @@ static SpkDecWs carve_spkdec(int H, int Ew, int B, int T, void* ws) {
   w.t = c.take((size_t)B * H);
   w.wc = c.take((size_t)B * H);
   w.htilde = c.take((size_t)B * H);
+  {
+    const int sms = device_num_sms(), nkb_h = kblocks(H), nkb_g = kblocks(Ew) + kblocks(H);
+    size_t mx = gemm_pk_plan(B, 4 * H, nkb_g, false, sms).bytes;
+    const int rows[3] = {2 * H, H, 4096};   // [t|hh], h~, vocabulary projection (sized for vocab <= 4096 rows; checked at call)
+    for (int i = 0; i < 3; ++i) {
+      const size_t b = gemm_pk_plan(B, rows[i], nkb_h, false, sms).bytes;
+      if (b > mx) mx = b;
+    }
+    w.pk_bytes = mx;
+    w.pk = c.take(mx / sizeof(float));
+    w.th = c.take((size_t)B * 2 * H);
+  }
   w.bytes = c.off;
   return w;
 }
@@ -922,6 +936,207 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
   if (q_next && drop_h && !ctx_k)   // train mode: the next query needs the un-dropped h_1 -> its own projection
     SFB_PROPAGATE(proj(base + P.a_q, h1, d.H, d.H, d.F, q_next, d.F, b_q, nullptr, 0, 0, 0, nullptr, 0, nullptr));
   return 0;
+}
+
+/* ---------------------------------------------------------------- speaker modules on the packed tcgen05 path */
+namespace {
+struct VisLstmPk { size_t a_q, b_q, a_gates, mq, bytes; int nkb_h, nkb_gates; };
+VisLstmPk layout_vislstm_pk(const sfb_dims& d) {
+  VisLstmPk L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t r = off; off += (bytes + 255) & ~size_t(255); return r; };
+  L.nkb_h = kblocks(d.H);
+  L.nkb_gates = kblocks(d.E) + kblocks(d.F) + kblocks(d.H);
+  L.a_q = take(pk_weight_bytes(d.F, L.nkb_h));
+  L.b_q = take((size_t)d.F * 4);
+  L.a_gates = take(pk_weight_bytes(4 * d.H, L.nkb_gates));
+  L.mq = take((size_t)d.F * d.H * 4);
+  L.bytes = off;
+  return L;
+}
+struct SpkDecPk { size_t a_gates, a_th, a_wc, a_voc, bytes; int nkb_h, nkb_gates; };
+SpkDecPk layout_spkdec_pk(int H, int Ew, int vocab) {
+  SpkDecPk L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t r = off; off += (bytes + 255) & ~size_t(255); return r; };
+  L.nkb_h = kblocks(H);
+  L.nkb_gates = kblocks(Ew) + kblocks(H);
+  L.a_gates = take(pk_weight_bytes(4 * H, L.nkb_gates));
+  L.a_th = take(pk_weight_bytes(2 * H, L.nkb_h));
+  L.a_wc = take(pk_weight_bytes(H, L.nkb_h));
+  L.a_voc = take(pk_weight_bytes(vocab, L.nkb_h));
+  L.bytes = off;
+  return L;
+}
+int32_t pack_plain(const float* w, int ldw, int rows, int k, unsigned char* out, cudaStream_t st) {
+  PackParams p{};
+  p.nseg = 1;
+  p.seg[0] = PackSeg{w, ldw, k, nullptr, 0, nullptr};
+  p.ntile = (rows + 127) / 128; p.R = 128; p.rows_per_tile = 128; p.rows_valid = rows; p.lstm_H = 0;
+  p.out = out;
+  return launch_pack_rows(p, st);
+}
+}  // namespace
+
+size_t sfb_vis_lstm_packed_bytes(const sfb_dims* dims) {
+  if (!dims || check_dims(dims) != 0 || check_packable(*dims) != 0) return 0;
+  return layout_vislstm_pk(*dims).bytes;
+}
+
+int32_t sfb_vis_lstm_pack_weights(const sfb_dims* dims, const sfb_vis_lstm_weights* wl, void* packed, size_t packed_bytes,
+                                  void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_PROPAGATE(check_packable(*dims));
+  SFB_CHECK_ARG(wl && packed, "NULL argument");
+  const sfb_dims& d = *dims;
+  const VisLstmPk L = layout_vislstm_pk(d);
+  SFB_CHECK_ARG(packed_bytes >= L.bytes && (reinterpret_cast<uintptr_t>(packed) & 255u) == 0, "packed buffer too small / misaligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned char* base = static_cast<unsigned char*>(packed);
+  float* mq = reinterpret_cast<float*>(base + L.mq);
+  SFB_PROPAGATE(launch_fold(wl->va_w_v, d.F, nullptr, wl->va_w_h, d.H, wl->va_b_h, d.D, d.F, d.H, mq, d.H,
+                            reinterpret_cast<float*>(base + L.b_q), nullptr, st));
+  SFB_PROPAGATE(pack_plain(mq, d.H, d.F, d.H, base + L.a_q, st));
+  PackParams p{};
+  p.nseg = 3;
+  p.seg[0] = PackSeg{wl->lstm_w_ih, d.E + d.F, d.E, nullptr, 0, nullptr};
+  p.seg[1] = PackSeg{wl->lstm_w_ih + d.E, d.E + d.F, d.F, nullptr, 0, nullptr};
+  p.seg[2] = PackSeg{wl->lstm_w_hh, d.H, d.H, nullptr, 0, nullptr};
+  p.ntile = d.H / 32; p.R = 128; p.rows_per_tile = 128; p.rows_valid = 4 * d.H; p.lstm_H = d.H;
+  p.out = base + L.a_gates;
+  return launch_pack_rows(p, st);
+}
+
+int32_t sfb_speaker_encoder_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* w, const void* packed,
+                                            size_t packed_bytes, int32_t B, const float* action_embedding,
+                                            const sfb_visual_source* vis, const float* h0, const float* c0,
+                                            const float* drop_x, float* h1, float* c1, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_PROPAGATE(check_packable(*dims));
+  SFB_CHECK_ARG(w && vis && packed && action_embedding && h0 && c0 && h1 && c1, "NULL argument");
+  SFB_CHECK_ARG(B >= 1, "B >= 1");
+  const sfb_dims& d = *dims;
+  const VisLstmPk P = layout_vislstm_pk(d);
+  SFB_CHECK_ARG(packed_bytes >= P.bytes && (reinterpret_cast<uintptr_t>(packed) & 255u) == 0, "packed buffer too small / misaligned");
+  FollowerWs ws = carve_follower(d, B, 1, 1, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned char* base = static_cast<const unsigned char*>(packed);
+  // model.py:431  feature = visual_attention_layer(h, world_state): q = M_q h + b_q on tcgen05
+  {
+    PkParams q{};
+    q.a_pk = base + P.a_q; q.nkb = P.nkb_h;
+    q.g.nseg = 1;
+    q.g.seg[0] = GemmSeg{h0, d.H, nullptr, nullptr, 0, nullptr, 0, d.H, 0};
+    q.g.M = B; q.g.N = d.F; q.g.out = ws.q; q.g.ldo = d.F; q.g.bias0 = reinterpret_cast<const float*>(base + P.b_q);
+    SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));
+  }
+  const PkPlan gpl = gemm_pk_plan(B, 4 * d.H, P.nkb_gates, true, device_num_sms());
+  {
+    AttnParams pk{};
+    pk.pk_out = ws.bpk; pk.pk_kb0 = kblocks(d.E); pk.pk_nkb = P.nkb_gates; pk.pk_NB = gpl.NB; pk.pk_rows_per_z = gpl.rows_per_z;
+    pk.pk_scale = drop_x ? drop_x + d.E : nullptr; pk.pk_ldscale = d.E + d.F;
+    pk.has_side = 1;
+    PackParams& side = pk.side;
+    side.nseg = 3;
+    side.seg[0] = PackSeg{action_embedding, d.E, d.E, drop_x, drop_x ? d.E + d.F : 0, nullptr};
+    side.seg[1] = PackSeg{nullptr, d.F, d.F, nullptr, 0, nullptr};
+    side.seg[2] = PackSeg{h0, d.H, d.H, nullptr, 0, nullptr};
+    side.ntile = gpl.nz; side.R = gpl.NB; side.rows_per_tile = gpl.rows_per_z; side.rows_valid = B; side.lstm_H = 0;
+    side.out = ws.bpk;
+    SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, nullptr, ws.av, ws.av_bytes, st, &pk));
+  }
+  // model.py:432-434  LSTMCell(drop(cat(action_embedding, feature)), (h, c))
+  PkParams q{};
+  q.a_pk = base + P.a_gates; q.b_pk = ws.bpk; q.nkb = P.nkb_gates;
+  q.g.M = B; q.g.N = 4 * d.H;
+  LstmEpilogue& e = q.g.lstm;
+  e.H = d.H; e.b_ih = w->lstm_b_ih; e.b_hh = w->lstm_b_hh; e.c0 = c0;
+  e.h1 = h1; e.c1 = c1; e.gates_act = ws.gates_act;
+  return launch_gemm_pk(q, st, ws.pk, ws.pk_bytes);
+}
+
+size_t sfb_speaker_decoder_packed_bytes(int32_t H, int32_t Ew, int32_t vocab) {
+  if (H < 128 || (H % 128) != 0 || Ew < 4 || (Ew % 4) != 0 || vocab < 1 || vocab > 4096) return 0;
+  return layout_spkdec_pk(H, Ew, vocab).bytes;
+}
+
+int32_t sfb_speaker_decoder_pack_weights(const sfb_speaker_decoder_weights* w, int32_t H, int32_t Ew, int32_t vocab,
+                                         void* packed, size_t packed_bytes, void* stream) {
+  reset_launch_count();
+  SFB_CHECK_ARG(w && packed, "NULL argument");
+  SFB_CHECK_ARG(sfb_speaker_decoder_packed_bytes(H, Ew, vocab) != 0, "packed path needs H % 128 == 0, Ew % 4 == 0, vocab <= 4096");
+  const SpkDecPk L = layout_spkdec_pk(H, Ew, vocab);
+  SFB_CHECK_ARG(packed_bytes >= L.bytes && (reinterpret_cast<uintptr_t>(packed) & 255u) == 0, "packed buffer too small / misaligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned char* base = static_cast<unsigned char*>(packed);
+  PackParams p{};
+  p.nseg = 2;
+  p.seg[0] = PackSeg{w->lstm_w_ih, Ew, Ew, nullptr, 0, nullptr};
+  p.seg[1] = PackSeg{w->lstm_w_hh, H, H, nullptr, 0, nullptr};
+  p.ntile = H / 32; p.R = 128; p.rows_per_tile = 128; p.rows_valid = 4 * H; p.lstm_H = H;
+  p.out = base + L.a_gates;
+  SFB_PROPAGATE(launch_pack_rows(p, st));
+  SFB_PROPAGATE(pack_plain(w->attn.w_in, H, H, H, base + L.a_th, st));
+  SFB_PROPAGATE(pack_plain(w->attn.w_out + H, 2 * H, H, H, base + L.a_th + pk_weight_bytes(H, L.nkb_h), st));
+  SFB_PROPAGATE(pack_plain(w->attn.w_out, 2 * H, H, H, base + L.a_wc, st));
+  return pack_plain(w->w_voc, H, vocab, H, base + L.a_voc, st);
+}
+
+int32_t sfb_speaker_decoder_step_packed_fwd(const sfb_speaker_decoder_weights* w, const void* packed, size_t packed_bytes,
+                                            int32_t H, int32_t Ew, int32_t vocab, int32_t B, int32_t T,
+                                            const int32_t* prev_word, const float* h0, const float* c0, const float* ctx,
+                                            const uint8_t* ctx_mask, const float* drop_e, const float* drop_h, float* h1,
+                                            float* c1, float* alpha, float* logit, void* workspace, size_t workspace_bytes,
+                                            void* stream) {
+  reset_launch_count();
+  SFB_CHECK_ARG(w && packed && prev_word && h0 && c0 && ctx && h1 && c1 && logit, "NULL argument");
+  SFB_CHECK_ARG(sfb_speaker_decoder_packed_bytes(H, Ew, vocab) != 0, "packed path needs H % 128 == 0, Ew % 4 == 0, vocab <= 4096");
+  SFB_CHECK_ARG(B >= 1 && T >= 1, "B, T >= 1");
+  const SpkDecPk P = layout_spkdec_pk(H, Ew, vocab);
+  SFB_CHECK_ARG(packed_bytes >= P.bytes && (reinterpret_cast<uintptr_t>(packed) & 255u) == 0, "packed buffer too small / misaligned");
+  SpkDecWs ws = carve_spkdec(H, Ew, B, T, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned char* base = static_cast<const unsigned char*>(packed);
+  // model.py:497-503,515  LSTMCell(embedding(previous_word)): embedding rows gathered + split on the fly
+  {
+    PkParams q{};
+    q.a_pk = base + P.a_gates; q.nkb = P.nkb_gates;
+    q.g.nseg = 2;
+    q.g.seg[0] = GemmSeg{w->embedding, Ew, prev_word, drop_e, drop_e ? Ew : 0, nullptr, 0, Ew, 0};
+    q.g.seg[1] = GemmSeg{h0, H, nullptr, nullptr, 0, nullptr, 0, H, 0};
+    q.g.M = B; q.g.N = 4 * H;
+    LstmEpilogue& e = q.g.lstm;
+    e.H = H; e.b_ih = w->lstm_b_ih; e.b_hh = w->lstm_b_hh; e.c0 = c0; e.drop_h = drop_h;
+    e.h1 = h1; e.c1 = c1; e.h1_drop = ws.h1d; e.gates_act = ws.gates_act;
+    SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));
+  }
+  auto proj = [&](const unsigned char* a_pk, const float* x, int n_out, float* out, int ldo, const float* bias,
+                  const float* padd, int ld_padd, int act) {
+    PkParams q{};
+    q.a_pk = a_pk; q.nkb = P.nkb_h;
+    q.g.nseg = 1;
+    q.g.seg[0] = GemmSeg{x, H, nullptr, nullptr, 0, nullptr, 0, H, 0};
+    q.g.M = B; q.g.N = n_out; q.g.out = out; q.g.ldo = ldo; q.g.bias0 = bias; q.g.padd = padd; q.g.ld_padd = ld_padd; q.g.act = act;
+    return launch_gemm_pk(q, st, ws.pk, ws.pk_bytes);
+  };
+  // model.py:516-517  SoftDotAttention(drop(h_1), ctx, path_mask)
+  SFB_PROPAGATE(proj(base + P.a_th, ws.h1d, 2 * H, ws.th, 2 * H, nullptr, nullptr, 0, 0));
+  {
+    AttnParams a{};
+    a.q = ws.th; a.ldq = 2 * H; a.R = T; a.D = H;
+    a.segA = ctx; a.strideA_b = (long long)T * H; a.strideA_r = H; a.lenA = H; a.lenB = 0;
+    a.mask = ctx_mask; a.ldmask = T;
+    a.out = ws.wc; a.ldo = H; a.alpha = alpha; a.ldalpha = T;
+    SFB_PROPAGATE(launch_soft_dot_attention(a, B, ws.at, ws.at_bytes, st));
+  }
+  SFB_PROPAGATE(proj(base + P.a_wc, ws.wc, H, ws.htilde, H, nullptr, ws.th + H, 2 * H, 1));
+  // model.py:518  logit = decoder2action(h_tilde)
+  return proj(base + P.a_voc, ws.htilde, vocab, logit, vocab, w->b_voc, nullptr, 0, 0);
 }
 
 }  // extern "C"

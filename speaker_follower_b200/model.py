@@ -245,6 +245,8 @@ class SpeakerEncoderLSTM(nn.Module):
         self.visual_attention_layer = VisualSoftDotAttention(hidden_size, world_embedding_size)
         self.lstm = nn.LSTMCell(action_embedding_size + world_embedding_size, hidden_size)
         self.encoder2decoder = nn.Linear(hidden_size, hidden_size)
+        self._packer = ops.PackedVisLstm()      # tcgen05 operand copies, refreshed when a weight changes
+        self._ws = None                         # step workspace reused across the path steps of a call
 
     def forward(self, batched_action_embeddings: List[torch.Tensor], world_state_embeddings: List[torch.Tensor]):
         assert isinstance(batched_action_embeddings, list)
@@ -253,6 +255,7 @@ class SpeakerEncoderLSTM(nn.Module):
         w = _sd(self)
         grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         names = list(w.keys())
+        packed = self._packer.get({k: v.detach() for k, v in w.items()})
         B = world_state_embeddings[0].shape[0]
         dev = world_state_embeddings[0].device
         h = torch.zeros(B, self.hidden_size, device=dev)
@@ -264,13 +267,14 @@ class SpeakerEncoderLSTM(nn.Module):
             if grad:   # forward on the CUDA kernels, gradients by torch autograd over _functional
                 def run_cuda(a=a, v=v, h=h, c=c, dx=dx):
                     with torch.no_grad():
-                        return ops.speaker_encoder_step({k: t.detach() for k, t in w.items()}, a, v, h.detach(), c.detach(), dx)
+                        return ops.speaker_encoder_step({k: t.detach() for k, t in w.items()}, a, v, h.detach(), c.detach(), dx,
+                                                        packed=packed)
 
                 def restate(a_, v_, h_, c_, *ps, dx=dx):
                     return Fn.speaker_encoder_step(dict(zip(names, ps)), a_, v_, h_, c_, dx)
                 h, c = Fn.RecomputeFn.apply(run_cuda, restate, (), a, v, h, c, *[w[k] for k in names])
             else:
-                h, c = ops.speaker_encoder_step(w, a, v, h, c, dx)
+                h, c = ops.speaker_encoder_step(w, a, v, h, c, dx, packed=packed)
             hs.append(h)
         # decoder_init = tanh(encoder2decoder(h_T)) (model.py:453): one [B,H]x[H,H] product per path, host plumbing
         decoder_init = torch.tanh(torch.addmm(self.encoder2decoder.bias, h, self.encoder2decoder.weight.t()))
@@ -303,6 +307,7 @@ class SpeakerDecoderLSTM(nn.Module):
         self.lstm = nn.LSTMCell(vocab_embedding_size, hidden_size)
         self.attention_layer = SoftDotAttention(hidden_size)
         self.decoder2action = nn.Linear(hidden_size, vocab_size)
+        self._packer = ops.PackedSpeakerDecoder()   # tcgen05 operand copies, refreshed when a weight changes
 
     def forward(self, previous_word, h_0, c_0, ctx, ctx_mask=None):
         B = h_0.shape[0]
@@ -311,15 +316,16 @@ class SpeakerDecoderLSTM(nn.Module):
         drop_h = self._drop.mask(self.training, (B, self.hidden_size), dev)
         w = _sd(self)
         h_0, c_0, ctx = h_0.contiguous(), c_0.contiguous(), ctx.contiguous()
+        packed = self._packer.get({k: v.detach() for k, v in w.items()})
         if torch.is_grad_enabled() and any(t.requires_grad for t in (h_0, c_0, ctx, *w.values())):
             names = list(w.keys())   # forward on the CUDA kernels, gradients by torch autograd over _functional
 
             def run_cuda():
                 with torch.no_grad():
                     return ops.speaker_decoder_step({k: t.detach() for k, t in w.items()}, previous_word, h_0.detach(),
-                                                    c_0.detach(), ctx.detach(), ctx_mask, drop_e, drop_h)
+                                                    c_0.detach(), ctx.detach(), ctx_mask, drop_e, drop_h, packed=packed)
 
             def restate(h_, c_, x_, *ps):
                 return Fn.speaker_decoder_step(dict(zip(names, ps)), previous_word, h_, c_, x_, ctx_mask, drop_e, drop_h)
             return Fn.RecomputeFn.apply(run_cuda, restate, (2,), h_0, c_0, ctx, *[w[k] for k in names])
-        return ops.speaker_decoder_step(w, previous_word, h_0, c_0, ctx, ctx_mask, drop_e, drop_h)
+        return ops.speaker_decoder_step(w, previous_word, h_0, c_0, ctx, ctx_mask, drop_e, drop_h, packed=packed)

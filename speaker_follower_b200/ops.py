@@ -223,6 +223,70 @@ class PackedFollower:
         return self.blob
 
 
+class _PackedCache:
+    """Blob re-packed when any of `keys`' storage or version changes (same policy as PackedFollower)."""
+    keys: tuple = ()
+
+    def __init__(self):
+        self.blob: Optional[Tensor] = None
+        self.key = None
+
+    def _pack(self, w, blob_or_none):   # -> (nbytes, pack_fn)
+        raise NotImplementedError
+
+    def get(self, w: Dict[str, Tensor]) -> Optional[Tensor]:
+        key = tuple((w[k].data_ptr(), w[k]._version) for k in self.keys)
+        if self.blob is not None and key == self.key:
+            return self.blob
+        n, pack = self._pack(w)
+        if n == 0:
+            return None
+        dev = w[self.keys[0]].device
+        if self.blob is None or self.blob.numel() < n or self.blob.device != dev:
+            self.blob = torch.empty(n, dtype=torch.uint8, device=dev)
+        pack(self.blob)
+        self.key = key
+        return self.blob
+
+
+class PackedVisLstm(_PackedCache):
+    """sfb_vis_lstm_pack_weights: visual attention + LSTM cell of SpeakerEncoderLSTM (model.py:415-418)."""
+    keys = ("lstm.weight_ih", "lstm.weight_hh", "visual_attention_layer.linear_in_h.weight",
+            "visual_attention_layer.linear_in_h.bias", "visual_attention_layer.linear_in_v.weight")
+
+    def _pack(self, w):
+        lib = _lib.load()
+        d = follower_dims(w)
+        wl = _vis_lstm_weights(w)
+        n = lib.sfb_vis_lstm_packed_bytes(C.byref(d))
+        return n, lambda blob: check(lib.sfb_vis_lstm_pack_weights(C.byref(d), C.byref(wl), blob.data_ptr(), blob.numel(), _stream()))
+
+
+def _spk_dec_weights(w: Dict[str, Tensor]) -> SpeakerDecoderWeights:
+    sw = SpeakerDecoderWeights()
+    sw.embedding = _p(w["embedding.weight"])
+    sw.lstm_w_ih = _p(w["lstm.weight_ih"]); sw.lstm_w_hh = _p(w["lstm.weight_hh"])
+    sw.lstm_b_ih = _p(w["lstm.bias_ih"]); sw.lstm_b_hh = _p(w["lstm.bias_hh"])
+    sw.attn = _softdot_weights(w, "attention_layer.")
+    sw.w_voc = _p(w["decoder2action.weight"]); sw.b_voc = _p(w["decoder2action.bias"])
+    return sw
+
+
+class PackedSpeakerDecoder(_PackedCache):
+    """sfb_speaker_decoder_pack_weights (model.py:469-485)."""
+    keys = ("lstm.weight_ih", "lstm.weight_hh", "attention_layer.linear_in.weight", "attention_layer.linear_out.weight",
+            "decoder2action.weight")
+
+    def _pack(self, w):
+        lib = _lib.load()
+        vocab, Ew = w["embedding.weight"].shape
+        H = w["lstm.weight_hh"].shape[1]
+        sw = _spk_dec_weights(w)
+        n = lib.sfb_speaker_decoder_packed_bytes(H, Ew, vocab)
+        return n, lambda blob: check(lib.sfb_speaker_decoder_pack_weights(C.byref(sw), H, Ew, vocab, blob.data_ptr(),
+                                                                          blob.numel(), _stream()))
+
+
 def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual: Optional[Tensor], h0: Tensor,
                   c0: Tensor, ctx: Tensor, ctx_mask: Optional[Tensor], drop_x: Optional[Tensor] = None,
                   drop_h: Optional[Tensor] = None, store: Optional[FeatureStore] = None,
@@ -439,8 +503,9 @@ def encoder_lstm(w: Dict[str, Tensor], seq: Tensor, lengths, bidirectional: bool
 
 
 def speaker_encoder_step(w: Dict[str, Tensor], action_embedding: Tensor, visual: Optional[Tensor], h0: Tensor,
-                         c0: Tensor, drop_x: Optional[Tensor] = None, store=None, vp_idx=None, view_idx=None):
-    """SpeakerEncoderLSTM._forward_one_step (model.py:429-435) -> (h1, c1)."""
+                         c0: Tensor, drop_x: Optional[Tensor] = None, store=None, vp_idx=None, view_idx=None,
+                         packed: Optional[Tensor] = None, workspace: Optional[Tensor] = None):
+    """SpeakerEncoderLSTM._forward_one_step (model.py:429-435) -> (h1, c1).  `packed` = PackedVisLstm().get(w)."""
     lib = _lib.load()
     B = h0.shape[0]
     V = visual.shape[1] if visual is not None else store.feat_table.shape[1]
@@ -449,8 +514,14 @@ def speaker_encoder_step(w: Dict[str, Tensor], action_embedding: Tensor, visual:
     vs = _visual_source(visual, store, vp_idx, view_idx, keep)
     wl = _vis_lstm_weights(w)
     need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, 1, 1)
-    ws = _workspace(need, h0.device)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, h0.device)
     h1 = torch.empty_like(h0); c1 = torch.empty_like(c0)
+    if packed is not None:
+        check(lib.sfb_speaker_encoder_step_packed_fwd(
+            C.byref(d), C.byref(wl), packed.data_ptr(), packed.numel(), B, _p(action_embedding, name="action_embedding"),
+            C.byref(vs), _p(h0, name="h_0"), _p(c0, name="c_0"), _p(drop_x, name="drop_x"), _p(h1), _p(c1),
+            ws.data_ptr(), ws.numel(), _stream()))
+        return h1, c1
     check(lib.sfb_speaker_encoder_step_fwd(C.byref(d), C.byref(wl), B, _p(action_embedding, name="action_embedding"),
                                            C.byref(vs), _p(h0, name="h_0"), _p(c0, name="c_0"), _p(drop_x, name="drop_x"),
                                            _p(h1), _p(c1), ws.data_ptr(), ws.numel(), _stream()))
@@ -458,24 +529,28 @@ def speaker_encoder_step(w: Dict[str, Tensor], action_embedding: Tensor, visual:
 
 
 def speaker_decoder_step(w: Dict[str, Tensor], prev_word: Tensor, h0: Tensor, c0: Tensor, ctx: Tensor,
-                         ctx_mask: Optional[Tensor], drop_e: Optional[Tensor] = None, drop_h: Optional[Tensor] = None):
-    """SpeakerDecoderLSTM.forward default branch (model.py:497-503,515-519) -> (h1, c1, alpha, logit)."""
+                         ctx_mask: Optional[Tensor], drop_e: Optional[Tensor] = None, drop_h: Optional[Tensor] = None,
+                         packed: Optional[Tensor] = None, workspace: Optional[Tensor] = None):
+    """SpeakerDecoderLSTM.forward default branch (model.py:497-503,515-519) -> (h1, c1, alpha, logit).
+    `packed` = PackedSpeakerDecoder().get(w) -> every projection on tcgen05 from packed weights."""
     lib = _lib.load()
     B, T, H = ctx.shape
     vocab, Ew = w["embedding.weight"].shape
     dev = h0.device
-    sw = SpeakerDecoderWeights()
-    sw.embedding = _p(w["embedding.weight"])
-    sw.lstm_w_ih = _p(w["lstm.weight_ih"]); sw.lstm_w_hh = _p(w["lstm.weight_hh"])
-    sw.lstm_b_ih = _p(w["lstm.bias_ih"]); sw.lstm_b_hh = _p(w["lstm.bias_hh"])
-    sw.attn = _softdot_weights(w, "attention_layer.")
-    sw.w_voc = _p(w["decoder2action.weight"]); sw.b_voc = _p(w["decoder2action.bias"])
+    sw = _spk_dec_weights(w)
     pw = _i32(prev_word.reshape(-1))
     m = _mask_u8(ctx_mask)
     need = lib.sfb_speaker_decoder_step_workspace_bytes(H, Ew, B, T)
-    ws = _workspace(need, dev)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, dev)
     h1 = torch.empty(B, H, device=dev); c1 = torch.empty(B, H, device=dev)
     alpha = torch.empty(B, T, device=dev); logit = torch.empty(B, vocab, device=dev)
+    if packed is not None:
+        check(lib.sfb_speaker_decoder_step_packed_fwd(
+            C.byref(sw), packed.data_ptr(), packed.numel(), H, Ew, vocab, B, T, _p(pw, torch.int32, "previous_word"),
+            _p(h0, name="h_0"), _p(c0, name="c_0"), _p(ctx, name="ctx"), _p(m, torch.uint8, "ctx_mask"),
+            _p(drop_e, name="drop_e"), _p(drop_h, name="drop_h"), _p(h1), _p(c1), _p(alpha), _p(logit),
+            ws.data_ptr(), ws.numel(), _stream()))
+        return h1, c1, alpha, logit
     check(lib.sfb_speaker_decoder_step_fwd(C.byref(sw), H, Ew, vocab, B, T, _p(pw, torch.int32, "previous_word"),
                                            _p(h0, name="h_0"), _p(c0, name="c_0"), _p(ctx, name="ctx"),
                                            _p(m, torch.uint8, "ctx_mask"), _p(drop_e, name="drop_e"),

@@ -110,7 +110,7 @@ def test_speaker_train_iteration_and_gradients():
     wdr = {k: v.clone().requires_grad_(k != "embedding.weight") for k, v in wd.items()}
     sc, l, words, wsc = O.speaker_score_teacher([a.cpu() for a in acts], [f.cpu() for f in feats], mask.cpu().bool(), instr, wer, wdr)
     l.backward()
-    assert abs(float(loss) - float(l)) < 1e-3 * max(1.0, abs(float(l)))
+    assert abs(float(loss.detach()) - float(l.detach())) < 1e-3 * max(1.0, abs(float(l.detach())))
     for mod, ref_w in ((enc, wer), (dec, wdr)):
         for k, p in mod.named_parameters():
             if not p.requires_grad:
