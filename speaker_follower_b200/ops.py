@@ -178,9 +178,26 @@ def follower_dims(w: Dict[str, Tensor], V: int = 36) -> Dims:
     return Dims(E, F, H, D, V)
 
 
-def _workspace(nbytes: int, device) -> Tensor:
-    """Zero-filled: the head of a workspace holds self-resetting semaphores (include/sf_b200.h contract)."""
-    return torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+_WS_CACHE: "Dict[tuple, Tensor]" = {}
+_WS_CACHE_MAX = 24
+
+
+def _workspace(nbytes: int, device, sig: tuple = ()) -> Tensor:
+    """Workspace for one (entry point, shape) signature on one device, zero-filled ONCE when it is allocated and then
+    reused by every later call with the same signature (no allocation, no memset per step).  The library's barrier
+    words sit at shape-dependent offsets and return to zero after every launch, so a buffer must not be shared
+    between different layouts — hence the signature in the key.  One stream at a time per device; callers that
+    overlap streams pass their own `workspace=`."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else (torch.cuda.current_device() if dev.type == "cuda" else -1)
+    key = (dev.type, idx, int(nbytes)) + tuple(sig)
+    ws = _WS_CACHE.get(key)
+    if ws is None:
+        if len(_WS_CACHE) >= _WS_CACHE_MAX:
+            _WS_CACHE.pop(next(iter(_WS_CACHE)))
+        ws = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+        _WS_CACHE[key] = ws
+    return ws
 
 
 _FOLLOWER_KEYS = ("lstm.weight_ih", "lstm.weight_hh", "lstm.bias_ih", "lstm.bias_hh",
@@ -320,7 +337,7 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
     mask = _mask_u8(ctx_mask)
     need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, L, A)
     if workspace is None or workspace.numel() < need:
-        workspace = _workspace(need, dev)
+        workspace = _workspace(need, dev, ("follower_step", B, L, A, packed is not None))
     if out is None:
         h1 = torch.empty(B, d.H, device=dev); c1 = torch.empty(B, d.H, device=dev)
         alpha = torch.empty(B, L, device=dev); logit = torch.empty(B, A, device=dev)
@@ -384,7 +401,7 @@ def follower_project_ctx(w: Dict[str, Tensor], packed: Tensor, ctx: Tensor, out:
     B, L, H = ctx.shape
     ctx_k, ctx_o = out if out is not None else (torch.zeros_like(ctx), torch.zeros_like(ctx))
     need = lib.sfb_follower_project_ctx_workspace_bytes(C.byref(d), B, L)
-    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, ctx.device)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, ctx.device, ("project_ctx", B, L))
     check(lib.sfb_follower_project_ctx(C.byref(d), packed.data_ptr(), packed.numel(), B, L, _p(ctx, name="ctx"),
                                        _p(rows, torch.int32, "rows"), 0 if rows is None else rows.numel(),
                                        _p(ctx_k), _p(ctx_o), ws.data_ptr(), ws.numel(), _stream()))
@@ -429,7 +446,7 @@ def visual_attention(w: Dict[str, Tensor], h: Tensor, visual: Optional[Tensor], 
     s.va_w_h = _p(w["visual_attention_layer.linear_in_h.weight"]); s.va_b_h = _p(w["visual_attention_layer.linear_in_h.bias"])
     s.va_w_v = _p(w["visual_attention_layer.linear_in_v.weight"]); s.va_b_v = _p(w["visual_attention_layer.linear_in_v.bias"])
     need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, 1, 1)
-    ws = _workspace(need, h.device)
+    ws = _workspace(need, h.device, ("visual_attention", B))
     feat = torch.empty(B, F, device=h.device); alpha_v = torch.empty(B, V, device=h.device)
     check(lib.sfb_visual_attention_fwd(C.byref(d), C.byref(s), B, _p(h, name="h"), C.byref(vs), _p(feat), _p(alpha_v),
                                        ws.data_ptr(), ws.numel(), _stream()))
@@ -451,7 +468,7 @@ def visual_attention_core(q: Tensor, visual: Optional[Tensor], store=None, vp_id
         feat, alpha_v = out
     need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, 1, 1)
     if workspace is None or workspace.numel() < need:
-        workspace = _workspace(need, q.device)
+        workspace = _workspace(need, q.device, ("visual_attention_core", B))
     check(lib.sfb_visual_attention_core_fwd(C.byref(d), B, _p(q, name="q"), C.byref(vs), _p(feat), _p(alpha_v),
                                             workspace.data_ptr(), workspace.numel(), _stream()))
     return feat, alpha_v
@@ -465,7 +482,7 @@ def soft_dot_attention(w: Dict[str, Tensor], prefix: str, h: Tensor, ctx: Tensor
     sw = _softdot_weights(w, prefix)
     m = _mask_u8(mask)
     need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, L, 1)
-    ws = _workspace(need, h.device)
+    ws = _workspace(need, h.device, ("soft_dot_attention", B, L))
     ht = torch.empty(B, H, device=h.device); alpha = torch.empty(B, L, device=h.device)
     check(lib.sfb_soft_dot_attention_fwd(C.byref(d), C.byref(sw), B, L, _p(h, name="h"), _p(ctx, name="ctx"),
                                          _p(m, torch.uint8, "mask"), _p(ht), _p(alpha), ws.data_ptr(), ws.numel(),
@@ -494,7 +511,7 @@ def encoder_lstm(w: Dict[str, Tensor], seq: Tensor, lengths, bidirectional: bool
         ew.b_ih[i] = _p(w["lstm.bias_ih" + suf]); ew.b_hh[i] = _p(w["lstm.bias_hh" + suf])
     ew.e2d_w = _p(w["encoder2decoder.weight"]); ew.e2d_b = _p(w["encoder2decoder.bias"])
     need = lib.sfb_encoder_lstm_workspace_bytes(ndir, Hd, Ew, B, maxlen)
-    ws = _workspace(need, dev)
+    ws = _workspace(need, dev, ("encoder_lstm", ndir, Hd, Ew, B, maxlen))
     ctx = torch.empty(B, maxlen, H, device=dev); dec = torch.empty(B, H, device=dev); c_t = torch.empty(B, H, device=dev)
     check(lib.sfb_encoder_lstm_fwd(C.byref(ew), ndir, Hd, Ew, B, maxlen, _p(seq32, torch.int32, "seq"),
                                    _p(lens_d, torch.int32, "lengths"), _p(drop_embed, name="drop_embed"),
@@ -514,7 +531,7 @@ def speaker_encoder_step(w: Dict[str, Tensor], action_embedding: Tensor, visual:
     vs = _visual_source(visual, store, vp_idx, view_idx, keep)
     wl = _vis_lstm_weights(w)
     need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, 1, 1)
-    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, h0.device)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, h0.device, ("spk_enc_step", B))
     h1 = torch.empty_like(h0); c1 = torch.empty_like(c0)
     if packed is not None:
         check(lib.sfb_speaker_encoder_step_packed_fwd(
@@ -541,7 +558,7 @@ def speaker_decoder_step(w: Dict[str, Tensor], prev_word: Tensor, h0: Tensor, c0
     pw = _i32(prev_word.reshape(-1))
     m = _mask_u8(ctx_mask)
     need = lib.sfb_speaker_decoder_step_workspace_bytes(H, Ew, B, T)
-    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, dev)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, dev, ("spk_dec_step", B, T))
     h1 = torch.empty(B, H, device=dev); c1 = torch.empty(B, H, device=dev)
     alpha = torch.empty(B, T, device=dev); logit = torch.empty(B, vocab, device=dev)
     if packed is not None:
