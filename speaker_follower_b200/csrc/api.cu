@@ -715,16 +715,15 @@ int32_t sfb_follower_pack_weights(const sfb_dims* dims, const sfb_vis_lstm_weigh
   return 0;
 }
 
+// workspace of the per-episode projection: [barrier words + partial tiles | packed ctx rows].  Bounds that hold for
+// every row count 1..B*L (the caller may pass a compacted subset): split-K only happens while all CTAs are
+// co-resident (<= #SMs tiles of <= 128 x 256 floats); the packed rows take <= 64 KB per K block per 128 rows (+ rounding).
+static size_t project_ctx_region_bytes() { return 4096 + (size_t)device_num_sms() * 128 * 256 * sizeof(float); }
+
 size_t sfb_follower_project_ctx_workspace_bytes(const sfb_dims* dims, int32_t B, int32_t L) {
   if (!dims || B < 1 || L < 1) return 0;
-  const int nkb = kblocks(dims->H);
-  size_t mx = 0;   // the row count may be anything up to B*L (compacted): size for the worst geometry
-  const int ms[3] = {B * L, 2048 < B * L ? 2048 : B * L, 1};
-  for (int i = 0; i < 3; ++i) {
-    const size_t b = gemm_pk_plan(ms[i], 2 * dims->H, nkb, true, device_num_sms(), true).bytes + ((pk_act_bytes(ms[i], nkb, true) + 255) & ~size_t(255));
-    if (b > mx) mx = b;
-  }
-  return mx + (size_t)B * L * 1024;   // slack: tile rounding of intermediate row counts
+  const size_t act = ((size_t)B * L / 128 + 2) * (size_t)kblocks(dims->H) * 65536;
+  return project_ctx_region_bytes() + act;
 }
 
 int32_t sfb_follower_project_ctx(const sfb_dims* dims, const void* packed, size_t packed_bytes, int32_t B, int32_t L,
@@ -744,8 +743,10 @@ int32_t sfb_follower_project_ctx(const sfb_dims* dims, const void* packed, size_
   SFB_CHECK_ARG(rows == nullptr || (n_rows >= 1 && n_rows <= B * L), "rows: 1 <= n_rows <= B*L");
   const int M = rows ? n_rows : B * L, nkb = kblocks(d.H);
   const PkPlan pl = gemm_pk_plan(M, 2 * d.H, nkb, true, device_num_sms(), true);
-  unsigned char* xpk = static_cast<unsigned char*>(workspace) + pl.bytes;
-  SFB_CHECK_ARG(pl.bytes + pk_act_bytes(M, nkb, true) <= workspace_bytes, "project_ctx: workspace too small for this row count");
+  const size_t region = project_ctx_region_bytes();
+  SFB_CHECK_ARG((pl.S == 1 ? pl.sem_bytes : pl.bytes) <= region && region + pk_act_bytes(M, nkb, true) <= workspace_bytes,
+                "project_ctx: workspace too small for this row count");
+  unsigned char* xpk = static_cast<unsigned char*>(workspace) + region;
   // 1. ctx rows -> bf16 hi/lo operand tiles, once (both projections and all four weight tiles of each share them)
   PackParams pp{};
   pp.nseg = 1;
@@ -760,7 +761,7 @@ int32_t sfb_follower_project_ctx(const sfb_dims* dims, const void* packed, size_
   q.g.n_split = d.H; q.g.out2 = ctx_o; q.g.ldo2 = d.H;
   q.g.out_rows = rows;
   q.wide = 1;
-  return launch_gemm_pk(q, st, workspace, pl.bytes);
+  return launch_gemm_pk(q, st, workspace, region);
 }
 
 int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* wl, const void* packed,
