@@ -58,3 +58,39 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.SfbError):
         ops.follower_step(w, x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
                           x["ctx_mask"])
+
+
+def test_packed_path_queries_and_argument_errors(lib):
+    """The packed fast paths report which dimensions they cover and validate arguments before any launch."""
+    d = _lib.Dims(2176, 2176, 512, 256, 36)
+    n = lib.sfb_follower_packed_bytes(C.byref(d))
+    assert n > 48_000_000 and n % 256 == 0                      # >= the 48.5 MB of fp32 weights, as bf16 hi/lo tiles
+    assert lib.sfb_vis_lstm_packed_bytes(C.byref(d)) > 39_000_000
+    assert lib.sfb_speaker_decoder_packed_bytes(512, 300, 991) > 0
+    small = _lib.Dims(48, 40, 32, 16, 36)                        # H % 128 != 0 -> in-place path only
+    assert lib.sfb_follower_packed_bytes(C.byref(small)) == 0
+    assert lib.sfb_vis_lstm_packed_bytes(C.byref(small)) == 0
+    assert lib.sfb_speaker_decoder_packed_bytes(96, 300, 991) == 0
+    assert lib.sfb_speaker_decoder_packed_bytes(512, 301, 991) == 0
+    assert lib.sfb_follower_project_ctx_workspace_bytes(C.byref(d), 100, 80) > 100 * 80 * 512 * 4
+    assert lib.sfb_follower_project_ctx_workspace_bytes(None, 100, 80) == 0
+    st = lib.sfb_follower_pack_weights(C.byref(d), None, None, None, None, 0, None)
+    assert st == -1 and b"NULL" in lib.sfb_last_error()
+    st = lib.sfb_follower_pack_weights(C.byref(small), None, None, None, None, 0, None)
+    assert st == -1 and b"packed path needs" in lib.sfb_last_error()
+    st = lib.sfb_follower_step_packed_fwd(C.byref(d), None, None, 0, 1, 1, 1, None, None, None, *([None] * 11), None, None,
+                                          None, None, None, None, None, 0, None)
+    assert st == -1
+    st = lib.sfb_follower_project_ctx(C.byref(d), None, 0, 1, 1, None, None, 0, None, None, None, 0, None)
+    assert st == -1
+    st = lib.sfb_speaker_decoder_pack_weights(None, 512, 300, 991, None, 0, None)
+    assert st == -1
+
+
+def test_ctx_rows_and_workspace_cache():
+    rows = ops.ctx_rows([3, 1, 0], 4, "cpu")
+    assert rows.dtype == torch.int32 and rows.tolist() == [0, 1, 2, 4]
+    a = ops._workspace(1000, "cpu", ("t", 1))
+    assert a.numel() >= 1000 and int(a.sum()) == 0
+    assert ops._workspace(1000, "cpu", ("t", 1)) is a            # same signature -> same buffer, no re-zeroing
+    assert ops._workspace(1000, "cpu", ("t", 2)) is not a        # different layout -> its own buffer
