@@ -404,8 +404,14 @@ def run_gpu(args, rank, local_rank, world):
                 dst.copy_(src, non_blocking=True)
             torch.cuda.current_stream().synchronize()  # the agent needs a_t on the host to step the simulator
         else:
+            spins = 0
             while np_at.min() < 0:                     # all B actions have landed in host memory
-                pass
+                spins += 1
+                if spins > 2_000_000:                  # ~seconds: something is wrong -> surface the CUDA error, do not hang
+                    torch.cuda.synchronize()
+                    if np_at.min() < 0:
+                        raise RuntimeError("e2e: a_t never reached the host buffer")
+                    break
 
     for i in range(4):
         e2e_step(i)
