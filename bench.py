@@ -36,6 +36,17 @@ def algorithmic_bytes(E, F, H, n_params):
     return 4 * (B * 36 * F + B * L * H + B * A * E + n_params + B * (E + 4 * H) + B * (36 + L + A))
 
 
+def bench_config(world):
+    """One config dict for both arms (the driver compares them key by key)."""
+    return {"workload": "follower decode step B=%d L=%d A=%d V=36 F=2176 (AttnDecoderLSTM.forward + rollout tail), per GPU" % (B, L, A),
+            "batch": B, "instr_len": L, "actions": A,
+            "parallelism": "replicas x%d (instance-sharded, no data-path collective)" % world,
+            "cache": "inputs larger than L2: every step gathers fresh slabs + action candidates from a 3.1 GB device table "
+                     "(%d step sets = 295 MB of distinct slabs), %d rotating episode contexts; ctx is constant within a "
+                     "10-step episode as in the reference rollout; weights (48.5 MB) are step-invariant" % (POOL, N_CTX),
+            "launch": "one CUDA graph per 10-step episode: per-episode ctx projection (inside the timed region) + 10 decode steps"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -91,39 +102,58 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ----------------------------------------------------------------------------------------------- CPU arm
+# ----------------------------------------------------------------------------------------------- reference arms
 _CPU_STATE = {}
+MIN_REF_SECONDS = 2.0         # the reference arm decides the headline ratio: never time less than this
 
 
-def _cpu_setup():
+def _ref_setup():
+    """The reference's own AttnDecoderLSTM (oracle/_ref/model.py, staged unmodified by oracle/make_ref.py) when it
+    travelled with the snapshot, else the oracle port of the same arithmetic."""
     if not _CPU_STATE:
         from oracle import r2r_oracle as O
+        from oracle import make_ref, ref_loader
         from speaker_follower_b200 import synth
+        make_ref.make()
         w = synth.follower_decoder_weights()
         xs = [synth.follower_step_inputs(B, L, A, seed=900 + i, n_viewpoints=128) for i in range(2)]
-        _CPU_STATE.update(O=O, w=w, xs=xs)
-    return _CPU_STATE["O"], _CPU_STATE["w"], _CPU_STATE["xs"]
+        dec = ref_loader.follower_decoder(w)
+        _CPU_STATE.update(O=O, w=w, xs=xs, dec=dec, kind="reference" if dec is not None else "port")
+    return _CPU_STATE
 
 
-def cpu_steps(n_steps, warmup, threads, budget_s=None):
-    """Times the oracle port of AttnDecoderLSTM.forward + tail on the host (reference arithmetic, torch CPU).
-    Stops early once `budget_s` seconds of timed work have been spent; returns (steps/s, seconds, steps done)."""
-    O, w, xs = _cpu_setup()
+def _ref_step(st, dec, w, u, x, h, c):
+    """One decode step + rollout tail with the reference arithmetic on whatever device the tensors live on."""
+    O = st["O"]
+    if dec is not None:   # model.py:377-397, unmodified; bool mask (torch >= 1.2 rejects the uint8 of model.py:135)
+        h, c, alpha, logit, alpha_v = dec(u, x["all_u_t"], x["visual_context"], h, c, x["ctx"], x["ctx_mask"])
+    else:
+        h, c, alpha, logit, alpha_v = O.attn_decoder_step(u, x["all_u_t"], x["visual_context"], h, c, x["ctx"], x["ctx_mask"], w)
+    _, _, a_t, u, sc = O.follower_step_tail(logit, x["is_valid"], None, "argmax", x["all_u_t"])   # follower.py:476-505
+    return h, c, u, a_t
+
+
+def cpu_steps(n_steps, warmup, threads, budget_s=None, min_s=0.0):
+    """Times the reference AttnDecoderLSTM.forward + tail on the host cores (torch CPU).  Runs at least `min_s`
+    seconds and `n_steps` steps, at most `budget_s` seconds; returns (steps/s, seconds, steps done)."""
+    st = _ref_setup()
+    xs, w, dec = st["xs"], st["w"], st["dec"]
     torch.set_num_threads(threads)
-    h, c = xs[0]["h_0"], xs[0]["c_0"]
-    u = xs[0]["u_t_prev"]
-    t0, done = None, 0
+    xs = [dict(x, ctx_mask=x["ctx_mask"].bool()) for x in xs]
+    h, c, u = xs[0]["h_0"], xs[0]["c_0"], xs[0]["u_t_prev"]
+    t0, done, i = None, 0, 0
     with torch.no_grad():
-        for i in range(warmup + n_steps):
+        while True:
             if i == warmup:
                 t0 = time.perf_counter()
-            x = xs[i % 2]
-            h, c, alpha, logit, alpha_v = O.attn_decoder_step(u, x["all_u_t"], x["visual_context"], h, c, x["ctx"],
-                                                              x["ctx_mask"], w)
-            _, _, a_t, u, sc = O.follower_step_tail(logit, x["is_valid"], None, "argmax", x["all_u_t"])
-            if i >= warmup:
+            h, c, u, _ = _ref_step(st, dec, w, u, xs[i % 2], h, c)
+            i += 1
+            if i > warmup:
                 done += 1
-                if budget_s is not None and time.perf_counter() - t0 > budget_s:
+                el = time.perf_counter() - t0
+                if budget_s is not None and el > budget_s:
+                    break
+                if done >= n_steps and el >= min_s:
                     break
     dt = time.perf_counter() - t0
     return done / dt, dt, done
@@ -142,22 +172,77 @@ def cpu_best_threads():
     return best
 
 
+def gpu_reference_steps(dev, seconds=2.0):
+    """BASELINE.md §2 'reference-GPU row' — the 10x denominator of north_star: the reference's own modules moved to
+    the GPU with stock torch kernels, (a) inputs already on the device, (b) including the reference's per-step host
+    batching: np.stack of the B observation slabs + H2D of the [B,36,F] slab and of the dense [B,A,E] action tensor
+    (follower.py:291-320, env.py:330-332).  Returns a dict for the bench line."""
+    st = _ref_setup()
+    w = {k: v.to(dev) for k, v in st["w"].items()}
+    dec = None
+    if st["dec"] is not None:
+        from oracle import ref_loader
+        dec = ref_loader.follower_decoder(st["w"], device=dev)
+    xs_host = st["xs"]
+    xs = [{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in x.items()} for x in xs_host]
+    xs = [dict(x, ctx_mask=x["ctx_mask"].bool()) for x in xs]
+    # what the reference holds on the host after env.observe: one float32 [36,F] array per observation + the action rows
+    slabs = [[np.ascontiguousarray(x["visual_context"][b].numpy()) for b in range(B)] for x in xs_host]
+    acts = [np.ascontiguousarray(x["all_u_t"].numpy()) for x in xs_host]
+
+    def run(with_host_batching):
+        h, c, u = xs[0]["h_0"], xs[0]["c_0"], xs[0]["u_t_prev"]
+        done, t0 = 0, None
+        with torch.no_grad():
+            i = 0
+            while True:
+                if i == 5:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                x = xs[i % 2]
+                if with_host_batching:
+                    vis = torch.from_numpy(np.stack(slabs[i % 2])).to(dev)           # follower.py:291-298, env.py:330-332
+                    allu = torch.from_numpy(acts[i % 2]).to(dev)                     # follower.py:300-320
+                    x = dict(x, visual_context=vis, all_u_t=allu)
+                h, c, u, a_t = _ref_step(st, dec, w, u, x, h, c)
+                a_host = a_t.cpu()                                                   # follower.py:509-513: the env needs a_t
+                i += 1
+                if i > 5:
+                    done += 1
+                    if time.perf_counter() - t0 > seconds:
+                        break
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return done / dt, done, dt
+
+    dev_sps, dev_n, dev_dt = run(False)
+    host_sps, host_n, host_dt = run(True)
+    return {"value": host_sps, "unit": "steps/s", "value_device_inputs": dev_sps, "kind": st["kind"],
+            "sample": "reference AttnDecoderLSTM.forward + rollout tail on this GPU with stock torch %s kernels, a_t read back "
+                      "every step: %d steps (%.1f s) with the reference's per-step host np.stack + H2D of the slab and action "
+                      "tensors (`value`), %d steps (%.1f s) with inputs already on the device (`value_device_inputs`)"
+                      % (torch.__version__, host_n, host_dt, dev_n, dev_dt)}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    st = _ref_setup()
     threads = cpu_best_threads()
-    # bounded sample: every step is the full B=100 workload; at most ~60 s of CPU work whatever --steps says
-    sps, dt, done = cpu_steps(args.steps, max(args.warmup, 3) if args.warmup < 20 else 5, threads, budget_s=60.0)
+    # bounded sample: every step is the full B=100 workload; at least MIN_REF_SECONDS, at most ~60 s of CPU work
+    sps, dt, done = cpu_steps(args.steps, max(args.warmup, 3) if args.warmup < 20 else 5, threads, budget_s=60.0,
+                              min_s=MIN_REF_SECONDS)
+    what = ("the reference's own tasks/R2R/model.py (oracle/_ref, staged unmodified)" if st["kind"] == "reference"
+            else "torch-CPU oracle port of tasks/R2R/model.py (oracle/_ref absent)")
     line = {
         "impl": "reference", "metric": "follower decode-steps/sec", "value": sps, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 / sps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "follower decode step B=%d L=%d A=%d V=36 F=2176 (AttnDecoderLSTM.forward + rollout tail)" % (B, L, A),
-                   "batch": B, "instr_len": L, "actions": A},
-        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
-                         "sample": "%d decode steps (%.1f s) of the same workload, torch-CPU oracle port of tasks/R2R/model.py; "
-                                   "thread count picked as the fastest of a short sweep up to %d hardware threads "
-                                   "(the reference is Python/torch and cannot travel to the GPU box)" % (done, dt, os.cpu_count() or 1)},
+        "config": bench_config(args.gpus),
+        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": st["kind"],
+                         "sample": "%d decode steps (%.1f s, never less than %.0f s) of the same workload, %s; "
+                                   "thread count picked as the fastest of a short sweep up to %d hardware threads"
+                                   % (done, dt, MIN_REF_SECONDS, what, os.cpu_count() or 1)},
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -458,17 +543,13 @@ def run_gpu(args, rank, local_rank, world):
     if rank == 0:
         threads = cpu_best_threads()
         cpu_sps, cpu_dt, cpu_n = cpu_steps(4000, 3, threads, budget_s=15.0)
+        gpu_base = gpu_reference_steps(dev)
+        log("reference-GPU baseline done")
         line = {
             "metric": "follower decode-steps/sec", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "follower decode step B=%d L=%d A=%d V=36 F=2176 (AttnDecoderLSTM.forward + rollout tail), per GPU" % (B, L, A),
-                       "batch": B, "instr_len": L, "actions": A, "parallelism": "replicas x%d (instance-sharded, no data-path collective)" % world,
-                       "cache": "inputs larger than L2: every step gathers fresh slabs + action candidates from a 3.1 GB device table "
-                                "(%d step sets = 295 MB of distinct slabs), %d rotating episode contexts; ctx is constant within a "
-                                "10-step episode as in the reference rollout; weights (48.5 MB) are step-invariant" % (POOL, N_CTX),
-                       "launch": "one CUDA graph per 10-step episode: per-episode ctx projection (2 launches, inside the timed region) "
-                                 "+ 10 decode steps"},
+            "config": bench_config(world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
@@ -481,9 +562,14 @@ def run_gpu(args, rank, local_rank, world):
                                 "per launch from profiles/r01_attn_ncu_full.txt" % n_attn},
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s",
                               "frac": step_gbs / hbm_peak, "bytes_per_step": step_bytes},
-            "cpu_baseline": {"value": cpu_sps, "unit": "steps/s", "cores": threads, "kind": "port",
-                             "sample": "%d decode steps (%.1f s) of the same workload, torch-CPU oracle port of tasks/R2R/model.py, "
-                                       "fastest thread count of a short sweep" % (cpu_n, cpu_dt)},
+            "cpu_baseline": {"value": cpu_sps, "unit": "steps/s", "cores": threads, "kind": _CPU_STATE["kind"],
+                             "sample": "%d decode steps (%.1f s) of the same workload, %s, fastest thread count of a short sweep"
+                                       % (cpu_n, cpu_dt, "the reference's own tasks/R2R/model.py (oracle/_ref)"
+                                          if _CPU_STATE["kind"] == "reference" else "torch-CPU oracle port of tasks/R2R/model.py")},
+            "gpu_baseline": dict(gpu_base, vs={"value_over_gpu_baseline": value / world / gpu_base["value"],
+                                              "e2e_over_gpu_baseline": e2e_value / world / gpu_base["value"],
+                                              "value_over_gpu_baseline_device_inputs": value / world / gpu_base["value_device_inputs"],
+                                              "e2e_over_gpu_baseline_device_inputs": e2e_value / world / gpu_base["value_device_inputs"]}),
         }
         print(json.dumps(line))
     if dist is not None:

@@ -104,6 +104,10 @@ int32_t sfb_debug_read_trace(int64_t* out, int32_t max_slots);
  * stream done, exit, smid, query ready} (8 int64 per CTA, globaltimer ns); returns the number of CTA records copied. */
 int32_t sfb_debug_read_cta_trace(int64_t* out, int32_t max_ctas);
 
+/* Bring-up: how many thread-block clusters of `cluster` CTAs (320 threads, `smem` dynamic bytes each) the device can
+ * hold at once (cudaOccupancyMaxActiveClusters on the tensor-core projection kernel); negative on error. */
+int32_t sfb_debug_max_active_clusters(int32_t cluster, int32_t smem);
+
 /* Device properties the library was built for / sees.  Fills sm (e.g. 100), number of SMs and max
  * opt-in shared memory per block; returns SFB_ERR_NO_DEVICE when there is no usable device. */
 int32_t sfb_device_info(int32_t* sm, int32_t* num_sms, int32_t* smem_per_block);

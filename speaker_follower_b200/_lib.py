@@ -72,6 +72,7 @@ SIGNATURES = {
     "sfb_debug_read_trace": (C.c_int32, [C.c_void_p, C.c_int32]),
     "sfb_debug_read_cta_trace": (C.c_int32, [C.c_void_p, C.c_int32]),
     "sfb_debug_read_timestamps": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "sfb_debug_max_active_clusters": (C.c_int32, [C.c_int32, C.c_int32]),
     "sfb_device_info": (C.c_int32, [C.POINTER(C.c_int32)] * 3),
     "sfb_follower_step_workspace_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32, C.c_int32, C.c_int32]),
     "sfb_speaker_decoder_step_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

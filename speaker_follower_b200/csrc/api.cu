@@ -24,7 +24,7 @@ unsigned long long* next_trace_slot() {
 
 static unsigned long long* g_cta_buf = nullptr;   // [4096][8]
 static int g_cta_on = 0;
-int g_attn_force_cl = 0, g_attn_force_stages = 0, g_attn_no_hint = 0;
+int g_attn_force_cl = 0, g_attn_force_stages = 0, g_attn_no_hint = 0, g_attn_ring_kb = 0, g_attn_rb = 0;
 static int g_q_with_hh = 0;
 unsigned long long* cta_trace_buffer() { return g_cta_on ? g_cta_buf : nullptr; }
 
@@ -349,6 +349,8 @@ int32_t sfb_set_option(const char* name, int32_t value) {
   if (n == "tc_debug") { gemm_tc_set_debug(value); return 0; }
   if (n == "attn_cl") { g_attn_force_cl = value; return 0; }
   if (n == "attn_stages") { g_attn_force_stages = value; return 0; }
+  if (n == "attn_ring_kb") { g_attn_ring_kb = value; return 0; }
+  if (n == "attn_rb") { g_attn_rb = value; return 0; }
   if (n == "q_with_hh") { g_q_with_hh = value; return 0; }
   if (n == "attn_nohint") { g_attn_no_hint = value; return 0; }
   if (n == "cta_trace") {   // per-CTA timeline of the attention kernel (last launch wins)
@@ -374,6 +376,8 @@ int32_t sfb_debug_read_cta_trace(int64_t* out, int32_t max_ctas) {
   if (cudaMemcpy(out, g_cta_buf, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return n;
 }
+
+int32_t sfb_debug_max_active_clusters(int32_t cluster, int32_t smem) { return pk_max_active_clusters(cluster, smem); }
 
 int32_t sfb_debug_read_timestamps(int64_t* out, int32_t n) {
   return gemm_tc_read_timestamps(reinterpret_cast<long long*>(out), n);

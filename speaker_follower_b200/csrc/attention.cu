@@ -33,8 +33,8 @@ constexpr size_t ATT_RING_BUDGET = 52 * 1024;  // bytes of ring per CTA -> 4 CTA
 }  // namespace
 
 // NJ float4 slices per thread, NT threads per CTA (D <= NJ * NT * 4), RB rows consumed per block barrier
-template <int NJ, int NT, int RB>
-__global__ void __launch_bounds__(NT, NT == 256 ? 4 : 8) soft_dot_attn_kernel(const AttnParams p) {
+template <int NJ, int NT, int RB, int MINB = (NT == 256 ? 4 : 8)>
+__global__ void __launch_bounds__(NT, MINB) soft_dot_attn_kernel(const AttnParams p) {
   constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -346,9 +346,9 @@ AttnPlan attention_plan(int B, int R, int D, int num_sms, bool kv) {
   return pl;
 }
 
-template <int NJ, int NT, int RB>
+template <int NJ, int NT, int RB, int MINB = (NT == 256 ? 4 : 8)>
 static int32_t launch_attn_t(const AttnParams& p, int B, int cl, cudaStream_t stream) {
-  auto kern = soft_dot_attn_kernel<NJ, NT, RB>;
+  auto kern = soft_dot_attn_kernel<NJ, NT, RB, MINB>;
   const size_t smem = attn_smem_bytes(p.stages, p.keyA ? 2 * p.D : p.D, p.rows_per_cta);
   static size_t configured = 0;  // per instantiation
   if (smem > configured) {
@@ -376,7 +376,8 @@ int32_t launch_soft_dot_attention(AttnParams p, int B, void* ws, size_t ws_bytes
   if (g_attn_force_cl > 0) {   // bring-up: force the cluster size
     pl.split = g_attn_force_cl;
     pl.rows_per_cta = (p.R + pl.split - 1) / pl.split;
-    int st = (int)(ATT_RING_BUDGET / ((size_t)SD * 4));
+    const size_t budget = g_attn_ring_kb > 0 ? (size_t)g_attn_ring_kb * 1024 : ATT_RING_BUDGET;
+    int st = (int)(budget / ((size_t)SD * 4));
     st = st > pl.rows_per_cta ? pl.rows_per_cta : st;
     pl.stages = st < 4 ? 4 : (st > ATT_MAX_STAGES ? ATT_MAX_STAGES : st);
   }
@@ -392,6 +393,10 @@ int32_t launch_soft_dot_attention(AttnParams p, int B, void* ws, size_t ws_bytes
   SFB_CHECK_ARG(attn_smem_bytes(p.stages, SD, p.rows_per_cta) <= 200 * 1024, "attention rows do not fit shared memory");
   if (p.D <= 512) return launch_attn_t<1, 128, 4>(p, B, pl.split, stream);
   if (p.D <= 1024) return launch_attn_t<1, 256, 4>(p, B, pl.split, stream);
+  if (g_attn_rb == 2) return launch_attn_t<3, 256, 2, 1>(p, B, pl.split, stream);
+  if (g_attn_rb == 3) return launch_attn_t<3, 256, 3, 1>(p, B, pl.split, stream);
+  if (g_attn_rb == 4) return launch_attn_t<3, 256, 4, 1>(p, B, pl.split, stream);
+  if (g_attn_rb == 1) return launch_attn_t<3, 256, 1, 1>(p, B, pl.split, stream);
   return launch_attn_t<3, 256, 1>(p, B, pl.split, stream);
 }
 

@@ -456,6 +456,24 @@ size_t pk_act_bytes(int M, int nkb, bool wide) {
   return (size_t)nz * nkb * 2 * (size_t)(NB / 8) * PSBO;
 }
 
+// bring-up: how many clusters of `cluster` CTAs of this kernel (320 threads, `smem` bytes) can be resident at once
+int pk_max_active_clusters(int cluster, int smem) {
+  auto kern = gemm_pk_kernel<true, false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+  if (cluster > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cluster * 64, 1, 1);
+  cfg.blockDim = dim3(320, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return -3; }
+  return n;
+}
+
 int32_t launch_gemm_pk(const PkParams& q_in, cudaStream_t stream, void* ws, size_t ws_bytes) {
   PkParams q = q_in;
   GemmParams& p = q.g;

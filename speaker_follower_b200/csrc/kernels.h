@@ -152,6 +152,7 @@ int pk_num_kblocks(const int* seg_k, int nseg);
 size_t pk_weight_bytes(int N_rows, int nkb);
 size_t pk_act_bytes(int M, int nkb, bool wide = false);
 int32_t launch_gemm_pk(const PkParams& q, cudaStream_t stream, void* ws, size_t ws_bytes);
+int pk_max_active_clusters(int cluster, int smem);
 
 // ---------------------------------------------------------------- pointwise.cu
 struct TailParams {
@@ -182,6 +183,6 @@ int32_t launch_follower_tail(const TailParams& p, cudaStream_t stream);
 int device_num_sms();
 unsigned long long* next_trace_slot();
 unsigned long long* cta_trace_buffer();  // NULL unless sfb_set_option("cta_trace", 1)
-extern int g_attn_force_cl, g_attn_force_stages, g_attn_no_hint;   // NULL unless sfb_set_option("trace", 1)
+extern int g_attn_force_cl, g_attn_force_stages, g_attn_no_hint, g_attn_ring_kb, g_attn_rb;   // NULL unless sfb_set_option("trace", 1)
 
 }  // namespace sfb
