@@ -129,6 +129,12 @@ def _ref_step(st, dec, w, u, x, h, c):
         h, c, alpha, logit, alpha_v = dec(u, x["all_u_t"], x["visual_context"], h, c, x["ctx"], x["ctx_mask"])
     else:
         h, c, alpha, logit, alpha_v = O.attn_decoder_step(u, x["all_u_t"], x["visual_context"], h, c, x["ctx"], x["ctx_mask"], w)
+    if logit.is_cuda:     # the reference's own tail ops (follower.py:476-505, argmax feedback) on the tensors' device
+        logit = logit.masked_fill(x["is_valid"] == 0, -float("inf"))
+        a_t = logit.max(1)[1]
+        u = x["all_u_t"][torch.arange(logit.shape[0], device=logit.device), a_t].detach()
+        sc = torch.log_softmax(logit, 1).gather(1, a_t.unsqueeze(1))
+        return h, c, u, a_t
     _, _, a_t, u, sc = O.follower_step_tail(logit, x["is_valid"], None, "argmax", x["all_u_t"])   # follower.py:476-505
     return h, c, u, a_t
 
@@ -179,10 +185,10 @@ def gpu_reference_steps(dev, seconds=2.0):
     (follower.py:291-320, env.py:330-332).  Returns a dict for the bench line."""
     st = _ref_setup()
     w = {k: v.to(dev) for k, v in st["w"].items()}
-    dec = None
-    if st["dec"] is not None:
-        from oracle import ref_loader
-        dec = ref_loader.follower_decoder(st["w"], device=dev)
+    if st["dec"] is None:
+        return {"unavailable": "oracle/_ref (the staged reference sources) is absent on this box"}
+    from oracle import ref_loader
+    dec = ref_loader.follower_decoder(st["w"], device=dev)
     xs_host = st["xs"]
     xs = [{k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in x.items()} for x in xs_host]
     xs = [dict(x, ctx_mask=x["ctx_mask"].bool()) for x in xs]
@@ -328,7 +334,8 @@ def run_gpu(args, rank, local_rank, world):
     ws = torch.zeros(1 << 26, dtype=torch.uint8, device=dev)   # zero-filled once (semaphores)
     launches_per_step = [0]
 
-    qbuf = [torch.empty(B, F, device=dev), torch.empty(B, F, device=dev)]   # visual query carried across steps
+    # state one step prepares for the next (visual query + packed gate-operand blocks), ping-pong
+    qbuf = [ops.follower_carry(w, B), ops.follower_carry(w, B)] if blob is not None else [None, None]
     # per-episode projections of ctx (ctx is constant over the 10 decode steps of a rollout): recomputed INSIDE the
     # timed region at the start of every episode (project()), never cached across episodes
     use_proj = blob is not None and not os.environ.get("SFB_NO_CTXPROJ")
@@ -355,10 +362,10 @@ def run_gpu(args, rank, local_rank, world):
             ops.follower_tail(logit, valid[j], U[j], "argmax", out=(a_t, ubuf[s ^ 1], score, None))
             launches_per_step[0] = n + ops.last_launch_count()
             return
-        # packed weights; q_next of this step is the q_in of the next one; rollout tail fused into the last kernel
+        # packed weights; carry_out of this step is the carry_in of the next one; rollout tail fused into the last kernel
         ops.follower_step(w, ubuf[s], None, None, hbuf[s], cbuf[s], ctx[e], mask, store=store, vp_idx=vp[j],
                           view_idx=view[j], workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit, alpha_v),
-                          packed=blob, q_in=None if first else qbuf[s], q_next=qbuf[s ^ 1],
+                          packed=blob, carry_in=None if first else qbuf[s], carry_out=qbuf[s ^ 1],
                           cand_view=cview[j], cand_trig=ctrig[j], ctx_proj=cproj[e],
                           tail={"is_valid": valid[j], "feedback": "argmax", "out": (a_t, ubuf[s ^ 1], score, None)})
         launches_per_step[0] = ops.last_launch_count()
@@ -388,7 +395,7 @@ def run_gpu(args, rank, local_rank, world):
         with torch.cuda.graph(gph):
             project(e)
             for i in range(POOL):
-                step(i, e=e)
+                step(i, first=(i == 0), e=e)   # a new episode starts from fresh (h_0, u_begin): no carried state
         episodes.append(gph)
     singles = []
     for i in range(POOL):
@@ -396,7 +403,7 @@ def run_gpu(args, rank, local_rank, world):
         with torch.cuda.graph(gph):
             if i == 0:
                 project(0)
-            step(i, e=0)
+            step(i, first=(i == 0), e=0)
         singles.append(gph)
 
     log("graphs captured")
@@ -472,7 +479,7 @@ def run_gpu(args, rank, local_rank, world):
                 else:
                     ops.follower_step(w, ubuf[s], None, None, hbuf[s], cbuf[s], ctx[0], mask, store=store, vp_idx=d_vp,
                                       view_idx=d_view, workspace=ws, out=(hbuf[s ^ 1], cbuf[s ^ 1], alpha, logit2, alpha_v),
-                                      packed=blob, q_in=qbuf[s], q_next=qbuf[s ^ 1], cand_view=d_cview, cand_trig=d_ctrig,
+                                      packed=blob, carry_in=None if with_proj else qbuf[s], carry_out=qbuf[s ^ 1], cand_view=d_cview, cand_trig=d_ctrig,
                                       ctx_proj=cproj[0],
                                       tail={"is_valid": d_valid, "feedback": "argmax", "out": (a_t2, ubuf[s ^ 1], score, None)})
             (graphs2_first if with_proj else graphs2).append(gph)
@@ -566,10 +573,11 @@ def run_gpu(args, rank, local_rank, world):
                              "sample": "%d decode steps (%.1f s) of the same workload, %s, fastest thread count of a short sweep"
                                        % (cpu_n, cpu_dt, "the reference's own tasks/R2R/model.py (oracle/_ref)"
                                           if _CPU_STATE["kind"] == "reference" else "torch-CPU oracle port of tasks/R2R/model.py")},
-            "gpu_baseline": dict(gpu_base, vs={"value_over_gpu_baseline": value / world / gpu_base["value"],
-                                              "e2e_over_gpu_baseline": e2e_value / world / gpu_base["value"],
-                                              "value_over_gpu_baseline_device_inputs": value / world / gpu_base["value_device_inputs"],
-                                              "e2e_over_gpu_baseline_device_inputs": e2e_value / world / gpu_base["value_device_inputs"]}),
+            "gpu_baseline": gpu_base if "unavailable" in gpu_base else dict(gpu_base, vs={
+                "value_over_gpu_baseline": value / world / gpu_base["value"],
+                "e2e_over_gpu_baseline": e2e_value / world / gpu_base["value"],
+                "value_over_gpu_baseline_device_inputs": value / world / gpu_base["value_device_inputs"],
+                "e2e_over_gpu_baseline_device_inputs": e2e_value / world / gpu_base["value_device_inputs"]}),
         }
         print(json.dumps(line))
     if dist is not None:

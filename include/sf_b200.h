@@ -204,6 +204,7 @@ typedef struct sfb_step_tail {
   float*         ce;            /* [B] or NULL */
 } sfb_step_tail;
 size_t  sfb_follower_packed_bytes(const sfb_dims* dims);
+size_t  sfb_follower_carry_bytes(const sfb_dims* dims, int32_t B);
 int32_t sfb_follower_pack_weights(const sfb_dims* dims, const sfb_vis_lstm_weights* wl,
                                   const sfb_softdot_weights* wt, const sfb_scoring_weights* ws,
                                   void* packed, size_t packed_bytes, void* stream);
@@ -214,7 +215,7 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
                                      const float* h0, const float* c0, const float* ctx, const uint8_t* ctx_mask,
                                      const float* drop_x, const float* drop_h,
                                      float* h1, float* c1, float* alpha, float* logit, float* alpha_v,
-                                     const float* q_in, float* q_next, const sfb_step_tail* tail,
+                                     void* carry_in, void* carry_out, const sfb_step_tail* tail,
                                      const sfb_action_source* act, const float* ctx_k, const float* ctx_o,
                                      void* workspace, size_t workspace_bytes, void* stream);
 

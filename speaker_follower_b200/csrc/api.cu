@@ -7,6 +7,7 @@
 namespace sfb {
 
 int g_disable_tc = 0;
+int g_disable_fused = 0;
 int g_disable_pdl = 0;
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
@@ -61,6 +62,7 @@ struct FollowerWs {
   void* pk; size_t pk_bytes;
   unsigned char* bpk; size_t bpk_bytes;
   float* th;
+  void* fz; size_t fz_bytes;              // fused gather + LSTM kernel: barrier / counter words + partial tiles
   int ldg;
   int splitk;
   size_t bytes;
@@ -109,9 +111,23 @@ static FollowerWs carve_follower(const sfb_dims& d, int B, int L, int A, void* w
     w.bpk_bytes = pk_act_bytes(B, nkb_g);
     w.bpk = reinterpret_cast<unsigned char*>(c.take(w.bpk_bytes / sizeof(float)));
     w.th = c.take((size_t)B * 2 * d.H);
+    const FusedPlan fp = vis_lstm_fused_plan(B, d.H, nkb_g, d.V, d.F, d.F, 0, sms);
+    w.fz_bytes = fp.ok ? fp.bytes : 256;
+    w.fz = c.take(w.fz_bytes / sizeof(float));
   }
   w.bytes = c.off;
   return w;
+}
+
+// ---- state carried from one decode step to the next (opaque to the caller): the visual query of the coming step and
+// the gate GEMM's packed activation operand, whose u_prev / h_0 blocks the previous step has already filled in
+struct CarryLayout { size_t q, bpk, bytes; };
+static CarryLayout layout_carry(const sfb_dims& d, int B) {
+  CarryLayout L{};
+  L.q = 0;
+  L.bpk = (((size_t)B * d.F * sizeof(float)) + 255) & ~size_t(255);
+  L.bytes = L.bpk + ((pk_act_bytes(B, kblocks(d.E) + kblocks(d.F) + kblocks(d.H)) + 255) & ~size_t(255));
+  return L;
 }
 
 // ---- packed follower-decoder weights: offsets into the caller-owned blob
@@ -337,6 +353,7 @@ int32_t sfb_set_option(const char* name, int32_t value) {
   const std::string n(name ? name : "");
   if (n == "disable_tc") { g_disable_tc = value; return 0; }
   if (n == "disable_pdl") { g_disable_pdl = value; return 0; }
+  if (n == "disable_fused") { g_disable_fused = value; return 0; }
   if (n == "trace") {   // value 1: (re)start recording kernel slots; 0: stop
     g_trace_on = value;
     g_trace_n = 0;
@@ -661,6 +678,11 @@ int32_t sfb_speaker_decoder_step_fwd(const sfb_speaker_decoder_weights* w, int32
   return launch_gemm(g, st);
 }
 
+size_t sfb_follower_carry_bytes(const sfb_dims* dims, int32_t B) {
+  if (!dims || check_dims(dims) != 0 || check_packable(*dims) != 0 || B < 1) return 0;
+  return layout_carry(*dims, B).bytes;
+}
+
 size_t sfb_follower_packed_bytes(const sfb_dims* dims) {
   if (!dims || check_dims(dims) != 0 || check_packable(*dims) != 0) return 0;
   return layout_follower_pk(*dims).bytes;
@@ -773,7 +795,7 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
                                      const float* all_u_t, const sfb_visual_source* vis, const float* h0,
                                      const float* c0, const float* ctx, const uint8_t* ctx_mask, const float* drop_x,
                                      const float* drop_h, float* h1, float* c1, float* alpha, float* logit,
-                                     float* alpha_v, const float* q_in, float* q_next, const sfb_step_tail* tail,
+                                     float* alpha_v, void* carry_in, void* carry_out, const sfb_step_tail* tail,
                                      const sfb_action_source* act, const float* ctx_k, const float* ctx_o,
                                      void* workspace, size_t workspace_bytes, void* stream) {
   reset_launch_count();
@@ -783,6 +805,8 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
   SFB_CHECK_ARG(u_prev && h0 && c0 && ctx && h1 && c1 && logit, "NULL tensor argument");
   SFB_CHECK_ARG(B >= 1 && L >= 1 && A >= 1, "B, L, A >= 1");
   SFB_CHECK_ARG((ctx_k == nullptr) == (ctx_o == nullptr), "ctx_k and ctx_o must be given together");
+  SFB_CHECK_ARG((!carry_in || (reinterpret_cast<uintptr_t>(carry_in) & 255u) == 0) && (!carry_out || (reinterpret_cast<uintptr_t>(carry_out) & 255u) == 0) &&
+                    (!carry_in || carry_in != carry_out), "carry buffers must be 256-byte aligned and distinct");
   const bool act_gather = act && act->all_u_t == nullptr;
   if (act_gather) {
     SFB_CHECK_ARG(act->feat_table && act->vp_idx && act->cand_view && act->cand_trig, "gather action source needs table, indices and trig values");
@@ -818,39 +842,89 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
     q.g.n_split = n_split; q.g.out2 = out2; q.g.ldo2 = ldo2; q.g.bias2 = bias2;
     return launch_gemm_pk(q, st, ws.pk, ws.pk_bytes);
   };
-  // model.py:389  visual query q = W_v^T (W_h h_0 + b_h) = M_q h_0 + b_q: carried over from the previous step's fused
-  // projection when the caller passes it (q_in), computed here otherwise
-  const float* qv = q_in;
-  if (!qv) {
-    SFB_PROPAGATE(proj(base + P.a_q, h0, d.H, d.H, d.F, ws.q, d.F, b_q, nullptr, 0, 0, 0, nullptr, 0, nullptr));
-    qv = ws.q;
-  }
-  // The gate GEMM's activation operand [u_prev | feature | h0] (.) drop_x is packed by the attention kernel: u_prev and
-  // h0 as a side job of all its threads, feature in its epilogue.
+  // ---- state carried across steps (see layout_carry): q of this step + the packed [u_prev | . | h_0] operand blocks.
+  // Train mode (drop_x) re-packs u_prev under this step's mask, so only eval steps consume a carried operand.
+  const CarryLayout CL = layout_carry(d, B);
   const PkPlan gpl = gemm_pk_plan(B, 4 * d.H, P.nkb_gates, true, device_num_sms());
-  {
-    AttnParams pk{};
-    pk.pk_out = ws.bpk; pk.pk_kb0 = kblocks(d.E); pk.pk_nkb = P.nkb_gates; pk.pk_NB = gpl.NB; pk.pk_rows_per_z = gpl.rows_per_z;
-    pk.pk_scale = drop_x ? drop_x + d.E : nullptr; pk.pk_ldscale = d.E + d.F;
-    pk.has_side = 1;
-    PackParams& side = pk.side;
+  const int vis_lenA = vis->visual ? d.F : vis->img_dim, vis_lenB = vis->visual ? 0 : d.F - vis->img_dim;
+  if (!vis->visual) {
+    SFB_CHECK_ARG(vis->feat_table && vis->loc_table && vis->vp_idx && vis->view_idx, "gather visual source needs tables + indices");
+    SFB_CHECK_ARG(vis->img_dim > 0 && vis->img_dim < d.F && (vis->img_dim % 4) == 0, "bad img_dim");
+  }
+  const FusedPlan fpl = vis_lstm_fused_plan(B, d.H, P.nkb_gates, d.V, d.F, vis_lenA, vis_lenB, device_num_sms());
+  const bool fused = fpl.ok && !g_disable_fused && gpl.nz == 1 && gpl.NB == fpl.NB;
+  const bool use_carry = carry_in != nullptr && drop_x == nullptr;
+  float* q_next = carry_out ? reinterpret_cast<float*>(static_cast<char*>(carry_out) + CL.q) : nullptr;
+  unsigned char* bpk_next = carry_out ? reinterpret_cast<unsigned char*>(carry_out) + CL.bpk : nullptr;
+  const float* qv = use_carry ? reinterpret_cast<const float*>(static_cast<char*>(carry_in) + CL.q) : nullptr;
+  unsigned char* bpk_cur = (use_carry && fused) ? reinterpret_cast<unsigned char*>(carry_in) + CL.bpk : ws.bpk;
+  auto side_pack = [&](PackParams& side) {   // [u_prev (.) drop | (attention output: written elsewhere) | h_0] -> bpk_cur
     side.nseg = 3;
     side.seg[0] = PackSeg{u_prev, d.E, d.E, drop_x, drop_x ? d.E + d.F : 0, nullptr};
-    side.seg[1] = PackSeg{nullptr, d.F, d.F, nullptr, 0, nullptr};   // written by the attention epilogue
+    side.seg[1] = PackSeg{nullptr, d.F, d.F, nullptr, 0, nullptr};
     side.seg[2] = PackSeg{h0, d.H, d.H, nullptr, 0, nullptr};
     side.ntile = gpl.nz; side.R = gpl.NB; side.rows_per_tile = gpl.rows_per_z; side.rows_valid = B; side.lstm_H = 0;
-    side.out = ws.bpk;
-    SFB_PROPAGATE(visual_attend(d, B, qv, *vis, ws.feat, alpha_v, ws.av, ws.av_bytes, st, &pk));
-  }
-  // model.py:391-393  LSTMCell(drop(cat(u_t_prev, feature)), (h_0, c_0)) on tcgen05 from the packed operands
-  {
+    side.out = bpk_cur;
+  };
+  // model.py:389  visual query q = W_v^T (W_h h_0 + b_h) = M_q h_0 + b_q: carried over from the previous step when the
+  // caller passes its carry, computed here otherwise (the fused path packs u_prev / h_0 as a side job of this launch)
+  if (!qv) {
     PkParams q{};
-    q.a_pk = base + P.a_gates; q.b_pk = ws.bpk; q.nkb = P.nkb_gates;
-    q.g.M = B; q.g.N = 4 * d.H;
-    LstmEpilogue& e = q.g.lstm;
-    e.H = d.H; e.b_ih = wl->lstm_b_ih; e.b_hh = wl->lstm_b_hh; e.c0 = c0; e.drop_h = drop_h;
-    e.h1 = h1; e.c1 = c1; e.h1_drop = ws.h1d; e.gates_act = ws.gates_act;
+    q.a_pk = base + P.a_q; q.b_pk = nullptr; q.nkb = kblocks(d.H);
+    q.g.nseg = 1;
+    q.g.seg[0] = GemmSeg{h0, d.H, nullptr, nullptr, 0, nullptr, 0, d.H, 0};
+    q.g.M = B; q.g.N = d.F; q.g.out = ws.q; q.g.ldo = d.F; q.g.bias0 = b_q;
+    if (fused) {
+      q.has_side = 1;
+      side_pack(q.side);
+    }
     SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));
+    qv = ws.q;
+  }
+  LstmEpilogue lstm_e{};
+  lstm_e.H = d.H; lstm_e.b_ih = wl->lstm_b_ih; lstm_e.b_hh = wl->lstm_b_hh; lstm_e.c0 = c0; lstm_e.drop_h = drop_h;
+  lstm_e.h1 = h1; lstm_e.c1 = c1; lstm_e.h1_drop = ws.h1d; lstm_e.gates_act = ws.gates_act;
+  if (bpk_next && gpl.nz == 1) {   // h_1 in packed form: the h_0 blocks of the next step's gate GEMM
+    lstm_e.hpk = bpk_next; lstm_e.hpk_kb0 = kblocks(d.E) + kblocks(d.F); lstm_e.hpk_nkb = P.nkb_gates;
+    lstm_e.hpk_NB = gpl.NB; lstm_e.hpk_rows_per_z = gpl.rows_per_z;
+  }
+  if (fused) {
+    // model.py:389-393 as ONE launch (step_fused.cu): attention gather + gate GEMM + LSTM cell
+    FusedVisLstmParams f{};
+    f.q = qv; f.ldq = d.F; f.R = d.V; f.D = d.F;
+    if (vis->visual) {
+      f.segA = vis->visual; f.strideA_b = (long long)d.V * d.F; f.lenA = d.F; f.lenB = 0;
+    } else {
+      const int loc = d.F - vis->img_dim;
+      f.segA = vis->feat_table; f.strideA_b = (long long)d.V * vis->img_dim; f.lenA = vis->img_dim; f.idxA = vis->vp_idx;
+      f.segB = vis->loc_table; f.strideB_b = (long long)d.V * loc; f.lenB = loc; f.idxB = vis->view_idx;
+    }
+    f.feat = ws.feat; f.ldfeat = d.F; f.alpha = alpha_v; f.ldalpha = d.V;
+    f.pk_scale = drop_x ? drop_x + d.E : nullptr; f.pk_ldscale = d.E + d.F;
+    f.a_pk = base + P.a_gates; f.b_pk = bpk_cur; f.nkb = P.nkb_gates;
+    f.post_kb0 = kblocks(d.E); f.post_kb1 = kblocks(d.E) + kblocks(d.F);
+    f.g.lstm = lstm_e; f.g.M = B; f.g.N = 4 * d.H;
+    f.B = B;
+    SFB_PROPAGATE(launch_vis_lstm_fused(f, st, ws.fz, ws.fz_bytes));
+  } else {
+    // The gate GEMM's activation operand [u_prev | feature | h0] (.) drop_x is packed by the attention kernel: u_prev and
+    // h0 as a side job of all its threads, feature in its epilogue.
+    {
+      AttnParams pk{};
+      pk.pk_out = ws.bpk; pk.pk_kb0 = kblocks(d.E); pk.pk_nkb = P.nkb_gates; pk.pk_NB = gpl.NB; pk.pk_rows_per_z = gpl.rows_per_z;
+      pk.pk_scale = drop_x ? drop_x + d.E : nullptr; pk.pk_ldscale = d.E + d.F;
+      pk.has_side = 1;
+      side_pack(pk.side);
+      SFB_PROPAGATE(visual_attend(d, B, qv, *vis, ws.feat, alpha_v, ws.av, ws.av_bytes, st, &pk));
+    }
+    // model.py:391-393  LSTMCell(drop(cat(u_t_prev, feature)), (h_0, c_0)) on tcgen05 from the packed operands
+    {
+      PkParams q{};
+      q.a_pk = base + P.a_gates; q.b_pk = ws.bpk; q.nkb = P.nkb_gates;
+      q.g.M = B; q.g.N = 4 * d.H;
+      q.g.lstm = lstm_e;
+      SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));
+    }
   }
   const float* b_g = reinterpret_cast<const float*>(base + P.b_g);
   if (ctx_k) {
@@ -936,6 +1010,9 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
     sp.has_tail = 1;
     sp.tail = TailParams{logit, tail->is_valid, tail->target, tail->feedback, tail->sample_u, sp.all_u_t, tail->a_t,
                          tail->u_next, tail->action_score, tail->ce, B, A, d.E, nullptr};
+    if (bpk_next && gpl.nz == 1) {   // the chosen candidate row also in packed form: the u_prev blocks of the next step's gate GEMM
+      sp.tail.upk = bpk_next; sp.tail.upk_NB = gpl.NB;
+    }
   }
   SFB_PROPAGATE(launch_action_scoring(sp, st));
   if (q_next && drop_h && !ctx_k)   // train mode: the next query needs the un-dropped h_1 -> its own projection

@@ -1,8 +1,22 @@
 // epilogue.cuh — GEMM epilogues shared by the FFMA (gemm_simt.cu) and tensor-core (gemm_tc.cu) kernels.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "kernels.h"
 
 namespace sfb {
+
+// h1 as bf16 (hi, lo) into the packed activation operand of the next step's gate GEMM (layout: pack.cu)
+__device__ __forceinline__ void lstm_pack_h(const LstmEpilogue& e, int m, int unit, float h1) {
+  const int zt = m / e.hpk_rows_per_z, r = m - zt * e.hpk_rows_per_z;
+  const size_t half = (size_t)e.hpk_NB * 128;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(h1);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(h1 - __bfloat162float(hi));
+  unsigned char* dst = e.hpk + ((size_t)zt * e.hpk_nkb + e.hpk_kb0 + (unit >> 6)) * (2 * half) + (size_t)(r >> 3) * 1024 +
+                       (size_t)((unit & 63) >> 3) * 128 + (size_t)(r & 7) * 16 + (size_t)(unit & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(dst + half) = lo;
+}
 
 // LSTM cell update for one (row, hidden unit); `g` are the four pre-activation gate sums WITHOUT biases.
 __device__ __forceinline__ void lstm_update(const GemmParams& p, int m, int unit, float gi, float gf, float gg,
@@ -30,6 +44,7 @@ __device__ __forceinline__ void lstm_update(const GemmParams& p, int m, int unit
   e.c1[idx] = c1;
   e.h1[idx] = h1;
   if (e.h1_drop) e.h1_drop[idx] = e.drop_h ? h1 * e.drop_h[idx] : h1;
+  if (e.hpk) lstm_pack_h(e, m, unit, h1);
   if (e.seq_out) e.seq_out[(size_t)m * e.ld_seq_out + unit] = h1;
   if (e.gates_act) {
     float* ga = e.gates_act + (size_t)m * 4 * H + unit;
@@ -167,6 +182,7 @@ __device__ __forceinline__ void lstm_update1_pre(const GemmParams& p, int m, int
   e.c1[idx] = c1;
   e.h1[idx] = h1;
   if (e.h1_drop) e.h1_drop[idx] = h1 * pre.dh;
+  if (e.hpk) lstm_pack_h(e, m, unit, h1);
   if (e.gates_act) {
     float* ga = e.gates_act + (size_t)m * 4 * H + unit;
     ga[0] = ig; ga[H] = fg; ga[2 * H] = gt; ga[3 * H] = og;

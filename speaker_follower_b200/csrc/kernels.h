@@ -95,6 +95,9 @@ struct LstmEpilogue {
   const float* h0;                            // previous hidden state, carried through when t >= lengths[m]
   const int32_t* lengths; int t;              // rows with t >= lengths[m] keep (h0, c0) and emit zeros
   float* seq_out; long long ld_seq_out;       // h1 (or 0 when inactive) written at seq_out[m*ld_seq_out + j]
+  // optional: h1 (un-dropped) also emitted as bf16 (hi, lo) into a packed activation operand (layout: pack.cu) at
+  // K blocks hpk_kb0.. of hpk_nkb — the h_0 blocks of the NEXT step's gate GEMM
+  unsigned char* hpk; int hpk_kb0, hpk_nkb, hpk_NB, hpk_rows_per_z;
 };
 struct GemmParams {
   GemmSeg seg[3];
@@ -128,6 +131,7 @@ int32_t launch_gemm_tc(const GemmParams& p, cudaStream_t stream, void* ws, size_
 void gemm_tc_set_debug(int flags);
 int gemm_tc_read_timestamps(long long* out, int n);
 extern int g_disable_tc;
+extern int g_disable_fused;
 
 // ---------------------------------------------------------------- gemm_pk.cu (tcgen05 from pre-packed weights)
 struct PkParams {
@@ -154,12 +158,43 @@ size_t pk_act_bytes(int M, int nkb, bool wide = false);
 int32_t launch_gemm_pk(const PkParams& q, cudaStream_t stream, void* ws, size_t ws_bytes);
 int pk_max_active_clusters(int cluster, int smem);
 
+// ---------------------------------------------------------------- step_fused.cu (attention gather + LSTM cell, one launch)
+struct FusedVisLstmParams {
+  // gather role: batch element b = one CTA; row r of b = concat(segA[idxA[b]][r], segB[idxB[b]][r]), rows contiguous
+  const float* q; int ldq;                // [B, D] visual query
+  const float* segA; long long strideA_b; int lenA;
+  const float* segB; long long strideB_b; int lenB;
+  const int32_t* idxA; const int32_t* idxB;
+  int R, D;
+  float* feat; int ldfeat;                // [B, D] attention output (fp32)
+  float* alpha; int ldalpha;              // [B, R] or NULL
+  const float* pk_scale; int pk_ldscale;  // dropout keep-scale of the feature part of the gate operand, or NULL
+  // GEMM role: packed weights [tiles][nkb][32 KB], packed activations [nkb][2*NB*128 B] whose blocks
+  // [post_kb0, post_kb1) (the attention output) are written by the gather role of this launch
+  const unsigned char* a_pk; unsigned char* b_pk; int nkb, post_kb0, post_kb1;
+  GemmParams g;                           // LSTM epilogue (g.lstm), M = B
+  int B;
+  // filled by the launcher
+  int NB, nch, chunk_rows;
+  float* partial; unsigned int* sem; unsigned int* sync;
+};
+struct FusedPlan {
+  bool ok;
+  int tiles, S, NB, nch, chunk_rows, gstages;
+  size_t smem, sem_bytes, bytes;
+};
+FusedPlan vis_lstm_fused_plan(int B, int H, int nkb, int R, int D, int lenA, int lenB, int num_sms);
+int32_t launch_vis_lstm_fused(const FusedVisLstmParams& q, cudaStream_t stream, void* ws, size_t ws_bytes);
+
 // ---------------------------------------------------------------- pointwise.cu
 struct TailParams {
   float* logit; const float* is_valid; const int32_t* target; int feedback; const float* sample_u;
   const float* all_u_t; int32_t* a_t; float* u_next; float* action_score; float* ce;
   int B, A, E;
   unsigned long long* trace;
+  // optional: the chosen candidate row also as bf16 (hi, lo) in the packed activation operand (K blocks 0..) of the
+  // NEXT step's gate GEMM (layout: pack.cu, one batch tile of upk_NB rows)
+  unsigned char* upk; int upk_NB;
 };
 // logit[b,a] = all_u_t[b,a,:] . g[b,:] + sum_d b_a[d] w_out[d] tp[b,d] + b_out   (EltwiseProdScoring rewritten)
 struct ScoringParams {

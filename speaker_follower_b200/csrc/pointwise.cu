@@ -1,5 +1,7 @@
 // pointwise.cu — the small fused kernels around the GEMMs: action scoring (EltwiseProdScoring, model.py:342-352, in its re-associated form) and
 // the per-step tail of the follower rollout (follower.py:476-505).
+#include <cuda_bf16.h>
+
 #include "kernels.h"
 
 namespace sfb {
@@ -63,10 +65,24 @@ __device__ __forceinline__ void tail_row(const TailParams& p, const int b, const
     if (p.action_score) p.action_score[b] = lg[a_t] - lse;
     if (p.ce) p.ce[b] = tgt < 0 ? 0.f : -(lg[tgt] - lse);
   }
-  if (p.u_next) {
+  if (p.u_next || p.upk) {
     const float4* src = reinterpret_cast<const float4*>(rows + (size_t)a_t * p.E);   // global all_u_t or staged smem rows
-    float4* dst = reinterpret_cast<float4*>(p.u_next + (size_t)b * p.E);
-    for (int j = lane; j < (p.E >> 2); j += 32) dst[j] = src[j];
+    float4* dst = p.u_next ? reinterpret_cast<float4*>(p.u_next + (size_t)b * p.E) : nullptr;
+    const size_t half = (size_t)p.upk_NB * 128;
+    for (int j = lane; j < (p.E >> 2); j += 32) {
+      const float4 o = src[j];
+      if (dst) dst[j] = o;
+      if (p.upk) {
+        const int k = j * 4;
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
+        unsigned char* pd = p.upk + (size_t)(k >> 6) * (2 * half) + (size_t)(b >> 3) * 1024 + (size_t)((k & 63) >> 3) * 128 +
+                            (size_t)(b & 7) * 16 + (size_t)(k & 7) * 2;
+        *reinterpret_cast<uint2*>(pd) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(pd + half) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      }
+    }
   }
 }
 

@@ -196,8 +196,9 @@ class Seq2SeqAgent(BaseAgent):
 
     def _step(self, u_t_prev, obs, h_t, c_t, ctx, seq_mask, target, feedback, carry=None):
         """One decode step + tail on the device.  Returns (h, c, alpha, masked logit, a_t[int32], u_next, score, ce).
-        ``carry``: a dict that lives as long as (h_t, c_t) are fed back unchanged (a rollout) — it holds the visual
-        query of the next step computed by this one (packed path), so the next call skips that projection."""
+        ``carry``: a dict that lives as long as (h_t, c_t) are fed back unchanged (a rollout) — it holds the state
+        this step prepares for the next one (visual query + packed gate operand; packed path), so the next call starts
+        directly with the fused gather + LSTM launch."""
         f_t = self._feature_variables(obs)[0]
         all_u_t, is_valid, _ = self._action_variable(obs)
         su = self._sample_uniform(len(obs), h_t.device) if feedback == "sample" else None
@@ -210,20 +211,20 @@ class Seq2SeqAgent(BaseAgent):
             return h_t, c_t, alpha, logit, a_t, u_next, score, ce
         if getattr(self.decoder, "supports_fused_step", False):
             tail = {"is_valid": is_valid, "feedback": feedback, "target": target, "sample_u": su}
-            q_in = q_next = None
+            c_in = c_out = None
             if carry is not None:
-                q_in = carry.get("q")
-                q_next = carry.get("spare")
-                if q_next is None or q_next.shape[0] != len(obs):
-                    q_next = torch.empty(len(obs), self.decoder.feature_size, device=h_t.device)
-                carry["spare"] = q_in
+                c_in = carry.get("state")          # written by the previous step of this rollout
+                c_out = carry.get("spare")
+                if c_out is None:
+                    c_out = self.decoder.new_carry(len(obs), h_t.device)
+                carry["spare"] = c_in
             if carry is not None and "ctx_proj" not in carry:      # once per rollout: ctx is constant over its steps
                 carry["ctx_proj"] = self.decoder.project_ctx(ctx)
             h_t, c_t, alpha, logit, alpha_v = self.decoder.decode_step(
-                u_t_prev, all_u_t, f_t, h_t, c_t, ctx, seq_mask, tail=tail, q_in=q_in, q_next=q_next,
+                u_t_prev, all_u_t, f_t, h_t, c_t, ctx, seq_mask, tail=tail, carry_in=c_in, carry_out=c_out,
                 ctx_proj=carry.get("ctx_proj") if carry is not None else None)
             if carry is not None:
-                carry["q"] = q_next
+                carry["state"] = c_out
             a_t, u_next, score, ce = tail["out"]
             return h_t, c_t, alpha, logit, a_t, u_next, score, ce
         h_t, c_t, alpha, logit, alpha_v = self.decoder(u_t_prev, all_u_t, f_t, h_t, c_t, ctx, seq_mask)

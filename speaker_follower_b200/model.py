@@ -181,10 +181,11 @@ class AttnDecoderLSTM(nn.Module):
         packed = self._packer.get(sd)
         return ops.follower_project_ctx(sd, packed, ctx.contiguous()) if packed is not None else None
 
-    def decode_step(self, u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask=None, tail=None, q_in=None,
-                    q_next=None, ctx_proj=None):
+    def decode_step(self, u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask=None, tail=None, carry_in=None,
+                    carry_out=None, ctx_proj=None):
         """forward() plus the fast-path extras of the packed C ABI (include/sf_b200.h): ``tail`` fuses the rollout
-        tail (follower.py:476-505) behind the logits, ``q_in``/``q_next`` carry the visual query across steps,
+        tail (follower.py:476-505) behind the logits, ``carry_in``/``carry_out`` (``new_carry()`` buffers) hand the next step's visual query and packed gate
+        operand across steps,
         ``ctx_proj`` = project_ctx(ctx) takes the text-side projections off the step's dependency chain."""
         B = h_0.shape[0]
         dev = h_0.device
@@ -197,8 +198,8 @@ class AttnDecoderLSTM(nn.Module):
         packed = self._packer.get(sd)           # None for dimensions the packed path does not cover
         extra = {}
         if packed is not None:
-            extra = dict(packed=packed, tail=tail, q_in=q_in, q_next=q_next, ctx_proj=ctx_proj)
-        elif tail is not None or q_in is not None or q_next is not None or ctx_proj is not None:
+            extra = dict(packed=packed, tail=tail, carry_in=carry_in, carry_out=carry_out, ctx_proj=ctx_proj)
+        elif tail is not None or carry_in is not None or carry_out is not None or ctx_proj is not None:
             raise NotImplementedError("fused tail / carried query need the packed path (H % 128 == 0)")
         if isinstance(visual_context, (tuple, list)):
             vp, view = visual_context
@@ -207,6 +208,10 @@ class AttnDecoderLSTM(nn.Module):
                                      store=self.feature_store, vp_idx=vp, view_idx=view, **extra)
         return ops.follower_step(sd, u_t_prev, all_u_t.contiguous(), visual_context.contiguous(),
                                  h_0.contiguous(), c_0.contiguous(), ctx.contiguous(), ctx_mask, drop_x, drop_h, **extra)
+
+    def new_carry(self, B, device=None):
+        """A state buffer for decode_step(carry_in=, carry_out=); allocate two and ping-pong them over a rollout."""
+        return ops.follower_carry(_sd(self), B, device)
 
     def _decode_step_autograd(self, sd, u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask, drop_x, drop_h):
         """Training: forward on the CUDA kernels (detached), gradients from torch autograd over the device-side

@@ -309,12 +309,15 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
                   drop_h: Optional[Tensor] = None, store: Optional[FeatureStore] = None,
                   vp_idx: Optional[Tensor] = None, view_idx: Optional[Tensor] = None,
                   workspace: Optional[Tensor] = None, out: Optional[tuple] = None,
-                  packed: Optional[Tensor] = None, q_in: Optional[Tensor] = None, q_next: Optional[Tensor] = None,
+                  packed: Optional[Tensor] = None, carry_in: Optional[Tensor] = None, carry_out: Optional[Tensor] = None,
                   tail: Optional[dict] = None, cand_view: Optional[Tensor] = None, cand_trig: Optional[Tensor] = None,
                   ctx_proj: Optional[tuple] = None):
     """AttnDecoderLSTM.forward (model.py:377-397) -> (h1, c1, alpha, logit, alpha_v).
     `packed`: blob from PackedFollower.get(w) -> the packed-weight tcgen05 path (sfb_follower_step_packed_fwd).
-    Packed path only: `q_in` / `q_next` [B,F] carry the visual query across steps (see include/sf_b200.h);
+    Packed path only: `carry_in` / `carry_out` (follower_carry() buffers) hand the state one step prepares for the
+    next across the call boundary — the next visual query and the gate GEMM's packed [u_prev | . | h_0] operand blocks
+    (see include/sf_b200.h); a step given the previous step's carry_out starts directly with the fused gather + LSTM
+    launch; `carry_out` is complete only when `tail` is given (its u_next is the next step's u_prev);
     `tail` = dict(is_valid, feedback, target=None, sample_u=None, out=(a_t, u_next, score, ce)) fuses the rollout
     tail (follower.py:476-505) behind the logits; the outputs are left in tail["out"];
     `all_u_t=None` with `cand_view` [B,A] int32 / `cand_trig` [B,A,4] (+ store, vp_idx): action candidates gathered
@@ -344,8 +347,13 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
         alpha_v = torch.empty(B, V, device=dev)
     else:
         h1, c1, alpha, logit, alpha_v = out
-    if packed is None and (q_in is not None or q_next is not None or tail is not None):
-        raise _lib.SfbError("q_in / q_next / tail need the packed path (packed=PackedFollower.get(w))")
+    if packed is None and (carry_in is not None or carry_out is not None or tail is not None):
+        raise _lib.SfbError("carry_in / carry_out / tail need the packed path (packed=PackedFollower.get(w))")
+    if packed is not None:
+        nc = lib.sfb_follower_carry_bytes(C.byref(d), B)
+        for nm, cbuf in (("carry_in", carry_in), ("carry_out", carry_out)):
+            if cbuf is not None and (not cbuf.is_cuda or cbuf.dtype != torch.float32 or not cbuf.is_contiguous() or cbuf.numel() * 4 < nc):
+                raise _lib.SfbError("%s must be a follower_carry() buffer for this batch size" % nm)
     if packed is not None:
         wl = _vis_lstm_weights(w)
         tl = None
@@ -370,8 +378,9 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
             C.byref(d), C.byref(wl), packed.data_ptr(), packed.numel(), B, L, A,
             _p(u_prev, name="u_t_prev"), _p(all_u_t, name="all_u_t"), C.byref(vs), _p(h0, name="h_0"),
             _p(c0, name="c_0"), _p(ctx, name="ctx"), _p(mask, torch.uint8, "ctx_mask"), _p(drop_x, name="drop_x"),
-            _p(drop_h, name="drop_h"), _p(h1), _p(c1), _p(alpha), _p(logit), _p(alpha_v), _p(q_in, name="q_in"),
-            _p(q_next, name="q_next"), C.byref(tl) if tl is not None else None,
+            _p(drop_h, name="drop_h"), _p(h1), _p(c1), _p(alpha), _p(logit), _p(alpha_v),
+            carry_in.data_ptr() if carry_in is not None else None,
+            carry_out.data_ptr() if carry_out is not None else None, C.byref(tl) if tl is not None else None,
             C.byref(act) if act is not None else None,
             _p(ctx_proj[0], name="ctx_k") if ctx_proj is not None else None,
             _p(ctx_proj[1], name="ctx_o") if ctx_proj is not None else None,
@@ -384,6 +393,22 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
         _p(ctx, name="ctx"), _p(mask, torch.uint8, "ctx_mask"), _p(drop_x, name="drop_x"), _p(drop_h, name="drop_h"),
         _p(h1), _p(c1), _p(alpha), _p(logit), _p(alpha_v), workspace.data_ptr(), workspace.numel(), _stream()))
     return h1, c1, alpha, logit, alpha_v
+
+
+def follower_carry(w: Dict[str, Tensor], B: int, device=None) -> Tensor:
+    """Opaque per-step state buffer for follower_step(carry_in=, carry_out=) (sfb_follower_carry_bytes); float32 so that
+    carry_query() can view the visual query it starts with."""
+    d = follower_dims(w)
+    n = _lib.load().sfb_follower_carry_bytes(C.byref(d), B)
+    if n == 0:
+        raise _lib.SfbError("these dimensions have no packed path")
+    dev = device if device is not None else w["lstm.weight_ih"].device
+    return torch.zeros((n + 3) // 4, dtype=torch.float32, device=dev)
+
+
+def carry_query(carry: Tensor, B: int, F: int) -> Tensor:
+    """The [B, F] visual query M_q h + b_q stored at the head of a carry buffer."""
+    return carry[:B * F].view(B, F)
 
 
 def ctx_rows(lengths, L: int, device) -> Tensor:

@@ -149,8 +149,9 @@ def test_packed_rollout_10_steps_drift(weights):
 
 
 def test_packed_query_carry_and_fused_tail(weights):
-    """Software pipelining across the recurrence: q_next of step t fed as q_in of step t+1, rollout tail fused into
-    the last kernel — same results as the plain packed step + separate tail, oracle parity, bit-exact actions."""
+    """Software pipelining across the recurrence: the carry written by step t (next visual query + packed gate operand
+    blocks of u_next / h_1) fed to step t+1, rollout tail fused into the last kernel — same results as the plain packed
+    step + separate tail, bit-exact actions."""
     w, wc, _, blob = weights
     B, L, A, S = 100, 80, 8, 4
     steps = [cu(synth.follower_step_inputs(B, L, A, seed=900 + s)) for s in range(S)]
@@ -166,12 +167,12 @@ def test_packed_query_carry_and_fused_tail(weights):
         ref.append((h.clone(), c.clone(), logit.clone(), a_t.clone(), score.clone(), u.clone()))
     # pipelined chain
     h, c, u = x0["h_0"].clone(), x0["c_0"].clone(), x0["u_t_prev"].clone()
-    q = [torch.empty(B, synth.FEAT, device="cuda") for _ in range(2)]
+    q = [ops.follower_carry(wc, B) for _ in range(2)]
     for s in range(S):
         st = steps[s]
         tail = {"is_valid": st["is_valid"], "feedback": "argmax"}
         h, c, alpha, logit, av = ops.follower_step(wc, u, st["all_u_t"], st["visual_context"], h, c, ctx, mask, packed=blob,
-                                                   q_in=q[s % 2] if s > 0 else None, q_next=q[(s + 1) % 2], tail=tail)
+                                                   carry_in=q[s % 2] if s > 0 else None, carry_out=q[(s + 1) % 2], tail=tail)
         a_t, u, score, _ = tail["out"]
         rh, rc, rl, ra, rs, ru = ref[s]
         close(h, rh.cpu(), 2e-5, "carry h step %d" % s)
@@ -191,9 +192,10 @@ def test_packed_query_carry_train_mode(weights):
     g = torch.Generator().manual_seed(5)
     drop_x = (torch.rand(B, 2 * synth.FEAT, generator=g) > 0.5).float() * 2.0
     drop_h = (torch.rand(B, synth.HID, generator=g) > 0.5).float() * 2.0
-    qn = torch.empty(B, synth.FEAT, device="cuda")
+    cn = ops.follower_carry(wc, B)
+    qn = ops.carry_query(cn, B, synth.FEAT)
     res = ops.follower_step(wc, xc["u_t_prev"], xc["all_u_t"], xc["visual_context"], xc["h_0"], xc["c_0"], xc["ctx"],
-                            xc["ctx_mask"], drop_x.cuda(), drop_h.cuda(), packed=blob, q_next=qn)
+                            xc["ctx_mask"], drop_x.cuda(), drop_h.cuda(), packed=blob, carry_out=cn)
     ref = O.attn_decoder_step(x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
                               x["ctx_mask"], w, drop_x, drop_h)
     for k, v, r in zip(NAMES, res, ref):
@@ -277,10 +279,11 @@ def test_ctx_projections_take_text_side_off_the_chain(weights, B, L, A):
     close(ck2, ref_k * keep, 2e-5, "ctx_k (compacted)")
     close(co2, ref_o * keep, 2e-5, "ctx_o (compacted)")
     ck, co = ck2, co2
-    qn = torch.empty(B, synth.FEAT, device="cuda")
+    cn = ops.follower_carry(wc, B)
+    qn = ops.carry_query(cn, B, synth.FEAT)
     tail = {"is_valid": xc["is_valid"], "feedback": "argmax"}
     res = ops.follower_step(wc, xc["u_t_prev"], xc["all_u_t"], xc["visual_context"], xc["h_0"], xc["c_0"], xc["ctx"],
-                            xc["ctx_mask"], packed=blob, ctx_proj=(ck, co), q_next=qn, tail=tail)
+                            xc["ctx_mask"], packed=blob, ctx_proj=(ck, co), carry_out=cn, tail=tail)
     ref = O.attn_decoder_step(x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
                               x["ctx_mask"], w)
     for k, v, r in zip(NAMES, res, ref):
@@ -299,7 +302,7 @@ def test_ctx_projections_take_text_side_off_the_chain(weights, B, L, A):
     drop_x = (torch.rand(B, 2 * synth.FEAT, generator=g) > 0.5).float() * 2.0
     drop_h = (torch.rand(B, synth.HID, generator=g) > 0.5).float() * 2.0
     res = ops.follower_step(wc, xc["u_t_prev"], xc["all_u_t"], xc["visual_context"], xc["h_0"], xc["c_0"], xc["ctx"],
-                            xc["ctx_mask"], drop_x.cuda(), drop_h.cuda(), packed=blob, ctx_proj=(ck, co), q_next=qn)
+                            xc["ctx_mask"], drop_x.cuda(), drop_h.cuda(), packed=blob, ctx_proj=(ck, co), carry_out=cn)
     ref = O.attn_decoder_step(x["u_t_prev"], x["all_u_t"], x["visual_context"], x["h_0"], x["c_0"], x["ctx"],
                               x["ctx_mask"], w, drop_x, drop_h)
     for k, v, r in zip(NAMES, res, ref):

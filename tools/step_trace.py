@@ -23,19 +23,19 @@ ub = [xs[0]["u_t_prev"].clone(), torch.empty(B, 2176, device=dev)]
 alpha = torch.empty(B, L, device=dev); logit = torch.empty(B, A, device=dev); av = torch.empty(B, 36, device=dev)
 a_t = torch.empty(B, dtype=torch.int32, device=dev); score = torch.empty(B, device=dev)
 blob = ops.PackedFollower().get(w) if PACKED else None
-qb = [torch.zeros(B, 2176, device=dev), torch.zeros(B, 2176, device=dev)]
+qb = [ops.follower_carry(w, B), ops.follower_carry(w, B)] if PACKED else [None, None]
 cp = [ops.follower_project_ctx(w, blob, x["ctx"]) for x in xs] if PACKED == 3 else None
 def step(i):
     x, s = xs[i % 2], i % 2
     if PACKED == 3:   # + per-episode ctx projections (text side off the chain, helper stream)
         ops.follower_step(w, ub[s], x["all_u_t"], x["visual_context"], hb[s], cb[s], x["ctx"], x["ctx_mask"], workspace=ws,
-                          out=(hb[s ^ 1], cb[s ^ 1], alpha, logit, av), packed=blob, q_in=qb[s], q_next=qb[s ^ 1],
+                          out=(hb[s ^ 1], cb[s ^ 1], alpha, logit, av), packed=blob, carry_in=qb[s], carry_out=qb[s ^ 1],
                           ctx_proj=cp[i % 2],
                           tail={"is_valid": x["is_valid"], "feedback": "argmax", "out": (a_t, ub[s ^ 1], score, None)})
         return
     if PACKED == 2:   # carried query + fused tail
         ops.follower_step(w, ub[s], x["all_u_t"], x["visual_context"], hb[s], cb[s], x["ctx"], x["ctx_mask"], workspace=ws,
-                          out=(hb[s ^ 1], cb[s ^ 1], alpha, logit, av), packed=blob, q_in=qb[s], q_next=qb[s ^ 1],
+                          out=(hb[s ^ 1], cb[s ^ 1], alpha, logit, av), packed=blob, carry_in=qb[s], carry_out=qb[s ^ 1],
                           tail={"is_valid": x["is_valid"], "feedback": "argmax", "out": (a_t, ub[s ^ 1], score, None)})
         return
     ops.follower_step(w, ub[s], x["all_u_t"], x["visual_context"], hb[s], cb[s], x["ctx"], x["ctx_mask"], workspace=ws,
@@ -62,7 +62,7 @@ names = ["gemm t_v", "gemm q", "attn visual", "gemm gates(TC)+lstm", "gemm t", "
 if PACKED:
     names = ["pk q", "attn visual(+pack)", "pk gates+lstm", "pk [t|hh]", "attn text", "pk h~", "pk g", "scoring", "tail"]
 if PACKED == 3:
-    names = ["attn visual(+pack)", "pk gates+lstm", "pk hh (late trigger)", "attn text (k/v, deferred wait)", "pk [g|q'] (tanh fused)", "scoring+tail"]
+    names = ["fused gather+gates+lstm", "pk hh (late trigger)", "attn text (k/v, deferred wait)", "pk [g|q'] (tanh fused)", "scoring+tail"]
 if PACKED == 2:
     names = ["attn visual(+pack)", "pk gates+lstm", "pk [t|hh|q']", "attn text", "pk h~", "pk g", "scoring+tail"]
 t0 = buf[0]
