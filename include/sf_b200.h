@@ -140,6 +140,13 @@ int32_t sfb_soft_dot_attention_fwd(const sfb_dims* dims, const sfb_softdot_weigh
                                    float* h_tilde, float* alpha,
                                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* EltwiseProdScoring.forward — model.py:342-352 (its `mask` argument is ignored there too):
+ *   logit[b,a] = w_out . ((W_h h~_b + b_h) (.) (W_a u_{b,a} + b_a)) + b_out,  h_tilde [B,H], all_u_t [B,A,E] -> logit [B,A].
+ * Workspace: sfb_follower_step_workspace_bytes(dims, B, 1, A). */
+int32_t sfb_eltwise_prod_scoring_fwd(const sfb_dims* dims, const sfb_scoring_weights* ws, int32_t B, int32_t A,
+                                     const float* h_tilde, const float* all_u_t, float* logit,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* AttnDecoderLSTM.forward — model.py:377-397: ONE follower decode step.
  *   u_prev [B,E], all_u_t [B,A,E], vis (dense or gather), h0,c0 [B,H], ctx [B,L,H], ctx_mask [B,L]|NULL
  *   drop_x [B,E+F] / drop_h [B,H]: scaled keep masks of the two nn.Dropout calls (model.py:392,394),

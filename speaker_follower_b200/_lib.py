@@ -102,6 +102,8 @@ SIGNATURES = {
                                                  c_float_p, c_float_p,
                                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_follower_carry_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32]),
+    "sfb_eltwise_prod_scoring_fwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(ScoringWeights), C.c_int32, C.c_int32,
+                                                 c_float_p, c_float_p, c_float_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_follower_project_ctx_workspace_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32, C.c_int32]),
     "sfb_follower_project_ctx": (C.c_int32, [C.POINTER(Dims), C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, c_float_p,
                                              c_int_p, C.c_int32, c_float_p, c_float_p, C.c_void_p, C.c_size_t,

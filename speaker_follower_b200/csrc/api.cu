@@ -29,16 +29,16 @@ int g_attn_force_cl = 0, g_attn_force_stages = 0, g_attn_no_hint = 0, g_attn_rin
 static int g_q_with_hh = 0;
 unsigned long long* cta_trace_buffer() { return g_cta_on ? g_cta_buf : nullptr; }
 
-int device_num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
-    sms = prop.multiProcessorCount;
-  }
-  return sms;
+int device_num_sms() {   // SM count of the CURRENT device (cached per device: a process may drive several GPUs)
+  static int sms[SFB_MAX_DEVICES] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  const bool tracked = dev >= 0 && dev < SFB_MAX_DEVICES;
+  if (tracked && sms[dev] > 0) return sms[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  if (tracked) sms[dev] = n;
+  return n;
 }
 
 // ---- workspace carving (all regions 256-byte aligned) ----
@@ -339,6 +339,26 @@ static int32_t soft_dot(int H, const sfb_softdot_weights& w, int B, int L, const
   return launch_gemm(g2, st);
 }
 
+// EltwiseProdScoring.forward (model.py:342-352) re-associated: tp = w_out (.) (W_h h~ + b_h), g = W_a^T tp,
+// logit_a = u_a . g + b_a . tp + b_out
+static int32_t eltwise_scoring(const sfb_dims& d, const sfb_scoring_weights& wsc, int B, int A, const float* h_tilde,
+                               const float* all_u_t, float* logit, float* tp, float* gbuf, cudaStream_t st) {
+  GemmParams g{};
+  g.nseg = 1;
+  g.seg[0] = GemmSeg{h_tilde, d.H, nullptr, nullptr, 0, wsc.w_h, d.H, d.H, 0};
+  g.M = B; g.N = d.D; g.splitk = gemm_pick_splitk(B, d.D, d.H, device_num_sms()); g.out = tp; g.ldo = d.D; g.bias0 = wsc.b_h; g.oscale = wsc.w_out;
+  SFB_PROPAGATE(launch_gemm(g, st));
+  GemmParams g2{};
+  g2.nseg = 1;
+  g2.seg[0] = GemmSeg{tp, d.D, nullptr, nullptr, 0, wsc.w_a, d.E, d.D, 1};
+  g2.M = B; g2.N = d.E; g2.splitk = gemm_pick_splitk(B, d.E, d.D, device_num_sms()); g2.out = gbuf; g2.ldo = d.E;
+  SFB_PROPAGATE(launch_gemm(g2, st));
+  ScoringParams sp{};
+  sp.all_u_t = all_u_t; sp.g = gbuf; sp.tp = tp; sp.b_a = wsc.b_a; sp.b_out = wsc.b_out; sp.ldg = d.E;
+  sp.logit = logit; sp.B = B; sp.A = A; sp.E = d.E; sp.D = d.D;
+  return launch_action_scoring(sp, st);
+}
+
 }  // namespace sfb
 
 using namespace sfb;
@@ -495,23 +515,20 @@ int32_t sfb_follower_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
   // model.py:395  h_tilde, alpha = text_attention_layer(h_1_drop, ctx, ctx_mask)
   SFB_PROPAGATE(soft_dot(d.H, *wt, B, L, ws.h1d, ctx, ctx_mask, ws.t, ws.wc, ws.htilde, alpha, ws.at, ws.at_bytes, st));
   // model.py:396  logit = decoder2action(h_tilde, all_u_t)
-  {
-    GemmParams g{};
-    g.nseg = 1;
-    g.seg[0] = GemmSeg{ws.htilde, d.H, nullptr, nullptr, 0, wsc->w_h, d.H, d.H, 0};
-    g.M = B; g.N = d.D; g.splitk = gemm_pick_splitk(B, d.D, d.H, device_num_sms()); g.out = ws.tp; g.ldo = d.D; g.bias0 = wsc->b_h; g.oscale = wsc->w_out;   // tp = w_out (.) (W_h ht + b_h)
-    SFB_PROPAGATE(launch_gemm(g, st));
-    GemmParams g2{};
-    g2.nseg = 1;
-    g2.seg[0] = GemmSeg{ws.tp, d.D, nullptr, nullptr, 0, wsc->w_a, d.E, d.D, 1};
-    g2.M = B; g2.N = d.E; g2.splitk = gemm_pick_splitk(B, d.E, d.D, device_num_sms()); g2.out = ws.g; g2.ldo = d.E;
-    SFB_PROPAGATE(launch_gemm(g2, st));
-    ScoringParams sp{};
-    sp.all_u_t = all_u_t; sp.g = ws.g; sp.tp = ws.tp; sp.b_a = wsc->b_a; sp.b_out = wsc->b_out; sp.ldg = d.E;
-    sp.logit = logit; sp.B = B; sp.A = A; sp.E = d.E; sp.D = d.D;
-    SFB_PROPAGATE(launch_action_scoring(sp, st));
-  }
+  SFB_PROPAGATE(eltwise_scoring(d, *wsc, B, A, ws.htilde, all_u_t, logit, ws.tp, ws.g, st));
   return 0;
+}
+
+int32_t sfb_eltwise_prod_scoring_fwd(const sfb_dims* dims, const sfb_scoring_weights* wsc, int32_t B, int32_t A,
+                                     const float* h_tilde, const float* all_u_t, float* logit, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_CHECK_ARG(wsc && h_tilde && all_u_t && logit, "NULL argument");
+  SFB_CHECK_ARG(B >= 1 && A >= 1, "B, A >= 1");
+  FollowerWs ws = carve_follower(*dims, B, 1, A, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
+  return eltwise_scoring(*dims, *wsc, B, A, h_tilde, all_u_t, logit, ws.tp, ws.g, static_cast<cudaStream_t>(stream));
 }
 
 int32_t sfb_follower_step_tail(int32_t B, int32_t A, int32_t E, float* logit, const float* is_valid,

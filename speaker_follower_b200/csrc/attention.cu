@@ -350,11 +350,8 @@ template <int NJ, int NT, int RB, int MINB = (NT == 256 ? 4 : 8)>
 static int32_t launch_attn_t(const AttnParams& p, int B, int cl, cudaStream_t stream) {
   auto kern = soft_dot_attn_kernel<NJ, NT, RB, MINB>;
   const size_t smem = attn_smem_bytes(p.stages, p.keyA ? 2 * p.D : p.D, p.rows_per_cta);
-  static size_t configured = 0;  // per instantiation
-  if (smem > configured) {
-    SFB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static SmemMarks marks;  // per instantiation, per device
+  SFB_CHECK_CUDA(ensure_dynamic_smem(kern, smem, marks));
   SFB_CHECK_CUDA(launch_ex(kern, dim3(cl, B, 1), dim3(NT, 1, 1), smem, stream, dim3(cl, 1, 1), p));
   count_launch();
   return 0;

@@ -78,6 +78,24 @@ inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 }
 #endif
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: a process that drives several GPUs (e.g.
+// speaker on cuda:0, follower on cuda:1) must set it on each of them, so the high-water marks are kept per device.
+constexpr int SFB_MAX_DEVICES = 64;
+struct SmemMarks { size_t v[SFB_MAX_DEVICES] = {}; };
+#ifdef __CUDACC__
+template <typename K>
+inline cudaError_t ensure_dynamic_smem(K kernel, size_t smem, SmemMarks& marks) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool tracked = dev >= 0 && dev < SFB_MAX_DEVICES;
+  if (tracked && smem <= marks.v[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && tracked) marks.v[dev] = smem;
+  return e;
+}
+#endif
+
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
 

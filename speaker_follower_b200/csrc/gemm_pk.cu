@@ -523,11 +523,8 @@ int32_t launch_gemm_pk(const PkParams& q_in, cudaStream_t stream, void* ws, size
   const dim3 grid(pl.tiles, pl.S, pl.nz), block(320, 1, 1), cl(1, 1, 1);
 #define SFB_PK_LAUNCH(BP, XS)                                                                                       \
   do {                                                                                                              \
-    static size_t configured = 0;                                                                                   \
-    if (smem > configured) {                                                                                        \
-      SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_pk_kernel<BP, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      configured = smem;                                                                                            \
-    }                                                                                                               \
+    static SmemMarks marks;                                                                                         \
+    SFB_CHECK_CUDA(ensure_dynamic_smem(gemm_pk_kernel<BP, XS>, smem, marks));                                       \
     SFB_CHECK_CUDA(launch_ex(gemm_pk_kernel<BP, XS>, grid, block, smem, stream, cl, q));                            \
   } while (0)
   if (b_packed) SFB_PK_LAUNCH(true, false);

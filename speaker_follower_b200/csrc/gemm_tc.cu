@@ -419,12 +419,9 @@ int32_t launch_gemm_tc(const GemmParams& p_in, cudaStream_t stream, void* ws, si
   const size_t smem = 3 * stage_bytes + 8 * sizeof(uint64_t) + 16;
   bool has_xs = false;
   for (int s = 0; s < p.nseg; ++s) has_xs |= p.seg[s].xs != nullptr;
-  static size_t configured[2] = {0, 0};
-  if (smem > configured[has_xs]) {
-    if (has_xs) SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_lstm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else SFB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_lstm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[has_xs] = smem;
-  }
+  static SmemMarks marks[2];
+  if (has_xs) SFB_CHECK_CUDA(ensure_dynamic_smem(gemm_tc_lstm_kernel<true>, smem, marks[1]));
+  else SFB_CHECK_CUDA(ensure_dynamic_smem(gemm_tc_lstm_kernel<false>, smem, marks[0]));
   const dim3 grid(pl.tiles, pl.S, pl.nz), cl(1, 1, 1);
   if (has_xs) SFB_CHECK_CUDA(launch_ex(gemm_tc_lstm_kernel<true>, grid, dim3(288, 1, 1), smem, stream, cl, p, pl.NB, pl.rows_per_z, partial, sem, g_tc_debug));
   else SFB_CHECK_CUDA(launch_ex(gemm_tc_lstm_kernel<false>, grid, dim3(288, 1, 1), smem, stream, cl, p, pl.NB, pl.rows_per_z, partial, sem, g_tc_debug));

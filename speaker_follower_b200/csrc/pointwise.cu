@@ -12,6 +12,8 @@ __device__ __forceinline__ void tail_row(const TailParams& p, const int b, const
   float* lg = p.logit + (size_t)b * p.A;
   const float* valid = p.is_valid + (size_t)b * p.A;
   // mask, max / first argmax (torch.max returns the first maximal index)
+  // (torch.max treats NaN as the maximum and always returns an in-range index: a row of NaNs / no valid action must
+  // not leave an out-of-range index behind, it is used as an address below)
   float m = -INFINITY;
   int am = 0x7fffffff;
   for (int a = lane; a < p.A; a += 32) {
@@ -20,6 +22,7 @@ __device__ __forceinline__ void tail_row(const TailParams& p, const int b, const
       v = -INFINITY;
       lg[a] = v;
     }
+    if (v != v) v = INFINITY;   // NaN wins, like torch.max
     if (v > m) { m = v; am = a; }
   }
   // warp arg-max with lowest-index tie break
@@ -28,6 +31,7 @@ __device__ __forceinline__ void tail_row(const TailParams& p, const int b, const
     const int oa = __shfl_xor_sync(0xffffffffu, am, o);
     if (om > m || (om == m && oa < am)) { m = om; am = oa; }
   }
+  if (am >= p.A) am = 0;       // every action masked: index 0 (torch.max over a row of -inf)
   __syncwarp();
   float z = 0.f;
   for (int a = lane; a < p.A; a += 32) {
@@ -37,7 +41,8 @@ __device__ __forceinline__ void tail_row(const TailParams& p, const int b, const
   z = warp_sum(z);
   const float lse = m + logf(z);
   int a_t;
-  const int tgt = p.target ? p.target[b] : -1;
+  int tgt = p.target ? p.target[b] : -1;
+  if (tgt >= p.A) tgt = p.A - 1;   // out-of-range teacher index: clamp instead of reading outside the row
   if (p.feedback == 0) {
     a_t = tgt < 0 ? 0 : tgt;
   } else if (p.feedback == 1) {
@@ -186,11 +191,8 @@ int32_t launch_action_scoring(const ScoringParams& p_in, cudaStream_t stream) {
   }
   const size_t smem = stage_rows ? staged : (size_t)p.E * sizeof(float) + 16;
   SFB_CHECK_ARG(smem <= 200 * 1024, "scoring: E too large");
-  static size_t configured = 0;
-  if (smem > configured) {
-    SFB_CHECK_CUDA(cudaFuncSetAttribute(action_scoring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static SmemMarks marks;
+  SFB_CHECK_CUDA(ensure_dynamic_smem(action_scoring_kernel, smem, marks));
   SFB_CHECK_CUDA(launch_ex(action_scoring_kernel, dim3(p.B, 1, 1), dim3(256, 1, 1), smem, stream, dim3(1, 1, 1), p, stage_rows));
   count_launch();
   return 0;

@@ -567,15 +567,8 @@ int32_t launch_vis_lstm_fused(const FusedVisLstmParams& q_in, cudaStream_t strea
   q.nch = pl.nch;
   q.chunk_rows = pl.chunk_rows;
   p.M = q.B;
-  {
-    static size_t configured[64] = {0};   // the attribute is per device
-    int dev = 0;
-    SFB_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || pl.smem > configured[dev]) {
-      SFB_CHECK_CUDA(cudaFuncSetAttribute(vis_lstm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-      if (dev >= 0 && dev < 64) configured[dev] = pl.smem;
-    }
-  }
+  static SmemMarks marks;
+  SFB_CHECK_CUDA(ensure_dynamic_smem(vis_lstm_fused_kernel, pl.smem, marks));
   SFB_CHECK_CUDA(launch_ex(vis_lstm_fused_kernel, dim3(pl.tiles, pl.S, 1), dim3(FNT, 1, 1), pl.smem, stream, dim3(1, 1, 1), q));
   count_launch();
   return 0;

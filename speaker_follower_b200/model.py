@@ -9,12 +9,14 @@ forward signatures and state_dict keys, with every forward running on the sm_100
 Parameters live in ordinary nn.Linear / nn.LSTMCell / nn.LSTM / nn.Embedding sub-modules so that
 ``state_dict()`` / ``load_state_dict()`` interoperate with the reference's snapshots (follower.py:1022-1035);
 those sub-modules are parameter containers only — their own forward is never called.  The library reads the
-parameter storage in place each step (nothing is cached or re-laid-out).
+parameter storage in place, or from packed tcgen05 operand copies that are refreshed whenever a parameter's
+storage or version changes (``invalidate_packed()`` forces it, e.g. after writes through ``.data``).
 
-Scope of this round: inference / scoring forward.  Calling a module while autograd is recording raises
-NotImplementedError (the backward kernels are the next row of SURVEY.md §8); dropout in ``train()`` mode is
-applied with masks drawn here (torch RNG) and passed to the kernels, exactly where the reference applies
-nn.Dropout.  Tensors must be CUDA: there is no CPU path in this package.
+Under ``torch.no_grad()`` the forward runs on the sm_100a kernels alone.  While autograd is recording, the
+decoder / encoder modules stay differentiable (``_functional.py``: forward on the kernels, backward as documented
+there); the bare attention sub-modules are forward-only on their own.  Dropout in ``train()`` mode is applied with
+masks drawn here (torch RNG) and passed to the kernels, exactly where the reference applies nn.Dropout.  Tensors
+must be CUDA: there is no CPU path in this package.
 """
 from __future__ import annotations
 
@@ -37,6 +39,20 @@ def _no_autograd(*tensors):
 def _sd(module: nn.Module):
     """name -> parameter tensor (no copies), reference state_dict key names."""
     return {k: v for k, v in module.named_parameters()}
+
+
+class _PackedWeights:
+    """Mixin of the modules that keep packed tcgen05 operand copies of their weights (``self._packer``)."""
+
+    def invalidate_packed(self) -> None:
+        """Re-pack on the next call.  Needed only after parameter writes that bypass autograd's version counter
+        (``p.data.copy_()``, EMA swaps, old-style optimizers); ordinary in-place updates are detected."""
+        self._packer.invalidate()
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._packer.invalidate()
+        return out
 
 
 class _Drop:
@@ -138,7 +154,8 @@ class VisualSoftDotAttention(nn.Module):
 
 
 class EltwiseProdScoring(nn.Module):
-    """model.py:329-352 — parameter container; scoring runs inside AttnDecoderLSTM's fused step."""
+    """model.py:329-352.  Inside AttnDecoderLSTM the scoring runs fused with the step; called on its own it is the
+    re-associated three-launch form (``mask`` is ignored by the reference too, model.py:342)."""
 
     def __init__(self, h_dim, a_dim, dot_dim=256):
         super().__init__()
@@ -146,8 +163,13 @@ class EltwiseProdScoring(nn.Module):
         self.linear_in_a = nn.Linear(a_dim, dot_dim, bias=True)
         self.linear_out = nn.Linear(dot_dim, 1, bias=True)
 
+    def forward(self, h, all_u_t, mask=None):
+        _no_autograd(h, all_u_t, *self.parameters())
+        w = {"s." + k: v for k, v in self.named_parameters()}
+        return ops.eltwise_prod_scoring(w, h.contiguous(), all_u_t.contiguous(), prefix="s.")
 
-class AttnDecoderLSTM(nn.Module):
+
+class AttnDecoderLSTM(_PackedWeights, nn.Module):
     """model.py:355-397: one follower decode step per call."""
 
     def __init__(self, embedding_size, hidden_size, dropout_ratio, feature_size=2048 + 128, image_attention_layers=None):
@@ -236,7 +258,7 @@ class AttnDecoderLSTM(nn.Module):
         return self._packer.get(_sd(self)) is not None
 
 
-class SpeakerEncoderLSTM(nn.Module):
+class SpeakerEncoderLSTM(_PackedWeights, nn.Module):
     """model.py:405-457."""
 
     def __init__(self, action_embedding_size, world_embedding_size, hidden_size, dropout_ratio, bidirectional=False):
@@ -290,7 +312,7 @@ class SpeakerEncoderLSTM(nn.Module):
         return ctx, decoder_init, c
 
 
-class SpeakerDecoderLSTM(nn.Module):
+class SpeakerDecoderLSTM(_PackedWeights, nn.Module):
     """model.py:460-519, default branch (use_input_att_feed=False is what train_speaker.py:188-193 builds)."""
 
     def __init__(self, vocab_size, vocab_embedding_size, hidden_size, dropout_ratio, glove=None, use_input_att_feed=False):

@@ -38,6 +38,33 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _first_cuda_tensor(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a
+        if isinstance(a, dict):
+            for v in a.values():
+                if isinstance(v, torch.Tensor) and v.is_cuda:
+                    return v
+    return None
+
+
+def _on_tensor_device(fn):
+    """Run `fn` with the CUDA device of its first device tensor current: the library launches on the current device's
+    stream and keeps per-device state (SM count, shared-memory attributes), so a process that drives several GPUs
+    (speaker on cuda:0, follower on cuda:1) must not launch one device's tensors from another device's context."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = _first_cuda_tensor(args, kwargs)
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def _mask_u8(mask: Optional[Tensor]) -> Optional[Tensor]:
     if mask is None:
         return None
@@ -217,6 +244,12 @@ class PackedFollower:
         self.blob: Optional[Tensor] = None
         self.key = None
 
+    def invalidate(self) -> None:
+        """Force a re-pack on the next get().  The cache key is (storage pointer, tensor version) per weight: in-place
+        updates through ``.data`` (``p.data.copy_``, EMA swaps, old-style optimizers) do NOT bump the version, so code
+        that writes weights that way must call this (the nn.Module layer does it from load_state_dict)."""
+        self.key = None
+
     @staticmethod
     def _key(w):
         return tuple((w[k].data_ptr(), w[k]._version) for k in _FOLLOWER_KEYS)
@@ -234,8 +267,9 @@ class PackedFollower:
         if self.blob is None or self.blob.numel() < n or self.blob.device != dev:
             self.blob = torch.empty(n, dtype=torch.uint8, device=dev)
         wl, wt, ws = _vis_lstm_weights(w), _softdot_weights(w, "text_attention_layer."), _scoring_weights(w)
-        check(lib.sfb_follower_pack_weights(C.byref(d), C.byref(wl), C.byref(wt), C.byref(ws), self.blob.data_ptr(),
-                                            self.blob.numel(), _stream()))
+        with torch.cuda.device(dev):
+            check(lib.sfb_follower_pack_weights(C.byref(d), C.byref(wl), C.byref(wt), C.byref(ws), self.blob.data_ptr(),
+                                                self.blob.numel(), _stream()))
         self.key = key
         return self.blob
 
@@ -251,6 +285,10 @@ class _PackedCache:
     def _pack(self, w, blob_or_none):   # -> (nbytes, pack_fn)
         raise NotImplementedError
 
+    def invalidate(self) -> None:
+        """See PackedFollower.invalidate()."""
+        self.key = None
+
     def get(self, w: Dict[str, Tensor]) -> Optional[Tensor]:
         key = tuple((w[k].data_ptr(), w[k]._version) for k in self.keys)
         if self.blob is not None and key == self.key:
@@ -261,7 +299,8 @@ class _PackedCache:
         dev = w[self.keys[0]].device
         if self.blob is None or self.blob.numel() < n or self.blob.device != dev:
             self.blob = torch.empty(n, dtype=torch.uint8, device=dev)
-        pack(self.blob)
+        with torch.cuda.device(dev):
+            pack(self.blob)
         self.key = key
         return self.blob
 
@@ -304,6 +343,7 @@ class PackedSpeakerDecoder(_PackedCache):
                                                                           blob.numel(), _stream()))
 
 
+@_on_tensor_device
 def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual: Optional[Tensor], h0: Tensor,
                   c0: Tensor, ctx: Tensor, ctx_mask: Optional[Tensor], drop_x: Optional[Tensor] = None,
                   drop_h: Optional[Tensor] = None, store: Optional[FeatureStore] = None,
@@ -417,6 +457,7 @@ def ctx_rows(lengths, L: int, device) -> Tensor:
     return torch.tensor(idx, dtype=torch.int32, device=device)
 
 
+@_on_tensor_device
 def follower_project_ctx(w: Dict[str, Tensor], packed: Tensor, ctx: Tensor, out: Optional[tuple] = None,
                          rows: Optional[Tensor] = None, workspace: Optional[Tensor] = None):
     """Per-episode (ctx_k, ctx_o) = (ctx W_in, ctx W_out_c^T) for follower_step(ctx_proj=...) — include/sf_b200.h.
@@ -433,6 +474,7 @@ def follower_project_ctx(w: Dict[str, Tensor], packed: Tensor, ctx: Tensor, out:
     return ctx_k, ctx_o
 
 
+@_on_tensor_device
 def follower_tail(logit: Tensor, is_valid: Tensor, all_u_t: Tensor, feedback: str, target: Optional[Tensor] = None,
                   sample_u: Optional[Tensor] = None, out: Optional[tuple] = None):
     """follower.py:476-505 -> (a_t int32 [B], u_next [B,E], action_score [B], ce [B]); masks `logit` in place."""
@@ -455,6 +497,7 @@ def follower_tail(logit: Tensor, is_valid: Tensor, all_u_t: Tensor, feedback: st
     return a_t, u_next, score, ce
 
 
+@_on_tensor_device
 def visual_attention(w: Dict[str, Tensor], h: Tensor, visual: Optional[Tensor], store=None, vp_idx=None,
                      view_idx=None):
     """VisualSoftDotAttention.forward (model.py:310-326) -> (feature [B,F], alpha_v [B,V])."""
@@ -478,6 +521,7 @@ def visual_attention(w: Dict[str, Tensor], h: Tensor, visual: Optional[Tensor], 
     return feat, alpha_v
 
 
+@_on_tensor_device
 def visual_attention_core(q: Tensor, visual: Optional[Tensor], store=None, vp_idx=None, view_idx=None,
                           out: Optional[tuple] = None, workspace: Optional[Tensor] = None):
     """The attention-gather kernel alone: q [B,F] -> (feature [B,F], alpha_v [B,V]); one launch."""
@@ -499,6 +543,7 @@ def visual_attention_core(q: Tensor, visual: Optional[Tensor], store=None, vp_id
     return feat, alpha_v
 
 
+@_on_tensor_device
 def soft_dot_attention(w: Dict[str, Tensor], prefix: str, h: Tensor, ctx: Tensor, mask: Optional[Tensor]):
     """SoftDotAttention.forward (model.py:122-143) -> (h_tilde [B,H], alpha [B,L])."""
     lib = _lib.load()
@@ -515,6 +560,24 @@ def soft_dot_attention(w: Dict[str, Tensor], prefix: str, h: Tensor, ctx: Tensor
     return ht, alpha
 
 
+@_on_tensor_device
+def eltwise_prod_scoring(w: Dict[str, Tensor], h_tilde: Tensor, all_u_t: Tensor, prefix: str = "decoder2action."):
+    """EltwiseProdScoring.forward (model.py:342-352) -> logit [B,A]."""
+    lib = _lib.load()
+    B, A, E = all_u_t.shape
+    H = h_tilde.shape[1]
+    D = w[prefix + "linear_in_h.weight"].shape[0]
+    d = Dims(E, E, H, D, 1)
+    sw = _scoring_weights(w, prefix)
+    need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, 1, A)
+    ws = _workspace(need, h_tilde.device, ("eltwise_prod_scoring", B, A))
+    logit = torch.empty(B, A, device=h_tilde.device)
+    check(lib.sfb_eltwise_prod_scoring_fwd(C.byref(d), C.byref(sw), B, A, _p(h_tilde, name="h"), _p(all_u_t, name="all_u_t"),
+                                           _p(logit), ws.data_ptr(), ws.numel(), _stream()))
+    return logit
+
+
+@_on_tensor_device
 def encoder_lstm(w: Dict[str, Tensor], seq: Tensor, lengths, bidirectional: bool = False,
                  drop_embed: Optional[Tensor] = None):
     """EncoderLSTM.forward (model.py:81-104), without the final ctx dropout -> (ctx, decoder_init, c_t)."""
@@ -544,6 +607,7 @@ def encoder_lstm(w: Dict[str, Tensor], seq: Tensor, lengths, bidirectional: bool
     return ctx, dec, c_t
 
 
+@_on_tensor_device
 def speaker_encoder_step(w: Dict[str, Tensor], action_embedding: Tensor, visual: Optional[Tensor], h0: Tensor,
                          c0: Tensor, drop_x: Optional[Tensor] = None, store=None, vp_idx=None, view_idx=None,
                          packed: Optional[Tensor] = None, workspace: Optional[Tensor] = None):
@@ -570,6 +634,7 @@ def speaker_encoder_step(w: Dict[str, Tensor], action_embedding: Tensor, visual:
     return h1, c1
 
 
+@_on_tensor_device
 def speaker_decoder_step(w: Dict[str, Tensor], prev_word: Tensor, h0: Tensor, c0: Tensor, ctx: Tensor,
                          ctx_mask: Optional[Tensor], drop_e: Optional[Tensor] = None, drop_h: Optional[Tensor] = None,
                          packed: Optional[Tensor] = None, workspace: Optional[Tensor] = None):
