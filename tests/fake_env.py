@@ -34,10 +34,19 @@ class FakeImageFeatures:
 
 class FakeR2RBatch:
     def __init__(self, n_viewpoints=24, n_instr=16, batch_size=8, seed=0, max_len=20, vocab=synth.VOCAB, beam_size=1,
-                 img_dim=synth.IMG_DIM):
+                 img_dim=synth.IMG_DIM, graph=None):
+        """graph: None = random ring + chords; a scan id from tests/golden/nav_graphs.npz (written from the reference's
+        connectivity/*.json by tests/golden/make_nav_graphs.py) = that REAL R2R navigation graph, edge headings and
+        elevations derived from the viewpoint positions (heading 0 = +y, clockwise, like the simulator)."""
         g = np.random.Generator(np.random.PCG64(seed))
         self.g = g
         self.batch_size, self.beam_size = batch_size, beam_size
+        real = None
+        if graph is not None:
+            import os
+            z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nav_graphs.npz"))
+            real = (z[graph + "/pos"], z[graph + "/adj"])
+            n_viewpoints = real[0].shape[0]
         self.table = synth.feature_table(n_viewpoints, seed + 5, img_dim).numpy()          # [V,36,img]
         self.loc = synth.loc_embedding_table().numpy()                                      # [36,36,128]
         self.image_features_list = [FakeImageFeatures(self.table, self.loc)]
@@ -53,15 +62,26 @@ class FakeR2RBatch:
             self.adj[a][b] = (head, float(g.uniform(-0.4, 0.4)))
             self.adj[b][a] = ((head + math.pi) % (2 * math.pi), -self.adj[a][b][1])
 
-        for v in range(n_viewpoints):
-            connect(v, (v + 1) % n_viewpoints)
-        for _ in range(n_viewpoints):
-            connect(int(g.integers(n_viewpoints)), int(g.integers(n_viewpoints)))
+        if real is None:
+            for v in range(n_viewpoints):
+                connect(v, (v + 1) % n_viewpoints)
+            for _ in range(n_viewpoints):
+                connect(int(g.integers(n_viewpoints)), int(g.integers(n_viewpoints)))
+        else:
+            pos, adj = real
+            for a in range(n_viewpoints):
+                for b in range(n_viewpoints):
+                    if adj[a, b] and a != b:
+                        d = pos[b] - pos[a]
+                        head = math.atan2(d[0], d[1]) % (2 * math.pi)
+                        self.adj[a][b] = (float(head), float(math.atan2(d[2], math.hypot(d[0], d[1]))))
         self.dist = {v: self._bfs(v) for v in range(n_viewpoints)}
         # instructions: start, goal, random tokens
         self.data = []
         for i in range(n_instr):
-            start, goal = int(g.integers(n_viewpoints)), int(g.integers(n_viewpoints))
+            start = int(g.integers(n_viewpoints))
+            reach = sorted(self.dist[start])                       # real graphs may have several components
+            goal = int(reach[int(g.integers(len(reach)))])
             n_tok = int(g.integers(5, max_len))
             self.data.append({"instr_id": "%d_0" % i, "path_id": i, "scan": "fake", "start": start, "goal": goal,
                               "heading": float(g.integers(12)) * math.pi / 6,

@@ -189,3 +189,81 @@ def test_speaker_beam_search():
         for x in four:
             assert abs(sum(float(s) for s in x["scores"]) - float(x["score"])) < 1e-3
             assert x["word_indices"][-1] == 2 or len(x["word_indices"]) == 12      # <EOS> or instruction_len
+
+
+# ------------------------------------------------------------------ search loops against the search oracle (real graphs)
+from oracle import search_oracle as SO   # noqa: E402
+
+
+def _same_candidates(got, want, tol=2e-4, what=""):
+    """Candidate lists of one instance: same length, same action sequences and end states in the same order, scores
+    within tol — unless the oracle's own neighbouring scores are closer than 10 tol (an order flip would be legal)."""
+    sw = [c["score"] for c in want]
+    if any(abs(a - b) < 10 * tol for a, b in zip(sw[:-1], sw[1:])):
+        return False
+    assert len(got) == len(want), (what, len(got), len(want))
+    for g, w in zip(got, want):
+        assert [int(a) for a in g["actions"]] == [int(a) for a in w["actions"]], what
+        assert [p[0] for p in g["trajectory"]] == [p[0] for p in w["trajectory"]], what
+        assert abs(float(g["score"]) - float(w["score"])) < tol, (what, g["score"], w["score"])
+        assert np.allclose([float(x) for x in g["scores"]], [float(x) for x in w["scores"]], atol=tol), what
+    return True
+
+
+@pytest.mark.parametrize("graph,beam", [("8194nk5LbLH", 3), ("pLe4wQe7qrG", 4)])
+def test_beam_search_matches_search_oracle(graph, beam):
+    """follower.py:541-718 — expansion, pruning, completion and ordering of the product's beam search equal the
+    plain-Python oracle's on a real R2R navigation graph (twin environments, same seed)."""
+    env = FakeR2RBatch(n_instr=6, batch_size=6, seed=21, graph=graph, beam_size=beam)
+    twin = FakeR2RBatch(n_instr=6, batch_size=6, seed=21, graph=graph, beam_size=beam)
+    agent, we, wd = make_follower(env)
+    with torch.no_grad():
+        got, _, _ = agent.beam_search(beam)
+        want, _ = SO.follower_beam_search(twin, we, wd, beam, episode_len=agent.episode_len,
+                                          max_length=agent.max_instruction_length)
+    checked = sum(_same_candidates(g, w, what="instance %d" % i) for i, (g, w) in enumerate(zip(got, want)))
+    assert checked >= 4
+
+
+@pytest.mark.parametrize("graph,completion,successor", [("8194nk5LbLH", 3, 1), ("GdvgFV5R1Z5", 4, 2), ("pLe4wQe7qrG", 5, 1)])
+def test_state_factored_search_matches_search_oracle(graph, completion, successor):
+    """follower.py:720-980 — world-state dedupe, strict-improvement replacement, heapq.nlargest expansion order,
+    completion bookkeeping and the traversal walk equal the oracle's."""
+    env = FakeR2RBatch(n_instr=5, batch_size=5, seed=22, graph=graph, beam_size=max(successor, 2))
+    twin = FakeR2RBatch(n_instr=5, batch_size=5, seed=22, graph=graph, beam_size=max(successor, 2))
+    agent, we, wd = make_follower(env)
+    with torch.no_grad():
+        got, _, walk_g = agent.state_factored_search(completion, successor)
+        want, _, walk_w = SO.follower_state_factored_search(twin, we, wd, completion, successor, episode_len=agent.episode_len,
+                                                            max_length=agent.max_instruction_length)
+    checked = 0
+    for i, (g, w) in enumerate(zip(got, want)):
+        if _same_candidates(g, w, tol=3e-4, what="instance %d" % i):
+            checked += 1
+            assert [s.world_state.viewpointId for s in walk_g[i]] == [s.world_state.viewpointId for s in walk_w[i]], i
+    assert checked >= 3
+
+
+def test_speaker_beam_search_matches_search_oracle():
+    """speaker.py:211-318 against the oracle on gold paths of a real graph."""
+    env = FakeR2RBatch(n_instr=6, batch_size=6, seed=23, graph="8194nk5LbLH")
+    we, wd = synth.speaker_encoder_weights(), synth.speaker_decoder_weights()
+    enc = M.SpeakerEncoderLSTM(synth.FEAT, synth.FEAT, synth.HID, 0.5).cuda().eval()
+    dec = M.SpeakerDecoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0.5, glove=wd["embedding.weight"].numpy()).cuda().eval()
+    enc.load_state_dict(we); dec.load_state_dict(wd)
+    spk = Sp.Seq2SeqSpeaker(env, "", enc, dec, instruction_len=10, max_episode_len=6)
+    path_obs, path_actions, _ = env.gold_obs_actions_and_instructions(6)
+    with torch.no_grad():
+        got = spk.beam_search(3, path_obs, path_actions)
+        want = SO.speaker_beam_search(path_obs, path_actions, we, wd, 3, instruction_len=10)
+    checked = 0
+    for g, w in zip(got, want):
+        sw = [c["score"] for c in w]
+        if any(abs(a - b) < 2e-3 for a, b in zip(sw[:-1], sw[1:])):
+            continue
+        checked += 1
+        assert len(g) == len(w)
+        for a, b in zip(g, w):
+            assert [int(x) for x in a["word_indices"]] == [int(x) for x in b["word_indices"]]
+            assert abs(float(a["score"]) - float(b["score"])) < 1e-3
+    assert checked >= 3
