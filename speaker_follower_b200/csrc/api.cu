@@ -63,6 +63,8 @@ struct FollowerWs {
   unsigned char* bpk; size_t bpk_bytes;
   float* th;
   void* fz; size_t fz_bytes;              // fused gather + LSTM kernel: barrier / counter words + partial tiles
+  unsigned char *hdpk, *htpk;             // fused text-side kernel: packed h1 (after dropout) and packed h~ operands
+  void* tsync;                            // fused text-side kernel: hand-off counters (256 B, zeroed once)
   int ldg;
   int splitk;
   size_t bytes;
@@ -114,6 +116,10 @@ static FollowerWs carve_follower(const sfb_dims& d, int B, int L, int A, void* w
     const FusedPlan fp = vis_lstm_fused_plan(B, d.H, nkb_g, d.V, d.F, d.F, 0, sms);
     w.fz_bytes = fp.ok ? fp.bytes : 256;
     w.fz = c.take(w.fz_bytes / sizeof(float));
+    const size_t hb = pk_act_bytes(B, nkb_h);
+    w.hdpk = reinterpret_cast<unsigned char*>(c.take(hb / sizeof(float)));
+    w.htpk = reinterpret_cast<unsigned char*>(c.take(hb / sizeof(float)));
+    w.tsync = c.take(64);
   }
   w.bytes = c.off;
   return w;
@@ -901,10 +907,15 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
   LstmEpilogue lstm_e{};
   lstm_e.H = d.H; lstm_e.b_ih = wl->lstm_b_ih; lstm_e.b_hh = wl->lstm_b_hh; lstm_e.c0 = c0; lstm_e.drop_h = drop_h;
   lstm_e.h1 = h1; lstm_e.c1 = c1; lstm_e.h1_drop = ws.h1d; lstm_e.gates_act = ws.gates_act;
+  lstm_e.hpk_NB = gpl.NB; lstm_e.hpk_rows_per_z = gpl.rows_per_z;
   if (bpk_next && gpl.nz == 1) {   // h_1 in packed form: the h_0 blocks of the next step's gate GEMM
     lstm_e.hpk = bpk_next; lstm_e.hpk_kb0 = kblocks(d.E) + kblocks(d.F); lstm_e.hpk_nkb = P.nkb_gates;
-    lstm_e.hpk_NB = gpl.NB; lstm_e.hpk_rows_per_z = gpl.rows_per_z;
   }
+  // the text side as ONE launch (step_fused_b.cu) when the per-episode ctx projections are given and the shape fits
+  const FusedTextPlan tpl = text_score_fused_plan(B, L, A, d.H, d.E, d.F, q_next != nullptr, device_num_sms());
+  const bool fused_b = ctx_k != nullptr && tpl.ok && !g_disable_fused && gpl.nz == 1 && gpl.NB == tpl.NB &&
+                       (!act_gather || (size_t)A * d.E * 4 <= 160 * 1024);
+  if (fused_b) lstm_e.hdpk = ws.hdpk;
   if (fused) {
     // model.py:389-393 as ONE launch (step_fused.cu): attention gather + gate GEMM + LSTM cell
     FusedVisLstmParams f{};
@@ -944,6 +955,32 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
     }
   }
   const float* b_g = reinterpret_cast<const float*>(base + P.b_g);
+  if (fused_b) {
+    FusedTextScoreParams t{};
+    t.B = B; t.L = L; t.A = A; t.H = d.H; t.E = d.E;
+    t.h1d = ws.h1d; t.ldh = d.H; t.ctx_k = ctx_k; t.ctx_o = ctx_o; t.mask = ctx_mask; t.ldmask = L;
+    t.alpha = alpha; t.ldalpha = L; t.h_tilde = ws.htilde; t.htpk = ws.htpk;
+    t.a_hh = base + P.a_th + pk_weight_bytes(d.H, P.nkb_h); t.hh_tiles = d.H / 128; t.hdpk = ws.hdpk; t.hh = ws.th; t.ldhh = d.H;
+    if (q_next) {
+      const size_t b_half = (size_t)(gpl.NB / 8) * 1024;
+      t.a_q = base + P.a_q; t.q_tiles = (d.F + 127) / 128; t.hpk = bpk_next + (size_t)(kblocks(d.E) + kblocks(d.F)) * 2 * b_half;
+      t.q_next = q_next; t.ldq = d.F; t.b_q = b_q; t.q_cols = d.F;
+    }
+    t.a_g = base + P.a_g; t.g_tiles = (d.E + 1 + 127) / 128; t.g = ws.g; t.ldg = ws.ldg; t.b_g = b_g; t.g_cols = d.E + 1;
+    t.all_u_t = all_u_t;
+    if (act_gather) {
+      t.all_u_t = nullptr; t.cand_table = act->feat_table; t.vp_idx = act->vp_idx; t.cand_view = act->cand_view;
+      t.cand_trig = act->cand_trig; t.img_dim = act->img_dim; t.cand_V = d.V;
+    }
+    t.logit = logit;
+    if (tail) {
+      t.has_tail = 1;
+      t.tail = TailParams{logit, tail->is_valid, tail->target, tail->feedback, tail->sample_u, t.all_u_t, tail->a_t,
+                          tail->u_next, tail->action_score, tail->ce, B, A, d.E, nullptr};
+      if (bpk_next) { t.tail.upk = bpk_next; t.tail.upk_NB = gpl.NB; }
+    }
+    return launch_text_score_fused(t, st, ws.tsync, 256);
+  }
   if (ctx_k) {
     // model.py:395-396 with the per-episode projections of ctx (sfb_follower_project_ctx): the text attention reads
     // h_1 directly (scores = (ctx W_in) . h, output = sum alpha (ctx W_out_c^T) = W_out_c wc), so NO projection sits

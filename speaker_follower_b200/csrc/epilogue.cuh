@@ -7,15 +7,19 @@
 namespace sfb {
 
 // h1 as bf16 (hi, lo) into the packed activation operand of the next step's gate GEMM (layout: pack.cu)
-__device__ __forceinline__ void lstm_pack_h(const LstmEpilogue& e, int m, int unit, float h1) {
-  const int zt = m / e.hpk_rows_per_z, r = m - zt * e.hpk_rows_per_z;
-  const size_t half = (size_t)e.hpk_NB * 128;
+__device__ __forceinline__ void lstm_pack_to(unsigned char* base, int nkb, int kb0, int NB, int rows_per_z, int m, int unit, float h1) {
+  const int zt = m / rows_per_z, r = m - zt * rows_per_z;
+  const size_t half = (size_t)NB * 128;
   const __nv_bfloat16 hi = __float2bfloat16_rn(h1);
   const __nv_bfloat16 lo = __float2bfloat16_rn(h1 - __bfloat162float(hi));
-  unsigned char* dst = e.hpk + ((size_t)zt * e.hpk_nkb + e.hpk_kb0 + (unit >> 6)) * (2 * half) + (size_t)(r >> 3) * 1024 +
+  unsigned char* dst = base + ((size_t)zt * nkb + kb0 + (unit >> 6)) * (2 * half) + (size_t)(r >> 3) * 1024 +
                        (size_t)((unit & 63) >> 3) * 128 + (size_t)(r & 7) * 16 + (size_t)(unit & 7) * 2;
   *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
   *reinterpret_cast<__nv_bfloat16*>(dst + half) = lo;
+}
+__device__ __forceinline__ void lstm_pack_h(const LstmEpilogue& e, int m, int unit, float h1, float h1d) {
+  if (e.hpk) lstm_pack_to(e.hpk, e.hpk_nkb, e.hpk_kb0, e.hpk_NB, e.hpk_rows_per_z, m, unit, h1);
+  if (e.hdpk) lstm_pack_to(e.hdpk, e.H / 64, 0, e.hpk_NB, e.hpk_rows_per_z, m, unit, h1d);
 }
 
 // LSTM cell update for one (row, hidden unit); `g` are the four pre-activation gate sums WITHOUT biases.
@@ -44,7 +48,7 @@ __device__ __forceinline__ void lstm_update(const GemmParams& p, int m, int unit
   e.c1[idx] = c1;
   e.h1[idx] = h1;
   if (e.h1_drop) e.h1_drop[idx] = e.drop_h ? h1 * e.drop_h[idx] : h1;
-  if (e.hpk) lstm_pack_h(e, m, unit, h1);
+  if (e.hpk || e.hdpk) lstm_pack_h(e, m, unit, h1, e.drop_h ? h1 * e.drop_h[idx] : h1);
   if (e.seq_out) e.seq_out[(size_t)m * e.ld_seq_out + unit] = h1;
   if (e.gates_act) {
     float* ga = e.gates_act + (size_t)m * 4 * H + unit;
@@ -167,7 +171,7 @@ __device__ __forceinline__ LstmPre1 lstm_preload1(const GemmParams& p, int m, in
   r.bo = __ldg(e.b_ih + 3 * H + unit) + __ldg(e.b_hh + 3 * H + unit);
   const size_t idx = (size_t)m * H + unit;
   r.c0 = e.c0[idx];
-  r.dh = (e.h1_drop && e.drop_h) ? e.drop_h[idx] : 1.f;
+  r.dh = e.drop_h ? e.drop_h[idx] : 1.f;
   return r;
 }
 __device__ __forceinline__ void lstm_update1_pre(const GemmParams& p, int m, int unit, float gi, float gf, float gg, float go,
@@ -182,7 +186,7 @@ __device__ __forceinline__ void lstm_update1_pre(const GemmParams& p, int m, int
   e.c1[idx] = c1;
   e.h1[idx] = h1;
   if (e.h1_drop) e.h1_drop[idx] = h1 * pre.dh;
-  if (e.hpk) lstm_pack_h(e, m, unit, h1);
+  if (e.hpk || e.hdpk) lstm_pack_h(e, m, unit, h1, h1 * pre.dh);
   if (e.gates_act) {
     float* ga = e.gates_act + (size_t)m * 4 * H + unit;
     ga[0] = ig; ga[H] = fg; ga[2 * H] = gt; ga[3 * H] = og;

@@ -98,6 +98,8 @@ struct LstmEpilogue {
   // optional: h1 (un-dropped) also emitted as bf16 (hi, lo) into a packed activation operand (layout: pack.cu) at
   // K blocks hpk_kb0.. of hpk_nkb — the h_0 blocks of the NEXT step's gate GEMM
   unsigned char* hpk; int hpk_kb0, hpk_nkb, hpk_NB, hpk_rows_per_z;
+  // optional: h1_drop as packed operand [H/64 blocks][2*hpk_NB*128 B] (one batch tile) for the fused text-side kernel
+  unsigned char* hdpk;
 };
 struct GemmParams {
   GemmSeg seg[3];
@@ -186,7 +188,7 @@ struct FusedPlan {
 FusedPlan vis_lstm_fused_plan(int B, int H, int nkb, int R, int D, int lenA, int lenB, int num_sms);
 int32_t launch_vis_lstm_fused(const FusedVisLstmParams& q, cudaStream_t stream, void* ws, size_t ws_bytes);
 
-// ---------------------------------------------------------------- pointwise.cu
+// rollout tail of one batch row (pointwise.cu / tail.cuh)
 struct TailParams {
   float* logit; const float* is_valid; const int32_t* target; int feedback; const float* sample_u;
   const float* all_u_t; int32_t* a_t; float* u_next; float* action_score; float* ce;
@@ -196,6 +198,45 @@ struct TailParams {
   // NEXT step's gate GEMM (layout: pack.cu, one batch tile of upk_NB rows)
   unsigned char* upk; int upk_NB;
 };
+
+// ---------------------------------------------------------------- step_fused_b.cu (text attention + projections + scoring + tail, one launch)
+struct FusedTextScoreParams {
+  int B, L, A, H, E;
+  // text attention over the per-episode key / value projections of ctx (sfb_follower_project_ctx)
+  const float* h1d; int ldh;                 // [B,H] query: h_1 after dropout
+  const float* ctx_k; const float* ctx_o;    // [B,L,H]
+  const uint8_t* mask; int ldmask;           // [B,L] 1 = masked, or NULL
+  float* alpha; int ldalpha;                 // [B,L] or NULL
+  float* h_tilde;                            // [B,H] fp32 (kept for the API / backward) or NULL
+  unsigned char* htpk;                       // h~ as packed bf16 (hi, lo) operand [H/64][2*NB*128 B]
+  // projections on tcgen05 from packed operands, K = H
+  const unsigned char* a_hh; int hh_tiles;   // W_out[:, H:2H] rows
+  const unsigned char* hdpk;                 // packed h1d
+  float* hh; int ldhh;                       // [B,H] scratch
+  const unsigned char* a_q; int q_tiles;     // M_q rows; q_tiles = 0: no next query
+  const unsigned char* hpk;                  // packed (un-dropped) h_1
+  float* q_next; int ldq; const float* b_q; int q_cols;
+  const unsigned char* a_g; int g_tiles;     // M_g rows + constant row
+  float* g; int ldg; const float* b_g; int g_cols;
+  // action candidates (dense or gathered, see ScoringParams) + logits + rollout tail
+  const float* all_u_t;
+  const float* cand_table; const int32_t* vp_idx; const int32_t* cand_view; const float* cand_trig; int img_dim, cand_V;
+  float* logit;
+  int has_tail; TailParams tail;
+  // filled by the launcher
+  int NB, P, nch, nkb;
+  unsigned int* sync;
+  unsigned long long* trace;
+};
+struct FusedTextPlan {
+  bool ok;
+  int NB, P, grid, nch;
+  size_t smem, sync_bytes;
+};
+FusedTextPlan text_score_fused_plan(int B, int L, int A, int H, int E, int F, bool with_q, int num_sms);
+int32_t launch_text_score_fused(const FusedTextScoreParams& q, cudaStream_t stream, void* sync_ws, size_t sync_bytes);
+
+// ---------------------------------------------------------------- pointwise.cu
 // logit[b,a] = all_u_t[b,a,:] . g[b,:] + sum_d b_a[d] w_out[d] tp[b,d] + b_out   (EltwiseProdScoring rewritten)
 struct ScoringParams {
   const float* all_u_t;                   // [B,A,E]

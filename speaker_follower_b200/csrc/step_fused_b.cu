@@ -1,0 +1,595 @@
+// step_fused_b.cu — the second half of a follower decode step as ONE launch (model.py:394-396 + follower.py:476-505):
+//
+//   hh   = W_out_h h1d                     q' = M_q h_1 + b_q   (next step's visual query, off the critical path)
+//   alpha = softmax_l(ctx_k[b,l] . h1d[b]) (masked),  h~ = tanh(sum_l alpha_l ctx_o[b,l] + hh[b])     (SoftDotAttention
+//           with the per-episode key / value projections of ctx, see sfb_follower_project_ctx)
+//   g    = M_g h~ + b_g                    logit[b,a] = u_{b,a} . g[b] + g[b][E]    (EltwiseProdScoring, folded)
+//   rollout tail of the row (mask, log-softmax, teacher / argmax / sample, next-u gather, score / CE terms)
+//
+// One resident wave of CTAs (one per SM) in clusters of two, with two roles:
+//   * projection pairs (the first 2P CTAs): a pair owns one 128-row weight tile per job and splits K between its two
+//     CTAs.  Warp 9 pulls the job's packed weights (cp.async.bulk) as soon as the buffer is free — for the g projection
+//     that is while the attention is still running — and streams the packed activation blocks through a 2-stage ring;
+//     warp 8 issues tcgen05.mma (bf16 x 3, fp32 accumulation in TMEM); the two partial accumulators are exchanged
+//     through DISTRIBUTED SHARED MEMORY (each CTA parks the columns its peer owns, one cluster barrier, pull) — no
+//     global partial tiles, no device-wide split-K barrier.
+//   * row CTAs (one per batch element): warp 9 streams the element's un-masked key / value rows into a ring before
+//     the dependency wait (they are per-episode constants); each of the 8 compute warps owns whole rows (warp-shuffle
+//     dot product, online softmax, no block barrier while streaming); the 8 partial results merge through shared
+//     memory; h~ is formed once hh has arrived and is published both as fp32 and as the packed operand of the g
+//     projection.  The same CTA then stages the element's action-candidate rows (from the feature table or the dense
+//     tensor) in the freed ring and, when g has arrived, forms the logits and runs the rollout tail.
+// The three hand-offs (hh -> rows, h~ -> g pairs, g -> rows) are device-wide arrival counters polled by one thread.
+#include <cuda_bf16.h>
+
+#include "epilogue.cuh"
+#include "kernels.h"
+#include "pack.cuh"
+#include "tail.cuh"
+
+namespace sfb {
+
+namespace {
+constexpr int TBM = 128, TBK = 64;
+constexpr int TNT = 320;                         // 8 compute warps + MMA issuer + producer
+constexpr uint32_t TCORE = 128;
+constexpr uint32_t TSBO = (TBK / 8) * TCORE;
+constexpr uint32_t TLBO = TCORE;
+constexpr uint32_t TA_HALF = (TBM / 8) * TSBO;   // 16 KB: one (hi | lo) weight tile block
+constexpr int T_RW = 8;                          // rows per ring chunk = compute warps
+constexpr int T_MAXCH = 8;                       // ring depth in chunks
+constexpr int T_MAXKH = 4;                       // K blocks per CTA of a pair (K <= 512)
+
+__device__ __forceinline__ bool t_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 26); ++i)
+    if (mbar_try_wait(bar, parity)) return true;
+  return false;
+}
+__device__ __forceinline__ uint64_t t_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(TLBO >> 4) << 16;
+  d |= (uint64_t)(TSBO >> 4) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+__device__ __forceinline__ void t_umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void t_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void t_bar256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ unsigned int t_ld_acq(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool t_spin_ge(const unsigned int* p, unsigned int target) {
+  for (uint32_t i = 0; i < (1u << 24); ++i)
+    if (t_ld_acq(p) >= target) return true;
+  return false;
+}
+}  // namespace
+
+// grid = 2P + (row CTAs), cluster (2,1,1), TNT threads
+__global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTextScoreParams q) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ int s_fail;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cid = blockIdx.x;
+  const int P = q.P, B = q.B, H = q.H, NB = q.NB;
+  const bool is_pair = cid < 2 * P;
+  unsigned int* cnt_hh = q.sync;         // arrivals: 2 per hh tile
+  unsigned int* cnt_ht = q.sync + 1;     // arrivals: 1 per batch element (h~ published)
+  unsigned int* cnt_g = q.sync + 2;      // arrivals: 2 per g tile
+  unsigned int* cnt_exit = q.sync + 3;
+  unsigned int* status = q.sync + 4;
+
+  if (tid == 0) s_fail = 0;
+  trace_mark(q.trace, 0);
+  pdl_launch_dependents();
+
+  if (is_pair) {
+    // =====================================================================================================
+    // projection pair
+    // =====================================================================================================
+    const int pair = cid >> 1, rank = cid & 1;
+    const uint32_t b_half = (uint32_t)(NB / 8) * TSBO;
+    const uint32_t bstage = 2 * b_half;
+    unsigned char* wbuf = smem;                                             // [T_MAXKH][32 KB]; later the parked partial
+    unsigned char* bst = smem + (size_t)T_MAXKH * 2 * TA_HALF;              // [2][bstage]
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(bst + 2 * bstage);
+    uint64_t* bfull = wfull + 1;      // [2]
+    uint64_t* bempty = bfull + 2;     // [2]
+    uint64_t* done = bempty + 2;
+    const uint32_t tmem_cols = NB <= 32 ? 32 : NB <= 64 ? 64 : NB <= 128 ? 128 : 256;
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_init(wfull, 1);
+        mbar_init(&bfull[0], 1); mbar_init(&bfull[1], 1);
+        mbar_init(&bempty[0], 1); mbar_init(&bempty[1], 1);
+        mbar_init(done, 1);
+      }
+      mbar_fence_init();
+      __syncwarp();
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = s_tmem;
+
+    // jobs of this pair, in order: phase 1 = hh tiles then q' tiles (inputs ready at kernel start), phase 2 = g tiles
+    const int n1 = q.hh_tiles + q.q_tiles, n2 = q.g_tiles;
+    const int nkb = q.nkb, kh0 = rank == 0 ? 0 : (nkb + 1) / 2, kh1 = rank == 0 ? (nkb + 1) / 2 : nkb, nkh = kh1 - kh0;
+    // batch columns whose epilogue this CTA runs: rank 0 the first groups of 16, rank 1 the rest
+    const int ngrp = NB / 16, g_split = (ngrp + 1) / 2;
+    const int my_g0 = rank == 0 ? 0 : g_split, my_g1 = rank == 0 ? g_split : ngrp;
+    const int peer_g0 = rank == 0 ? g_split : 0, peer_g1 = rank == 0 ? ngrp : g_split;
+    int njobs_done = 0, bcount = 0;   // running counters -> mbarrier parities
+    bool waited_pdl = false, fail = false;
+
+    for (int phase = 1; phase <= 2; ++phase) {
+      const int njobs = phase == 1 ? n1 : n2;
+      for (int job = pair; job < njobs; job += P) {
+        // ---- job description
+        const unsigned char* a_base; const unsigned char* b_base; float* out; int ldo, ncols, tile; const float* bias; unsigned int* cnt;
+        if (phase == 1 && job < q.hh_tiles) {
+          tile = job; a_base = q.a_hh; b_base = q.hdpk; out = q.hh; ldo = q.ldhh; ncols = H; bias = nullptr; cnt = cnt_hh;
+        } else if (phase == 1) {
+          tile = job - q.hh_tiles; a_base = q.a_q; b_base = q.hpk; out = q.q_next; ldo = q.ldq; ncols = q.q_cols; bias = q.b_q; cnt = nullptr;
+        } else {
+          tile = job; a_base = q.a_g; b_base = q.htpk; out = q.g; ldo = q.ldg; ncols = q.g_cols; bias = q.b_g; cnt = cnt_g;
+        }
+        const uint32_t jpar = (uint32_t)njobs_done & 1u;
+        if (warp == 9) {
+          if (lane == 0) {
+            const uint64_t pol = policy_evict_last();
+            // weights of the job: the buffer is free (the end-of-job cluster barrier of the previous job was passed)
+            mbar_expect_tx(wfull, (uint32_t)nkh * 2 * TA_HALF);
+            for (int k = 0; k < nkh; ++k)
+              bulk_g2s_hint(wbuf + (size_t)k * 2 * TA_HALF, a_base + ((size_t)tile * nkb + kh0 + k) * (2 * TA_HALF), 2 * TA_HALF, wfull, pol);
+            if (!waited_pdl) {
+              pdl_wait();   // packed h1d / h_1 come from the kernel before this one
+              waited_pdl = true;
+            }
+            if (phase == 2) {   // the packed h~ operand is complete when every row CTA has published its element
+              fail = !t_spin_ge(cnt_ht, (unsigned int)B) || fail;
+              asm volatile("fence.proxy.async;" ::: "memory");
+            }
+            for (int k = 0; k < nkh; ++k, ++bcount) {
+              const int s = bcount & 1;
+              if (bcount >= 2) fail = !t_wait(&bempty[s], (uint32_t)((bcount >> 1) - 1) & 1u) || fail;
+              mbar_expect_tx(&bfull[s], bstage);
+              bulk_g2s(bst + (size_t)s * bstage, b_base + (size_t)(kh0 + k) * bstage, bstage, &bfull[s]);
+            }
+          } else {
+            bcount += nkh;
+          }
+        } else if (warp == 8) {
+          const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+          fail = !t_wait(wfull, jpar) || fail;
+          for (int k = 0; k < nkh; ++k, ++bcount) {
+            const int s = bcount & 1;
+            fail = !t_wait(&bfull[s], (uint32_t)(bcount >> 1) & 1u) || fail;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+              const uint32_t a_hi = smem_u32(wbuf + (size_t)k * 2 * TA_HALF), a_lo = a_hi + TA_HALF;
+              const uint32_t b_hi = smem_u32(bst + (size_t)s * bstage), b_lo = b_hi + b_half;
+#pragma unroll
+              for (int j = 0; j < TBK / 16; ++j) {
+                const uint32_t ko = (uint32_t)j * 2u * TCORE;
+                const uint64_t dah = t_desc(a_hi + ko), dal = t_desc(a_lo + ko);
+                const uint64_t dbh = t_desc(b_hi + ko), dbl = t_desc(b_lo + ko);
+                t_umma(tmem_d, dal, dbh, idesc, (k > 0 || j > 0) ? 1u : 0u);
+                t_umma(tmem_d, dah, dbl, idesc, 1u);
+                t_umma(tmem_d, dah, dbh, idesc, 1u);
+              }
+              t_commit(&bempty[s]);
+              if (k + 1 == nkh) t_commit(done);
+            }
+            __syncwarp();
+          }
+        } else {
+          bcount += nkh;
+          // ---- epilogue part 1: park the columns the PEER owns (TMEM -> registers -> own shared memory, [col][row])
+          fail = !t_wait(done, jpar) || fail;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int lq = warp & 3, hf = warp >> 2, row = lq * 32 + lane;
+          float* park = reinterpret_cast<float*>(wbuf);   // the weights are consumed: all MMAs of the job have completed
+          for (int gq = peer_g0 + hf; gq < peer_g1; gq += 2) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(gq * 16);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) park[(size_t)((gq - peer_g0) * 16 + j) * TBM + row] = __uint_as_float(v[j]);
+          }
+        }
+        cluster_sync_all();   // both partials parked
+        if (warp < 8) {
+          // ---- epilogue part 2: own columns = own accumulator + the peer's parked values, bias, store
+          const int lq = warp & 3, hf = warp >> 2, row = lq * 32 + lane;
+          const uint32_t peer_park = dsmem_addr(wbuf, (uint32_t)(rank ^ 1));
+          const int n = tile * TBM + row;
+          const float bv = (bias && n < ncols) ? __ldg(bias + n) : 0.f;
+          for (int gq = my_g0 + hf; gq < my_g1; gq += 2) {
+            if (gq * 16 >= B) break;
+            uint32_t v[16];
+            const uint32_t taddr = tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(gq * 16);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr));
+            float pv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              pv[j] = dsmem_ld_f32(peer_park + (uint32_t)(((gq - my_g0) * 16 + j) * TBM + row) * 4u);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (n < ncols) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int m = gq * 16 + j;
+                // rank 0 holds the low K half: fixed summation order (low + high) on both sides
+                const float lo = rank == 0 ? __uint_as_float(v[j]) : pv[j], hi = rank == 0 ? pv[j] : __uint_as_float(v[j]);
+                if (m < B) out[(size_t)m * ldo + n] = lo + hi + bv;
+              }
+            }
+          }
+          __threadfence();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        cluster_sync_all();   // outputs stored + fenced, parked data consumed: the weight buffer is free again
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0 && cnt) atomicAdd(cnt, 1u);
+        ++njobs_done;
+      }
+    }
+    if (warp == 9 && lane == 0 && !waited_pdl) pdl_wait();
+    if (fail) s_fail = 1;
+    __syncthreads();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+  } else {
+    // =====================================================================================================
+    // row CTA: text attention, h~, action scoring and rollout tail of ONE batch element
+    // =====================================================================================================
+    const int b = cid - 2 * P;
+    const int L = q.L, A = q.A, E = q.E, NCH = q.nch;
+    auto rmark = [&](int which) {   // bring-up timeline of the first row CTA
+      if (q.trace && tid == 0 && b == 0) q.trace[which] = globaltimer_ns();
+    };
+    const int nv = H >> 2;                              // float4 per row; each lane owns NJ = nv / 32 of them
+    const uint32_t row_bytes = (uint32_t)H * 4u, chunk_bytes = (uint32_t)T_RW * 2u * row_bytes;
+    float* ring = reinterpret_cast<float*>(smem);      // [NCH][T_RW][2][H]  (key row, value row)
+    const size_t ring_bytes = (size_t)NCH * chunk_bytes;
+    float* gs = reinterpret_cast<float*>(smem + ring_bytes);                 // [E + 4]
+    float* sc = gs + ((E + 4 + 3) & ~3);                                     // [L] raw scores (by list position)
+    int* list = reinterpret_cast<int*>(sc + ((L + 3) & ~3));                 // [L] un-masked positions
+    uint64_t* rfull = reinterpret_cast<uint64_t*>(list + ((L + 3) & ~3) + 2);
+    rfull = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(rfull) + 7) & ~uintptr_t(7));
+    uint64_t* rempty = rfull + T_MAXCH;
+    uint64_t* candfull = rempty + T_MAXCH;
+    uint64_t* ring_free = candfull + 1;
+    float* wstat = reinterpret_cast<float*>(ring_free + 1);                  // [8][2] (max, sum) per warp
+    __shared__ int s_nvalid;
+    if (b < B) {
+      const uint8_t* mrow = q.mask ? q.mask + (size_t)b * q.ldmask : nullptr;
+      if (warp == 0) {
+        if (lane < T_MAXCH) {
+          mbar_init(&rfull[lane], 1);
+          mbar_init(&rempty[lane], T_RW);
+        }
+        if (lane == 0) {
+          mbar_init(candfull, 1);
+          mbar_init(ring_free, 1);
+        }
+        mbar_fence_init();
+        // compact the un-masked positions (padding masks are a prefix complement in practice, any mask works)
+        int n = 0;
+        for (int base = 0; base < L; base += 32) {
+          const int l = base + lane;
+          const bool ok = l < L && !(mrow && mrow[l]);
+          const unsigned bal = __ballot_sync(0xffffffffu, ok);
+          if (ok) list[n + __popc(bal & ((1u << lane) - 1u))] = l;
+          n += __popc(bal);
+        }
+        if (lane == 0) s_nvalid = n;
+      }
+      __syncthreads();
+      const int nvalid = s_nvalid, nchunks = (nvalid + T_RW - 1) / T_RW;
+      if (warp == 9) {
+        // ---- producer: key / value rows (per-episode constants: no dependency wait), later the candidate rows
+        const uint64_t pol = policy_evict_normal();
+        const float* kb_ = q.ctx_k + (size_t)b * L * H;
+        const float* vb_ = q.ctx_o + (size_t)b * L * H;
+        bool ok = true;
+        for (int c = 0; c < nchunks; ++c) {
+          const int slot = c % NCH;
+          if (c >= NCH) ok = t_wait(&rempty[slot], (uint32_t)(c / NCH - 1) & 1u) && ok;
+          const int rows = min(T_RW, nvalid - c * T_RW);
+          if (lane == 0) mbar_expect_tx(&rfull[slot], (uint32_t)rows * 2u * row_bytes);
+          __syncwarp();
+          if (lane < 2 * rows) {   // lanes 0..rows-1: key rows, rows..2rows-1: value rows
+            const int r = lane < rows ? lane : lane - rows;
+            const int l = list[c * T_RW + r];
+            float* dst = ring + ((size_t)slot * T_RW + r) * 2 * H + (lane < rows ? 0 : H);
+            bulk_g2s_hint(dst, (lane < rows ? kb_ : vb_) + (size_t)l * H, row_bytes, &rfull[slot], pol);
+          }
+        }
+        // candidate rows of the element into the freed ring (step inputs)
+        ok = t_wait(ring_free, 0) && ok;
+        if (lane == 0) {
+          const uint64_t pol2 = policy_evict_first();
+          float* us = ring;
+          if (q.cand_table == nullptr) {
+            mbar_expect_tx(candfull, (uint32_t)((size_t)A * E * 4));
+            for (int a = 0; a < A; ++a)
+              bulk_g2s_hint(us + (size_t)a * E, q.all_u_t + ((size_t)b * A + a) * E, (uint32_t)E * 4u, candfull, pol2);
+          } else {
+            int n = 0;
+            for (int a = 0; a < A; ++a) n += q.cand_view[(size_t)b * A + a] >= 0;
+            mbar_expect_tx(candfull, (uint32_t)((size_t)n * q.img_dim * 4));
+            const float* slab = q.cand_table + (size_t)q.vp_idx[b] * q.cand_V * q.img_dim;
+            for (int a = 0; a < A; ++a) {
+              const int v = q.cand_view[(size_t)b * A + a];
+              if (v >= 0) bulk_g2s_hint(us + (size_t)a * E, slab + (size_t)v * q.img_dim, (uint32_t)q.img_dim * 4u, candfull, pol2);
+            }
+          }
+        }
+        if (!ok) s_fail = 1;
+        pdl_wait();
+      } else if (warp == 8) {
+        pdl_wait();
+      } else {
+        // ---- compute warps: each warp owns whole rows (row r of a chunk -> warp r)
+        pdl_wait();   // h1d is produced by the kernel before this one
+        rmark(1);
+        float4 qv[4], acc[4];
+        {
+          const float4* q4 = reinterpret_cast<const float4*>(q.h1d + (size_t)b * q.ldh);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int idx = lane + 32 * j;
+            qv[j] = idx < nv ? q4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        float m = -INFINITY, Z = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+          const int slot = c % NCH, i = c * T_RW + warp;
+          if (!t_wait(&rfull[slot], (uint32_t)(c / NCH) & 1u)) s_fail = 1;
+          if (i < nvalid) {
+            const float4* key4 = reinterpret_cast<const float4*>(ring + ((size_t)slot * T_RW + warp) * 2 * H);
+            const float4* val4 = key4 + nv;
+            float part = 0.f;
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int idx = lane + 32 * j;
+              if (idx < nv) {
+                const float4 k4 = key4[idx];
+                v[j] = val4[idx];
+                part = fmaf(k4.x, qv[j].x, part); part = fmaf(k4.y, qv[j].y, part);
+                part = fmaf(k4.z, qv[j].z, part); part = fmaf(k4.w, qv[j].w, part);
+              } else {
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+            part = warp_sum(part);
+            if (lane == 0) sc[i] = part;
+            const float mn = fmaxf(m, part), corr = __expf(m - mn), e = __expf(part - mn);
+            Z = fmaf(Z, corr, e);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[j].x = fmaf(e, v[j].x, acc[j].x * corr); acc[j].y = fmaf(e, v[j].y, acc[j].y * corr);
+              acc[j].z = fmaf(e, v[j].z, acc[j].z * corr); acc[j].w = fmaf(e, v[j].w, acc[j].w * corr);
+            }
+            m = mn;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&rempty[slot]);
+        }
+        t_bar256();   // nobody reads the ring any more
+        rmark(4);
+        // ---- merge the 8 per-warp partials through shared memory (the ring's first bytes)
+        float* mbuf = ring;   // [8][H]
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int idx = lane + 32 * j;
+          if (idx < nv) reinterpret_cast<float4*>(mbuf + (size_t)warp * H)[idx] = acc[j];
+        }
+        if (lane == 0) { wstat[2 * warp] = m; wstat[2 * warp + 1] = Z; }
+        t_bar256();
+        float M = -INFINITY, Zt = 0.f, wk[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) M = fmaxf(M, wstat[2 * w]);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          wk[w] = wstat[2 * w] != -INFINITY ? __expf(wstat[2 * w] - M) : 0.f;
+          Zt = fmaf(wstat[2 * w + 1], wk[w], Zt);
+        }
+        const float inv = Zt > 0.f ? 1.0f / Zt : 0.f;    // every position masked -> zeros (the reference would give NaN)
+        if (q.alpha) {
+          float* arow = q.alpha + (size_t)b * q.ldalpha;
+          for (int l = tid; l < L; l += 256) arow[l] = 0.f;
+          t_bar256();
+          for (int i = tid; i < nvalid; i += 256) arow[list[i]] = __expf(sc[i] - M) * inv;
+        }
+        // h~ = tanh(sum_l alpha_l ctx_o[l] + hh) once hh (W_out_h h1d, from the projection pairs) has arrived
+        if (tid == 0 && !t_spin_ge(cnt_hh, 2u * (unsigned int)q.hh_tiles)) s_fail = 1;
+        t_bar256();
+        const size_t half = (size_t)NB * 128;
+        for (int col = tid; col < nv; col += 256) {
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            const float4 pw = reinterpret_cast<const float4*>(mbuf + (size_t)w * H)[col];
+            const float wgt = wk[w] * inv;
+            o.x = fmaf(wgt, pw.x, o.x); o.y = fmaf(wgt, pw.y, o.y); o.z = fmaf(wgt, pw.z, o.z); o.w = fmaf(wgt, pw.w, o.w);
+          }
+          const float4 hh4 = __ldcg(reinterpret_cast<const float4*>(q.hh + (size_t)b * q.ldhh + col * 4));
+          o.x = tanhf(o.x + hh4.x); o.y = tanhf(o.y + hh4.y); o.z = tanhf(o.z + hh4.z); o.w = tanhf(o.w + hh4.w);
+          if (q.h_tilde) *reinterpret_cast<float4*>(q.h_tilde + (size_t)b * H + col * 4) = o;
+          const int k = col * 4;
+          const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+          const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
+          unsigned char* dst = q.htpk + (size_t)(k >> 6) * (2 * half) + (size_t)(b >> 3) * 1024 + (size_t)((k & 63) >> 3) * 128 +
+                               (size_t)(b & 7) * 16 + (size_t)(k & 7) * 2;
+          *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+          *reinterpret_cast<uint2*>(dst + half) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
+        t_bar256();   // h~ published; the merge buffer is consumed -> the ring can take the candidate rows
+        if (tid == 0) {
+          atomicAdd(cnt_ht, 1u);
+          mbar_arrive(ring_free);
+        }
+        rmark(5);
+        // ---- action scoring + rollout tail (model.py:396, follower.py:476-505)
+        float* us = ring;   // [A][E]
+        if (q.cand_table) {
+          // env.py:60-75: [feature[absViewIndex, :img_dim], sin(rh) x n, cos(rh) x n, sin(re) x n, cos(re) x n]; rows
+          // without a view (stop, padding) are zero.  The image part arrives by bulk copy; this fills the rest.
+          const int loc = E - q.img_dim, grp = loc >> 2;
+          // the bulk copies target the same rows: wait until the producer may have started them is not needed — the
+          // regions written here (orientation part, whole rows without a view) are disjoint from the copied ones
+          if (!t_wait(ring_free, 0)) s_fail = 1;
+          for (int i = tid; i < A * loc; i += 256) {
+            const int a = i / loc, j = i - a * loc;
+            const bool okv = q.cand_view[(size_t)b * A + a] >= 0;
+            us[(size_t)a * E + q.img_dim + j] = okv ? q.cand_trig[((size_t)b * A + a) * 4 + j / grp] : 0.f;
+          }
+          for (int a = 0; a < A; ++a)
+            if (q.cand_view[(size_t)b * A + a] < 0)
+              for (int i = tid; i < q.img_dim; i += 256) us[(size_t)a * E + i] = 0.f;
+        }
+        if (tid == 0 && !t_spin_ge(cnt_g, 2u * (unsigned int)q.g_tiles)) s_fail = 1;
+        t_bar256();
+        rmark(6);
+        for (int j = tid; j < (E >> 2) + 1; j += 256) {
+          const int k = j * 4;
+          if (k + 3 < E + 1) reinterpret_cast<float4*>(gs)[j] = __ldcg(reinterpret_cast<const float4*>(q.g + (size_t)b * q.ldg + k));
+          else
+            for (int t = k; t < E + 1; ++t) gs[t] = __ldcg(q.g + (size_t)b * q.ldg + t);
+        }
+        if (!t_wait(candfull, 0)) s_fail = 1;
+        t_bar256();
+        const float cst = gs[E];
+        for (int a = warp; a < A; a += 8) {
+          const float4* u4 = reinterpret_cast<const float4*>(us + (size_t)a * E);
+          float accd = 0.f;
+          for (int j = lane; j < (E >> 2); j += 32) {
+            const float4 u = u4[j];
+            const float4 g4 = reinterpret_cast<const float4*>(gs)[j];
+            accd = fmaf(u.x, g4.x, accd); accd = fmaf(u.y, g4.y, accd);
+            accd = fmaf(u.z, g4.z, accd); accd = fmaf(u.w, g4.w, accd);
+          }
+          accd = warp_sum(accd);
+          if (lane == 0) q.logit[(size_t)b * A + a] = accd + cst;
+        }
+        t_bar256();
+        if (q.has_tail && warp == 0) tail_row(q.tail, b, lane, us);
+        rmark(7);
+      }
+    } else {
+      pdl_wait();
+    }
+    __syncthreads();
+  }
+  // ---- exit bookkeeping: the last CTA resets the hand-off counters (no launch of this kernel overlaps another)
+  if (tid == 0) {
+    if (s_fail) atomicExch(status, 1u);
+    __threadfence();
+    const unsigned int seen = atomicAdd(cnt_exit, 1u);
+    if (seen == gridDim.x - 1u) {
+      atomicExch(cnt_hh, 0u);
+      atomicExch(cnt_ht, 0u);
+      atomicExch(cnt_g, 0u);
+      atomicExch(cnt_exit, 0u);
+    }
+  }
+  trace_mark(q.trace, 2);
+}
+
+// ------------------------------------------------------------------ host side
+
+FusedTextPlan text_score_fused_plan(int B, int L, int A, int H, int E, int F, bool with_q, int num_sms) {
+  FusedTextPlan pl{};
+  pl.ok = false;
+  if (H < 128 || H > 512 || (H % 128) != 0 || (E % 4) != 0 || B < 1 || L < 1 || A < 1) return pl;
+  const int nkb = H / TBK;
+  if ((nkb + 1) / 2 > T_MAXKH) return pl;
+  pl.NB = (B + 15) & ~15;
+  if (pl.NB > 256 || B > 128) return pl;
+  const int grid_max = (num_sms / 2) * 2;
+  int rows = (B + 1) & ~1;                          // row CTAs (padded to whole clusters)
+  pl.P = (grid_max - rows) / 2;
+  const int n1 = H / 128 + (with_q ? (F + 127) / 128 : 0), n2 = (E + 1 + 127) / 128;
+  const int want = n1 > n2 ? n1 : n2;
+  if (pl.P > want) pl.P = want;
+  if (pl.P < 4) return pl;                          // too few projection pairs: the unfused chain is faster
+  pl.grid = 2 * pl.P + rows;
+  // shared memory: the larger of the two roles
+  const size_t b_half = (size_t)(pl.NB / 8) * TSBO;
+  const size_t pair_bytes = (size_t)T_MAXKH * 2 * TA_HALF + 2 * 2 * b_half + 8 * sizeof(uint64_t) + 64;
+  const size_t chunk = (size_t)T_RW * 2 * H * 4;
+  const size_t row_fixed = ((size_t)(E + 4 + 3) & ~size_t(3)) * 4 + 2 * ((size_t)(L + 3) & ~size_t(3)) * 4 + 16 +
+                           (2 * T_MAXCH + 2) * sizeof(uint64_t) + 16 * sizeof(float) + 64;
+  const size_t budget = 227 * 1024 - 2048;
+  const size_t cand = (size_t)A * E * 4, mrg = (size_t)8 * H * 4;
+  size_t ring_min = cand > mrg ? cand : mrg;
+  if (ring_min < 2 * chunk) ring_min = 2 * chunk;
+  if (row_fixed + ring_min > budget) return pl;
+  int nch = (int)((budget - row_fixed) / chunk);
+  if (nch > T_MAXCH) nch = T_MAXCH;
+  const int nchunks = (L + T_RW - 1) / T_RW;
+  if (nch > nchunks && (size_t)nchunks * chunk >= ring_min) nch = nchunks;
+  while ((size_t)nch * chunk < ring_min) ++nch;
+  if (nch > T_MAXCH || row_fixed + (size_t)nch * chunk > budget) return pl;
+  pl.nch = nch;
+  const size_t row_bytes = row_fixed + (size_t)nch * chunk;
+  pl.smem = row_bytes > pair_bytes ? row_bytes : pair_bytes;
+  pl.sync_bytes = 256;
+  pl.ok = true;
+  return pl;
+}
+
+int32_t launch_text_score_fused(const FusedTextScoreParams& q_in, cudaStream_t stream, void* sync_ws, size_t sync_bytes) {
+  FusedTextScoreParams q = q_in;
+  const FusedTextPlan pl = text_score_fused_plan(q.B, q.L, q.A, q.H, q.E, q.q_cols, q.q_tiles > 0, device_num_sms());
+  SFB_CHECK_ARG(pl.ok, "fused text attention + scoring step: unsupported shape");
+  SFB_CHECK_ARG(sync_ws && sync_bytes >= pl.sync_bytes && (reinterpret_cast<uintptr_t>(sync_ws) & 15u) == 0, "fused text step: counter words");
+  SFB_CHECK_ARG(q.h1d && q.ctx_k && q.ctx_o && q.hh && q.g && q.logit && q.a_hh && q.a_g && q.hdpk && q.htpk, "fused text step: NULL argument");
+  SFB_CHECK_ARG(q.q_tiles == 0 || (q.a_q && q.hpk && q.q_next), "fused text step: next-query operands");
+  SFB_CHECK_ARG((reinterpret_cast<uintptr_t>(q.ctx_k) & 15u) == 0 && (reinterpret_cast<uintptr_t>(q.ctx_o) & 15u) == 0 &&
+                    (reinterpret_cast<uintptr_t>(q.h1d) & 15u) == 0 && (q.ldh % 4) == 0 && (q.ldhh % 4) == 0 && (q.ldg % 4) == 0,
+                "fused text step: alignment");
+  q.trace = next_trace_slot();
+  q.sync = static_cast<unsigned int*>(sync_ws);
+  q.NB = pl.NB;
+  q.P = pl.P;
+  q.nch = pl.nch;
+  q.nkb = q.H / TBK;
+  static SmemMarks marks;
+  SFB_CHECK_CUDA(ensure_dynamic_smem(text_score_fused_kernel, pl.smem, marks));
+  SFB_CHECK_CUDA(launch_ex(text_score_fused_kernel, dim3(pl.grid, 1, 1), dim3(TNT, 1, 1), pl.smem, stream, dim3(2, 1, 1), q));
+  count_launch();
+  return 0;
+}
+
+}  // namespace sfb

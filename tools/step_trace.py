@@ -62,7 +62,7 @@ names = ["gemm t_v", "gemm q", "attn visual", "gemm gates(TC)+lstm", "gemm t", "
 if PACKED:
     names = ["pk q", "attn visual(+pack)", "pk gates+lstm", "pk [t|hh]", "attn text", "pk h~", "pk g", "scoring", "tail"]
 if PACKED == 3:
-    names = ["fused gather+gates+lstm", "pk hh (late trigger)", "attn text (k/v, deferred wait)", "pk [g|q'] (tanh fused)", "scoring+tail"]
+    names = ["fused gather+gates+lstm", "fused text attn+proj+scoring+tail"]
 if PACKED == 2:
     names = ["attn visual(+pack)", "pk gates+lstm", "pk [t|hh|q']", "attn text", "pk h~", "pk g", "scoring+tail"]
 t0 = buf[0]
