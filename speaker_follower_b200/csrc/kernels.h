@@ -174,8 +174,10 @@ struct FusedVisLstmParams {
   // GEMM role: packed weights [tiles][nkb][32 KB], packed activations [nkb][2*NB*128 B] whose blocks
   // [post_kb0, post_kb1) (the attention output) are written by the gather role of this launch
   const unsigned char* a_pk; unsigned char* b_pk; int nkb, post_kb0, post_kb1;
+  int feat_kb0;                           // first K block of the attention output inside b_pk
   GemmParams g;                           // LSTM epilogue (g.lstm), M = B
   int B;
+  int pre_weight_free;                    // share of the pre K blocks a CTA without a gather role takes, relative to 1 for a gather CTA
   // filled by the launcher
   int NB, nch, chunk_rows;
   float* partial; unsigned int* sem; unsigned int* sync;

@@ -148,8 +148,14 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
   // K blocks of this CTA: a slice of the "pre" blocks (everything outside [post_kb0, post_kb1)) first, then a slice of
   // the "post" blocks (the attention output)
   const int npost_all = q.post_kb1 - q.post_kb0, npre_all = q.nkb - npost_all;
-  const int per_pre = (npre_all + S - 1) / S, per_post = (npost_all + S - 1) / S;
-  const int pre0 = min(npre_all, rank * per_pre), pre1 = min(npre_all, pre0 + per_pre);
+  const int per_post = (npost_all + S - 1) / S;
+  // pre blocks: CTAs that also gather take a small share (their shared-memory bandwidth belongs to the slab stream),
+  // the others proportionally more: rank r of this tile gathers iff r * tiles + tile < B
+  const int ng = B > tile ? min(S, (B - tile + tiles - 1) / tiles) : 0;
+  const int wf = q.pre_weight_free > 0 ? q.pre_weight_free : 1;
+  const int wsum = ng + (S - ng) * wf;
+  auto cumw = [&](int r) { return r <= ng ? r : ng + (r - ng) * wf; };
+  const int pre0 = (int)((long long)npre_all * cumw(rank) / wsum), pre1 = (int)((long long)npre_all * cumw(rank + 1) / wsum);
   const int post0 = min(npost_all, rank * per_post), post1 = min(npost_all, post0 + per_post);
   const int n_pre = pre1 - pre0, n_post = post1 - post0, nit = n_pre + n_post;
   auto kblock = [&](int it) {   // iteration -> K block index in the packed operands
@@ -162,7 +168,6 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
 
   trace_mark(p.trace, 0);
   pdl_launch_dependents();
-  unsigned int sem_gen = 0;
 
   if (warp == 10) {
     // =============================== gather producer: the slab of this CTA's batch element ===============================
@@ -232,8 +237,10 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
       for (int j = 0; j < pf; ++j) issue_a(n_pre + j);
       if (n_post > 0) {
         bool arrived = false;
-        for (uint32_t i = 0; i < (1u << 24); ++i)
+        for (uint32_t i = 0; i < (1u << 22); ++i) {   // one poller per SM: back off so the arrivals are not starved
           if (ld_acquire_u32(q.sync) >= (unsigned int)B) { arrived = true; break; }
+          __nanosleep(40);
+        }
         ok = ok && arrived;
         asm volatile("fence.proxy.async;" ::: "memory");   // the feature blocks were written with generic-proxy stores
         for (int j = 0; j < pf; ++j) issue_b(n_pre + j);
@@ -305,6 +312,8 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
         const int nb = min(F_RB, R - i0);
         const int slot = c % NCH;
         if (!f_wait(&rfull[slot], (uint32_t)(c / NCH) & 1u)) s_fail = 1;
+        if (c == 0) trace_mark(p.trace, 8);
+        if (i0 + F_RB >= R) trace_mark(p.trace, 9);
         const float4* chunk4 = reinterpret_cast<const float4*>(ring + (size_t)slot * chunk_floats);
         float4 v[F_RB][F_NJ];
         float part[F_RB];
@@ -331,14 +340,22 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
             for (int j = 0; j < F_NJ; ++j) v[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-          for (int r = 0; r < F_RB; ++r) part[r] += __shfl_xor_sync(0xffffffffu, part[r], o);
+        // 4 row sums per warp with 6 shuffles (transposed butterfly): after two halving exchanges every lane holds
+        // ONE row's partial (row = lane bits 4,3), three more steps finish the sum inside each group of 8 lanes
         float* rb = red + (c & 1) * 8 * F_RB;
-        if (lane == 0)
-#pragma unroll
-          for (int r = 0; r < F_RB; ++r) rb[warp * F_RB + r] = part[r];
+        {
+          static_assert(F_RB == 4, "the reduction below is written for 4 rows per chunk");
+          const bool up = (lane & 16) != 0;
+          const float s0 = up ? part[0] : part[2], s1 = up ? part[1] : part[3];     // the half this lane gives away
+          const float k0 = up ? part[2] : part[0], k1 = up ? part[3] : part[1];     // the half it keeps
+          const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16), a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+          const bool up2 = (lane & 8) != 0;
+          float v = (up2 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up2 ? a0 : a1, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          if ((lane & 7) == 0) rb[warp * F_RB + (lane >> 3)] = v;   // lanes 0, 8, 16, 24 hold rows 0, 1, 2, 3
+        }
         bar_sync_256();   // every thread holds its slices in registers -> the chunk is free
         if (tid == 0) mbar_arrive(&rempty[slot]);
         float sr[F_RB], mn = m;
@@ -399,7 +416,7 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
           const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
           const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
           const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
-          unsigned char* dst = q.b_pk + (size_t)(q.post_kb0 + (k >> 6)) * (2 * half) + (size_t)(b >> 3) * 1024 +
+          unsigned char* dst = q.b_pk + (size_t)(q.feat_kb0 + (k >> 6)) * (2 * half) + (size_t)(b >> 3) * 1024 +
                                (size_t)((k & 63) >> 3) * 128 + (size_t)(b & 7) * 16 + (size_t)(k & 7) * 2;
           *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
           *reinterpret_cast<uint2*>(dst + half) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
@@ -411,7 +428,6 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
       if (tid == 0) atomicAdd(q.sync, 1u);   // this batch element's feature blocks are visible device-wide
       trace_mark(p.trace, 5);
     }
-    if (tid == 0 && S > 1) sem_gen = ld_acquire_u32(q.sem + 2 * tile + 1);
   }
 
   // ---- epilogue 1: TMEM -> registers -> [col][row] partial tile in L2
@@ -457,19 +473,21 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
   }
   __threadfence();
   __syncthreads();
-  unsigned int* my_sem = q.sem + 2 * tile;
+  // split-K barrier of this tile: a monotonic arrival counter (S arrivals per launch, never reset: one atomic per CTA,
+  // the release of the last arriver IS its arrival); a launch ends when the count reaches the next multiple of S
+  // (64-bit: never wraps)
+  unsigned long long* my_sem = reinterpret_cast<unsigned long long*>(q.sem) + tile;
   if (S > 1) {
     if (tid == 0) {
-      const unsigned int old = atomicAdd(my_sem, 1u);
-      if (old == (unsigned int)S - 1u) {
-        atomicExch(my_sem, 0u);
-        __threadfence();
-        atomicAdd(my_sem + 1, 1u);
-      } else {
-        unsigned int gen = sem_gen;
-        for (uint32_t i = 0; i < (1u << 24) && gen == sem_gen; ++i) gen = ld_acquire_u32(my_sem + 1);
-        if (gen == sem_gen) s_fail = 1;
+      const unsigned long long old = atomicAdd(my_sem, 1ull);
+      const unsigned long long target = (old / (unsigned long long)S + 1ull) * (unsigned long long)S;
+      bool ok = false;
+      for (uint32_t i = 0; i < (1u << 24); ++i) {
+        unsigned long long cur;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(my_sem) : "memory");
+        if (cur >= target) { ok = true; break; }
       }
+      if (!ok) s_fail = 1;
       __threadfence();
     }
     __syncthreads();
@@ -554,7 +572,8 @@ int32_t launch_vis_lstm_fused(const FusedVisLstmParams& q_in, cudaStream_t strea
   SFB_CHECK_ARG(pl.ok, "fused gather + LSTM step: unsupported shape");
   SFB_CHECK_ARG(q.a_pk && q.b_pk && (reinterpret_cast<uintptr_t>(q.a_pk) & 127u) == 0 && (reinterpret_cast<uintptr_t>(q.b_pk) & 127u) == 0,
                 "fused step: packed operands missing / misaligned");
-  SFB_CHECK_ARG(q.post_kb0 >= 0 && q.post_kb1 <= q.nkb && q.post_kb1 - q.post_kb0 == (q.D + FBK - 1) / FBK, "fused step: bad post K range");
+  SFB_CHECK_ARG(q.post_kb0 >= 0 && q.post_kb1 <= q.nkb && q.post_kb0 <= q.feat_kb0 && q.feat_kb0 + (q.D + FBK - 1) / FBK <= q.post_kb1,
+                "fused step: the post K range must cover the feature blocks");
   SFB_CHECK_ARG(q.q && q.segA && (q.lenB == 0 || q.segB) && (reinterpret_cast<uintptr_t>(q.segA) & 15u) == 0 &&
                     (q.strideA_b % 4) == 0 && (q.lenB == 0 || ((reinterpret_cast<uintptr_t>(q.segB) & 15u) == 0 && (q.strideB_b % 4) == 0)),
                 "fused step: visual source missing / misaligned");

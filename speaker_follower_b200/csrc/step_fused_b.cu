@@ -39,6 +39,7 @@ constexpr uint32_t TA_HALF = (TBM / 8) * TSBO;   // 16 KB: one (hi | lo) weight 
 constexpr int T_RW = 8;                          // rows per ring chunk = compute warps
 constexpr int T_MAXCH = 8;                       // ring depth in chunks
 constexpr int T_MAXKH = 4;                       // K blocks per CTA of a pair (K <= 512)
+constexpr int T_BST = 3;                         // activation stages of a projection CTA
 
 __device__ __forceinline__ bool t_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t i = 0; i < (1u << 26); ++i)
@@ -70,8 +71,10 @@ __device__ __forceinline__ unsigned int t_ld_acq(const unsigned int* p) {
   return v;
 }
 __device__ __forceinline__ bool t_spin_ge(const unsigned int* p, unsigned int target) {
-  for (uint32_t i = 0; i < (1u << 24); ++i)
+  for (uint32_t i = 0; i < (1u << 22); ++i) {   // one poller per CTA, backing off: the arrivals must not be starved
     if (t_ld_acq(p) >= target) return true;
+    __nanosleep(40);
+  }
   return false;
 }
 }  // namespace
@@ -103,17 +106,16 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
     const uint32_t b_half = (uint32_t)(NB / 8) * TSBO;
     const uint32_t bstage = 2 * b_half;
     unsigned char* wbuf = smem;                                             // [T_MAXKH][32 KB]; later the parked partial
-    unsigned char* bst = smem + (size_t)T_MAXKH * 2 * TA_HALF;              // [2][bstage]
-    uint64_t* wfull = reinterpret_cast<uint64_t*>(bst + 2 * bstage);
-    uint64_t* bfull = wfull + 1;      // [2]
-    uint64_t* bempty = bfull + 2;     // [2]
-    uint64_t* done = bempty + 2;
+    unsigned char* bst = smem + (size_t)T_MAXKH * 2 * TA_HALF;              // [T_BST][bstage]
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(bst + (size_t)T_BST * bstage);
+    uint64_t* bfull = wfull + 1;      // [T_BST]
+    uint64_t* bempty = bfull + T_BST; // [T_BST]
+    uint64_t* done = bempty + T_BST;
     const uint32_t tmem_cols = NB <= 32 ? 32 : NB <= 64 ? 64 : NB <= 128 ? 128 : 256;
     if (warp == 0) {
       if (lane == 0) {
         mbar_init(wfull, 1);
-        mbar_init(&bfull[0], 1); mbar_init(&bfull[1], 1);
-        mbar_init(&bempty[0], 1); mbar_init(&bempty[1], 1);
+        for (int i = 0; i < T_BST; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
         mbar_init(done, 1);
       }
       mbar_fence_init();
@@ -165,8 +167,8 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
               asm volatile("fence.proxy.async;" ::: "memory");
             }
             for (int k = 0; k < nkh; ++k, ++bcount) {
-              const int s = bcount & 1;
-              if (bcount >= 2) fail = !t_wait(&bempty[s], (uint32_t)((bcount >> 1) - 1) & 1u) || fail;
+              const int s = bcount % T_BST;
+              if (bcount >= T_BST) fail = !t_wait(&bempty[s], (uint32_t)(bcount / T_BST - 1) & 1u) || fail;
               mbar_expect_tx(&bfull[s], bstage);
               bulk_g2s(bst + (size_t)s * bstage, b_base + (size_t)(kh0 + k) * bstage, bstage, &bfull[s]);
             }
@@ -177,8 +179,8 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
           const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
           fail = !t_wait(wfull, jpar) || fail;
           for (int k = 0; k < nkh; ++k, ++bcount) {
-            const int s = bcount & 1;
-            fail = !t_wait(&bfull[s], (uint32_t)(bcount >> 1) & 1u) || fail;
+            const int s = bcount % T_BST;
+            fail = !t_wait(&bfull[s], (uint32_t)(bcount / T_BST) & 1u) || fail;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
               const uint32_t a_hi = smem_u32(wbuf + (size_t)k * 2 * TA_HALF), a_lo = a_hi + TA_HALF;
@@ -264,72 +266,102 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
   } else {
     // =====================================================================================================
-    // row CTA: text attention, h~, action scoring and rollout tail of ONE batch element
+    // row CTAs: a cluster of two serves TWO batch elements — a long one and a short one (element c and B-1-c: the
+    // batch is sorted by instruction length, so the pair streams about the same number of rows as every other pair).
+    // CTA `rank` streams every other un-masked row of BOTH elements; each CTA then finalises one element (rank 0 the
+    // first, rank 1 the second): the partial softmax state of the other element is parked in shared memory and pulled
+    // by its owner through distributed shared memory.  The owner goes on to h~, action scoring and the rollout tail.
     // =====================================================================================================
-    const int b = cid - 2 * P;
+    const int rc = (cid - 2 * P) >> 1, rank = cid & 1;
     const int L = q.L, A = q.A, E = q.E, NCH = q.nch;
+    const int eA = rc < B ? rc : -1, eB = (B - 1 - rc > rc) ? B - 1 - rc : -1;
+    const int own = rank == 0 ? eA : eB, other = rank == 0 ? eB : eA;
+    const int els[2] = {other, own};
     auto rmark = [&](int which) {   // bring-up timeline of the first row CTA
-      if (q.trace && tid == 0 && b == 0) q.trace[which] = globaltimer_ns();
+      if (q.trace && tid == 0 && cid == 2 * P) q.trace[which] = globaltimer_ns();
     };
-    const int nv = H >> 2;                              // float4 per row; each lane owns NJ = nv / 32 of them
+    const int nv = H >> 2;                              // float4 per row; a lane owns up to 4 of them (H <= 512)
+    const int Lr = (L + 3) & ~3;
     const uint32_t row_bytes = (uint32_t)H * 4u, chunk_bytes = (uint32_t)T_RW * 2u * row_bytes;
-    float* ring = reinterpret_cast<float*>(smem);      // [NCH][T_RW][2][H]  (key row, value row)
+    float* ring = reinterpret_cast<float*>(smem);      // [NCH][T_RW][2][H]  (key row, value row); later the candidate rows
     const size_t ring_bytes = (size_t)NCH * chunk_bytes;
-    float* gs = reinterpret_cast<float*>(smem + ring_bytes);                 // [E + 4]
-    float* sc = gs + ((E + 4 + 3) & ~3);                                     // [L] raw scores (by list position)
-    int* list = reinterpret_cast<int*>(sc + ((L + 3) & ~3));                 // [L] un-masked positions
-    uint64_t* rfull = reinterpret_cast<uint64_t*>(list + ((L + 3) & ~3) + 2);
-    rfull = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(rfull) + 7) & ~uintptr_t(7));
+    float* wacc = reinterpret_cast<float*>(smem + ring_bytes);               // [8][H] per-warp partial sums
+    float* xacc = wacc + 8 * H;                                              // [H] this CTA's partial of the OTHER element (pulled by the peer)
+    float* xstat = xacc + H;                                                 // (m, Z) of: other, own  (read by the peer)
+    float* wst = xstat + 4;                                                  // [8][2] per-warp (max, sum)
+    float* gs = wst + 16;                                                    // [E + 4]
+    float* sc = gs + ((E + 4 + 3) & ~3);                                     // [2][Lr] raw scores by list position
+    float* slog = sc + 2 * Lr;                                               // [Ar] logits of the own element
+    float* sval = slog + ((A + 3) & ~3);                                     // [Ar] validity flags
+    int* list = reinterpret_cast<int*>(sval + ((A + 3) & ~3));               // [2][Lr] un-masked positions
+    uint64_t* rfull = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(list + 2 * Lr) + 15) & ~uintptr_t(7));
     uint64_t* rempty = rfull + T_MAXCH;
     uint64_t* candfull = rempty + T_MAXCH;
     uint64_t* ring_free = candfull + 1;
-    float* wstat = reinterpret_cast<float*>(ring_free + 1);                  // [8][2] (max, sum) per warp
-    __shared__ int s_nvalid;
-    if (b < B) {
-      const uint8_t* mrow = q.mask ? q.mask + (size_t)b * q.ldmask : nullptr;
-      if (warp == 0) {
-        if (lane < T_MAXCH) {
-          mbar_init(&rfull[lane], 1);
-          mbar_init(&rempty[lane], T_RW);
-        }
-        if (lane == 0) {
-          mbar_init(candfull, 1);
-          mbar_init(ring_free, 1);
-        }
-        mbar_fence_init();
-        // compact the un-masked positions (padding masks are a prefix complement in practice, any mask works)
-        int n = 0;
-        for (int base = 0; base < L; base += 32) {
-          const int l = base + lane;
-          const bool ok = l < L && !(mrow && mrow[l]);
-          const unsigned bal = __ballot_sync(0xffffffffu, ok);
-          if (ok) list[n + __popc(bal & ((1u << lane) - 1u))] = l;
-          n += __popc(bal);
-        }
-        if (lane == 0) s_nvalid = n;
+    __shared__ int s_nvalid[2];
+    __shared__ int s_at;
+    if (warp == 0) {
+      if (lane < T_MAXCH) {
+        mbar_init(&rfull[lane], 1);
+        mbar_init(&rempty[lane], T_RW);
       }
-      __syncthreads();
-      const int nvalid = s_nvalid, nchunks = (nvalid + T_RW - 1) / T_RW;
-      if (warp == 9) {
-        // ---- producer: key / value rows (per-episode constants: no dependency wait), later the candidate rows
-        const uint64_t pol = policy_evict_normal();
-        const float* kb_ = q.ctx_k + (size_t)b * L * H;
-        const float* vb_ = q.ctx_o + (size_t)b * L * H;
-        bool ok = true;
-        for (int c = 0; c < nchunks; ++c) {
-          const int slot = c % NCH;
-          if (c >= NCH) ok = t_wait(&rempty[slot], (uint32_t)(c / NCH - 1) & 1u) && ok;
-          const int rows = min(T_RW, nvalid - c * T_RW);
+      if (lane == 0) {
+        mbar_init(candfull, 1);
+        mbar_init(ring_free, 1);
+      }
+      mbar_fence_init();
+      // compact the un-masked positions of both elements (padding masks are suffixes in practice; any mask works)
+      for (int k = 0; k < 2; ++k) {
+        const int e = els[k];
+        int n = 0;
+        if (e >= 0) {
+          const uint8_t* mrow = q.mask ? q.mask + (size_t)e * q.ldmask : nullptr;
+          for (int base = 0; base < L; base += 32) {
+            const int l = base + lane;
+            const bool ok = l < L && !(mrow && mrow[l]);
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (ok) list[k * Lr + n + __popc(bal & ((1u << lane) - 1u))] = l;
+            n += __popc(bal);
+          }
+        }
+        if (lane == 0) s_nvalid[k] = n;
+      }
+    }
+    __syncthreads();
+    // rows of element k this CTA streams: list positions rank, rank + 2, ...
+    int nmine[2], nchk[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      nmine[k] = s_nvalid[k] > rank ? (s_nvalid[k] - rank + 1) / 2 : 0;
+      nchk[k] = (nmine[k] + T_RW - 1) / T_RW;
+    }
+    if (warp == 9) {
+      // ---- producer: key / value rows (per-episode constants: no dependency wait), later the candidate rows
+      const uint64_t pol = policy_evict_normal();
+      bool ok = true;
+      int cg = 0;
+      for (int k = 0; k < 2; ++k) {
+        if (els[k] < 0) continue;
+        const float* kb_ = q.ctx_k + (size_t)els[k] * L * H;
+        const float* vb_ = q.ctx_o + (size_t)els[k] * L * H;
+        for (int c = 0; c < nchk[k]; ++c, ++cg) {
+          const int slot = cg % NCH;
+          if (cg >= NCH) ok = t_wait(&rempty[slot], (uint32_t)(cg / NCH - 1) & 1u) && ok;
+          const int rows = min(T_RW, nmine[k] - c * T_RW);
           if (lane == 0) mbar_expect_tx(&rfull[slot], (uint32_t)rows * 2u * row_bytes);
           __syncwarp();
           if (lane < 2 * rows) {   // lanes 0..rows-1: key rows, rows..2rows-1: value rows
             const int r = lane < rows ? lane : lane - rows;
-            const int l = list[c * T_RW + r];
+            const int l = list[k * Lr + rank + 2 * (c * T_RW + r)];
             float* dst = ring + ((size_t)slot * T_RW + r) * 2 * H + (lane < rows ? 0 : H);
             bulk_g2s_hint(dst, (lane < rows ? kb_ : vb_) + (size_t)l * H, row_bytes, &rfull[slot], pol);
           }
         }
-        // candidate rows of the element into the freed ring (step inputs)
+      }
+      cluster_sync_all();   // X1: partials parked
+      cluster_sync_all();   // X2: partials pulled
+      if (own >= 0) {
+        // candidate rows of the own element into the freed ring (step inputs)
         ok = t_wait(ring_free, 0) && ok;
         if (lane == 0) {
           const uint64_t pol2 = policy_evict_first();
@@ -337,109 +369,161 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
           if (q.cand_table == nullptr) {
             mbar_expect_tx(candfull, (uint32_t)((size_t)A * E * 4));
             for (int a = 0; a < A; ++a)
-              bulk_g2s_hint(us + (size_t)a * E, q.all_u_t + ((size_t)b * A + a) * E, (uint32_t)E * 4u, candfull, pol2);
+              bulk_g2s_hint(us + (size_t)a * E, q.all_u_t + ((size_t)own * A + a) * E, (uint32_t)E * 4u, candfull, pol2);
           } else {
             int n = 0;
-            for (int a = 0; a < A; ++a) n += q.cand_view[(size_t)b * A + a] >= 0;
+            for (int a = 0; a < A; ++a) n += q.cand_view[(size_t)own * A + a] >= 0;
             mbar_expect_tx(candfull, (uint32_t)((size_t)n * q.img_dim * 4));
-            const float* slab = q.cand_table + (size_t)q.vp_idx[b] * q.cand_V * q.img_dim;
+            const float* slab = q.cand_table + (size_t)q.vp_idx[own] * q.cand_V * q.img_dim;
             for (int a = 0; a < A; ++a) {
-              const int v = q.cand_view[(size_t)b * A + a];
+              const int v = q.cand_view[(size_t)own * A + a];
               if (v >= 0) bulk_g2s_hint(us + (size_t)a * E, slab + (size_t)v * q.img_dim, (uint32_t)q.img_dim * 4u, candfull, pol2);
             }
           }
         }
-        if (!ok) s_fail = 1;
-        pdl_wait();
-      } else if (warp == 8) {
-        pdl_wait();
-      } else {
-        // ---- compute warps: each warp owns whole rows (row r of a chunk -> warp r)
-        pdl_wait();   // h1d is produced by the kernel before this one
-        rmark(1);
-        float4 qv[4], acc[4];
-        {
-          const float4* q4 = reinterpret_cast<const float4*>(q.h1d + (size_t)b * q.ldh);
+      }
+      if (!ok) s_fail = 1;
+      pdl_wait();
+    } else if (warp == 8) {
+      cluster_sync_all();
+      cluster_sync_all();
+      pdl_wait();
+    } else {
+      // ---- compute warps: each warp owns whole rows (row r of a chunk -> warp r)
+      pdl_wait();   // h1d is produced by the kernel before this one
+      rmark(1);
+      float4 o_own = make_float4(0.f, 0.f, 0.f, 0.f);   // threads < nv: the CTA-level partial of the own element
+      int cg = 0;
+      for (int k = 0; k < 2; ++k) {
+        const int e = els[k];
+        float m = -INFINITY, Z = 0.f;
+        float4 acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e >= 0) {
+          float4 qv[4];
+          const float4* q4 = reinterpret_cast<const float4*>(q.h1d + (size_t)e * q.ldh);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int idx = lane + 32 * j;
             qv[j] = idx < nv ? q4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-            acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-        }
-        float m = -INFINITY, Z = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
-          const int slot = c % NCH, i = c * T_RW + warp;
-          if (!t_wait(&rfull[slot], (uint32_t)(c / NCH) & 1u)) s_fail = 1;
-          if (i < nvalid) {
-            const float4* key4 = reinterpret_cast<const float4*>(ring + ((size_t)slot * T_RW + warp) * 2 * H);
-            const float4* val4 = key4 + nv;
-            float part = 0.f;
-            float4 v[4];
+          for (int c = 0; c < nchk[k]; ++c, ++cg) {
+            const int slot = cg % NCH, i = c * T_RW + warp;
+            if (!t_wait(&rfull[slot], (uint32_t)(cg / NCH) & 1u)) s_fail = 1;
+            if (i < nmine[k]) {
+              const float4* key4 = reinterpret_cast<const float4*>(ring + ((size_t)slot * T_RW + warp) * 2 * H);
+              const float4* val4 = key4 + nv;
+              float part = 0.f;
+              float4 v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int idx = lane + 32 * j;
-              if (idx < nv) {
-                const float4 k4 = key4[idx];
-                v[j] = val4[idx];
-                part = fmaf(k4.x, qv[j].x, part); part = fmaf(k4.y, qv[j].y, part);
-                part = fmaf(k4.z, qv[j].z, part); part = fmaf(k4.w, qv[j].w, part);
-              } else {
-                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int j = 0; j < 4; ++j) {
+                const int idx = lane + 32 * j;
+                if (idx < nv) {
+                  const float4 k4 = key4[idx];
+                  v[j] = val4[idx];
+                  part = fmaf(k4.x, qv[j].x, part); part = fmaf(k4.y, qv[j].y, part);
+                  part = fmaf(k4.z, qv[j].z, part); part = fmaf(k4.w, qv[j].w, part);
+                } else {
+                  v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
               }
-            }
-            part = warp_sum(part);
-            if (lane == 0) sc[i] = part;
-            const float mn = fmaxf(m, part), corr = __expf(m - mn), e = __expf(part - mn);
-            Z = fmaf(Z, corr, e);
+              part = warp_sum(part);
+              if (lane == 0) sc[k * Lr + rank + 2 * i] = part;
+              const float mn = fmaxf(m, part), corr = __expf(m - mn), ex = __expf(part - mn);
+              Z = fmaf(Z, corr, ex);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              acc[j].x = fmaf(e, v[j].x, acc[j].x * corr); acc[j].y = fmaf(e, v[j].y, acc[j].y * corr);
-              acc[j].z = fmaf(e, v[j].z, acc[j].z * corr); acc[j].w = fmaf(e, v[j].w, acc[j].w * corr);
+              for (int j = 0; j < 4; ++j) {
+                acc[j].x = fmaf(ex, v[j].x, acc[j].x * corr); acc[j].y = fmaf(ex, v[j].y, acc[j].y * corr);
+                acc[j].z = fmaf(ex, v[j].z, acc[j].z * corr); acc[j].w = fmaf(ex, v[j].w, acc[j].w * corr);
+              }
+              m = mn;
             }
-            m = mn;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rempty[slot]);
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&rempty[slot]);
         }
-        t_bar256();   // nobody reads the ring any more
-        rmark(4);
-        // ---- merge the 8 per-warp partials through shared memory (the ring's first bytes)
-        float* mbuf = ring;   // [8][H]
+        // the 8 per-warp partials of this element -> one CTA partial
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int idx = lane + 32 * j;
-          if (idx < nv) reinterpret_cast<float4*>(mbuf + (size_t)warp * H)[idx] = acc[j];
+          if (idx < nv) reinterpret_cast<float4*>(wacc + (size_t)warp * H)[idx] = acc[j];
         }
-        if (lane == 0) { wstat[2 * warp] = m; wstat[2 * warp + 1] = Z; }
+        if (lane == 0) { wst[2 * warp] = m; wst[2 * warp + 1] = Z; }
         t_bar256();
-        float M = -INFINITY, Zt = 0.f, wk[8];
+        float Mc = -INFINITY, Zc = 0.f, wk[8];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) M = fmaxf(M, wstat[2 * w]);
+        for (int w = 0; w < 8; ++w) Mc = fmaxf(Mc, wst[2 * w]);
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
-          wk[w] = wstat[2 * w] != -INFINITY ? __expf(wstat[2 * w] - M) : 0.f;
-          Zt = fmaf(wstat[2 * w + 1], wk[w], Zt);
+          wk[w] = wst[2 * w] != -INFINITY ? __expf(wst[2 * w] - Mc) : 0.f;
+          Zc = fmaf(wst[2 * w + 1], wk[w], Zc);
         }
-        const float inv = Zt > 0.f ? 1.0f / Zt : 0.f;    // every position masked -> zeros (the reference would give NaN)
-        if (q.alpha) {
-          float* arow = q.alpha + (size_t)b * q.ldalpha;
-          for (int l = tid; l < L; l += 256) arow[l] = 0.f;
-          t_bar256();
-          for (int i = tid; i < nvalid; i += 256) arow[list[i]] = __expf(sc[i] - M) * inv;
+        if (tid < nv) {
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            const float4 pw = reinterpret_cast<const float4*>(wacc + (size_t)w * H)[tid];
+            o.x = fmaf(wk[w], pw.x, o.x); o.y = fmaf(wk[w], pw.y, o.y); o.z = fmaf(wk[w], pw.z, o.z); o.w = fmaf(wk[w], pw.w, o.w);
+          }
+          if (k == 0) reinterpret_cast<float4*>(xacc)[tid] = o;
+          else o_own = o;
         }
+        if (tid == 0) { xstat[2 * k] = Mc; xstat[2 * k + 1] = Zc; }
+        t_bar256();   // wacc / wst are free again
+      }
+      rmark(4);
+      cluster_sync_all();   // X1: both CTAs have parked the partial of the element they do not own + both stats
+      // merged softmax state of both elements (this CTA's partial + the peer's)
+      const uint32_t pstat = dsmem_addr(xstat, (uint32_t)(rank ^ 1)), pacc = dsmem_addr(xacc, (uint32_t)(rank ^ 1));
+      float Mm[2], inv[2], wmine[2], wpeer[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {   // my slot k pairs with the peer's slot 1 - k (its "own" is my "other")
+        const float m0 = xstat[2 * k], z0 = xstat[2 * k + 1];
+        const float m1 = dsmem_ld_f32(pstat + (uint32_t)(2 * (1 - k)) * 4u), z1 = dsmem_ld_f32(pstat + (uint32_t)(2 * (1 - k) + 1) * 4u);
+        Mm[k] = fmaxf(m0, m1);
+        wmine[k] = m0 != -INFINITY ? __expf(m0 - Mm[k]) : 0.f;
+        wpeer[k] = m1 != -INFINITY ? __expf(m1 - Mm[k]) : 0.f;
+        const float zt = z0 * wmine[k] + z1 * wpeer[k];
+        inv[k] = zt > 0.f ? 1.0f / zt : 0.f;            // every position masked -> zeros (the reference would give NaN)
+      }
+      if (own >= 0 && tid < nv) {
+        const float4 pp = dsmem_ld_f32x4(pacc + (uint32_t)tid * 16u);
+        // fixed summation order (rank 0's partial first) whichever CTA owns the element
+        const float wa = (rank == 0 ? wmine[1] : wpeer[1]) * inv[1], wb = (rank == 0 ? wpeer[1] : wmine[1]) * inv[1];
+        const float4 pa = rank == 0 ? o_own : pp, pb = rank == 0 ? pp : o_own;
+        o_own.x = pa.x * wa + pb.x * wb; o_own.y = pa.y * wa + pb.y * wb;
+        o_own.z = pa.z * wa + pb.z * wb; o_own.w = pa.w * wa + pb.w * wb;
+      }
+      if (q.alpha) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (els[k] < 0) continue;
+          float* arow = q.alpha + (size_t)els[k] * q.ldalpha;
+          for (int i = tid; i < nmine[k]; i += 256) {
+            const int li = rank + 2 * i;
+            arow[list[k * Lr + li]] = __expf(sc[k * Lr + li] - Mm[k]) * inv[k];
+          }
+        }
+        if (own >= 0 && q.mask) {   // masked positions of the own element: zero
+          const uint8_t* mrow = q.mask + (size_t)own * q.ldmask;
+          for (int l = tid; l < L; l += 256)
+            if (mrow[l]) q.alpha[(size_t)own * q.ldalpha + l] = 0.f;
+        }
+      }
+      cluster_sync_all();   // X2: nobody needs the peer's shared memory any more
+      if (own >= 0) {
+        const int b = own;
+        // inputs of the tail, fetched while hh / g are still on their way
+        if (q.has_tail)
+          for (int a = tid; a < A; a += 256) sval[a] = q.tail.is_valid[(size_t)b * A + a];
         // h~ = tanh(sum_l alpha_l ctx_o[l] + hh) once hh (W_out_h h1d, from the projection pairs) has arrived
         if (tid == 0 && !t_spin_ge(cnt_hh, 2u * (unsigned int)q.hh_tiles)) s_fail = 1;
         t_bar256();
         const size_t half = (size_t)NB * 128;
-        for (int col = tid; col < nv; col += 256) {
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int w = 0; w < 8; ++w) {
-            const float4 pw = reinterpret_cast<const float4*>(mbuf + (size_t)w * H)[col];
-            const float wgt = wk[w] * inv;
-            o.x = fmaf(wgt, pw.x, o.x); o.y = fmaf(wgt, pw.y, o.y); o.z = fmaf(wgt, pw.z, o.z); o.w = fmaf(wgt, pw.w, o.w);
-          }
+        if (tid < nv) {
+          const int col = tid;
+          float4 o = o_own;
           const float4 hh4 = __ldcg(reinterpret_cast<const float4*>(q.hh + (size_t)b * q.ldhh + col * 4));
           o.x = tanhf(o.x + hh4.x); o.y = tanhf(o.y + hh4.y); o.z = tanhf(o.z + hh4.z); o.w = tanhf(o.w + hh4.w);
           if (q.h_tilde) *reinterpret_cast<float4*>(q.h_tilde + (size_t)b * H + col * 4) = o;
@@ -451,10 +535,10 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
                                (size_t)(b & 7) * 16 + (size_t)(k & 7) * 2;
           *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
           *reinterpret_cast<uint2*>(dst + half) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+          asm volatile("fence.proxy.async;" ::: "memory");
+          __threadfence();
         }
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __threadfence();
-        t_bar256();   // h~ published; the merge buffer is consumed -> the ring can take the candidate rows
+        t_bar256();   // h~ published; the ring can take the candidate rows
         if (tid == 0) {
           atomicAdd(cnt_ht, 1u);
           mbar_arrive(ring_free);
@@ -464,11 +548,9 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
         float* us = ring;   // [A][E]
         if (q.cand_table) {
           // env.py:60-75: [feature[absViewIndex, :img_dim], sin(rh) x n, cos(rh) x n, sin(re) x n, cos(re) x n]; rows
-          // without a view (stop, padding) are zero.  The image part arrives by bulk copy; this fills the rest.
+          // without a view (stop, padding) are zero.  The image part arrives by bulk copy (disjoint bytes); this fills
+          // the rest.
           const int loc = E - q.img_dim, grp = loc >> 2;
-          // the bulk copies target the same rows: wait until the producer may have started them is not needed — the
-          // regions written here (orientation part, whole rows without a view) are disjoint from the copied ones
-          if (!t_wait(ring_free, 0)) s_fail = 1;
           for (int i = tid; i < A * loc; i += 256) {
             const int a = i / loc, j = i - a * loc;
             const bool okv = q.cand_view[(size_t)b * A + a] >= 0;
@@ -500,14 +582,21 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
             accd = fmaf(u.z, g4.z, accd); accd = fmaf(u.w, g4.w, accd);
           }
           accd = warp_sum(accd);
-          if (lane == 0) q.logit[(size_t)b * A + a] = accd + cst;
+          if (lane == 0) slog[a] = accd + cst;
         }
         t_bar256();
-        if (q.has_tail && warp == 0) tail_row(q.tail, b, lane, us);
+        if (q.has_tail) {
+          if (warp == 0) {
+            const int a_t = tail_row(q.tail, b, lane, us, slog, sval, false);
+            if (lane == 0) s_at = a_t;
+          }
+          t_bar256();
+          tail_copy_u(q.tail, b, s_at, us, tid, 256);
+        } else {
+          for (int a = tid; a < A; a += 256) q.logit[(size_t)b * A + a] = slog[a];
+        }
         rmark(7);
       }
-    } else {
-      pdl_wait();
     }
     __syncthreads();
   }
@@ -546,13 +635,14 @@ FusedTextPlan text_score_fused_plan(int B, int L, int A, int H, int E, int F, bo
   pl.grid = 2 * pl.P + rows;
   // shared memory: the larger of the two roles
   const size_t b_half = (size_t)(pl.NB / 8) * TSBO;
-  const size_t pair_bytes = (size_t)T_MAXKH * 2 * TA_HALF + 2 * 2 * b_half + 8 * sizeof(uint64_t) + 64;
+  const size_t pair_bytes = (size_t)T_MAXKH * 2 * TA_HALF + (size_t)T_BST * 2 * b_half + (2 * T_BST + 2) * sizeof(uint64_t) + 64;
   const size_t chunk = (size_t)T_RW * 2 * H * 4;
-  const size_t row_fixed = ((size_t)(E + 4 + 3) & ~size_t(3)) * 4 + 2 * ((size_t)(L + 3) & ~size_t(3)) * 4 + 16 +
-                           (2 * T_MAXCH + 2) * sizeof(uint64_t) + 16 * sizeof(float) + 64;
+  const size_t Lr = (size_t)(L + 3) & ~size_t(3), Ar = (size_t)(A + 3) & ~size_t(3);
+  const size_t row_fixed = ((size_t)8 * H + H + 4 + 16) * 4 + ((size_t)(E + 4 + 3) & ~size_t(3)) * 4 + 4 * Lr * 4 + 2 * Ar * 4 + 32 +
+                           (2 * T_MAXCH + 2) * sizeof(uint64_t) + 64;
   const size_t budget = 227 * 1024 - 2048;
-  const size_t cand = (size_t)A * E * 4, mrg = (size_t)8 * H * 4;
-  size_t ring_min = cand > mrg ? cand : mrg;
+  const size_t cand = (size_t)A * E * 4;
+  size_t ring_min = cand;
   if (ring_min < 2 * chunk) ring_min = 2 * chunk;
   if (row_fixed + ring_min > budget) return pl;
   int nch = (int)((budget - row_fixed) / chunk);
