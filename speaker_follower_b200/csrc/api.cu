@@ -8,7 +8,7 @@ namespace sfb {
 
 int g_disable_tc = 0;
 int g_disable_fused = 0;
-static int g_fused_pre_weight = 4, g_fused_nopre = 0;
+static int g_fused_pre_weight = 4, g_fused_nopre = 0, g_fused_dbg = 0;
 int g_disable_pdl = 0;
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
@@ -383,6 +383,7 @@ int32_t sfb_set_option(const char* name, int32_t value) {
   if (n == "disable_fused") { g_disable_fused = value; return 0; }
   if (n == "fused_pre_weight") { g_fused_pre_weight = value; return 0; }
   if (n == "fused_nopre") { g_fused_nopre = value; return 0; }
+  if (n == "fused_dbg") { g_fused_dbg = value; return 0; }
   if (n == "trace") {   // value 1: (re)start recording kernel slots; 0: stop
     g_trace_on = value;
     g_trace_n = 0;
@@ -937,6 +938,7 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
     f.g.lstm = lstm_e; f.g.M = B; f.g.N = 4 * d.H;
     f.B = B;
     f.pre_weight_free = g_fused_pre_weight;
+    f.dbg = g_fused_dbg;
     if (g_fused_nopre) { f.post_kb0 = 0; f.post_kb1 = P.nkb_gates; }   // bring-up: no overlap of the gate GEMM with the gather
     SFB_PROPAGATE(launch_vis_lstm_fused(f, st, ws.fz, ws.fz_bytes));
   } else {

@@ -177,6 +177,7 @@ struct FusedVisLstmParams {
   int feat_kb0;                           // first K block of the attention output inside b_pk
   GemmParams g;                           // LSTM epilogue (g.lstm), M = B
   int B;
+  int dbg;                                // bring-up: 1 = gather without arithmetic, 2 = dot products only
   int pre_weight_free;                    // share of the pre K blocks a CTA without a gather role takes, relative to 1 for a gather CTA
   // filled by the launcher
   int NB, nch, chunk_rows;

@@ -29,19 +29,22 @@ namespace sfb {
 
 namespace {
 constexpr int FBM = 128, FBK = 64;
-constexpr int FNT = 352;                         // 8 compute warps + MMA issuer + GEMM producer + gather producer
+constexpr int FNT = 384;                         // 8 compute warps + MMA issuer + GEMM producer + gather producer + 1 epilogue helper
 constexpr int FGS = 3;                           // GEMM stages at most (1 dedicated + 2 carved from the ring)
 constexpr uint32_t FCORE = 128;
 constexpr uint32_t FSBO = (FBK / 8) * FCORE;
 constexpr uint32_t FLBO = FCORE;
 constexpr uint32_t FA_HALF = (FBM / 8) * FSBO;   // 16 KB
-constexpr int F_RB = 4;                          // slab rows per chunk = rows consumed per block barrier
-constexpr int F_NJ = 3;                          // float4 slices per thread (D <= 3072)
+constexpr int F_RB = 6;                          // slab rows per ring chunk (one bulk copy); <= 8 so that a warp owns at most one row of a chunk
+constexpr int F_D = 2176;                        // row length this kernel is built for (2048 image + 128 orientation floats)
 constexpr int F_MAXCH = 8;                       // ring depth in chunks
 
 __device__ __forceinline__ bool f_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t i = 0; i < (1u << 26); ++i)
+#pragma unroll 1
+  for (uint32_t i = 0; i < (1u << 24); ++i) {
     if (mbar_try_wait(bar, parity)) return true;
+    __nanosleep(32);   // a hot try_wait loop competes with the compute warps for the shared-memory pipe
+  }
   return false;   // never hang the device: the launch is flagged as failed instead
 }
 __device__ __forceinline__ uint64_t f_desc(uint32_t smem_addr) {
@@ -111,8 +114,8 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
   uint64_t* rempty = rfull + F_MAXCH;                                                   // [F_MAXCH]
   uint64_t* locfull = rempty + F_MAXCH;
   uint64_t* ring_free = locfull + 1;
-  float* red = reinterpret_cast<float*>(ring_free + 1);                                 // [2][8][F_RB]
-  float* sc = red + 2 * 8 * F_RB;                                                       // [R] raw scores
+  float* red = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ring_free + 1) + 15) & ~uintptr_t(15));   // [2][8 warps][8 rows]
+  float* sc = red + 2 * 8 * 8;                                                          // [R] raw scores
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sc + ((R + 3) & ~3));
   __shared__ int s_fail;
 
@@ -242,6 +245,7 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
           __nanosleep(40);
         }
         ok = ok && arrived;
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[11] = globaltimer_ns();
         asm volatile("fence.proxy.async;" ::: "memory");   // the feature blocks were written with generic-proxy stores
         for (int j = 0; j < pf; ++j) issue_b(n_pre + j);
         for (int j = pf; j < n_post; ++j) {
@@ -288,84 +292,113 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
     }
     if (!ok && lane == 0) s_fail = 1;
     pdl_wait();
+  } else if (warp >= 8) {
+    pdl_wait();   // epilogue helper warp
   } else {
     // =============================== warps 0-7: gather consumers ===============================
     pdl_wait();   // q is produced by the previous step
     trace_mark(p.trace, 1);
     if (has_gather) {
+      // Column ownership: thread t owns float4 columns t and 256 + t of the feature-table part of a row and (threads
+      // 0-31) column t of its tail (orientation block, or the last 128 floats of a dense row).  Few registers per
+      // thread, so the F_RB x 3 shared-memory loads of a chunk are all issued before the first use (branch-free:
+      // addresses are always valid, lanes without a tail column select zero), F_RB independent dot products, one
+      // transposed-butterfly reduction and ONE block barrier per chunk.
       const int b = cid;
-      float4 qv[F_NJ], acc[F_NJ];
+      const int nvA = lenA >> 2;
+      const bool has_tail = tid < nvec - 512;           // D = 2176: 544 float4 per row = 2 x 256 + 32
+      const int tcol = tid & 31;
+      float4 qv[3], acc[3];
       {
         const float4* q4 = reinterpret_cast<const float4*>(q.q + (size_t)b * q.ldq);
+        qv[0] = q4[tid]; qv[1] = q4[256 + tid];
+        qv[2] = has_tail ? q4[512 + tcol] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < F_NJ; ++j) {
-          const int idx = tid + 256 * j;
-          qv[j] = idx < nvec ? q4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-          acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int j = 0; j < 3; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const int nvA = lenA >> 2, nvB = lenB >> 2;
+      // tail columns: orientation block [R][lenB/4] (gather source) or columns 512.. of the dense chunk row
+      const float4* tail_base = lenB > 0 ? reinterpret_cast<const float4*>(locb) + tcol : nullptr;
+      const int tail_stride = lenB > 0 ? (lenB >> 2) : nvA;
       if (lenB > 0 && !f_wait(locfull, 0)) s_fail = 1;
       float m = -INFINITY, Z = 0.f;
       int c = 0;
+      long long waited = 0;   // bring-up: cycles thread 0 spent waiting for slab data
       for (int i0 = 0; i0 < R; i0 += F_RB, ++c) {
         const int nb = min(F_RB, R - i0);
         const int slot = c % NCH;
+        const long long t0 = p.trace ? clock64() : 0;
         if (!f_wait(&rfull[slot], (uint32_t)(c / NCH) & 1u)) s_fail = 1;
+        if (p.trace) waited += clock64() - t0;
         if (c == 0) trace_mark(p.trace, 8);
         if (i0 + F_RB >= R) trace_mark(p.trace, 9);
-        const float4* chunk4 = reinterpret_cast<const float4*>(ring + (size_t)slot * chunk_floats);
-        float4 v[F_RB][F_NJ];
-        float part[F_RB];
+        const float4* pA = reinterpret_cast<const float4*>(ring + (size_t)slot * chunk_floats) + tid;
+        const float4* pT = lenB > 0 ? tail_base + (size_t)i0 * tail_stride : pA - tid + 512 + tcol;
+        float4 v[F_RB][3];
+        if (q.dbg == 1) {   // bring-up: stream only
+          bar_sync_256();
+          if (tid == 0) mbar_arrive(&rempty[slot]);
+          continue;
+        }
 #pragma unroll
         for (int r = 0; r < F_RB; ++r) {
-          part[r] = 0.f;
-          if (r < nb) {
-            const float4* rowA = chunk4 + (size_t)r * nvA;
-            const float4* rowB = reinterpret_cast<const float4*>(locb) + (size_t)(i0 + r) * nvB;
-#pragma unroll
-            for (int j = 0; j < F_NJ; ++j) {
-              const int idx = tid + 256 * j;
-              float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (idx < nvA) x = rowA[idx];
-              else if (idx < nvec) x = rowB[idx - nvA];
-              v[r][j] = x;
-              part[r] = fmaf(x.x, qv[j].x, part[r]);
-              part[r] = fmaf(x.y, qv[j].y, part[r]);
-              part[r] = fmaf(x.z, qv[j].z, part[r]);
-              part[r] = fmaf(x.w, qv[j].w, part[r]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < F_NJ; ++j) v[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          const int rr = r < nb ? r : nb - 1;           // rows past the end re-read the last row (their weight is zero)
+          v[r][0] = pA[(size_t)rr * nvA];
+          v[r][1] = pA[(size_t)rr * nvA + 256];
+          v[r][2] = pT[(size_t)rr * tail_stride];
         }
-        // 4 row sums per warp with 6 shuffles (transposed butterfly): after two halving exchanges every lane holds
-        // ONE row's partial (row = lane bits 4,3), three more steps finish the sum inside each group of 8 lanes
-        float* rb = red + (c & 1) * 8 * F_RB;
+        float part[8];
+#pragma unroll
+        for (int r = 0; r < F_RB; ++r) {
+          if (!has_tail) v[r][2] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float d0 = fmaf(v[r][0].w, qv[0].w, fmaf(v[r][0].z, qv[0].z, fmaf(v[r][0].y, qv[0].y, v[r][0].x * qv[0].x)));
+          const float d1 = fmaf(v[r][1].w, qv[1].w, fmaf(v[r][1].z, qv[1].z, fmaf(v[r][1].y, qv[1].y, v[r][1].x * qv[1].x)));
+          const float d2 = fmaf(v[r][2].w, qv[2].w, fmaf(v[r][2].z, qv[2].z, fmaf(v[r][2].y, qv[2].y, v[r][2].x * qv[2].x)));
+          part[r] = (d0 + d1) + d2;
+        }
+#pragma unroll
+        for (int r = F_RB; r < 8; ++r) part[r] = 0.f;
+        // up to 8 row sums per warp with 9 shuffles (transposed butterfly): three halving exchanges leave every lane with
+        // ONE row's partial (row = lane bits 4,3,2), two more steps finish the sum inside each group of 4 lanes
+        float* rb = red + (c & 1) * 8 * 8;
+        if (q.dbg == 2) {   // bring-up: loads + dot products only
+          if (part[0] + part[1] + part[2] + part[3] + part[4] + part[5] == 123.456f) sc[0] = 1.f;
+          bar_sync_256();
+          if (tid == 0) mbar_arrive(&rempty[slot]);
+          continue;
+        }
         {
-          static_assert(F_RB == 4, "the reduction below is written for 4 rows per chunk");
-          const bool up = (lane & 16) != 0;
-          const float s0 = up ? part[0] : part[2], s1 = up ? part[1] : part[3];     // the half this lane gives away
-          const float k0 = up ? part[2] : part[0], k1 = up ? part[3] : part[1];     // the half it keeps
-          const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16), a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
-          const bool up2 = (lane & 8) != 0;
-          float v = (up2 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up2 ? a0 : a1, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          if ((lane & 7) == 0) rb[warp * F_RB + (lane >> 3)] = v;   // lanes 0, 8, 16, 24 hold rows 0, 1, 2, 3
+          const bool u4 = (lane & 16) != 0;
+          float a4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a4[i] = (u4 ? part[4 + i] : part[i]) + __shfl_xor_sync(0xffffffffu, u4 ? part[i] : part[4 + i], 16);
+          const bool u3 = (lane & 8) != 0;
+          float a2[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) a2[i] = (u3 ? a4[2 + i] : a4[i]) + __shfl_xor_sync(0xffffffffu, u3 ? a4[i] : a4[2 + i], 8);
+          const bool u2 = (lane & 4) != 0;
+          float t = (u2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, u2 ? a2[0] : a2[1], 4);
+          t += __shfl_xor_sync(0xffffffffu, t, 2);
+          t += __shfl_xor_sync(0xffffffffu, t, 1);
+          if ((lane & 3) == 0) rb[warp * 8 + (lane >> 2)] = t;   // lanes 0, 4, ..., 28 hold rows 0..7
         }
         bar_sync_256();   // every thread holds its slices in registers -> the chunk is free
         if (tid == 0) mbar_arrive(&rempty[slot]);
+        if (q.dbg == 3) continue;   // bring-up: no softmax / accumulation
         float sr[F_RB], mn = m;
+        {
+          float4 lo4 = make_float4(0.f, 0.f, 0.f, 0.f), hi4 = lo4;
 #pragma unroll
-        for (int r = 0; r < F_RB; ++r) {
-          sr[r] = 0.f;
+          for (int w = 0; w < 8; ++w) {
+            const float4 x0 = *reinterpret_cast<const float4*>(rb + w * 8), x1 = *reinterpret_cast<const float4*>(rb + w * 8 + 4);
+            lo4.x += x0.x; lo4.y += x0.y; lo4.z += x0.z; lo4.w += x0.w;
+            hi4.x += x1.x; hi4.y += x1.y; hi4.z += x1.z; hi4.w += x1.w;
+          }
+          const float all[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
 #pragma unroll
-          for (int w = 0; w < 8; ++w) sr[r] += rb[w * F_RB + r];
-          if (r >= nb) sr[r] = -INFINITY;
-          mn = fmaxf(mn, sr[r]);
+          for (int r = 0; r < F_RB; ++r) {
+            sr[r] = r < nb ? all[r] : -INFINITY;
+            mn = fmaxf(mn, sr[r]);
+          }
         }
 #pragma unroll
         for (int r = 0; r < F_RB; ++r)
@@ -374,12 +407,12 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
         float e[F_RB], esum = 0.f;
 #pragma unroll
         for (int r = 0; r < F_RB; ++r) {
-          e[r] = __expf(sr[r] - mn);
+          e[r] = __expf(sr[r] - mn);   // rows past the end: exp(-inf) = 0
           esum += e[r];
         }
         Z = fmaf(Z, corr, esum);
 #pragma unroll
-        for (int j = 0; j < F_NJ; ++j) {
+        for (int j = 0; j < 3; ++j) {
           float4 a = acc[j];
           a.x *= corr; a.y *= corr; a.z *= corr; a.w *= corr;
 #pragma unroll
@@ -396,15 +429,16 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
       bar_sync_256();   // all scores are in sc[]; nobody reads the ring any more
       if (tid == 0) mbar_arrive(ring_free);   // the ring becomes GEMM stages 1, 2
       trace_mark(p.trace, 4);
+      if (p.trace && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) p.trace[10] = p.trace[1] + (unsigned long long)(waited / 2);   // ~ns at ~2 GHz
       // the CTA owns the whole batch element: normalise and emit (fp32 + packed bf16 hi/lo for the post part)
       const float inv = Z > 0.f ? 1.0f / Z : 0.f;
       if (q.alpha)
         for (int i = tid; i < R; i += 256) q.alpha[(size_t)b * q.ldalpha + i] = __expf(sc[i] - m) * inv;
       const size_t half = (size_t)NB * 128;
 #pragma unroll
-      for (int j = 0; j < F_NJ; ++j) {
-        const int col = tid + 256 * j;
-        if (col < nvec) {
+      for (int j = 0; j < 3; ++j) {
+        const int col = j < 2 ? tid + 256 * j : 512 + tcol;
+        if (j < 2 || has_tail) {
           float4 o = acc[j];
           o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
           if (q.feat) *reinterpret_cast<float4*>(q.feat + (size_t)b * q.ldfeat + col * 4) = o;
@@ -422,10 +456,12 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
           *reinterpret_cast<uint2*>(dst + half) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
         }
       }
-      asm volatile("fence.proxy.async;" ::: "memory");
-      __threadfence();
-      bar_sync_256();
-      if (tid == 0) atomicAdd(q.sync, 1u);   // this batch element's feature blocks are visible device-wide
+      bar_sync_256();   // every thread's stores are ordered before thread 0's device-scope fence (cumulativity)
+      if (tid == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
+        atomicAdd(q.sync, 1u);   // this batch element's feature blocks are visible device-wide
+      }
       trace_mark(p.trace, 5);
     }
   }
@@ -461,6 +497,7 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  trace_mark(p.trace, 12);
   // epilogue operands of this thread's first-pass elements: requested now, consumed after the barrier
   LstmPre1 lpre0, lpre1;
   lpre0.ok = false; lpre1.ok = false;
@@ -471,14 +508,15 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
     if (e0 < e_end) lpre0 = lstm_preload1(p, e0 >> 5, tile * 32 + (e0 & 31));
     if (e1 < e_end) lpre1 = lstm_preload1(p, e1 >> 5, tile * 32 + (e1 & 31));
   }
-  __threadfence();
-  __syncthreads();
+  __syncthreads();   // the CTA's partial stores are ordered before thread 0's device-scope fence below
+  trace_mark(p.trace, 13);
   // split-K barrier of this tile: a monotonic arrival counter (S arrivals per launch, never reset: one atomic per CTA,
   // the release of the last arriver IS its arrival); a launch ends when the count reaches the next multiple of S
   // (64-bit: never wraps)
   unsigned long long* my_sem = reinterpret_cast<unsigned long long*>(q.sem) + tile;
   if (S > 1) {
     if (tid == 0) {
+      __threadfence();
       const unsigned long long old = atomicAdd(my_sem, 1ull);
       const unsigned long long target = (old / (unsigned long long)S + 1ull) * (unsigned long long)S;
       bool ok = false;
@@ -516,12 +554,14 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) g4[gq] += v[k][gq];
         }
+      trace_mark(p.trace, 14);
       const int which = (e - e_beg - tid) / FNT;
       if (which == 0) lstm_update1_pre(p, col, tile * 32 + ul, g4[0], g4[1], g4[2], g4[3], lpre0);
       else if (which == 1) lstm_update1_pre(p, col, tile * 32 + ul, g4[0], g4[1], g4[2], g4[3], lpre1);
       else lstm_update(p, col, tile * 32 + ul, g4[0], g4[1], g4[2], g4[3]);
     }
   }
+  trace_mark(p.trace, 15);
   __syncthreads();
   if (s_fail && tid == 0) atomicExch(q.sync + 2, 1u);   // sticky status word (sfb_debug_status)
   trace_mark(p.trace, 2);
@@ -534,8 +574,8 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
 FusedPlan vis_lstm_fused_plan(int B, int H, int nkb, int R, int D, int lenA, int lenB, int num_sms) {
   FusedPlan pl{};
   pl.ok = false;
-  if (H < 32 || (H % 32) != 0 || B < 1 || B > 128 || D > F_NJ * 256 * 4 || (D % 4) != 0 || R < 1 || R > 256) return pl;
-  if ((lenA % 4) != 0 || (lenB % 4) != 0 || lenA + lenB != D || lenA <= 0) return pl;
+  if (H < 32 || (H % 32) != 0 || B < 1 || B > 128 || D != F_D || R < 1 || R > 256) return pl;
+  if (lenA + lenB != D || !((lenA == 2048 && lenB == 128) || (lenA == D && lenB == 0))) return pl;   // the reference's slab layouts
   pl.tiles = H / 32;
   pl.S = num_sms / pl.tiles;
   if (pl.S > 16) pl.S = 16;
@@ -545,7 +585,7 @@ FusedPlan vis_lstm_fused_plan(int B, int H, int nkb, int R, int D, int lenA, int
   const size_t stage = 2 * (size_t)FA_HALF + 2 * (size_t)(pl.NB / 8) * FSBO;
   const size_t chunk = (size_t)F_RB * lenA * 4;
   const size_t fixed = stage + (size_t)R * lenB * 4 + (2 * FGS + 1 + 2 * F_MAXCH + 2) * sizeof(uint64_t) +
-                       (2 * 8 * F_RB + ((R + 3) & ~3)) * sizeof(float) + 64;
+                       (2 * 8 * 8 + ((R + 3) & ~3)) * sizeof(float) + 96;
   const size_t budget = 227 * 1024 - 2048;                  // static shared + alignment slack
   if (fixed + 2 * chunk > budget) return pl;
   int nch = (int)((budget - fixed) / chunk);

@@ -42,8 +42,11 @@ constexpr int T_MAXKH = 4;                       // K blocks per CTA of a pair (
 constexpr int T_BST = 3;                         // activation stages of a projection CTA
 
 __device__ __forceinline__ bool t_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t i = 0; i < (1u << 26); ++i)
+#pragma unroll 1
+  for (uint32_t i = 0; i < (1u << 24); ++i) {
     if (mbar_try_wait(bar, parity)) return true;
+    __nanosleep(32);   // a hot try_wait loop competes with the compute warps for the shared-memory pipe
+  }
   return false;
 }
 __device__ __forceinline__ uint64_t t_desc(uint32_t smem_addr) {
@@ -571,6 +574,7 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
         }
         if (!t_wait(candfull, 0)) s_fail = 1;
         t_bar256();
+        rmark(8);
         const float cst = gs[E];
         for (int a = warp; a < A; a += 8) {
           const float4* u4 = reinterpret_cast<const float4*>(us + (size_t)a * E);
@@ -585,12 +589,14 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
           if (lane == 0) slog[a] = accd + cst;
         }
         t_bar256();
+        rmark(9);
         if (q.has_tail) {
           if (warp == 0) {
             const int a_t = tail_row(q.tail, b, lane, us, slog, sval, false);
             if (lane == 0) s_at = a_t;
           }
           t_bar256();
+          rmark(10);
           tail_copy_u(q.tail, b, s_at, us, tid, 256);
         } else {
           for (int a = tid; a < A; a += 256) q.logit[(size_t)b * A + a] = slog[a];

@@ -248,6 +248,9 @@ def test_speaker_beam_search_matches_search_oracle():
     """speaker.py:211-318 against the oracle on gold paths of a real graph."""
     env = FakeR2RBatch(n_instr=6, batch_size=6, seed=23, graph="8194nk5LbLH")
     we, wd = synth.speaker_encoder_weights(), synth.speaker_decoder_weights()
+    # random-init word logits are nearly uniform (beam scores would tie within fp32 noise): spread them out
+    wd = dict(wd)
+    wd["decoder2action.weight"] = wd["decoder2action.weight"] * 40.0
     enc = M.SpeakerEncoderLSTM(synth.FEAT, synth.FEAT, synth.HID, 0.5).cuda().eval()
     dec = M.SpeakerDecoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0.5, glove=wd["embedding.weight"].numpy()).cuda().eval()
     enc.load_state_dict(we); dec.load_state_dict(wd)

@@ -72,7 +72,7 @@ for k in range(n):
     print("%2d %-22s entry %8.2f  wait_done %8.2f  exit %8.2f  (dur %6.2f us, after wait %6.2f us)%s" % (
         k, names[k % len(names)], (e - t0) / 1e3, (wt - t0) / 1e3, (x - t0) / 1e3, (x - e) / 1e3, (x - wt) / 1e3,
         ("  merge_exit %.2f" % ((x2 - t0) / 1e3)) if x2 else ""))
-    ph = [buf[16 * k + j] for j in range(4, 12)]
+    ph = [buf[16 * k + j] for j in range(4, 16)]
     if any(ph):
         print("      phases(us since wait): " + "  ".join("%d:%.2f" % (j + 4, (v - wt) / 1e3) for j, v in enumerate(ph) if v))
 # per-CTA timeline of the LAST attention launch of the step (the text attention)
