@@ -584,12 +584,107 @@ def run_gpu(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------- C4 / C5 (BASELINE.json configs[3], [4])
+def _agents(env, dev, beam=1, instruction_len=80):
+    from speaker_follower_b200 import follower as Fo, model as M, ops, speaker as Sp, synth
+    glove = synth.follower_encoder_weights()["embedding.weight"].numpy()
+    enc = M.EncoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0, 0.5, glove=glove).to(dev).eval()
+    dec = M.AttnDecoderLSTM(synth.FEAT, synth.HID, 0.5).to(dev).eval()
+    enc.load_state_dict(synth.follower_encoder_weights()); dec.load_state_dict(synth.follower_decoder_weights())
+    dec.feature_store = ops.FeatureStore(torch.from_numpy(env.table).to(dev), torch.from_numpy(env.loc).to(dev))
+    follower = Fo.Seq2SeqAgent(env, "", enc, dec, episode_len=10, max_instruction_length=80)
+    swd = synth.speaker_decoder_weights()
+    senc = M.SpeakerEncoderLSTM(synth.FEAT, synth.FEAT, synth.HID, 0.5).to(dev).eval()
+    sdec = M.SpeakerDecoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0.5, glove=swd["embedding.weight"].numpy()).to(dev).eval()
+    senc.load_state_dict(synth.speaker_encoder_weights()); sdec.load_state_dict(swd)
+    speaker = Sp.Seq2SeqSpeaker(env, "", senc, sdec, instruction_len=instruction_len, max_episode_len=10)
+    return follower, speaker
+
+
+def run_pragmatic(args, rank, local_rank, world):
+    """--config c4: state-factored search (completion 40, successor 1) over 64 instructions on a navigation-graph
+    environment, speaker rescoring of every candidate (up to 2 560), sharded by instruction over the ranks; one
+    all-gather of the score records + one all-reduce of the statistics; every rank forms the weighted argmax.
+    --config c5: greedy speaker generation over synthetic trajectories, sharded, JSON records gathered in order."""
+    import __graft_entry__ as ge
+    ge.build()
+    from speaker_follower_b200 import dist as sfdist, pragmatic as PR
+    from speaker_follower_b200.navgraph_env import FakeR2RBatch
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    c4 = args.config == "c4"
+    n_inst = 64 if c4 else 256 * max(world, 1) * 2
+    beam = 40 if c4 else 1
+
+    def make_env():
+        return FakeR2RBatch(n_viewpoints=160, n_instr=n_inst, batch_size=64 if c4 else 256, seed=77, max_len=40,
+                            beam_size=max(beam, 1))
+
+    def one_pass(shard):
+        env = make_env()
+        gi = PR.shard_env(env) if shard else list(range(n_inst))
+        follower, speaker = _agents(env, dev, instruction_len=30)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if c4:
+            by_w, cands, records = PR.run_rational_follower(env, follower, speaker, beam_size=beam, global_index=gi)
+            out = {w: {int(k): int(v) for k, v in ch.items()} for w, ch in PR.rational_combine(records).items()}
+            n_cand = int(records.shape[0])
+        else:
+            merged = PR.generate_speaker_instructions(env, speaker, global_index=gi)
+            out, n_cand = merged, len(merged)
+        torch.cuda.synchronize()
+        return out, n_cand, time.perf_counter() - t0
+
+    ref_out = None
+    if world > 1 and rank == 0:      # the single-process answer (untimed), to compare the sharded one against
+        saved = (sfdist.world,)
+        sfdist.world = lambda: (0, 1)
+        try:
+            ref_out, _, _ = one_pass(False)
+        finally:
+            sfdist.world = saved[0]
+    if dist is not None:
+        dist.barrier()
+    one_pass(True)                   # warm-up (kernel attributes, allocator)
+    if dist is not None:
+        dist.barrier()
+    out, n_cand, dt = one_pass(True)
+    t = torch.tensor([dt], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    if rank == 0:
+        same = None if ref_out is None else (ref_out == out)
+        line = {"metric": "pragmatic-inference instructions/sec" if c4 else "speaker-generated trajectories/sec",
+                "value": n_inst / dt, "unit": "instr/s" if c4 else "traj/s", "n_gpus": world, "steps": 1, "warmup": 1,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": ("C4: state-factored search, completion 40, successor 1, 64 instructions, %d candidates "
+                                        "rescored by the speaker" % n_cand) if c4 else
+                                       ("C5: greedy speaker generation over %d synthetic trajectories, batch 256 per GPU" % n_inst),
+                           "env": "navigation-graph stand-in (160 viewpoints), random-init weights",
+                           "parallelism": "instances strided over %d ranks; collectives: all_gather(score records) + "
+                                          "all_reduce(n, sum, sum^2)" % world if c4 else
+                                          "instances strided over %d ranks; collectives: all_gather(JSON bytes)" % world},
+                "identical_to_single_process": same}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="decode", choices=["decode", "c2", "c4", "c5"],
+                    help="decode (default): the headline decode-steps/sec; c2: training step; c4: pragmatic inference; c5: data augmentation")
     ap.add_argument("--profile-steps", type=int, default=0,
                     help="run this many eager (no CUDA graph) steps after warm-up and exit: the command ncu wraps")
     args = ap.parse_args()
@@ -598,6 +693,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.config in ("c4", "c5"):
+        run_pragmatic(args, rank, local_rank, world)
     else:
         run_gpu(args, rank, local_rank, world)
 

@@ -270,3 +270,45 @@ def test_speaker_beam_search_matches_search_oracle():
             assert [int(x) for x in a["word_indices"]] == [int(x) for x in b["word_indices"]]
             assert abs(float(a["score"]) - float(b["score"])) < 1e-3
     assert checked >= 3
+
+
+# ------------------------------------------------------------------ pragmatic inference / data augmentation (C4 / C5)
+def make_speaker(env, instruction_len=10):
+    we, wd = synth.speaker_encoder_weights(), synth.speaker_decoder_weights()
+    enc = M.SpeakerEncoderLSTM(synth.FEAT, synth.FEAT, synth.HID, 0.5).cuda().eval()
+    dec = M.SpeakerDecoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0.5, glove=wd["embedding.weight"].numpy()).cuda().eval()
+    enc.load_state_dict(we); dec.load_state_dict(wd)
+    return Sp.Seq2SeqSpeaker(env, "", enc, dec, instruction_len=instruction_len, max_episode_len=6), we, wd
+
+
+def test_rational_follower_pipeline_and_combine():
+    """rational_follower.py:11-150 on a real graph: state-factored candidates, speaker rescoring of every candidate,
+    product combine == oracle combine on the same records, weight 0 picks the follower's own best candidate."""
+    from speaker_follower_b200 import pragmatic as PR
+    env = FakeR2RBatch(n_instr=6, batch_size=3, seed=31, graph="pLe4wQe7qrG", beam_size=4)
+    agent, _, _ = make_follower(env)
+    spk, _, _ = make_speaker(env)
+    by_w, cands, records = PR.run_rational_follower(env, agent, spk, beam_size=4)
+    assert len(cands) == 6 and records.shape[1] == 4 and records.shape[0] == sum(len(c) for c in cands.values())
+    groups = [int(g) for g in records[:, 0]]
+    for w in (0.0, 0.95):
+        best = O.rational_combine(records[:, 3], records[:, 2], groups, w)
+        order = list(cands.keys())
+        for k, iid in enumerate(order):
+            chosen = by_w[w]["results"][iid]
+            assert chosen is cands[iid][int(records[best[k], 1])]
+    for iid, c in cands.items():                       # weight 0 = follower score alone
+        assert by_w[0.0]["results"][iid] is max(c, key=lambda x: x["follower_score"])
+        assert all("speaker_score" in x and "observations" not in x for x in c)
+
+
+def test_speaker_generation_records_in_trajectory_order(tmp_path):
+    """data_augmentation_from_speaker.py:66 (literal speaker): one record per trajectory, in env order, JSON written."""
+    from speaker_follower_b200 import pragmatic as PR
+    env = FakeR2RBatch(n_instr=7, batch_size=3, seed=32, graph="8194nk5LbLH")
+    spk, _, _ = make_speaker(env, instruction_len=8)
+    out = PR.generate_speaker_instructions(env, spk, path=str(tmp_path / "aug.json"))
+    assert [r["instr_id"] for r in out] == [it["instr_id"] for it in env.data]
+    assert all(1 <= len(r["word_indices"]) <= 8 for r in out)
+    import json
+    assert json.load(open(tmp_path / "aug.json")) == out

@@ -10,6 +10,7 @@ import torch.multiprocessing as mp
 
 from oracle import r2r_oracle as O
 from speaker_follower_b200 import dist as D
+from speaker_follower_b200 import pragmatic as PR
 
 
 def _free_port():
@@ -35,7 +36,9 @@ def _worker(rank, world, port, q):
         traj = [(i, {"path_id": i, "instr_id": "%d_0" % i, "words": ["w%d" % ((i * 7 + k) % 11) for k in range(3 + i % 4)],
                      "score": float(spk[i % n_instr, 0])}) for i in D.shard_indices(11, rank, world)]
         shards = D.gather_json_shards(traj)
-        q.put((rank, allr.numpy(), s_std, f_std, rate, ms, spk, fol, shards))
+        # the PRODUCT combine (speaker_follower_b200/pragmatic.py) on the gathered records + reduced statistics
+        choice = PR.rational_combine(allr.numpy(), (0.0, 0.95), stds=(f_std, s_std))
+        q.put((rank, allr.numpy(), s_std, f_std, rate, ms, spk, fol, shards, choice))
     finally:
         dist.destroy_process_group()
 
@@ -52,7 +55,8 @@ def test_two_rank_sharded_combine_equals_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     outs.sort(key=lambda o: o[0])
-    _, allr0, s_std, f_std, rate, ms, spk, fol, shards0 = outs[0]
+    _, allr0, s_std, f_std, rate, ms, spk, fol, shards0, choice0 = outs[0]
+    assert choice0 == outs[1][9]                                   # every rank forms the same decision
     # JSON shard gather (data_augmentation_from_speaker.py:52-82 sharded): both ranks hold all 11 records in index order
     assert shards0 == outs[1][8] and [r["path_id"] for r in shards0] == list(range(11))
     assert all(r["words"] == ["w%d" % ((r["path_id"] * 7 + k) % 11) for k in range(3 + r["path_id"] % 4)] for r in shards0)
@@ -67,6 +71,8 @@ def test_two_rank_sharded_combine_equals_single_process():
     comb = 0.95 * spk / np.std(spk) + 0.05 * fol / np.std(fol)
     for i in range(7):
         assert int(allr0[best[i], 1]) == int(np.argmax(comb[i]))
+        assert choice0[0.95][i] == int(np.argmax(comb[i]))         # product combine == oracle combine == numpy
+        assert choice0[0.0][i] == int(np.argmax(fol[i]))
 
 
 def test_shard_indices_cover_and_balance():
