@@ -11,9 +11,9 @@ from test_gpu_parity import close, cu
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("N,T", [(1, 3), (37, 10), (256, 6), (300, 4)])
+@pytest.mark.parametrize("N,T", [(1, 3), (37, 10), (256, 6), (300, 4), (2560, 7)])
 def test_speaker_decoder_packed_vs_oracle(N, T):
-    """C3 shape (N=256 paths, T=6 path steps, vocabulary 991) and ragged neighbours."""
+    """C3 shape (N=256 paths, T=6 path steps, vocabulary 991), ragged neighbours, and the C4 rescoring size (N=2560)."""
     g = torch.Generator().manual_seed(9 + N)
     H = synth.HID
     wd = synth.speaker_decoder_weights()
@@ -44,7 +44,7 @@ def test_speaker_decoder_packed_vs_oracle(N, T):
         close(a, b, what="train:" + k)
 
 
-@pytest.mark.parametrize("N", [1, 64, 256])
+@pytest.mark.parametrize("N", [1, 64, 256, 2560])
 def test_speaker_encoder_step_packed_vs_oracle(N):
     we = synth.speaker_encoder_weights()
     wc = cu(we)
