@@ -243,6 +243,30 @@ int32_t sfb_follower_project_ctx(const sfb_dims* dims, const void* packed, size_
                                  float* ctx_k, float* ctx_o,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Table-driven navigation environment: R2RBatch.step + R2RBatch.observe (env.py:628-641, 763-804)
+ * as look-ups.  A world state is discretised to (viewpoint, heading bin[, elevation bin]) = one of S ids; for every id
+ * the tables hold what `observe` would return for it: the feature-table row and view index of the slab, the candidate
+ * list (view index of each navigable direction, sin/cos of its relative heading / elevation — env.py:60-75 —, how many
+ * are valid), the successor state of every candidate, and optionally the teacher action per goal (env.py:742-761).
+ * sfb_nav_step: rows that have not ended first move along a_prev (a_prev = NULL on the first call; a_prev[b] = 0 ends
+ * the row AFTER it is logged, follower.py:531-533; the action is recorded in actions_log, -1 for ended rows), then the
+ * step inputs of every row are written: vp_idx, view_idx, cand_view [B,A], cand_trig [B,A,4], is_valid [B,A] and the
+ * teacher target [B] (-1 for ended rows or without a teach table).  One tiny launch, no host involvement. */
+typedef struct sfb_nav_tables {
+  const int32_t* vp;      /* [S] feature-table row */
+  const int32_t* view;    /* [S] view index 0..35 */
+  const int32_t* nvalid;  /* [S] number of candidates (incl. stop) */
+  const int32_t* cv;      /* [S,A] candidate view index, -1 = stop / padding */
+  const float*   trig;    /* [S,A,4] */
+  const int32_t* next;    /* [S,A] successor state id */
+  const int32_t* teach;   /* [S,G] teacher action or NULL */
+  int32_t        S, A, G;
+} sfb_nav_tables;
+int32_t sfb_nav_step(const sfb_nav_tables* t, int32_t B, int32_t* state, int32_t* ended, const int32_t* goal,
+                     const int32_t* a_prev, int32_t* actions_log,
+                     int32_t* vp_idx, int32_t* view_idx, int32_t* cand_view, float* cand_trig, float* is_valid,
+                     int32_t* target, void* stream);
+
 /* Per-step tail of Seq2SeqAgent._rollout_with_loss — follower.py:476-505.
  *   logit [B,A] is masked IN PLACE with -inf where is_valid == 0 (477);
  *   feedback: 0 = teacher (a_t = max(target,0)), 1 = argmax, 2 = sample (inverse CDF of

@@ -63,6 +63,11 @@ class EncoderWeights(C.Structure):
                 ("b_ih", c_float_p * 2), ("b_hh", c_float_p * 2), ("e2d_w", c_float_p), ("e2d_b", c_float_p)]
 
 
+class NavTables(C.Structure):
+    _fields_ = [("vp", c_int_p), ("view", c_int_p), ("nvalid", c_int_p), ("cv", c_int_p), ("trig", c_float_p),
+                ("next", c_int_p), ("teach", c_int_p), ("S", C.c_int32), ("A", C.c_int32), ("G", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/sf_b200.h declares
 SIGNATURES = {
     "sfb_abi_version": (C.c_int32, []),
@@ -102,6 +107,8 @@ SIGNATURES = {
                                                  c_float_p, c_float_p,
                                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_follower_carry_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32]),
+    "sfb_nav_step": (C.c_int32, [C.POINTER(NavTables), C.c_int32, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p,
+                                 c_int_p, c_int_p, c_int_p, c_float_p, c_float_p, c_int_p, C.c_void_p]),
     "sfb_eltwise_prod_scoring_fwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(ScoringWeights), C.c_int32, C.c_int32,
                                                  c_float_p, c_float_p, c_float_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_follower_project_ctx_workspace_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32, C.c_int32]),

@@ -556,6 +556,19 @@ int32_t sfb_follower_step_tail(int32_t B, int32_t A, int32_t E, float* logit, co
   return launch_follower_tail(p, static_cast<cudaStream_t>(stream));
 }
 
+int32_t sfb_nav_step(const sfb_nav_tables* t, int32_t B, int32_t* state, int32_t* ended, const int32_t* goal,
+                     const int32_t* a_prev, int32_t* actions_log, int32_t* vp_idx, int32_t* view_idx, int32_t* cand_view,
+                     float* cand_trig, float* is_valid, int32_t* target, void* stream) {
+  reset_launch_count();
+  SFB_CHECK_ARG(t && t->vp && t->view && t->nvalid && t->cv && t->trig && t->next && t->A >= 1 && t->S >= 1, "nav tables missing");
+  SFB_CHECK_ARG(B >= 1 && state && ended && vp_idx && view_idx && cand_view && cand_trig && is_valid, "NULL argument");
+  SFB_CHECK_ARG(!target || !t->teach || goal, "teacher targets need the goal of every row");
+  SFB_CHECK_ARG((reinterpret_cast<uintptr_t>(t->trig) & 15u) == 0 && (reinterpret_cast<uintptr_t>(cand_trig) & 15u) == 0, "trig tables must be 16-byte aligned");
+  NavStepParams p{t->vp, t->view, t->nvalid, t->cv, t->trig, t->next, t->teach, goal, B, t->A, t->G, state, ended, a_prev, actions_log,
+                  vp_idx, view_idx, cand_view, cand_trig, is_valid, target};
+  return launch_nav_step(p, static_cast<cudaStream_t>(stream));
+}
+
 size_t sfb_encoder_lstm_workspace_bytes(int32_t ndir, int32_t Hd, int32_t Ew, int32_t B, int32_t maxlen) {
   if (ndir < 1 || ndir > 2 || Hd < 1 || Ew < 1 || B < 1 || maxlen < 1) return 0;
   return carve_encoder(ndir, Hd, Ew, B, maxlen, nullptr).bytes;

@@ -259,6 +259,18 @@ int32_t launch_action_scoring(const ScoringParams& p, cudaStream_t stream);
 
 int32_t launch_follower_tail(const TailParams& p, cudaStream_t stream);
 
+// table-driven navigation environment: S discretised world states, A candidate slots per state, G goals
+struct NavStepParams {
+  const int32_t* vp; const int32_t* view; const int32_t* nvalid;   // [S]
+  const int32_t* cv; const float* trig; const int32_t* next;       // [S,A], [S,A,4], [S,A]
+  const int32_t* teach; const int32_t* goal;                       // [S,G] or NULL, [B]
+  int B, A, G;
+  int32_t* state; int32_t* ended;                                  // [B] in/out
+  const int32_t* a_prev; int32_t* actions_log;                     // [B] or NULL
+  int32_t* vp_idx; int32_t* view_idx; int32_t* cand_view; float* cand_trig; float* is_valid; int32_t* target;
+};
+int32_t launch_nav_step(const NavStepParams& p, cudaStream_t stream);
+
 int device_num_sms();
 unsigned long long* next_trace_slot();
 unsigned long long* cta_trace_buffer();  // NULL unless sfb_set_option("cta_trace", 1)

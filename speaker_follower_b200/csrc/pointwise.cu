@@ -114,6 +114,45 @@ int32_t launch_action_scoring(const ScoringParams& p_in, cudaStream_t stream) {
   return 0;
 }
 
+// ---------------------------------------------------------------- table-driven navigation environment
+// One thread per batch row: apply the previous action to the row's discretised world state (viewpoint, heading bin)
+// through the precomputed transition table, then emit everything the next decode step needs from the observation
+// tables — what R2RBatch.step + R2RBatch.observe (env.py:628-641, 763-804) produce per row, as pure table look-ups.
+__global__ void nav_step_kernel(const NavStepParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  int s = p.state[b];
+  int ended = p.ended[b];
+  if (p.a_prev) {
+    const int a = p.a_prev[b];
+    if (p.actions_log) p.actions_log[b] = ended ? -1 : a;
+    if (!ended) {
+      if (a > 0 && a < p.A) s = p.next[(size_t)s * p.A + a];
+      if (a == 0) ended = 1;        // follower.py:531-533: the row ends after its stop action has been recorded
+    }
+    p.state[b] = s;
+    p.ended[b] = ended;
+  }
+  p.vp_idx[b] = p.vp[s];
+  p.view_idx[b] = p.view[s];
+  const int nv = p.nvalid[s];
+  for (int a = 0; a < p.A; ++a) {
+    p.cand_view[(size_t)b * p.A + a] = p.cv[(size_t)s * p.A + a];
+    p.is_valid[(size_t)b * p.A + a] = a < nv ? 1.f : 0.f;
+    const float4 t = reinterpret_cast<const float4*>(p.trig)[(size_t)s * p.A + a];
+    reinterpret_cast<float4*>(p.cand_trig)[(size_t)b * p.A + a] = t;
+  }
+  if (p.target) p.target[b] = (ended || !p.teach) ? -1 : p.teach[(size_t)s * p.G + p.goal[b]];
+}
+
+int32_t launch_nav_step(const NavStepParams& p, cudaStream_t stream) {
+  SFB_CHECK_CUDA(launch_ex(nav_step_kernel, dim3((p.B + 127) / 128, 1, 1), dim3(128, 1, 1), 0, stream, dim3(1, 1, 1), p));
+  count_launch();
+  return 0;
+}
+
 // ---------------------------------------------------------------- follower rollout tail (one warp per row)
 __global__ void __launch_bounds__(128) follower_tail_kernel(const TailParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -238,10 +238,187 @@ class Seq2SeqAgent(BaseAgent):
         beams, _, _ = self.beam_search(self.beam_size)
         return [beam[0] for beam in beams]
 
+    # ---------------------------------------------------------------- device-resident greedy rollout
+    def _staged_rollout(self, world_states, obs):
+        """follower.py:430-539 for inference (no autograd) when the slabs live in the decoder's device feature store:
+        per step the host ships ONE pinned staging buffer (viewpoint row, view index, candidate view indices, 4 trig
+        values per candidate, validity, teacher target: ~20 KB at B=100 instead of the 38 MB the reference copies,
+        follower.py:291-320), the step runs as two launches on the carried state, and the only thing read back is a_t,
+        written by the last kernel straight into page-locked host memory.  Scores stay on the device until the end."""
+        dev = _device(self.decoder)
+        B = len(obs)
+        feedback = self.feedback
+        seq, seq_mask, seq_lengths = self._proc_batch(obs)
+        ctx, h_t, c_t = self.encoder(seq, seq_lengths)
+        ctx_proj = self.decoder.project_ctx(ctx)
+        E = self.decoder.embedding_size
+        A_cap = 16
+        ni = 2 * B + B * A_cap + B                     # int32: vp, view, cand_view, target
+        nf = 5 * B * A_cap + B                         # f32: trig [B,A,4], valid [B,A], sample_u [B]
+        host = torch.empty(ni + nf, dtype=torch.int32).pin_memory()
+        hi, hf = host[:ni].numpy(), host[ni:].view(torch.float32).numpy()
+        stage = torch.empty(ni + nf, dtype=torch.int32, device=dev)
+        di, df = stage[:ni], stage[ni:].view(torch.float32)
+        a_host = torch.full((B,), -1, dtype=torch.int32).pin_memory()
+        a_np = a_host.numpy()
+        carry = [self.decoder.new_carry(B, dev), self.decoder.new_carry(B, dev)]
+        hb = [h_t.contiguous(), torch.empty_like(h_t)]
+        cb = [c_t.contiguous(), torch.empty_like(c_t)]
+        ub = [self.decoder.u_begin.expand(B, -1).contiguous(), torch.empty(B, E, device=dev)]
+        L = ctx.shape[1]
+        ws = ops.follower_workspace({k: v for k, v in self.decoder.named_parameters()}, B, L, A_cap, dev)
+        alpha = torch.empty(B, L, device=dev)
+        alpha_v = torch.empty(B, self.decoder.feature_store.feat_table.shape[1], device=dev)
+        step_scores, step_ce, n_keeps = [], [], []
+        traj = [{"instr_id": ob["instr_id"], "trajectory": [path_element_from_observation(ob)], "actions": [],
+                 "scores": [], "observations": [ob], "instr_encoding": ob["instr_encoding"]} for ob in obs]
+        ended = np.zeros(B, dtype=bool)
+        end_step = np.full(B, -1)
+        stream = torch.cuda.current_stream(dev)
+        for t in range(self.episode_len):
+            A = max(len(ob["adj_loc_list"]) for ob in obs)
+            if A > A_cap:
+                raise RuntimeError("more than %d action candidates" % A_cap)
+            cv = hi[2 * B:2 * B + B * A].reshape(B, A)
+            tg = hi[2 * B + B * A_cap:]
+            trig = hf[:4 * B * A].reshape(B, A, 4)
+            valid = hf[4 * B * A_cap:4 * B * A_cap + B * A].reshape(B, A)
+            cv.fill(-1); trig.fill(0.0); valid.fill(0.0)
+            for i, ob in enumerate(obs):
+                hi[i] = ob["vp_index"]; hi[B + i] = ob["viewIndex"]
+                tg[i] = -1 if ended[i] else int(ob.get("teacher", 0))
+                adj = ob["adj_loc_list"]
+                valid[i, :len(adj)] = 1.0
+                for a in range(1, len(adj)):                       # env.py:60-75: row 0 (stop) stays zero
+                    d = adj[a]
+                    cv[i, a] = d["absViewIndex"]
+                    rh, re = d["rel_heading"], d["rel_elevation"]
+                    trig[i, a, 0] = np.sin(rh); trig[i, a, 1] = np.cos(rh); trig[i, a, 2] = np.sin(re); trig[i, a, 3] = np.cos(re)
+            if feedback == "sample":
+                hf[5 * B * A_cap:] = self._sample_uniform(B, dev).cpu().numpy()
+            a_np.fill(-1)
+            stage.copy_(host, non_blocking=True)                   # the one H2D of the step
+            p = t % 2
+            d_cv = di[2 * B:2 * B + B * A].view(B, A)
+            d_trig = df[:4 * B * A].view(B, A, 4)
+            d_valid = df[4 * B * A_cap:4 * B * A_cap + B * A].view(B, A)
+            logit = torch.empty(B, A, device=dev)
+            score = torch.empty(B, device=dev)
+            ce = torch.empty(B, device=dev)
+            tail = {"is_valid": d_valid, "feedback": feedback, "target": di[2 * B + B * A_cap:],
+                    "sample_u": df[5 * B * A_cap:] if feedback == "sample" else None, "out": (a_host, ub[p ^ 1], score, ce)}
+            self.decoder.decode_step(ub[p], None, (di[:B], di[B:2 * B]), hb[p], cb[p], ctx, seq_mask, tail=tail,
+                                     carry_in=None if t == 0 else carry[p], carry_out=carry[p ^ 1], ctx_proj=ctx_proj,
+                                     cand_view=d_cv, cand_trig=d_trig, out=(hb[p ^ 1], cb[p ^ 1], alpha, logit, alpha_v),
+                                     workspace=ws)
+            step_scores.append(score); step_ce.append(ce)
+            n_keeps.append(int((~ended).sum()))
+            stream.synchronize()                                   # a_t is in host memory: the simulator can move
+            env_action = a_np.tolist()
+            world_states = self.env.step(world_states, env_action, obs)
+            obs = self.env.observe(world_states)
+            for i, ob in enumerate(obs):                           # follower.py:518-530
+                if not ended[i]:
+                    traj[i]["trajectory"].append(path_element_from_observation(ob))
+                    traj[i]["actions"].append(env_action[i])
+                    traj[i]["observations"].append(ob)
+                    end_step[i] = t
+                if env_action[i] == 0:
+                    ended[i] = True
+            if ended.all():
+                break
+        sc = torch.stack(step_scores, 1).cpu().numpy()             # [B, T]: one read-back for the whole rollout
+        cum = np.cumsum(sc.astype(np.float32), axis=1, dtype=np.float32)
+        for i in range(B):
+            e = int(end_step[i])
+            traj[i]["scores"] = [float(x) for x in sc[i, :e + 1]]
+            traj[i]["score"] = float(cum[i, e]) if e >= 0 else 0.0
+        ces = torch.stack(step_ce, 1)
+        loss = torch.zeros((), device=dev)
+        for t, n in enumerate(n_keeps):
+            loss = loss + (ces[:, t].sum() / n if n > 0 else ces[:, t].sum() * float("nan"))
+        self.loss = loss
+        self.losses.append(float(loss))
+        return traj
+
+    def device_rollout(self, nav, start_states, goals, instr_encodings, feedback="argmax", cuda_graph=False):
+        """The whole rollout (follower.py:430-539, inference) on the device: the environment is a DeviceNavTables
+        (SURVEY.md §8 f-2), so a step is [sfb_nav_step -> fused gather + LSTM -> fused text side + tail] with NO host
+        round trip; actions and scores come back once, at the end.  ``start_states`` / ``goals``: int lists (state ids,
+        goal viewpoints); ``instr_encodings``: token lists, already sorted by length like env.reset(sort=True) does.
+        cuda_graph=True captures the episode's steps into one CUDA graph (returned for replay with new start states
+        written into the returned buffers).  Returns dict(actions [B,T] int32 (-1 after the end), scores [B,T], loss)."""
+        dev = _device(self.decoder)
+        B, T, A = len(start_states), self.episode_len, nav.A
+        seq, seq_mask, seq_lengths = batch_instructions_from_encoded(instr_encodings, self.max_instruction_length,
+                                                                     reverse=self.reverse_instruction, device=dev)
+        sd = {k: v for k, v in self.decoder.named_parameters()}
+        E = self.decoder.embedding_size
+        buf = {"state": torch.tensor(start_states, dtype=torch.int32, device=dev), "state0": None,
+               "ended": torch.zeros(B, dtype=torch.int32, device=dev),
+               "goal": torch.tensor(goals, dtype=torch.int32, device=dev),
+               "vp_idx": torch.empty(B, dtype=torch.int32, device=dev), "view_idx": torch.empty(B, dtype=torch.int32, device=dev),
+               "cand_view": torch.empty(B, A, dtype=torch.int32, device=dev), "cand_trig": torch.empty(B, A, 4, device=dev),
+               "is_valid": torch.empty(B, A, device=dev), "target": torch.empty(B, dtype=torch.int32, device=dev),
+               "a_t": torch.zeros(B, dtype=torch.int32, device=dev), "actions": torch.full((T, B), -1, dtype=torch.int32, device=dev),
+               "scores": torch.zeros(T, B, device=dev), "ce": torch.zeros(T, B, device=dev)}
+        buf["state0"] = buf["state"].clone()
+        with torch.no_grad():
+            ctx, h0, c0 = self.encoder(seq, seq_lengths)
+            ctx_proj = self.decoder.project_ctx(ctx)
+            L = ctx.shape[1]
+            ws = ops.follower_workspace(sd, B, L, A, dev)
+            carry = [self.decoder.new_carry(B, dev), self.decoder.new_carry(B, dev)]
+            hb, cb = [h0.contiguous(), torch.empty_like(h0)], [c0.contiguous(), torch.empty_like(c0)]
+            ub = [self.decoder.u_begin.expand(B, -1).contiguous(), torch.empty(B, E, device=dev)]
+            h_init, c_init = hb[0].clone(), cb[0].clone()
+            alpha = torch.empty(B, L, device=dev)
+            alpha_v = torch.empty(B, self.decoder.feature_store.feat_table.shape[1], device=dev)
+            logit = torch.empty(B, A, device=dev)
+
+            def episode():
+                buf["state"].copy_(buf["state0"]); buf["ended"].zero_()
+                hb[0].copy_(h_init); cb[0].copy_(c_init); ub[0].zero_()
+                for t in range(T):
+                    ops.nav_step(nav, buf["state"], buf["ended"], buf["goal"], buf["a_t"] if t > 0 else None,
+                                 buf["actions"][t - 1] if t > 0 else None, buf)
+                    p = t % 2
+                    tail = {"is_valid": buf["is_valid"], "feedback": feedback, "target": buf["target"],
+                            "out": (buf["a_t"], ub[p ^ 1], buf["scores"][t], buf["ce"][t])}
+                    self.decoder.decode_step(ub[p], None, (buf["vp_idx"], buf["view_idx"]), hb[p], cb[p], ctx, seq_mask, tail=tail,
+                                             carry_in=None if t == 0 else carry[p], carry_out=carry[p ^ 1], ctx_proj=ctx_proj,
+                                             cand_view=buf["cand_view"], cand_trig=buf["cand_trig"],
+                                             out=(hb[p ^ 1], cb[p ^ 1], alpha, logit, alpha_v), workspace=ws)
+                ops.nav_step(nav, buf["state"], buf["ended"], buf["goal"], buf["a_t"], buf["actions"][T - 1], buf)
+
+            graph = None
+            if cuda_graph:
+                side = torch.cuda.Stream(device=dev)
+                with torch.cuda.stream(side):
+                    episode()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    episode()
+                graph.replay()
+            else:
+                episode()
+        live = buf["actions"] >= 0
+        return {"actions": buf["actions"].t(), "scores": torch.where(live, buf["scores"], torch.zeros_like(buf["scores"])).t(),
+                "ce": buf["ce"].t(), "graph": graph, "buffers": buf, "final_state": buf["state"]}
+
+    def _can_stage(self, obs):
+        return (not torch.is_grad_enabled() and getattr(self.decoder, "supports_fused_step", False)
+                and getattr(self.decoder, "feature_store", None) is not None and not self.decoder.training
+                and all("vp_index" in ob for ob in obs))
+
     def _rollout_with_loss(self):
         """follower.py:430-539."""
         world_states = self.env.reset(sort=True)
         obs = self.env.observe(world_states)
+        if self._can_stage(obs):
+            return self._staged_rollout(world_states, obs)
         batch_size = len(obs)
         seq, seq_mask, seq_lengths = self._proc_batch(obs)
         dev = _device(self.decoder)

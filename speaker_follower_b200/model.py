@@ -204,7 +204,7 @@ class AttnDecoderLSTM(_PackedWeights, nn.Module):
         return ops.follower_project_ctx(sd, packed, ctx.contiguous()) if packed is not None else None
 
     def decode_step(self, u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask=None, tail=None, carry_in=None,
-                    carry_out=None, ctx_proj=None):
+                    carry_out=None, ctx_proj=None, cand_view=None, cand_trig=None, out=None, workspace=None):
         """forward() plus the fast-path extras of the packed C ABI (include/sf_b200.h): ``tail`` fuses the rollout
         tail (follower.py:476-505) behind the logits, ``carry_in``/``carry_out`` (``new_carry()`` buffers) hand the next step's visual query and packed gate
         operand across steps,
@@ -215,7 +215,7 @@ class AttnDecoderLSTM(_PackedWeights, nn.Module):
         drop_h = self._drop.mask(self.training, (B, self.hidden_size), dev)
         u_t_prev = u_t_prev.contiguous()        # u_begin.expand(B, -1) is a stride-0 view (follower.py:462)
         sd = _sd(self)
-        if torch.is_grad_enabled() and any(t.requires_grad for t in (u_t_prev, all_u_t, h_0, c_0, ctx, *sd.values())):
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (u_t_prev, all_u_t, h_0, c_0, ctx, *sd.values())):
             return self._decode_step_autograd(sd, u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask, drop_x, drop_h)
         packed = self._packer.get(sd)           # None for dimensions the packed path does not cover
         extra = {}
@@ -225,7 +225,9 @@ class AttnDecoderLSTM(_PackedWeights, nn.Module):
             raise NotImplementedError("fused tail / carried query need the packed path (H % 128 == 0)")
         if isinstance(visual_context, (tuple, list)):
             vp, view = visual_context
-            return ops.follower_step(sd, u_t_prev, all_u_t.contiguous(), None, h_0.contiguous(),
+            if all_u_t is None:   # action candidates gathered on the device too (env.py:60-75): view index + 4 trig values
+                extra.update(cand_view=cand_view, cand_trig=cand_trig, out=out, workspace=workspace)
+            return ops.follower_step(sd, u_t_prev, None if all_u_t is None else all_u_t.contiguous(), None, h_0.contiguous(),
                                      c_0.contiguous(), ctx.contiguous(), ctx_mask, drop_x, drop_h,
                                      store=self.feature_store, vp_idx=vp, view_idx=view, **extra)
         return ops.follower_step(sd, u_t_prev, all_u_t.contiguous(), visual_context.contiguous(),

@@ -35,13 +35,16 @@ class FakeImageFeatures:
 
 class FakeR2RBatch:
     def __init__(self, n_viewpoints=24, n_instr=16, batch_size=8, seed=0, max_len=20, vocab=synth.VOCAB, beam_size=1,
-                 img_dim=synth.IMG_DIM, graph=None):
+                 img_dim=synth.IMG_DIM, graph=None, with_features=True):
         """graph: None = random ring + chords; a scan id from tests/golden/nav_graphs.npz (written from the reference's
         connectivity/*.json by tests/golden/make_nav_graphs.py) = that REAL R2R navigation graph, edge headings and
         elevations derived from the viewpoint positions (heading 0 = +y, clockwise, like the simulator)."""
         g = np.random.Generator(np.random.PCG64(seed))
         self.g = g
         self.batch_size, self.beam_size = batch_size, beam_size
+        # with_features=False: observations carry indices only (vp_index, viewIndex, adj_loc_list) — the configuration
+        # in which the slabs live in a device feature store and nothing of size 36 x 2176 is touched on the host
+        self.with_features = with_features
         real = None
         if graph is not None:
             import os
@@ -129,7 +132,7 @@ class FakeR2RBatch:
     def _observe_one(self, ws, item, include_teacher=True):
         v = ws.viewpointId
         view = self._view_index(ws.heading, ws.elevation)
-        feat = np.concatenate((self.table[v], self.loc[view]), axis=1).astype(np.float32)
+        feat = np.concatenate((self.table[v], self.loc[view]), axis=1).astype(np.float32) if self.with_features else None
         adj = [{"absViewIndex": -1, "nextViewpointId": v, "rel_heading": 0.0, "rel_elevation": 0.0, "distance": 0.0}]
         others = []
         for w, (head, elev) in self.adj[v].items():
@@ -137,10 +140,10 @@ class FakeR2RBatch:
             others.append({"absViewIndex": 12 + int(round(head / (math.pi / 6))) % 12, "nextViewpointId": w,
                            "rel_heading": rel, "rel_elevation": elev - ws.elevation, "distance": 1.0, "abs_heading": head})
         adj += sorted(others, key=lambda a: abs(a["rel_heading"]))                                # env.py:218-222
-        emb = np.zeros((len(adj), feat.shape[1]), np.float32)                                     # env.py:60-75
+        emb = np.zeros((len(adj), self.table.shape[2] + self.loc.shape[2]), np.float32) if self.with_features else None   # env.py:60-75
         img = self.table.shape[2]
         for a, d in enumerate(adj):
-            if a == 0:
+            if a == 0 or emb is None:
                 continue
             emb[a, :img] = self.table[v, d["absViewIndex"]]
             emb[a, img:img + 32] = math.sin(d["rel_heading"]); emb[a, img + 32:img + 64] = math.cos(d["rel_heading"])
@@ -202,3 +205,59 @@ class FakeR2RBatch:
         for i in range(len(ws)):
             path_obs[i].append(final[i])          # len(obs) == len(actions) + 1 (speaker.py:98)
         return path_obs, path_actions, [it["instr_encoding"] for it in self.batch]
+
+
+class DeviceNavTables:
+    """the environment as device-resident look-up tables.  ``observe`` is a pure function of the
+    discretised world state (viewpoint, heading bin; env.py:763-804 + MatterSim's 30-degree discretisation) and ``step``
+    a pure function of (state, action) (env.py:628-641), so both are tabulated once per environment: per state the
+    feature-table row + view index of the slab, the candidate list (view index, sin/cos of relative heading /
+    elevation, count), the successor of every candidate and the teacher action per goal.  A rollout then needs no host
+    round trip at all: ``sfb_nav_step`` advances the states with the actions the decode step left on the device and
+    writes the next step's inputs."""
+    HEADINGS = 12
+
+    def __init__(self, env: FakeR2RBatch, device, a_cap: int = 16, with_teacher: bool = True):
+        import torch
+        nvp = len(env.adj)
+        S = nvp * self.HEADINGS
+        dummy = {"instr_id": "", "instr_encoding": np.zeros(1, np.int64), "goal": 0}
+        vp = np.zeros(S, np.int32); view = np.zeros(S, np.int32); nvalid = np.zeros(S, np.int32)
+        cv = np.full((S, a_cap), -1, np.int32); trig = np.zeros((S, a_cap, 4), np.float32)
+        nxt = np.zeros((S, a_cap), np.int32)
+        teach = np.zeros((S, nvp), np.int32) if with_teacher else None
+        keep = env.with_features
+        env.with_features = False
+        try:
+            for v in range(nvp):
+                for hb in range(self.HEADINGS):
+                    s = v * self.HEADINGS + hb
+                    ob = env._observe_one(WorldState("fake", v, hb * math.pi / 6, 0.0), dummy, include_teacher=False)
+                    adj = ob["adj_loc_list"]
+                    if len(adj) > a_cap:
+                        raise ValueError("state with %d candidates > a_cap" % len(adj))
+                    vp[s], view[s], nvalid[s] = v, ob["viewIndex"], len(adj)
+                    nxt[s, :] = s
+                    for a, d in enumerate(adj):
+                        if a == 0:
+                            continue
+                        cv[s, a] = d["absViewIndex"]
+                        trig[s, a] = (math.sin(d["rel_heading"]), math.cos(d["rel_heading"]),
+                                      math.sin(d["rel_elevation"]), math.cos(d["rel_elevation"]))
+                        nh = round(d["abs_heading"] / (math.pi / 6)) % 12
+                        nxt[s, a] = d["nextViewpointId"] * self.HEADINGS + nh
+                    if teach is not None:
+                        for goal in range(nvp):
+                            if v != goal:
+                                teach[s, goal] = min(range(1, len(adj)),
+                                                     key=lambda a: (env.dist[goal].get(adj[a]["nextViewpointId"], 1e9), a)) if len(adj) > 1 else 0
+        finally:
+            env.with_features = keep
+        t = lambda x: torch.from_numpy(x).to(device).contiguous()
+        self.vp, self.view, self.nvalid, self.cv, self.trig, self.next = t(vp), t(view), t(nvalid), t(cv), t(trig), t(nxt)
+        self.teach = t(teach) if teach is not None else None
+        self.S, self.A, self.G = S, a_cap, nvp
+        self.device = device
+
+    def state_ids(self, world_states):
+        return [int(ws.viewpointId) * self.HEADINGS + int(round(ws.heading / (math.pi / 6))) % 12 for ws in world_states]

@@ -435,6 +435,15 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
     return h1, c1, alpha, logit, alpha_v
 
 
+def follower_workspace(w: Dict[str, Tensor], B: int, L: int, A: int, device=None) -> Tensor:
+    """A zero-filled workspace for follower_step(workspace=...): one buffer serves every candidate count <= A of a
+    rollout (the layout does not depend on A), so an agent allocates it once instead of once per distinct A."""
+    d = follower_dims(w)
+    n = _lib.load().sfb_follower_step_workspace_bytes(C.byref(d), B, L, A)
+    dev = device if device is not None else w["lstm.weight_ih"].device
+    return _workspace(n, dev, ("follower_rollout", B, L))
+
+
 def follower_carry(w: Dict[str, Tensor], B: int, device=None) -> Tensor:
     """Opaque per-step state buffer for follower_step(carry_in=, carry_out=) (sfb_follower_carry_bytes); float32 so that
     carry_query() can view the visual query it starts with."""
@@ -664,6 +673,22 @@ def speaker_decoder_step(w: Dict[str, Tensor], prev_word: Tensor, h0: Tensor, c0
                                            _p(drop_h, name="drop_h"), _p(h1), _p(c1), _p(alpha), _p(logit),
                                            ws.data_ptr(), ws.numel(), _stream()))
     return h1, c1, alpha, logit
+
+
+def nav_step(nav, state: Tensor, ended: Tensor, goal: Optional[Tensor], a_prev: Optional[Tensor], actions_log: Optional[Tensor],
+             out: dict, with_target: bool = True) -> None:
+    """sfb_nav_step: advance the table-driven environment `nav` (navgraph_env.DeviceNavTables) by the actions `a_prev`
+    and write the next decode step's inputs into `out` (vp_idx, view_idx, cand_view, cand_trig, is_valid, target)."""
+    lib = _lib.load()
+    t = _lib.NavTables(_p(nav.vp, torch.int32), _p(nav.view, torch.int32), _p(nav.nvalid, torch.int32), _p(nav.cv, torch.int32),
+                       _p(nav.trig), _p(nav.next, torch.int32), _p(nav.teach, torch.int32) if nav.teach is not None else None,
+                       nav.S, nav.A, nav.G)
+    with torch.cuda.device(state.device):
+        check(lib.sfb_nav_step(C.byref(t), state.numel(), _p(state, torch.int32), _p(ended, torch.int32),
+                               _p(goal, torch.int32), _p(a_prev, torch.int32), _p(actions_log, torch.int32),
+                               _p(out["vp_idx"], torch.int32), _p(out["view_idx"], torch.int32), _p(out["cand_view"], torch.int32),
+                               _p(out["cand_trig"]), _p(out["is_valid"]),
+                               _p(out["target"], torch.int32) if with_target else None, _stream()))
 
 
 def set_option(name: str, value: int) -> None:

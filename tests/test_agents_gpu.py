@@ -312,3 +312,35 @@ def test_speaker_generation_records_in_trajectory_order(tmp_path):
     assert all(1 <= len(r["word_indices"]) <= 8 for r in out)
     import json
     assert json.load(open(tmp_path / "aug.json")) == out
+
+
+@pytest.mark.parametrize("graph_capture", [False, True])
+def test_device_rollout_matches_host_loop(graph_capture):
+    """SURVEY f-2: the table-driven environment (DeviceNavTables + sfb_nav_step) reproduces R2RBatch.step / observe, and
+    the fully device-resident rollout (optionally one CUDA graph per episode) takes the same actions with the same scores
+    as the host-driven rollout — for the staged host loop and, through it, for the oracle (test_greedy_rollout...)."""
+    from speaker_follower_b200.navgraph_env import DeviceNavTables
+    env = FakeR2RBatch(n_instr=8, batch_size=8, seed=41, graph="pLe4wQe7qrG")
+    agent, we, wd = make_follower(env, store=True)
+    agent.feedback = "argmax"
+    with torch.no_grad():
+        traj = agent.rollout()                                  # staged host loop (vp_index observations + device store)
+    oracle_check(agent, traj, we, wd, "argmax")
+    nav = DeviceNavTables(env, "cuda")
+    batch = env.batch                                           # the minibatch the rollout ran on, sorted by length
+    ws0 = [WorldStateOf(it) for it in batch]
+    res = agent.device_rollout(nav, nav.state_ids(ws0), [it["goal"] for it in batch], [it["instr_encoding"] for it in batch],
+                               cuda_graph=graph_capture)
+    acts, scores = res["actions"].cpu(), res["scores"].cpu()
+    for i, t in enumerate(traj):
+        n = len(t["actions"])
+        assert acts[i, :n].tolist() == [int(a) for a in t["actions"]], i
+        assert (acts[i, n:] == -1).all()
+        assert np.allclose(scores[i, :n].numpy(), np.array(t["scores"], dtype=np.float32), atol=1e-5)
+        # the table-driven environment ended where the simulator stand-in did
+        assert int(res["final_state"][i]) // nav.HEADINGS == t["trajectory"][-1][0]
+
+
+def WorldStateOf(item):
+    from speaker_follower_b200.navgraph_env import WorldState
+    return WorldState("fake", item["start"], item["heading"], 0.0)
