@@ -84,6 +84,10 @@ typedef struct sfb_visual_source {
   const int32_t* vp_idx;      /* [B] row into feat_table */
   const int32_t* view_idx;    /* [B] agent viewIndex 0..V-1 */
   int32_t        img_dim;     /* 2048 */
+  int32_t        idx_dependent; /* 1: vp_idx / view_idx are WRITTEN by work enqueued on the same stream just before this
+                                   call (e.g. sfb_nav_step): kernels read them only after their dependency wait instead of
+                                   prefetching slabs while the predecessor is still running.  0: they are step inputs
+                                   that were complete before the previous kernel started (host copies, earlier steps). */
 } sfb_visual_source;
 
 /* ---------------------------------------------------------------------------------------------- */

@@ -39,7 +39,7 @@ class ScoringWeights(C.Structure):
 
 class VisualSource(C.Structure):
     _fields_ = [("visual", c_float_p), ("feat_table", c_float_p), ("loc_table", c_float_p),
-                ("vp_idx", c_int_p), ("view_idx", c_int_p), ("img_dim", C.c_int32)]
+                ("vp_idx", c_int_p), ("view_idx", c_int_p), ("img_dim", C.c_int32), ("idx_dependent", C.c_int32)]
 
 
 class StepTail(C.Structure):

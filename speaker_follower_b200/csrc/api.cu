@@ -293,6 +293,7 @@ static int32_t visual_attend(const sfb_dims& d, int B, const float* q, const sfb
     const int loc = d.F - v.img_dim;
     a.segA = v.feat_table; a.strideA_b = (long long)d.V * v.img_dim; a.strideA_r = v.img_dim; a.lenA = v.img_dim;
     a.idxA = v.vp_idx;
+    a.idx_dependent = v.idx_dependent;
     a.segB = v.loc_table; a.strideB_b = (long long)d.V * loc; a.strideB_r = loc; a.lenB = loc;
     a.idxB = v.view_idx;
   }
@@ -950,6 +951,7 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
     f.post_kb0 = kblocks(d.E); f.post_kb1 = kblocks(d.E) + kblocks(d.F); f.feat_kb0 = kblocks(d.E);
     f.g.lstm = lstm_e; f.g.M = B; f.g.N = 4 * d.H;
     f.B = B;
+    f.idx_dependent = vis->idx_dependent;
     f.pre_weight_free = g_fused_pre_weight;
     f.dbg = g_fused_dbg;
     if (g_fused_nopre) { f.post_kb0 = 0; f.post_kb1 = P.nkb_gates; }   // bring-up: no overlap of the gate GEMM with the gather

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(NT, MINB) soft_dot_attn_kernel(const AttnParam
     if (p.lenB > 0)
       bulk_g2s_hint(dst + p.lenA, p.segB + bb + (size_t)gr * p.strideB_r, (uint32_t)p.lenB * 4u, &full[stage], pol);
   };
+  if (p.idx_dependent) pdl_wait();
   if (warp == 0) {
     // the slab addresses hang on a dependent index load: request it first, use it after the barrier setup
     const long long ia = p.idxA ? (long long)p.idxA[b] : (long long)b;

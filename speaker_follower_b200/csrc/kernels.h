@@ -52,6 +52,7 @@ struct AttnParams {
   // of the kernel so that this grid's completion still implies the predecessor's
   int defer_wait;
   const float* post_add; int ld_post; int post_tanh;   // out = tanh?(attention output + post_add[b, :]) (read after the wait)
+  int idx_dependent;                      // 1: idxA / idxB are written by the preceding kernel: read them after the dependency wait
   int no_hint;                            // bring-up: plain L2 policy instead of evict-first
   unsigned long long* cta_trace;          // bring-up: per-CTA {entry, first row landed, stream done, exit, smid}
   unsigned long long* trace;              // bring-up: 3 timestamps of block 0, or NULL
@@ -177,6 +178,7 @@ struct FusedVisLstmParams {
   int feat_kb0;                           // first K block of the attention output inside b_pk
   GemmParams g;                           // LSTM epilogue (g.lstm), M = B
   int B;
+  int idx_dependent;                      // 1: idxA / idxB are written by the preceding kernel -> read them after the dependency wait
   int dbg;                                // bring-up: 1 = gather without arithmetic, 2 = dot products only
   int pre_weight_free;                    // share of the pre K blocks a CTA without a gather role takes, relative to 1 for a gather CTA
   // filled by the launcher

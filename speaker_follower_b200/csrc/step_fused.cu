@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(FNT, 1) vis_lstm_fused_kernel(const FusedVisLs
 
   if (warp == 10) {
     // =============================== gather producer: the slab of this CTA's batch element ===============================
+    if (q.idx_dependent) pdl_wait();   // the slab indices come from the kernel before this one (table-driven environment)
     if (has_gather && lane == 0) {
       const int b = cid;
       const long long ia = q.idxA ? (long long)q.idxA[b] : (long long)b;

@@ -388,7 +388,7 @@ class Seq2SeqAgent(BaseAgent):
                     self.decoder.decode_step(ub[p], None, (buf["vp_idx"], buf["view_idx"]), hb[p], cb[p], ctx, seq_mask, tail=tail,
                                              carry_in=None if t == 0 else carry[p], carry_out=carry[p ^ 1], ctx_proj=ctx_proj,
                                              cand_view=buf["cand_view"], cand_trig=buf["cand_trig"],
-                                             out=(hb[p ^ 1], cb[p ^ 1], alpha, logit, alpha_v), workspace=ws)
+                                             out=(hb[p ^ 1], cb[p ^ 1], alpha, logit, alpha_v), workspace=ws, idx_dependent=True)
                 ops.nav_step(nav, buf["state"], buf["ended"], buf["goal"], buf["a_t"], buf["actions"][T - 1], buf)
 
             graph = None

@@ -204,7 +204,8 @@ class AttnDecoderLSTM(_PackedWeights, nn.Module):
         return ops.follower_project_ctx(sd, packed, ctx.contiguous()) if packed is not None else None
 
     def decode_step(self, u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask=None, tail=None, carry_in=None,
-                    carry_out=None, ctx_proj=None, cand_view=None, cand_trig=None, out=None, workspace=None):
+                    carry_out=None, ctx_proj=None, cand_view=None, cand_trig=None, out=None, workspace=None,
+                    idx_dependent=False):
         """forward() plus the fast-path extras of the packed C ABI (include/sf_b200.h): ``tail`` fuses the rollout
         tail (follower.py:476-505) behind the logits, ``carry_in``/``carry_out`` (``new_carry()`` buffers) hand the next step's visual query and packed gate
         operand across steps,
@@ -226,7 +227,7 @@ class AttnDecoderLSTM(_PackedWeights, nn.Module):
         if isinstance(visual_context, (tuple, list)):
             vp, view = visual_context
             if all_u_t is None:   # action candidates gathered on the device too (env.py:60-75): view index + 4 trig values
-                extra.update(cand_view=cand_view, cand_trig=cand_trig, out=out, workspace=workspace)
+                extra.update(cand_view=cand_view, cand_trig=cand_trig, out=out, workspace=workspace, idx_dependent=idx_dependent)
             return ops.follower_step(sd, u_t_prev, None if all_u_t is None else all_u_t.contiguous(), None, h_0.contiguous(),
                                      c_0.contiguous(), ctx.contiguous(), ctx_mask, drop_x, drop_h,
                                      store=self.feature_store, vp_idx=vp, view_idx=view, **extra)

@@ -155,8 +155,9 @@ class FeatureStore:
         return torch.cat((self.feat_table[vp_idx.long()], self.loc_table[view_idx.long()]), dim=2).contiguous()
 
 
-def _visual_source(visual, store: Optional[FeatureStore], vp_idx, view_idx, keep):
+def _visual_source(visual, store: Optional[FeatureStore], vp_idx, view_idx, keep, idx_dependent: bool = False):
     vs = VisualSource()
+    vs.idx_dependent = 1 if idx_dependent else 0
     if visual is not None:
         vs.visual = _p(visual, name="visual_context")
         keep.append(visual)
@@ -351,7 +352,7 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
                   workspace: Optional[Tensor] = None, out: Optional[tuple] = None,
                   packed: Optional[Tensor] = None, carry_in: Optional[Tensor] = None, carry_out: Optional[Tensor] = None,
                   tail: Optional[dict] = None, cand_view: Optional[Tensor] = None, cand_trig: Optional[Tensor] = None,
-                  ctx_proj: Optional[tuple] = None):
+                  ctx_proj: Optional[tuple] = None, idx_dependent: bool = False):
     """AttnDecoderLSTM.forward (model.py:377-397) -> (h1, c1, alpha, logit, alpha_v).
     `packed`: blob from PackedFollower.get(w) -> the packed-weight tcgen05 path (sfb_follower_step_packed_fwd).
     Packed path only: `carry_in` / `carry_out` (follower_carry() buffers) hand the state one step prepares for the
@@ -363,7 +364,8 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
     `all_u_t=None` with `cand_view` [B,A] int32 / `cand_trig` [B,A,4] (+ store, vp_idx): action candidates gathered
     on the device from the feature table (env.py:60-75) instead of being shipped as a dense [B,A,E] tensor;
     `ctx_proj` = (ctx_k, ctx_o) from follower_project_ctx(): per-episode projections of ctx that take the text-side
-    projections off the step's dependency chain."""
+    projections off the step's dependency chain; `idx_dependent`: the index tensors (vp_idx, view_idx, cand_view, ...)
+    are produced by the kernel enqueued just before this call (nav_step) — no prefetch ahead of the dependency wait."""
     lib = _lib.load()
     L = ctx.shape[1]
     V = visual.shape[1] if visual is not None else store.feat_table.shape[1]
@@ -376,7 +378,7 @@ def follower_step(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual:
         (B, A), E = cand_view.shape, d.E
     dev = h0.device
     keep = []
-    vs = _visual_source(visual, store, vp_idx, view_idx, keep)
+    vs = _visual_source(visual, store, vp_idx, view_idx, keep, idx_dependent)
     mask = _mask_u8(ctx_mask)
     need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, L, A)
     if workspace is None or workspace.numel() < need:
