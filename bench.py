@@ -522,6 +522,54 @@ def run_gpu(args, rank, local_rank, world):
     d2h = sum(t.numel() * t.element_size() for t in h_out)
 
     log("e2e done")
+    # ---- agent level: Seq2SeqAgent on a navigation-graph environment, (a) the whole rollout on the device (table-driven
+    # environment, one CUDA graph per 10-step episode, nav kernels included), (b) the host loop with the Python
+    # environment and one pinned staging buffer per step
+    agent_stats = None
+    if blob is not None and not os.environ.get("SFB_NO_AGENT"):
+        try:
+            from speaker_follower_b200 import follower as Fo, model as M
+            from speaker_follower_b200.navgraph_env import DeviceNavTables, FakeR2RBatch, WorldState
+            nenv = FakeR2RBatch(n_viewpoints=256, n_instr=B, batch_size=B, seed=9, max_len=L, with_features=False)
+            glove = synth.follower_encoder_weights()["embedding.weight"].numpy()
+            enc = M.EncoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0, 0.5, glove=glove).to(dev).eval()
+            dec = M.AttnDecoderLSTM(synth.FEAT, synth.HID, 0.5).to(dev).eval()
+            enc.load_state_dict(synth.follower_encoder_weights()); dec.load_state_dict(w_cpu)
+            dec.feature_store = store
+            agent = Fo.Seq2SeqAgent(nenv, "", enc, dec, episode_len=POOL, max_instruction_length=L)
+            nav = DeviceNavTables(nenv, dev)
+            nenv.reset(sort=True)
+            batch = nenv.batch
+            starts = nav.state_ids([WorldState("fake", it["start"], it["heading"], 0.0) for it in batch])
+            res = agent.device_rollout(nav, starts, [it["goal"] for it in batch], [it["instr_encoding"] for it in batch], cuda_graph=True)
+            gph = res["graph"]
+            for _ in range(5):
+                gph.replay()
+            torch.cuda.synchronize()
+            n_ep = 100
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            for _ in range(n_ep):
+                gph.replay()
+            eb.record(); torch.cuda.synchronize()
+            dev_sps = n_ep * POOL / (ea.elapsed_time(eb) * 1e-3)
+            agent.feedback = "argmax"
+            with torch.no_grad():
+                agent.rollout()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter(); n_steps = 0
+                for _ in range(5):
+                    tr = agent.rollout()
+                    n_steps += max(len(t["actions"]) for t in tr)
+                torch.cuda.synchronize()
+                host_sps = n_steps / (time.perf_counter() - t0)
+            agent_stats = {"device_rollout_steps_per_s": dev_sps, "host_loop_steps_per_s": host_sps,
+                           "how": "Seq2SeqAgent at B=%d on a 256-viewpoint navigation graph: device_rollout = table-driven environment "
+                                  "(sfb_nav_step) + decode steps, one CUDA graph per %d-step episode, encoder excluded; host loop = "
+                                  "agent.rollout() with the Python environment (index-only observations), encoder included" % (B, POOL)}
+            log("agent level: %.0f steps/s on the device, %.0f steps/s host loop" % (dev_sps, host_sps))
+        except Exception as e:  # the agent numbers are an extra: never lose the headline line over them
+            agent_stats = {"error": repr(e)}
     # ---- roofline of the attention-gather kernel, timed alone with CUDA events on its launch stream;
     # every launch reads a different random set of slabs from the 3.1 GB table (inputs >> L2).
     q = torch.randn(B, F, device=dev, generator=g) * 0.05
@@ -560,6 +608,7 @@ def run_gpu(args, rank, local_rank, world):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
+            "agent": agent_stats,
             "gpu_launches": launches_per_step[0] * args.steps + proj_launches * (args.steps // POOL + (1 if args.steps % POOL else 0)),
             "roofline": {"kernel": "soft_dot_attn_kernel (36-view attention gather)", "bound": "hbm",
                          "achieved": attn_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": attn_gbs / hbm_peak,
