@@ -214,6 +214,37 @@ typedef struct sfb_step_tail {
   float*         action_score;  /* [B] or NULL */
   float*         ce;            /* [B] or NULL */
 } sfb_step_tail;
+/* Backward of ONE follower decode step: torch autograd of AttnDecoderLSTM.forward (model.py:377-397) as driven by
+ * Seq2SeqAgent.train (follower.py:1001-1020, loss.backward() at :1018), hand-written.
+ *   forward inputs  : as for sfb_follower_step_fwd (u_prev, action candidates, visual source, h0, c0, ctx, mask, masks)
+ *   saved results   : c1, alpha, alpha_v (forward outputs) and `fwd_workspace`, the workspace buffer the forward call of
+ *                     THIS step ran in (it still holds feature, activated gates, dropped h1 and h~; a training rollout
+ *                     therefore gives every step its own workspace)
+ *   upstream grads  : g_h1, g_c1 [B,H], g_logit [B,A] (any may be NULL = zero)
+ *   outputs         : d_h0, d_c0 [B,H], d_ctx [B,L,H] (overwritten), parameter gradients in `grads` (state_dict layouts;
+ *                     accumulate != 0: added to what is there, as autograd does across the steps of a rollout).
+ * u_prev and the action candidates are treated as constants (follower.py:502 detaches them); linear_in_v.bias gets no
+ * gradient (it cancels in the softmax).  Every product runs on this library's kernels (skinny GEMMs, attention /
+ * LSTM / scoring backward kernels of backward.cu); workspace: sfb_follower_step_bwd_workspace_bytes. */
+typedef struct sfb_follower_grads {
+  float *lstm_w_ih, *lstm_w_hh, *lstm_b_ih, *lstm_b_hh;
+  float *va_w_h, *va_b_h, *va_w_v;
+  float *w_in, *w_out;
+  float *sc_w_h, *sc_b_h, *sc_w_a, *sc_b_a, *sc_w_out, *sc_b_out;
+} sfb_follower_grads;
+size_t  sfb_follower_step_bwd_workspace_bytes(const sfb_dims* dims, int32_t B, int32_t L, int32_t A);
+int32_t sfb_follower_step_bwd(const sfb_dims* dims, const sfb_vis_lstm_weights* wl,
+                              const sfb_softdot_weights* wt, const sfb_scoring_weights* ws,
+                              int32_t B, int32_t L, int32_t A,
+                              const float* u_prev, const sfb_action_source* act, const sfb_visual_source* vis,
+                              const float* h0, const float* c0, const float* ctx, const uint8_t* ctx_mask,
+                              const float* drop_x, const float* drop_h,
+                              const float* c1, const float* alpha, const float* alpha_v, const void* fwd_workspace,
+                              const float* g_h1, const float* g_c1, const float* g_logit,
+                              float* d_h0, float* d_c0, float* d_ctx,
+                              const sfb_follower_grads* grads, int32_t accumulate,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 size_t  sfb_follower_packed_bytes(const sfb_dims* dims);
 size_t  sfb_follower_carry_bytes(const sfb_dims* dims, int32_t B);
 int32_t sfb_follower_pack_weights(const sfb_dims* dims, const sfb_vis_lstm_weights* wl,

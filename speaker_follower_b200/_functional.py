@@ -49,8 +49,46 @@ def follower_step(w: Dict[str, Tensor], u_t_prev: Tensor, all_u_t: Tensor, visua
     return h_1, c_1, alpha, logit, alpha_v
 
 
+class FollowerStepKernelFn(torch.autograd.Function):
+    """One decode step, forward AND backward on the sm_100a library: the forward call runs in its own workspace, which
+    keeps the step's intermediates (attention output, activated gates, dropped h_1, h~) for sfb_follower_step_bwd
+    (backward.cu); parameter gradients are returned to autograd, which accumulates them over the steps of a rollout.
+    u_t_prev, the action candidates and the visual context are constants of the step (follower.py:502)."""
+
+    @staticmethod
+    def forward(ctx_, run_cuda, names, n_in, ctx_mask, drop_x, drop_h, *tensors):
+        inputs, params = tensors[:n_in], tensors[n_in:]
+        outs, fwd_ws = run_cuda()
+        ctx_.names, ctx_.n_in = names, n_in
+        ctx_.ctx_mask, ctx_.drop_x, ctx_.drop_h, ctx_.fwd_ws = ctx_mask, drop_x, drop_h, fwd_ws
+        ctx_.save_for_backward(*inputs, *params, outs[1], outs[2], outs[4])
+        ctx_.mark_non_differentiable(outs[2], outs[4])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx_, g_h1, g_c1, g_alpha, g_logit, g_alpha_v):
+        from . import ops
+        saved = ctx_.saved_tensors
+        n_in, names = ctx_.n_in, ctx_.names
+        u, U, V, h0, c0, c = saved[:n_in]
+        params = saved[n_in:n_in + len(names)]
+        c1, alpha, alpha_v = saved[n_in + len(names):]
+        w = {k: p.detach() for k, p in zip(names, params)}
+        grads = {k: torch.zeros_like(p) for k, p in w.items() if k != "visual_attention_layer.linear_in_v.bias"}
+        with torch.no_grad():
+            d_h0, d_c0, d_ctx = ops.follower_step_bwd(w, u.detach(), U.detach(), V.detach(), h0.detach(), c0.detach(), c.detach(),
+                                                       ctx_.ctx_mask, ctx_.drop_x, ctx_.drop_h, c1, alpha, alpha_v, ctx_.fwd_ws,
+                                                       g_h1, g_c1, g_logit, grads, accumulate=False)
+        need = ctx_.needs_input_grad[6:]
+        gin = [None, None, None, d_h0, d_c0, d_ctx]
+        gin = [g if nd else None for g, nd in zip(gin, need[:n_in])]
+        gpar = [(grads.get(k) if nd else None) for k, nd in zip(names, need[n_in:])]
+        return (None, None, None, None, None, None, *gin, *gpar)
+
+
 class FollowerStepFn(torch.autograd.Function):
-    """Forward on the CUDA kernels, backward by torch autograd over the restatement above (same inputs, same masks)."""
+    """Forward on the CUDA kernels, backward by torch autograd over the restatement above (same inputs, same masks).
+    Kept as the independent check of FollowerStepKernelFn in tests/test_gpu_train.py."""
 
     @staticmethod
     def forward(ctx_, run_cuda, names, n_in, ctx_mask, drop_x, drop_h, *tensors):

@@ -68,6 +68,11 @@ class NavTables(C.Structure):
                 ("next", c_int_p), ("teach", c_int_p), ("S", C.c_int32), ("A", C.c_int32), ("G", C.c_int32)]
 
 
+class FollowerGrads(C.Structure):
+    _fields_ = [(n, c_float_p) for n in ("lstm_w_ih", "lstm_w_hh", "lstm_b_ih", "lstm_b_hh", "va_w_h", "va_b_h", "va_w_v",
+                                         "w_in", "w_out", "sc_w_h", "sc_b_h", "sc_w_a", "sc_b_a", "sc_w_out", "sc_b_out")]
+
+
 # name -> (restype, argtypes); every symbol include/sf_b200.h declares
 SIGNATURES = {
     "sfb_abi_version": (C.c_int32, []),
@@ -107,6 +112,15 @@ SIGNATURES = {
                                                  c_float_p, c_float_p,
                                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_follower_carry_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32]),
+    "sfb_follower_step_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32, C.c_int32, C.c_int32]),
+    "sfb_follower_step_bwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(VisLstmWeights), C.POINTER(SoftDotWeights),
+                                          C.POINTER(ScoringWeights), C.c_int32, C.c_int32, C.c_int32,
+                                          c_float_p, C.POINTER(ActionSource), C.POINTER(VisualSource), c_float_p, c_float_p,
+                                          c_float_p, c_u8_p, c_float_p, c_float_p,
+                                          c_float_p, c_float_p, c_float_p, C.c_void_p,
+                                          c_float_p, c_float_p, c_float_p,
+                                          c_float_p, c_float_p, c_float_p,
+                                          C.POINTER(FollowerGrads), C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_nav_step": (C.c_int32, [C.POINTER(NavTables), C.c_int32, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p,
                                  c_int_p, c_int_p, c_int_p, c_float_p, c_float_p, c_int_p, C.c_void_p]),
     "sfb_eltwise_prod_scoring_fwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(ScoringWeights), C.c_int32, C.c_int32,

@@ -1096,6 +1096,146 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
   return 0;
 }
 
+/* ---------------------------------------------------------------- follower decode step: backward */
+namespace {
+struct BwdWs {
+  float *dg, *dsum, *th, *v, *r, *dth, *prod, *dht, *dz, *dwc_dh, *t, *dt, *wc, *dh1d, *dgates, *x, *dfeat, *dq, *tv, *dtv;
+  size_t bytes;
+};
+BwdWs carve_bwd(const sfb_dims& d, int B, void* ws) {
+  BwdWs w;
+  Carver c(ws);
+  w.dg = c.take((size_t)B * d.E); w.dsum = c.take(B);
+  w.th = c.take((size_t)B * d.D); w.v = c.take((size_t)B * d.D); w.r = c.take((size_t)B * d.D);
+  w.dth = c.take((size_t)B * d.D); w.prod = c.take((size_t)B * d.D);
+  w.dht = c.take((size_t)B * d.H); w.dz = c.take((size_t)B * d.H); w.dwc_dh = c.take((size_t)B * 2 * d.H);
+  w.t = c.take((size_t)B * d.H); w.dt = c.take((size_t)B * d.H); w.wc = c.take((size_t)B * d.H); w.dh1d = c.take((size_t)B * d.H);
+  w.dgates = c.take((size_t)B * 4 * d.H); w.x = c.take((size_t)B * (d.E + d.F));
+  w.dfeat = c.take((size_t)B * d.F); w.dq = c.take((size_t)B * d.F);
+  w.tv = c.take((size_t)B * d.D); w.dtv = c.take((size_t)B * d.D);
+  w.bytes = c.off;
+  return w;
+}
+// out[M,N] = x[M,K] · W^T (kn = 0: W is [N,K]) or x · W (kn = 1: W is [K,N]), + bias, + padd
+int32_t bgemm(int M, int N, int K, const float* x, int ldx, const float* W, int ldw, int kn, float* out, int ldo,
+              const float* bias, const float* padd, int ld_padd, cudaStream_t st) {
+  GemmParams g{};
+  g.nseg = 1;
+  g.seg[0] = GemmSeg{x, ldx, nullptr, nullptr, 0, W, ldw, K, kn};
+  g.M = M; g.N = N; g.splitk = gemm_pick_splitk(M, N, K, device_num_sms());
+  g.out = out; g.ldo = ldo; g.bias0 = bias; g.padd = padd; g.ld_padd = ld_padd;
+  return launch_gemm(g, st);
+}
+int32_t outer(const float* Y, int ldy, const float* X, int ldx, int B, int N, int K, float* out, int ldo, int acc, cudaStream_t st) {
+  if (!out) return 0;
+  OuterParams o{Y, ldy, X, ldx, B, N, K, out, ldo, acc};
+  return launch_outer_accum(o, st);
+}
+}  // namespace
+
+size_t sfb_follower_step_bwd_workspace_bytes(const sfb_dims* dims, int32_t B, int32_t L, int32_t A) {
+  (void)L; (void)A;
+  if (!dims || B < 1) return 0;
+  return carve_bwd(*dims, B, nullptr).bytes;
+}
+
+int32_t sfb_follower_step_bwd(const sfb_dims* dims, const sfb_vis_lstm_weights* wl, const sfb_softdot_weights* wt,
+                              const sfb_scoring_weights* wsc, int32_t B, int32_t L, int32_t A, const float* u_prev,
+                              const sfb_action_source* act, const sfb_visual_source* vis, const float* h0, const float* c0,
+                              const float* ctx, const uint8_t* ctx_mask, const float* drop_x, const float* drop_h,
+                              const float* c1, const float* alpha, const float* alpha_v, const void* fwd_workspace,
+                              const float* g_h1, const float* g_c1, const float* g_logit, float* d_h0, float* d_c0,
+                              float* d_ctx, const sfb_follower_grads* gr, int32_t accumulate, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_CHECK_ARG(wl && wt && wsc && act && vis && gr, "NULL struct argument");
+  SFB_CHECK_ARG(u_prev && h0 && c0 && ctx && c1 && alpha && alpha_v && fwd_workspace && d_h0 && d_c0 && d_ctx, "NULL tensor argument");
+  SFB_CHECK_ARG(B >= 1 && L >= 1 && A >= 1, "B, L, A >= 1");
+  const sfb_dims& d = *dims;
+  const FollowerWs fw = carve_follower(d, B, L, A, const_cast<void*>(fwd_workspace));   // where the forward left its intermediates
+  const BwdWs w = carve_bwd(d, B, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, w.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int acc = accumulate ? 1 : 0;
+  const float* h_tilde = fw.htilde; const float* h1d = fw.h1d; const float* feat = fw.feat; const float* gates_act = fw.gates_act;
+  const int E = d.E, F = d.F, H = d.H, D = d.D;
+
+  // ---- EltwiseProdScoring backward (model.py:342-352)
+  if (g_logit) {
+    ScoreBwdParams sp{};
+    sp.dlogit = g_logit; sp.B = B; sp.A = A; sp.E = E; sp.dg = w.dg; sp.dsum = w.dsum;
+    if (act->all_u_t) sp.all_u_t = act->all_u_t;
+    else { sp.cand_table = act->feat_table; sp.vp_idx = act->vp_idx; sp.cand_view = act->cand_view; sp.cand_trig = act->cand_trig;
+           sp.img_dim = act->img_dim; sp.cand_V = d.V; }
+    SFB_PROPAGATE(launch_score_bwd(sp, st));
+    SFB_PROPAGATE(bgemm(B, D, H, h_tilde, H, wsc->w_h, H, 0, w.th, D, wsc->b_h, nullptr, 0, st));          // th = W_h h~ + b_h
+    SFB_PROPAGATE(bgemm(B, D, E, w.dg, E, wsc->w_a, E, 0, w.v, D, nullptr, nullptr, 0, st));               // v = W_a dg
+    SFB_PROPAGATE(launch_scoring_mid(w.th, w.v, wsc->w_out, wsc->b_a, w.dsum, w.r, w.dth, w.prod, B, D, st));
+    SFB_PROPAGATE(outer(w.r, D, w.dg, E, B, D, E, gr->sc_w_a, E, acc, st));                                 // dW_a = r^T dg
+    SFB_PROPAGATE(outer(w.r, D, w.dsum, 1, B, D, 1, gr->sc_b_a, 1, acc, st));                               // db_a = r^T dsum
+    if (gr->sc_w_out) SFB_PROPAGATE(launch_colsum(w.prod, D, B, D, gr->sc_w_out, acc, st));                 // dw_o
+    if (gr->sc_b_out) SFB_PROPAGATE(launch_colsum(w.dsum, 1, B, 1, gr->sc_b_out, acc, st));                 // db_o
+    SFB_PROPAGATE(outer(w.dth, D, h_tilde, H, B, D, H, gr->sc_w_h, H, acc, st));                            // dW_h' = dth^T h~
+    if (gr->sc_b_h) SFB_PROPAGATE(launch_colsum(w.dth, D, B, D, gr->sc_b_h, acc, st));
+    SFB_PROPAGATE(bgemm(B, H, D, w.dth, D, wsc->w_h, H, 1, w.dht, H, nullptr, nullptr, 0, st));            // dh~ = dth W_h'
+  } else {
+    SFB_CHECK_CUDA(cudaMemsetAsync(w.dht, 0, (size_t)B * H * sizeof(float), st));
+  }
+  // ---- SoftDotAttention backward (model.py:122-143)
+  SFB_PROPAGATE(launch_tanh_bwd(w.dht, h_tilde, w.dz, B * H, st));
+  SFB_PROPAGATE(bgemm(B, 2 * H, H, w.dz, H, wt->w_out, 2 * H, 1, w.dwc_dh, 2 * H, nullptr, nullptr, 0, st));   // [dwc | dh1d] = dz W_out
+  SFB_PROPAGATE(bgemm(B, H, H, h1d, H, wt->w_in, H, 0, w.t, H, nullptr, nullptr, 0, st));                      // t = W_in h1d
+  {
+    AttnBwdParams a{};
+    a.segA = ctx; a.strideA_b = (long long)L * H; a.strideA_r = H; a.lenA = H; a.lenB = 0;
+    a.mask = ctx_mask; a.ldmask = L; a.R = L; a.D = H;
+    a.alpha = alpha; a.ldalpha = L; a.dout = w.dwc_dh; a.lddout = 2 * H; a.qv = w.t; a.ldq = H;
+    a.dq = w.dt; a.lddq = H; a.drows = d_ctx; a.wsum = w.wc; a.ldwsum = H;
+    SFB_PROPAGATE(launch_attn_bwd(a, B, st));
+  }
+  SFB_PROPAGATE(outer(w.dt, H, h1d, H, B, H, H, gr->w_in, H, acc, st));                                      // dW_in = dt^T h1d
+  SFB_PROPAGATE(outer(w.dz, H, w.wc, H, B, H, H, gr->w_out, 2 * H, acc, st));                                 // dW_out[:, :H] = dz^T wc
+  SFB_PROPAGATE(outer(w.dz, H, h1d, H, B, H, H, gr->w_out ? gr->w_out + H : nullptr, 2 * H, acc, st));       // dW_out[:, H:] = dz^T h1d
+  SFB_PROPAGATE(bgemm(B, H, H, w.dt, H, wt->w_in, H, 1, w.dh1d, H, nullptr, w.dwc_dh + H, 2 * H, st));       // dh1d = dt W_in + dz W_out_h
+  // ---- LSTMCell backward (model.py:393-394)
+  {
+    LstmBwdParams lp{B, H, gates_act, c0, c1, g_h1, g_c1, w.dh1d, drop_h, w.dgates, d_c0};
+    SFB_PROPAGATE(launch_lstm_cell_bwd(lp, st));
+  }
+  if (gr->lstm_w_ih) {
+    SFB_PROPAGATE(launch_assemble_x(u_prev, feat, drop_x, w.x, B, E, F, st));
+    SFB_PROPAGATE(outer(w.dgates, 4 * H, w.x, E + F, B, 4 * H, E + F, gr->lstm_w_ih, E + F, acc, st));
+  }
+  SFB_PROPAGATE(outer(w.dgates, 4 * H, h0, H, B, 4 * H, H, gr->lstm_w_hh, H, acc, st));
+  if (gr->lstm_b_ih) SFB_PROPAGATE(launch_colsum(w.dgates, 4 * H, B, 4 * H, gr->lstm_b_ih, acc, st));
+  if (gr->lstm_b_hh) SFB_PROPAGATE(launch_colsum(w.dgates, 4 * H, B, 4 * H, gr->lstm_b_hh, acc, st));
+  SFB_PROPAGATE(bgemm(B, F, 4 * H, w.dgates, 4 * H, wl->lstm_w_ih + E, E + F, 1, w.dfeat, F, nullptr, nullptr, 0, st));   // d(x_f) = dgates W_ih[:, E:]
+  SFB_PROPAGATE(bgemm(B, H, 4 * H, w.dgates, 4 * H, wl->lstm_w_hh, H, 1, d_h0, H, nullptr, nullptr, 0, st));              // dh0 = dgates W_hh
+  // ---- VisualSoftDotAttention backward (model.py:310-326)
+  {
+    AttnBwdParams a{};
+    if (vis->visual) {
+      a.segA = vis->visual; a.strideA_b = (long long)d.V * F; a.strideA_r = F; a.lenA = F; a.lenB = 0;
+    } else {
+      const int loc = F - vis->img_dim;
+      a.segA = vis->feat_table; a.strideA_b = (long long)d.V * vis->img_dim; a.strideA_r = vis->img_dim; a.lenA = vis->img_dim; a.idxA = vis->vp_idx;
+      a.segB = vis->loc_table; a.strideB_b = (long long)d.V * loc; a.strideB_r = loc; a.lenB = loc; a.idxB = vis->view_idx;
+    }
+    a.R = d.V; a.D = F; a.alpha = alpha_v; a.ldalpha = d.V;
+    a.dout = w.dfeat; a.lddout = F; a.dout_scale = drop_x ? drop_x + E : nullptr; a.ldscale = E + F;
+    a.dq = w.dq; a.lddq = F;
+    SFB_PROPAGATE(launch_attn_bwd(a, B, st));
+  }
+  SFB_PROPAGATE(bgemm(B, D, H, h0, H, wl->va_w_h, H, 0, w.tv, D, wl->va_b_h, nullptr, 0, st));               // t_v = W_h h0 + b_h
+  SFB_PROPAGATE(outer(w.tv, D, w.dq, F, B, D, F, gr->va_w_v, F, acc, st));                                   // dW_v = t_v^T dq
+  SFB_PROPAGATE(bgemm(B, D, F, w.dq, F, wl->va_w_v, F, 0, w.dtv, D, nullptr, nullptr, 0, st));              // dt_v = W_v dq
+  SFB_PROPAGATE(outer(w.dtv, D, h0, H, B, D, H, gr->va_w_h, H, acc, st));
+  if (gr->va_b_h) SFB_PROPAGATE(launch_colsum(w.dtv, D, B, D, gr->va_b_h, acc, st));
+  SFB_PROPAGATE(bgemm(B, H, D, w.dtv, D, wl->va_w_h, H, 1, d_h0, H, nullptr, d_h0, H, st));                  // dh0 += dt_v W_h
+  return 0;
+}
+
 /* ---------------------------------------------------------------- speaker modules on the packed tcgen05 path */
 namespace {
 struct VisLstmPk { size_t a_q, b_q, a_gates, mq, bytes; int nkb_h, nkb_gates; };

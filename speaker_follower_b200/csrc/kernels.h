@@ -273,6 +273,49 @@ struct NavStepParams {
 };
 int32_t launch_nav_step(const NavStepParams& p, cudaStream_t stream);
 
+// ---------------------------------------------------------------- backward.cu
+struct ScoreBwdParams {
+  const float* dlogit; int B, A, E;
+  const float* all_u_t;
+  const float* cand_table; const int32_t* vp_idx; const int32_t* cand_view; const float* cand_trig; int img_dim, cand_V;
+  float* dg; float* dsum;                 // [B,E], [B]
+};
+int32_t launch_score_bwd(const ScoreBwdParams& p, cudaStream_t st);
+int32_t launch_tanh_bwd(const float* dy, const float* y, float* dz, int n, cudaStream_t st);
+int32_t launch_scoring_mid(const float* th, const float* v, const float* w_o, const float* b_a, const float* dsum, float* r,
+                           float* dth, float* prod, int B, int D, cudaStream_t st);
+struct LstmBwdParams {
+  int B, H;
+  const float* gates_act; const float* c0; const float* c1;
+  const float* g_h1; const float* g_c1; const float* dh1d; const float* drop_h;   // any of the three gradients may be NULL
+  float* dgates; float* dc0;
+};
+int32_t launch_lstm_cell_bwd(const LstmBwdParams& p, cudaStream_t st);
+int32_t launch_assemble_x(const float* u, const float* f, const float* drop, float* x, int B, int E, int F, cudaStream_t st);
+struct AttnBwdParams {
+  const float* segA; long long strideA_b; int strideA_r, lenA;     // rows as in AttnParams (dense or gathered)
+  const float* segB; long long strideB_b; int strideB_r, lenB;
+  const int32_t* idxA; const int32_t* idxB;
+  const uint8_t* mask; int ldmask;
+  int R, D;
+  const float* alpha; int ldalpha;        // forward softmax weights [B,R]
+  const float* dout; int lddout;          // gradient of the weighted sum [B,D]
+  const float* dout_scale; int ldscale;   // optional elementwise factor of dout (dropout keep mask)
+  const float* qv; int ldq;               // query of the scores (only read when drows != NULL)
+  float* dq; int lddq;                    // [B,D] gradient w.r.t. the query
+  float* drows;                           // [B,R,D] gradient w.r.t. the rows, or NULL
+  float* wsum; int ldwsum;                // [B,D] the forward weighted sum (recomputed), or NULL
+  int stage_rows;                         // filled by the launcher
+};
+int32_t launch_attn_bwd(AttnBwdParams p, int B, cudaStream_t st);
+struct OuterParams {
+  const float* Y; int ldy; const float* X; int ldx;
+  int B, N, K;
+  float* out; int ldo; int accumulate;
+};
+int32_t launch_outer_accum(const OuterParams& p, cudaStream_t st);
+int32_t launch_colsum(const float* Y, int ldy, int B, int N, float* out, int accumulate, cudaStream_t st);
+
 int device_num_sms();
 unsigned long long* next_trace_slot();
 unsigned long long* cta_trace_buffer();  // NULL unless sfb_set_option("cta_trace", 1)

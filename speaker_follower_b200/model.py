@@ -239,8 +239,8 @@ class AttnDecoderLSTM(_PackedWeights, nn.Module):
         return ops.follower_carry(_sd(self), B, device)
 
     def _decode_step_autograd(self, sd, u_t_prev, all_u_t, visual_context, h_0, c_0, ctx, ctx_mask, drop_x, drop_h):
-        """Training: forward on the CUDA kernels (detached), gradients from torch autograd over the device-side
-        restatement in _functional.py with the same dropout masks (hand-written backward kernels: DESIGN.md §10)."""
+        """Training: forward on the CUDA kernels in a per-step workspace, backward on the hand-written kernels of
+        backward.cu (sfb_follower_step_bwd) through _functional.FollowerStepKernelFn."""
         if isinstance(visual_context, (tuple, list)):
             vp, view = visual_context
             visual_context = self.feature_store.dense(vp, view)
@@ -252,9 +252,14 @@ class AttnDecoderLSTM(_PackedWeights, nn.Module):
             with torch.no_grad():
                 d = [t.detach() for t in inputs]
                 w = {k: v.detach() for k, v in sd.items()}
-                return ops.follower_step(w, d[0], d[1], d[2], d[3], d[4], d[5], ctx_mask, drop_x, drop_h,
-                                         packed=self._packer.get(w))
-        return Fn.FollowerStepFn.apply(run_cuda, names, len(inputs), ctx_mask, drop_x, drop_h, *inputs, *params)
+                B, A = d[1].shape[0], d[1].shape[1]
+                # the step's own workspace: its intermediates are what sfb_follower_step_bwd reads
+                need = ops._lib.load().sfb_follower_step_workspace_bytes(ops.C.byref(ops.follower_dims(w, d[2].shape[1])), B, d[5].shape[1], A)
+                fwd_ws = torch.zeros(need, dtype=torch.uint8, device=d[3].device)
+                outs = ops.follower_step(w, d[0], d[1], d[2], d[3], d[4], d[5], ctx_mask, drop_x, drop_h,
+                                         packed=self._packer.get(w), workspace=fwd_ws)
+                return outs, fwd_ws
+        return Fn.FollowerStepKernelFn.apply(run_cuda, names, len(inputs), ctx_mask, drop_x, drop_h, *inputs, *params)
 
     @property
     def supports_fused_step(self) -> bool:

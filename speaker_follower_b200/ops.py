@@ -462,6 +462,57 @@ def carry_query(carry: Tensor, B: int, F: int) -> Tensor:
     return carry[:B * F].view(B, F)
 
 
+_GRAD_FIELDS = {"lstm_w_ih": "lstm.weight_ih", "lstm_w_hh": "lstm.weight_hh", "lstm_b_ih": "lstm.bias_ih", "lstm_b_hh": "lstm.bias_hh",
+                "va_w_h": "visual_attention_layer.linear_in_h.weight", "va_b_h": "visual_attention_layer.linear_in_h.bias",
+                "va_w_v": "visual_attention_layer.linear_in_v.weight", "w_in": "text_attention_layer.linear_in.weight",
+                "w_out": "text_attention_layer.linear_out.weight", "sc_w_h": "decoder2action.linear_in_h.weight",
+                "sc_b_h": "decoder2action.linear_in_h.bias", "sc_w_a": "decoder2action.linear_in_a.weight",
+                "sc_b_a": "decoder2action.linear_in_a.bias", "sc_w_out": "decoder2action.linear_out.weight",
+                "sc_b_out": "decoder2action.linear_out.bias"}
+
+
+@_on_tensor_device
+def follower_step_bwd(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, visual: Optional[Tensor], h0: Tensor, c0: Tensor,
+                      ctx: Tensor, ctx_mask: Optional[Tensor], drop_x: Optional[Tensor], drop_h: Optional[Tensor],
+                      c1: Tensor, alpha: Tensor, alpha_v: Tensor, fwd_workspace: Tensor,
+                      g_h1: Optional[Tensor], g_c1: Optional[Tensor], g_logit: Optional[Tensor],
+                      grads: Dict[str, Tensor], accumulate: bool = True, store: Optional[FeatureStore] = None,
+                      vp_idx=None, view_idx=None, cand_view=None, cand_trig=None):
+    """sfb_follower_step_bwd: hand-written backward of one decode step.  `fwd_workspace` is the workspace tensor the
+    forward call of this step ran in; `grads` maps reference state_dict names to gradient buffers (accumulated into).
+    Returns (d_h0, d_c0, d_ctx)."""
+    lib = _lib.load()
+    B, L, H = ctx.shape
+    V = visual.shape[1] if visual is not None else store.feat_table.shape[1]
+    d = follower_dims(w, V)
+    A = all_u_t.shape[1] if all_u_t is not None else cand_view.shape[1]
+    keep = []
+    vs = _visual_source(visual, store, vp_idx, view_idx, keep)
+    if all_u_t is not None:
+        act = _lib.ActionSource(_p(all_u_t, name="all_u_t"), None, None, None, None, 0)
+    else:
+        act = _lib.ActionSource(None, _p(store.feat_table), _p(_i32(vp_idx), torch.int32), _p(cand_view, torch.int32),
+                                _p(cand_trig), store.feat_table.shape[2])
+    wl, wt, wsc = _vis_lstm_weights(w), _softdot_weights(w, "text_attention_layer."), _scoring_weights(w)
+    gs = _lib.FollowerGrads()
+    for f, k in _GRAD_FIELDS.items():
+        setattr(gs, f, _p(grads.get(k), name="grad " + k))
+    dev = h0.device
+    need = lib.sfb_follower_step_bwd_workspace_bytes(C.byref(d), B, L, A)
+    ws = _workspace(need, dev, ("follower_step_bwd", B))
+    d_h0 = torch.empty(B, H, device=dev); d_c0 = torch.empty(B, H, device=dev); d_ctx = torch.empty(B, L, H, device=dev)
+    mask = _mask_u8(ctx_mask)
+    gc = lambda t: None if t is None else t.contiguous()
+    g_h1, g_c1, g_logit = gc(g_h1), gc(g_c1), gc(g_logit)
+    check(lib.sfb_follower_step_bwd(
+        C.byref(d), C.byref(wl), C.byref(wt), C.byref(wsc), B, L, A, _p(u_prev, name="u_t_prev"), C.byref(act), C.byref(vs),
+        _p(h0, name="h_0"), _p(c0, name="c_0"), _p(ctx, name="ctx"), _p(mask, torch.uint8, "ctx_mask"), _p(drop_x), _p(drop_h),
+        _p(c1, name="c_1"), _p(alpha, name="alpha"), _p(alpha_v, name="alpha_v"), fwd_workspace.data_ptr(),
+        _p(g_h1), _p(g_c1), _p(g_logit), _p(d_h0), _p(d_c0), _p(d_ctx), C.byref(gs), 1 if accumulate else 0,
+        ws.data_ptr(), ws.numel(), _stream()))
+    return d_h0, d_c0, d_ctx
+
+
 def ctx_rows(lengths, L: int, device) -> Tensor:
     """Flat (b*L + l) indices of the un-padded positions of a padded [B, L] batch (int32, on `device`)."""
     idx = [b * L + l for b, n in enumerate(lengths) for l in range(min(int(n), L))]

@@ -38,6 +38,40 @@ def test_reference_gradients_small_train_golden():
         close(wc[k].grad, rest["gw." + k], 1e-4, "gw." + k)
 
 
+def test_kernel_backward_reproduces_reference_gradients_small_train_golden():
+    """The hand-written backward (sfb_follower_step_bwd, backward.cu — no torch op computes a gradient) against the
+    gradients the REFERENCE's own modules produced for the same inputs, dropout masks and cotangents."""
+    import ctypes as C
+    w, x, out, rest = split_golden(load_golden("follower_step_small_train"))
+    names = list(w.keys())
+    wc = {k: v.cuda().requires_grad_(True) for k, v in w.items()}
+    xin = [x[k].cuda().requires_grad_(True) for k in IN]
+    mask, dx, dh = x["ctx_mask"].cuda(), rest["drop.x"].cuda(), rest["drop.h"].cuda()
+    B, A = xin[1].shape[0], xin[1].shape[1]
+
+    def run_cuda():
+        with torch.no_grad():
+            wd = {k: v.detach() for k, v in wc.items()}
+            d = ops.follower_dims(wd, xin[2].shape[1])
+            need = ops._lib.load().sfb_follower_step_workspace_bytes(C.byref(d), B, xin[5].shape[1], A)
+            fwd_ws = torch.zeros(need, dtype=torch.uint8, device="cuda")
+            return ops.follower_step(wd, *[t.detach() for t in xin], mask, dx, dh, workspace=fwd_ws), fwd_ws
+    res = Fn.FollowerStepKernelFn.apply(run_cuda, names, len(xin), mask, dx, dh, *xin, *[wc[k] for k in names])
+    for k, v in zip(NAMES, res):
+        close(v, out[k], what="fwd:" + k)
+    loss = (res[0] * rest["cot.h_1"].cuda()).sum() + (res[1] * rest["cot.c_1"].cuda()).sum() + \
+           (res[3] * rest["cot.logit"].cuda()).sum()
+    loss.backward()
+    for k, t in zip(IN, xin):
+        if k in ("h_0", "c_0", "ctx"):                     # u_t_prev / candidates / slab are constants of the step
+            close(t.grad, rest["gin." + k], 5e-5, "gin." + k)
+    for k in names:
+        if k == "visual_attention_layer.linear_in_v.bias":  # cancels in the softmax: the reference's gradient is ~0 too
+            assert rest["gw." + k].abs().max() < 1e-6
+            continue
+        close(wc[k].grad, rest["gw." + k], 1e-4, "gw." + k)
+
+
 def test_module_gradients_match_oracle_autograd_full_size():
     """nn.Module level (eval mode: no dropout), reference dimensions, packed forward: grads == autograd through the oracle."""
     B, L, A = 8, 20, 6
