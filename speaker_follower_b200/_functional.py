@@ -74,7 +74,7 @@ class FollowerStepKernelFn(torch.autograd.Function):
         params = saved[n_in:n_in + len(names)]
         c1, alpha, alpha_v = saved[n_in + len(names):]
         w = {k: p.detach() for k, p in zip(names, params)}
-        grads = {k: torch.zeros_like(p) for k, p in w.items() if k != "visual_attention_layer.linear_in_v.bias"}
+        grads = {k: torch.zeros_like(p) for k, p in w.items()}   # linear_in_v.bias stays zero: it cancels in the softmax
         with torch.no_grad():
             d_h0, d_c0, d_ctx = ops.follower_step_bwd(w, u.detach(), U.detach(), V.detach(), h0.detach(), c0.detach(), c.detach(),
                                                        ctx_.ctx_mask, ctx_.drop_x, ctx_.drop_h, c1, alpha, alpha_v, ctx_.fwd_ws,
