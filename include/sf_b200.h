@@ -334,6 +334,26 @@ typedef struct sfb_encoder_weights {
 
 size_t sfb_encoder_lstm_workspace_bytes(int32_t ndir, int32_t Hd, int32_t Ew, int32_t B, int32_t maxlen);
 
+/* Training (autograd of EncoderLSTM.forward, model.py:81-104, unidirectional): sfb_encoder_lstm_train_fwd is the same
+ * forward that additionally keeps a TAPE (activated gates and the (h, c) state around every time step, caller-owned,
+ * sfb_encoder_lstm_tape_bytes); sfb_encoder_lstm_bwd back-propagates through time over it, hand-written:
+ *   g_ctx [B,maxlen,H] / g_decoder_init [B,H] / g_c_t [B,H]: upstream gradients (NULL = zero);
+ *   grads: state_dict layouts (lstm.weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, encoder2decoder.weight/.bias),
+ *   accumulated when accumulate != 0.  The embedding is frozen GloVe in the reference configuration (model.py:58-60)
+ *   and receives no gradient here. */
+typedef struct sfb_encoder_grads { float *w_ih, *w_hh, *b_ih, *b_hh, *e2d_w, *e2d_b; } sfb_encoder_grads;
+size_t  sfb_encoder_lstm_tape_bytes(int32_t Hd, int32_t B, int32_t maxlen);
+int32_t sfb_encoder_lstm_train_fwd(const sfb_encoder_weights* w, int32_t Hd, int32_t Ew, int32_t B, int32_t maxlen,
+                                   const int32_t* seq, const int32_t* lengths, const float* drop_embed,
+                                   float* ctx, float* decoder_init, float* c_t, void* tape, size_t tape_bytes,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+size_t  sfb_encoder_lstm_bwd_workspace_bytes(int32_t Hd, int32_t Ew, int32_t B, int32_t maxlen);
+int32_t sfb_encoder_lstm_bwd(const sfb_encoder_weights* w, int32_t Hd, int32_t Ew, int32_t B, int32_t maxlen,
+                             const int32_t* seq, const int32_t* lengths, const float* drop_embed, const void* tape,
+                             const float* decoder_init, const float* g_ctx, const float* g_decoder_init, const float* g_c_t,
+                             const sfb_encoder_grads* grads, int32_t accumulate,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t Hd, int32_t Ew, int32_t B,
                              int32_t maxlen, const int32_t* seq, const int32_t* lengths, const float* drop_embed,
                              float* ctx, float* decoder_init, float* c_t,

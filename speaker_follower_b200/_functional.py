@@ -86,6 +86,32 @@ class FollowerStepKernelFn(torch.autograd.Function):
         return (None, None, None, None, None, None, *gin, *gpar)
 
 
+class EncoderLstmKernelFn(torch.autograd.Function):
+    """EncoderLSTM.forward (model.py:81-104, unidirectional) forward AND backward on the library: the forward keeps a
+    tape of every time step, sfb_encoder_lstm_bwd back-propagates through time over it (backward.cu + skinny GEMMs)."""
+
+    @staticmethod
+    def forward(ctx_, seq, lengths, drop_embed, names, *params):
+        from . import ops
+        w = {k: p.detach() for k, p in zip(names, params)}
+        with torch.no_grad():
+            ctx, dec, c_t, saved = ops.encoder_lstm_train(w, seq, lengths, drop_embed)
+        ctx_.names, ctx_.saved, ctx_.drop_embed = names, saved, drop_embed
+        ctx_.save_for_backward(dec, *params)
+        return ctx, dec, c_t
+
+    @staticmethod
+    def backward(ctx_, g_ctx, g_dec, g_c):
+        from . import ops
+        dec, *params = ctx_.saved_tensors
+        w = {k: p.detach() for k, p in zip(ctx_.names, params)}
+        grads = {k: torch.zeros_like(p) for k, p in w.items() if k != "embedding.weight"}
+        with torch.no_grad():
+            ops.encoder_lstm_bwd(w, ctx_.saved, dec, g_ctx, g_dec, g_c, grads, ctx_.drop_embed)
+        need = ctx_.needs_input_grad[4:]
+        return (None, None, None, None, *[(grads.get(k) if nd else None) for k, nd in zip(ctx_.names, need)])
+
+
 class FollowerStepFn(torch.autograd.Function):
     """Forward on the CUDA kernels, backward by torch autograd over the restatement above (same inputs, same masks).
     Kept as the independent check of FollowerStepKernelFn in tests/test_gpu_train.py."""

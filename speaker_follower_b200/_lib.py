@@ -68,6 +68,10 @@ class NavTables(C.Structure):
                 ("next", c_int_p), ("teach", c_int_p), ("S", C.c_int32), ("A", C.c_int32), ("G", C.c_int32)]
 
 
+class EncoderGrads(C.Structure):
+    _fields_ = [(n, c_float_p) for n in ("w_ih", "w_hh", "b_ih", "b_hh", "e2d_w", "e2d_b")]
+
+
 class FollowerGrads(C.Structure):
     _fields_ = [(n, c_float_p) for n in ("lstm_w_ih", "lstm_w_hh", "lstm_b_ih", "lstm_b_hh", "va_w_h", "va_b_h", "va_w_v",
                                          "w_in", "w_out", "sc_w_h", "sc_b_h", "sc_w_a", "sc_b_a", "sc_w_out", "sc_b_out")]
@@ -112,6 +116,14 @@ SIGNATURES = {
                                                  c_float_p, c_float_p,
                                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_follower_carry_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32]),
+    "sfb_encoder_lstm_tape_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "sfb_encoder_lstm_train_fwd": (C.c_int32, [C.POINTER(EncoderWeights), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                               c_int_p, c_int_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                               C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sfb_encoder_lstm_bwd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "sfb_encoder_lstm_bwd": (C.c_int32, [C.POINTER(EncoderWeights), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         c_int_p, c_int_p, c_float_p, C.c_void_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                         C.POINTER(EncoderGrads), C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_follower_step_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32, C.c_int32, C.c_int32]),
     "sfb_follower_step_bwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(VisLstmWeights), C.POINTER(SoftDotWeights),
                                           C.POINTER(ScoringWeights), C.c_int32, C.c_int32, C.c_int32,

@@ -575,10 +575,49 @@ size_t sfb_encoder_lstm_workspace_bytes(int32_t ndir, int32_t Hd, int32_t Ew, in
   return carve_encoder(ndir, Hd, Ew, B, maxlen, nullptr).bytes;
 }
 
+// tape of a training forward (unidirectional): activated gates of every time step and the (h, c) state before / after it
+struct EncTape { float* gates; float* h; float* c; size_t bytes; };
+static EncTape carve_enc_tape(int Hd, int B, int maxlen, void* p) {
+  EncTape t;
+  Carver c(p);
+  t.gates = c.take((size_t)maxlen * B * 4 * Hd);
+  t.h = c.take((size_t)(maxlen + 1) * B * Hd);
+  t.c = c.take((size_t)(maxlen + 1) * B * Hd);
+  t.bytes = c.off;
+  return t;
+}
+
+static int32_t encoder_fwd_impl(const sfb_encoder_weights* w, int32_t ndir, int32_t Hd, int32_t Ew, int32_t B,
+                                int32_t maxlen, const int32_t* seq, const int32_t* lengths, const float* drop_embed,
+                                float* ctx, float* decoder_init, float* c_t, void* workspace, size_t workspace_bytes,
+                                void* stream, void* tape_mem);
+
 int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t Hd, int32_t Ew, int32_t B,
                              int32_t maxlen, const int32_t* seq, const int32_t* lengths, const float* drop_embed,
                              float* ctx, float* decoder_init, float* c_t, void* workspace, size_t workspace_bytes,
                              void* stream) {
+  return encoder_fwd_impl(w, ndir, Hd, Ew, B, maxlen, seq, lengths, drop_embed, ctx, decoder_init, c_t, workspace, workspace_bytes,
+                          stream, nullptr);
+}
+
+size_t sfb_encoder_lstm_tape_bytes(int32_t Hd, int32_t B, int32_t maxlen) {
+  if (Hd < 1 || B < 1 || maxlen < 1) return 0;
+  return carve_enc_tape(Hd, B, maxlen, nullptr).bytes;
+}
+
+int32_t sfb_encoder_lstm_train_fwd(const sfb_encoder_weights* w, int32_t Hd, int32_t Ew, int32_t B, int32_t maxlen,
+                                   const int32_t* seq, const int32_t* lengths, const float* drop_embed, float* ctx,
+                                   float* decoder_init, float* c_t, void* tape, size_t tape_bytes, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  SFB_CHECK_ARG(tape && (reinterpret_cast<uintptr_t>(tape) & 255u) == 0 && tape_bytes >= sfb_encoder_lstm_tape_bytes(Hd, B, maxlen),
+                "encoder tape missing, misaligned or too small");
+  return encoder_fwd_impl(w, 1, Hd, Ew, B, maxlen, seq, lengths, drop_embed, ctx, decoder_init, c_t, workspace, workspace_bytes, stream, tape);
+}
+
+static int32_t encoder_fwd_impl(const sfb_encoder_weights* w, int32_t ndir, int32_t Hd, int32_t Ew, int32_t B,
+                                int32_t maxlen, const int32_t* seq, const int32_t* lengths, const float* drop_embed,
+                                float* ctx, float* decoder_init, float* c_t, void* workspace, size_t workspace_bytes,
+                                void* stream, void* tape_mem) {
   reset_launch_count();
   SFB_CHECK_ARG(w && seq && lengths && ctx && decoder_init && c_t, "NULL argument");
   SFB_CHECK_ARG(ndir == 1 || ndir == 2, "ndir must be 1 or 2");
@@ -590,6 +629,15 @@ int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t
   const size_t state = (size_t)B * Hd;
   SFB_CHECK_CUDA(cudaMemsetAsync(ws.h[0], 0, ndir * state * sizeof(float), st));
   SFB_CHECK_CUDA(cudaMemsetAsync(ws.c[0], 0, ndir * state * sizeof(float), st));
+  EncTape tape{};
+  const bool taped = tape_mem != nullptr;
+  if (taped) {
+    SFB_CHECK_ARG(ndir == 1, "the training tape covers the unidirectional encoder");
+    tape = carve_enc_tape(Hd, B, maxlen, tape_mem);
+    SFB_CHECK_CUDA(cudaMemsetAsync(tape.h, 0, state * sizeof(float), st));
+    SFB_CHECK_CUDA(cudaMemsetAsync(tape.c, 0, state * sizeof(float), st));
+    SFB_CHECK_CUDA(cudaMemsetAsync(tape.gates, 0, (size_t)maxlen * B * 4 * Hd * sizeof(float), st));   // rows past their length stay zero
+  }
   int cur[2] = {0, 0};
   // recurrent projection on tcgen05 from packed W_hh (gemm_pk.cu): pack once per call, then one launch per time step
   const bool use_pk = !g_disable_tc && (Hd % 32) == 0 && (Hd % 8) == 0 &&
@@ -627,10 +675,10 @@ int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t
     }
     for (int s = 0; s < maxlen; ++s) {
       const int t = dir == 0 ? s : maxlen - 1 - s;
-      float* hp = ws.h[cur[dir]] + dir * state;
-      float* cp = ws.c[cur[dir]] + dir * state;
-      float* hn = ws.h[cur[dir] ^ 1] + dir * state;
-      float* cn = ws.c[cur[dir] ^ 1] + dir * state;
+      float* hp = taped ? tape.h + (size_t)s * state : ws.h[cur[dir]] + dir * state;
+      float* cp = taped ? tape.c + (size_t)s * state : ws.c[cur[dir]] + dir * state;
+      float* hn = taped ? tape.h + (size_t)(s + 1) * state : ws.h[cur[dir] ^ 1] + dir * state;
+      float* cn = taped ? tape.c + (size_t)(s + 1) * state : ws.c[cur[dir] ^ 1] + dir * state;
       GemmParams r{};
       r.nseg = 1;
       r.seg[0] = GemmSeg{hp, Hd, nullptr, nullptr, 0, w->w_hh[dir], Hd, Hd, 0};
@@ -641,6 +689,7 @@ int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t
       p.addend = xp + (size_t)t * 4 * Hd; p.ld_addend = (long long)maxlen * 4 * Hd;
       p.lengths = lengths; p.t = t;
       p.seq_out = ctx + (size_t)t * H + dir * Hd; p.ld_seq_out = (long long)maxlen * H;
+      if (taped) p.gates_act = tape.gates + (size_t)s * B * 4 * Hd;
       if (use_pk) {
         PkParams q{};
         q.g = r;
@@ -656,9 +705,11 @@ int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t
   }
   // decoder_init = tanh(encoder2decoder(h_t)), h_t = cat(reverse, forward) when bidirectional (model.py:92-99)
   GemmParams e{};
+  const float* h_last = taped ? tape.h + (size_t)maxlen * state : ws.h[cur[0]];
+  const float* c_last = taped ? tape.c + (size_t)maxlen * state : ws.c[cur[0]];
   if (ndir == 1) {
     e.nseg = 1;
-    e.seg[0] = GemmSeg{ws.h[cur[0]], Hd, nullptr, nullptr, 0, w->e2d_w, H, Hd, 0};
+    e.seg[0] = GemmSeg{h_last, Hd, nullptr, nullptr, 0, w->e2d_w, H, Hd, 0};
   } else {
     e.nseg = 2;
     e.seg[0] = GemmSeg{ws.h[cur[1]] + state, Hd, nullptr, nullptr, 0, w->e2d_w, H, Hd, 0};
@@ -667,7 +718,7 @@ int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t
   e.M = B; e.N = H; e.splitk = gemm_pick_splitk(B, H, H, device_num_sms()); e.out = decoder_init; e.ldo = H; e.bias0 = w->e2d_b; e.act = 1;
   SFB_PROPAGATE(launch_gemm(e, st));
   if (ndir == 1) {
-    SFB_CHECK_CUDA(cudaMemcpyAsync(c_t, ws.c[cur[0]], state * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SFB_CHECK_CUDA(cudaMemcpyAsync(c_t, c_last, state * sizeof(float), cudaMemcpyDeviceToDevice, st));
   } else {
     SFB_CHECK_CUDA(cudaMemcpy2DAsync(c_t, (size_t)H * 4, ws.c[cur[1]] + state, (size_t)Hd * 4, (size_t)Hd * 4, B,
                                      cudaMemcpyDeviceToDevice, st));
@@ -1133,6 +1184,79 @@ int32_t outer(const float* Y, int ldy, const float* X, int ldx, int B, int N, in
 }
 }  // namespace
 
+/* ---------------------------------------------------------------- EncoderLSTM backward (BPTT over the taped forward) */
+namespace {
+struct EncBwdWs { float *dgates, *xemb, *dpre, *dh[2], *dc[2], *pass; size_t bytes; };
+EncBwdWs carve_enc_bwd(int Hd, int Ew, int B, int maxlen, void* p) {
+  EncBwdWs w;
+  Carver c(p);
+  w.dgates = c.take((size_t)maxlen * B * 4 * Hd);
+  w.xemb = c.take((size_t)maxlen * B * Ew);
+  w.dpre = c.take((size_t)B * Hd);
+  for (int i = 0; i < 2; ++i) { w.dh[i] = c.take((size_t)B * Hd); w.dc[i] = c.take((size_t)B * Hd); }
+  w.pass = c.take((size_t)B * Hd);
+  w.bytes = c.off;
+  return w;
+}
+}  // namespace
+
+size_t sfb_encoder_lstm_bwd_workspace_bytes(int32_t Hd, int32_t Ew, int32_t B, int32_t maxlen) {
+  if (Hd < 1 || Ew < 1 || B < 1 || maxlen < 1) return 0;
+  return carve_enc_bwd(Hd, Ew, B, maxlen, nullptr).bytes;
+}
+
+int32_t sfb_encoder_lstm_bwd(const sfb_encoder_weights* w, int32_t Hd, int32_t Ew, int32_t B, int32_t maxlen,
+                             const int32_t* seq, const int32_t* lengths, const float* drop_embed, const void* tape_mem,
+                             const float* decoder_init, const float* g_ctx, const float* g_decoder_init, const float* g_c_t,
+                             const sfb_encoder_grads* gr, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  reset_launch_count();
+  SFB_CHECK_ARG(w && seq && lengths && tape_mem && decoder_init && gr, "NULL argument");
+  SFB_CHECK_ARG(Hd >= 4 && (Hd % 4) == 0 && Ew >= 4 && (Ew % 4) == 0 && B >= 1 && maxlen >= 1, "bad sizes");
+  const EncTape tape = carve_enc_tape(Hd, B, maxlen, const_cast<void*>(tape_mem));
+  const EncBwdWs bw = carve_enc_bwd(Hd, Ew, B, maxlen, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, bw.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int acc = accumulate ? 1 : 0, H = Hd;
+  const size_t state = (size_t)B * Hd;
+  const float* h_last = tape.h + (size_t)maxlen * state;
+  // decoder_init = tanh(encoder2decoder(h_T))  (model.py:99)
+  int cur = 0;
+  if (g_decoder_init) {
+    SFB_PROPAGATE(launch_tanh_bwd(g_decoder_init, decoder_init, bw.dpre, B * H, st));
+    SFB_PROPAGATE(outer(bw.dpre, H, h_last, H, B, H, H, gr->e2d_w, H, acc, st));
+    if (gr->e2d_b) SFB_PROPAGATE(launch_colsum(bw.dpre, H, B, H, gr->e2d_b, acc, st));
+    SFB_PROPAGATE(bgemm(B, H, H, bw.dpre, H, w->e2d_w, H, 1, bw.dh[0], H, nullptr, nullptr, 0, st));   // dh_T = dpre W_e
+  } else {
+    SFB_CHECK_CUDA(cudaMemsetAsync(bw.dh[0], 0, state * sizeof(float), st));
+  }
+  if (g_c_t) SFB_CHECK_CUDA(cudaMemcpyAsync(bw.dc[0], g_c_t, state * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  else SFB_CHECK_CUDA(cudaMemsetAsync(bw.dc[0], 0, state * sizeof(float), st));
+  // back-propagation through time (packed sequence: a row is active at step t iff t < lengths[row], model.py:89-90)
+  for (int t = maxlen - 1; t >= 0; --t) {
+    LstmSeqBwdParams p{};
+    p.B = B; p.H = H; p.t = t; p.lengths = lengths;
+    p.gates_act = tape.gates + (size_t)t * B * 4 * H; p.c_prev = tape.c + (size_t)t * state; p.c_cur = tape.c + (size_t)(t + 1) * state;
+    p.dh_in = bw.dh[cur]; p.dc_in = bw.dc[cur];
+    p.g_out = g_ctx ? g_ctx + (size_t)t * H : nullptr; p.ld_g_out = (long long)maxlen * H;
+    p.dgates = bw.dgates + (size_t)t * B * 4 * H; p.dc_prev = bw.dc[cur ^ 1]; p.dh_pass = bw.pass;
+    SFB_PROPAGATE(launch_lstm_seq_bwd(p, st));
+    SFB_PROPAGATE(bgemm(B, H, 4 * H, p.dgates, 4 * H, w->w_hh[0], H, 1, bw.dh[cur ^ 1], H, nullptr, bw.pass, H, st));   // dh_{t-1} = dgates W_hh (+ pass-through)
+    cur ^= 1;
+  }
+  // weight gradients, batched over all time steps: dW_hh = sum_t dgates_t^T h_{t-1}, dW_ih = sum_t dgates_t^T x_t
+  const int rows = maxlen * B;
+  SFB_PROPAGATE(outer(bw.dgates, 4 * H, tape.h, H, rows, 4 * H, H, gr->w_hh, H, acc, st));
+  if (gr->w_ih) {
+    SFB_PROPAGATE(launch_gather_embed(w->embedding, Ew, seq, drop_embed, bw.xemb, B, maxlen, st));
+    SFB_PROPAGATE(outer(bw.dgates, 4 * H, bw.xemb, Ew, rows, 4 * H, Ew, gr->w_ih, Ew, acc, st));
+  }
+  if (gr->b_ih) SFB_PROPAGATE(launch_colsum(bw.dgates, 4 * H, rows, 4 * H, gr->b_ih, acc, st));
+  if (gr->b_hh) SFB_PROPAGATE(launch_colsum(bw.dgates, 4 * H, rows, 4 * H, gr->b_hh, acc, st));
+  return 0;
+}
+
+/* ---------------------------------------------------------------- follower decode step: backward (entry points) */
 size_t sfb_follower_step_bwd_workspace_bytes(const sfb_dims* dims, int32_t B, int32_t L, int32_t A) {
   (void)L; (void)A;
   if (!dims || B < 1) return 0;

@@ -114,6 +114,54 @@ int32_t launch_lstm_cell_bwd(const LstmBwdParams& p, cudaStream_t st) {
   return 0;
 }
 
+// EncoderLSTM BPTT (model.py:81-104 under autograd): one cell step of the packed sequence
+__global__ void lstm_seq_bwd_kernel(const LstmSeqBwdParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.B * p.H) return;
+  const int b = idx / p.H, j = idx - b * p.H;
+  float* dg = p.dgates + (size_t)b * 4 * p.H + j;
+  if (p.t >= p.lengths[b]) {      // the row ended before this step: its state was carried, nothing was emitted
+    dg[0] = 0.f; dg[p.H] = 0.f; dg[2 * p.H] = 0.f; dg[3 * p.H] = 0.f;
+    p.dc_prev[idx] = p.dc_in[idx];
+    p.dh_pass[idx] = p.dh_in[idx];
+    return;
+  }
+  const float* ga = p.gates_act + (size_t)b * 4 * p.H + j;
+  const float ig = ga[0], fg = ga[p.H], gt = ga[2 * p.H], og = ga[3 * p.H];
+  const float dh = p.dh_in[idx] + (p.g_out ? p.g_out[(size_t)b * p.ld_g_out + j] : 0.f);
+  const float tc = tanhf(p.c_cur[idx]);
+  const float dc = p.dc_in[idx] + dh * og * (1.f - tc * tc);
+  dg[0] = dc * gt * ig * (1.f - ig);
+  dg[p.H] = dc * p.c_prev[idx] * fg * (1.f - fg);
+  dg[2 * p.H] = dc * ig * (1.f - gt * gt);
+  dg[3 * p.H] = dh * tc * og * (1.f - og);
+  p.dc_prev[idx] = dc * fg;
+  p.dh_pass[idx] = 0.f;
+}
+int32_t launch_lstm_seq_bwd(const LstmSeqBwdParams& p, cudaStream_t st) {
+  lstm_seq_bwd_kernel<<<(p.B * p.H + 255) / 256, 256, 0, st>>>(p);
+  SFB_CHECK_LAUNCH();
+  return 0;
+}
+// out[(t*B + b), :] = embedding[seq[b, t], :] (.) drop[(b*maxlen + t), :]   (the x_t rows, in the tape's [t][b] order)
+__global__ void gather_embed_kernel(const float* emb, int Ew, const int32_t* seq, const float* drop, float* out, int B, int maxlen) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * maxlen * Ew) return;
+  const int k = (int)(i % Ew);
+  const long long r = i / Ew;
+  const int b = (int)(r % B), t = (int)(r / B);
+  const size_t m = (size_t)b * maxlen + t;
+  float v = emb[(size_t)seq[m] * Ew + k];
+  if (drop) v *= drop[m * Ew + k];
+  out[i] = v;
+}
+int32_t launch_gather_embed(const float* emb, int Ew, const int32_t* seq, const float* drop, float* out, int B, int maxlen, cudaStream_t st) {
+  const long long n = (long long)B * maxlen * Ew;
+  gather_embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(emb, Ew, seq, drop, out, B, maxlen);
+  SFB_CHECK_LAUNCH();
+  return 0;
+}
+
 // x = [u_prev | feat] (.) drop_x   (the LSTM input of model.py:391-392, needed as the right factor of dW_ih)
 __global__ void assemble_x_kernel(const float* u, const float* f, const float* drop, float* x, int B, int E, int F) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, W = E + F;

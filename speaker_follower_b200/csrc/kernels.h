@@ -291,6 +291,16 @@ struct LstmBwdParams {
   float* dgates; float* dc0;
 };
 int32_t launch_lstm_cell_bwd(const LstmBwdParams& p, cudaStream_t st);
+// EncoderLSTM BPTT cell step: rows with t >= lengths[row] pass (dh, dc) through untouched (packed sequence)
+struct LstmSeqBwdParams {
+  int B, H, t; const int32_t* lengths;
+  const float* gates_act; const float* c_prev; const float* c_cur;
+  const float* dh_in; const float* dc_in;
+  const float* g_out; long long ld_g_out;   // gradient of the emitted h_t (ctx[:, t, :]) or NULL
+  float* dgates; float* dc_prev; float* dh_pass;
+};
+int32_t launch_lstm_seq_bwd(const LstmSeqBwdParams& p, cudaStream_t st);
+int32_t launch_gather_embed(const float* emb, int Ew, const int32_t* seq, const float* drop, float* out, int B, int maxlen, cudaStream_t st);
 int32_t launch_assemble_x(const float* u, const float* f, const float* drop, float* x, int B, int E, int F, cudaStream_t st);
 struct AttnBwdParams {
   const float* segA; long long strideA_b; int strideA_r, lenA;     // rows as in AttnParams (dense or gathered)

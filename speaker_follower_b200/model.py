@@ -108,8 +108,20 @@ class EncoderLSTM(nn.Module):
 
 
     def _forward_autograd(self, inputs, lengths):
-        """Training: the once-per-rollout encoder runs on torch's own LSTM (cuDNN) so that autograd reaches its weights
-        — model.py:81-104 verbatim; the inference path above stays on the sm_100a kernels."""
+        """Training.  Unidirectional (the reference default, train.py:194) with frozen GloVe: forward on the sm_100a kernels
+        with a tape, backward by the hand-written BPTT (sfb_encoder_lstm_bwd) through _functional.EncoderLstmKernelFn.
+        Otherwise (bidirectional, or a trainable embedding table): torch's own LSTM, model.py:81-104 verbatim."""
+        if self.num_directions == 1 and not self.embedding.weight.requires_grad:
+            B = inputs.size(0)
+            maxlen = int(max(int(x) for x in lengths))
+            drop_e = None
+            if not self.use_glove:
+                drop_e = self._drop.mask(self.training, (B * maxlen, self.embedding_size), inputs.device)
+            sd = _sd(self)
+            names = list(sd.keys())
+            ctx, decoder_init, c_t = Fn.EncoderLstmKernelFn.apply(inputs, [int(x) for x in lengths], drop_e, names, *[sd[k] for k in names])
+            m = self._drop.mask(self.training, ctx.shape, ctx.device)
+            return (ctx * m if m is not None else ctx), decoder_init, c_t
         embeds = self.embedding(inputs)
         if not self.use_glove:
             embeds = self.drop(embeds)

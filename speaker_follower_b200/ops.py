@@ -669,6 +669,61 @@ def encoder_lstm(w: Dict[str, Tensor], seq: Tensor, lengths, bidirectional: bool
     return ctx, dec, c_t
 
 
+def _encoder_weights(w: Dict[str, Tensor], ndir: int) -> EncoderWeights:
+    ew = EncoderWeights()
+    ew.embedding = _p(w["embedding.weight"])
+    for i, suf in enumerate(["_l0", "_l0_reverse"][:ndir]):
+        ew.w_ih[i] = _p(w["lstm.weight_ih" + suf]); ew.w_hh[i] = _p(w["lstm.weight_hh" + suf])
+        ew.b_ih[i] = _p(w["lstm.bias_ih" + suf]); ew.b_hh[i] = _p(w["lstm.bias_hh" + suf])
+    ew.e2d_w = _p(w["encoder2decoder.weight"]); ew.e2d_b = _p(w["encoder2decoder.bias"])
+    return ew
+
+
+@_on_tensor_device
+def encoder_lstm_train(w: Dict[str, Tensor], seq: Tensor, lengths, drop_embed: Optional[Tensor] = None):
+    """sfb_encoder_lstm_train_fwd (unidirectional): forward that keeps the tape sfb_encoder_lstm_bwd needs.
+    -> (ctx, decoder_init, c_t, saved) with saved = (tape, seq32, lens_d, maxlen)."""
+    lib = _lib.load()
+    dev = seq.device
+    Hd = w["lstm.weight_hh_l0"].shape[1]
+    Ew = w["embedding.weight"].shape[1]
+    B = seq.shape[0]
+    lens = torch.as_tensor([int(x) for x in lengths], dtype=torch.int32)
+    maxlen = int(lens.max())
+    seq32 = seq[:, :maxlen].to(torch.int32).contiguous()
+    lens_d = lens.to(dev)
+    ew = _encoder_weights(w, 1)
+    need = lib.sfb_encoder_lstm_workspace_bytes(1, Hd, Ew, B, maxlen)
+    ws = _workspace(need, dev, ("encoder_lstm", 1, Hd, Ew, B, maxlen))
+    tape = torch.empty(lib.sfb_encoder_lstm_tape_bytes(Hd, B, maxlen), dtype=torch.uint8, device=dev)
+    ctx = torch.empty(B, maxlen, Hd, device=dev); dec = torch.empty(B, Hd, device=dev); c_t = torch.empty(B, Hd, device=dev)
+    check(lib.sfb_encoder_lstm_train_fwd(C.byref(ew), Hd, Ew, B, maxlen, _p(seq32, torch.int32, "seq"), _p(lens_d, torch.int32, "lengths"),
+                                         _p(drop_embed, name="drop_embed"), _p(ctx), _p(dec), _p(c_t), tape.data_ptr(), tape.numel(),
+                                         ws.data_ptr(), ws.numel(), _stream()))
+    return ctx, dec, c_t, (tape, seq32, lens_d, maxlen)
+
+
+@_on_tensor_device
+def encoder_lstm_bwd(w: Dict[str, Tensor], saved, decoder_init: Tensor, g_ctx, g_dec, g_c, grads: Dict[str, Tensor],
+                     drop_embed: Optional[Tensor] = None, accumulate: bool = False) -> None:
+    """sfb_encoder_lstm_bwd: hand-written BPTT over the tape of encoder_lstm_train; fills `grads` (state_dict names)."""
+    lib = _lib.load()
+    tape, seq32, lens_d, maxlen = saved
+    Hd = w["lstm.weight_hh_l0"].shape[1]
+    Ew = w["embedding.weight"].shape[1]
+    B = seq32.shape[0]
+    ew = _encoder_weights(w, 1)
+    gs = _lib.EncoderGrads(_p(grads.get("lstm.weight_ih_l0")), _p(grads.get("lstm.weight_hh_l0")), _p(grads.get("lstm.bias_ih_l0")),
+                           _p(grads.get("lstm.bias_hh_l0")), _p(grads.get("encoder2decoder.weight")), _p(grads.get("encoder2decoder.bias")))
+    need = lib.sfb_encoder_lstm_bwd_workspace_bytes(Hd, Ew, B, maxlen)
+    ws = _workspace(need, seq32.device, ("encoder_lstm_bwd", Hd, Ew, B, maxlen))
+    gc = lambda t: None if t is None else t.contiguous()
+    g_ctx, g_dec, g_c = gc(g_ctx), gc(g_dec), gc(g_c)
+    check(lib.sfb_encoder_lstm_bwd(C.byref(ew), Hd, Ew, B, maxlen, _p(seq32, torch.int32), _p(lens_d, torch.int32), _p(drop_embed),
+                                   tape.data_ptr(), _p(decoder_init), _p(g_ctx), _p(g_dec), _p(g_c), C.byref(gs),
+                                   1 if accumulate else 0, ws.data_ptr(), ws.numel(), _stream()))
+
+
 @_on_tensor_device
 def speaker_encoder_step(w: Dict[str, Tensor], action_embedding: Tensor, visual: Optional[Tensor], h0: Tensor,
                          c0: Tensor, drop_x: Optional[Tensor] = None, store=None, vp_idx=None, view_idx=None,

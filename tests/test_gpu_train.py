@@ -162,3 +162,28 @@ def test_speaker_train_iteration_and_gradients():
         env.reset_epoch()
         spk.train(eo, do, 1)
     assert spk.losses[-1] < first
+
+
+def test_encoder_kernel_backward_matches_oracle_autograd():
+    """EncoderLSTM under autograd (model.py:81-104): taped forward + hand-written BPTT (sfb_encoder_lstm_bwd) against torch
+    autograd through the CPU oracle — ragged lengths, all three outputs carrying gradient, no cuDNN involved."""
+    B, L = 12, 20
+    we = synth.follower_encoder_weights()
+    seq, mask, lengths = synth.instruction_batch(B, L, seed=5)
+    enc = M.EncoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0, 0.0, glove=we["embedding.weight"].numpy()).cuda().train()
+    enc.load_state_dict(we)
+    g = torch.Generator().manual_seed(3)
+    maxlen = max(lengths)
+    cots = [torch.randn(B, maxlen, synth.HID, generator=g), torch.randn(B, synth.HID, generator=g), torch.randn(B, synth.HID, generator=g)]
+    ctx, dec, c = enc(seq.cuda(), lengths)
+    assert ctx.grad_fn is not None and "EncoderLstmKernelFn" in type(ctx.grad_fn).__name__
+    ((ctx * cots[0].cuda()).sum() + (dec * cots[1].cuda()).sum() + (c * cots[2].cuda()).sum()).backward()
+    wr = {k: v.clone().requires_grad_(k != "embedding.weight") for k, v in we.items()}
+    rc, rd, rct = O.encoder_lstm(seq[:, :maxlen], lengths, wr)
+    ((rc * cots[0]).sum() + (rd * cots[1]).sum() + (rct * cots[2]).sum()).backward()
+    close(ctx, rc, what="ctx"); close(dec, rd, what="decoder_init"); close(c, rct, what="c_t")
+    for k, p in enc.named_parameters():
+        if not p.requires_grad:
+            continue
+        scale = max(1.0, float(wr[k].grad.abs().max()))
+        close(p.grad / scale, wr[k].grad / scale, 1e-4, "d " + k)
