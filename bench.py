@@ -726,6 +726,103 @@ def run_pragmatic(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------- C2 (BASELINE.json configs[1]: training step)
+def run_train(args, rank, local_rank, world):
+    """--config c2: one follower training iteration = encoder forward, 10 teacher-forced decode steps with dropout 0.5,
+    summed cross-entropy, backward through everything, Adam step (follower.py:1001-1020) at B=100, L=80.  Forward AND
+    backward run on this library's kernels (hand-written backward: backward.cu); torch contributes the loss terms, the
+    gradient accumulation of autograd and the optimizer."""
+    import __graft_entry__ as ge
+    ge.build()
+    from speaker_follower_b200 import model as M, synth
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    T = POOL
+    glove = synth.follower_encoder_weights()["embedding.weight"].numpy()
+    enc = M.EncoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0, 0.5, glove=glove).to(dev).train()
+    dec = M.AttnDecoderLSTM(synth.FEAT, synth.HID, 0.5).to(dev).train()
+    enc.load_state_dict(synth.follower_encoder_weights()); dec.load_state_dict(synth.follower_decoder_weights())
+    eo = torch.optim.Adam([p for p in enc.parameters() if p.requires_grad], lr=1e-4)
+    do = torch.optim.Adam(dec.parameters(), lr=1e-4)
+    seq, mask, lengths = synth.instruction_batch(B, L, seed=41)
+    seq, mask = seq.to(dev), mask.to(dev)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    steps = []
+    for t in range(T):
+        x = synth.follower_step_inputs(B, L, A, seed=300 + t, n_viewpoints=256)
+        steps.append({"U": x["all_u_t"].to(dev), "V": x["visual_context"].to(dev), "valid": x["is_valid"].to(dev),
+                      "target": torch.randint(0, 2, (B,), device=dev, generator=g)})
+
+    def iteration():
+        eo.zero_grad(set_to_none=True); do.zero_grad(set_to_none=True)
+        ctx, h, c = enc(seq, lengths)
+        u = dec.u_begin.expand(B, -1)
+        loss = torch.zeros((), device=dev)
+        for st in steps:
+            h, c, alpha, logit, av = dec(u, st["U"], st["V"], h, c, ctx, mask)
+            lg = logit.masked_fill(st["valid"] == 0, -float("inf"))
+            loss = loss + torch.nn.functional.cross_entropy(lg, st["target"])
+            u = st["U"][torch.arange(B, device=dev), st["target"]].detach()
+        loss.backward()
+        eo.step(); do.step()
+        return loss
+
+    for _ in range(max(3, min(args.warmup, 5))):
+        iteration()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    n = max(5, min(args.steps, 30))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        loss = iteration()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    t = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        # the reference's CPU path for the same iteration (oracle port of model.py under torch autograd), bounded sample
+        cpu_ms = None
+        try:
+            from oracle import r2r_oracle as O
+            we = {k: v.clone().requires_grad_(k != "embedding.weight") for k, v in synth.follower_encoder_weights().items()}
+            wd = {k: v.clone().requires_grad_(True) for k, v in synth.follower_decoder_weights().items()}
+            cs = [{k: v.cpu() for k, v in st.items()} for st in steps[:T]]
+            t0 = time.perf_counter(); reps = 0
+            while time.perf_counter() - t0 < 10.0 and reps < 3:
+                ctxc, hc, cc = O.encoder_lstm(seq.cpu()[:, :max(lengths)], lengths, we)
+                uc = torch.zeros(B, synth.FEAT)
+                lc = torch.zeros(())
+                for st in cs:
+                    hc, cc, _, lg, _ = O.attn_decoder_step(uc, st["U"], st["V"], hc, cc, ctxc, mask.cpu(), wd)
+                    lc = lc + torch.nn.functional.cross_entropy(lg.masked_fill(st["valid"] == 0, -float("inf")), st["target"])
+                    uc = st["U"][torch.arange(B), st["target"]]
+                lc.backward()
+                reps += 1
+            cpu_ms = (time.perf_counter() - t0) * 1e3 / max(reps, 1)
+        except Exception as e:  # pragma: no cover
+            cpu_ms = None
+        line = {"metric": "follower training iterations/sec", "value": world * 1e3 / ms, "unit": "iter/s", "n_gpus": world, "steps": n,
+                "warmup": max(3, min(args.warmup, 5)), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "C2: follower training iteration, B=%d, L=%d, %d teacher-forced decode steps, dropout 0.5, "
+                                       "encoder + decoder forward and hand-written backward, Adam step" % (B, L, T),
+                           "batch": B, "instr_len": L, "actions": A},
+                "final_loss": float(loss),
+                "cpu_baseline": {"value": (1e3 / cpu_ms) if cpu_ms else None, "unit": "iter/s", "ms_per_iter": cpu_ms, "cores": torch.get_num_threads(),
+                                 "kind": "port", "sample": "the same iteration (fwd + bwd, no optimizer) through the torch-CPU oracle port under autograd"}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -744,6 +841,8 @@ def main():
         run_reference(args, rank, world)
     elif args.config in ("c4", "c5"):
         run_pragmatic(args, rank, local_rank, world)
+    elif args.config == "c2":
+        run_train(args, rank, local_rank, world)
     else:
         run_gpu(args, rank, local_rank, world)
 

@@ -268,8 +268,17 @@ class AttnDecoderLSTM(_PackedWeights, nn.Module):
                 # the step's own workspace: its intermediates are what sfb_follower_step_bwd reads
                 need = ops._lib.load().sfb_follower_step_workspace_bytes(ops.C.byref(ops.follower_dims(w, d[2].shape[1])), B, d[5].shape[1], A)
                 fwd_ws = torch.zeros(need, dtype=torch.uint8, device=d[3].device)
+                packed = self._packer.get(w)
+                # per-episode projections of ctx (constant over the steps of a rollout): computed once per (ctx, weights)
+                cproj = None
+                if packed is not None:
+                    key = (d[5].data_ptr(), d[5]._version, tuple(d[5].shape), self._packer.key)
+                    if getattr(self, "_cproj_key", None) != key:
+                        self._cproj = ops.follower_project_ctx(w, packed, d[5])
+                        self._cproj_key = key
+                    cproj = self._cproj
                 outs = ops.follower_step(w, d[0], d[1], d[2], d[3], d[4], d[5], ctx_mask, drop_x, drop_h,
-                                         packed=self._packer.get(w), workspace=fwd_ws)
+                                         packed=packed, workspace=fwd_ws, ctx_proj=cproj)
                 return outs, fwd_ws
         return Fn.FollowerStepKernelFn.apply(run_cuda, names, len(inputs), ctx_mask, drop_x, drop_h, *inputs, *params)
 
