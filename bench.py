@@ -26,7 +26,7 @@ import torch  # noqa: E402
 
 B, L, A = 100, 80, 8
 N_VIEWPOINTS = 10567          # R2R viewpoints -> 3.1 GB table, >> L2
-ATTN_NCU_TRAFFIC = 32172544   # dram__bytes_read.sum + dram__bytes_write.sum of one attention launch (ncu --set full)
+ATTN_NCU_TRAFFIC = 74742528   # dram__bytes_read.sum + dram__bytes_write.sum of one vis_lstm_fused_kernel launch (ncu --set full, cold)
 POOL = 10                     # per-step input sets = the steps of one episode (episode_len = 10, train.py:29)
 N_CTX = 4                     # rotating episodes: instruction contexts (16 MB each + 32 MB of per-episode projections)
 
@@ -570,25 +570,33 @@ def run_gpu(args, rank, local_rank, world):
             log("agent level: %.0f steps/s on the device, %.0f steps/s host loop" % (dev_sps, host_sps))
         except Exception as e:  # the agent numbers are an extra: never lose the headline line over them
             agent_stats = {"error": repr(e)}
-    # ---- roofline of the attention-gather kernel, timed alone with CUDA events on its launch stream;
-    # every launch reads a different random set of slabs from the 3.1 GB table (inputs >> L2).
-    q = torch.randn(B, F, device=dev, generator=g) * 0.05
+    # ---- roofline of the dominant kernel (vis_lstm_fused_kernel: attention gather + gate GEMM + LSTM cell), timed alone
+    # with CUDA events on its launch stream; every launch reads a different random set of slabs from the 3.1 GB table
+    # (inputs >> L2) and the step-invariant LSTM weights (35.7 + 4.2 MB fp32), which may be L2-resident as in a rollout.
     feat = torch.empty(B, F, device=dev)
     n_attn = 400
     vps = [torch.randint(0, N_VIEWPOINTS, (B,), device=dev, dtype=torch.int32, generator=g) for _ in range(n_attn)]
+    hh1, cc1 = torch.empty(B, H, device=dev), torch.empty(B, H, device=dev)
+
+    def ka(i):
+        if blob is not None:
+            ops.follower_gather_lstm(w, blob, qbuf[0], cbuf[0], store=store, vp_idx=vps[i], view_idx=view[0],
+                                     out=(hh1, cc1, alpha_v), workspace=ws)
+        else:
+            ops.visual_attention_core(torch.zeros(B, F, device=dev), None, store=store, vp_idx=vps[i], view_idx=view[0],
+                                      out=(feat, alpha_v), workspace=ws)
     for i in range(5):
-        ops.visual_attention_core(q, None, store=store, vp_idx=vps[i], view_idx=view[0], out=(feat, alpha_v), workspace=ws)
+        ka(i)
     torch.cuda.synchronize()
-    # average launch duration over a timed region of n_attn launches on the launch stream (CUDA events around the
-    # region, a synchronize on both sides); every launch gathers a fresh random set of slabs (12.5 GB touched in total)
     ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ea.record()
     for i in range(n_attn):
-        ops.visual_attention_core(q, None, store=store, vp_idx=vps[i], view_idx=view[0], out=(feat, alpha_v), workspace=ws)
+        ka(i)
     eb.record()
     torch.cuda.synchronize()
     attn_ms = ea.elapsed_time(eb) / n_attn
-    attn_bytes = 4 * B * 36 * F
+    lstm_w_bytes = 4 * (4 * H * (E + F) + 4 * H * H + 8 * H)
+    attn_bytes = 4 * B * 36 * F + (lstm_w_bytes if blob is not None else 0) + (4 * B * (E + 4 * H) if blob is not None else 0)
     hbm_peak, peak_src = peaks()
     attn_gbs = attn_bytes / (attn_ms * 1e-3) / 1e9
     step_bytes = algorithmic_bytes(E, F, H, n_params)
@@ -610,12 +618,13 @@ def run_gpu(args, rank, local_rank, world):
                     "steps": e2e_steps},
             "agent": agent_stats,
             "gpu_launches": launches_per_step[0] * args.steps + proj_launches * (args.steps // POOL + (1 if args.steps % POOL else 0)),
-            "roofline": {"kernel": "soft_dot_attn_kernel (36-view attention gather)", "bound": "hbm",
+            "roofline": {"kernel": "vis_lstm_fused_kernel (36-view attention gather + gate GEMM + LSTM cell, one launch)", "bound": "hbm",
                          "achieved": attn_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": attn_gbs / hbm_peak,
                          "traffic": ATTN_NCU_TRAFFIC, "peak_source": peak_src, "bytes_per_launch": attn_bytes,
                          "us_per_launch": attn_ms * 1e3,
-                         "how": "%d back-to-back launches between two CUDA events, fresh slabs per launch; traffic = dram read+write "
-                                "per launch from profiles/r01_attn_ncu_full.txt" % n_attn},
+                         "how": "%d back-to-back launches between two CUDA events, fresh slabs per launch; algorithmic bytes = slabs "
+                                "4*B*36*F + fp32 LSTM weights 4*(4H*(E+F)+4H*H+8H) + states 4*B*(E+4H) (DESIGN.md section 6); traffic = "
+                                "dram read+write per launch from profiles/r02_ncu_full_summary.txt (cold caches)" % n_attn},
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s",
                               "frac": step_gbs / hbm_peak, "bytes_per_step": step_bytes},
             "cpu_baseline": {"value": cpu_sps, "unit": "steps/s", "cores": threads, "kind": _CPU_STATE["kind"],

@@ -261,6 +261,16 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
                                      const sfb_action_source* act, const float* ctx_k, const float* ctx_o,
                                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* The first half of a decode step alone — VisualSoftDotAttention + nn.LSTMCell (model.py:389-393) from carried state — as
+ * ONE launch (vis_lstm_fused_kernel): what sfb_follower_step_packed_fwd enqueues first when it is given carry_in.  Used by
+ * bench.py to time that kernel in isolation (roofline) and usable as a building block (the speaker encoder step has the
+ * same shape).  B <= 128, F = 2176.  feature may be NULL. */
+int32_t sfb_follower_gather_lstm_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* wl,
+                                     const void* packed, size_t packed_bytes, int32_t B, void* carry_in,
+                                     const sfb_visual_source* vis, const float* c0, float* h1, float* c1,
+                                     float* feature, float* alpha_v,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* Per-EPISODE projections of the encoder context (ctx is constant over the decode steps of a rollout,
  * follower.py:446-473): ctx_k = ctx W_in (so that SoftDotAttention's scores ctx . (W_in h) = ctx_k . h, model.py:129-
  * 132) and ctx_o = ctx W_out_c^T (so that W_out_c (sum alpha ctx) = sum alpha ctx_o, model.py:139-141).  Passing both

@@ -116,6 +116,9 @@ SIGNATURES = {
                                                  c_float_p, c_float_p,
                                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_follower_carry_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32]),
+    "sfb_follower_gather_lstm_fwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(VisLstmWeights), C.c_void_p, C.c_size_t, C.c_int32,
+                                                 C.c_void_p, C.POINTER(VisualSource), c_float_p, c_float_p, c_float_p, c_float_p,
+                                                 c_float_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_encoder_lstm_tape_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "sfb_encoder_lstm_train_fwd": (C.c_int32, [C.POINTER(EncoderWeights), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                c_int_p, c_int_p, c_float_p, c_float_p, c_float_p, c_float_p,

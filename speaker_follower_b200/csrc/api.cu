@@ -1360,6 +1360,47 @@ int32_t sfb_follower_step_bwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
   return 0;
 }
 
+/* The first half of a decode step alone (model.py:389-393): attention gather + gate GEMM + LSTM cell from carried
+ * state, ONE launch of vis_lstm_fused_kernel.  carry_in holds the visual query and the packed [u_prev | . | h_0] blocks. */
+int32_t sfb_follower_gather_lstm_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* wl, const void* packed, size_t packed_bytes,
+                                     int32_t B, void* carry_in, const sfb_visual_source* vis, const float* c0, float* h1, float* c1,
+                                     float* feature, float* alpha_v, void* workspace, size_t workspace_bytes, void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_PROPAGATE(check_packable(*dims));
+  SFB_CHECK_ARG(wl && packed && carry_in && vis && c0 && h1 && c1, "NULL argument");
+  const sfb_dims& d = *dims;
+  const FollowerPk P = layout_follower_pk(d);
+  SFB_CHECK_ARG(packed_bytes >= P.bytes && (reinterpret_cast<uintptr_t>(packed) & 255u) == 0, "packed buffer too small / misaligned");
+  FollowerWs ws = carve_follower(d, B, 1, 1, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
+  const CarryLayout CL = layout_carry(d, B);
+  const PkPlan gpl = gemm_pk_plan(B, 4 * d.H, P.nkb_gates, true, device_num_sms());
+  const int lenA = vis->visual ? d.F : vis->img_dim, lenB = vis->visual ? 0 : d.F - vis->img_dim;
+  const FusedPlan fpl = vis_lstm_fused_plan(B, d.H, P.nkb_gates, d.V, d.F, lenA, lenB, device_num_sms());
+  SFB_CHECK_ARG(fpl.ok && gpl.nz == 1 && gpl.NB == fpl.NB, "gather + LSTM launch: unsupported shape (B <= 128, F = 2176)");
+  const unsigned char* base = static_cast<const unsigned char*>(packed);
+  FusedVisLstmParams f{};
+  f.q = reinterpret_cast<const float*>(static_cast<char*>(carry_in) + CL.q); f.ldq = d.F; f.R = d.V; f.D = d.F;
+  if (vis->visual) {
+    f.segA = vis->visual; f.strideA_b = (long long)d.V * d.F; f.lenA = d.F; f.lenB = 0;
+  } else {
+    SFB_CHECK_ARG(vis->feat_table && vis->loc_table && vis->vp_idx && vis->view_idx, "gather visual source needs tables + indices");
+    f.segA = vis->feat_table; f.strideA_b = (long long)d.V * vis->img_dim; f.lenA = vis->img_dim; f.idxA = vis->vp_idx;
+    f.segB = vis->loc_table; f.strideB_b = (long long)d.V * lenB; f.lenB = lenB; f.idxB = vis->view_idx;
+  }
+  f.feat = feature ? feature : ws.feat; f.ldfeat = d.F; f.alpha = alpha_v; f.ldalpha = d.V;
+  f.a_pk = base + P.a_gates; f.b_pk = reinterpret_cast<unsigned char*>(carry_in) + CL.bpk; f.nkb = P.nkb_gates;
+  f.post_kb0 = kblocks(d.E); f.post_kb1 = kblocks(d.E) + kblocks(d.F); f.feat_kb0 = kblocks(d.E);
+  LstmEpilogue& e = f.g.lstm;
+  e.H = d.H; e.b_ih = wl->lstm_b_ih; e.b_hh = wl->lstm_b_hh; e.c0 = c0; e.h1 = h1; e.c1 = c1; e.gates_act = ws.gates_act;
+  e.hpk_NB = gpl.NB; e.hpk_rows_per_z = gpl.rows_per_z;
+  f.g.M = B; f.g.N = 4 * d.H; f.B = B;
+  f.idx_dependent = vis->idx_dependent;
+  f.pre_weight_free = g_fused_pre_weight;
+  return launch_vis_lstm_fused(f, static_cast<cudaStream_t>(stream), ws.fz, ws.fz_bytes);
+}
+
 /* ---------------------------------------------------------------- speaker modules on the packed tcgen05 path */
 namespace {
 struct VisLstmPk { size_t a_q, b_q, a_gates, mq, bytes; int nkb_h, nkb_gates; };

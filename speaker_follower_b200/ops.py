@@ -513,6 +513,29 @@ def follower_step_bwd(w: Dict[str, Tensor], u_prev: Tensor, all_u_t: Tensor, vis
     return d_h0, d_c0, d_ctx
 
 
+@_on_tensor_device
+def follower_gather_lstm(w: Dict[str, Tensor], packed: Tensor, carry_in: Tensor, c0: Tensor, visual: Optional[Tensor] = None,
+                         store: Optional[FeatureStore] = None, vp_idx=None, view_idx=None, out: Optional[tuple] = None,
+                         workspace: Optional[Tensor] = None):
+    """sfb_follower_gather_lstm_fwd: attention gather + gate GEMM + LSTM cell from carried state, one launch.
+    -> (h1, c1, alpha_v)."""
+    lib = _lib.load()
+    B, H = c0.shape
+    V = visual.shape[1] if visual is not None else store.feat_table.shape[1]
+    d = follower_dims(w, V)
+    keep = []
+    vs = _visual_source(visual, store, vp_idx, view_idx, keep)
+    wl = _vis_lstm_weights(w)
+    need = lib.sfb_follower_step_workspace_bytes(C.byref(d), B, 1, 1)
+    if workspace is None or workspace.numel() < need:
+        workspace = _workspace(need, c0.device, ("gather_lstm", B))
+    h1, c1, av = out if out is not None else (torch.empty_like(c0), torch.empty_like(c0), torch.empty(B, V, device=c0.device))
+    check(lib.sfb_follower_gather_lstm_fwd(C.byref(d), C.byref(wl), packed.data_ptr(), packed.numel(), B, carry_in.data_ptr(),
+                                           C.byref(vs), _p(c0, name="c_0"), _p(h1), _p(c1), None, _p(av),
+                                           workspace.data_ptr(), workspace.numel(), _stream()))
+    return h1, c1, av
+
+
 def ctx_rows(lengths, L: int, device) -> Tensor:
     """Flat (b*L + l) indices of the un-padded positions of a padded [B, L] batch (int32, on `device`)."""
     idx = [b * L + l for b, n in enumerate(lengths) for l in range(min(int(n), L))]
