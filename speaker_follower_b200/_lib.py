@@ -191,6 +191,11 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if lib.sfb_abi_version() != 1:
         raise SfbError("libsf_b200.so ABI version mismatch")
+    # bring-up: SFB_OPTIONS="name=value,..." applies sfb_set_option() at load time (e.g. disable_merged=1)
+    for kv in filter(None, os.environ.get("SFB_OPTIONS", "").split(",")):
+        k, _, v = kv.partition("=")
+        if lib.sfb_set_option(k.strip().encode(), int(v)) != 0:
+            raise SfbError("SFB_OPTIONS: unknown option %r" % k)
     _lib = lib
     return lib
 

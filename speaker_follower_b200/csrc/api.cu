@@ -8,6 +8,8 @@ namespace sfb {
 
 int g_disable_tc = 0;
 int g_disable_fused = 0;
+int g_disable_merged = 0;
+int g_merged_prefetch = 1;
 static int g_fused_pre_weight = 4, g_fused_nopre = 0, g_fused_dbg = 0;
 int g_disable_pdl = 0;
 static thread_local std::string g_err;
@@ -382,6 +384,8 @@ int32_t sfb_set_option(const char* name, int32_t value) {
   if (n == "disable_tc") { g_disable_tc = value; return 0; }
   if (n == "disable_pdl") { g_disable_pdl = value; return 0; }
   if (n == "disable_fused") { g_disable_fused = value; return 0; }
+  if (n == "disable_merged") { g_disable_merged = value; return 0; }
+  if (n == "merged_prefetch") { g_merged_prefetch = value; return 0; }
   if (n == "fused_pre_weight") { g_fused_pre_weight = value; return 0; }
   if (n == "fused_nopre") { g_fused_nopre = value; return 0; }
   if (n == "fused_dbg") { g_fused_dbg = value; return 0; }
@@ -985,9 +989,12 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
   const bool fused_b = ctx_k != nullptr && tpl.ok && !g_disable_fused && gpl.nz == 1 && gpl.NB == tpl.NB &&
                        (!act_gather || (size_t)A * d.E * 4 <= 160 * 1024);
   if (fused_b) lstm_e.hdpk = ws.hdpk;
+  // ... and the WHOLE step as one launch (step_fused_b.cu: step_kernel) when both halves are fused and fit one geometry
+  const bool merged = fused && fused_b && !g_disable_merged &&
+                      step_fused_plan(B, L, A, d.H, d.E, d.F, q_next != nullptr, P.nkb_gates, d.V, d.F, vis_lenA, vis_lenB, device_num_sms()).ok;
+  FusedVisLstmParams f{};
   if (fused) {
     // model.py:389-393 as ONE launch (step_fused.cu): attention gather + gate GEMM + LSTM cell
-    FusedVisLstmParams f{};
     f.q = qv; f.ldq = d.F; f.R = d.V; f.D = d.F;
     if (vis->visual) {
       f.segA = vis->visual; f.strideA_b = (long long)d.V * d.F; f.lenA = d.F; f.lenB = 0;
@@ -1006,7 +1013,7 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
     f.pre_weight_free = g_fused_pre_weight;
     f.dbg = g_fused_dbg;
     if (g_fused_nopre) { f.post_kb0 = 0; f.post_kb1 = P.nkb_gates; }   // bring-up: no overlap of the gate GEMM with the gather
-    SFB_PROPAGATE(launch_vis_lstm_fused(f, st, ws.fz, ws.fz_bytes));
+    if (!merged) SFB_PROPAGATE(launch_vis_lstm_fused(f, st, ws.fz, ws.fz_bytes));
   } else {
     // The gate GEMM's activation operand [u_prev | feature | h0] (.) drop_x is packed by the attention kernel: u_prev and
     // h0 as a side job of all its threads, feature in its epilogue.
@@ -1052,6 +1059,7 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
                           tail->u_next, tail->action_score, tail->ce, B, A, d.E, nullptr};
       if (bpk_next) { t.tail.upk = bpk_next; t.tail.upk_NB = gpl.NB; }
     }
+    if (merged) return launch_step_fused(f, t, st, ws.fz, ws.fz_bytes, ws.tsync, 256);
     return launch_text_score_fused(t, st, ws.tsync, 256);
   }
   if (ctx_k) {

@@ -199,6 +199,13 @@ __device__ __forceinline__ float dsmem_ld_f32(uint32_t addr) {
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void dsmem_st_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// arrive on an mbarrier that lives in another CTA of the cluster (address from dsmem_addr)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
 __device__ __forceinline__ float4 dsmem_ld_f32x4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"

@@ -189,6 +189,7 @@ struct FusedPlan {
   bool ok;
   int tiles, S, NB, nch, chunk_rows, gstages;
   size_t smem, sem_bytes, bytes;
+  size_t data_bytes;   // leading part of the dynamic shared memory that holds only staged data (free once the MMAs have retired)
 };
 FusedPlan vis_lstm_fused_plan(int B, int H, int nkb, int R, int D, int lenA, int lenB, int num_sms);
 int32_t launch_vis_lstm_fused(const FusedVisLstmParams& q, cudaStream_t stream, void* ws, size_t ws_bytes);
@@ -240,6 +241,26 @@ struct FusedTextPlan {
 };
 FusedTextPlan text_score_fused_plan(int B, int L, int A, int H, int E, int F, bool with_q, int num_sms);
 int32_t launch_text_score_fused(const FusedTextScoreParams& q, cudaStream_t stream, void* sync_ws, size_t sync_bytes);
+
+// both halves of the step as one launch (step_fused_b.cu: step_kernel)
+struct FusedStepParams {
+  FusedVisLstmParams a;
+  FusedTextScoreParams b;
+  unsigned int* phase;      // arrivals: one per CTA when its share of the first half is visible device-wide
+  int top_off, tiles, S;
+  int prefetch;             // bring-up option "merged_prefetch"
+};
+struct FusedStepPlan {
+  bool ok;
+  FusedPlan a;
+  FusedTextPlan b;          // P / nch for the merged geometry
+  size_t smem, top_off;
+};
+FusedStepPlan step_fused_plan(int B, int L, int A, int H, int E, int F, bool with_q, int nkb, int R, int D, int lenA, int lenB, int num_sms);
+// ws / ws_bytes: the first half's workspace; sync_ws: the second half's counter words (word 8 = the phase counter)
+extern int g_merged_prefetch;
+int32_t launch_step_fused(const FusedVisLstmParams& qa, const FusedTextScoreParams& qb, cudaStream_t stream, void* ws, size_t ws_bytes,
+                          void* sync_ws, size_t sync_bytes);
 
 // ---------------------------------------------------------------- pointwise.cu
 // logit[b,a] = all_u_t[b,a,:] . g[b,:] + sum_d b_a[d] w_out[d] tp[b,d] + b_out   (EltwiseProdScoring rewritten)

@@ -20,11 +20,13 @@
 //     projection.  The same CTA then stages the element's action-candidate rows (from the feature table or the dense
 //     tensor) in the freed ring and, when g has arrived, forms the logits and runs the rollout tail.
 // The three hand-offs (hh -> rows, h~ -> g pairs, g -> rows) are device-wide arrival counters polled by one thread.
-#include <cuda_bf16.h>
-
-#include "epilogue.cuh"
-#include "kernels.h"
-#include "pack.cuh"
+//
+// step_kernel (bottom of this file) runs BOTH halves of the step — the gather + gate GEMM + LSTM cell of step_fused.cu
+// and the above — as ONE launch over one resident wave of CTAs: the second half starts in every CTA as soon as the
+// CTA's own share of the first half is finished, its input-independent reads (key / value rows, projection weights)
+// are issued by an otherwise idle warp while the first half's epilogue is still running, and the hand-over between
+// the halves is one more device-wide arrival counter instead of a kernel boundary.
+#include "step_fused_a.cuh"
 #include "tail.cuh"
 
 namespace sfb {
@@ -82,11 +84,28 @@ __device__ __forceinline__ bool t_spin_ge(const unsigned int* p, unsigned int ta
 }
 }  // namespace
 
-// grid = 2P + (row CTAs), cluster (2,1,1), TNT threads
-__global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTextScoreParams q) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ int s_fail;
-  __shared__ uint32_t s_tmem;
+// One CTA of the kernel.  Stand-alone (MERGED = false): STAGE = T_ALL does everything.  Inside the one-launch step
+// kernel the same code is entered four times: T_INIT (all threads, before the first half: barriers), T_LISTS (producer
+// warp, early: the un-masked positions), T_PREFETCH (producer warp, when the first half has released the data region:
+// the first key / value rows or the first job's weights), T_MAIN (all threads, after the first half).
+// `top` = barriers + position lists: in the merged kernel a region the first half never touches.
+enum { T_ALL = 0, T_INIT = 1, T_LISTS = 2, T_PREFETCH = 3, T_MAIN = 4 };
+struct TShared {   // static shared state of a CTA (declared by the kernel: one copy whatever the number of stages)
+  int fail, pre, nvalid[2], at;
+  uint32_t tmem;
+};
+template <bool MERGED, int STAGE>
+__device__ __forceinline__ void text_score_body(const FusedTextScoreParams& q, unsigned char* smem, unsigned char* top_in,
+                                                TShared& sh, const uint32_t tmem_in, const unsigned int* phase) {
+  int& s_fail = sh.fail;
+  uint32_t& s_tmem = sh.tmem;
+  int* s_nvalid = sh.nvalid;
+  int& s_at = sh.at;
+  int& s_pre = sh.pre;                    // merged: key / value chunks (row CTA) or weight sets (pair CTA) issued by T_PREFETCH
+  constexpr int PW = MERGED ? 10 : 9;     // producer warp (the merged kernel's warp 9 belongs to the first half)
+  constexpr bool DO_INIT = STAGE == T_ALL || STAGE == T_INIT;
+  constexpr bool DO_LISTS = STAGE == T_ALL || STAGE == T_LISTS;
+  constexpr bool DO_MAIN = STAGE == T_ALL || STAGE == T_MAIN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cid = blockIdx.x;
   const int P = q.P, B = q.B, H = q.H, NB = q.NB;
@@ -96,10 +115,26 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
   unsigned int* cnt_g = q.sync + 2;      // arrivals: 2 per g tile
   unsigned int* cnt_exit = q.sync + 3;
   unsigned int* status = q.sync + 4;
+  // merged: "the first half is complete device-wide" replaces the dependency on the preceding kernel
+  auto wait_inputs = [&]() -> bool {
+    if (!MERGED) {
+      pdl_wait();
+      return true;
+    }
+    return t_spin_ge(phase, gridDim.x);
+  };
 
-  if (tid == 0) s_fail = 0;
-  trace_mark(q.trace, 0);
-  pdl_launch_dependents();
+  if (DO_INIT) {
+    if (tid == 0) {
+      s_fail = 0;
+      s_pre = 0;
+    }
+  }
+  if (STAGE == T_ALL) {
+    trace_mark(q.trace, 0);
+    pdl_launch_dependents();
+  }
+  if (STAGE == T_MAIN) trace_mark(q.trace, 0);
 
   if (is_pair) {
     // =====================================================================================================
@@ -110,30 +145,51 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
     const uint32_t bstage = 2 * b_half;
     unsigned char* wbuf = smem;                                             // [T_MAXKH][32 KB]; later the parked partial
     unsigned char* bst = smem + (size_t)T_MAXKH * 2 * TA_HALF;              // [T_BST][bstage]
-    uint64_t* wfull = reinterpret_cast<uint64_t*>(bst + (size_t)T_BST * bstage);
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(MERGED ? top_in : bst + (size_t)T_BST * bstage);
     uint64_t* bfull = wfull + 1;      // [T_BST]
     uint64_t* bempty = bfull + T_BST; // [T_BST]
     uint64_t* done = bempty + T_BST;
+    uint64_t* pdone = done + 1;       // the PEER's MMAs of the job have retired (remote arrival): its weight buffer may be written
     const uint32_t tmem_cols = NB <= 32 ? 32 : NB <= 64 ? 64 : NB <= 128 ? 128 : 256;
-    if (warp == 0) {
+    if (DO_INIT && warp == (MERGED ? 1 : 0)) {
       if (lane == 0) {
         mbar_init(wfull, 1);
         for (int i = 0; i < T_BST; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
         mbar_init(done, 1);
+        mbar_init(pdone, 1);
       }
       mbar_fence_init();
       __syncwarp();
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+      if (!MERGED) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+      }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = s_tmem;
+    if (STAGE == T_ALL) {
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const uint32_t tmem_d = MERGED ? tmem_in : s_tmem;
 
     // jobs of this pair, in order: phase 1 = hh tiles then q' tiles (inputs ready at kernel start), phase 2 = g tiles
     const int n1 = q.hh_tiles + q.q_tiles, n2 = q.g_tiles;
     const int nkb = q.nkb, kh0 = rank == 0 ? 0 : (nkb + 1) / 2, kh1 = rank == 0 ? (nkb + 1) / 2 : nkb, nkh = kh1 - kh0;
+    // the weights of a job: all K blocks of this CTA's half into the weight buffer, one barrier phase
+    auto issue_weights = [&](const unsigned char* a_base, int tile) {
+      const uint64_t pol = policy_evict_last();
+      mbar_expect_tx(wfull, (uint32_t)nkh * 2 * TA_HALF);
+      for (int k = 0; k < nkh; ++k)
+        bulk_g2s_hint(wbuf + (size_t)k * 2 * TA_HALF, a_base + ((size_t)tile * nkb + kh0 + k) * (2 * TA_HALF), 2 * TA_HALF, wfull, pol);
+    };
+    if (STAGE == T_PREFETCH) {   // the first job's weights (a pair always has a phase-1 job when it has any)
+      if (lane == 0 && pair < n1) {
+        if (pair < q.hh_tiles) issue_weights(q.a_hh, pair);
+        else issue_weights(q.a_q, pair - q.hh_tiles);
+        s_pre = 1;
+      }
+    }
+    if (DO_MAIN) {
     // batch columns whose epilogue this CTA runs: rank 0 the first groups of 16, rank 1 the rest
     const int ngrp = NB / 16, g_split = (ngrp + 1) / 2;
     const int my_g0 = rank == 0 ? 0 : g_split, my_g1 = rank == 0 ? g_split : ngrp;
@@ -141,31 +197,30 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
     int njobs_done = 0, bcount = 0;   // running counters -> mbarrier parities
     bool waited_pdl = false, fail = false;
 
-    for (int phase = 1; phase <= 2; ++phase) {
-      const int njobs = phase == 1 ? n1 : n2;
+    for (int jp = 1; jp <= 2; ++jp) {   // job phase
+      const int njobs = jp == 1 ? n1 : n2;
       for (int job = pair; job < njobs; job += P) {
         // ---- job description
         const unsigned char* a_base; const unsigned char* b_base; float* out; int ldo, ncols, tile; const float* bias; unsigned int* cnt;
-        if (phase == 1 && job < q.hh_tiles) {
+        if (jp == 1 && job < q.hh_tiles) {
           tile = job; a_base = q.a_hh; b_base = q.hdpk; out = q.hh; ldo = q.ldhh; ncols = H; bias = nullptr; cnt = cnt_hh;
-        } else if (phase == 1) {
+        } else if (jp == 1) {
           tile = job - q.hh_tiles; a_base = q.a_q; b_base = q.hpk; out = q.q_next; ldo = q.ldq; ncols = q.q_cols; bias = q.b_q; cnt = nullptr;
         } else {
           tile = job; a_base = q.a_g; b_base = q.htpk; out = q.g; ldo = q.ldg; ncols = q.g_cols; bias = q.b_g; cnt = cnt_g;
         }
         const uint32_t jpar = (uint32_t)njobs_done & 1u;
-        if (warp == 9) {
+        if (warp == PW) {
           if (lane == 0) {
-            const uint64_t pol = policy_evict_last();
             // weights of the job: the buffer is free (the end-of-job cluster barrier of the previous job was passed)
-            mbar_expect_tx(wfull, (uint32_t)nkh * 2 * TA_HALF);
-            for (int k = 0; k < nkh; ++k)
-              bulk_g2s_hint(wbuf + (size_t)k * 2 * TA_HALF, a_base + ((size_t)tile * nkb + kh0 + k) * (2 * TA_HALF), 2 * TA_HALF, wfull, pol);
+            if (!(MERGED && njobs_done == 0 && jp == 1 && s_pre)) issue_weights(a_base, tile);
             if (!waited_pdl) {
-              pdl_wait();   // packed h1d / h_1 come from the kernel before this one
+              fail = !wait_inputs() || fail;   // packed h1d / h_1 come from the first half of the step
+              if (MERGED) asm volatile("fence.proxy.async;" ::: "memory");   // ... written with generic-proxy stores in this launch
               waited_pdl = true;
+              if (q.trace && cid == 0) q.trace[11] = globaltimer_ns();
             }
-            if (phase == 2) {   // the packed h~ operand is complete when every row CTA has published its element
+            if (jp == 2) {   // the packed h~ operand is complete when every row CTA has published its element
               fail = !t_spin_ge(cnt_ht, (unsigned int)B) || fail;
               asm volatile("fence.proxy.async;" ::: "memory");
             }
@@ -202,13 +257,19 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
             }
             __syncwarp();
           }
+        } else if (warp >= 8) {
+          bcount += nkh;   // merged: warps of the first half without a role here
         } else {
           bcount += nkh;
-          // ---- epilogue part 1: park the columns the PEER owns (TMEM -> registers -> own shared memory, [col][row])
+          // ---- epilogue part 1: PUSH the columns the peer owns into the peer's shared memory (TMEM -> registers ->
+          // st.shared::cluster, [col][row] over the peer's weight buffer, which is free once the peer's MMAs have retired)
           fail = !t_wait(done, jpar) || fail;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (q.trace && cid == 0 && tid == 0 && njobs_done == 0) q.trace[12] = globaltimer_ns();
+          if (tid == 0) mbar_arrive_remote(dsmem_addr(pdone, (uint32_t)(rank ^ 1)));
+          fail = !t_wait(pdone, jpar) || fail;
           const int lq = warp & 3, hf = warp >> 2, row = lq * 32 + lane;
-          float* park = reinterpret_cast<float*>(wbuf);   // the weights are consumed: all MMAs of the job have completed
+          const uint32_t peer_park = dsmem_addr(wbuf, (uint32_t)(rank ^ 1));
           for (int gq = peer_g0 + hf; gq < peer_g1; gq += 2) {
             uint32_t v[16];
             const uint32_t taddr = tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(gq * 16);
@@ -219,14 +280,16 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 16; ++j) park[(size_t)((gq - peer_g0) * 16 + j) * TBM + row] = __uint_as_float(v[j]);
+            for (int j = 0; j < 16; ++j)
+              dsmem_st_f32(peer_park + (uint32_t)(((gq - peer_g0) * 16 + j) * TBM + row) * 4u, __uint_as_float(v[j]));
           }
         }
-        cluster_sync_all();   // both partials parked
+        cluster_sync_all();   // both partials delivered (release / acquire at cluster scope)
+        if (q.trace && cid == 0 && tid == 0 && njobs_done == 0) q.trace[13] = globaltimer_ns();
         if (warp < 8) {
           // ---- epilogue part 2: own columns = own accumulator + the peer's parked values, bias, store
           const int lq = warp & 3, hf = warp >> 2, row = lq * 32 + lane;
-          const uint32_t peer_park = dsmem_addr(wbuf, (uint32_t)(rank ^ 1));
+          const float* park = reinterpret_cast<const float*>(wbuf);   // what the peer pushed: this CTA's columns of ITS partial
           const int n = tile * TBM + row;
           const float bv = (bias && n < ncols) ? __ldg(bias + n) : 0.f;
           for (int gq = my_g0 + hf; gq < my_g1; gq += 2) {
@@ -241,7 +304,7 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
             float pv[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              pv[j] = dsmem_ld_f32(peer_park + (uint32_t)(((gq - my_g0) * 16 + j) * TBM + row) * 4u);
+              pv[j] = park[(size_t)((gq - my_g0) * 16 + j) * TBM + row];
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (n < ncols) {
 #pragma unroll
@@ -254,20 +317,23 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
             }
           }
           __threadfence();
+          if (q.trace && cid == 0 && tid == 0 && njobs_done == 0) q.trace[14] = globaltimer_ns();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         cluster_sync_all();   // outputs stored + fenced, parked data consumed: the weight buffer is free again
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (tid == 0 && cnt) atomicAdd(cnt, 1u);
+        if (q.trace && cid == 0 && tid == 0 && njobs_done == 0) q.trace[15] = globaltimer_ns();
         ++njobs_done;
       }
     }
-    if (warp == 9 && lane == 0 && !waited_pdl) pdl_wait();
+    if (!MERGED && warp == PW && lane == 0 && !waited_pdl) pdl_wait();
     if (fail) s_fail = 1;
     __syncthreads();
-    if (warp == 0)
+    if (!MERGED && warp == 0)
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
-  } else {
+    }   // DO_MAIN
+  } else if (((cid - 2 * P) >> 1) < (B + 1) / 2) {
     // =====================================================================================================
     // row CTAs: a cluster of two serves TWO batch elements — a long one and a short one (element c and B-1-c: the
     // batch is sorted by instruction length, so the pair streams about the same number of rows as every other pair).
@@ -296,14 +362,13 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
     float* sc = gs + ((E + 4 + 3) & ~3);                                     // [2][Lr] raw scores by list position
     float* slog = sc + 2 * Lr;                                               // [Ar] logits of the own element
     float* sval = slog + ((A + 3) & ~3);                                     // [Ar] validity flags
-    int* list = reinterpret_cast<int*>(sval + ((A + 3) & ~3));               // [2][Lr] un-masked positions
-    uint64_t* rfull = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(list + 2 * Lr) + 15) & ~uintptr_t(7));
+    unsigned char* top = MERGED ? top_in : reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sval + ((A + 3) & ~3)) + 15) & ~uintptr_t(15));
+    uint64_t* rfull = reinterpret_cast<uint64_t*>(top);
     uint64_t* rempty = rfull + T_MAXCH;
     uint64_t* candfull = rempty + T_MAXCH;
     uint64_t* ring_free = candfull + 1;
-    __shared__ int s_nvalid[2];
-    __shared__ int s_at;
-    if (warp == 0) {
+    int* list = reinterpret_cast<int*>(ring_free + 1);                       // [2][Lr] un-masked positions
+    if (DO_INIT && warp == (MERGED ? 1 : 0)) {
       if (lane < T_MAXCH) {
         mbar_init(&rfull[lane], 1);
         mbar_init(&rempty[lane], T_RW);
@@ -313,6 +378,8 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
         mbar_init(ring_free, 1);
       }
       mbar_fence_init();
+    }
+    if (DO_LISTS && warp == (MERGED ? PW : 0)) {
       // compact the un-masked positions of both elements (padding masks are suffixes in practice; any mask works)
       for (int k = 0; k < 2; ++k) {
         const int e = els[k];
@@ -329,8 +396,10 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
         }
         if (lane == 0) s_nvalid[k] = n;
       }
+      __syncwarp();
     }
-    __syncthreads();
+    if (STAGE == T_ALL) __syncthreads();
+    if (STAGE == T_ALL || STAGE == T_PREFETCH || STAGE == T_MAIN) {
     // rows of element k this CTA streams: list positions rank, rank + 2, ...
     int nmine[2], nchk[2];
 #pragma unroll
@@ -338,16 +407,20 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
       nmine[k] = s_nvalid[k] > rank ? (s_nvalid[k] - rank + 1) / 2 : 0;
       nchk[k] = (nmine[k] + T_RW - 1) / T_RW;
     }
-    if (warp == 9) {
-      // ---- producer: key / value rows (per-episode constants: no dependency wait), later the candidate rows
+    if (warp == PW) {
+      // ---- producer: key / value rows (per-episode constants: no dependency wait), later the candidate rows.
+      // T_PREFETCH issues the chunks that fit the empty ring and leaves; T_MAIN resumes behind them.
       const uint64_t pol = policy_evict_normal();
       bool ok = true;
       int cg = 0;
+      const int resume = STAGE == T_MAIN ? s_pre : 0;
       for (int k = 0; k < 2; ++k) {
         if (els[k] < 0) continue;
         const float* kb_ = q.ctx_k + (size_t)els[k] * L * H;
         const float* vb_ = q.ctx_o + (size_t)els[k] * L * H;
         for (int c = 0; c < nchk[k]; ++c, ++cg) {
+          if (cg < resume) continue;
+          if (STAGE == T_PREFETCH && cg >= NCH) break;
           const int slot = cg % NCH;
           if (cg >= NCH) ok = t_wait(&rempty[slot], (uint32_t)(cg / NCH - 1) & 1u) && ok;
           const int rows = min(T_RW, nmine[k] - c * T_RW);
@@ -361,8 +434,11 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
           }
         }
       }
+      if (STAGE == T_PREFETCH) {
+        if (lane == 0) s_pre = cg < NCH ? cg : NCH;
+      }
+      if (DO_MAIN) {
       cluster_sync_all();   // X1: partials parked
-      cluster_sync_all();   // X2: partials pulled
       if (own >= 0) {
         // candidate rows of the own element into the freed ring (step inputs)
         ok = t_wait(ring_free, 0) && ok;
@@ -385,16 +461,25 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
           }
         }
       }
+      if (!MERGED) pdl_wait();
+      }   // DO_MAIN
       if (!ok) s_fail = 1;
-      pdl_wait();
-    } else if (warp == 8) {
-      cluster_sync_all();
-      cluster_sync_all();
-      pdl_wait();
+    } else if (!DO_MAIN) {
+    } else if (warp >= 8) {
+      cluster_sync_all();   // X1
+      if (!MERGED) pdl_wait();
     } else {
       // ---- compute warps: each warp owns whole rows (row r of a chunk -> warp r)
-      pdl_wait();   // h1d is produced by the kernel before this one
+      if (!MERGED) {
+        pdl_wait();   // h1d is produced by the kernel before this one
+      } else {        // ... by the first half of this launch, in every CTA of the grid
+        if (tid == 0 && !wait_inputs()) s_fail = 1;
+        t_bar256();
+      }
       rmark(1);
+      // inputs of the tail, fetched while everything else is still on its way
+      if (q.has_tail && own >= 0)
+        for (int a = tid; a < A; a += 256) sval[a] = q.tail.is_valid[(size_t)own * A + a];
       float4 o_own = make_float4(0.f, 0.f, 0.f, 0.f);   // threads < nv: the CTA-level partial of the own element
       int cg = 0;
       for (int k = 0; k < 2; ++k) {
@@ -409,7 +494,7 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int idx = lane + 32 * j;
-            qv[j] = idx < nv ? q4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+            qv[j] = idx < nv ? __ldcg(q4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           for (int c = 0; c < nchk[k]; ++c, ++cg) {
             const int slot = cg % NCH, i = c * T_RW + warp;
@@ -498,7 +583,8 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
         o_own.x = pa.x * wa + pb.x * wb; o_own.y = pa.y * wa + pb.y * wb;
         o_own.z = pa.z * wa + pb.z * wb; o_own.w = pa.w * wa + pb.w * wb;
       }
-      if (q.alpha) {
+      auto write_alpha = [&]() {   // attention weights of the rows this CTA streamed (both elements) — off the critical path
+        if (!q.alpha) return;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           if (els[k] < 0) continue;
@@ -513,13 +599,10 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
           for (int l = tid; l < L; l += 256)
             if (mrow[l]) q.alpha[(size_t)own * q.ldalpha + l] = 0.f;
         }
-      }
-      cluster_sync_all();   // X2: nobody needs the peer's shared memory any more
+      };
+      if (own < 0) write_alpha();
       if (own >= 0) {
         const int b = own;
-        // inputs of the tail, fetched while hh / g are still on their way
-        if (q.has_tail)
-          for (int a = tid; a < A; a += 256) sval[a] = q.tail.is_valid[(size_t)b * A + a];
         // h~ = tanh(sum_l alpha_l ctx_o[l] + hh) once hh (W_out_h h1d, from the projection pairs) has arrived
         if (tid == 0 && !t_spin_ge(cnt_hh, 2u * (unsigned int)q.hh_tiles)) s_fail = 1;
         t_bar256();
@@ -547,6 +630,7 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
           mbar_arrive(ring_free);
         }
         rmark(5);
+        write_alpha();
         // ---- action scoring + rollout tail (model.py:396, follower.py:476-505)
         float* us = ring;   // [A][E]
         if (q.cand_table) {
@@ -563,49 +647,99 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
             if (q.cand_view[(size_t)b * A + a] < 0)
               for (int i = tid; i < q.img_dim; i += 256) us[(size_t)a * E + i] = 0.f;
         }
+        // the tail's per-row scalars, requested before the wait for g
+        int tgt_pre = -1;
+        float u_pre = 0.f;
+        if (q.has_tail && warp == 0) {
+          tgt_pre = q.tail.target ? q.tail.target[b] : -1;
+          u_pre = (q.tail.feedback == 2 && q.tail.sample_u) ? q.tail.sample_u[b] : 0.f;
+        }
         if (tid == 0 && !t_spin_ge(cnt_g, 2u * (unsigned int)q.g_tiles)) s_fail = 1;
         t_bar256();
         rmark(6);
-        for (int j = tid; j < (E >> 2) + 1; j += 256) {
-          const int k = j * 4;
-          if (k + 3 < E + 1) reinterpret_cast<float4*>(gs)[j] = __ldcg(reinterpret_cast<const float4*>(q.g + (size_t)b * q.ldg + k));
-          else
-            for (int t = k; t < E + 1; ++t) gs[t] = __ldcg(q.g + (size_t)b * q.ldg + t);
-        }
-        if (!t_wait(candfull, 0)) s_fail = 1;
-        t_bar256();
-        rmark(8);
-        const float cst = gs[E];
-        for (int a = warp; a < A; a += 8) {
-          const float4* u4 = reinterpret_cast<const float4*>(us + (size_t)a * E);
-          float accd = 0.f;
-          for (int j = lane; j < (E >> 2); j += 32) {
-            const float4 u = u4[j];
-            const float4 g4 = reinterpret_cast<const float4*>(gs)[j];
-            accd = fmaf(u.x, g4.x, accd); accd = fmaf(u.y, g4.y, accd);
-            accd = fmaf(u.z, g4.z, accd); accd = fmaf(u.w, g4.w, accd);
+        // logit[a] = u_a . g + g[E]: warp w owns a 1/8 slice of the E columns for ALL candidates — its slice of g comes
+        // straight from L2 into registers (<= 3 float4 per lane), the candidate rows are in the ring; up to 8 candidates
+        // are reduced together (transposed butterfly), the 8 per-warp partials meet in shared memory
+        {
+          const int nE4 = E >> 2, per_w = (nE4 + 7) >> 3, j0 = warp * per_w;
+          const float4* g4 = reinterpret_cast<const float4*>(q.g + (size_t)b * q.ldg);
+          float4 gv[3];
+          int jj[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int jl = lane + 32 * i, j = j0 + jl;
+            const bool okj = jl < per_w && j < nE4;
+            jj[i] = okj ? j : 0;
+            gv[i] = okj ? __ldcg(g4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          accd = warp_sum(accd);
-          if (lane == 0) slog[a] = accd + cst;
+          const float cst = (warp == 0) ? __ldcg(q.g + (size_t)b * q.ldg + E) : 0.f;
+          if (!t_wait(candfull, 0)) s_fail = 1;
+          rmark(8);
+          float* spart = wacc;   // [8 warps][Ar] (the attention's scratch is free)
+          const int Ar = (A + 3) & ~3;
+          for (int a0 = 0; a0 < A; a0 += 8) {
+            float part[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const int a = a0 + r < A ? a0 + r : A - 1;   // rows past the end repeat the last one (discarded below)
+              const float4* u4 = reinterpret_cast<const float4*>(us + (size_t)a * E);
+              float acc0 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                const float4 u = u4[jj[i]];
+                acc0 = fmaf(u.x, gv[i].x, acc0); acc0 = fmaf(u.y, gv[i].y, acc0);
+                acc0 = fmaf(u.z, gv[i].z, acc0); acc0 = fmaf(u.w, gv[i].w, acc0);
+              }
+              part[r] = acc0;
+            }
+            const bool u4b = (lane & 16) != 0;
+            float a4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a4[i] = (u4b ? part[4 + i] : part[i]) + __shfl_xor_sync(0xffffffffu, u4b ? part[i] : part[4 + i], 16);
+            const bool u3 = (lane & 8) != 0;
+            float a2[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) a2[i] = (u3 ? a4[2 + i] : a4[i]) + __shfl_xor_sync(0xffffffffu, u3 ? a4[i] : a4[2 + i], 8);
+            const bool u2 = (lane & 4) != 0;
+            float t = (u2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, u2 ? a2[0] : a2[1], 4);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            if ((lane & 3) == 0 && a0 + (lane >> 2) < A) spart[warp * Ar + a0 + (lane >> 2)] = t;
+          }
+          t_bar256();
+          rmark(9);
+          if (warp == 0) {
+            for (int a = lane; a < A; a += 32) {
+              float sum = 0.f;
+#pragma unroll
+              for (int w = 0; w < 8; ++w) sum += spart[w * Ar + a];   // fixed order
+              slog[a] = sum + cst;
+            }
+            __syncwarp();
+          }
         }
-        t_bar256();
-        rmark(9);
         if (q.has_tail) {
           if (warp == 0) {
-            const int a_t = tail_row(q.tail, b, lane, us, slog, sval, false);
+            const int a_t = tail_row(q.tail, b, lane, us, slog, sval, false, tgt_pre, q.tail.feedback == 2 && q.tail.sample_u ? u_pre : -1.f);
             if (lane == 0) s_at = a_t;
           }
           t_bar256();
           rmark(10);
           tail_copy_u(q.tail, b, s_at, us, tid, 256);
         } else {
-          for (int a = tid; a < A; a += 256) q.logit[(size_t)b * A + a] = slog[a];
+          if (warp == 0)
+            for (int a = lane; a < A; a += 32) q.logit[(size_t)b * A + a] = slog[a];
         }
         rmark(7);
       }
     }
-    __syncthreads();
+    if (DO_MAIN) {
+      cluster_sync_all();   // X2: the peer has pulled what it needed from this CTA's shared memory (it may go away now)
+      __syncthreads();
+    }
+    }   // T_ALL / T_PREFETCH / T_MAIN
   }
+  if (!DO_MAIN) return;
   // ---- exit bookkeeping: the last CTA resets the hand-off counters (no launch of this kernel overlaps another)
   if (tid == 0) {
     if (s_fail) atomicExch(status, 1u);
@@ -616,9 +750,51 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
       atomicExch(cnt_ht, 0u);
       atomicExch(cnt_g, 0u);
       atomicExch(cnt_exit, 0u);
+      if (MERGED) atomicExch(const_cast<unsigned int*>(phase), 0u);   // every CTA has passed its wait on it: it arrived here
     }
   }
   trace_mark(q.trace, 2);
+}
+
+// grid = 2P + (row CTAs), cluster (2,1,1), TNT threads
+__global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTextScoreParams q) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ TShared sh;
+  text_score_body<false, T_ALL>(q, smem, nullptr, sh, 0u, nullptr);
+}
+
+// ------------------------------------------------------------------ the whole step as one launch
+namespace {
+struct StepHooks {
+  const FusedTextScoreParams& qb;
+  unsigned char* smem;
+  unsigned char* top;
+  TShared& sh;
+  __device__ __forceinline__ void early(int) const { text_score_body<true, T_LISTS>(qb, smem, top, sh, 0u, nullptr); }
+  int mode;   // bring-up: 0 = no early reads, 1 = projection weights only, 2 = weights + key / value rows
+  __device__ __forceinline__ void smem_free(int) const {
+    if (mode == 0 || (mode == 1 && (int)blockIdx.x >= 2 * qb.P)) return;
+    text_score_body<true, T_PREFETCH>(qb, smem, top, sh, 0u, nullptr);
+  }
+};
+}  // namespace
+
+// grid = tiles * S CTAs (one per SM, the first half's arrangement: CTA c = tile c % tiles, rank c / tiles), cluster
+// (2,1,1) for the second half's pairs, FNT threads.  Dynamic smem = the first half's layout + the second half's `top`
+// region (barriers + position lists) behind it; the second half's data region aliases the first half's.
+__global__ void __launch_bounds__(FNT, 1) step_kernel(const FusedStepParams q) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ TShared sh;
+  unsigned char* top = smem + q.top_off;
+  text_score_body<true, T_INIT>(q.b, smem, top, sh, 0u, nullptr);   // barriers of the second half (made visible by the first half's first block barrier)
+  uint32_t tmem_d = 0;
+  const int cid = blockIdx.x;
+  vis_lstm_body<true>(q.a, smem, cid % q.tiles, q.tiles, cid / q.tiles, q.S, StepHooks{q.b, smem, top, sh, q.prefetch}, q.phase, tmem_d);
+  text_score_body<true, T_MAIN>(q.b, smem, top, sh, tmem_d, q.phase);
+  if (threadIdx.x < 32) {
+    const uint32_t tmem_cols = q.a.NB <= 32 ? 32 : q.a.NB <= 64 ? 64 : q.a.NB <= 128 ? 128 : 256;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -626,7 +802,7 @@ __global__ void __launch_bounds__(TNT, 1) text_score_fused_kernel(const FusedTex
 FusedTextPlan text_score_fused_plan(int B, int L, int A, int H, int E, int F, bool with_q, int num_sms) {
   FusedTextPlan pl{};
   pl.ok = false;
-  if (H < 128 || H > 512 || (H % 128) != 0 || (E % 4) != 0 || B < 1 || L < 1 || A < 1) return pl;
+  if (H < 128 || H > 512 || (H % 128) != 0 || (E % 4) != 0 || E > 3072 || B < 1 || L < 1 || A < 1) return pl;
   const int nkb = H / TBK;
   if ((nkb + 1) / 2 > T_MAXKH) return pl;
   pl.NB = (B + 15) & ~15;
@@ -641,7 +817,7 @@ FusedTextPlan text_score_fused_plan(int B, int L, int A, int H, int E, int F, bo
   pl.grid = 2 * pl.P + rows;
   // shared memory: the larger of the two roles
   const size_t b_half = (size_t)(pl.NB / 8) * TSBO;
-  const size_t pair_bytes = (size_t)T_MAXKH * 2 * TA_HALF + (size_t)T_BST * 2 * b_half + (2 * T_BST + 2) * sizeof(uint64_t) + 64;
+  const size_t pair_bytes = (size_t)T_MAXKH * 2 * TA_HALF + (size_t)T_BST * 2 * b_half + (2 * T_BST + 3) * sizeof(uint64_t) + 64;
   const size_t chunk = (size_t)T_RW * 2 * H * 4;
   const size_t Lr = (size_t)(L + 3) & ~size_t(3), Ar = (size_t)(A + 3) & ~size_t(3);
   const size_t row_fixed = ((size_t)8 * H + H + 4 + 16) * 4 + ((size_t)(E + 4 + 3) & ~size_t(3)) * 4 + 4 * Lr * 4 + 2 * Ar * 4 + 32 +
@@ -684,6 +860,99 @@ int32_t launch_text_score_fused(const FusedTextScoreParams& q_in, cudaStream_t s
   static SmemMarks marks;
   SFB_CHECK_CUDA(ensure_dynamic_smem(text_score_fused_kernel, pl.smem, marks));
   SFB_CHECK_CUDA(launch_ex(text_score_fused_kernel, dim3(pl.grid, 1, 1), dim3(TNT, 1, 1), pl.smem, stream, dim3(2, 1, 1), q));
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------ one-launch step: host side
+
+FusedStepPlan step_fused_plan(int B, int L, int A, int H, int E, int F, bool with_q, int nkb, int R, int D, int lenA, int lenB, int num_sms) {
+  FusedStepPlan pl{};
+  pl.ok = false;
+  pl.a = vis_lstm_fused_plan(B, H, nkb, R, D, lenA, lenB, num_sms);
+  pl.b = text_score_fused_plan(B, L, A, H, E, F, with_q, num_sms);
+  if (!pl.a.ok || !pl.b.ok || pl.a.NB != pl.b.NB) return pl;
+  const int grid = pl.a.tiles * pl.a.S;
+  const int rows = (B + 1) & ~1;
+  if ((grid & 1) || grid < rows + 8) return pl;
+  // second half inside the first half's geometry: projection pairs from the CTAs that are not row CTAs, the data
+  // region (ring / weight buffer / scratch) inside the first half's data region, barriers + lists behind everything
+  int P = (grid - rows) / 2;
+  const int n1 = H / 128 + (with_q ? (F + 127) / 128 : 0), n2 = (E + 1 + 127) / 128;
+  const int want = n1 > n2 ? n1 : n2;
+  if (P > want) P = want;
+  if (P < 4) return pl;
+  const size_t b_half = (size_t)(pl.b.NB / 8) * TSBO;
+  const size_t pair_data = (size_t)T_MAXKH * 2 * TA_HALF + (size_t)T_BST * 2 * b_half;
+  const size_t chunk = (size_t)T_RW * 2 * H * 4;
+  const size_t Lr = (size_t)(L + 3) & ~size_t(3), Ar = (size_t)(A + 3) & ~size_t(3);
+  const size_t row_arrays = ((size_t)8 * H + H + 4 + 16) * 4 + ((size_t)(E + 4 + 3) & ~size_t(3)) * 4 + 2 * Lr * 4 + 2 * Ar * 4 + 16;
+  const size_t limit = pl.a.data_bytes;
+  if (pair_data > limit || row_arrays + 2 * chunk > limit) return pl;
+  int nch = (int)((limit - row_arrays) / chunk);
+  if (nch > T_MAXCH) nch = T_MAXCH;
+  size_t ring_min = (size_t)A * E * 4;   // the candidate rows are staged in the ring
+  if (ring_min < 2 * chunk) ring_min = 2 * chunk;
+  if ((size_t)nch * chunk < ring_min) return pl;
+  const int nchunks = (L + T_RW - 1) / T_RW;
+  if (nch > nchunks && (size_t)nchunks * chunk >= ring_min) nch = nchunks;
+  pl.b.P = P;
+  pl.b.nch = nch;
+  pl.b.grid = grid;
+  const size_t top_rows = (2 * T_MAXCH + 2) * sizeof(uint64_t) + 2 * Lr * 4, top_pairs = (2 * T_BST + 3) * sizeof(uint64_t);
+  pl.top_off = (pl.a.smem + 15) & ~size_t(15);
+  pl.smem = pl.top_off + (top_rows > top_pairs ? top_rows : top_pairs) + 16;
+  if (pl.smem > 227 * 1024 - 1024 - 64) return pl;   // static shared memory of the kernel
+  pl.ok = true;
+  return pl;
+}
+
+int32_t launch_step_fused(const FusedVisLstmParams& qa, const FusedTextScoreParams& qb, cudaStream_t stream, void* ws, size_t ws_bytes,
+                          void* sync_ws, size_t sync_bytes) {
+  FusedStepParams q{};
+  q.a = qa;
+  q.b = qb;
+  GemmParams& p = q.a.g;
+  const FusedStepPlan pl = step_fused_plan(qb.B, qb.L, qb.A, qb.H, qb.E, qb.q_cols, qb.q_tiles > 0, qa.nkb, qa.R, qa.D, qa.lenA, qa.lenB,
+                                           device_num_sms());
+  SFB_CHECK_ARG(pl.ok && qa.B == qb.B, "one-launch step: unsupported shape");
+  // the argument checks of the two stand-alone launchers
+  SFB_CHECK_ARG(qa.a_pk && qa.b_pk && (reinterpret_cast<uintptr_t>(qa.a_pk) & 127u) == 0 && (reinterpret_cast<uintptr_t>(qa.b_pk) & 127u) == 0,
+                "one-launch step: packed operands missing / misaligned");
+  SFB_CHECK_ARG(qa.post_kb0 >= 0 && qa.post_kb1 <= qa.nkb && qa.post_kb0 <= qa.feat_kb0 && qa.feat_kb0 + (qa.D + FBK - 1) / FBK <= qa.post_kb1,
+                "one-launch step: the post K range must cover the feature blocks");
+  SFB_CHECK_ARG(qa.q && qa.segA && (qa.lenB == 0 || qa.segB) && (reinterpret_cast<uintptr_t>(qa.segA) & 15u) == 0 &&
+                    (qa.strideA_b % 4) == 0 && (qa.lenB == 0 || ((reinterpret_cast<uintptr_t>(qa.segB) & 15u) == 0 && (qa.strideB_b % 4) == 0)),
+                "one-launch step: visual source missing / misaligned");
+  SFB_CHECK_ARG(ws && ws_bytes >= pl.a.bytes && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, "one-launch step: workspace");
+  SFB_CHECK_ARG(sync_ws && sync_bytes >= 64 && (reinterpret_cast<uintptr_t>(sync_ws) & 15u) == 0, "one-launch step: counter words");
+  SFB_CHECK_ARG(qb.h1d && qb.ctx_k && qb.ctx_o && qb.hh && qb.g && qb.logit && qb.a_hh && qb.a_g && qb.hdpk && qb.htpk, "one-launch step: NULL argument");
+  SFB_CHECK_ARG(qb.q_tiles == 0 || (qb.a_q && qb.hpk && qb.q_next), "one-launch step: next-query operands");
+  SFB_CHECK_ARG((reinterpret_cast<uintptr_t>(qb.ctx_k) & 15u) == 0 && (reinterpret_cast<uintptr_t>(qb.ctx_o) & 15u) == 0 &&
+                    (reinterpret_cast<uintptr_t>(qb.h1d) & 15u) == 0 && (qb.ldh % 4) == 0 && (qb.ldhh % 4) == 0 && (qb.ldg % 4) == 0,
+                "one-launch step: alignment");
+  p.trace = next_trace_slot();
+  q.b.trace = next_trace_slot();
+  q.a.sem = static_cast<unsigned int*>(ws);
+  q.a.sync = q.a.sem + 2 * pl.a.tiles + 16;
+  q.a.partial = reinterpret_cast<float*>(static_cast<char*>(ws) + pl.a.sem_bytes);
+  q.a.NB = pl.a.NB;
+  q.a.nch = pl.a.nch;
+  q.a.chunk_rows = pl.a.chunk_rows;
+  p.M = qa.B;
+  q.b.sync = static_cast<unsigned int*>(sync_ws);
+  q.b.NB = pl.b.NB;
+  q.b.P = pl.b.P;
+  q.b.nch = pl.b.nch;
+  q.b.nkb = qb.H / TBK;
+  q.phase = q.b.sync + 8;
+  q.top_off = (int)pl.top_off;
+  q.prefetch = g_merged_prefetch;
+  q.tiles = pl.a.tiles;
+  q.S = pl.a.S;
+  static SmemMarks marks;
+  SFB_CHECK_CUDA(ensure_dynamic_smem(step_kernel, pl.smem, marks));
+  SFB_CHECK_CUDA(launch_ex(step_kernel, dim3(pl.a.tiles * pl.a.S, 1, 1), dim3(FNT, 1, 1), pl.smem, stream, dim3(2, 1, 1), q));
   count_launch();
   return 0;
 }

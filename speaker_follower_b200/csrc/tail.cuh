@@ -33,9 +33,13 @@ __device__ __forceinline__ void tail_copy_u(const TailParams& p, const int b, co
 
 // `lgw` (optional): a shared-memory working copy of the row's raw logits — the tail then reads and masks that copy and
 // writes the masked row back to p.logit once at the end; `valid_s` (optional): the row's validity flags in shared memory.
-// copy_u = false: the caller copies the chosen row itself (tail_copy_u) with more threads.  Returns a_t.
+// copy_u = false: the caller copies the chosen row itself (tail_copy_u) with more threads.  tgt_pre / u_pre: the row's
+// teacher index / uniform draw when the caller has fetched them ahead of time (TAIL_NOT_LOADED / negative: read here).
+// Returns a_t.
+constexpr int TAIL_NOT_LOADED = -0x7fffffff - 1;
 __device__ __forceinline__ int tail_row(const TailParams& p, const int b, const int lane, const float* rows,
-                                        float* lgw = nullptr, const float* valid_s = nullptr, bool copy_u = true) {
+                                        float* lgw = nullptr, const float* valid_s = nullptr, bool copy_u = true,
+                                        int tgt_pre = TAIL_NOT_LOADED, float u_pre = -1.f) {
   float* lg = lgw ? lgw : p.logit + (size_t)b * p.A;
   const float* valid = valid_s ? valid_s : p.is_valid + (size_t)b * p.A;
   // mask, max / first argmax (torch.max returns the first maximal index)
@@ -68,7 +72,7 @@ __device__ __forceinline__ int tail_row(const TailParams& p, const int b, const 
   z = warp_sum(z);
   const float lse = m + logf(z);
   int a_t;
-  int tgt = p.target ? p.target[b] : -1;
+  int tgt = tgt_pre != TAIL_NOT_LOADED ? tgt_pre : (p.target ? p.target[b] : -1);
   if (tgt >= p.A) tgt = p.A - 1;   // out-of-range teacher index: clamp instead of reading outside the row
   if (p.feedback == 0) {
     a_t = tgt < 0 ? 0 : tgt;
@@ -78,7 +82,7 @@ __device__ __forceinline__ int tail_row(const TailParams& p, const int b, const 
     // inverse-CDF draw over softmax(logit)*valid (follower.py:491-497), sequential in lane 0 (A is tiny)
     a_t = 0;
     if (lane == 0) {
-      const float u = p.sample_u[b];
+      const float u = u_pre >= 0.f ? u_pre : p.sample_u[b];
       float cdf = 0.f;
       int last_valid = 0, pick = -1;
       for (int a = 0; a < p.A; ++a) {
