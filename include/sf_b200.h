@@ -344,6 +344,14 @@ typedef struct sfb_encoder_weights {
 
 size_t sfb_encoder_lstm_workspace_bytes(int32_t ndir, int32_t Hd, int32_t Ew, int32_t B, int32_t maxlen);
 
+/* Same as sfb_encoder_lstm_fwd, with the number of rows of w->embedding stated: without dropout on the embedding
+ * (drop_embed == NULL) the input projection is then computed once per VOCABULARY row instead of once per (row, time)
+ * position (nn.Embedding + the W_ih half of nn.LSTM, model.py:62-66,85-90).  Same results. */
+int32_t sfb_encoder_lstm_fwd_vocab(const sfb_encoder_weights* w, int32_t vocab, int32_t ndir, int32_t Hd, int32_t Ew,
+                                   int32_t B, int32_t maxlen, const int32_t* seq, const int32_t* lengths,
+                                   const float* drop_embed, float* ctx, float* decoder_init, float* c_t,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* Training (autograd of EncoderLSTM.forward, model.py:81-104, unidirectional): sfb_encoder_lstm_train_fwd is the same
  * forward that additionally keeps a TAPE (activated gates and the (h, c) state around every time step, caller-owned,
  * sfb_encoder_lstm_tape_bytes); sfb_encoder_lstm_bwd back-propagates through time over it, hand-written:

@@ -151,6 +151,9 @@ SIGNATURES = {
     "sfb_encoder_lstm_fwd": (C.c_int32, [C.POINTER(EncoderWeights), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, c_int_p, c_int_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                          C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sfb_encoder_lstm_fwd_vocab": (C.c_int32, [C.POINTER(EncoderWeights), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_int32, c_int_p, c_int_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                               C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_speaker_encoder_step_fwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(VisLstmWeights), C.c_int32, c_float_p,
                                                  C.POINTER(VisualSource), c_float_p, c_float_p, c_float_p,
                                                  c_float_p, c_float_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -9,7 +9,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libsf_b200.so")
-SOURCES = ["api.cu", "attention.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_pk.cu", "pack.cu", "pointwise.cu", "step_fused.cu", "step_fused_b.cu", "backward.cu"]
+SOURCES = ["api.cu", "attention.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_pk.cu", "pack.cu", "pointwise.cu", "step_fused.cu", "step_fused_b.cu", "backward.cu", "encoder_persist.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -9,6 +9,7 @@ namespace sfb {
 int g_disable_tc = 0;
 int g_disable_fused = 0;
 int g_disable_merged = 0;
+int g_disable_persist = 0;
 int g_merged_prefetch = 1;
 static int g_fused_pre_weight = 4, g_fused_nopre = 0, g_fused_dbg = 0;
 int g_disable_pdl = 0;
@@ -215,6 +216,7 @@ struct EncWs {
   unsigned char* whh_pk[2]; size_t whh_bytes;   // W_hh packed per call (4 MB: negligible next to maxlen recurrent steps)
   unsigned char* wih_pk[2]; size_t wih_bytes;   // W_ih packed per call for the hoisted input projection
   float *xproj, *h[2], *c[2];
+  unsigned char* ep_hpk; unsigned long long* ep_bar;   // persistent recurrent kernel: packed h between steps, step counters
   int splitk;
   size_t bytes;
 };
@@ -239,6 +241,9 @@ static EncWs carve_encoder(int ndir, int Hd, int Ew, int B, int maxlen, void* ws
   w.xproj = c.take((size_t)ndir * B * maxlen * 4 * Hd);
   for (int i = 0; i < 2; ++i) w.h[i] = c.take((size_t)ndir * B * Hd);
   for (int i = 0; i < 2; ++i) w.c[i] = c.take((size_t)ndir * B * Hd);
+  const EncPersistPlan ep = encoder_persist_plan(ndir, Hd, B, device_num_sms());
+  w.ep_hpk = reinterpret_cast<unsigned char*>(c.take((ep.ok ? ep.hpk_bytes : 256) / sizeof(float)));
+  w.ep_bar = reinterpret_cast<unsigned long long*>(c.take((ep.ok ? ep.bar_bytes : 256) / sizeof(float)));
   w.bytes = c.off;
   return w;
 }
@@ -385,6 +390,7 @@ int32_t sfb_set_option(const char* name, int32_t value) {
   if (n == "disable_pdl") { g_disable_pdl = value; return 0; }
   if (n == "disable_fused") { g_disable_fused = value; return 0; }
   if (n == "disable_merged") { g_disable_merged = value; return 0; }
+  if (n == "disable_persist") { g_disable_persist = value; return 0; }
   if (n == "merged_prefetch") { g_merged_prefetch = value; return 0; }
   if (n == "fused_pre_weight") { g_fused_pre_weight = value; return 0; }
   if (n == "fused_nopre") { g_fused_nopre = value; return 0; }
@@ -594,14 +600,23 @@ static EncTape carve_enc_tape(int Hd, int B, int maxlen, void* p) {
 static int32_t encoder_fwd_impl(const sfb_encoder_weights* w, int32_t ndir, int32_t Hd, int32_t Ew, int32_t B,
                                 int32_t maxlen, const int32_t* seq, const int32_t* lengths, const float* drop_embed,
                                 float* ctx, float* decoder_init, float* c_t, void* workspace, size_t workspace_bytes,
-                                void* stream, void* tape_mem);
+                                void* stream, void* tape_mem, int32_t vocab);
 
 int32_t sfb_encoder_lstm_fwd(const sfb_encoder_weights* w, int32_t ndir, int32_t Hd, int32_t Ew, int32_t B,
                              int32_t maxlen, const int32_t* seq, const int32_t* lengths, const float* drop_embed,
                              float* ctx, float* decoder_init, float* c_t, void* workspace, size_t workspace_bytes,
                              void* stream) {
   return encoder_fwd_impl(w, ndir, Hd, Ew, B, maxlen, seq, lengths, drop_embed, ctx, decoder_init, c_t, workspace, workspace_bytes,
-                          stream, nullptr);
+                          stream, nullptr, 0);
+}
+
+int32_t sfb_encoder_lstm_fwd_vocab(const sfb_encoder_weights* w, int32_t vocab, int32_t ndir, int32_t Hd, int32_t Ew, int32_t B,
+                                   int32_t maxlen, const int32_t* seq, const int32_t* lengths, const float* drop_embed,
+                                   float* ctx, float* decoder_init, float* c_t, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  SFB_CHECK_ARG(vocab >= 1, "vocab >= 1");
+  return encoder_fwd_impl(w, ndir, Hd, Ew, B, maxlen, seq, lengths, drop_embed, ctx, decoder_init, c_t, workspace, workspace_bytes,
+                          stream, nullptr, vocab);
 }
 
 size_t sfb_encoder_lstm_tape_bytes(int32_t Hd, int32_t B, int32_t maxlen) {
@@ -615,13 +630,13 @@ int32_t sfb_encoder_lstm_train_fwd(const sfb_encoder_weights* w, int32_t Hd, int
                                    size_t workspace_bytes, void* stream) {
   SFB_CHECK_ARG(tape && (reinterpret_cast<uintptr_t>(tape) & 255u) == 0 && tape_bytes >= sfb_encoder_lstm_tape_bytes(Hd, B, maxlen),
                 "encoder tape missing, misaligned or too small");
-  return encoder_fwd_impl(w, 1, Hd, Ew, B, maxlen, seq, lengths, drop_embed, ctx, decoder_init, c_t, workspace, workspace_bytes, stream, tape);
+  return encoder_fwd_impl(w, 1, Hd, Ew, B, maxlen, seq, lengths, drop_embed, ctx, decoder_init, c_t, workspace, workspace_bytes, stream, tape, 0);
 }
 
 static int32_t encoder_fwd_impl(const sfb_encoder_weights* w, int32_t ndir, int32_t Hd, int32_t Ew, int32_t B,
                                 int32_t maxlen, const int32_t* seq, const int32_t* lengths, const float* drop_embed,
                                 float* ctx, float* decoder_init, float* c_t, void* workspace, size_t workspace_bytes,
-                                void* stream, void* tape_mem) {
+                                void* stream, void* tape_mem, int32_t vocab) {
   reset_launch_count();
   SFB_CHECK_ARG(w && seq && lengths && ctx && decoder_init && c_t, "NULL argument");
   SFB_CHECK_ARG(ndir == 1 || ndir == 2, "ndir must be 1 or 2");
@@ -662,13 +677,19 @@ static int32_t encoder_fwd_impl(const sfb_encoder_weights* w, int32_t ndir, int3
       SFB_PROPAGATE(launch_pack_rows(pi, st));
     }
   }
+  // the recurrence as ONE launch with W_hh resident in shared memory (encoder_persist.cu) when the shape fits
+  const bool persist = use_pk && !g_disable_persist && encoder_persist_plan(ndir, Hd, B, device_num_sms()).ok;
+  // Without dropout on the embedding the input projection depends on the word id only: project the vocab rows of the
+  // embedding table once (T = Emb W_ih^T, [vocab, 4Hd]) and let the recurrent kernel pick rows by word id, instead of
+  // projecting B * maxlen gathered rows
+  const bool by_token = persist && drop_embed == nullptr && vocab > 0 && vocab <= B * maxlen;
   for (int dir = 0; dir < ndir; ++dir) {
     // hoisted input projection for every time step at once: [B*maxlen, Ew] x W_ih^T  (model.py:85,90)
     float* xp = ws.xproj + (size_t)dir * B * maxlen * 4 * Hd;
     GemmParams g{};
     g.nseg = 1;
-    g.seg[0] = GemmSeg{w->embedding, Ew, seq, drop_embed, drop_embed ? Ew : 0, w->w_ih[dir], Ew, Ew, 0};
-    g.M = B * maxlen; g.N = 4 * Hd; g.splitk = 1; g.out = xp; g.ldo = 4 * Hd;
+    g.seg[0] = GemmSeg{w->embedding, Ew, by_token ? nullptr : seq, drop_embed, drop_embed ? Ew : 0, w->w_ih[dir], Ew, Ew, 0};
+    g.M = by_token ? vocab : B * maxlen; g.N = 4 * Hd; g.splitk = 1; g.out = xp; g.ldo = 4 * Hd;
     if (use_pk && (reinterpret_cast<uintptr_t>(w->w_ih[dir]) & 15u) == 0 && (reinterpret_cast<uintptr_t>(w->embedding) & 15u) == 0) {
       PkParams q{};   // tcgen05, weights bulk-copied, embedding rows gathered + split on the fly
       q.g = g;
@@ -677,7 +698,7 @@ static int32_t encoder_fwd_impl(const sfb_encoder_weights* w, int32_t ndir, int3
     } else {
       SFB_PROPAGATE(launch_gemm(g, st));
     }
-    for (int s = 0; s < maxlen; ++s) {
+    for (int s = 0; s < maxlen && !persist; ++s) {
       const int t = dir == 0 ? s : maxlen - 1 - s;
       float* hp = taped ? tape.h + (size_t)s * state : ws.h[cur[dir]] + dir * state;
       float* cp = taped ? tape.c + (size_t)s * state : ws.c[cur[dir]] + dir * state;
@@ -706,6 +727,21 @@ static int32_t encoder_fwd_impl(const sfb_encoder_weights* w, int32_t ndir, int3
       }
       cur[dir] ^= 1;
     }
+  }
+  if (persist) {
+    EncPersistParams ep{};
+    for (int dir = 0; dir < ndir; ++dir) {
+      ep.whh_pk[dir] = ws.whh_pk[dir]; ep.xproj[dir] = ws.xproj + (size_t)dir * B * maxlen * 4 * Hd;
+      ep.b_ih[dir] = w->b_ih[dir]; ep.b_hh[dir] = w->b_hh[dir];
+    }
+    ep.seq = by_token ? seq : nullptr;
+    ep.lengths = lengths; ep.ctx = ctx; ep.ld_ctx = (long long)maxlen * H; ep.H = H;
+    ep.h_fin = ws.h[0]; ep.c_fin = ws.c[0];
+    if (taped) { ep.tape_h = tape.h; ep.tape_c = tape.c; ep.tape_g = tape.gates; }
+    ep.hpk = ws.ep_hpk; ep.bar = ws.ep_bar;
+    ep.ndir = ndir; ep.Hd = Hd; ep.B = B; ep.maxlen = maxlen;
+    SFB_PROPAGATE(launch_encoder_persist(ep, st));
+    cur[0] = cur[1] = 0;
   }
   // decoder_init = tanh(encoder2decoder(h_t)), h_t = cat(reverse, forward) when bidirectional (model.py:92-99)
   GemmParams e{};

@@ -242,6 +242,34 @@ struct FusedTextPlan {
 FusedTextPlan text_score_fused_plan(int B, int L, int A, int H, int E, int F, bool with_q, int num_sms);
 int32_t launch_text_score_fused(const FusedTextScoreParams& q, cudaStream_t stream, void* sync_ws, size_t sync_bytes);
 
+// ---------------------------------------------------------------- encoder_persist.cu
+// the recurrent part of EncoderLSTM for all time steps in one launch (W_hh resident in shared memory)
+struct EncPersistParams {
+  const unsigned char* whh_pk[2];     // per direction: gate-interleaved packed W_hh (pack.cu, lstm_H = Hd)
+  const float* xproj[2];              // per direction: hoisted input projection [B * maxlen][4 Hd], or with `seq` the
+                                      // per-token table [vocab][4 Hd] = Emb W_ih^T
+  const int32_t* seq;                 // [B][maxlen] word ids selecting the rows of xproj, or NULL (rows by position)
+  const float* b_ih[2]; const float* b_hh[2];
+  const int32_t* lengths;
+  float* ctx; long long ld_ctx; int H;   // [B][maxlen][H = ndir * Hd]
+  float* h_fin; float* c_fin;         // [ndir][B][Hd] final states
+  float* tape_h; float* tape_c; float* tape_g;   // optional training tape: h, c [maxlen + 1][B][Hd], gate activations [maxlen][B][4 Hd]
+  unsigned char* hpk;                 // [groups][2 parities][Hd / 64][2 * (N / 8) * 1024] packed h between steps
+  unsigned long long* bar;            // [groups] step counters (+ status word)
+  int ndir, Hd, B, maxlen;
+  // filled by the launcher
+  int NG, Bg, N;
+  unsigned int* status;
+  unsigned long long* trace;
+};
+struct EncPersistPlan {
+  bool ok;
+  int NG, Bg, N, grid;
+  size_t smem, hpk_bytes, bar_bytes;
+};
+EncPersistPlan encoder_persist_plan(int ndir, int Hd, int B, int num_sms);
+int32_t launch_encoder_persist(const EncPersistParams& q, cudaStream_t stream);
+
 // both halves of the step as one launch (step_fused_b.cu: step_kernel)
 struct FusedStepParams {
   FusedVisLstmParams a;

@@ -686,9 +686,10 @@ def encoder_lstm(w: Dict[str, Tensor], seq: Tensor, lengths, bidirectional: bool
     need = lib.sfb_encoder_lstm_workspace_bytes(ndir, Hd, Ew, B, maxlen)
     ws = _workspace(need, dev, ("encoder_lstm", ndir, Hd, Ew, B, maxlen))
     ctx = torch.empty(B, maxlen, H, device=dev); dec = torch.empty(B, H, device=dev); c_t = torch.empty(B, H, device=dev)
-    check(lib.sfb_encoder_lstm_fwd(C.byref(ew), ndir, Hd, Ew, B, maxlen, _p(seq32, torch.int32, "seq"),
-                                   _p(lens_d, torch.int32, "lengths"), _p(drop_embed, name="drop_embed"),
-                                   _p(ctx), _p(dec), _p(c_t), ws.data_ptr(), ws.numel(), _stream()))
+    vocab = int(w["embedding.weight"].shape[0])
+    check(lib.sfb_encoder_lstm_fwd_vocab(C.byref(ew), vocab, ndir, Hd, Ew, B, maxlen, _p(seq32, torch.int32, "seq"),
+                                         _p(lens_d, torch.int32, "lengths"), _p(drop_embed, name="drop_embed"),
+                                         _p(ctx), _p(dec), _p(c_t), ws.data_ptr(), ws.numel(), _stream()))
     return ctx, dec, c_t
 
 

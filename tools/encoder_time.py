@@ -18,9 +18,13 @@ def t(fn, n=20):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) * 1e3 / n
 for opt in (0, 1):
+    ops.set_option("disable_persist", opt)
+    print("encoder_lstm B=%d L=%d (disable_persist=%d): %.1f us per call, %d launches" % (B, L, opt, t(lambda: ops.encoder_lstm(we, seq, lengths)), ops.last_launch_count()))
+for opt in (0, 1):
     ops.set_option("disable_tc", opt)
     print("encoder_lstm B=%d L=%d (disable_tc=%d): %.1f us per call, %d launches" % (B, L, opt, t(lambda: ops.encoder_lstm(we, seq, lengths)), ops.last_launch_count()))
 ops.set_option("disable_tc", 0)
+ops.set_option("disable_persist", 0)
 import ctypes as C
 from speaker_follower_b200 import _lib
 ops.set_option("trace", 1)
@@ -31,4 +35,8 @@ t0 = buf[0]
 for k in range(min(n, 8)):
     e, wt, x = buf[16 * k], buf[16 * k + 1], buf[16 * k + 2]
     print("launch %d: entry %.1f wait_done %.1f exit %.1f us" % (k, (e - t0) / 1e3, (wt - t0) / 1e3, (x - t0) / 1e3))
+    ph = [buf[16 * k + j] for j in range(4, 16)]
+    if any(ph):
+        base = min(v for v in ph if v)
+        print("      marks (us since the first): " + "  ".join("%d:%.2f" % (j + 4, (v - base) / 1e3) for j, v in enumerate(ph) if v))
 print("launch %d: entry %.1f" % (n - 1, (buf[16 * (n - 1)] - t0) / 1e3))
