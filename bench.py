@@ -832,14 +832,121 @@ def run_train(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_speaker(args, rank, local_rank, world):
+    """--config c3: one speaker scoring pass (speaker.py:123-202) at the C3 shape — N=256 paths of T=6 steps through
+    SpeakerEncoderLSTM, then 80 teacher-forced words through SpeakerDecoderLSTM — through the module API of
+    speaker_follower_b200.model, replayed from one CUDA graph.  Launch-latency bound at this size: the
+    line reports the time per word step and the algorithmic bytes of a decoder step beside it, not a roofline claim."""
+    import __graft_entry__ as ge
+    ge.build()
+    from speaker_follower_b200 import model as M, synth
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    N, T, W = 256, 6, 80
+    we, wd = synth.speaker_encoder_weights(), synth.speaker_decoder_weights()
+    enc = M.SpeakerEncoderLSTM(synth.FEAT, synth.FEAT, synth.HID, 0.5).to(dev).eval()
+    dec = M.SpeakerDecoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0.5, glove=wd["embedding.weight"].numpy()).to(dev).eval()
+    enc.load_state_dict(we, strict=False); dec.load_state_dict(wd, strict=False)
+    g = torch.Generator().manual_seed(5 + rank)
+    x = synth.follower_step_inputs(N, 8, 6, seed=3)
+    feats = [(x["visual_context"] * (0.9 + 0.02 * t)).to(dev) for t in range(T)]          # T x [N, 36, 2176]
+    acts = [x["all_u_t"][:, 1 + (t % 4)].contiguous().to(dev) for t in range(T)]          # T x [N, 2176]
+    mask = (torch.arange(T).unsqueeze(0) >= torch.randint(4, T + 1, (N, 1), generator=g)).to(dev)
+    words = torch.randint(4, synth.VOCAB, (N, W), generator=g).to(dev)
+
+    def scoring_pass():
+        with torch.no_grad():
+            ctx, h, c = enc(acts, feats)
+            score = torch.zeros(N, device=dev)
+            for w in range(W):
+                h, c, alpha, logit = dec(words[:, w:w + 1], h, c, ctx, mask)
+                score = score + torch.log_softmax(logit, 1).gather(1, words[:, w:w + 1]).squeeze(1)
+        return score
+
+    for _ in range(3):
+        ref_score = scoring_pass()
+    torch.cuda.synchronize()
+    launch = "eager"
+    replay = scoring_pass
+    try:
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            out = scoring_pass()
+        gr.replay(); torch.cuda.synchronize()
+        assert torch.allclose(out, ref_score, atol=1e-3, rtol=1e-4)
+        replay, launch = gr.replay, "one CUDA graph per scoring pass"
+    except Exception as e:  # pragma: no cover
+        launch = "eager (graph capture failed: %s)" % str(e)[:80]
+    if dist is not None:
+        dist.barrier()
+    n = max(5, min(args.steps, 50))
+    for _ in range(3):
+        replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        replay()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    t = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        cpu = {"value": None, "unit": "word-steps/s", "cores": torch.get_num_threads(), "kind": "reference", "sample": "unavailable"}
+        try:
+            from oracle import make_ref, ref_loader
+            make_ref.make()
+            mods = ref_loader.speaker_modules(we, wd)
+            if mods is not None:
+                renc, rdec = mods
+                fc, ac, mc, wc = [f.cpu() for f in feats], [a.cpu() for a in acts], mask.cpu().bool(), words.cpu()
+                torch.cuda.disabled = True      # the reference's own switch (utils.py:195-204, --no_cuda): keep its zeros on the host
+                t0 = time.perf_counter()
+                with torch.no_grad():
+                    ctx, h, c = renc(ac, fc)
+                    nw = 0
+                    while nw < W and time.perf_counter() - t0 < 20.0:
+                        h, c, alpha, logit = rdec(wc[:, nw:nw + 1], h, c, ctx, mc)
+                        nw += 1
+                dt = time.perf_counter() - t0
+                torch.cuda.disabled = False
+                cpu.update(value=nw / dt, sample="encoder (T=%d) + %d of %d word steps of the same pass (%.1f s), the reference's own "
+                                                "model.py (oracle/_ref) on the host cores" % (T, nw, W, dt))
+        except Exception as e:  # pragma: no cover
+            cpu["sample"] = "failed: %s" % str(e)[:120]
+        P_dec = 2961887
+        dec_bytes = 4 * (N * T * synth.HID + P_dec + N * synth.WORD + 4 * N * synth.HID + N * synth.VOCAB)
+        line = {"metric": "speaker scoring word-steps/sec", "value": world * W * 1e3 / ms, "unit": "word-steps/s", "n_gpus": world, "steps": n,
+                "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "C3: speaker scoring pass, N=%d paths, T=%d path steps (SpeakerEncoderLSTM) + %d teacher-forced "
+                                       "words (SpeakerDecoderLSTM + log-softmax gather), per GPU" % (N, T, W),
+                           "launch": launch, "parallelism": "replicas x%d" % world},
+                "us_per_word_step_incl_encoder": ms * 1e3 / W,
+                "decoder_step_algorithmic_bytes": dec_bytes,
+                "note": "latency-bound at this size: %.1f MB per decoder step would take %.1f us at the measured HBM peak" % (
+                    dec_bytes / 1e6, dec_bytes / (peaks()[0] * 1e3)),
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="decode", choices=["decode", "c2", "c4", "c5"],
-                    help="decode (default): the headline decode-steps/sec; c2: training step; c4: pragmatic inference; c5: data augmentation")
+    ap.add_argument("--config", default="decode", choices=["decode", "c2", "c3", "c4", "c5"],
+                    help="decode (default): the headline decode-steps/sec; c2: training step; c3: speaker scoring pass; "
+                         "c4: pragmatic inference; c5: data augmentation")
     ap.add_argument("--profile-steps", type=int, default=0,
                     help="run this many eager (no CUDA graph) steps after warm-up and exit: the command ncu wraps")
     args = ap.parse_args()
@@ -852,6 +959,8 @@ def main():
         run_pragmatic(args, rank, local_rank, world)
     elif args.config == "c2":
         run_train(args, rank, local_rank, world)
+    elif args.config == "c3":
+        run_speaker(args, rank, local_rank, world)
     else:
         run_gpu(args, rank, local_rank, world)
 

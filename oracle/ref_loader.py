@@ -52,3 +52,21 @@ def follower_decoder(weights, device="cpu"):
     missing = dec.load_state_dict({k: v for k, v in weights.items()}, strict=False)
     assert not missing.unexpected_keys, missing
     return dec.to(device).eval()
+
+
+def speaker_modules(enc_weights, dec_weights, device="cpu"):
+    """The reference's SpeakerEncoderLSTM / SpeakerDecoderLSTM (model.py:400-519) carrying the given weights, eval mode."""
+    m = load()
+    if m is None:
+        return None
+    import numpy as np
+    H = enc_weights["lstm.weight_hh"].shape[1]
+    F = enc_weights["visual_attention_layer.linear_in_v.weight"].shape[1]
+    E = enc_weights["lstm.weight_ih"].shape[1] - F
+    enc = m.SpeakerEncoderLSTM(E, F, H, 0.5)
+    vocab, word = dec_weights["embedding.weight"].shape
+    dec = m.SpeakerDecoderLSTM(vocab, word, H, 0.5, glove=np.asarray(dec_weights["embedding.weight"].cpu().numpy()))
+    for mod, w in ((enc, enc_weights), (dec, dec_weights)):
+        missing = mod.load_state_dict({k: v for k, v in w.items()}, strict=False)
+        assert not missing.unexpected_keys, missing
+    return enc.to(device).eval(), dec.to(device).eval()
