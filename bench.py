@@ -27,6 +27,7 @@ import torch  # noqa: E402
 B, L, A = 100, 80, 8
 N_VIEWPOINTS = 10567          # R2R viewpoints -> 3.1 GB table, >> L2
 ATTN_NCU_TRAFFIC = 74742528   # dram__bytes_read.sum + dram__bytes_write.sum of one vis_lstm_fused_kernel launch (ncu --set full, cold)
+STEP_NCU_TRAFFIC = 110616064  # same for one step_kernel launch (profiles/r02_ncu_full_summary.txt: 103.64 MB read + 6.98 MB written)
 POOL = 10                     # per-step input sets = the steps of one episode (episode_len = 10, train.py:29)
 N_CTX = 4                     # rotating episodes: instruction contexts (16 MB each + 32 MB of per-episode projections)
 
@@ -406,6 +407,14 @@ def run_gpu(args, rank, local_rank, world):
             step(i, first=(i == 0), e=0)
         singles.append(gph)
 
+    # the step kernel alone (the dominant kernel: one launch = one decode step): steps 1..POOL-1 of an episode chained in
+    # one graph, no per-episode projection, fresh slabs / candidates per launch
+    chain = None
+    if blob is not None:
+        chain = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(chain):
+            for i in range(1, POOL):
+                step(i, first=False, e=0)
     log("graphs captured")
 
     def run_steps(k):
@@ -433,6 +442,19 @@ def run_gpu(args, rank, local_rank, world):
     value, ms = sfdist.aggregate_rate(args.steps, e0.elapsed_time(e1), device=dev)   # whole job / slowest rank
 
     log("timed region done: %.3f ms/step" % (ms / args.steps))
+    step_kernel_us = None
+    if chain is not None and launches_per_step[0] == 1:
+        for _ in range(3):
+            chain.replay()
+        torch.cuda.synchronize()
+        ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_chain = 40
+        ec0.record()
+        for _ in range(n_chain):
+            chain.replay()
+        ec1.record(); torch.cuda.synchronize()
+        step_kernel_us = ec0.elapsed_time(ec1) * 1e3 / (n_chain * (POOL - 1))
+        log("step kernel alone: %.2f us per launch" % step_kernel_us)
     # ---- e2e: same step through the public ops API with HOST buffers (pinned), H2D + D2H inside the timed region.
     # Host inputs per step (what the agent holds on the host after env.observe): viewpoint / view indices, the
     # action-candidate embeddings + validity (follower.py:300-320); result read back: a_t + logits (follower.py:510).
@@ -618,13 +640,22 @@ def run_gpu(args, rank, local_rank, world):
                     "steps": e2e_steps},
             "agent": agent_stats,
             "gpu_launches": launches_per_step[0] * args.steps + proj_launches * (args.steps // POOL + (1 if args.steps % POOL else 0)),
-            "roofline": {"kernel": "vis_lstm_fused_kernel (36-view attention gather + gate GEMM + LSTM cell, one launch)", "bound": "hbm",
+            "roofline": ({"kernel": "step_kernel (the whole decode step in one launch)", "bound": "hbm",
+                          "achieved": step_bytes / (step_kernel_us * 1e-6) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": step_bytes / (step_kernel_us * 1e-6) / 1e9 / hbm_peak, "traffic": STEP_NCU_TRAFFIC,
+                          "peak_source": peak_src, "bytes_per_launch": step_bytes, "us_per_launch": step_kernel_us,
+                          "how": "360 launches (40 replays of a graph of 9 chained steps, no per-episode projection) between two "
+                                 "CUDA events, fresh slabs and candidates per launch; algorithmic bytes = SURVEY 8d's 104.9 MB per "
+                                 "step; traffic = dram read+write of one launch from profiles/r02_ncu_full_summary.txt (cold caches)"}
+                         if step_kernel_us else None),
+            "roofline_first_half": {"kernel": "vis_lstm_fused_kernel (36-view attention gather + gate GEMM + LSTM cell) launched alone",
+                         "bound": "hbm",
                          "achieved": attn_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": attn_gbs / hbm_peak,
                          "traffic": ATTN_NCU_TRAFFIC, "peak_source": peak_src, "bytes_per_launch": attn_bytes,
                          "us_per_launch": attn_ms * 1e3,
                          "how": "%d back-to-back launches between two CUDA events, fresh slabs per launch; algorithmic bytes = slabs "
                                 "4*B*36*F + fp32 LSTM weights 4*(4H*(E+F)+4H*H+8H) + states 4*B*(E+4H) (DESIGN.md section 6); traffic = "
-                                "dram read+write per launch from profiles/r02_ncu_full_summary.txt (cold caches)" % n_attn},
+                                "dram read+write per launch (ncu --set full, cold caches)" % n_attn},
             "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s",
                               "frac": step_gbs / hbm_peak, "bytes_per_step": step_bytes},
             "cpu_baseline": {"value": cpu_sps, "unit": "steps/s", "cores": threads, "kind": _CPU_STATE["kind"],
@@ -637,6 +668,8 @@ def run_gpu(args, rank, local_rank, world):
                 "value_over_gpu_baseline_device_inputs": value / world / gpu_base["value_device_inputs"],
                 "e2e_over_gpu_baseline_device_inputs": e2e_value / world / gpu_base["value_device_inputs"]}),
         }
+        if line["roofline"] is None:   # the step was not one launch on this shape / with these options
+            line["roofline"] = line["roofline_first_half"]
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
