@@ -438,6 +438,36 @@ int32_t sfb_speaker_decoder_step_packed_fwd(const sfb_speaker_decoder_weights* w
 /* Number of kernels the last successful call on this thread enqueued (bench.py's gpu_launches). */
 int32_t sfb_last_launch_count(void);
 
+/* ---- speaker modules under autograd (train_speaker.py:67-118 -> speaker.py:376-395 loss.backward()).
+ * Hand-written backward of SpeakerEncoderLSTM._forward_one_step (model.py:429-435) and of SpeakerDecoderLSTM.forward
+ * (model.py:487-519, default branch), on the same kernels as sfb_follower_step_bwd.  fwd_workspace: the workspace the
+ * step's FORWARD call ran in (sfb_speaker_encoder_step_fwd / _packed_fwd, sfb_speaker_decoder_step_fwd / _packed_fwd):
+ * it still holds the attention output, the attention weights, the activated gates, the dropped h_1 and h~.
+ * Gradients w.r.t. parameters are written to (accumulate == 0) or added to (accumulate != 0) the state_dict-shaped
+ * buffers of `grads` (NULL = skip); gradients w.r.t. the recurrent state (and the decoder's ctx) are returned.  The
+ * word embedding is frozen GloVe in the reference configuration (model.py:469-472) and receives no gradient; the
+ * action embeddings and image features are data. */
+size_t  sfb_speaker_encoder_step_bwd_workspace_bytes(const sfb_dims* dims, int32_t B);
+int32_t sfb_speaker_encoder_step_bwd(const sfb_dims* dims, const sfb_vis_lstm_weights* w, int32_t B,
+                                     const float* action_embedding, const sfb_visual_source* vis, const float* h0,
+                                     const float* c0, const float* drop_x, const float* c1, const void* fwd_workspace,
+                                     const float* g_h1, const float* g_c1, float* d_h0, float* d_c0,
+                                     const sfb_follower_grads* grads /* lstm_* and va_* fields */, int32_t accumulate,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+typedef struct sfb_speaker_decoder_grads {
+  float *lstm_w_ih, *lstm_w_hh, *lstm_b_ih, *lstm_b_hh;
+  float *w_in, *w_out;      /* attention_layer.linear_in / linear_out */
+  float *w_voc, *b_voc;     /* decoder2action */
+} sfb_speaker_decoder_grads;
+size_t  sfb_speaker_decoder_step_bwd_workspace_bytes(int32_t H, int32_t Ew, int32_t vocab, int32_t B);
+int32_t sfb_speaker_decoder_step_bwd(const sfb_speaker_decoder_weights* w, int32_t H, int32_t Ew, int32_t vocab,
+                                     int32_t B, int32_t T, const int32_t* prev_word, const float* h0, const float* c0,
+                                     const float* ctx, const uint8_t* ctx_mask, const float* drop_e, const float* drop_h,
+                                     const float* c1, const float* alpha, const void* fwd_workspace,
+                                     const float* g_h1, const float* g_c1, const float* g_logit,
+                                     float* d_h0, float* d_c0, float* d_ctx, const sfb_speaker_decoder_grads* grads,
+                                     int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

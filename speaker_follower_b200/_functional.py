@@ -112,6 +112,60 @@ class EncoderLstmKernelFn(torch.autograd.Function):
         return (None, None, None, None, *[(grads.get(k) if nd else None) for k, nd in zip(ctx_.names, need)])
 
 
+class SpeakerEncStepKernelFn(torch.autograd.Function):
+    """SpeakerEncoderLSTM._forward_one_step (model.py:429-435) forward AND backward on the library.  The forward runs in its
+    own workspace (attention output, attention weights and activated gates stay there for sfb_speaker_encoder_step_bwd);
+    the action embedding and the image features are data."""
+
+    @staticmethod
+    def forward(ctx_, run_cuda, names, drop_x, a, v, h0, c0, *params):
+        (h1, c1), fwd_ws = run_cuda()
+        ctx_.names, ctx_.drop_x, ctx_.fwd_ws = names, drop_x, fwd_ws
+        ctx_.save_for_backward(a, v, h0, c0, c1, *params)
+        return h1, c1
+
+    @staticmethod
+    def backward(ctx_, g_h1, g_c1):
+        from . import ops
+        a, v, h0, c0, c1, *params = ctx_.saved_tensors
+        w = {k: p.detach() for k, p in zip(ctx_.names, params)}
+        grads = {k: torch.zeros_like(p) for k, p in w.items() if not k.startswith("encoder2decoder.")}
+        with torch.no_grad():
+            d_h0, d_c0 = ops.speaker_encoder_step_bwd(w, a.detach(), v.detach(), h0.detach(), c0.detach(), ctx_.drop_x, c1, ctx_.fwd_ws,
+                                                      g_h1, g_c1, grads, accumulate=False)
+        need = ctx_.needs_input_grad
+        gpar = [(grads.get(k) if nd else None) for k, nd in zip(ctx_.names, need[7:])]
+        return (None, None, None, None, None, d_h0 if need[5] else None, d_c0 if need[6] else None, *gpar)
+
+
+class SpeakerDecStepKernelFn(torch.autograd.Function):
+    """SpeakerDecoderLSTM.forward (model.py:487-519, default branch) forward AND backward on the library.  The word
+    embedding is frozen GloVe in the reference configuration and receives no gradient here."""
+
+    @staticmethod
+    def forward(ctx_, run_cuda, names, prev_word, ctx_mask, drop_e, drop_h, h0, c0, ctx, *params):
+        (h1, c1, alpha, logit), fwd_ws = run_cuda()
+        ctx_.names, ctx_.prev_word, ctx_.ctx_mask, ctx_.drop_e, ctx_.drop_h, ctx_.fwd_ws = names, prev_word, ctx_mask, drop_e, drop_h, fwd_ws
+        ctx_.save_for_backward(h0, c0, ctx, c1, alpha, *params)
+        ctx_.mark_non_differentiable(alpha)
+        return h1, c1, alpha, logit
+
+    @staticmethod
+    def backward(ctx_, g_h1, g_c1, g_alpha, g_logit):
+        from . import ops
+        h0, c0, ctx, c1, alpha, *params = ctx_.saved_tensors
+        w = {k: p.detach() for k, p in zip(ctx_.names, params)}
+        grads = {k: torch.zeros_like(p) for k, p in w.items() if k != "embedding.weight"}
+        with torch.no_grad():
+            d_h0, d_c0, d_ctx = ops.speaker_decoder_step_bwd(w, ctx_.prev_word, h0.detach(), c0.detach(), ctx.detach(), ctx_.ctx_mask,
+                                                             ctx_.drop_e, ctx_.drop_h, c1, alpha, ctx_.fwd_ws, g_h1, g_c1, g_logit,
+                                                             grads, accumulate=False)
+        need = ctx_.needs_input_grad
+        gin = [d_h0 if need[6] else None, d_c0 if need[7] else None, d_ctx if need[8] else None]
+        gpar = [(grads.get(k) if nd else None) for k, nd in zip(ctx_.names, need[9:])]
+        return (None, None, None, None, None, None, *gin, *gpar)
+
+
 class FollowerStepFn(torch.autograd.Function):
     """Forward on the CUDA kernels, backward by torch autograd over the restatement above (same inputs, same masks).
     Kept as the independent check of FollowerStepKernelFn in tests/test_gpu_train.py."""

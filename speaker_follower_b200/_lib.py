@@ -77,6 +77,10 @@ class FollowerGrads(C.Structure):
                                          "w_in", "w_out", "sc_w_h", "sc_b_h", "sc_w_a", "sc_b_a", "sc_w_out", "sc_b_out")]
 
 
+class SpeakerDecoderGrads(C.Structure):
+    _fields_ = [(n, c_float_p) for n in ("lstm_w_ih", "lstm_w_hh", "lstm_b_ih", "lstm_b_hh", "w_in", "w_out", "w_voc", "b_voc")]
+
+
 # name -> (restype, argtypes); every symbol include/sf_b200.h declares
 SIGNATURES = {
     "sfb_abi_version": (C.c_int32, []),
@@ -136,6 +140,17 @@ SIGNATURES = {
                                           c_float_p, c_float_p, c_float_p,
                                           c_float_p, c_float_p, c_float_p,
                                           C.POINTER(FollowerGrads), C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sfb_speaker_encoder_step_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(Dims), C.c_int32]),
+    "sfb_speaker_encoder_step_bwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(VisLstmWeights), C.c_int32, c_float_p,
+                                                 C.POINTER(VisualSource), c_float_p, c_float_p, c_float_p, c_float_p, C.c_void_p,
+                                                 c_float_p, c_float_p, c_float_p, c_float_p, C.POINTER(FollowerGrads), C.c_int32,
+                                                 C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sfb_speaker_decoder_step_bwd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "sfb_speaker_decoder_step_bwd": (C.c_int32, [C.POINTER(SpeakerDecoderWeights), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                 C.c_int32, c_int_p, c_float_p, c_float_p, c_float_p, c_u8_p, c_float_p, c_float_p,
+                                                 c_float_p, c_float_p, C.c_void_p, c_float_p, c_float_p, c_float_p,
+                                                 c_float_p, c_float_p, c_float_p, C.POINTER(SpeakerDecoderGrads), C.c_int32,
+                                                 C.c_void_p, C.c_size_t, C.c_void_p]),
     "sfb_nav_step": (C.c_int32, [C.POINTER(NavTables), C.c_int32, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p,
                                  c_int_p, c_int_p, c_int_p, c_float_p, c_float_p, c_int_p, C.c_void_p]),
     "sfb_eltwise_prod_scoring_fwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(ScoringWeights), C.c_int32, C.c_int32,

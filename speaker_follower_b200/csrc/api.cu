@@ -781,7 +781,8 @@ int32_t sfb_speaker_encoder_step_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
   SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SFB_PROPAGATE(visual_query(d, *w, B, h0, ws.tv, ws.q, st));
-  SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, nullptr, ws.av, ws.av_bytes, st));
+  // the attention weights stay in the workspace (tp region, [B,V] <= [B,D]) for sfb_speaker_encoder_step_bwd
+  SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, d.V <= d.D ? ws.tp : nullptr, ws.av, ws.av_bytes, st));
   return lstm_cell(d.E, d.F, d.H, w->lstm_w_ih, w->lstm_w_hh, w->lstm_b_ih, w->lstm_b_hh, B, action_embedding, nullptr,
                    ws.feat, h0, c0, drop_x, nullptr, ws.gates_act, h1, c1, nullptr, ws.tc, ws.tc_bytes, st);
 }
@@ -1300,6 +1301,53 @@ int32_t sfb_encoder_lstm_bwd(const sfb_encoder_weights* w, int32_t Hd, int32_t E
   return 0;
 }
 
+/* LSTMCell + VisualSoftDotAttention backward (model.py:389-394 / 431-434): shared by the follower step and the speaker
+ * encoder step.  dh1d: gradient w.r.t. the DROPPED h_1 (NULL when nothing consumes it), feat / gates_act / alpha_v: what
+ * the forward left behind. */
+static int32_t vis_lstm_bwd(const sfb_dims& d, const sfb_vis_lstm_weights* wl, int B, const float* u_prev, const sfb_visual_source* vis,
+                            const float* h0, const float* c0, const float* drop_x, const float* drop_h, const float* c1,
+                            const float* alpha_v, const float* feat, const float* gates_act, const float* g_h1, const float* g_c1,
+                            const float* dh1d, float* d_h0, float* d_c0, const sfb_follower_grads* gr, int acc, const BwdWs& w,
+                            cudaStream_t st) {
+  const int E = d.E, F = d.F, H = d.H, D = d.D;
+  // ---- LSTMCell backward (model.py:393-394)
+  {
+    LstmBwdParams lp{B, H, gates_act, c0, c1, g_h1, g_c1, dh1d, drop_h, w.dgates, d_c0};
+    SFB_PROPAGATE(launch_lstm_cell_bwd(lp, st));
+  }
+  if (gr->lstm_w_ih) {
+    SFB_PROPAGATE(launch_assemble_x(u_prev, feat, drop_x, w.x, B, E, F, st));
+    SFB_PROPAGATE(outer(w.dgates, 4 * H, w.x, E + F, B, 4 * H, E + F, gr->lstm_w_ih, E + F, acc, st));
+  }
+  SFB_PROPAGATE(outer(w.dgates, 4 * H, h0, H, B, 4 * H, H, gr->lstm_w_hh, H, acc, st));
+  if (gr->lstm_b_ih) SFB_PROPAGATE(launch_colsum(w.dgates, 4 * H, B, 4 * H, gr->lstm_b_ih, acc, st));
+  if (gr->lstm_b_hh) SFB_PROPAGATE(launch_colsum(w.dgates, 4 * H, B, 4 * H, gr->lstm_b_hh, acc, st));
+  SFB_PROPAGATE(bgemm(B, F, 4 * H, w.dgates, 4 * H, wl->lstm_w_ih + E, E + F, 1, w.dfeat, F, nullptr, nullptr, 0, st));   // d(x_f) = dgates W_ih[:, E:]
+  SFB_PROPAGATE(bgemm(B, H, 4 * H, w.dgates, 4 * H, wl->lstm_w_hh, H, 1, d_h0, H, nullptr, nullptr, 0, st));              // dh0 = dgates W_hh
+  // ---- VisualSoftDotAttention backward (model.py:310-326)
+  {
+    AttnBwdParams a{};
+    if (vis->visual) {
+      a.segA = vis->visual; a.strideA_b = (long long)d.V * F; a.strideA_r = F; a.lenA = F; a.lenB = 0;
+    } else {
+      const int loc = F - vis->img_dim;
+      a.segA = vis->feat_table; a.strideA_b = (long long)d.V * vis->img_dim; a.strideA_r = vis->img_dim; a.lenA = vis->img_dim; a.idxA = vis->vp_idx;
+      a.segB = vis->loc_table; a.strideB_b = (long long)d.V * loc; a.strideB_r = loc; a.lenB = loc; a.idxB = vis->view_idx;
+    }
+    a.R = d.V; a.D = F; a.alpha = alpha_v; a.ldalpha = d.V;
+    a.dout = w.dfeat; a.lddout = F; a.dout_scale = drop_x ? drop_x + E : nullptr; a.ldscale = E + F;
+    a.dq = w.dq; a.lddq = F;
+    SFB_PROPAGATE(launch_attn_bwd(a, B, st));
+  }
+  SFB_PROPAGATE(bgemm(B, D, H, h0, H, wl->va_w_h, H, 0, w.tv, D, wl->va_b_h, nullptr, 0, st));               // t_v = W_h h0 + b_h
+  SFB_PROPAGATE(outer(w.tv, D, w.dq, F, B, D, F, gr->va_w_v, F, acc, st));                                   // dW_v = t_v^T dq
+  SFB_PROPAGATE(bgemm(B, D, F, w.dq, F, wl->va_w_v, F, 0, w.dtv, D, nullptr, nullptr, 0, st));              // dt_v = W_v dq
+  SFB_PROPAGATE(outer(w.dtv, D, h0, H, B, D, H, gr->va_w_h, H, acc, st));
+  if (gr->va_b_h) SFB_PROPAGATE(launch_colsum(w.dtv, D, B, D, gr->va_b_h, acc, st));
+  SFB_PROPAGATE(bgemm(B, H, D, w.dtv, D, wl->va_w_h, H, 1, d_h0, H, nullptr, d_h0, H, st));                  // dh0 += dt_v W_h
+  return 0;
+}
+
 /* ---------------------------------------------------------------- follower decode step: backward (entry points) */
 size_t sfb_follower_step_bwd_workspace_bytes(const sfb_dims* dims, int32_t B, int32_t L, int32_t A) {
   (void)L; (void)A;
@@ -1366,42 +1414,109 @@ int32_t sfb_follower_step_bwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
   SFB_PROPAGATE(outer(w.dz, H, w.wc, H, B, H, H, gr->w_out, 2 * H, acc, st));                                 // dW_out[:, :H] = dz^T wc
   SFB_PROPAGATE(outer(w.dz, H, h1d, H, B, H, H, gr->w_out ? gr->w_out + H : nullptr, 2 * H, acc, st));       // dW_out[:, H:] = dz^T h1d
   SFB_PROPAGATE(bgemm(B, H, H, w.dt, H, wt->w_in, H, 1, w.dh1d, H, nullptr, w.dwc_dh + H, 2 * H, st));       // dh1d = dt W_in + dz W_out_h
-  // ---- LSTMCell backward (model.py:393-394)
+  return vis_lstm_bwd(d, wl, B, u_prev, vis, h0, c0, drop_x, drop_h, c1, alpha_v, feat, gates_act, g_h1, g_c1, w.dh1d, d_h0, d_c0,
+                      gr, acc, w, st);
+}
+
+/* ---------------------------------------------------------------- speaker modules: backward (train_speaker.py, speaker.py:376-395) */
+size_t sfb_speaker_encoder_step_bwd_workspace_bytes(const sfb_dims* dims, int32_t B) {
+  if (!dims || B < 1) return 0;
+  return carve_bwd(*dims, B, nullptr).bytes;
+}
+
+int32_t sfb_speaker_encoder_step_bwd(const sfb_dims* dims, const sfb_vis_lstm_weights* wl, int32_t B, const float* action_embedding,
+                                     const sfb_visual_source* vis, const float* h0, const float* c0, const float* drop_x,
+                                     const float* c1, const void* fwd_workspace, const float* g_h1, const float* g_c1,
+                                     float* d_h0, float* d_c0, const sfb_follower_grads* gr, int32_t accumulate,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  reset_launch_count();
+  SFB_PROPAGATE(check_dims(dims));
+  SFB_CHECK_ARG(wl && vis && gr, "NULL struct argument");
+  SFB_CHECK_ARG(action_embedding && h0 && c0 && c1 && fwd_workspace && d_h0 && d_c0, "NULL tensor argument");
+  SFB_CHECK_ARG(B >= 1 && dims->V <= dims->D, "B >= 1, V <= D (the forward keeps the attention weights in a [B,D] region)");
+  const sfb_dims& d = *dims;
+  const FollowerWs fw = carve_follower(d, B, 1, 1, const_cast<void*>(fwd_workspace));   // where the forward left feat / gates / alpha_v
+  const BwdWs w = carve_bwd(d, B, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, w.bytes));
+  return vis_lstm_bwd(d, wl, B, action_embedding, vis, h0, c0, drop_x, nullptr, c1, fw.tp, fw.feat, fw.gates_act, g_h1, g_c1, nullptr,
+                      d_h0, d_c0, gr, accumulate ? 1 : 0, w, static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+struct SpkDecBwdWs { float *dht, *dz, *dwc_dh, *t, *dt, *wc, *dh1d, *dgates, *x, *gT; size_t bytes; };
+SpkDecBwdWs carve_spkdec_bwd(int H, int Ew, int vocab, int B, void* p) {
+  SpkDecBwdWs w;
+  Carver c(p);
+  w.dht = c.take((size_t)B * H); w.dz = c.take((size_t)B * H); w.dwc_dh = c.take((size_t)B * 2 * H);
+  w.t = c.take((size_t)B * H); w.dt = c.take((size_t)B * H); w.wc = c.take((size_t)B * H); w.dh1d = c.take((size_t)B * H);
+  w.dgates = c.take((size_t)B * 4 * H); w.x = c.take((size_t)B * Ew);
+  w.gT = c.take((size_t)vocab * B);
+  w.bytes = c.off;
+  return w;
+}
+}  // namespace
+
+size_t sfb_speaker_decoder_step_bwd_workspace_bytes(int32_t H, int32_t Ew, int32_t vocab, int32_t B) {
+  if (H < 1 || Ew < 1 || vocab < 1 || B < 1) return 0;
+  return carve_spkdec_bwd(H, Ew, vocab, B, nullptr).bytes;
+}
+
+int32_t sfb_speaker_decoder_step_bwd(const sfb_speaker_decoder_weights* w, int32_t H, int32_t Ew, int32_t vocab, int32_t B,
+                                     int32_t T, const int32_t* prev_word, const float* h0, const float* c0, const float* ctx,
+                                     const uint8_t* ctx_mask, const float* drop_e, const float* drop_h, const float* c1,
+                                     const float* alpha, const void* fwd_workspace, const float* g_h1, const float* g_c1,
+                                     const float* g_logit, float* d_h0, float* d_c0, float* d_ctx,
+                                     const sfb_speaker_decoder_grads* gr, int32_t accumulate, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  reset_launch_count();
+  SFB_CHECK_ARG(w && gr && prev_word && h0 && c0 && ctx && c1 && alpha && fwd_workspace && d_h0 && d_c0 && d_ctx, "NULL argument");
+  SFB_CHECK_ARG(H >= 4 && (H % 4) == 0 && Ew >= 4 && (Ew % 4) == 0 && vocab >= 1 && B >= 1 && T >= 1, "bad sizes");
+  const SpkDecWs fw = carve_spkdec(H, Ew, B, T, const_cast<void*>(fwd_workspace));
+  const SpkDecBwdWs bw = carve_spkdec_bwd(H, Ew, vocab, B, workspace);
+  SFB_PROPAGATE(check_ws(workspace, workspace_bytes, bw.bytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int acc = accumulate ? 1 : 0;
+  const float* h_tilde = fw.htilde; const float* h1d = fw.h1d;
+  // ---- decoder2action backward (model.py:518): logit = W_voc h~ + b
+  if (g_logit) {
+    SFB_PROPAGATE(outer(g_logit, vocab, h_tilde, H, B, vocab, H, gr->w_voc, H, acc, st));
+    if (gr->b_voc) SFB_PROPAGATE(launch_colsum(g_logit, vocab, B, vocab, gr->b_voc, acc, st));
+    // dh~ = dlogit W_voc: a reduction over the vocabulary (991: not a multiple of 4, so not a skinny-GEMM K) — the
+    // exact-fp32 outer-product kernel with the vocabulary as its reduction dimension
+    SFB_PROPAGATE(launch_transpose(g_logit, vocab, B, vocab, bw.gT, B, st));
+    SFB_PROPAGATE(outer(bw.gT, B, w->w_voc, H, vocab, B, H, bw.dht, H, 0, st));
+  } else {
+    SFB_CHECK_CUDA(cudaMemsetAsync(bw.dht, 0, (size_t)B * H * sizeof(float), st));
+  }
+  // ---- SoftDotAttention backward (model.py:122-143), as in the follower step
+  SFB_PROPAGATE(launch_tanh_bwd(bw.dht, h_tilde, bw.dz, B * H, st));
+  SFB_PROPAGATE(bgemm(B, 2 * H, H, bw.dz, H, w->attn.w_out, 2 * H, 1, bw.dwc_dh, 2 * H, nullptr, nullptr, 0, st));   // [dwc | dh1d] = dz W_out
+  SFB_PROPAGATE(bgemm(B, H, H, h1d, H, w->attn.w_in, H, 0, bw.t, H, nullptr, nullptr, 0, st));                      // t = W_in h1d
   {
-    LstmBwdParams lp{B, H, gates_act, c0, c1, g_h1, g_c1, w.dh1d, drop_h, w.dgates, d_c0};
+    AttnBwdParams a{};
+    a.segA = ctx; a.strideA_b = (long long)T * H; a.strideA_r = H; a.lenA = H; a.lenB = 0;
+    a.mask = ctx_mask; a.ldmask = T; a.R = T; a.D = H;
+    a.alpha = alpha; a.ldalpha = T; a.dout = bw.dwc_dh; a.lddout = 2 * H; a.qv = bw.t; a.ldq = H;
+    a.dq = bw.dt; a.lddq = H; a.drows = d_ctx; a.wsum = bw.wc; a.ldwsum = H;
+    SFB_PROPAGATE(launch_attn_bwd(a, B, st));
+  }
+  SFB_PROPAGATE(outer(bw.dt, H, h1d, H, B, H, H, gr->w_in, H, acc, st));
+  SFB_PROPAGATE(outer(bw.dz, H, bw.wc, H, B, H, H, gr->w_out, 2 * H, acc, st));
+  SFB_PROPAGATE(outer(bw.dz, H, h1d, H, B, H, H, gr->w_out ? gr->w_out + H : nullptr, 2 * H, acc, st));
+  SFB_PROPAGATE(bgemm(B, H, H, bw.dt, H, w->attn.w_in, H, 1, bw.dh1d, H, nullptr, bw.dwc_dh + H, 2 * H, st));       // dh1d = dt W_in + dz W_out_h
+  // ---- LSTMCell backward (model.py:515); x = embedding(previous_word) (.) drop_e, the embedding is frozen GloVe
+  {
+    LstmBwdParams lp{B, H, fw.gates_act, c0, c1, g_h1, g_c1, bw.dh1d, drop_h, bw.dgates, d_c0};
     SFB_PROPAGATE(launch_lstm_cell_bwd(lp, st));
   }
   if (gr->lstm_w_ih) {
-    SFB_PROPAGATE(launch_assemble_x(u_prev, feat, drop_x, w.x, B, E, F, st));
-    SFB_PROPAGATE(outer(w.dgates, 4 * H, w.x, E + F, B, 4 * H, E + F, gr->lstm_w_ih, E + F, acc, st));
+    SFB_PROPAGATE(launch_gather_embed(w->embedding, Ew, prev_word, drop_e, bw.x, B, 1, st));
+    SFB_PROPAGATE(outer(bw.dgates, 4 * H, bw.x, Ew, B, 4 * H, Ew, gr->lstm_w_ih, Ew, acc, st));
   }
-  SFB_PROPAGATE(outer(w.dgates, 4 * H, h0, H, B, 4 * H, H, gr->lstm_w_hh, H, acc, st));
-  if (gr->lstm_b_ih) SFB_PROPAGATE(launch_colsum(w.dgates, 4 * H, B, 4 * H, gr->lstm_b_ih, acc, st));
-  if (gr->lstm_b_hh) SFB_PROPAGATE(launch_colsum(w.dgates, 4 * H, B, 4 * H, gr->lstm_b_hh, acc, st));
-  SFB_PROPAGATE(bgemm(B, F, 4 * H, w.dgates, 4 * H, wl->lstm_w_ih + E, E + F, 1, w.dfeat, F, nullptr, nullptr, 0, st));   // d(x_f) = dgates W_ih[:, E:]
-  SFB_PROPAGATE(bgemm(B, H, 4 * H, w.dgates, 4 * H, wl->lstm_w_hh, H, 1, d_h0, H, nullptr, nullptr, 0, st));              // dh0 = dgates W_hh
-  // ---- VisualSoftDotAttention backward (model.py:310-326)
-  {
-    AttnBwdParams a{};
-    if (vis->visual) {
-      a.segA = vis->visual; a.strideA_b = (long long)d.V * F; a.strideA_r = F; a.lenA = F; a.lenB = 0;
-    } else {
-      const int loc = F - vis->img_dim;
-      a.segA = vis->feat_table; a.strideA_b = (long long)d.V * vis->img_dim; a.strideA_r = vis->img_dim; a.lenA = vis->img_dim; a.idxA = vis->vp_idx;
-      a.segB = vis->loc_table; a.strideB_b = (long long)d.V * loc; a.strideB_r = loc; a.lenB = loc; a.idxB = vis->view_idx;
-    }
-    a.R = d.V; a.D = F; a.alpha = alpha_v; a.ldalpha = d.V;
-    a.dout = w.dfeat; a.lddout = F; a.dout_scale = drop_x ? drop_x + E : nullptr; a.ldscale = E + F;
-    a.dq = w.dq; a.lddq = F;
-    SFB_PROPAGATE(launch_attn_bwd(a, B, st));
-  }
-  SFB_PROPAGATE(bgemm(B, D, H, h0, H, wl->va_w_h, H, 0, w.tv, D, wl->va_b_h, nullptr, 0, st));               // t_v = W_h h0 + b_h
-  SFB_PROPAGATE(outer(w.tv, D, w.dq, F, B, D, F, gr->va_w_v, F, acc, st));                                   // dW_v = t_v^T dq
-  SFB_PROPAGATE(bgemm(B, D, F, w.dq, F, wl->va_w_v, F, 0, w.dtv, D, nullptr, nullptr, 0, st));              // dt_v = W_v dq
-  SFB_PROPAGATE(outer(w.dtv, D, h0, H, B, D, H, gr->va_w_h, H, acc, st));
-  if (gr->va_b_h) SFB_PROPAGATE(launch_colsum(w.dtv, D, B, D, gr->va_b_h, acc, st));
-  SFB_PROPAGATE(bgemm(B, H, D, w.dtv, D, wl->va_w_h, H, 1, d_h0, H, nullptr, d_h0, H, st));                  // dh0 += dt_v W_h
-  return 0;
+  SFB_PROPAGATE(outer(bw.dgates, 4 * H, h0, H, B, 4 * H, H, gr->lstm_w_hh, H, acc, st));
+  if (gr->lstm_b_ih) SFB_PROPAGATE(launch_colsum(bw.dgates, 4 * H, B, 4 * H, gr->lstm_b_ih, acc, st));
+  if (gr->lstm_b_hh) SFB_PROPAGATE(launch_colsum(bw.dgates, 4 * H, B, 4 * H, gr->lstm_b_hh, acc, st));
+  return bgemm(B, H, 4 * H, bw.dgates, 4 * H, w->lstm_w_hh, H, 1, d_h0, H, nullptr, nullptr, 0, st);                // dh0 = dgates W_hh
 }
 
 /* The first half of a decode step alone (model.py:389-393): attention gather + gate GEMM + LSTM cell from carried
@@ -1554,7 +1669,7 @@ int32_t sfb_speaker_encoder_step_packed_fwd(const sfb_dims* dims, const sfb_vis_
     side.seg[2] = PackSeg{h0, d.H, d.H, nullptr, 0, nullptr};
     side.ntile = gpl.nz; side.R = gpl.NB; side.rows_per_tile = gpl.rows_per_z; side.rows_valid = B; side.lstm_H = 0;
     side.out = ws.bpk;
-    SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, nullptr, ws.av, ws.av_bytes, st, &pk));
+    SFB_PROPAGATE(visual_attend(d, B, ws.q, *vis, ws.feat, d.V <= d.D ? ws.tp : nullptr, ws.av, ws.av_bytes, st, &pk));
   }
   // model.py:432-434  LSTMCell(drop(cat(action_embedding, feature)), (h, c))
   PkParams q{};

@@ -320,15 +320,14 @@ class SpeakerEncoderLSTM(_PackedWeights, nn.Module):
         for a, v in zip(batched_action_embeddings, world_state_embeddings):
             dx = self._drop.mask(self.training, (B, self.action_embedding_size + self.word_embedding_size), dev)
             a, v = a.contiguous(), v.contiguous()
-            if grad:   # forward on the CUDA kernels, gradients by torch autograd over _functional
+            if grad:   # forward AND backward on the CUDA kernels (sfb_speaker_encoder_step_bwd); a per-step workspace is the tape
                 def run_cuda(a=a, v=v, h=h, c=c, dx=dx):
                     with torch.no_grad():
-                        return ops.speaker_encoder_step({k: t.detach() for k, t in w.items()}, a, v, h.detach(), c.detach(), dx,
-                                                        packed=packed)
-
-                def restate(a_, v_, h_, c_, *ps, dx=dx):
-                    return Fn.speaker_encoder_step(dict(zip(names, ps)), a_, v_, h_, c_, dx)
-                h, c = Fn.RecomputeFn.apply(run_cuda, restate, (), a, v, h, c, *[w[k] for k in names])
+                        wd = {k: t.detach() for k, t in w.items()}
+                        need = ops._lib.load().sfb_follower_step_workspace_bytes(ops.C.byref(ops.follower_dims(wd, v.shape[1])), B, 1, 1)
+                        fwd_ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+                        return ops.speaker_encoder_step(wd, a, v, h.detach(), c.detach(), dx, packed=packed, workspace=fwd_ws), fwd_ws
+                h, c = Fn.SpeakerEncStepKernelFn.apply(run_cuda, names, dx, a, v, h, c, *[w[k] for k in names])
             else:
                 h, c = ops.speaker_encoder_step(w, a, v, h, c, dx, packed=packed)
             hs.append(h)
@@ -374,14 +373,27 @@ class SpeakerDecoderLSTM(_PackedWeights, nn.Module):
         h_0, c_0, ctx = h_0.contiguous(), c_0.contiguous(), ctx.contiguous()
         packed = self._packer.get({k: v.detach() for k, v in w.items()})
         if torch.is_grad_enabled() and any(t.requires_grad for t in (h_0, c_0, ctx, *w.values())):
-            names = list(w.keys())   # forward on the CUDA kernels, gradients by torch autograd over _functional
+            names = list(w.keys())
+            if w["embedding.weight"].requires_grad:
+                # a trainable embedding (no GloVe) needs a scatter-add the library does not have: differentiate through the
+                # torch restatement, forward still on the kernels
+                def run_cuda():
+                    with torch.no_grad():
+                        return ops.speaker_decoder_step({k: t.detach() for k, t in w.items()}, previous_word, h_0.detach(),
+                                                        c_0.detach(), ctx.detach(), ctx_mask, drop_e, drop_h, packed=packed)
 
+                def restate(h_, c_, x_, *ps):
+                    return Fn.speaker_decoder_step(dict(zip(names, ps)), previous_word, h_, c_, x_, ctx_mask, drop_e, drop_h)
+                return Fn.RecomputeFn.apply(run_cuda, restate, (2,), h_0, c_0, ctx, *[w[k] for k in names])
+
+            # forward AND backward on the CUDA kernels (sfb_speaker_decoder_step_bwd); a per-step workspace is the tape
             def run_cuda():
                 with torch.no_grad():
-                    return ops.speaker_decoder_step({k: t.detach() for k, t in w.items()}, previous_word, h_0.detach(),
-                                                    c_0.detach(), ctx.detach(), ctx_mask, drop_e, drop_h, packed=packed)
-
-            def restate(h_, c_, x_, *ps):
-                return Fn.speaker_decoder_step(dict(zip(names, ps)), previous_word, h_, c_, x_, ctx_mask, drop_e, drop_h)
-            return Fn.RecomputeFn.apply(run_cuda, restate, (2,), h_0, c_0, ctx, *[w[k] for k in names])
+                    T = ctx.shape[1]
+                    need = ops._lib.load().sfb_speaker_decoder_step_workspace_bytes(self.hidden_size, self.vocab_embedding_size, B, T)
+                    fwd_ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+                    return ops.speaker_decoder_step({k: t.detach() for k, t in w.items()}, previous_word, h_0.detach(), c_0.detach(),
+                                                    ctx.detach(), ctx_mask, drop_e, drop_h, packed=packed, workspace=fwd_ws), fwd_ws
+            return Fn.SpeakerDecStepKernelFn.apply(run_cuda, names, previous_word, ctx_mask, drop_e, drop_h, h_0, c_0, ctx,
+                                                   *[w[k] for k in names])
         return ops.speaker_decoder_step(w, previous_word, h_0, c_0, ctx, ctx_mask, drop_e, drop_h, packed=packed)

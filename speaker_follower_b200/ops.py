@@ -807,6 +807,67 @@ def speaker_decoder_step(w: Dict[str, Tensor], prev_word: Tensor, h0: Tensor, c0
     return h1, c1, alpha, logit
 
 
+_SPK_DEC_GRAD_FIELDS = {"lstm_w_ih": "lstm.weight_ih", "lstm_w_hh": "lstm.weight_hh", "lstm_b_ih": "lstm.bias_ih",
+                        "lstm_b_hh": "lstm.bias_hh", "w_in": "attention_layer.linear_in.weight",
+                        "w_out": "attention_layer.linear_out.weight", "w_voc": "decoder2action.weight", "b_voc": "decoder2action.bias"}
+
+
+@_on_tensor_device
+def speaker_encoder_step_bwd(w: Dict[str, Tensor], action_embedding: Tensor, visual: Tensor, h0: Tensor, c0: Tensor,
+                             drop_x: Optional[Tensor], c1: Tensor, fwd_workspace: Tensor, g_h1: Optional[Tensor],
+                             g_c1: Optional[Tensor], grads: Dict[str, Tensor], accumulate: bool = True):
+    """sfb_speaker_encoder_step_bwd: hand-written backward of SpeakerEncoderLSTM._forward_one_step.  `fwd_workspace` is the
+    workspace the forward call of this step ran in.  Returns (d_h0, d_c0)."""
+    lib = _lib.load()
+    B, H = h0.shape
+    d = follower_dims(w, visual.shape[1])
+    keep = []
+    vs = _visual_source(visual, None, None, None, keep)
+    wl = _vis_lstm_weights(w)
+    gs = _lib.FollowerGrads()
+    for f, k in _GRAD_FIELDS.items():
+        if f.startswith("lstm_") or f.startswith("va_"):
+            setattr(gs, f, _p(grads.get(k), name="grad " + k))
+    need = lib.sfb_speaker_encoder_step_bwd_workspace_bytes(C.byref(d), B)
+    ws = _workspace(need, h0.device, ("spk_enc_step_bwd", B))
+    d_h0 = torch.empty_like(h0); d_c0 = torch.empty_like(c0)
+    gc = lambda t: None if t is None else t.contiguous()
+    g_h1, g_c1 = gc(g_h1), gc(g_c1)
+    check(lib.sfb_speaker_encoder_step_bwd(
+        C.byref(d), C.byref(wl), B, _p(action_embedding, name="action_embedding"), C.byref(vs), _p(h0, name="h_0"), _p(c0, name="c_0"),
+        _p(drop_x, name="drop_x"), _p(c1, name="c_1"), fwd_workspace.data_ptr(), _p(g_h1), _p(g_c1), _p(d_h0), _p(d_c0),
+        C.byref(gs), 1 if accumulate else 0, ws.data_ptr(), ws.numel(), _stream()))
+    return d_h0, d_c0
+
+
+@_on_tensor_device
+def speaker_decoder_step_bwd(w: Dict[str, Tensor], prev_word: Tensor, h0: Tensor, c0: Tensor, ctx: Tensor, ctx_mask: Optional[Tensor],
+                             drop_e: Optional[Tensor], drop_h: Optional[Tensor], c1: Tensor, alpha: Tensor, fwd_workspace: Tensor,
+                             g_h1: Optional[Tensor], g_c1: Optional[Tensor], g_logit: Optional[Tensor], grads: Dict[str, Tensor],
+                             accumulate: bool = True):
+    """sfb_speaker_decoder_step_bwd: hand-written backward of SpeakerDecoderLSTM.forward.  Returns (d_h0, d_c0, d_ctx)."""
+    lib = _lib.load()
+    B, T, H = ctx.shape
+    vocab, Ew = w["embedding.weight"].shape
+    sw = _spk_dec_weights(w)
+    gs = _lib.SpeakerDecoderGrads()
+    for f, k in _SPK_DEC_GRAD_FIELDS.items():
+        setattr(gs, f, _p(grads.get(k), name="grad " + k))
+    pw = _i32(prev_word.reshape(-1))
+    m = _mask_u8(ctx_mask)
+    need = lib.sfb_speaker_decoder_step_bwd_workspace_bytes(H, Ew, vocab, B)
+    ws = _workspace(need, h0.device, ("spk_dec_step_bwd", B))
+    d_h0 = torch.empty_like(h0); d_c0 = torch.empty_like(c0); d_ctx = torch.empty_like(ctx)
+    gc = lambda t: None if t is None else t.contiguous()
+    g_h1, g_c1, g_logit = gc(g_h1), gc(g_c1), gc(g_logit)
+    check(lib.sfb_speaker_decoder_step_bwd(
+        C.byref(sw), H, Ew, vocab, B, T, _p(pw, torch.int32, "previous_word"), _p(h0, name="h_0"), _p(c0, name="c_0"),
+        _p(ctx, name="ctx"), _p(m, torch.uint8, "ctx_mask"), _p(drop_e, name="drop_e"), _p(drop_h, name="drop_h"),
+        _p(c1, name="c_1"), _p(alpha, name="alpha"), fwd_workspace.data_ptr(), _p(g_h1), _p(g_c1), _p(g_logit),
+        _p(d_h0), _p(d_c0), _p(d_ctx), C.byref(gs), 1 if accumulate else 0, ws.data_ptr(), ws.numel(), _stream()))
+    return d_h0, d_c0, d_ctx
+
+
 def nav_step(nav, state: Tensor, ended: Tensor, goal: Optional[Tensor], a_prev: Optional[Tensor], actions_log: Optional[Tensor],
              out: dict, with_target: bool = True) -> None:
     """sfb_nav_step: advance the table-driven environment `nav` (navgraph_env.DeviceNavTables) by the actions `a_prev`

@@ -10,6 +10,7 @@ from fake_env import FakeR2RBatch
 from oracle import r2r_oracle as O
 from speaker_follower_b200 import _functional as Fn, follower as Fo, model as M, ops, synth
 from test_gpu_parity import NAMES, close, cu
+from test_gpu_parity import close as _close
 
 pytestmark = pytest.mark.gpu
 IN = ("u_t_prev", "all_u_t", "visual_context", "h_0", "c_0", "ctx")
@@ -187,3 +188,58 @@ def test_encoder_kernel_backward_matches_oracle_autograd():
             continue
         scale = max(1.0, float(wr[k].grad.abs().max()))
         close(p.grad / scale, wr[k].grad / scale, 1e-4, "d " + k)
+
+
+def test_speaker_step_kernel_backward_with_dropout_masks():
+    """sfb_speaker_encoder_step_bwd / sfb_speaker_decoder_step_bwd with dropout masks (train_speaker.py trains with p=0.5):
+    gradients of a random linear functional of the outputs against torch autograd over the fp32 restatement of the same
+    step (speaker_follower_b200/_functional.py: model.py:429-435, 487-519) with the SAME masks."""
+    torch.manual_seed(3)
+    close = lambda a, b, tol, what: _close(a, torch.as_tensor(b).detach().cpu(), tol, what)
+    N, T = 24, 5
+    we = cu(synth.speaker_encoder_weights()); wd = cu(synth.speaker_decoder_weights())
+    x = cu(synth.follower_step_inputs(N, 8, 6, seed=9))
+    a, V, h0, c0 = x["all_u_t"][:, 1].contiguous(), x["visual_context"], x["h_0"], x["c_0"]
+    keep = lambda *s: (torch.rand(*s, device="cuda") > 0.5).float() * 2.0
+    # ---- encoder step
+    dx = keep(N, 2 * synth.FEAT)
+    lib = ops._lib.load()
+    need = lib.sfb_follower_step_workspace_bytes(ops.C.byref(ops.follower_dims(we, V.shape[1])), N, 1, 1)
+    for packed in (None, ops.PackedVisLstm().get(we)):
+        ws = torch.zeros(need, dtype=torch.uint8, device="cuda")
+        h1, c1 = ops.speaker_encoder_step(we, a, V, h0, c0, dx, packed=packed, workspace=ws)
+        gh, gc = torch.randn_like(h1), torch.randn_like(c1)
+        grads = {k: torch.zeros_like(v) for k, v in we.items() if not k.startswith("encoder2decoder.")}
+        d_h0, d_c0 = ops.speaker_encoder_step_bwd(we, a, V, h0, c0, dx, c1, ws, gh, gc, grads, accumulate=False)
+        wr = {k: v.clone().requires_grad_(True) for k, v in we.items()}
+        h0r, c0r = h0.clone().requires_grad_(True), c0.clone().requires_grad_(True)
+        h1r, c1r = Fn.speaker_encoder_step(wr, a, V, h0r, c0r, dx)
+        ((h1r * gh).sum() + (c1r * gc).sum()).backward()
+        close(h1, h1r.detach(), 1e-4, "enc h1"); close(d_h0, h0r.grad, 2e-4, "enc d_h0"); close(d_c0, c0r.grad, 2e-4, "enc d_c0")
+        for k, g in grads.items():
+            ref = wr[k].grad if wr[k].grad is not None else torch.zeros_like(g)
+            scale = max(1.0, float(ref.abs().max()))
+            close(g / scale, ref / scale, 2e-4, "enc d " + k)
+    # ---- decoder step
+    ctx = torch.tanh(torch.randn(N, T, synth.HID, device="cuda"))
+    mask = torch.arange(T, device="cuda").unsqueeze(0) >= torch.randint(2, T + 1, (N, 1), device="cuda")
+    prev = torch.randint(4, synth.VOCAB, (N,), device="cuda")
+    dh = keep(N, synth.HID)
+    need = lib.sfb_speaker_decoder_step_workspace_bytes(synth.HID, synth.WORD, N, T)
+    for packed in (None, ops.PackedSpeakerDecoder().get(wd)):
+        ws = torch.zeros(need, dtype=torch.uint8, device="cuda")
+        h1, c1, alpha, logit = ops.speaker_decoder_step(wd, prev, h0, c0, ctx, mask, None, dh, packed=packed, workspace=ws)
+        gh, gc, gl = torch.randn_like(h1), torch.randn_like(c1), torch.randn_like(logit) * 0.1
+        grads = {k: torch.zeros_like(v) for k, v in wd.items() if k != "embedding.weight"}
+        d_h0, d_c0, d_ctx = ops.speaker_decoder_step_bwd(wd, prev, h0, c0, ctx, mask, None, dh, c1, alpha, ws, gh, gc, gl, grads,
+                                                          accumulate=False)
+        wr = {k: v.clone().requires_grad_(k != "embedding.weight") for k, v in wd.items()}
+        h0r, c0r, ctxr = h0.clone().requires_grad_(True), c0.clone().requires_grad_(True), ctx.clone().requires_grad_(True)
+        h1r, c1r, alphar, logitr = Fn.speaker_decoder_step(wr, prev, h0r, c0r, ctxr, mask, None, dh)
+        ((h1r * gh).sum() + (c1r * gc).sum() + (logitr * gl).sum()).backward()
+        close(logit, logitr.detach(), 1e-4, "dec logit")
+        close(d_h0, h0r.grad, 2e-4, "dec d_h0"); close(d_c0, c0r.grad, 2e-4, "dec d_c0"); close(d_ctx, ctxr.grad, 2e-4, "dec d_ctx")
+        for k, g in grads.items():
+            ref = wr[k].grad
+            scale = max(1.0, float(ref.abs().max()))
+            close(g / scale, ref / scale, 2e-4, "dec d " + k)
