@@ -316,13 +316,15 @@ __device__ __forceinline__ void text_score_body(const FusedTextScoreParams& q, u
               }
             }
           }
-          __threadfence();
           if (q.trace && cid == 0 && tid == 0 && njobs_done == 0) q.trace[14] = globaltimer_ns();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        cluster_sync_all();   // outputs stored + fenced, parked data consumed: the weight buffer is free again
+        cluster_sync_all();   // outputs stored, parked data consumed: the weight buffer is free again
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (tid == 0 && cnt) atomicAdd(cnt, 1u);
+        if (tid == 0 && cnt) {   // the CTA's stores are ordered before this thread by the barrier: one device-scope fence, then arrive
+          __threadfence();
+          atomicAdd(cnt, 1u);
+        }
         if (q.trace && cid == 0 && tid == 0 && njobs_done == 0) q.trace[15] = globaltimer_ns();
         ++njobs_done;
       }
@@ -621,12 +623,12 @@ __device__ __forceinline__ void text_score_body(const FusedTextScoreParams& q, u
                                (size_t)(b & 7) * 16 + (size_t)(k & 7) * 2;
           *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
           *reinterpret_cast<uint2*>(dst + half) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+        }
+        t_bar256();   // every thread's stores are ordered before thread 0's fences + arrival (cumulativity); the ring can take the candidate rows
+        if (tid == 0) {
           asm volatile("fence.proxy.async;" ::: "memory");
           __threadfence();
-        }
-        t_bar256();   // h~ published; the ring can take the candidate rows
-        if (tid == 0) {
-          atomicAdd(cnt_ht, 1u);
+          atomicAdd(cnt_ht, 1u);   // h~ of this element is published
           mbar_arrive(ring_free);
         }
         rmark(5);

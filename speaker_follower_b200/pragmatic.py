@@ -24,12 +24,21 @@ import torch
 from . import dist as D
 
 
-def shard_env(env) -> List[int]:
-    """Keep only this rank's strided share of ``env.data`` (instances are independent); returns the GLOBAL indices kept,
-    in local order.  The batch size is clipped so that the last minibatch does not wrap around a short shard."""
+def shard_env(env, whole_batches: bool = False) -> List[int]:
+    """Keep only this rank's share of ``env.data`` (instances are independent); returns the GLOBAL indices kept, in local
+    order.  Default: strided by instance.  ``whole_batches``: the consecutive minibatches a single process would form
+    (env.batch_size items each) are dealt out round-robin instead, so that every minibatch has exactly the members it has
+    in the single-process run — needed where a result depends on its minibatch: SpeakerEncoderLSTM runs every row for the
+    longest path of its batch (model.py:437-457), so generated instructions are a function of the batch composition in
+    the reference as well.  The batch size is clipped so that the last minibatch does not wrap around a short shard."""
     rank, ws = D.world()
     n = len(env.data)
-    mine = D.shard_indices(n, rank, ws)
+    if whole_batches and hasattr(env, "batch_size"):
+        bs = max(1, int(env.batch_size))
+        chunks = [list(range(i, min(n, i + bs))) for i in range(0, n, bs)]
+        mine = [i for c in chunks[rank::ws] for i in c]
+    else:
+        mine = D.shard_indices(n, rank, ws)
     env.data = [env.data[i] for i in mine]
     env.ix = 0
     if hasattr(env, "batch_size"):
