@@ -61,7 +61,14 @@ __device__ __forceinline__ void e_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void e_bar256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ float e_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+// activations through ex2.approx (__expf: ~2 ulp): absolute error ~1e-7, far inside the 1e-4 contract, a fraction of the
+// instructions of expf / tanhf on the per-step critical path
+__device__ __forceinline__ float e_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float e_tanh(float x) {
+  const float ax = fminf(fabsf(x), 15.0f);               // tanh(15) == 1 in fp32; keeps e^{2x} finite
+  const float t = 1.0f - 2.0f / (__expf(2.0f * ax) + 1.0f);
+  return copysignf(t, x);
+}
 }  // namespace
 
 // grid = ndir * NG * tiles * 2, cluster (2,1,1), ENT threads
@@ -86,7 +93,7 @@ __global__ void __launch_bounds__(ENT, 1) encoder_persist_kernel(const EncPersis
   uint64_t* wfull = reinterpret_cast<uint64_t*>(park + 4 * cmax * 32);
   uint64_t* bfull = wfull + 1;
   uint64_t* done = bfull + 1;
-  const uint32_t tmem_cols = N <= 32 ? 32 : 64;
+  const uint32_t tmem_cols = 2 * N <= 32 ? 32 : 2 * N <= 64 ? 64 : 128;   // accumulator columns [0, N) and [N, 2N), see the MMA issuer
   if (warp == 0) {
     if (lane == 0) {
       mbar_init(wfull, 1);
@@ -149,7 +156,12 @@ __global__ void __launch_bounds__(ENT, 1) encoder_persist_kernel(const EncPersis
     }
   } else if (warp == 8) {
     // =============================== MMA issuer ===============================
+    // bf16 x 3 with TWO instructions per K step instead of three: the packed operand holds the hi rows followed by the lo
+    // rows, so A_hi x [B_hi | B_lo] is ONE N = 2N instruction whose accumulator columns [N, 2N) collect the A_hi x B_lo term
+    // (added by the epilogue); A_lo x B_hi goes into columns [0, N).  The resident A tile — whose shared-memory read
+    // paces these tiny-N instructions — is read twice per K step instead of three times.
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(EBM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(EBM >> 4) << 24);
     fail = !e_wait(wfull, 0) || fail;
     // the operands sit at the same shared-memory addresses every step: descriptors once, per MMA only an add
     // (the address field counts 16-byte units: a K step of 16 elements = 2 core matrices = 256 bytes = +16)
@@ -171,9 +183,8 @@ __global__ void __launch_bounds__(ENT, 1) encoder_persist_kernel(const EncPersis
 #pragma unroll
             for (int j = 0; j < EBK / 16; ++j) {
               const uint64_t ko = (uint64_t)(j * 2 * (int)ECORE / 16);
-              e_umma(tmem_d, dA[k][1] + ko, dB[k][0] + ko, idesc, (k > 0 || j > 0) ? 1u : 0u);   // small terms first
-              e_umma(tmem_d, dA[k][0] + ko, dB[k][1] + ko, idesc, 1u);
-              e_umma(tmem_d, dA[k][0] + ko, dB[k][0] + ko, idesc, 1u);
+              e_umma(tmem_d, dA[k][0] + ko, dB[k][0] + ko, idesc2, (k > 0 || j > 0) ? 1u : 0u);   // A_hi x [B_hi | B_lo]
+              e_umma(tmem_d, dA[k][1] + ko, dB[k][0] + ko, idesc, 1u);                              // A_lo x B_hi
             }
           }
         }
@@ -234,14 +245,21 @@ __global__ void __launch_bounds__(ENT, 1) encoder_persist_kernel(const EncPersis
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (tid == 0) mark(s, 6);
       for (int gq = hf; gq < ngrp; gq += 2) {
-        uint32_t v[16];
+        uint32_t v[16], v2[16];
         const uint32_t taddr = tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(gq * 16);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
             : "r"(taddr));
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v2[0]), "=r"(v2[1]), "=r"(v2[2]), "=r"(v2[3]), "=r"(v2[4]), "=r"(v2[5]), "=r"(v2[6]), "=r"(v2[7]),
+              "=r"(v2[8]), "=r"(v2[9]), "=r"(v2[10]), "=r"(v2[11]), "=r"(v2[12]), "=r"(v2[13]), "=r"(v2[14]), "=r"(v2[15])
+            : "r"(taddr + (uint32_t)N));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));   // + the A_hi x B_lo term
         const bool own = gq >= my_g0 && gq < my_g1;
         if (own) {
           float* dst = mine + ((size_t)lq * cmax + (size_t)(gq - my_g0) * 16) * 32 + lane;
@@ -273,9 +291,9 @@ __global__ void __launch_bounds__(ENT, 1) encoder_persist_kernel(const EncPersis
             // fixed summation order: the low K half (rank 0's partial) first, whichever CTA finalises
             g4[g] = (rank == 0 ? a + b : b + a) + (add[i][g] + bsum[g]);
           }
-          ig = e_sigmoid(g4[0]); fg = e_sigmoid(g4[1]); gt = tanhf(g4[2]); og = e_sigmoid(g4[3]);
+          ig = e_sigmoid(g4[0]); fg = e_sigmoid(g4[1]); gt = e_tanh(g4[2]); og = e_sigmoid(g4[3]);
           c_reg[i] = fg * c_reg[i] + ig * gt;
-          h_reg[i] = og * tanhf(c_reg[i]);
+          h_reg[i] = og * e_tanh(c_reg[i]);
         }
         // packed h for the next step (every column of the group, so that the operand block is fully defined)
         {

@@ -81,3 +81,46 @@ def test_shard_indices_cover_and_balance():
             parts = [D.shard_indices(n, r, w) for r in range(w)]
             assert sorted(sum(parts, [])) == list(range(n))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+class _Env(object):
+    def __init__(self, n, bs):
+        self.data = [{"instr_id": "%d_0" % i} for i in range(n)]
+        self.batch_size = bs
+        self.ix = 0
+
+
+def _shard_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        env = _Env(22, 4)
+        mine = PR.shard_env(env, whole_batches=True)
+        env2 = _Env(22, 4)
+        strided = PR.shard_env(env2)
+        q.put((rank, mine, [d["instr_id"] for d in env.data], env.batch_size, strided))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_whole_minibatch_sharding_keeps_single_process_batches():
+    """C5 sharding (pragmatic.shard_env(whole_batches=True)): every minibatch a rank runs has exactly the members it has in
+    the single-process run (consecutive chunks of batch_size), the ranks' shares are disjoint and cover the data."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=120) for _ in procs], key=lambda o: o[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    single = [list(range(i, min(22, i + 4))) for i in range(0, 22, 4)]
+    for rank, mine, ids, bs, strided in outs:
+        assert ids == ["%d_0" % i for i in mine] and bs == 4
+        local = [mine[i:i + 4] for i in range(0, len(mine), 4)]
+        assert local == single[rank::2]                      # whole single-process minibatches, dealt out round-robin
+        assert strided == list(range(rank, 22, 2))
+    assert sorted(outs[0][1] + outs[1][1]) == list(range(22))
