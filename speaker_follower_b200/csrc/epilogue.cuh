@@ -180,9 +180,9 @@ __device__ __forceinline__ void lstm_update1_pre(const GemmParams& p, int m, int
   const LstmEpilogue& e = p.lstm;
   const int H = e.H;
   const size_t idx = (size_t)m * H + unit;
-  const float ig = sigmoidf_acc(gi + pre.bi), fg = sigmoidf_acc(gf + pre.bf), gt = tanhf(gg + pre.bg), og = sigmoidf_acc(go + pre.bo);
+  const float ig = sigmoidf_fast(gi + pre.bi), fg = sigmoidf_fast(gf + pre.bf), gt = tanhf_fast(gg + pre.bg), og = sigmoidf_fast(go + pre.bo);
   const float c1 = fg * pre.c0 + ig * gt;
-  const float h1 = og * tanhf(c1);
+  const float h1 = og * tanhf_fast(c1);
   e.c1[idx] = c1;
   e.h1[idx] = h1;
   if (e.h1_drop) e.h1_drop[idx] = h1 * pre.dh;
