@@ -688,6 +688,7 @@ def _agents(env, dev, beam=1, instruction_len=80):
     senc = M.SpeakerEncoderLSTM(synth.FEAT, synth.FEAT, synth.HID, 0.5).to(dev).eval()
     sdec = M.SpeakerDecoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0.5, glove=swd["embedding.weight"].numpy()).to(dev).eval()
     senc.load_state_dict(synth.speaker_encoder_weights()); sdec.load_state_dict(swd)
+    senc.feature_store = dec.feature_store   # rescoring batches carry (viewpoint, view) indices instead of T x N slabs
     speaker = Sp.Seq2SeqSpeaker(env, "", senc, sdec, instruction_len=instruction_len, max_episode_len=10)
     return follower, speaker
 
@@ -765,6 +766,8 @@ def run_pragmatic(args, rank, local_rank, world):
                                           "all_reduce(n, sum, sum^2)" % world if c4 else
                                           "minibatches of 256 dealt out over %d ranks; collectives: all_gather(JSON bytes)" % world},
                 "identical_to_single_process": same}
+        if c4:   # where the time of rank 0's pass went (wall clock, device synchronised at the boundaries)
+            line["phases_rank0"] = {k: round(v, 4) for k, v in PR.LAST_PHASES.items()}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -303,8 +303,14 @@ class SpeakerEncoderLSTM(_PackedWeights, nn.Module):
         self.encoder2decoder = nn.Linear(hidden_size, hidden_size)
         self._packer = ops.PackedVisLstm()      # tcgen05 operand copies, refreshed when a weight changes
         self._ws = None                         # step workspace reused across the path steps of a call
+        self.feature_store = None               # ops.FeatureStore: world_state_embeddings may then be (vp_idx, view_idx) pairs
 
-    def forward(self, batched_action_embeddings: List[torch.Tensor], world_state_embeddings: List[torch.Tensor]):
+    def forward(self, batched_action_embeddings: List[torch.Tensor], world_state_embeddings: List[torch.Tensor], step_masks=None):
+        """model.py:437-457.  Besides the reference's dense [N,36,F] tensors, a path step's world state may be given as a
+        (viewpoint row, view index) pair of int32 tensors when `feature_store` is set: the kernel gathers the slab from the
+        device table.  `step_masks` (optional, per step [N, E+F] or None): multiplied into the LSTM input like a dropout mask
+        — an all-zero row makes that row's step see zero features and a zero action, which is how the reference's
+        zero-padded path steps behave (speaker.py:87-95)."""
         assert isinstance(batched_action_embeddings, list)
         assert isinstance(world_state_embeddings, list)
         assert len(batched_action_embeddings) == len(world_state_embeddings)
@@ -312,14 +318,22 @@ class SpeakerEncoderLSTM(_PackedWeights, nn.Module):
         grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         names = list(w.keys())
         packed = self._packer.get({k: v.detach() for k, v in w.items()})
-        B = world_state_embeddings[0].shape[0]
-        dev = world_state_embeddings[0].device
+        B = batched_action_embeddings[0].shape[0]
+        dev = batched_action_embeddings[0].device
         h = torch.zeros(B, self.hidden_size, device=dev)
         c = torch.zeros(B, self.hidden_size, device=dev)
         hs = []
-        for a, v in zip(batched_action_embeddings, world_state_embeddings):
+        for t, (a, v) in enumerate(zip(batched_action_embeddings, world_state_embeddings)):
             dx = self._drop.mask(self.training, (B, self.action_embedding_size + self.word_embedding_size), dev)
-            a, v = a.contiguous(), v.contiguous()
+            if step_masks is not None and step_masks[t] is not None:
+                dx = step_masks[t] if dx is None else dx * step_masks[t]
+            a = a.contiguous()
+            if isinstance(v, (tuple, list)):     # gathered from the device-resident store (inference paths)
+                assert self.feature_store is not None and not grad, "index-addressed world states need feature_store (eval)"
+                h, c = ops.speaker_encoder_step(w, a, None, h, c, dx, store=self.feature_store, vp_idx=v[0], view_idx=v[1], packed=packed)
+                hs.append(h)
+                continue
+            v = v.contiguous()
             if grad:   # forward AND backward on the CUDA kernels (sfb_speaker_encoder_step_bwd); a per-step workspace is the tape
                 def run_cuda(a=a, v=v, h=h, c=c, dx=dx):
                     with torch.no_grad():

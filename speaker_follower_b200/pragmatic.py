@@ -24,6 +24,9 @@ import torch
 from . import dist as D
 
 
+LAST_PHASES: Dict[str, float] = {}   # wall-clock split of the last run_rational_follower call on this rank (reporting only)
+
+
 def shard_env(env, whole_batches: bool = False) -> List[int]:
     """Keep only this rank's share of ``env.data`` (instances are independent); returns the GLOBAL indices kept, in local
     order.  Default: strided by instance.  ``whole_batches``: the consecutive minibatches a single process would form
@@ -84,17 +87,30 @@ def run_rational_follower(env, follower, speaker, beam_size: int, state_factored
     candidate_lists: Dict[str, list] = {}
     order: List[str] = []
     looped = False
+    import time as _time
+    phases = {"search_s": 0.0, "rescoring_s": 0.0, "exchange_s": 0.0}   # wall clock with a device sync at each boundary
+    LAST_PHASES.clear(); LAST_PHASES.update(phases)
+
+    def _tick():
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        return _time.perf_counter()
     with torch.no_grad():
         while not looped:
+            t0 = _tick()
             if state_factored_search:
                 beam_candidates, inf_states, traversed = follower.state_factored_search(
                     beam_size, 1, load_next_minibatch=True, first_n_ws_key=state_first_n_ws_key)
             else:
                 beam_candidates, inf_states, traversed = follower.beam_search(beam_size, load_next_minibatch=True)
+            t1 = _tick()
             flat = [c for cands in beam_candidates for c in cands]
             scored, _ = speaker._score_obs_actions_and_instructions(
                 [c["observations"] for c in flat], [c["actions"] for c in flat], [c["instr_encoding"] for c in flat], "teacher")
             assert len(scored) == len(flat)
+            t2 = _tick()
+            LAST_PHASES["search_s"] += t1 - t0
+            LAST_PHASES["rescoring_s"] += t2 - t1
             start = 0
             for ii, cands in enumerate(beam_candidates):
                 for i, c in enumerate(cands):
@@ -117,6 +133,7 @@ def run_rational_follower(env, follower, speaker, beam_size: int, state_factored
                     candidate_lists[iid] = cands
                     order.append(iid)
     # ---- the one exchange of the pass: candidate records + global standard deviations
+    t3 = _tick()
     gi = global_index if global_index is not None else list(range(len(order)))
     local = torch.tensor([[gi[k], j, c["follower_score"], c["speaker_score"]]
                           for k, iid in enumerate(order) for j, c in enumerate(candidate_lists[iid])], dtype=torch.float64)
@@ -127,6 +144,7 @@ def run_rational_follower(env, follower, speaker, beam_size: int, state_factored
     records = D.gather_records(local)
     f_std, s_std = D.global_std(local[:, 2]), D.global_std(local[:, 3])
     best = rational_combine(records.cpu().numpy(), weights, stds=(f_std, s_std))
+    LAST_PHASES["exchange_s"] = _tick() - t3
     results_by_weight = {}
     for w, choice in best.items():
         res, counts = {}, Counter()

@@ -50,6 +50,9 @@ class Seq2SeqSpeaker(object):
         N = len(path_obs)
         assert N == len(path_actions)
         mask = np.ones((N, T), np.uint8)
+        store = getattr(self.encoder, "feature_store", None)
+        if store is not None and all("vp_index" in ob for obs in path_obs for ob in obs[:-1]):
+            return self._batch_by_index(store, path_obs, path_actions, encoded_instructions, mask, seq_lengths, T, N, dev)
         E = path_obs[0][0]["action_embedding"].shape[-1]
         fshape = path_obs[0][0]["feature"][0].shape
         acts = np.zeros((T, N, E), np.float32)
@@ -66,6 +69,51 @@ class Seq2SeqSpeaker(object):
         return ([o[0] for o in path_obs], [feats_t[t] for t in range(T)], [acts_t[t] for t in range(T)],
                 torch.from_numpy(mask).to(dev), list(seq_lengths), encoded_instructions, list(range(N)))
 
+    def _batch_by_index(self, store, path_obs, path_actions, encoded_instructions, mask, seq_lengths, T, N, dev):
+        """The same batch (speaker.py:68-121) without materialising T x N slabs on the host: the encoder gathers each
+        step's 36-view slab from the device-resident feature store by (viewpoint row, view index), and the action
+        embeddings (env.py:60-75: slab row of the chosen direction + sin/cos of the relative angles) are assembled on the
+        device from (view index, 4 angles).  Padded steps must see zero features and zero actions like the reference's
+        zero-initialised arrays (speaker.py:87-95): their rows carry a zero input mask (`step_masks`)."""
+        vp = np.zeros((T, N), np.int32); view = np.zeros((T, N), np.int32)
+        aview = np.full((T, N), -1, np.int32); trig = np.zeros((T, N, 4), np.float32)
+        valid = np.zeros((T, N), np.float32)
+        for i, (obs, actions) in enumerate(zip(path_obs, path_actions)):
+            assert len(obs) == len(actions) + 1
+            n = len(actions)
+            mask[i, :n] = 0
+            valid[:n, i] = 1.0
+            for t in range(n):
+                ob, a = obs[t], actions[t]
+                assert a >= 0
+                vp[t, i] = ob["vp_index"]; view[t, i] = ob["viewIndex"]
+                d = ob["adj_loc_list"][a]
+                if d["absViewIndex"] >= 0:
+                    aview[t, i] = d["absViewIndex"]
+                    rh, re = d["rel_heading"], d["rel_elevation"]
+                    trig[t, i] = (np.sin(rh), np.cos(rh), np.sin(re), np.cos(re))
+        vp_t, view_t = torch.from_numpy(vp).to(dev), torch.from_numpy(view).to(dev)
+        aview_t, trig_t, valid_t = torch.from_numpy(aview).to(dev), torch.from_numpy(trig).to(dev), torch.from_numpy(valid).to(dev)
+        img = store.img_dim
+        loc = store.loc_table.shape[2]
+        rows = store.feat_table[vp_t.long(), aview_t.clamp(min=0).long()]                         # [T, N, img]
+        has = (aview_t >= 0).unsqueeze(-1).float()
+        acts_t = torch.cat((rows * has, (trig_t.repeat_interleave(loc // 4, dim=2)) * has), dim=2).contiguous()   # [T, N, img + loc]
+        feats = [(vp_t[t].contiguous(), view_t[t].contiguous()) for t in range(T)]
+        E = acts_t.shape[2]
+        F_ = img + loc
+        self._step_masks = [None if bool(valid[t].all()) else valid_t[t].unsqueeze(1).expand(N, E + F_).contiguous() for t in range(T)]
+        return ([o[0] for o in path_obs], feats, [acts_t[t] for t in range(T)],
+                torch.from_numpy(mask).to(dev), list(seq_lengths), encoded_instructions, list(range(N)))
+
+    def _encode(self, acts, feats):
+        """SpeakerEncoderLSTM over the batch from _batch_observations_and_actions (dense slabs or store indices)."""
+        masks = getattr(self, "_step_masks", None)
+        self._step_masks = None
+        if feats and isinstance(feats[0], tuple):
+            return self.encoder(acts, feats, step_masks=masks)
+        return self.encoder(acts, feats)
+
     # ---------------------------------------------------------------- scoring / decoding (speaker.py:123-202)
     def _score_obs_actions_and_instructions(self, path_obs, path_actions, encoded_instructions, feedback):
         assert len(path_obs) == len(path_actions) == len(encoded_instructions)
@@ -74,7 +122,7 @@ class Seq2SeqSpeaker(object):
         dev = _device(self.decoder)
         instr_seq, _, _ = batch_instructions_from_encoded(encoded_instructions, self.instruction_len, device=dev)
         N = len(start_obs)
-        ctx, h_t, c_t = self.encoder(acts, feats)
+        ctx, h_t, c_t = self._encode(acts, feats)
         w_t = torch.full((N,), vocab_bos_idx, dtype=torch.long, device=dev)
         ended = np.zeros(N, dtype=bool)
         outputs = [{"instr_id": start_obs[i]["instr_id"], "word_indices": [], "scores": []} for i in range(N)]
@@ -129,7 +177,7 @@ class Seq2SeqSpeaker(object):
         start_obs, feats, acts, path_mask, _, _, perm = self._batch_observations_and_actions(path_obs, path_actions, None)
         N = len(start_obs)
         dev = _device(self.decoder)
-        ctx, h_t, c_t = self.encoder(acts, feats)
+        ctx, h_t, c_t = self._encode(acts, feats)
         completed = [[] for _ in range(N)]
         beams = [[InferenceState(None, i, vocab_bos_idx, 0, np.float32(0.0), None)] for i in range(N)]
         for t in range(self.instruction_len):

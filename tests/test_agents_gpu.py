@@ -127,6 +127,34 @@ def test_speaker_teacher_scoring_matches_oracle():
     assert len(res) == 6
 
 
+def test_speaker_scoring_from_feature_store_equals_dense_batching():
+    """speaker.py:68-121 without host slabs: with `encoder.feature_store` set the batch carries (viewpoint row, view index)
+    pairs and the action embeddings are assembled on the device; ragged path lengths (padded steps must see zero input).
+    Scores and words equal the dense-batching path (same kernels, gathered vs. dense source) and the CPU oracle."""
+    env = FakeR2RBatch(n_viewpoints=24, n_instr=10, batch_size=10, seed=16)
+    we, wd = synth.speaker_encoder_weights(), synth.speaker_decoder_weights()
+    enc = M.SpeakerEncoderLSTM(synth.FEAT, synth.FEAT, synth.HID, 0.5).cuda().eval()
+    dec = M.SpeakerDecoderLSTM(synth.VOCAB, synth.WORD, synth.HID, 0.5, glove=wd["embedding.weight"].numpy()).cuda().eval()
+    enc.load_state_dict(we); dec.load_state_dict(wd)
+    spk = Sp.Seq2SeqSpeaker(env, "", enc, dec, instruction_len=12, max_episode_len=6)
+    path_obs, path_actions, encoded = env.gold_obs_actions_and_instructions(6)
+    assert len(set(len(a) for a in path_actions)) > 1, "the batch must be ragged for this test to mean something"
+    with torch.no_grad():
+        dense, loss_d = spk._score_obs_actions_and_instructions(path_obs, path_actions, encoded, "teacher")
+        _, feats_d, acts_d, _, _, _, _ = spk._batch_observations_and_actions(path_obs, path_actions, encoded)
+        enc.feature_store = ops.FeatureStore(torch.from_numpy(env.table).cuda(), torch.from_numpy(env.loc).cuda())
+        _, feats_i, acts_i, _, _, _, _ = spk._batch_observations_and_actions(path_obs, path_actions, encoded)
+        assert isinstance(feats_i[0], tuple)
+        for a_d, a_i in zip(acts_d, acts_i):                      # device-assembled action embeddings == env.py:60-75 on the host
+            assert torch.equal(a_d, a_i)
+        spk._step_masks = None
+        idx, loss_i = spk._score_obs_actions_and_instructions(path_obs, path_actions, encoded, "teacher")
+    for d, i in zip(dense, idx):
+        assert d["word_indices"] == i["word_indices"]
+        assert abs(d["score"] - i["score"]) < 1e-4 * max(1.0, abs(d["score"]))
+    assert abs(float(loss_d) - float(loss_i)) < 1e-5 * max(1.0, abs(float(loss_d)))
+
+
 def test_state_factored_search_invariants():
     """follower.py:720-980 on the fake env: distinct end states per instance, sorted by score, per-step scores add up
     (rational_speaker.py:87-89), teacher-forced rescoring of every candidate reproduces its score (the invariant
