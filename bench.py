@@ -713,8 +713,10 @@ def run_pragmatic(args, rank, local_rank, world):
     beam = 40 if c4 else 1
 
     def make_env():
+        # index-only observations: slabs and action-embedding rows are gathered from the device feature store, the
+        # environment ships (viewpoint row, view index, candidate view indices + angles) only
         return FakeR2RBatch(n_viewpoints=160, n_instr=n_inst, batch_size=64 if c4 else 256, seed=77, max_len=40,
-                            beam_size=max(beam, 1))
+                            beam_size=max(beam, 1), with_features=False)
 
     def one_pass(shard):
         env = make_env()

@@ -13,6 +13,7 @@ Written from the behaviour described in SURVEY.md A.2; no reference code is reus
 from __future__ import annotations
 
 import json
+import math
 import random
 from collections import namedtuple
 from typing import List, Optional
@@ -177,6 +178,33 @@ class Seq2SeqAgent(BaseAgent):
             is_valid[i, :n] = 1.0
             emb[i, :n] = ob["action_embedding"]
         return torch.from_numpy(emb).to(dev), torch.from_numpy(is_valid).to(dev), is_valid
+
+    def _action_indices(self, obs):
+        """The action candidates of `obs` as indices (env.py:60-75 without the rows): per candidate the view index into the
+        observation's own slab (-1: stop / padding) and sin/cos of the relative heading / elevation.  Returns
+        (cand_view int32 [N,A], cand_trig [N,A,4], is_valid [N,A]) on the device plus is_valid as numpy."""
+        dev = _device(self.decoder)
+        max_a = max(len(ob["adj_loc_list"]) for ob in obs)
+        is_valid = np.zeros((len(obs), max_a), np.float32)
+        cv = np.full((len(obs), max_a), -1, np.int32)
+        tr = np.zeros((len(obs), max_a, 4), np.float32)
+        for i, ob in enumerate(obs):
+            adj = ob["adj_loc_list"]
+            is_valid[i, :len(adj)] = 1.0
+            for a in range(1, len(adj)):
+                d = adj[a]
+                cv[i, a] = d["absViewIndex"]
+                rh, re = d["rel_heading"], d["rel_elevation"]
+                tr[i, a] = (math.sin(rh), math.cos(rh), math.sin(re), math.cos(re))
+        return torch.from_numpy(cv).to(dev), torch.from_numpy(tr).to(dev), torch.from_numpy(is_valid).to(dev), is_valid, cv, tr
+
+    def _embed_actions(self, vp, aview, trig):
+        """Action-embedding rows (env.py:60-75) assembled on the device: vp / aview int tensors [n], trig [n,4]."""
+        store = self.decoder.feature_store
+        has = (aview >= 0).unsqueeze(-1).float()
+        rows = store.feat_table[vp.long(), aview.clamp(min=0).long()]
+        loc = store.loc_table.shape[2]
+        return torch.cat((rows * has, trig.repeat_interleave(loc // 4, dim=1) * has), dim=1).contiguous()
 
     def _teacher_action(self, obs, ended):
         a = [(-1 if ended[i] else int(ob["teacher"])) for i, ob in enumerate(obs)]
@@ -593,14 +621,29 @@ class Seq2SeqAgent(BaseAgent):
         def ws_key(ws):
             return tuple(ws[0:first_n_ws_key])
 
+        # index mode: observations carry (viewpoint row, view index) and the decoder owns a device feature store — no slab
+        # and no action-embedding row ever exists on the host; a state's last action embedding is kept as
+        # (viewpoint row, view index of the chosen direction, 4 angle terms) and assembled on the device when needed
+        store = getattr(self.decoder, "feature_store", None)
+        index_mode = store is not None and all("vp_index" in o[0] for o in initial_obs) and \
+            getattr(self.decoder, "supports_fused_step", False)
+        NO_ACTION = (0, -1, (0.0, 0.0, 0.0, 0.0))
+
         completed = [dict() for _ in range(n_inst)]      # key -> finished inference state that has been expanded
         holding = [dict() for _ in range(n_inst)]        # key -> [finished inference state, expanded?]
         cache, beams = [], []                            # key -> [open inference state, expanded?]
         for i, (ws, o) in enumerate(zip(world_states, initial_obs)):
-            root = InferenceState(None, ws[0], o[0], None, -1, self.decoder.u_begin.view(-1), 0, np.float32(0.0),
-                                  h_t[i], c_t[i], None)
+            root = InferenceState(None, ws[0], o[0], None, -1, NO_ACTION if index_mode else self.decoder.u_begin.view(-1), 0,
+                                  np.float32(0.0), h_t[i], c_t[i], None)
             cache.append({ws_key(ws[0]): [root, True]})
             beams.append([root])
+        # Selection of the best not-yet-expanded entry (follower.py:903-908, heapq.nlargest over cache + holding) as a lazy
+        # max-heap per instance: an entry is pushed when it is inserted / replaced; stale entries (replaced since, or
+        # expanded) are skipped when popped.  Ties resolve like nlargest over [cache entries..., holding entries...] in
+        # dict order: open before finished, then first insertion of the key first.
+        heaps = [[] for _ in range(n_inst)]
+        first_seen = [dict() for _ in range(n_inst)]     # (finished?, key) -> order of first insertion
+        use_heap = successor_size == 1
         last_expanded = [beam[0] for beam in beams]
         traversed_lists = [[beam[0]] for beam in beams]
 
@@ -620,13 +663,23 @@ class Seq2SeqAgent(BaseAgent):
             owner = [bi for bi, beam in enumerate(beams) for _ in beam]
             flat_obs = [st.observation for st in flat]
             own_t = torch.tensor(owner, dtype=torch.long, device=dev)
-            u_prev = torch.stack([st.last_action_embedding for st in flat], 0).contiguous()
             h_in = torch.stack([st.h_t for st in flat], 0).contiguous()
             c_in = torch.stack([st.c_t for st in flat], 0).contiguous()
             f_t = self._feature_variables(flat_obs)[0]
-            all_u_t, is_valid, is_valid_np = self._action_variable(flat_obs)
-            h_new, c_new, alpha, logit, _ = self.decoder(u_prev, all_u_t, f_t, h_in, c_in, ctx[own_t].contiguous(),
-                                                         seq_mask[own_t].contiguous())
+            if index_mode:
+                lae = [st.last_action_embedding for st in flat]
+                u_prev = self._embed_actions(torch.tensor([x[0] for x in lae], dtype=torch.int32, device=dev),
+                                             torch.tensor([x[1] for x in lae], dtype=torch.int32, device=dev),
+                                             torch.tensor([x[2] for x in lae], dtype=torch.float32, device=dev))
+                cand_view, cand_trig, is_valid, is_valid_np, cv_np, tr_np = self._action_indices(flat_obs)
+                h_new, c_new, alpha, logit, _ = self.decoder.decode_step(u_prev, None, f_t, h_in, c_in, ctx[own_t].contiguous(),
+                                                                        seq_mask[own_t].contiguous(), cand_view=cand_view,
+                                                                        cand_trig=cand_trig)
+            else:
+                u_prev = torch.stack([st.last_action_embedding for st in flat], 0).contiguous()
+                all_u_t, is_valid, is_valid_np = self._action_variable(flat_obs)
+                h_new, c_new, alpha, logit, _ = self.decoder(u_prev, all_u_t, f_t, h_in, c_in, ctx[own_t].contiguous(),
+                                                             seq_mask[own_t].contiguous())
             logit = logit.masked_fill(is_valid == 0, -float("inf"))                       # 808
             lp_host = torch.log_softmax(logit, dim=1).cpu().numpy()                       # the one D2H of the iteration
 
@@ -638,7 +691,9 @@ class Seq2SeqAgent(BaseAgent):
                     for ai in range(lp_host.shape[1]):
                         if is_valid_np[fi, ai] == 0:
                             continue
-                        succ.append(InferenceState(st, st.world_state, flat_obs[fi], None, ai, all_u_t[fi, ai],
+                        emb = (flat_obs[fi]["vp_index"], int(cv_np[fi, ai]), tuple(float(v) for v in tr_np[fi, ai])) if index_mode \
+                            else all_u_t[fi, ai]
+                        succ.append(InferenceState(st, st.world_state, flat_obs[fi], None, ai, emb,
                                                    st.action_count + 1, np.float32(st.score + lp_host[fi, ai]),
                                                    h_new[fi], c_new[fi], alpha[fi]))
                     fi += 1
@@ -656,13 +711,30 @@ class Seq2SeqAgent(BaseAgent):
                     continue
                 for x in succ:                                                            # keep the best per world state
                     k = ws_key(x.world_state)
-                    table = holding[i] if (x.last_action == 0 or x.action_count == self.episode_len) else cache[i]
+                    fin = x.last_action == 0 or x.action_count == self.episode_len
+                    table = holding[i] if fin else cache[i]
                     if k not in table or table[k][0].score < x.score:
                         table[k] = [x, False]
-                pool = [(k, e[0], False) for k, e in cache[i].items() if not e[1]] + \
-                       [(k, e[0], True) for k, e in holding[i].items() if not e[1]]
+                        if use_heap:
+                            order = first_seen[i].setdefault((fin, k), len(first_seen[i]))
+                            heapq.heappush(heaps[i], (-float(x.score), fin, order, id(x), k, x))
+                if use_heap:
+                    chosen = []
+                    while heaps[i]:
+                        _, fin, _, _, k, x = heaps[i][0]
+                        entry = (holding[i] if fin else cache[i]).get(k)
+                        if entry is None or entry[0] is not x or entry[1]:
+                            heapq.heappop(heaps[i])                                       # stale: replaced or already expanded
+                            continue
+                        heapq.heappop(heaps[i])
+                        chosen.append((k, x, fin))
+                        break
+                else:
+                    pool = [(k, e[0], False) for k, e in cache[i].items() if not e[1]] + \
+                           [(k, e[0], True) for k, e in holding[i].items() if not e[1]]
+                    chosen = heapq.nlargest(successor_size, pool, key=lambda t: t[1].score)
                 beam = []
-                for k, st, finished in heapq.nlargest(successor_size, pool, key=lambda t: t[1].score):
+                for k, st, finished in chosen:
                     if finished:
                         holding[i][k][1] = True
                         if k not in completed[i] or completed[i][k].score < st.score:

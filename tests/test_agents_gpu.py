@@ -253,13 +253,16 @@ def test_beam_search_matches_search_oracle(graph, beam):
     assert checked >= 4
 
 
-@pytest.mark.parametrize("graph,completion,successor", [("8194nk5LbLH", 3, 1), ("GdvgFV5R1Z5", 4, 2), ("pLe4wQe7qrG", 5, 1)])
-def test_state_factored_search_matches_search_oracle(graph, completion, successor):
+@pytest.mark.parametrize("graph,completion,successor,store", [("8194nk5LbLH", 3, 1, False), ("GdvgFV5R1Z5", 4, 2, False),
+                                                             ("pLe4wQe7qrG", 5, 1, False), ("pLe4wQe7qrG", 5, 1, True),
+                                                             ("8194nk5LbLH", 6, 1, True), ("GdvgFV5R1Z5", 4, 2, True)])
+def test_state_factored_search_matches_search_oracle(graph, completion, successor, store):
     """follower.py:720-980 — world-state dedupe, strict-improvement replacement, heapq.nlargest expansion order,
-    completion bookkeeping and the traversal walk equal the oracle's."""
-    env = FakeR2RBatch(n_instr=5, batch_size=5, seed=22, graph=graph, beam_size=max(successor, 2))
+    completion bookkeeping and the traversal walk equal the oracle's.  store=True: the index mode (observations WITHOUT
+    slabs and action-embedding rows, everything gathered from the device feature store) with the lazy-heap selection."""
+    env = FakeR2RBatch(n_instr=5, batch_size=5, seed=22, graph=graph, beam_size=max(successor, 2), with_features=not store)
     twin = FakeR2RBatch(n_instr=5, batch_size=5, seed=22, graph=graph, beam_size=max(successor, 2))
-    agent, we, wd = make_follower(env)
+    agent, we, wd = make_follower(env, store=store)
     with torch.no_grad():
         got, _, walk_g = agent.state_factored_search(completion, successor)
         want, _, walk_w = SO.follower_state_factored_search(twin, we, wd, completion, successor, episode_len=agent.episode_len,
