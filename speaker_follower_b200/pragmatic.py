@@ -132,6 +132,11 @@ def run_rational_follower(env, follower, speaker, beam_size: int, state_factored
                 else:
                     candidate_lists[iid] = cands
                     order.append(iid)
+            # the reference keeps drawing minibatches until an instruction repeats (rational_follower.py:44-69), i.e. it runs
+            # one more search + rescoring pass whose results it throws away whenever the data divides into whole batches;
+            # every instruction of the split has its candidates once each id has been seen
+            if hasattr(env, "data") and len(candidate_lists) >= len({it["instr_id"] for it in env.data}):
+                looped = True
     # ---- the one exchange of the pass: candidate records + global standard deviations
     t3 = _tick()
     gi = global_index if global_index is not None else list(range(len(order)))

@@ -13,7 +13,7 @@ torch.cuda.set_device(dev)
 
 
 def make_env():
-    return FakeR2RBatch(n_viewpoints=160, n_instr=n_inst, batch_size=64, seed=77, max_len=40, beam_size=40)
+    return FakeR2RBatch(n_viewpoints=160, n_instr=n_inst, batch_size=64, seed=77, max_len=40, beam_size=40, with_features=False)
 
 
 def one_pass():
