@@ -312,6 +312,34 @@ int32_t sfb_nav_step(const sfb_nav_tables* t, int32_t B, int32_t* state, int32_t
                      int32_t* vp_idx, int32_t* view_idx, int32_t* cand_view, float* cand_trig, float* is_valid,
                      int32_t* target, void* stream);
 
+/* State-factored search bookkeeping on the device — follower.py:886-924 for successor_size = 1 over the
+ * table-driven environment, where the world-state key (scan, viewpoint, heading, elevation; follower.py:739,894) is the
+ * state id of sfb_nav_tables.  The reference's per-instance dicts become dense arrays over the S states: cache (best open
+ * inference state per world state), holding (best finished one), completed; inference states live in a per-instance node
+ * pool.  One call per search iteration, after the decode step of the states selected by the previous call:
+ *   lp [B,A] = log_softmax of the step's masked logits (808-810); `iter` = iteration index (the step's h / c / alpha are
+ *   kept by the caller in slot iter + 1);
+ *   the successors of beam_node[b] are inserted where they strictly improve their table entry (896-900; a successor is
+ *   finished after the stop action or at episode_len, 895), then the best not-yet-expanded entry is selected (903-908): an
+ *   open one becomes beam_node[b], a finished one moves to completed (912-916); instances with completion_size
+ *   completions stop (889-891, 921).  flags[0] is raised when no instance has a state left to expand (925-926) and makes
+ *   further calls no-ops, so the host may look at it every few iterations only.  flags[2]: node pool exhausted.
+ * All arrays are caller-owned device memory; scores start at -inf, nodes / flags at 0, beam_node at the root node. */
+typedef struct sfb_sf_search_state {
+  int32_t* beam_node;                                   /* [B] */
+  float* c_score; int32_t* c_node; uint8_t* c_exp;     /* [B,S] cache */
+  float* h_score; int32_t* h_node; uint8_t* h_exp;     /* [B,S] holding */
+  float* d_score; int32_t* d_node; int32_t* n_done;    /* [B,S], [B,S], [B] completed */
+  int32_t* n_nodes;                                     /* [B] nodes in use */
+  int32_t *node_parent, *node_state, *node_action, *node_count, *node_slot;   /* [B,max_nodes] */
+  float* node_score;                                    /* [B,max_nodes] */
+  int32_t* trav;                                        /* [B,max_iter] node selected after iteration t, or -1 */
+  int32_t* flags;                                       /* [4] ended, scratch, pool overflow, iterations done */
+  int32_t max_nodes, max_iter;
+} sfb_sf_search_state;
+int32_t sfb_sf_search_update(const sfb_sf_search_state* st, const sfb_nav_tables* nav, int32_t B, int32_t iter,
+                             int32_t episode_len, int32_t completion_size, const float* lp, void* stream);
+
 /* Per-step tail of Seq2SeqAgent._rollout_with_loss — follower.py:476-505.
  *   logit [B,A] is masked IN PLACE with -inf where is_valid == 0 (477);
  *   feedback: 0 = teacher (a_t = max(target,0)), 1 = argmax, 2 = sample (inverse CDF of

@@ -77,6 +77,15 @@ class FollowerGrads(C.Structure):
                                          "w_in", "w_out", "sc_w_h", "sc_b_h", "sc_w_a", "sc_b_a", "sc_w_out", "sc_b_out")]
 
 
+class SfSearchState(C.Structure):
+    _fields_ = [("beam_node", c_int_p), ("c_score", c_float_p), ("c_node", c_int_p), ("c_exp", c_u8_p),
+                ("h_score", c_float_p), ("h_node", c_int_p), ("h_exp", c_u8_p),
+                ("d_score", c_float_p), ("d_node", c_int_p), ("n_done", c_int_p), ("n_nodes", c_int_p),
+                ("node_parent", c_int_p), ("node_state", c_int_p), ("node_action", c_int_p), ("node_count", c_int_p),
+                ("node_slot", c_int_p), ("node_score", c_float_p), ("trav", c_int_p), ("flags", c_int_p),
+                ("max_nodes", C.c_int32), ("max_iter", C.c_int32)]
+
+
 class SpeakerDecoderGrads(C.Structure):
     _fields_ = [(n, c_float_p) for n in ("lstm_w_ih", "lstm_w_hh", "lstm_b_ih", "lstm_b_hh", "w_in", "w_out", "w_voc", "b_voc")]
 
@@ -151,6 +160,8 @@ SIGNATURES = {
                                                  c_float_p, c_float_p, C.c_void_p, c_float_p, c_float_p, c_float_p,
                                                  c_float_p, c_float_p, c_float_p, C.POINTER(SpeakerDecoderGrads), C.c_int32,
                                                  C.c_void_p, C.c_size_t, C.c_void_p]),
+    "sfb_sf_search_update": (C.c_int32, [C.POINTER(SfSearchState), C.POINTER(NavTables), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         c_float_p, C.c_void_p]),
     "sfb_nav_step": (C.c_int32, [C.POINTER(NavTables), C.c_int32, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p,
                                  c_int_p, c_int_p, c_int_p, c_float_p, c_float_p, c_int_p, C.c_void_p]),
     "sfb_eltwise_prod_scoring_fwd": (C.c_int32, [C.POINTER(Dims), C.POINTER(ScoringWeights), C.c_int32, C.c_int32,

@@ -1418,6 +1418,25 @@ int32_t sfb_follower_step_bwd(const sfb_dims* dims, const sfb_vis_lstm_weights* 
                       gr, acc, w, st);
 }
 
+int32_t sfb_sf_search_update(const sfb_sf_search_state* st, const sfb_nav_tables* nav, int32_t B, int32_t iter,
+                             int32_t episode_len, int32_t completion_size, const float* lp, void* stream) {
+  reset_launch_count();
+  SFB_CHECK_ARG(st && nav && lp, "NULL argument");
+  SFB_CHECK_ARG(st->beam_node && st->c_score && st->c_node && st->c_exp && st->h_score && st->h_node && st->h_exp && st->d_score &&
+                    st->d_node && st->n_done && st->n_nodes && st->node_parent && st->node_state && st->node_action &&
+                    st->node_count && st->node_slot && st->node_score && st->trav && st->flags, "search state: NULL array");
+  SFB_CHECK_ARG(nav->next && nav->nvalid && nav->S >= 1 && nav->A >= 1, "navigation tables missing");
+  SfSearchParams p{};
+  p.B = B; p.A = nav->A; p.S = nav->S; p.M = st->max_nodes; p.max_iter = st->max_iter; p.episode_len = episode_len;
+  p.completion_size = completion_size; p.iter = iter; p.lp = lp; p.nav_next = nav->next; p.nav_nvalid = nav->nvalid;
+  p.beam_node = st->beam_node; p.c_score = st->c_score; p.c_node = st->c_node; p.c_exp = st->c_exp;
+  p.h_score = st->h_score; p.h_node = st->h_node; p.h_exp = st->h_exp; p.d_score = st->d_score; p.d_node = st->d_node;
+  p.n_done = st->n_done; p.n_nodes = st->n_nodes; p.node_parent = st->node_parent; p.node_state = st->node_state;
+  p.node_action = st->node_action; p.node_count = st->node_count; p.node_slot = st->node_slot; p.node_score = st->node_score;
+  p.trav = st->trav; p.flags = st->flags;
+  return launch_sf_search_update(p, static_cast<cudaStream_t>(stream));
+}
+
 /* ---------------------------------------------------------------- speaker modules: backward (train_speaker.py, speaker.py:376-395) */
 size_t sfb_speaker_encoder_step_bwd_workspace_bytes(const sfb_dims* dims, int32_t B) {
   if (!dims || B < 1) return 0;

@@ -322,6 +322,22 @@ struct NavStepParams {
 };
 int32_t launch_nav_step(const NavStepParams& p, cudaStream_t stream);
 
+// state-factored search bookkeeping on the device (pointwise.cu, follower.py:886-924, successor_size = 1)
+struct SfSearchParams {
+  int B, A, S, M, max_iter, episode_len, completion_size, iter;
+  const float* lp;                       // [B,A] log-softmax of this iteration's masked logits
+  const int32_t* nav_next; const int32_t* nav_nvalid;
+  int32_t* beam_node;                    // [B] in: node expanded this iteration (-1: none); out: node to expand next
+  float* c_score; int32_t* c_node; uint8_t* c_exp;    // [B,S] cache
+  float* h_score; int32_t* h_node; uint8_t* h_exp;    // [B,S] holding
+  float* d_score; int32_t* d_node; int32_t* n_done;   // [B,S], [B] completed
+  int32_t* n_nodes;                      // [B]
+  int32_t *node_parent, *node_state, *node_action, *node_count, *node_slot; float* node_score;   // [B,M]
+  int32_t* trav;                         // [B,max_iter] node selected for expansion after iteration t, or -1
+  int32_t* flags;                        // [0] ended, [1] scratch, [2] node pool overflow, [3] iterations done
+};
+int32_t launch_sf_search_update(const SfSearchParams& p, cudaStream_t stream);
+
 // ---------------------------------------------------------------- backward.cu
 struct ScoreBwdParams {
   const float* dlogit; int B, A, E;

@@ -153,6 +153,115 @@ int32_t launch_nav_step(const NavStepParams& p, cudaStream_t stream) {
   return 0;
 }
 
+// ---------------------------------------------------------------- state-factored search bookkeeping
+// follower.py:886-924 for successor_size = 1 over the table-driven environment, one CTA per instance.  The world-state
+// key (scan, viewpoint, heading, elevation) is the discretised state id, so the reference's per-instance dicts are dense
+// arrays over the S states: `cache` (best open inference state per world state), `holding` (best finished one),
+// `completed`.  Inference states live in a per-instance node pool (parent, state, action, count, score, and the slot of
+// the expansion whose (h, c, alpha) they carry).  Per iteration: the successors of the state expanded in this iteration
+// are inserted where they strictly improve their table entry, then the best not-yet-expanded entry is selected: an open
+// one becomes the next iteration's state, a finished one moves to `completed`.
+__global__ void __launch_bounds__(128) sf_search_update_kernel(const SfSearchParams p) {
+  const int i = blockIdx.x, tid = threadIdx.x;
+  if (p.flags[0]) return;                                   // the search has ended (no instance had a state to expand)
+  const size_t so = (size_t)i * p.S, no = (size_t)i * p.M;
+  __shared__ float s_best[128];
+  __shared__ int s_arg[128];
+  const int n = p.beam_node[i];
+  const bool full = p.n_done[i] >= p.completion_size;      // follower.py:889-891: nothing is inserted or selected any more
+  if (tid == 0 && n >= 0 && !full) {
+    const int s = p.node_state[no + n];
+    const int nv = p.nav_nvalid[s];
+    const float base = p.node_score[no + n];
+    const int cnt = p.node_count[no + n] + 1;
+    for (int a = 0; a < nv && a < p.A; ++a) {
+      const float sc = base + p.lp[(size_t)i * p.A + a];   // np.float32(st.score + lp) (follower.py:851)
+      const int ns = a == 0 ? s : p.nav_next[(size_t)s * p.A + a];
+      const bool fin = a == 0 || cnt == p.episode_len;     // follower.py:895
+      float* tsc = fin ? p.h_score : p.c_score;
+      if (tsc[so + ns] < sc) {                             // absent (-inf) or strictly better (follower.py:896-900)
+        int m = p.n_nodes[i];
+        if (m >= p.M) { p.flags[2] = 1; break; }           // node pool exhausted: reported, the host falls back
+        p.n_nodes[i] = m + 1;
+        p.node_parent[no + m] = n; p.node_state[no + m] = ns; p.node_action[no + m] = a; p.node_count[no + m] = cnt;
+        p.node_score[no + m] = sc; p.node_slot[no + m] = p.iter + 1;   // this iteration's outputs sit in slot iter + 1
+        tsc[so + ns] = sc;
+        (fin ? p.h_node : p.c_node)[so + ns] = m;
+        (fin ? p.h_exp : p.c_exp)[so + ns] = 0;
+      }
+    }
+  }
+  __syncthreads();
+  // best not-yet-expanded entry over cache and holding (heapq.nlargest(1, ...), follower.py:903-908); ties: open before
+  // finished, then the lower state id
+  float best = -INFINITY;
+  int arg = -1;                                            // state id, + S for a holding entry
+  if (!full) {
+    for (int s = tid; s < p.S; s += 128) {
+      const float c = p.c_exp[so + s] ? -INFINITY : p.c_score[so + s];
+      if (c > best) { best = c; arg = s; }
+    }
+    for (int s = tid; s < p.S; s += 128) {
+      const float h = p.h_exp[so + s] ? -INFINITY : p.h_score[so + s];
+      if (h > best) { best = h; arg = p.S + s; }
+    }
+  }
+  s_best[tid] = best; s_arg[tid] = arg;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (tid < o) {
+      const float ob = s_best[tid + o];
+      const int oa = s_arg[tid + o];
+      if (oa >= 0 && (s_arg[tid] < 0 || ob > s_best[tid] || (ob == s_best[tid] && oa < s_arg[tid]))) { s_best[tid] = ob; s_arg[tid] = oa; }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int beam = -1;
+    const int a = s_arg[0];
+    if (!full && a >= 0) {
+      if (a >= p.S) {                                      // a finished state: mark expanded, move to completed (912-916)
+        const int s = a - p.S;
+        p.h_exp[so + s] = 1;
+        if (p.d_score[so + s] < s_best[0]) {
+          if (p.d_score[so + s] == -INFINITY) p.n_done[i] += 1;
+          p.d_score[so + s] = s_best[0];
+          p.d_node[so + s] = p.h_node[so + s];
+        }
+      } else {                                             // an open state: it is expanded in the next iteration
+        p.c_exp[so + a] = 1;
+        beam = p.c_node[so + a];
+      }
+    }
+    if (p.n_done[i] >= p.completion_size) beam = -1;       // follower.py:921
+    p.beam_node[i] = beam;
+    p.trav[(size_t)i * p.max_iter + p.iter] = beam;
+    if (beam >= 0) atomicAdd(&p.flags[1], 1);              // flags[1]: instances with a state to expand (reset by the flags kernel)
+  }
+}
+
+// follower.py:925-926 `if not any(beams): break`, evaluated on the device so that the host need not look every iteration
+__global__ void sf_search_flags_kernel(int* flags) {
+  if (threadIdx.x == 0) {
+    if (!flags[0]) {
+      flags[3] += 1;                                        // iterations the search really ran
+      if (flags[1] == 0) flags[0] = 1;
+    }
+    flags[1] = 0;
+  }
+}
+
+int32_t launch_sf_search_update(const SfSearchParams& p, cudaStream_t stream) {
+  SFB_CHECK_ARG(p.B >= 1 && p.A >= 1 && p.S >= 1 && p.M >= 1 && p.iter >= 0 && p.iter < p.max_iter, "sf_search_update: bad sizes");
+  sf_search_update_kernel<<<p.B, 128, 0, stream>>>(p);
+  SFB_CHECK_LAUNCH();
+  sf_search_flags_kernel<<<1, 32, 0, stream>>>(p.flags);
+  SFB_CHECK_LAUNCH();
+  count_launch();
+  count_launch();
+  return 0;
+}
+
 // ---------------------------------------------------------------- follower rollout tail (one warp per row)
 __global__ void __launch_bounds__(128) follower_tail_kernel(const TailParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -767,6 +767,129 @@ class Seq2SeqAgent(BaseAgent):
             trajs.append(out)
         return trajs, completed_list, traversed_lists
 
+    def device_state_factored_search(self, nav, completion_size, load_next_minibatch=True, max_iter=1024, check_every=8):
+        """state_factored_search(completion_size, successor_size=1) — the configuration of pragmatic inference
+        (rational_follower.py:44-69) — with the search state ON THE DEVICE: `nav` is the environment as
+        look-up tables (navgraph_env.DeviceNavTables), the per-instance cache / holding / completed tables, the inference-state
+        pool and the selection of the next state to expand live in device arrays (ops.SfSearchState, sfb_sf_search_update),
+        every expansion's (h, c, alpha) stays in a device pool.  The host only launches iterations and looks at one flag
+        every `check_every` iterations; when the search has ended it downloads the node arrays once and rebuilds the
+        reference's result structures (trajectories, completed lists, traversal walk) for the nodes that matter.
+        Returns what state_factored_search returns."""
+        assert getattr(self.decoder, "supports_fused_step", False) and getattr(self.decoder, "feature_store", None) is not None
+        world_states = self.env.reset(sort=True, beamed=True, load_next_minibatch=load_next_minibatch)
+        initial_obs = self.env.observe(world_states, beamed=True)
+        B = len(world_states)
+        seq, seq_mask, seq_lengths = self._proc_batch(initial_obs, beamed=True)
+        ctx, h_t, c_t = self.encoder(seq, seq_lengths)
+        dev = _device(self.decoder)
+        H, L, A = h_t.shape[1], ctx.shape[1], nav.A
+        st = ops.SfSearchState(B, nav.S, torch.tensor(nav.state_ids([ws[0] for ws in world_states]), dtype=torch.int32),
+                               max_iter, max_iter * A, dev)
+        pool_h = torch.empty(max_iter + 1, B, H, device=dev); pool_c = torch.empty(max_iter + 1, B, H, device=dev)
+        pool_alpha = torch.zeros(max_iter + 1, B, L, device=dev)
+        pool_h[0].copy_(h_t); pool_c[0].copy_(c_t)
+        rows = torch.arange(B, device=dev)
+        a_ids = torch.arange(A, device=dev).unsqueeze(0)
+        logit = torch.empty(B, A, device=dev)
+        alpha_v = torch.empty(B, self.decoder.feature_store.feat_table.shape[1], device=dev)
+        ctx, seq_mask = ctx.contiguous(), seq_mask.contiguous()
+        cproj = self.decoder.project_ctx(ctx) if hasattr(self.decoder, "project_ctx") else None
+        ended_at = None
+        for t in range(max_iter):
+            n = st.beam_node.long().clamp(min=0)                      # instances without a state run a dummy row (ignored)
+            s = st.node_state[rows, n].long()
+            par = st.node_parent[rows, n].long().clamp(min=0)
+            act = st.node_action[rows, n].long()
+            ps = st.node_state[rows, par].long()
+            slot = st.node_slot[rows, n].long()
+            h0, c0 = pool_h[slot, rows].contiguous(), pool_c[slot, rows].contiguous()
+            has_act = act > 0
+            u_prev = self._embed_actions(nav.vp[ps], torch.where(has_act, nav.cv[ps, act.clamp(min=0)], torch.full_like(nav.vp[ps], -1)),
+                                         nav.trig[ps, act.clamp(min=0)])
+            is_valid = (a_ids < nav.nvalid[s].unsqueeze(1))
+            self.decoder.decode_step(u_prev, None, (nav.vp[s].contiguous(), nav.view[s].contiguous()), h0, c0, ctx, seq_mask,
+                                     cand_view=nav.cv[s].contiguous(), cand_trig=nav.trig[s].contiguous(), ctx_proj=cproj,
+                                     out=(pool_h[t + 1], pool_c[t + 1], pool_alpha[t + 1], logit, alpha_v))
+            lp = torch.log_softmax(logit.masked_fill(~is_valid, -float("inf")), dim=1).contiguous()   # follower.py:808-810
+            ops.sf_search_update(st, nav, t, self.episode_len, completion_size, lp)
+            if (t + 1) % check_every == 0 and int(st.flags[0]) != 0:  # the one host look at the device every few iterations
+                ended_at = t
+                break
+        flags = st.flags.tolist()
+        if flags[2]:
+            raise RuntimeError("device_state_factored_search: node pool exhausted (max_iter=%d)" % max_iter)
+        if not flags[0]:
+            raise RuntimeError("device_state_factored_search: not finished after %d iterations" % max_iter)
+        T = flags[3]
+        # ---- one download, then the reference's result structures for the nodes that matter
+        parent, state, action = st.node_parent.cpu().numpy(), st.node_state.cpu().numpy(), st.node_action.cpu().numpy()
+        count, slot_h, score = st.node_count.cpu().numpy(), st.node_slot.cpu().numpy(), st.node_score.cpu().numpy()
+        trav = st.trav[:, :T].cpu().numpy()
+        d_score, d_node = st.d_score.cpu().numpy(), st.d_node.cpu().numpy()
+        expanded = [sorted({0} | {int(m) for m in trav[i] if m >= 0}) for i in range(B)]
+        exp_obs = self.env.observe([[nav.world_state(state[i, m]) for m in expanded[i]] for i in range(B)], beamed=True)
+        own_obs = [dict(zip(expanded[i], exp_obs[i])) for i in range(B)]
+        for i in range(B):
+            own_obs[i][0] = initial_obs[i][0]            # the root keeps the observation env.reset produced
+        built = [dict() for _ in range(B)]
+
+        def node(i, m):
+            """The InferenceState (follower.py:27-30) of node m of instance i, ancestors first."""
+            chain, k = [], m
+            while k >= 0 and k not in built[i]:
+                chain.append(k)
+                k = int(parent[i, k])
+            for k in reversed(chain):
+                p_ = int(parent[i, k])
+                prev = built[i][p_] if p_ >= 0 else None
+                ob = own_obs[i].get(k, prev.observation if prev is not None else None)   # a never-expanded state keeps its parent's
+                if p_ < 0:
+                    ws_k = world_states[i][0]
+                elif int(action[i, k]) == 0:
+                    ws_k = prev.world_state                  # the stop action leaves the world state untouched (env.py:628-641)
+                else:
+                    ws_k = nav.world_state(state[i, k])
+                built[i][k] = InferenceState(prev, ws_k, ob, None,
+                                             int(action[i, k]), None, int(count[i, k]), np.float32(score[i, k]), None, None,
+                                             pool_alpha[int(slot_h[i, k]), i] if p_ >= 0 else None)
+            return built[i][m]
+
+        roots = [node(i, 0) for i in range(B)]
+        last_expanded = list(roots)
+        traversed_lists = [[r] for r in roots]
+
+        def extend_traversed(groups):                    # follower.py:764-779
+            for i, group in enumerate(groups):
+                cur = last_expanded[i]
+                for x in group:
+                    walk = least_common_viewpoint_path(cur, x)
+                    traversed_lists[i].extend(walk[1:])
+                    cur = x
+                last_expanded[i] = cur
+        for t in range(T):
+            extend_traversed([[node(i, int(trav[i, t]))] if trav[i, t] >= 0 else [] for i in range(B)])
+        completed_list = []
+        for i in range(B):
+            done = [node(i, int(d_node[i, s_])) for s_ in np.nonzero(d_score[i] > -np.inf)[0]]
+            completed_list.append(sorted(done, key=lambda x: x.score, reverse=True)[:completion_size])
+        final_obs = self.env.observe([[x.world_state for x in cl] for cl in completed_list], beamed=True)
+        completed_list = [[x._replace(observation=o) for x, o in zip(cl, os_)] for cl, os_ in zip(completed_list, final_obs)]
+        extend_traversed(completed_list)
+        trajs = []
+        for cl in completed_list:
+            assert cl
+            out = []
+            for x in cl:
+                states, observations, actions, scores, attentions = backchain_inference_states(x)
+                out.append({"instr_id": observations[0]["instr_id"], "instr_encoding": observations[0]["instr_encoding"],
+                            "trajectory": [path_element_from_observation(o) for o in observations],
+                            "observations": observations, "actions": actions, "score": x.score, "scores": scores,
+                            "attentions": attentions})
+            trajs.append(out)
+        self.last_search_iterations = T
+        return trajs, completed_list, traversed_lists
+
     # ---------------------------------------------------------------- driver methods (follower.py:982-1035)
     def set_beam_size(self, beam_size):
         if self.env.beam_size < beam_size:

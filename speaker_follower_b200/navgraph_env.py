@@ -259,5 +259,9 @@ class DeviceNavTables:
         self.S, self.A, self.G = S, a_cap, nvp
         self.device = device
 
+    def world_state(self, s: int):
+        """The WorldState (env.py:227) of state id `s`."""
+        return WorldState("fake", int(s) // self.HEADINGS, (int(s) % self.HEADINGS) * (math.pi / 6), 0.0)
+
     def state_ids(self, world_states):
         return [int(ws.viewpointId) * self.HEADINGS + int(round(ws.heading / (math.pi / 6))) % 12 for ws in world_states]

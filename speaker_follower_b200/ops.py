@@ -884,6 +884,58 @@ def nav_step(nav, state: Tensor, ended: Tensor, goal: Optional[Tensor], a_prev: 
                                _p(out["target"], torch.int32) if with_target else None, _stream()))
 
 
+class SfSearchState:
+    """Device arrays of the state-factored search bookkeeping (include/sf_b200.h: sfb_sf_search_state) for B instances
+    over a table-driven environment with S states; node 0 of every instance is the root (start state, score 0)."""
+
+    def __init__(self, B: int, S: int, start_states: Tensor, max_iter: int, max_nodes: int, device):
+        i32 = lambda *shape, fill=0: torch.full(shape, fill, dtype=torch.int32, device=device)
+        f32 = lambda *shape: torch.full(shape, -float("inf"), dtype=torch.float32, device=device)
+        u8 = lambda *shape: torch.zeros(shape, dtype=torch.uint8, device=device)
+        self.B, self.S, self.max_iter, self.max_nodes = B, S, max_iter, max_nodes
+        self.beam_node = i32(B)
+        self.c_score, self.c_node, self.c_exp = f32(B, S), i32(B, S), u8(B, S)
+        self.h_score, self.h_node, self.h_exp = f32(B, S), i32(B, S), u8(B, S)
+        self.d_score, self.d_node, self.n_done = f32(B, S), i32(B, S), i32(B)
+        self.n_nodes = i32(B, fill=1)
+        self.node_parent, self.node_state, self.node_action = i32(B, max_nodes, fill=-1), i32(B, max_nodes), i32(B, max_nodes, fill=-1)
+        self.node_count, self.node_slot = i32(B, max_nodes), i32(B, max_nodes)
+        self.node_score = torch.zeros(B, max_nodes, dtype=torch.float32, device=device)
+        self.trav = i32(B, max_iter, fill=-1)
+        self.flags = i32(4)
+        rows = torch.arange(B, device=device)
+        st = start_states.to(device=device, dtype=torch.int32)
+        self.node_state[:, 0] = st
+        self.c_score[rows, st.long()] = 0.0            # cache[key(start)] = [root, expanded] (follower.py:752-756)
+        self.c_exp[rows, st.long()] = 1
+
+    def struct(self):
+        s = _lib.SfSearchState()
+        for name in ("beam_node", "c_node", "h_node", "d_node", "n_done", "n_nodes", "node_parent", "node_state", "node_action",
+                     "node_count", "node_slot", "trav", "flags"):
+            setattr(s, name, _p(getattr(self, name), torch.int32))
+        for name in ("c_score", "h_score", "d_score", "node_score"):
+            setattr(s, name, _p(getattr(self, name)))
+        for name in ("c_exp", "h_exp"):
+            setattr(s, name, _p(getattr(self, name), torch.uint8))
+        s.max_nodes, s.max_iter = self.max_nodes, self.max_iter
+        return s
+
+
+def nav_tables_struct(nav):
+    return _lib.NavTables(_p(nav.vp, torch.int32), _p(nav.view, torch.int32), _p(nav.nvalid, torch.int32), _p(nav.cv, torch.int32),
+                          _p(nav.trig), _p(nav.next, torch.int32), _p(nav.teach, torch.int32) if nav.teach is not None else None,
+                          nav.S, nav.A, nav.G)
+
+
+def sf_search_update(state: SfSearchState, nav, iteration: int, episode_len: int, completion_size: int, lp: Tensor) -> None:
+    """sfb_sf_search_update: one iteration of the state-factored search bookkeeping (follower.py:886-924) on the device."""
+    lib = _lib.load()
+    with torch.cuda.device(lp.device):
+        check(lib.sfb_sf_search_update(C.byref(state.struct()), C.byref(nav_tables_struct(nav)), state.B, iteration, episode_len,
+                                       completion_size, _p(lp, name="lp"), _stream()))
+
+
 def set_option(name: str, value: int) -> None:
     """Testing hook: 'disable_tc' (1 = exact-fp32 FFMA gates GEMM), 'tc_debug'."""
     check(_lib.load().sfb_set_option(name.encode(), int(value)))

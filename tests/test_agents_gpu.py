@@ -275,6 +275,36 @@ def test_state_factored_search_matches_search_oracle(graph, completion, successo
     assert checked >= 3
 
 
+@pytest.mark.parametrize("graph,completion", [("8194nk5LbLH", 4), ("pLe4wQe7qrG", 6), ("GdvgFV5R1Z5", 8)])
+def test_device_state_factored_search_matches_host_search_and_oracle(graph, completion):
+    """the state-factored search with its state on the device (sfb_sf_search_update: cache / holding /
+    completed tables, node pool, selection; successor_size = 1) against the host implementation of follower.py:720-980 AND
+    against the plain-Python search oracle, on a real R2R navigation graph: same candidates (end state, actions, scores)
+    and the same traversal walk."""
+    from speaker_follower_b200.navgraph_env import DeviceNavTables
+    mk = lambda feats: FakeR2RBatch(n_instr=6, batch_size=6, seed=23, graph=graph, beam_size=2, with_features=feats)
+    env_d, env_h, twin = mk(False), mk(False), mk(True)
+    agent_d, we, wd = make_follower(env_d, store=True)
+    agent_h, _, _ = make_follower(env_h, store=True)
+    nav = DeviceNavTables(env_d, "cuda", with_teacher=False)
+    with torch.no_grad():
+        got, _, walk_g = agent_d.device_state_factored_search(nav, completion)
+        host, _, walk_h = agent_h.state_factored_search(completion, 1)
+        want, _, walk_w = SO.follower_state_factored_search(twin, we, wd, completion, 1, episode_len=agent_d.episode_len,
+                                                            max_length=agent_d.max_instruction_length)
+    assert agent_d.last_search_iterations > completion
+    checked = 0
+    for i, (g, h, w) in enumerate(zip(got, host, want)):
+        if _same_candidates(g, h, tol=3e-4, what="device vs host, instance %d" % i) and \
+                _same_candidates(g, w, tol=3e-4, what="device vs oracle, instance %d" % i):
+            checked += 1
+            vps = lambda walk: [s_.world_state.viewpointId for s_ in walk]
+            assert vps(walk_g[i]) == vps(walk_h[i]) == vps(walk_w[i]), i
+            for cg, ch in zip(g, h):
+                assert cg["trajectory"] == ch["trajectory"] and len(cg["attentions"]) == len(ch["attentions"])
+    assert checked >= 4
+
+
 def test_speaker_beam_search_matches_search_oracle():
     """speaker.py:211-318 against the oracle on gold paths of a real graph."""
     env = FakeR2RBatch(n_instr=6, batch_size=6, seed=23, graph="8194nk5LbLH")
