@@ -724,10 +724,14 @@ def run_pragmatic(args, rank, local_rank, world):
         # (a generated instruction depends on its minibatch's longest path, in the reference too)
         gi = PR.shard_env(env, whole_batches=not c4) if shard else list(range(n_inst))
         follower, speaker = _agents(env, dev, instruction_len=30)
+        nav = None
+        if c4 and not os.environ.get("SFB_HOST_SEARCH"):
+            from speaker_follower_b200.navgraph_env import DeviceNavTables
+            nav = DeviceNavTables(env, dev, with_teacher=False)   # environment set-up, like the feature-store upload
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         if c4:
-            by_w, cands, records = PR.run_rational_follower(env, follower, speaker, beam_size=beam, global_index=gi)
+            by_w, cands, records = PR.run_rational_follower(env, follower, speaker, beam_size=beam, global_index=gi, nav=nav)
             out = {w: {int(k): int(v) for k, v in ch.items()} for w, ch in PR.rational_combine(records).items()}
             n_cand = int(records.shape[0])
         else:
@@ -760,7 +764,7 @@ def run_pragmatic(args, rank, local_rank, world):
                 "value": n_inst / dt, "unit": "instr/s" if c4 else "traj/s", "n_gpus": world, "steps": 1, "warmup": 1,
                 "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": ("C4: state-factored search, completion 40, successor 1, 64 instructions, %d candidates "
+                "config": {"workload": ("C4: state-factored search (search state on the device), completion 40, successor 1, 64 instructions, %d candidates "
                                         "rescored by the speaker" % n_cand) if c4 else
                                        ("C5: greedy speaker generation over %d synthetic trajectories, batch 256 per GPU" % n_inst),
                            "env": "navigation-graph stand-in (160 viewpoints), random-init weights",

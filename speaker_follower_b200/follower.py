@@ -603,7 +603,7 @@ class Seq2SeqAgent(BaseAgent):
         return trajs, completed, None
 
     def state_factored_search(self, completion_size, successor_size, load_next_minibatch=True, mask_undo=False,
-                              first_n_ws_key=4):
+                              first_n_ws_key=4, _pad_batch=False):
         """follower.py:720-980.  Search over WORLD STATES instead of action sequences: per instance a table keeps the
         best-scoring inference state reaching each world-state key (scan, viewpoint, heading, elevation); every
         iteration the `successor_size` best not-yet-expanded entries (open or finished) are expanded; finished ones move
@@ -659,6 +659,13 @@ class Seq2SeqAgent(BaseAgent):
                 last_expanded[i] = cur
 
         while any(len(c) < completion_size for c in completed):
+            if _pad_batch:
+                # test hook (successor_size 1): every instance contributes a row every iteration (its root when it has no
+                # state to expand; the row's results are dropped), so that the decode step sees the same batch as the
+                # device search and the two can be compared bit for bit
+                assert successor_size == 1
+                real = [bool(beam) for beam in beams]
+                beams = [beam if beam else [traversed_lists[i][0]] for i, beam in enumerate(beams)]
             flat = [st for beam in beams for st in beam]
             owner = [bi for bi, beam in enumerate(beams) for _ in beam]
             flat_obs = [st.observation for st in flat]
@@ -685,11 +692,11 @@ class Seq2SeqAgent(BaseAgent):
 
             # every valid action of every beam state is a successor (follower.py:832-857), best first
             all_succ, fi = [], 0
-            for beam in beams:
+            for bi_, beam in enumerate(beams):
                 succ = []
                 for st in beam:
                     for ai in range(lp_host.shape[1]):
-                        if is_valid_np[fi, ai] == 0:
+                        if is_valid_np[fi, ai] == 0 or (_pad_batch and not real[bi_]):
                             continue
                         emb = (flat_obs[fi]["vp_index"], int(cv_np[fi, ai]), tuple(float(v) for v in tr_np[fi, ai])) if index_mode \
                             else all_u_t[fi, ai]
@@ -767,7 +774,8 @@ class Seq2SeqAgent(BaseAgent):
             trajs.append(out)
         return trajs, completed_list, traversed_lists
 
-    def device_state_factored_search(self, nav, completion_size, load_next_minibatch=True, max_iter=1024, check_every=8):
+    def device_state_factored_search(self, nav, completion_size, load_next_minibatch=True, max_iter=1024, check_every=8,
+                                     use_ctx_proj=True):
         """state_factored_search(completion_size, successor_size=1) — the configuration of pragmatic inference
         (rational_follower.py:44-69) — with the search state ON THE DEVICE: `nav` is the environment as
         look-up tables (navgraph_env.DeviceNavTables), the per-instance cache / holding / completed tables, the inference-state
@@ -794,7 +802,7 @@ class Seq2SeqAgent(BaseAgent):
         logit = torch.empty(B, A, device=dev)
         alpha_v = torch.empty(B, self.decoder.feature_store.feat_table.shape[1], device=dev)
         ctx, seq_mask = ctx.contiguous(), seq_mask.contiguous()
-        cproj = self.decoder.project_ctx(ctx) if hasattr(self.decoder, "project_ctx") else None
+        cproj = self.decoder.project_ctx(ctx) if (use_ctx_proj and hasattr(self.decoder, "project_ctx")) else None
         ended_at = None
         for t in range(max_iter):
             n = st.beam_node.long().clamp(min=0)                      # instances without a state run a dummy row (ignored)

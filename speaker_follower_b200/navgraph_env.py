@@ -88,7 +88,9 @@ class FakeR2RBatch:
             goal = int(reach[int(g.integers(len(reach)))])
             n_tok = int(g.integers(5, max_len))
             self.data.append({"instr_id": "%d_0" % i, "path_id": i, "scan": "fake", "start": start, "goal": goal,
-                              "heading": float(g.integers(12)) * math.pi / 6,
+                              "heading": float(g.integers(12)) * (math.pi / 6),   # step * increment, the one expression every
+                              # discretised heading is formed with (MatterSim.cpp:339-367 snaps the same way): a state
+                              # reached by stepping has the SAME float as the state a reset produces
                               "instr_encoding": g.integers(4, vocab, size=n_tok).astype(np.int64)})
         self.ix = 0
         self.batch = None
@@ -232,7 +234,7 @@ class DeviceNavTables:
             for v in range(nvp):
                 for hb in range(self.HEADINGS):
                     s = v * self.HEADINGS + hb
-                    ob = env._observe_one(WorldState("fake", v, hb * math.pi / 6, 0.0), dummy, include_teacher=False)
+                    ob = env._observe_one(WorldState("fake", v, hb * (math.pi / 6), 0.0), dummy, include_teacher=False)
                     adj = ob["adj_loc_list"]
                     if len(adj) > a_cap:
                         raise ValueError("state with %d candidates > a_cap" % len(adj))

@@ -72,7 +72,7 @@ def rational_combine(records, weights: Sequence[float] = (0.0, 0.95), stds: Opti
 
 def run_rational_follower(env, follower, speaker, beam_size: int, state_factored_search: bool = True,
                           state_first_n_ws_key: int = 4, physical_traversal: bool = False,
-                          weights: Sequence[float] = (0.0, 0.95), global_index: Optional[List[int]] = None):
+                          weights: Sequence[float] = (0.0, 0.95), global_index: Optional[List[int]] = None, nav=None):
     """The candidate generation + rescoring + combine of run_rational_follower for the instances of ``env`` (already
     sharded with shard_env() under torch.distributed).  Returns (results_by_weight, candidate_lists, records) where
     results_by_weight[w][instr_id] is the chosen candidate dict (only for this rank's instructions), candidate_lists
@@ -98,7 +98,10 @@ def run_rational_follower(env, follower, speaker, beam_size: int, state_factored
     with torch.no_grad():
         while not looped:
             t0 = _tick()
-            if state_factored_search:
+            if state_factored_search and nav is not None and state_first_n_ws_key == 4:
+                # the environment as device tables: the whole search state lives on the device
+                beam_candidates, inf_states, traversed = follower.device_state_factored_search(nav, beam_size, load_next_minibatch=True)
+            elif state_factored_search:
                 beam_candidates, inf_states, traversed = follower.state_factored_search(
                     beam_size, 1, load_next_minibatch=True, first_n_ws_key=state_first_n_ws_key)
             else:

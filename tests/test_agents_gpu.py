@@ -305,6 +305,31 @@ def test_device_state_factored_search_matches_host_search_and_oracle(graph, comp
     assert checked >= 4
 
 
+def test_device_state_factored_search_long_run_equals_host_bit_for_bit():
+    """The pragmatic-inference configuration at a size where near-ties would flip a rounding-level comparison (24 instances,
+    completion 30, episode_len 10, > 100 iterations): both searches run the same kernels on the same batch (host side padded
+    to one row per instance, device side without per-episode projections), so every candidate, score and the traversal
+    walk must be EQUAL — what is compared is the search logic of sfb_sf_search_update against follower.py:886-924."""
+    from speaker_follower_b200.navgraph_env import DeviceNavTables
+    mk = lambda: FakeR2RBatch(n_viewpoints=120, n_instr=24, batch_size=24, seed=31, max_len=30, beam_size=30, with_features=False)
+    env_d, env_h = mk(), mk()
+    agent_d, _, _ = make_follower(env_d, store=True)
+    agent_h, _, _ = make_follower(env_h, store=True)
+    agent_d.episode_len = agent_h.episode_len = 10
+    nav = DeviceNavTables(env_d, "cuda", with_teacher=False)
+    with torch.no_grad():
+        got, _, walk_g = agent_d.device_state_factored_search(nav, 30, use_ctx_proj=False)
+        want, _, walk_w = agent_h.state_factored_search(30, 1, _pad_batch=True)
+    assert agent_d.last_search_iterations > 100
+    assert sum(len(g) for g in got) == sum(len(w) for w in want) == 24 * 30
+    for i, (g, w) in enumerate(zip(got, want)):
+        for cg, cw in zip(g, w):
+            assert [int(a) for a in cg["actions"]] == [int(a) for a in cw["actions"]], i
+            assert cg["trajectory"] == cw["trajectory"], i
+            assert abs(float(cg["score"]) - float(cw["score"])) < 1e-6, i
+        assert [x.world_state for x in walk_g[i]] == [x.world_state for x in walk_w[i]], i
+
+
 def test_speaker_beam_search_matches_search_oracle():
     """speaker.py:211-318 against the oracle on gold paths of a real graph."""
     env = FakeR2RBatch(n_instr=6, batch_size=6, seed=23, graph="8194nk5LbLH")
