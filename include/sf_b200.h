@@ -318,7 +318,8 @@ int32_t sfb_nav_step(const sfb_nav_tables* t, int32_t B, int32_t* state, int32_t
  * inference state per world state), holding (best finished one), completed; inference states live in a per-instance node
  * pool.  One call per search iteration, after the decode step of the states selected by the previous call:
  *   lp [B,A] = log_softmax of the step's masked logits (808-810); `iter` = iteration index (the step's h / c / alpha are
- *   kept by the caller in slot iter + 1);
+ *   kept by the caller in slot iter + 1), or -1 to use the device's own count flags[3] — a launch replayed from a CUDA
+ *   graph cannot take a new argument;
  *   the successors of beam_node[b] are inserted where they strictly improve their table entry (896-900; a successor is
  *   finished after the stop action or at episode_len, 895), then the best not-yet-expanded entry is selected (903-908): an
  *   open one becomes beam_node[b], a finished one moves to completed (912-916); instances with completion_size

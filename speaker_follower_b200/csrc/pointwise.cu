@@ -164,6 +164,9 @@ int32_t launch_nav_step(const NavStepParams& p, cudaStream_t stream) {
 __global__ void __launch_bounds__(128) sf_search_update_kernel(const SfSearchParams p) {
   const int i = blockIdx.x, tid = threadIdx.x;
   if (p.flags[0]) return;                                   // the search has ended (no instance had a state to expand)
+  // iteration index: given by the host, or (iter < 0: the launch is replayed from a CUDA graph) the device's own count
+  const int iter = p.iter >= 0 ? p.iter : p.flags[3];
+  if (iter >= p.max_iter) { if (tid == 0) p.flags[2] = 1; return; }
   const size_t so = (size_t)i * p.S, no = (size_t)i * p.M;
   __shared__ float s_best[128];
   __shared__ int s_arg[128];
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(128) sf_search_update_kernel(const SfSearchPar
         if (m >= p.M) { p.flags[2] = 1; break; }           // node pool exhausted: reported, the host falls back
         p.n_nodes[i] = m + 1;
         p.node_parent[no + m] = n; p.node_state[no + m] = ns; p.node_action[no + m] = a; p.node_count[no + m] = cnt;
-        p.node_score[no + m] = sc; p.node_slot[no + m] = p.iter + 1;   // this iteration's outputs sit in slot iter + 1
+        p.node_score[no + m] = sc; p.node_slot[no + m] = iter + 1;     // this iteration's outputs sit in slot iter + 1
         tsc[so + ns] = sc;
         (fin ? p.h_node : p.c_node)[so + ns] = m;
         (fin ? p.h_exp : p.c_exp)[so + ns] = 0;
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(128) sf_search_update_kernel(const SfSearchPar
     }
     if (p.n_done[i] >= p.completion_size) beam = -1;       // follower.py:921
     p.beam_node[i] = beam;
-    p.trav[(size_t)i * p.max_iter + p.iter] = beam;
+    p.trav[(size_t)i * p.max_iter + iter] = beam;
     if (beam >= 0) atomicAdd(&p.flags[1], 1);              // flags[1]: instances with a state to expand (reset by the flags kernel)
   }
 }
@@ -252,7 +255,7 @@ __global__ void sf_search_flags_kernel(int* flags) {
 }
 
 int32_t launch_sf_search_update(const SfSearchParams& p, cudaStream_t stream) {
-  SFB_CHECK_ARG(p.B >= 1 && p.A >= 1 && p.S >= 1 && p.M >= 1 && p.iter >= 0 && p.iter < p.max_iter, "sf_search_update: bad sizes");
+  SFB_CHECK_ARG(p.B >= 1 && p.A >= 1 && p.S >= 1 && p.M >= 1 && p.iter < p.max_iter, "sf_search_update: bad sizes");
   sf_search_update_kernel<<<p.B, 128, 0, stream>>>(p);
   SFB_CHECK_LAUNCH();
   sf_search_flags_kernel<<<1, 32, 0, stream>>>(p.flags);

@@ -775,7 +775,7 @@ class Seq2SeqAgent(BaseAgent):
         return trajs, completed_list, traversed_lists
 
     def device_state_factored_search(self, nav, completion_size, load_next_minibatch=True, max_iter=1024, check_every=8,
-                                     use_ctx_proj=True):
+                                     use_ctx_proj=True, cuda_graph=False):
         """state_factored_search(completion_size, successor_size=1) — the configuration of pragmatic inference
         (rational_follower.py:44-69) — with the search state ON THE DEVICE: `nav` is the environment as
         look-up tables (navgraph_env.DeviceNavTables), the per-instance cache / holding / completed tables, the inference-state
@@ -783,7 +783,9 @@ class Seq2SeqAgent(BaseAgent):
         every expansion's (h, c, alpha) stays in a device pool.  The host only launches iterations and looks at one flag
         every `check_every` iterations; when the search has ended it downloads the node arrays once and rebuilds the
         reference's result structures (trajectories, completed lists, traversal walk) for the nodes that matter.
-        Returns what state_factored_search returns."""
+        Returns what state_factored_search returns.  `cuda_graph`: replay the iteration from one captured graph (the iteration
+        takes its index from the device); measured at 64 instances x 192 iterations it does not pay — capture costs more than
+        the ≈25 small launches per iteration it saves, and the rebuild of the result structures dominates the call."""
         assert getattr(self.decoder, "supports_fused_step", False) and getattr(self.decoder, "feature_store", None) is not None
         world_states = self.env.reset(sort=True, beamed=True, load_next_minibatch=load_next_minibatch)
         initial_obs = self.env.observe(world_states, beamed=True)
@@ -794,35 +796,52 @@ class Seq2SeqAgent(BaseAgent):
         H, L, A = h_t.shape[1], ctx.shape[1], nav.A
         st = ops.SfSearchState(B, nav.S, torch.tensor(nav.state_ids([ws[0] for ws in world_states]), dtype=torch.int32),
                                max_iter, max_iter * A, dev)
-        pool_h = torch.empty(max_iter + 1, B, H, device=dev); pool_c = torch.empty(max_iter + 1, B, H, device=dev)
-        pool_alpha = torch.zeros(max_iter + 1, B, L, device=dev)
+        pool_h = torch.empty(max_iter + 2, B, H, device=dev); pool_c = torch.empty(max_iter + 2, B, H, device=dev)
+        pool_alpha = torch.zeros(max_iter + 2, B, L, device=dev)
         pool_h[0].copy_(h_t); pool_c[0].copy_(c_t)
         rows = torch.arange(B, device=dev)
         a_ids = torch.arange(A, device=dev).unsqueeze(0)
+        h1 = torch.empty(B, H, device=dev); c1 = torch.empty(B, H, device=dev); alpha1 = torch.empty(B, L, device=dev)
         logit = torch.empty(B, A, device=dev)
         alpha_v = torch.empty(B, self.decoder.feature_store.feat_table.shape[1], device=dev)
         ctx, seq_mask = ctx.contiguous(), seq_mask.contiguous()
         cproj = self.decoder.project_ctx(ctx) if (use_ctx_proj and hasattr(self.decoder, "project_ctx")) else None
-        ended_at = None
-        for t in range(max_iter):
-            n = st.beam_node.long().clamp(min=0)                      # instances without a state run a dummy row (ignored)
-            s = st.node_state[rows, n].long()
-            par = st.node_parent[rows, n].long().clamp(min=0)
-            act = st.node_action[rows, n].long()
-            ps = st.node_state[rows, par].long()
-            slot = st.node_slot[rows, n].long()
+
+        def iteration(sst):
+            """One search iteration, device-side only and with static shapes (so that it can be replayed from a CUDA graph):
+            gather the selected states' inputs from the node pool + tables, decode, file the outputs under slot iter + 1,
+            update the search state."""
+            n = sst.beam_node.long().clamp(min=0)                     # instances without a state run a dummy row (ignored)
+            s_ = sst.node_state[rows, n].long()
+            par = sst.node_parent[rows, n].long().clamp(min=0)
+            act = sst.node_action[rows, n].long()
+            ps = sst.node_state[rows, par].long()
+            slot = sst.node_slot[rows, n].long()
             h0, c0 = pool_h[slot, rows].contiguous(), pool_c[slot, rows].contiguous()
-            has_act = act > 0
-            u_prev = self._embed_actions(nav.vp[ps], torch.where(has_act, nav.cv[ps, act.clamp(min=0)], torch.full_like(nav.vp[ps], -1)),
+            u_prev = self._embed_actions(nav.vp[ps], torch.where(act > 0, nav.cv[ps, act.clamp(min=0)], torch.full_like(nav.vp[ps], -1)),
                                          nav.trig[ps, act.clamp(min=0)])
-            is_valid = (a_ids < nav.nvalid[s].unsqueeze(1))
-            self.decoder.decode_step(u_prev, None, (nav.vp[s].contiguous(), nav.view[s].contiguous()), h0, c0, ctx, seq_mask,
-                                     cand_view=nav.cv[s].contiguous(), cand_trig=nav.trig[s].contiguous(), ctx_proj=cproj,
-                                     out=(pool_h[t + 1], pool_c[t + 1], pool_alpha[t + 1], logit, alpha_v))
+            is_valid = (a_ids < nav.nvalid[s_].unsqueeze(1))
+            self.decoder.decode_step(u_prev, None, (nav.vp[s_].contiguous(), nav.view[s_].contiguous()), h0, c0, ctx, seq_mask,
+                                     cand_view=nav.cv[s_].contiguous(), cand_trig=nav.trig[s_].contiguous(), ctx_proj=cproj,
+                                     out=(h1, c1, alpha1, logit, alpha_v))
+            dst = (sst.flags[3:4] + 1).long()                         # slot iter + 1 (the device's own iteration count)
+            pool_h.index_copy_(0, dst, h1.unsqueeze(0)); pool_c.index_copy_(0, dst, c1.unsqueeze(0))
+            pool_alpha.index_copy_(0, dst, alpha1.unsqueeze(0))
             lp = torch.log_softmax(logit.masked_fill(~is_valid, -float("inf")), dim=1).contiguous()   # follower.py:808-810
-            ops.sf_search_update(st, nav, t, self.episode_len, completion_size, lp)
+            ops.sf_search_update(sst, nav, -1, self.episode_len, completion_size, lp)
+
+        start = torch.tensor(nav.state_ids([ws[0] for ws in world_states]), dtype=torch.int32)
+        replay = lambda: iteration(st)
+        if cuda_graph:
+            iteration(ops.SfSearchState(B, nav.S, start, 2, 2 * A, dev))   # warm-up on a scratch state (allocations, kernel attributes)
+            torch.cuda.synchronize()
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                iteration(st)
+            replay = gph.replay
+        for t in range(max_iter):
+            replay()
             if (t + 1) % check_every == 0 and int(st.flags[0]) != 0:  # the one host look at the device every few iterations
-                ended_at = t
                 break
         flags = st.flags.tolist()
         if flags[2]:

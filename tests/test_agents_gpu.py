@@ -288,7 +288,7 @@ def test_device_state_factored_search_matches_host_search_and_oracle(graph, comp
     agent_h, _, _ = make_follower(env_h, store=True)
     nav = DeviceNavTables(env_d, "cuda", with_teacher=False)
     with torch.no_grad():
-        got, _, walk_g = agent_d.device_state_factored_search(nav, completion)
+        got, _, walk_g = agent_d.device_state_factored_search(nav, completion, cuda_graph=(completion == 6))   # one case through the graph
         host, _, walk_h = agent_h.state_factored_search(completion, 1)
         want, _, walk_w = SO.follower_state_factored_search(twin, we, wd, completion, 1, episode_len=agent_d.episode_len,
                                                             max_length=agent_d.max_instruction_length)
@@ -321,7 +321,7 @@ def test_device_state_factored_search_long_run_equals_host_bit_for_bit():
         got, _, walk_g = agent_d.device_state_factored_search(nav, 30, use_ctx_proj=False)
         want, _, walk_w = agent_h.state_factored_search(30, 1, _pad_batch=True)
     assert agent_d.last_search_iterations > 100
-    assert sum(len(g) for g in got) == sum(len(w) for w in want) == 24 * 30
+    assert [len(g) for g in got] == [len(w) for w in want] and sum(len(g) for g in got) > 24 * 25   # (a few instances run out of states)
     for i, (g, w) in enumerate(zip(got, want)):
         for cg, cw in zip(g, w):
             assert [int(a) for a in cg["actions"]] == [int(a) for a in cw["actions"]], i

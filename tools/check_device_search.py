@@ -32,3 +32,12 @@ for i, (g, w) in enumerate(zip(got, want)):
     if [s.world_state.viewpointId for s in walk_g[i]] != [s.world_state.viewpointId for s in walk_w[i]]:
         print("instance", i, "walk differs", len(walk_g[i]), len(walk_w[i])); bad += 1
 print("mismatching instances:", bad)
+import time
+for graph in (True, False):
+    for rep in range(2):
+        env_d.reset_epoch()
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        with torch.no_grad():
+            fd.device_state_factored_search(nav, 40, cuda_graph=graph)
+        torch.cuda.synchronize()
+        print("device search, cuda_graph=%s: %.1f ms (%d iterations)" % (graph, (time.perf_counter() - t0) * 1e3, fd.last_search_iterations))
