@@ -265,5 +265,17 @@ class DeviceNavTables:
         """The WorldState (env.py:227) of state id `s`."""
         return WorldState("fake", int(s) // self.HEADINGS, (int(s) % self.HEADINGS) * (math.pi / 6), 0.0)
 
+    def observe_states(self, env, per_instance_states):
+        """Observations (env.py:763-804, without the teacher action) of lists of state ids, one list per instance of
+        env.batch: an observation is a function of the state apart from the instruction fields of its instance, so every
+        distinct state is observed once and stamped per instance."""
+        uniq = sorted({int(s) for states in per_instance_states for s in states})
+        tmpl = {s: env._observe_one(self.world_state(s), env.batch[0], include_teacher=False) for s in uniq}
+        out = []
+        for item, states in zip(env.batch, per_instance_states):
+            stamp = {"instr_id": item["instr_id"], "instr_encoding": item["instr_encoding"], "instr_length": len(item["instr_encoding"])}
+            out.append([dict(tmpl[int(s)], **stamp) for s in states])
+        return out
+
     def state_ids(self, world_states):
         return [int(ws.viewpointId) * self.HEADINGS + int(round(ws.heading / (math.pi / 6))) % 12 for ws in world_states]
