@@ -903,7 +903,14 @@ class Seq2SeqAgent(BaseAgent):
         for i in range(B):
             done = [node(i, int(d_node[i, s_])) for s_ in np.nonzero(d_score[i] > -np.inf)[0]]
             completed_list.append(sorted(done, key=lambda x: x.score, reverse=True)[:completion_size])
-        final_obs = self.env.observe([[x.world_state for x in cl] for cl in completed_list], beamed=True)
+        if hasattr(nav, "observe_states"):
+            final_obs = nav.observe_states(self.env, [[nav.state_ids([x.world_state])[0] for x in cl] for cl in completed_list])
+            for i, cl in enumerate(completed_list):      # a completed state reached by the stop action at the root keeps the
+                for j, x in enumerate(cl):               # root's own world-state floats (heading as env.reset produced it)
+                    if x.world_state is world_states[i][0]:
+                        final_obs[i][j] = dict(final_obs[i][j], heading=x.world_state.heading, elevation=x.world_state.elevation)
+        else:
+            final_obs = self.env.observe([[x.world_state for x in cl] for cl in completed_list], beamed=True)
         completed_list = [[x._replace(observation=o) for x, o in zip(cl, os_)] for cl, os_ in zip(completed_list, final_obs)]
         extend_traversed(completed_list)
         trajs = []
