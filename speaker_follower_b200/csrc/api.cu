@@ -10,6 +10,7 @@ int g_disable_tc = 0;
 int g_disable_fused = 0;
 int g_disable_merged = 0;
 int g_disable_persist = 0;
+int g_disable_hoist = 0;
 int g_merged_prefetch = 1;
 static int g_fused_pre_weight = 4, g_fused_nopre = 0, g_fused_dbg = 0;
 int g_disable_pdl = 0;
@@ -391,6 +392,7 @@ int32_t sfb_set_option(const char* name, int32_t value) {
   if (n == "disable_fused") { g_disable_fused = value; return 0; }
   if (n == "disable_merged") { g_disable_merged = value; return 0; }
   if (n == "disable_persist") { g_disable_persist = value; return 0; }
+  if (n == "disable_hoist") { g_disable_hoist = value; return 0; }
   if (n == "merged_prefetch") { g_merged_prefetch = value; return 0; }
   if (n == "fused_pre_weight") { g_fused_pre_weight = value; return 0; }
   if (n == "fused_nopre") { g_fused_nopre = value; return 0; }
@@ -1595,7 +1597,7 @@ VisLstmPk layout_vislstm_pk(const sfb_dims& d) {
   L.bytes = off;
   return L;
 }
-struct SpkDecPk { size_t a_gates, a_th, a_wc, a_voc, bytes; int nkb_h, nkb_gates; };
+struct SpkDecPk { size_t a_gates, a_th, a_wc, a_voc, a_hh, tdec, bytes; int nkb_h, nkb_gates; };
 SpkDecPk layout_spkdec_pk(int H, int Ew, int vocab) {
   SpkDecPk L{};
   size_t off = 0;
@@ -1606,6 +1608,10 @@ SpkDecPk layout_spkdec_pk(int H, int Ew, int vocab) {
   L.a_th = take(pk_weight_bytes(2 * H, L.nkb_h));
   L.a_wc = take(pk_weight_bytes(H, L.nkb_h));
   L.a_voc = take(pk_weight_bytes(vocab, L.nkb_h));
+  // hoisted input projection (speaker.py:158-182 feeds words from a fixed vocabulary through a frozen embedding): the
+  // per-token table T = Emb W_ih^T [vocab, 4H] and the recurrent weights alone as a packed operand
+  L.a_hh = take(pk_weight_bytes(4 * H, L.nkb_h));
+  L.tdec = take((size_t)vocab * 4 * H * sizeof(float));
   L.bytes = off;
   return L;
 }
@@ -1724,7 +1730,18 @@ int32_t sfb_speaker_decoder_pack_weights(const sfb_speaker_decoder_weights* w, i
   SFB_PROPAGATE(pack_plain(w->attn.w_in, H, H, H, base + L.a_th, st));
   SFB_PROPAGATE(pack_plain(w->attn.w_out + H, 2 * H, H, H, base + L.a_th + pk_weight_bytes(H, L.nkb_h), st));
   SFB_PROPAGATE(pack_plain(w->attn.w_out, 2 * H, H, H, base + L.a_wc, st));
-  return pack_plain(w->w_voc, H, vocab, H, base + L.a_voc, st);
+  SFB_PROPAGATE(pack_plain(w->w_voc, H, vocab, H, base + L.a_voc, st));
+  {
+    PackParams ph{};
+    ph.nseg = 1;
+    ph.seg[0] = PackSeg{w->lstm_w_hh, H, H, nullptr, 0, nullptr};
+    ph.ntile = H / 32; ph.R = 128; ph.rows_per_tile = 128; ph.rows_valid = 4 * H; ph.lstm_H = H;
+    ph.out = base + L.a_hh;
+    SFB_PROPAGATE(launch_pack_rows(ph, st));
+  }
+  // T[v, :] = W_ih emb[v]  (exact fp32 products; biases are added by the cell epilogue as before)
+  return bgemm(vocab, 4 * H, Ew, w->embedding, Ew, w->lstm_w_ih, Ew, 0, reinterpret_cast<float*>(base + L.tdec), 4 * H, nullptr, nullptr,
+               0, st);
 }
 
 int32_t sfb_speaker_decoder_step_packed_fwd(const sfb_speaker_decoder_weights* w, const void* packed, size_t packed_bytes,
@@ -1743,15 +1760,26 @@ int32_t sfb_speaker_decoder_step_packed_fwd(const sfb_speaker_decoder_weights* w
   SFB_PROPAGATE(check_ws(workspace, workspace_bytes, ws.bytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned char* base = static_cast<const unsigned char*>(packed);
-  // model.py:497-503,515  LSTMCell(embedding(previous_word)): embedding rows gathered + split on the fly
+  // model.py:497-503,515  LSTMCell(embedding(previous_word)).  Without dropout on the embedding (GloVe: model.py:499-502)
+  // the input half of the gates depends on the word id only: it is read from the per-token table built at pack time and
+  // only W_hh h_0 is multiplied per step; otherwise the embedding rows are gathered + split on the fly
   {
     PkParams q{};
-    q.a_pk = base + P.a_gates; q.nkb = P.nkb_gates;
-    q.g.nseg = 2;
-    q.g.seg[0] = GemmSeg{w->embedding, Ew, prev_word, drop_e, drop_e ? Ew : 0, nullptr, 0, Ew, 0};
-    q.g.seg[1] = GemmSeg{h0, H, nullptr, nullptr, 0, nullptr, 0, H, 0};
+    const bool hoist = drop_e == nullptr && !g_disable_hoist;
+    q.a_pk = base + (hoist ? P.a_hh : P.a_gates); q.nkb = hoist ? P.nkb_h : P.nkb_gates;
+    if (hoist) {
+      q.g.nseg = 1;
+      q.g.seg[0] = GemmSeg{h0, H, nullptr, nullptr, 0, nullptr, 0, H, 0};
+    } else {
+      q.g.nseg = 2;
+      q.g.seg[0] = GemmSeg{w->embedding, Ew, prev_word, drop_e, drop_e ? Ew : 0, nullptr, 0, Ew, 0};
+      q.g.seg[1] = GemmSeg{h0, H, nullptr, nullptr, 0, nullptr, 0, H, 0};
+    }
     q.g.M = B; q.g.N = 4 * H;
     LstmEpilogue& e = q.g.lstm;
+    if (hoist) {
+      e.addend = reinterpret_cast<const float*>(base + P.tdec); e.ld_addend = 4 * H; e.addend_rows = prev_word;
+    }
     e.H = H; e.b_ih = w->lstm_b_ih; e.b_hh = w->lstm_b_hh; e.c0 = c0; e.drop_h = drop_h;
     e.h1 = h1; e.c1 = c1; e.h1_drop = ws.h1d; e.gates_act = ws.gates_act;
     SFB_PROPAGATE(launch_gemm_pk(q, st, ws.pk, ws.pk_bytes));

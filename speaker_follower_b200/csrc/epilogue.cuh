@@ -39,7 +39,7 @@ __device__ __forceinline__ void lstm_update(const GemmParams& p, int m, int unit
   gg += __ldg(e.b_ih + 2 * H + unit) + __ldg(e.b_hh + 2 * H + unit);
   go += __ldg(e.b_ih + 3 * H + unit) + __ldg(e.b_hh + 3 * H + unit);
   if (e.addend) {
-    const float* a = e.addend + (size_t)m * e.ld_addend + unit;
+    const float* a = e.addend + (size_t)(e.addend_rows ? e.addend_rows[m] : m) * e.ld_addend + unit;
     gi += a[0]; gf += a[H]; gg += a[2 * H]; go += a[3 * H];
   }
   const float ig = sigmoidf_acc(gi), fg = sigmoidf_acc(gf), gt = tanhf(gg), og = sigmoidf_acc(go);

@@ -93,6 +93,7 @@ struct LstmEpilogue {
   float* gates_act;                       // [M,4H] activated gates (i,f,g,o) kept for backward; may be NULL
   // sequence mode (EncoderLSTM, model.py:89-90): precomputed input projection + packed-sequence masking
   const float* addend; long long ld_addend;   // [M,4H] rows at stride ld_addend (x_t W_ih^T), or NULL
+  const int32_t* addend_rows;                 // optional: row m reads addend row addend_rows[m] (a per-token table)
   const float* h0;                            // previous hidden state, carried through when t >= lengths[m]
   const int32_t* lengths; int t;              // rows with t >= lengths[m] keep (h0, c0) and emit zeros
   float* seq_out; long long ld_seq_out;       // h1 (or 0 when inactive) written at seq_out[m*ld_seq_out + j]

@@ -332,7 +332,7 @@ def _spk_dec_weights(w: Dict[str, Tensor]) -> SpeakerDecoderWeights:
 class PackedSpeakerDecoder(_PackedCache):
     """sfb_speaker_decoder_pack_weights (model.py:469-485)."""
     keys = ("lstm.weight_ih", "lstm.weight_hh", "attention_layer.linear_in.weight", "attention_layer.linear_out.weight",
-            "decoder2action.weight")
+            "decoder2action.weight", "embedding.weight")   # the blob holds the per-token table Emb W_ih^T
 
     def _pack(self, w):
         lib = _lib.load()
