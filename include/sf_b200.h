@@ -262,9 +262,10 @@ int32_t sfb_follower_step_packed_fwd(const sfb_dims* dims, const sfb_vis_lstm_we
                                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* The first half of a decode step alone — VisualSoftDotAttention + nn.LSTMCell (model.py:389-393) from carried state — as
- * ONE launch (vis_lstm_fused_kernel): what sfb_follower_step_packed_fwd enqueues first when it is given carry_in.  Used by
- * bench.py to time that kernel in isolation (roofline) and usable as a building block (the speaker encoder step has the
- * same shape).  B <= 128, F = 2176.  feature may be NULL. */
+ * ONE launch (vis_lstm_fused_kernel): the first half of the one-launch step kernel that sfb_follower_step_packed_fwd
+ * enqueues when it is given carry_in and the ctx projections, as a launch of its own.  Used by bench.py to time that half
+ * in isolation (roofline_first_half) and usable as a building block (the speaker encoder step has the same shape).
+ * B <= 128, F = 2176.  feature may be NULL. */
 int32_t sfb_follower_gather_lstm_fwd(const sfb_dims* dims, const sfb_vis_lstm_weights* wl,
                                      const void* packed, size_t packed_bytes, int32_t B, void* carry_in,
                                      const sfb_visual_source* vis, const float* c0, float* h1, float* c1,
